@@ -1,0 +1,286 @@
+"""Mesh inputs of the Bloch-Torrey path: readers for the reference's fixture formats and
+deterministic synthetic generators for the benchmark shapes.
+
+Readers follow the numbering rules of the reference's tooling so that "mesh numbering"
+means the same thing on both sides:
+
+* gmsh v2 ASCII ``.msh``: vertices = the nodes used by tetrahedra, numbered in the order
+  they appear in ``$Nodes``; cells in file order
+  (comri/meshes/neuron_download/dolfin-convert.py:357-597); cell marker = first gmsh tag
+  (DmriFemLib.py:703-742, token ``x[3]``).
+* DOLFIN XML ``<mesh>``: vertex ``index`` / tetrahedron ``index`` attributes.
+
+Meshes are plain numpy: xyz (nv,3) float64, tets (nc,4) int32, optional marker (nc,) int32.
+"""
+import io
+import re
+import zipfile
+
+import numpy as np
+
+
+# ----------------------------------------------------------------------------- readers
+
+
+def _open_text(path):
+    if str(path).endswith(".zip"):
+        with zipfile.ZipFile(path) as z:
+            names = [n for n in z.namelist() if not n.startswith("__MACOSX") and not n.endswith("/")]
+            return io.StringIO(z.read(names[0]).decode("utf-8", "replace"))
+    return open(path, "r")
+
+
+def read_gmsh2(path):
+    """Read a gmsh v2 ASCII tetrahedral mesh (optionally zipped)."""
+    with _open_text(path) as f:
+        lines = f.read().split("\n")
+    i = lines.index("$Nodes")
+    nn = int(lines[i + 1])
+    node_ids = np.empty(nn, dtype=np.int64)
+    coords = np.empty((nn, 3))
+    for k in range(nn):
+        p = lines[i + 2 + k].split()
+        node_ids[k] = int(p[0])
+        coords[k] = (float(p[1]), float(p[2]), float(p[3]))
+    j = lines.index("$Elements")
+    ne = int(lines[j + 1])
+    tets, marks = [], []
+    for k in range(ne):
+        p = lines[j + 2 + k].split()
+        if int(p[1]) == 4:
+            nt = int(p[2])
+            tets.append([int(a) for a in p[3 + nt:3 + nt + 4]])
+            marks.append(int(p[3]) if nt > 0 else 0)
+    tets = np.array(tets, dtype=np.int64)
+    used = np.zeros(node_ids.max() + 1, dtype=bool)
+    used[tets.ravel()] = True
+    keep = used[node_ids]                       # file order of $Nodes, unused nodes dropped
+    new_id = -np.ones(node_ids.max() + 1, dtype=np.int64)
+    new_id[node_ids[keep]] = np.arange(int(keep.sum()))
+    return coords[keep].copy(), new_id[tets].astype(np.int32), np.array(marks, dtype=np.int32)
+
+
+def read_dolfin_xml(path):
+    """Read a DOLFIN XML tetrahedral mesh (optionally zipped)."""
+    with _open_text(path) as f:
+        txt = f.read()
+    nv = int(re.search(r'<vertices size="(\d+)"', txt).group(1))
+    nc = int(re.search(r'<cells size="(\d+)"', txt).group(1))
+    xyz = np.zeros((nv, 3))
+    for m in re.finditer(r'<vertex index="(\d+)" x="([^"]+)" y="([^"]+)"(?: z="([^"]+)")?', txt):
+        xyz[int(m.group(1))] = (float(m.group(2)), float(m.group(3)), float(m.group(4) or 0.0))
+    tets = np.zeros((nc, 4), dtype=np.int32)
+    for m in re.finditer(r'<tetrahedron index="(\d+)" v0="(\d+)" v1="(\d+)" v2="(\d+)" v3="(\d+)"', txt):
+        tets[int(m.group(1))] = [int(m.group(k)) for k in (2, 3, 4, 5)]
+    return xyz, tets
+
+
+def phase_from_submesh(xyz, tets, sub_xyz, sub_tets, decimals=9):
+    """Cells of (xyz,tets) that are also cells of the sub-mesh get phase 1, others 0.
+
+    Restates CreatePhaseFunc(mymesh, [], [cmpt_mesh], None) (DmriFemLib.py:766-793;
+    PreprocessingMultiCompt.py:107-114): a cell is in the odd group when its midpoint lies
+    inside the compartment mesh.  For a sub-mesh that is a cell subset of the parent this
+    is the same as matching rounded cell midpoints."""
+    mid = np.round(xyz[tets].mean(axis=1), decimals)
+    smid = np.round(sub_xyz[sub_tets].mean(axis=1), decimals)
+    keys = {tuple(r) for r in smid}
+    return np.array([1 if tuple(r) in keys else 0 for r in mid], dtype=np.int32)
+
+
+# ----------------------------------------------------------------------------- generators
+
+# Kuhn/Freudenthal split of the unit cube around the (0,0,0)-(1,1,1) diagonal, cube corner
+# numbering v = i + 2j + 4k.  Same triangulation DOLFIN's BoxMesh produces (SURVEY App. B note ii).
+_KUHN = np.array([[0, 1, 3, 7], [0, 1, 7, 5], [0, 5, 7, 4], [0, 3, 2, 7], [0, 6, 4, 7], [0, 2, 6, 7]])
+
+
+def box_mesh(p0, p1, nx, ny, nz):
+    """Structured box, vertices numbered x-fastest, 6 Kuhn tets per cube."""
+    xs = np.linspace(p0[0], p1[0], nx + 1)
+    ys = np.linspace(p0[1], p1[1], ny + 1)
+    zs = np.linspace(p0[2], p1[2], nz + 1)
+    Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+    xyz = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    base = (i + (nx + 1) * (j + (ny + 1) * k)).ravel()
+    off = np.array([di + (nx + 1) * (dj + (ny + 1) * dk) for dk in (0, 1) for dj in (0, 1) for di in (0, 1)])
+    corners = base[:, None] + off[None, :]                       # (ncube, 8)
+    tets = corners[:, _KUHN].reshape(-1, 4).astype(np.int32)
+    return xyz, tets
+
+
+def extrude_triangulation(xy, tris, zs):
+    """Extrude a 2-D triangulation into prisms and split each prism into 3 tets with the
+    smallest-global-index rule, which makes neighbouring prisms agree on every shared quad."""
+    nv2 = len(xy)
+    nl = len(zs)
+    xyz = np.concatenate([np.column_stack([xy, np.full(nv2, z)]) for z in zs], axis=0)
+    tets = []
+    tris = np.sort(np.asarray(tris), axis=1)                    # a<b<c within each triangle
+    for l in range(nl - 1):
+        a, b, c = (tris[:, m] + l * nv2 for m in range(3))
+        A, B, C = a + nv2, b + nv2, c + nv2
+        # bottom (a,b,c), top (A,B,C); a<b<c and x<X, so the diagonals chosen are a-B, a-C, b-C
+        tets.append(np.stack([a, b, c, C], axis=1))
+        tets.append(np.stack([a, b, C, B], axis=1))
+        tets.append(np.stack([a, B, C, A], axis=1))
+    return xyz, np.concatenate(tets, axis=0).astype(np.int32)
+
+
+def disk_triangulation(radii, nr_per_layer, nsec):
+    """Polar triangulation of concentric rings.  radii: increasing layer radii
+    [R1, R2, ...]; nr_per_layer: radial subdivisions per layer; nsec: sectors.
+    Returns xy, tris, layer (per triangle, 0 = innermost)."""
+    rs, lay = [], []
+    r_prev = 0.0
+    for li, (R, n) in enumerate(zip(radii, nr_per_layer)):
+        for m in range(1, n + 1):
+            rs.append(r_prev + (R - r_prev) * m / n)
+            lay.append(li)
+        r_prev = R
+    th = 2 * np.pi * np.arange(nsec) / nsec
+    xy = [np.zeros((1, 2))]
+    for r in rs:
+        xy.append(np.column_stack([r * np.cos(th), r * np.sin(th)]))
+    xy = np.concatenate(xy, axis=0)
+    tris, tl = [], []
+    ring = lambda m, s: 1 + m * nsec + (s % nsec)
+    for s in range(nsec):
+        tris.append([0, ring(0, s), ring(0, s + 1)])
+        tl.append(lay[0])
+    for m in range(1, len(rs)):
+        for s in range(nsec):
+            a, b = ring(m - 1, s), ring(m - 1, s + 1)
+            c, d = ring(m, s), ring(m, s + 1)
+            tris.append([a, c, d])
+            tris.append([a, d, b])
+            tl += [lay[m], lay[m]]
+    return xy, np.array(tris, dtype=np.int64), np.array(tl, dtype=np.int32)
+
+
+def layered_cylinder(radii=(5.0, 7.5, 10.0), height=5.0, nr_per_layer=(6, 3, 3), nsec=48, nz=4):
+    """Concentric-layer cylinder (axis z) with conforming interfaces; marker = layer index
+    (phase = marker % 2, DmriFemLib.py:764)."""
+    xy, tris, tl = disk_triangulation(radii, nr_per_layer, nsec)
+    zs = np.linspace(-height / 2, height / 2, nz + 1)
+    xyz, tets = extrude_triangulation(xy, tris, zs)
+    marker = np.concatenate([np.concatenate([tl, tl, tl]) for _ in range(nz)]).astype(np.int32)
+    return xyz, tets, marker
+
+
+def cylinder(radius=3.0, length=25.0, nr=4, nsec=16, nz=20):
+    """Single-compartment cylinder of the `cyl*_r_3E_6` shape (axis z)."""
+    xyz, tets, _ = layered_cylinder((radius,), length, (nr,), nsec, nz)
+    return xyz, tets
+
+
+def box_with_sphere(half=10.0, n=20, radius=5.0):
+    """Cell-in-box: Kuhn box [-half,half]^3 with phase 1 where the cell centroid lies in the
+    sphere (synthetic)."""
+    xyz, tets = box_mesh((-half,) * 3, (half,) * 3, n, n, n)
+    cen = xyz[tets].mean(axis=1)
+    phase = (np.linalg.norm(cen, axis=1) < radius).astype(np.int32)
+    return xyz, tets, phase
+
+
+def ecs_slab(nx, ny, nz=2, lx=77.09, ly=75.89, lz=1.0, ncyl=226, rmin=2.0, rmax=5.0, seed=226):
+    """Slab with `ncyl` seeded non-overlapping circular cylinders (axis z); phase 1 inside
+    the cylinders by cell-centroid test (ECS_226Cylinders.ipynb bbox)."""
+    rng = np.random.default_rng(seed)
+    cs, rs = [], []
+    tries = 0
+    while len(cs) < ncyl and tries < 200000:
+        tries += 1
+        r = rng.uniform(rmin, rmax)
+        c = np.array([rng.uniform(-lx + r, lx - r), rng.uniform(-ly + r, ly - r)])
+        if all(np.linalg.norm(c - c2) > r + r2 + 0.3 for c2, r2 in zip(cs, rs)):
+            cs.append(c)
+            rs.append(r)
+    cs, rs = np.array(cs), np.array(rs)
+    xyz, tets = box_mesh((-lx, -ly, -lz), (lx, ly, lz), nx, ny, nz)
+    cen = xyz[tets].mean(axis=1)[:, :2]
+    phase = np.zeros(len(tets), dtype=np.int32)
+    for c, r in zip(cs, rs):
+        phase |= (np.linalg.norm(cen - c[None], axis=1) < r).astype(np.int32)
+    return xyz, tets, phase
+
+
+def neuron_like(n_dend=8, soma_r=10.0, dend_r=1.0, dend_len=200.0, h=1.0, seed=5):
+    """Neuron-like shape: a soma ball with straight dendrite tubes, carved out of a Kuhn
+    grid of spacing h by a cell-centroid test (synthetic)."""
+    rng = np.random.default_rng(seed)
+    dirs = rng.normal(size=(n_dend, 3))
+    dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    L = soma_r + dend_len
+    n = int(np.ceil(2 * L / h))
+    # build only the occupied cubes: march along each dendrite
+    cubes = set()
+    rr = int(np.ceil(soma_r / h)) + 1
+    for i in range(-rr, rr + 1):
+        for j in range(-rr, rr + 1):
+            for k in range(-rr, rr + 1):
+                cubes.add((i, j, k))
+    dr = int(np.ceil(dend_r / h)) + 1
+    for d in dirs:
+        for s in np.arange(0.0, L, h / 2):
+            c = np.floor(d * s / h).astype(int)
+            for i in range(-dr, dr + 1):
+                for j in range(-dr, dr + 1):
+                    for k in range(-dr, dr + 1):
+                        cubes.add((c[0] + i, c[1] + j, c[2] + k))
+    cubes = np.array(sorted(cubes), dtype=np.int64)
+    offs = np.array([[di, dj, dk] for dk in (0, 1) for dj in (0, 1) for di in (0, 1)])
+    corner_ijk = cubes[:, None, :] + offs[None, :, :]                      # (ncube,8,3)
+    big = 1 << 20
+    key = (corner_ijk[..., 0] + big) + ((corner_ijk[..., 1] + big) << 21) + ((corner_ijk[..., 2] + big) << 42)
+    uk, inv = np.unique(key.ravel(), return_inverse=True)
+    corners = inv.reshape(-1, 8)
+    vi = (uk & ((1 << 21) - 1)) - big
+    vj = ((uk >> 21) & ((1 << 21) - 1)) - big
+    vk = (uk >> 42) - big
+    xyz = np.column_stack([vi, vj, vk]).astype(float) * h
+    tets = corners[:, _KUHN].reshape(-1, 4)
+    cen = xyz[tets].mean(axis=1)
+    inside = np.linalg.norm(cen, axis=1) < soma_r
+    for d in dirs:
+        s = cen @ d
+        perp = np.linalg.norm(cen - s[:, None] * d[None], axis=1)
+        inside |= (s > 0) & (s < L) & (perp < dend_r)
+    tets = tets[inside]
+    used = np.unique(tets)
+    remap = -np.ones(len(xyz), dtype=np.int64)
+    remap[used] = np.arange(len(used))
+    return xyz[used].copy(), remap[tets].astype(np.int32)
+
+
+def shuffle_vertices(xyz, tets, seed=0):
+    """Random vertex renumbering (what an unstructured mesher hands you)."""
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(len(xyz))
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    return xyz[perm].copy(), inv[tets].astype(np.int32)
+
+
+def rcm_order(xyz, tets):
+    """Reverse Cuthill-McKee vertex renumbering for gather locality in the SpMV."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    nv = len(xyz)
+    r = np.repeat(tets, 4, axis=1).ravel()
+    c = np.tile(tets, (1, 4)).ravel()
+    A = sp.coo_matrix((np.ones(len(r), dtype=np.int8), (r, c)), shape=(nv, nv)).tocsr()
+    perm = reverse_cuthill_mckee(A, symmetric_mode=True)
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(nv)
+    return xyz[perm].copy(), inv[tets].astype(np.int32)
+
+
+def fibonacci_hemisphere(n, seed=64):
+    """n gradient directions spread over the half-sphere (HARDI sweep)."""
+    i = np.arange(n) + 0.5
+    z = i / n
+    phi = np.pi * (1 + 5 ** 0.5) * i
+    r = np.sqrt(1 - z * z)
+    return np.column_stack([r * np.cos(phi), r * np.sin(phi), z])

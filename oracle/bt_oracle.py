@@ -1,0 +1,474 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (numpy/scipy) of the reference's
+Bloch-Torrey theta-scheme path.  Nothing in the product path may import this module;
+only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference arm.
+
+What it restates (all citations are files under /root/reference):
+
+* weak forms              DmriFemLib.py:41-50 (FuncF_wBC, icondition_wBC),
+                          :58-145 (ThetaMethodL/F_wBC1c/2c), :240-254 (mass, ident_zeros)
+* time loop               DmriFemLib.py:878-915 (MRI_simulation.solve)
+* signal                  DmriFemLib.py:917-931, 970-971
+* sequence scalars        DmriFemLib.py:826-858, GCloudDmriSolver.py:188-193
+* weak pseudo-periodic BC DmriFemLib.py:256-324, 386-450, 599-610
+* pre-assembled variant   comri/one-comp/fenics-python/Theta_solver_BT_one_comp.py:162-236,
+                          comri/one-comp/hpc-fenics-cpp/main.cpp:263-328
+
+Third-party arithmetic that is NOT under /root/reference and is restated from its
+published algorithm: DOLFIN 2019.1.0 `assemble` (P1 element integrals, exact for these
+polynomial integrands -> closed forms below, cross-checked against the reference's own
+FFC-generated `tabulate_tensor` via oracle/_ref, see tests/test_oracle_vs_ufc.py) and
+PETSc 3.7.7 `KSPSolve_BCGS` + `PCJACOBI` + `KSPConvergedDefault` (left-preconditioned
+BiCGStab, real arithmetic on the re/im-split system).
+
+Parity pinning: element level against oracle/_ref (reference code, built here); whole
+path against the recorded `ConvergenceTest.ipynb cell 10` signal 8.440078e-01 and the
+analytic value 0.84389487095614 (tests/test_oracle_golden.py).
+
+Discrete layout used here (and by the CUDA library): the unknowns are the ACTIVE
+(vertex, compartment) pairs, one complex number each, numbered vertex-major.  The
+reference instead carries 2 (1c) or 4 (2c) real fields on every vertex and pins the
+inactive ones with ident_zeros (DmriFemLib.py:246); `expand_to_reference_layout`
+converts.  On that numbering
+    A_n = P + i*theta*c_n*Jg,     P = M/k + theta*(S + R + I + B)
+    b_n = (Q - i*(1-theta)*c_{n-1}*Jg) u^n + (1-theta)*B*u_bc,
+    Q  = M/k - (1-theta)*(S + R + I)
+with c_n = q*f(t_n) and all of M,S,R,Jx,Jy,Jz,I,B real on one shared CSR pattern.
+"""
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+# --------------------------------------------------------------------------- geometry
+
+
+def tet_geometry(xyz, tets):
+    """Signed 6*volume, |T| and P1 gradients (nc,4,3) of each tet."""
+    x = xyz[tets]                                   # (nc,4,3)
+    J = np.stack([x[:, 1] - x[:, 0], x[:, 2] - x[:, 0], x[:, 3] - x[:, 0]], axis=2)  # columns = edges
+    det = np.linalg.det(J)
+    Jinv = np.linalg.inv(J)                         # rows = grad of barycentric 1..3
+    g = np.empty((len(tets), 4, 3))
+    g[:, 1:, :] = Jinv
+    g[:, 0, :] = -Jinv.sum(axis=1)
+    return det, np.abs(det) / 6.0, g
+
+
+def element_matrices(xyz, tets, D=1.0, invT2=0.0):
+    """Closed-form P1 element matrices.
+
+    D: scalar, (nc,) per-cell scalar, or (nc,3,3) / (3,3) tensor (DmriFemLib.py:611-616).
+    invT2: scalar or (nc,) per-cell 1/T2 (DmriFemLib.py:43-44).
+    Returns dict of (nc,4,4) arrays M,S,R,Jx,Jy,Jz and vol (nc,).
+    """
+    nc = len(tets)
+    _, vol, g = tet_geometry(xyz, tets)
+    I4 = np.eye(4)
+    M = vol[:, None, None] * (1.0 + I4)[None] / 20.0
+    D = np.asarray(D, dtype=float)
+    if D.ndim == 0:
+        Dg = D * g
+    elif D.ndim == 1:
+        Dg = D[:, None, None] * g
+    elif D.ndim == 2:
+        Dg = np.einsum("ab,ckb->cka", D, g)
+    else:
+        Dg = np.einsum("cab,ckb->cka", D, g)
+    S = vol[:, None, None] * np.einsum("cia,cja->cij", g, Dg)
+    it2 = np.broadcast_to(np.asarray(invT2, dtype=float), (nc,))
+    R = it2[:, None, None] * M
+    x = xyz[tets]
+    out = {"M": M, "S": S, "R": R, "vol": vol}
+    for d, name in enumerate(("Jx", "Jy", "Jz")):
+        xd = x[:, :, d]                              # (nc,4)
+        sx = xd.sum(axis=1)
+        Jm = sx[:, None, None] + xd[:, :, None] + xd[:, None, :]          # i != j
+        Jd = 2.0 * sx[:, None] + 4.0 * xd                                  # i == j
+        Jm = Jm * (1 - I4)[None] + Jd[:, :, None] * I4[None]
+        out[name] = vol[:, None, None] * Jm / 120.0
+    return out
+
+
+# --------------------------------------------------------------------------- dof map / pattern
+
+
+def dof_map(nv, tets, phase=None):
+    """Number the active (vertex, compartment) pairs vertex-major.
+
+    phase: None (one compartment) or (nc,) int in {0,1} = marker % 2 (DmriFemLib.py:764).
+    Returns cell_dofs (nc,4) int32, ndof, dof_vertex (ndof,), dof_comp (ndof,),
+    vc2dof (nv,2) int32 (-1 where inactive).
+    """
+    tets = np.asarray(tets)
+    if phase is None:
+        phase = np.zeros(len(tets), dtype=np.int32)
+    phase = np.asarray(phase).astype(np.int32)
+    active = np.zeros((nv, 2), dtype=bool)
+    for c in (0, 1):
+        active[np.unique(tets[phase == c]), c] = True
+    flat = active.ravel()
+    ids = np.cumsum(flat) - 1
+    vc2dof = np.where(flat, ids, -1).reshape(nv, 2).astype(np.int32)
+    ndof = int(flat.sum())
+    cell_dofs = vc2dof[tets, phase[:, None]].astype(np.int32)
+    dv, dc = np.nonzero(active)
+    return cell_dofs, ndof, dv.astype(np.int32), dc.astype(np.int32), vc2dof
+
+
+_FACES = np.array([[1, 2, 3], [0, 2, 3], [0, 1, 3], [0, 1, 2]])  # facet i is opposite vertex i (UFC)
+
+
+def facets(tets):
+    """All (cell, local facet) sorted by vertex triple.  Returns key (nf,3), cell, lf."""
+    nc = len(tets)
+    f = np.sort(tets[:, _FACES], axis=2).reshape(nc * 4, 3)
+    cell = np.repeat(np.arange(nc), 4)
+    lf = np.tile(np.arange(4), nc)
+    order = np.lexsort((f[:, 2], f[:, 1], f[:, 0]))
+    return f[order], cell[order], lf[order]
+
+
+def interface_facets(tets, phase):
+    """Interior facets whose two cells have different phase (|jump(phase)| = 1).
+
+    Returns verts (ni,3), cell0 (phase 0 side), cell1 (phase 1 side)."""
+    f, cell, _ = facets(tets)
+    same = np.all(f[1:] == f[:-1], axis=1)
+    i0 = np.nonzero(same)[0]
+    ca, cb = cell[i0], cell[i0 + 1]
+    keep = phase[ca] != phase[cb]
+    ca, cb, fv = ca[keep], cb[keep], f[i0][keep]
+    swap = phase[ca] == 1
+    c0 = np.where(swap, cb, ca)
+    c1 = np.where(swap, ca, cb)
+    return fv, c0, c1
+
+
+def boundary_facets(tets):
+    """Exterior facets: verts (nb,3), owning cell (nb,)."""
+    f, cell, _ = facets(tets)
+    n = len(f)
+    same_next = np.zeros(n, dtype=bool)
+    same_next[:-1] = np.all(f[1:] == f[:-1], axis=1)
+    same_prev = np.zeros(n, dtype=bool)
+    same_prev[1:] = same_next[:-1]
+    ext = ~(same_next | same_prev)
+    return f[ext], cell[ext]
+
+
+def tri_area(xyz, fv):
+    a = xyz[fv[:, 1]] - xyz[fv[:, 0]]
+    b = xyz[fv[:, 2]] - xyz[fv[:, 0]]
+    return 0.5 * np.linalg.norm(np.cross(a, b), axis=1)
+
+
+def scalar_pattern(nv, tets):
+    """The reference's scalar P1 sparsity in mesh-vertex numbering: row v couples to every
+    w sharing a cell with v, diagonal included, columns sorted (UFC dofmap
+    comri/one-comp/hpc-fenics-cpp/ufc/Bloch_Torrey3D.cpp:3869-3884 + PETSc sorted AIJ)."""
+    r = np.repeat(tets, 4, axis=1).ravel()
+    c = np.tile(tets, (1, 4)).ravel()
+    A = sp.coo_matrix((np.ones(len(r), dtype=np.int8), (r, c)), shape=(nv, nv)).tocsr()
+    A.sort_indices()
+    return A.indptr.astype(np.int32), A.indices.astype(np.int32)
+
+
+def _assemble(n, rows, cols, vals):
+    A = sp.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsr()
+    A.sort_indices()
+    return A
+
+
+class Operators:
+    """All real matrices of the path on the active-dof numbering, sharing one pattern."""
+
+
+def assemble(xyz, tets, phase=None, D=1.0, invT2=0.0, kappa=0.0, kappa_facet=None,
+             bnd_kappa_vertex=None):
+    """Assemble M,S,R,Jx,Jy,Jz,(I),(B) + lumped mass on the active-dof numbering.
+
+    kappa: scalar membrane permeability (`-p`); kappa_facet: optional callable
+    (fv, c0, c1)->(ni,) or array aligned with interface_facets() for variable permeability.
+    bnd_kappa_vertex: optional (nv,) vertex values of the P1-interpolated artificial
+    permeability marker kappa_e^h (DmriFemLib.py:601-610) -> boundary matrix B.
+    """
+    xyz = np.asarray(xyz, dtype=float)
+    tets = np.asarray(tets)
+    nv = len(xyz)
+    cell_dofs, ndof, dv, dc, vc2dof = dof_map(nv, tets, phase)
+    em = element_matrices(xyz, tets, D, invT2)
+    rows = np.repeat(cell_dofs, 4, axis=1).ravel()
+    cols = np.tile(cell_dofs, (1, 4)).ravel()
+    ops = Operators()
+    ops.ndof, ops.nv, ops.cell_dofs, ops.dof_vertex, ops.dof_comp, ops.vc2dof = ndof, nv, cell_dofs, dv, dc, vc2dof
+    ops.phase = None if phase is None else np.asarray(phase).astype(np.int32)
+    trip = {k: (rows, cols, em[k].ravel()) for k in ("M", "S", "R", "Jx", "Jy", "Jz")}
+    # interface (DmriFemLib.py:47-50, 112, 139): kappa*(u0-u1)(v0-v1) on facets with |jump(phase)|=1
+    if phase is not None:
+        fv, c0, c1 = interface_facets(tets, ops.phase)
+        if len(fv):
+            if kappa_facet is None:
+                kf = np.full(len(fv), float(kappa))
+            elif callable(kappa_facet):
+                kf = np.asarray(kappa_facet(fv, c0, c1), dtype=float)
+            else:
+                kf = np.asarray(kappa_facet, dtype=float)
+            area = tri_area(xyz, fv)
+            fm = (kf * area)[:, None, None] * (1.0 + np.eye(3))[None] / 12.0      # (ni,3,3)
+            d0 = vc2dof[fv, 0]
+            d1 = vc2dof[fv, 1]
+            assert (d0 >= 0).all() and (d1 >= 0).all()
+            rr, cc, vv = [], [], []
+            for (ra, ca, sgn) in ((d0, d0, 1.0), (d1, d1, 1.0), (d0, d1, -1.0), (d1, d0, -1.0)):
+                rr.append(np.repeat(ra, 3, axis=1).ravel())
+                cc.append(np.tile(ca, (1, 3)).ravel())
+                vv.append(sgn * fm.ravel())
+            trip["I"] = (np.concatenate(rr), np.concatenate(cc), np.concatenate(vv))
+        ops.iface = (fv, c0, c1)
+    # boundary mass with P1-interpolated kappa_e (DmriFemLib.py:92, 143, 601-610; Appendix A.6)
+    if bnd_kappa_vertex is not None:
+        bf, bcell = boundary_facets(tets)
+        kv = np.asarray(bnd_kappa_vertex, dtype=float)[bf]                 # (nb,3)
+        keep = np.any(kv != 0.0, axis=1)
+        bf, bcell, kv = bf[keep], bcell[keep], kv[keep]
+        area = tri_area(xyz, bf)
+        # int phi_i phi_j phi_k = |F| * {1/10, 1/30, 1/60}
+        sk = kv.sum(axis=1)
+        Bm = (sk[:, None, None] + kv[:, :, None] + kv[:, None, :])          # i != j  -> /60
+        Bd = 2.0 * sk[:, None] + 4.0 * kv                                   # i == j  -> /60
+        I3 = np.eye(3)
+        Bm = (Bm * (1 - I3)[None] + Bd[:, :, None] * I3[None]) * area[:, None, None] / 60.0
+        ph = np.zeros(len(tets), dtype=np.int32) if phase is None else ops.phase
+        bd = vc2dof[bf, ph[bcell][:, None]]
+        trip["B"] = (np.repeat(bd, 3, axis=1).ravel(), np.tile(bd, (1, 3)).ravel(), Bm.ravel())
+        ops.bnd = (bf, bcell)
+    # shared pattern = union of every structural entry (cell couplings + interface couplings)
+    rr = np.concatenate([trip[k][0] for k in ("M", "I") if k in trip]).astype(np.int64)
+    cc = np.concatenate([trip[k][1] for k in ("M", "I") if k in trip]).astype(np.int64)
+    keys = np.unique(rr * ndof + cc)
+    prow = (keys // ndof).astype(np.int64)
+    ops.colidx = (keys % ndof).astype(np.int32)
+    ops.rowptr = np.concatenate([[0], np.cumsum(np.bincount(prow, minlength=ndof))]).astype(np.int32)
+    ops.nnz = len(keys)
+    for name in ("M", "S", "R", "Jx", "Jy", "Jz", "I", "B"):
+        data = np.zeros(ops.nnz)
+        if name in trip:
+            r_, c_, v_ = trip[name]
+            idx = np.searchsorted(keys, r_.astype(np.int64) * ndof + c_)
+            assert np.array_equal(keys[idx], r_.astype(np.int64) * ndof + c_)
+            data = np.bincount(idx, weights=v_, minlength=ops.nnz)
+        setattr(ops, name, sp.csr_matrix((data, ops.colidx, ops.rowptr), shape=(ndof, ndof)))
+    ops.lumped = np.asarray(ops.M.sum(axis=1)).ravel()       # 1^T M  -> signal weights
+    return ops
+
+
+def expand_to_reference_layout(ops, u):
+    """Active-dof complex vector -> the reference's blocked real layout
+    (u0r,u0i[,u1r,u1i]) with dof = comp*N_vert + vertex
+    (comri/two-comp/hpc-fenics-cpp/ufc/Bloch_Torrey_NoTime3D.cpp:6372-6400); inactive = 0."""
+    ncomp = 1 if ops.phase is None else 2
+    out = np.zeros((2 * ncomp, ops.nv))
+    out[2 * ops.dof_comp, ops.dof_vertex] = u.real
+    out[2 * ops.dof_comp + 1, ops.dof_vertex] = u.imag
+    return out.ravel()
+
+
+# --------------------------------------------------------------------------- sequences
+
+
+class Sequence:
+    """f(s), F(s)=int_0^s f, int_0^T F^2 evaluated exactly for piecewise profiles.
+
+    Mirrors MRI_parameters (DmriFemLib.py:800-858): `fs_sym` is a sympy Piecewise in `s`,
+    itime_profile_sym integrates it symbolically, integral_term_for_gb integrates F^2 over
+    [0,T], convert_b2q gives q = sqrt(b)/sqrt(int F^2).  sympy is what the reference uses,
+    so the oracle uses it too (the product driver has its own copy of this logic)."""
+
+    def __init__(self, fs_sym, T, s=None):
+        import sympy
+        self.sympy = sympy
+        self.s = s if s is not None else sympy.Symbol("s")
+        self.fs_sym = fs_sym
+        self.T = T
+        u = sympy.Symbol("u")
+        self.ifs_sym = sympy.integrate(fs_sym.subs(self.s, u), (u, 0, self.s))
+        self.int4gb = float(sympy.integrate(self.ifs_sym * self.ifs_sym, (self.s, 0, T)))
+
+    def f(self, t):
+        return float(self.fs_sym.subs(self.s, t))
+
+    def F(self, t):
+        return float(self.ifs_sym.subs(self.s, t))
+
+    def q_from_b(self, b):
+        return np.sqrt(b) / np.sqrt(self.int4gb)
+
+
+def pgse(delta, Delta):
+    """GCloudDmriSolver.py:187-193 (strict `<`: f(delta)=0, f(Delta)=-1, f(T)=0)."""
+    import sympy
+    s = sympy.Symbol("s")
+    T = Delta + delta
+    fs = sympy.Piecewise((1.0, s < delta), (0.0, s < Delta), (-1.0, s < T), (0.0, True))
+    return Sequence(fs, T, s)
+
+
+def q2g(q):
+    return q / 2.675e8 * 1e12          # DmriFemLib.py:684-686
+
+
+def time_grid(T, k, closed=True):
+    """t_n of the loop `while t < T + k` (DmriFemLib.py:897-910), t accumulated in floating
+    point exactly like the reference.  closed=False gives the `t < T` loop of
+    ConvergenceTest.ipynb cell 10 / comri multilayer main.cpp:301."""
+    ts = []
+    t = 0.0
+    lim = T + k if closed else T
+    while t < lim:
+        ts.append(t)
+        t += k
+    return np.array(ts)
+
+
+# --------------------------------------------------------------------------- Krylov (PETSc restated)
+
+
+def bicgstab_petsc(matvec, b, diag, rtol=1e-9, atol=1e-10, maxit=100000, x0=None, dtol=1e4):
+    """PETSc 3.7 KSPSolve_BCGS with left PCJACOBI and the default convergence test
+    (preconditioned residual 2-norm <= max(rtol*||K^-1 b||, atol)), on COMPLEX storage but
+    with REAL inner products Re(a^H b): identical to running it on the reference's
+    real (re,im)-split system.  `diag` is the real Jacobi diagonal P_ii.
+    Returns x, iterations, final preconditioned residual norm, reason (>0 converged)."""
+    rdot = lambda a, c: float(np.dot(a.real, c.real) + np.dot(a.imag, c.imag))
+    Kinv = 1.0 / diag
+    n = len(b)
+    if x0 is None:
+        x = np.zeros(n, dtype=complex)
+        r = Kinv * b
+        bnorm = np.sqrt(rdot(r, r))
+    else:
+        x = x0.astype(complex).copy()
+        r = Kinv * (b - matvec(x))
+        kb = Kinv * b
+        bnorm = np.sqrt(rdot(kb, kb))
+    dp = np.sqrt(rdot(r, r))
+    ttol = max(rtol * bnorm, atol)
+    if dp <= ttol:
+        return x, 0, dp, 2 if dp <= atol and not dp <= rtol * bnorm else 2
+    rp = r.copy()
+    rhoold = alpha = omegaold = 1.0
+    p = np.zeros(n, dtype=complex)
+    v = np.zeros(n, dtype=complex)
+    i = 0
+    while i < maxit:
+        rho = rdot(r, rp)
+        beta = (rho / rhoold) * (alpha / omegaold)
+        p = r - (omegaold * beta) * v + beta * p
+        v = Kinv * matvec(p)
+        d1 = rdot(v, rp)
+        if d1 == 0.0:
+            return x, i, dp, -5
+        alpha = rho / d1
+        s = r - alpha * v
+        t = Kinv * matvec(s)
+        d1 = rdot(s, t)
+        d2 = rdot(t, t)
+        if d2 == 0.0:
+            if rdot(s, s) != 0.0:
+                return x, i, dp, -5
+            x = x + alpha * p
+            return x, i + 1, 0.0, 2
+        omega = d1 / d2
+        x = x + alpha * p + omega * s
+        r = s - omega * t
+        dp = np.sqrt(rdot(r, r))
+        rhoold, omegaold = rho, omega
+        i += 1
+        if not np.isfinite(dp):
+            return x, i, dp, -9
+        if dp <= ttol:
+            return x, i, dp, 2
+        if dp >= dtol * bnorm:
+            return x, i, dp, -4
+        if rho == 0.0:
+            return x, i, dp, -5
+    return x, i, dp, -3
+
+
+# --------------------------------------------------------------------------- weak pseudo-periodic
+
+
+def domain_sizes(xyz, tets):
+    """bbox, hmin, hmax.  h of a cell = longest edge (DOLFIN >= 2017 `Cell::h`, third party;
+    SURVEY Appendix C.17)."""
+    x = xyz[tets]
+    e = [np.linalg.norm(x[:, i] - x[:, j], axis=1) for i in range(4) for j in range(i + 1, 4)]
+    h = np.max(np.stack(e, axis=1), axis=1)
+    return xyz.min(axis=0), xyz.max(axis=0), float(h.min()), float(h.max())
+
+
+def periodic_marker(xyz, pdir, lo, hi, hmin):
+    """Vertex values of kappa_e^h = (3e-3/hmin) * 1[vertex within 1e-2*hmin of a periodic
+    face] (DmriFemLib.py:590, 599-610; the C `||` of products makes it 0/1)."""
+    eps = 1e-2 * hmin
+    m = np.zeros(len(xyz), dtype=bool)
+    for d in range(3):
+        if pdir[d]:
+            m |= (xyz[:, d] < lo[d] + eps) | (xyz[:, d] > hi[d] - eps)
+    return (3e-3 / hmin) * m.astype(float)
+
+
+# --------------------------------------------------------------------------- the theta loop
+
+
+def theta_solve(ops, seq, q, gdir, k, theta=0.5, solver="lu", rtol=1e-9, atol=1e-10, maxit=100000,
+                closed=True, ic=None, nonzero_guess=False, rhs_uses_current_f=False,
+                periodic=None, return_history=False):
+    """MRI_simulation.solve (DmriFemLib.py:878-915) on the pre-assembled operators.
+
+    A_n uses f(t_n); b_n uses f(t_{n-1}), t_{-1}=0 (DmriFemLib.py:901-902, 909); the comri
+    C++ solvers use f(t_n) on both sides (one-comp/hpc-fenics-cpp/main.cpp:300-301)
+    -> rhs_uses_current_f=True.  solver: "lu" (exact discrete solve; stands for MUMPS) or
+    "bicgstab" (PETSc restatement with Jacobi).  periodic: None or a callable
+    (u, F_prev) -> (1-theta)*B*u_bc contribution vector.
+    Returns dict(u, signal, voi, iters, n_steps)."""
+    g = np.asarray(gdir, dtype=float)
+    g = g / np.linalg.norm(g)                                   # DmriFemLib.py:819-821
+    Jg = (g[0] * ops.Jx + g[1] * ops.Jy + g[2] * ops.Jz).tocsr()
+    K0 = ops.S + ops.R + ops.I
+    P = (ops.M / k + theta * (K0 + ops.B)).tocsr()
+    Q = (ops.M / k - (1.0 - theta) * K0).tocsr()
+    diag = P.diagonal()
+    ic = np.ones(ops.ndof) if ic is None else np.asarray(ic, dtype=float)
+    u = ic.astype(complex)
+    ts = time_grid(seq.T, k, closed)
+    lus = {}
+    iters = []
+    hist = []
+    tp = 0.0
+    for t in ts:
+        cA = q * seq.f(t)
+        cb = cA if rhs_uses_current_f else q * seq.f(tp)
+        b = Q @ u - 1j * (1.0 - theta) * cb * (Jg @ u)
+        if periodic is not None:
+            b = b + periodic(u, seq.F(tp))
+        if solver == "lu":
+            key = round(cA, 300)
+            if key not in lus:
+                lus[key] = spla.splu((P + 1j * theta * cA * Jg).tocsc())
+            u = lus[key].solve(b)
+            iters.append(0)
+        else:
+            mv = lambda x, cA=cA: P @ x + 1j * theta * cA * (Jg @ x)
+            u, it, dp, reason = bicgstab_petsc(mv, b, diag, rtol, atol, maxit,
+                                               x0=u if nonzero_guess else None)
+            if reason < 0:
+                raise RuntimeError("Krylov solver did not converge: reason %d" % reason)
+            iters.append(it)
+        if return_history:
+            hist.append(float(ops.lumped @ u.real))
+        tp = t
+    out = dict(u=u, signal=float(ops.lumped @ u.real), voi=float(ops.lumped @ ic),
+               iters=np.array(iters), n_steps=len(ts))
+    if return_history:
+        out["history"] = np.array(hist)
+    return out
