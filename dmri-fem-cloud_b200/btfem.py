@@ -1,0 +1,262 @@
+"""ctypes binding of libbtfem.so (include/btfem.h) -- the only way the Python host layer
+reaches the GPU.  There is no CPU fallback: if the shared library is missing or no CUDA
+device is usable, construction raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbtfem.so")
+
+MAT_IDS = {"M": 0, "S": 1, "R": 2, "Jx": 3, "Jy": 4, "Jz": 5, "I": 6, "B": 7}
+KSP_IDS = {"bicgstab": 0, "gmres": 1}
+PC_IDS = {"jacobi": 0, "none": 1}
+
+_c_double_p = C.POINTER(C.c_double)
+_c_int32_p = C.POINTER(C.c_int32)
+_c_int64_p = C.POINTER(C.c_int64)
+
+
+class SolveArgs(C.Structure):
+    _fields_ = [("nsteps", C.c_int64), ("dt", C.c_double), ("theta", C.c_double),
+                ("cA", _c_double_p), ("cb", _c_double_p), ("Fb", _c_double_p),
+                ("gdir", C.c_double * 3), ("q", C.c_double),
+                ("ksp", C.c_int64), ("pc", C.c_int64), ("rtol", C.c_double), ("atol", C.c_double),
+                ("maxit", C.c_int64), ("nonzero_guess", C.c_int64), ("restart", C.c_int64)]
+
+
+class SolveOut(C.Structure):
+    _fields_ = [("signal", C.c_double), ("signal_comp", C.c_double * 2), ("voi", C.c_double),
+                ("voi_comp", C.c_double * 2), ("whole_vol", C.c_double), ("loop_ms", C.c_double),
+                ("setup_ms", C.c_double), ("total_iters", C.c_int64), ("max_iters", C.c_int64),
+                ("n_spmv", C.c_int64), ("n_kernels", C.c_int64), ("last_reason", C.c_int64)]
+
+
+class BTFemError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libbtfem error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """Load libbtfem.so and declare every prototype of include/btfem.h."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError("libbtfem.so not found at %s -- build it with `python __graft_entry__.py` "
+                           "(there is no CPU fallback)" % path)
+    lib = C.CDLL(path)
+    H = C.c_void_p
+    proto = {
+        "btfem_create": (C.c_int, [C.c_int, C.POINTER(H)]),
+        "btfem_destroy": (None, [H]),
+        "btfem_last_error": (C.c_char_p, [H]),
+        "btfem_version": (C.c_int, []),
+        "btfem_set_mesh": (C.c_int, [H, C.c_int64, _c_double_p, C.c_int64, _c_int32_p, _c_int32_p]),
+        "btfem_set_diffusion": (C.c_int, [H, C.c_int, _c_double_p]),
+        "btfem_set_relaxation": (C.c_int, [H, C.c_int, _c_double_p]),
+        "btfem_set_permeability": (C.c_int, [H, C.c_int, _c_double_p, C.c_int32, _c_int32_p]),
+        "btfem_set_periodic": (C.c_int, [H, _c_int32_p, C.c_double, C.c_double, _c_double_p, _c_double_p]),
+        "btfem_set_initial": (C.c_int, [H, _c_double_p]),
+        "btfem_assemble": (C.c_int, [H]),
+        "btfem_get_sizes": (C.c_int, [H, _c_int64_p, _c_int64_p, _c_int64_p, _c_int64_p]),
+        "btfem_get_pattern": (C.c_int, [H, _c_int32_p, _c_int32_p]),
+        "btfem_get_dofmap": (C.c_int, [H, _c_int32_p, _c_int32_p]),
+        "btfem_get_values": (C.c_int, [H, C.c_int, _c_double_p]),
+        "btfem_get_lumped_mass": (C.c_int, [H, _c_double_p]),
+        "btfem_spmv": (C.c_int, [H, C.c_double, C.c_double, C.c_double, _c_double_p, _c_double_p, _c_double_p]),
+        "btfem_spmv_bench": (C.c_int, [H, C.c_double, C.c_double, C.c_double, _c_double_p, C.c_int32, C.c_int32,
+                                       C.c_int32, _c_double_p]),
+        "btfem_set_lanes": (C.c_int, [H, C.c_int32]),
+        "btfem_solve": (C.c_int, [H, C.POINTER(SolveArgs), C.POINTER(SolveOut), _c_int32_p]),
+        "btfem_get_solution": (C.c_int, [H, _c_double_p]),
+    }
+    for name, (res, args) in proto.items():
+        f = getattr(lib, name)
+        f.restype = res
+        f.argtypes = args
+    lib._btfem_symbols = sorted(proto)
+    if path == LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(_c_double_p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(_c_int32_p)
+
+
+class BTFem:
+    """One problem (mesh + coefficients) on one GPU."""
+
+    def __init__(self, device=0, lib=None):
+        self.lib = lib or load_library()
+        self.h = C.c_void_p()
+        rc = self.lib.btfem_create(int(device), C.byref(self.h))
+        if rc != 0:
+            raise BTFemError(rc, "btfem_create failed: no usable CUDA device %d (libbtfem has no CPU fallback)" % device)
+        self.nv = self.nc = 0
+        self.ndof = self.nnz = 0
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.btfem_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise BTFemError(rc, (self.lib.btfem_last_error(self.h) or b"").decode())
+
+    # ---- problem definition
+    def set_mesh(self, xyz, tets, phase=None):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        tets = np.ascontiguousarray(tets, dtype=np.int32)
+        ph = None if phase is None else np.ascontiguousarray(phase, dtype=np.int32)
+        self.nv, self.nc = len(xyz), len(tets)
+        self.two_comp = ph is not None
+        self._ck(self.lib.btfem_set_mesh(self.h, self.nv, _dp(xyz), self.nc, _ip(tets), None if ph is None else _ip(ph)))
+        self.h2d_bytes = xyz.nbytes + tets.nbytes + (0 if ph is None else ph.nbytes)
+
+    def set_diffusion(self, D):
+        D = np.ascontiguousarray(D, dtype=np.float64)
+        if D.ndim == 0:
+            kind, D = 0, D.reshape(1)
+        elif D.ndim == 1:
+            kind = 1
+            assert len(D) == self.nc
+        else:
+            D = np.ascontiguousarray(np.broadcast_to(D, (self.nc, 3, 3)))
+            kind = 2
+        self._ck(self.lib.btfem_set_diffusion(self.h, kind, _dp(D)))
+
+    def set_relaxation(self, inv_t2):
+        a = np.ascontiguousarray(inv_t2, dtype=np.float64)
+        kind = 0 if a.ndim == 0 else 1
+        a = a.reshape(1) if kind == 0 else a
+        self._ck(self.lib.btfem_set_relaxation(self.h, kind, _dp(a)))
+
+    def set_permeability(self, kappa, marker=None):
+        k = np.ascontiguousarray(kappa, dtype=np.float64)
+        if k.ndim == 0:
+            self._ck(self.lib.btfem_set_permeability(self.h, 0, _dp(k.reshape(1)), 0, None))
+        else:
+            m = np.ascontiguousarray(marker, dtype=np.int32)
+            assert k.ndim == 2 and k.shape[0] == k.shape[1]
+            self._ck(self.lib.btfem_set_permeability(self.h, 1, _dp(k), k.shape[0], _ip(m)))
+
+    def set_periodic(self, pdir, kappa_e, tol, lo, hi):
+        p = np.ascontiguousarray(pdir, dtype=np.int32)
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        self._ck(self.lib.btfem_set_periodic(self.h, _ip(p), float(kappa_e), float(tol), _dp(lo), _dp(hi)))
+
+    def set_initial(self, ic=None):
+        if ic is None:
+            self._ck(self.lib.btfem_set_initial(self.h, None))
+        else:
+            a = np.ascontiguousarray(ic, dtype=np.float64)
+            assert len(a) == self.nv
+            self._ck(self.lib.btfem_set_initial(self.h, _dp(a)))
+
+    def set_lanes(self, lanes):
+        self._ck(self.lib.btfem_set_lanes(self.h, int(lanes)))
+
+    # ---- assembly + parity hooks
+    def assemble(self):
+        self._ck(self.lib.btfem_assemble(self.h))
+        s = [C.c_int64() for _ in range(4)]
+        self._ck(self.lib.btfem_get_sizes(self.h, *[C.byref(x) for x in s]))
+        self.ndof, self.nnz, self.n_iface, self.n_bfacet = (int(x.value) for x in s)
+
+    def pattern(self):
+        rp = np.empty(self.ndof + 1, dtype=np.int32)
+        ci = np.empty(self.nnz, dtype=np.int32)
+        self._ck(self.lib.btfem_get_pattern(self.h, _ip(rp), _ip(ci)))
+        return rp, ci
+
+    def dofmap(self):
+        dv = np.empty(self.ndof, dtype=np.int32)
+        dc = np.empty(self.ndof, dtype=np.int32)
+        self._ck(self.lib.btfem_get_dofmap(self.h, _ip(dv), _ip(dc)))
+        return dv, dc
+
+    def values(self, which):
+        out = np.empty(self.nnz, dtype=np.float64)
+        self._ck(self.lib.btfem_get_values(self.h, MAT_IDS[which], _dp(out)))
+        return out
+
+    def lumped_mass(self):
+        out = np.empty(self.ndof, dtype=np.float64)
+        self._ck(self.lib.btfem_get_lumped_mass(self.h, _dp(out)))
+        return out
+
+    def spmv(self, dt, theta, c, gdir, x):
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        assert len(x) == self.ndof
+        y = np.empty(self.ndof, dtype=np.complex128)
+        g = np.ascontiguousarray(gdir, dtype=np.float64)
+        self._ck(self.lib.btfem_spmv(self.h, dt, theta, c, _dp(g), x.ctypes.data_as(_c_double_p),
+                                     y.ctypes.data_as(_c_double_p)))
+        return y
+
+    def spmv_bench(self, dt, theta, c, gdir, lanes=8, nrep=20, flush_l2=False):
+        g = np.ascontiguousarray(gdir, dtype=np.float64)
+        ms = C.c_double()
+        self._ck(self.lib.btfem_spmv_bench(self.h, dt, theta, c, _dp(g), lanes, nrep, int(flush_l2), C.byref(ms)))
+        return ms.value
+
+    # ---- theta loop
+    def solve(self, dt, theta, cA, cb, gdir, q=0.0, Fb=None, ksp="bicgstab", pc="jacobi", rtol=1e-9, atol=1e-10,
+              maxit=100000, nonzero_guess=False, restart=30, want_iters=False):
+        cA = np.ascontiguousarray(cA, dtype=np.float64)
+        cb = np.ascontiguousarray(cb, dtype=np.float64)
+        assert len(cA) == len(cb)
+        a = SolveArgs()
+        a.nsteps = len(cA)
+        a.dt, a.theta = float(dt), float(theta)
+        a.cA, a.cb = _dp(cA), _dp(cb)
+        if Fb is not None:
+            Fb = np.ascontiguousarray(Fb, dtype=np.float64)
+            a.Fb = _dp(Fb)
+        g = np.asarray(gdir, dtype=np.float64)
+        a.gdir[0], a.gdir[1], a.gdir[2] = g
+        a.q = float(q)
+        a.ksp, a.pc = KSP_IDS[ksp], PC_IDS[pc]
+        a.rtol, a.atol, a.maxit = float(rtol), float(atol), int(maxit)
+        a.nonzero_guess, a.restart = int(bool(nonzero_guess)), int(restart)
+        o = SolveOut()
+        iters = np.zeros(len(cA), dtype=np.int32) if want_iters else None
+        self._ck(self.lib.btfem_solve(self.h, C.byref(a), C.byref(o), None if iters is None else _ip(iters)))
+        res = {k: getattr(o, k) for k, _ in SolveOut._fields_ if k not in ("signal_comp", "voi_comp")}
+        res["signal_comp"] = (o.signal_comp[0], o.signal_comp[1])
+        res["voi_comp"] = (o.voi_comp[0], o.voi_comp[1])
+        res["n_steps"] = len(cA)
+        if want_iters:
+            res["iters"] = iters
+        return res
+
+    def solution(self):
+        u = np.empty(self.ndof, dtype=np.complex128)
+        self._ck(self.lib.btfem_get_solution(self.h, u.ctypes.data_as(_c_double_p)))
+        return u

@@ -1,0 +1,242 @@
+// extern "C" entry points of libbtfem.so: argument checking, error capture, call order.
+#include <cstring>
+
+#include "btfem_internal.cuh"
+
+namespace {
+
+template <typename F>
+int guarded(btfem* h, F&& f) {
+  if (!h) return BTFEM_EINVAL;
+  try {
+    BT_CUDA(cudaSetDevice(h->device));
+    f();
+    h->err.clear();
+    return BTFEM_OK;
+  } catch (const BtError& e) {
+    h->err = e.msg;
+    return e.code;
+  } catch (const std::exception& e) {
+    h->err = e.what();
+    return BTFEM_EINVAL;
+  }
+}
+
+void invalidate(btfem* h) {
+  h->assembled = false;
+  h->comb_dt = -1;
+  h->have_solution = false;
+}
+
+}  // namespace
+
+extern "C" {
+
+int btfem_version(void) { return 100; }
+
+int btfem_create(int device, btfem_t** out) {
+  if (!out) return BTFEM_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return BTFEM_ECUDA;
+  btfem* h = new btfem();
+  h->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return BTFEM_ECUDA;
+  }
+  *out = h;
+  return BTFEM_OK;
+}
+
+void btfem_destroy(btfem_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+  cudaStream_t st = h->stream;
+  delete h;   // frees device arrays
+  if (st) cudaStreamDestroy(st);
+}
+
+const char* btfem_last_error(btfem_t* h) { return h ? h->err.c_str() : "null handle"; }
+
+int btfem_set_mesh(btfem_t* h, int64_t nv, const double* xyz, int64_t nc, const int32_t* tets, const int32_t* phase) {
+  return guarded(h, [&] {
+    BT_REQUIRE(nv > 0 && nc > 0 && xyz && tets, "empty mesh");
+    BT_REQUIRE(nv < (1LL << 30) && nc < (1LL << 27), "mesh too large for 32-bit indices");
+    for (int64_t i = 0; i < 4 * nc; ++i) BT_REQUIRE(tets[i] >= 0 && tets[i] < nv, "tet vertex index out of range");
+    if (phase)
+      for (int64_t i = 0; i < nc; ++i) BT_REQUIRE(phase[i] == 0 || phase[i] == 1, "phase must be 0 or 1");
+    invalidate(h);
+    h->nv = nv;
+    h->nc = nc;
+    h->two_comp = phase != nullptr;
+    h->h_xyz.assign(xyz, xyz + 3 * nv);
+    h->h_tets.assign(tets, tets + 4 * nc);
+    if (phase) h->h_phase.assign(phase, phase + nc); else h->h_phase.clear();
+    h->d_xyz.upload(xyz, 3 * nv, h->stream);
+    h->d_tets.upload(tets, 4 * nc, h->stream);
+    if (phase) h->d_phase.upload(phase, nc, h->stream); else h->d_phase.release();
+    BT_CUDA(cudaStreamSynchronize(h->stream));
+  });
+}
+
+int btfem_set_diffusion(btfem_t* h, int kind, const double* D) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->nc > 0, "set the mesh first");
+    BT_REQUIRE(D && kind >= 0 && kind <= 2, "bad diffusion kind");
+    size_t n = kind == 0 ? 1 : (kind == 1 ? (size_t)h->nc : (size_t)9 * h->nc);
+    h->dkind = kind;
+    h->h_D.assign(D, D + n);
+    invalidate(h);
+  });
+}
+
+int btfem_set_relaxation(btfem_t* h, int kind, const double* inv_t2) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->nc > 0, "set the mesh first");
+    BT_REQUIRE(inv_t2 && kind >= 0 && kind <= 1, "bad relaxation kind");
+    h->t2kind = kind;
+    h->h_invT2.assign(inv_t2, inv_t2 + (kind == 0 ? 1 : (size_t)h->nc));
+    invalidate(h);
+  });
+}
+
+int btfem_set_permeability(btfem_t* h, int kind, const double* kappa, int32_t nmark, const int32_t* marker) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->nc > 0, "set the mesh first");
+    BT_REQUIRE(kappa && kind >= 0 && kind <= 1, "bad permeability kind");
+    if (kind == 0) {
+      h->h_kappa.assign(kappa, kappa + 1);
+      h->h_marker.clear();
+      h->nmark = 0;
+    } else {
+      BT_REQUIRE(nmark > 0 && marker, "permeability table needs cell markers");
+      for (int64_t i = 0; i < h->nc; ++i) BT_REQUIRE(marker[i] >= 0 && marker[i] < nmark, "cell marker out of range");
+      h->h_kappa.assign(kappa, kappa + (size_t)nmark * nmark);
+      h->h_marker.assign(marker, marker + h->nc);
+      h->nmark = nmark;
+    }
+    h->kkind = kind;
+    invalidate(h);
+  });
+}
+
+int btfem_set_periodic(btfem_t* h, const int32_t pdir[3], double kappa_e, double tol, const double lo[3],
+                       const double hi[3]) {
+  return guarded(h, [&] {
+    BT_REQUIRE(pdir && lo && hi, "null argument");
+    h->periodic = (pdir[0] + pdir[1] + pdir[2]) > 0;
+    for (int d = 0; d < 3; ++d) {
+      h->pdir[d] = pdir[d];
+      h->lo[d] = lo[d];
+      h->hi[d] = hi[d];
+    }
+    h->kappa_e = kappa_e;
+    h->ptol = tol;
+    invalidate(h);
+  });
+}
+
+int btfem_set_initial(btfem_t* h, const double* ic) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->nv > 0, "set the mesh first");
+    if (ic) h->h_ic.assign(ic, ic + h->nv); else h->h_ic.clear();
+    invalidate(h);
+  });
+}
+
+int btfem_assemble(btfem_t* h) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->nc > 0, "set the mesh first");
+    if (h->assembled) return;
+    bt_build_dofmap(h);
+    bt_build_facets(h);
+    bt_build_pattern(h);
+    bt_assemble_values(h);
+    h->assembled = true;
+  });
+}
+
+int btfem_get_sizes(btfem_t* h, int64_t* ndof, int64_t* nnz, int64_t* n_iface, int64_t* n_bfacet) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->assembled, "call btfem_assemble first");
+    if (ndof) *ndof = h->ndof;
+    if (nnz) *nnz = h->nnz;
+    if (n_iface) *n_iface = h->n_iface;
+    if (n_bfacet) *n_bfacet = h->n_bfacet;
+  });
+}
+
+int btfem_get_pattern(btfem_t* h, int32_t* rowptr, int32_t* colidx) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->assembled && rowptr && colidx, "call btfem_assemble first");
+    h->d_rowptr.download(rowptr, h->stream);
+    h->d_colidx.download(colidx, h->stream);
+  });
+}
+
+int btfem_get_dofmap(btfem_t* h, int32_t* dof_vertex, int32_t* dof_comp) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->assembled && dof_vertex && dof_comp, "call btfem_assemble first");
+    memcpy(dof_vertex, h->h_dof_vertex.data(), sizeof(int32_t) * h->ndof);
+    memcpy(dof_comp, h->h_dof_comp.data(), sizeof(int32_t) * h->ndof);
+  });
+}
+
+int btfem_get_values(btfem_t* h, int which, double* out) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->assembled && out, "call btfem_assemble first");
+    BT_REQUIRE(which >= 0 && which < 8, "bad matrix id");
+    h->d_vals[which].download(out, h->stream);
+  });
+}
+
+int btfem_get_lumped_mass(btfem_t* h, double* out) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->assembled && out, "call btfem_assemble first");
+    h->d_lumped.download(out, h->stream);
+  });
+}
+
+int btfem_set_lanes(btfem_t* h, int32_t lanes) {
+  return guarded(h, [&] {
+    BT_REQUIRE(lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32, "lanes must be 4, 8, 16 or 32");
+    h->lanes = lanes;
+  });
+}
+
+int btfem_spmv(btfem_t* h, double dt, double theta, double c, const double gdir[3], const double* x, double* y) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->assembled && gdir && x && y, "call btfem_assemble first");
+    bt_spmv_host(h, dt, theta, c, gdir, x, y);
+  });
+}
+
+int btfem_spmv_bench(btfem_t* h, double dt, double theta, double c, const double gdir[3], int32_t lanes, int32_t nrep,
+                     int32_t flush_l2, double* ms_per_launch) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->assembled && gdir && ms_per_launch && nrep > 0, "call btfem_assemble first");
+    bt_spmv_bench(h, dt, theta, c, gdir, lanes, nrep, flush_l2, ms_per_launch);
+  });
+}
+
+int btfem_solve(btfem_t* h, const btfem_solve_args* args, btfem_solve_out* out, int32_t* iters_per_step) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->assembled, "call btfem_assemble first");
+    BT_REQUIRE(args && out && args->cA && args->cb, "null argument");
+    memset(out, 0, sizeof(*out));
+    bt_solve(h, args, out, iters_per_step);
+  });
+}
+
+int btfem_get_solution(btfem_t* h, double* u) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->have_solution && u, "no solution yet");
+    h->d_u.download(reinterpret_cast<double2*>(u), h->stream);
+  });
+}
+
+}  // extern "C"

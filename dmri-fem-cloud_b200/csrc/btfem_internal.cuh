@@ -1,0 +1,170 @@
+// Internal declarations of libbtfem.so (not part of the C-ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/btfem.h"
+
+#define BT_NUM_SMS 148          // B200: 2 dies x 74 SMs
+#define BT_MAX_PARTIALS 4096    // upper bound on the grid of any reducing kernel
+
+struct BtError {
+  int code;
+  std::string msg;
+};
+
+#define BT_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      throw BtError{e_ == cudaErrorMemoryAllocation ? BTFEM_ENOMEM : BTFEM_ECUDA,          \
+                    std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + \
+                        ":" + std::to_string(__LINE__) + ")"};                             \
+    }                                                                                      \
+  } while (0)
+
+#define BT_REQUIRE(cond, text)                         \
+  do {                                                 \
+    if (!(cond)) throw BtError{BTFEM_EINVAL, (text)}; \
+  } while (0)
+
+template <typename T>
+struct DevArray {
+  T* p = nullptr;
+  size_t n = 0;
+  DevArray() {}
+  DevArray(const DevArray&) = delete;
+  DevArray& operator=(const DevArray&) = delete;
+  ~DevArray() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count) {
+    if (count == n && p) return;
+    release();
+    if (count) BT_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    n = count;
+  }
+  void upload(const T* src, size_t count, cudaStream_t s) {
+    alloc(count);
+    if (count) BT_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void download(T* dst, cudaStream_t s) const {
+    if (n) BT_CUDA(cudaMemcpyAsync(dst, p, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+    BT_CUDA(cudaStreamSynchronize(s));
+  }
+  void zero(cudaStream_t s) {
+    if (n) BT_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+  }
+};
+
+// Device-resident Krylov control block: every scalar of the BiCGStab recurrence lives here so
+// that one iteration is a fixed sequence of kernel launches with constant arguments (CUDA graph).
+struct KrylovCtrl {
+  double rho, rho_old, alpha, omega;
+  double bnorm, ttol, rnorm;
+  double rtol, atol, dtol;
+  double theta_cA_scale;   // theta          (A side:   c = theta * cA[step])
+  double theta_cb_scale;   // -(1 - theta)   (RHS side: c = -(1-theta) * cb[step])
+  int maxit;
+  int iters;
+  int done;
+  int reason;
+  int step;        // time step the iteration kernels work on
+  int step_next;   // time step the next RHS launch starts
+  int nonzero_guess;
+  int pad_;
+  unsigned int ticket[8];
+};
+
+struct FacetKey {
+  uint32_t a, b, c;   // sorted vertex ids
+  uint32_t cf;        // cell*4 + local facet
+};
+
+struct btfem {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  // ---- inputs (host copies are kept: they are small next to the matrices and make setters order-free)
+  int64_t nv = 0, nc = 0;
+  bool two_comp = false;
+  std::vector<double> h_xyz;
+  std::vector<int32_t> h_tets, h_phase;
+  int dkind = 0;
+  std::vector<double> h_D{1.0};
+  int t2kind = 0;
+  std::vector<double> h_invT2{0.0};
+  int kkind = 0;
+  std::vector<double> h_kappa{0.0};
+  int32_t nmark = 0;
+  std::vector<int32_t> h_marker;
+  bool periodic = false;
+  int32_t pdir[3] = {0, 0, 0};
+  double kappa_e = 0.0, ptol = 0.0, lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  std::vector<double> h_ic;   // empty = all ones
+
+  // ---- device mesh
+  DevArray<double> d_xyz, d_D, d_invT2, d_kappa_tab, d_bmark /*kappa_e^h per vertex*/;
+  DevArray<int32_t> d_tets, d_phase, d_marker, d_cell_dofs, d_dof_vertex, d_dof_comp, d_vc2dof;
+  std::vector<int32_t> h_dof_vertex, h_dof_comp;
+
+  // ---- facets
+  int64_t n_iface = 0, n_bfacet = 0;
+  DevArray<int32_t> d_if_dofs;     // [n_iface*6]: d0[3], d1[3]
+  DevArray<int32_t> d_if_verts;    // [n_iface*3]
+  DevArray<double> d_if_kappa;     // [n_iface]
+  DevArray<int32_t> d_bf_verts;    // [n_bfacet*3]
+  DevArray<int32_t> d_bf_dofs;     // [n_bfacet*3]
+
+  // ---- pattern
+  bool assembled = false;
+  int64_t ndof = 0, nnz = 0, nsrc = 0;
+  DevArray<int32_t> d_rowptr, d_colidx, d_rowidx, d_diagpos;
+  DevArray<uint32_t> d_src;        // contribution ids sorted by (row,col), stable
+  DevArray<int64_t> d_seg;         // [nnz+1] segment offsets into d_src
+  DevArray<double> d_vals[8];      // M,S,R,Jx,Jy,Jz,I,B
+  DevArray<double> d_lumped, d_ic_dof;
+  double whole_vol = 0, voi = 0, voi_comp[2] = {0, 0};
+
+  // ---- per-solve state
+  DevArray<double2> d_PJ, d_QJ;
+  DevArray<double> d_Bhat, d_dinv;
+  DevArray<double2> d_u, d_r, d_rp, d_p, d_v, d_s, d_t;
+  DevArray<double> d_cA, d_cb, d_Fb;
+  DevArray<double> d_partials;     // [8][BT_MAX_PARTIALS]
+  DevArray<KrylovCtrl> d_ctrl;
+  KrylovCtrl* h_ctrl = nullptr;    // pinned
+  double comb_dt = -1, comb_theta = -1, comb_g[3] = {0, 0, 0};
+  int comb_pc = -1;
+  bool have_solution = false;
+  int lanes = 8;                   // threads per row of the fused SpMV
+
+  // periodic gather operator G: u_bc[b] = phase * sum_k w[b][k] * u[idx[b][k]]
+  int64_t n_pb = 0;
+  DevArray<int32_t> d_pb_dof, d_pb_src;   // [n_pb], [n_pb*3]
+  DevArray<double> d_pb_w, d_pb_gdx;      // [n_pb*3], [n_pb] (g . dx premultiplied per direction at solve)
+  DevArray<double> d_pb_dx;               // [n_pb*3] displacement to the mirrored point
+  DevArray<double2> d_ubc;                // [ndof] (zero off the periodic faces)
+};
+
+// setup.cu
+void bt_build_dofmap(btfem* h);
+void bt_build_facets(btfem* h);
+void bt_build_pattern(btfem* h);
+void bt_assemble_values(btfem* h);
+void bt_build_periodic(btfem* h);
+
+// solve.cu
+void bt_combine(btfem* h, double dt, double theta, const double g[3], int pc);
+void bt_spmv_host(btfem* h, double dt, double theta, double c, const double g[3], const double* x, double* y);
+void bt_spmv_bench(btfem* h, double dt, double theta, double c, const double g[3], int lanes, int nrep, int flush_l2,
+                   double* ms);
+void bt_solve(btfem* h, const btfem_solve_args* a, btfem_solve_out* out, int32_t* iters_per_step);

@@ -1,0 +1,555 @@
+// One-time setup on the GPU: dof map, interface/boundary facets, CSR pattern (sort + unique),
+// and deterministic gather-assembly of M, S, R, Jx, Jy, Jz, I, B.
+//
+// Reference behaviour being replaced (files under /root/reference):
+//   dof numbering           comri/*/hpc-fenics-cpp/ufc/Bloch_Torrey3D.cpp `tabulate_dofs` (blocked by
+//                           component, dof = comp*N + vertex) + ident_zeros pinning, DmriFemLib.py:246
+//   element integrals       FFC `tabulate_tensor` (cell / interior facet / exterior facet integrals)
+//   matrix insertion        DOLFIN Assembler -> PETSc MatSetValues, every time step (DmriFemLib.py:904-905)
+// Here: assembled ONCE; closed-form P1 integrals (exact for these integrands); contributions are
+// summed per nonzero in a fixed order (no atomics), so the matrices are bit-reproducible.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+
+#include "btfem_internal.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+inline int nblocks(int64_t n, int tpb = TPB) { return (int)std::max<int64_t>(1, (n + tpb - 1) / tpb); }
+
+struct TempStorage {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~TempStorage() {
+    if (p) cudaFree(p);
+  }
+  void reserve(size_t b) {
+    if (b <= bytes) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    BT_CUDA(cudaMalloc(&p, b));
+    bytes = b;
+  }
+};
+
+// ------------------------------------------------------------------------------------ facets
+
+__global__ void k_gen_facets(int64_t nc, const int32_t* __restrict__ tets, FacetKey* __restrict__ keys) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nc * 4) return;
+  int64_t c = i >> 2;
+  int lf = (int)(i & 3);
+  uint32_t v[3];
+  int m = 0;
+  for (int k = 0; k < 4; ++k)
+    if (k != lf) v[m++] = (uint32_t)tets[c * 4 + k];   // facet lf is opposite vertex lf (UFC)
+  if (v[0] > v[1]) { uint32_t t = v[0]; v[0] = v[1]; v[1] = t; }
+  if (v[1] > v[2]) { uint32_t t = v[1]; v[1] = v[2]; v[2] = t; }
+  if (v[0] > v[1]) { uint32_t t = v[0]; v[0] = v[1]; v[1] = t; }
+  keys[i] = FacetKey{v[0], v[1], v[2], (uint32_t)i};
+}
+
+struct FacetLess {
+  __host__ __device__ bool operator()(const FacetKey& x, const FacetKey& y) const {
+    if (x.a != y.a) return x.a < y.a;
+    if (x.b != y.b) return x.b < y.b;
+    if (x.c != y.c) return x.c < y.c;
+    return x.cf < y.cf;   // total order -> deterministic result
+  }
+};
+
+__device__ inline bool same_facet(const FacetKey& x, const FacetKey& y) {
+  return x.a == y.a && x.b == y.b && x.c == y.c;
+}
+
+// flag_if[i] = facet i and i+1 are the two sides of an interface facet (|jump(phase)| = 1)
+// flag_bd[i] = facet i is exterior and touches the periodic marker
+__global__ void k_flag_facets(int64_t nf, const FacetKey* __restrict__ keys, const int32_t* __restrict__ phase,
+                              const double* __restrict__ bmark, uint8_t* __restrict__ flag_if,
+                              uint8_t* __restrict__ flag_bd) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nf) return;
+  FacetKey k = keys[i];
+  bool next_same = (i + 1 < nf) && same_facet(k, keys[i + 1]);
+  bool prev_same = (i > 0) && same_facet(k, keys[i - 1]);
+  uint8_t fi = 0, fb = 0;
+  if (next_same && phase) {
+    fi = phase[k.cf >> 2] != phase[keys[i + 1].cf >> 2];
+  }
+  if (!next_same && !prev_same && bmark) {
+    fb = (bmark[k.a] != 0.0) || (bmark[k.b] != 0.0) || (bmark[k.c] != 0.0);
+  }
+  flag_if[i] = fi;
+  flag_bd[i] = fb;
+}
+
+__global__ void k_fill_iface(int64_t ni, const int64_t* __restrict__ sel, const FacetKey* __restrict__ keys,
+                             const int32_t* __restrict__ phase, const int32_t* __restrict__ vc2dof,
+                             int kkind, const double* __restrict__ kappa_tab, int nmark,
+                             const int32_t* __restrict__ marker, int32_t* __restrict__ if_verts,
+                             int32_t* __restrict__ if_dofs, double* __restrict__ if_kappa) {
+  int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (f >= ni) return;
+  int64_t i = sel[f];
+  FacetKey k = keys[i];
+  uint32_t v[3] = {k.a, k.b, k.c};
+  for (int m = 0; m < 3; ++m) {
+    if_verts[f * 3 + m] = (int32_t)v[m];
+    if_dofs[f * 6 + m] = vc2dof[2 * (int64_t)v[m] + 0];
+    if_dofs[f * 6 + 3 + m] = vc2dof[2 * (int64_t)v[m] + 1];
+  }
+  double kap;
+  if (kkind == 0) {
+    kap = kappa_tab[0];
+  } else {
+    int ma = marker[k.cf >> 2], mb = marker[keys[i + 1].cf >> 2];
+    int lo = ma < mb ? ma : mb, hi = ma < mb ? mb : ma;
+    kap = kappa_tab[lo * nmark + hi];
+  }
+  if_kappa[f] = kap;
+}
+
+__global__ void k_fill_bfacet(int64_t nb, const int64_t* __restrict__ sel, const FacetKey* __restrict__ keys,
+                              const int32_t* __restrict__ phase, const int32_t* __restrict__ vc2dof,
+                              int32_t* __restrict__ bf_verts, int32_t* __restrict__ bf_dofs) {
+  int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (f >= nb) return;
+  FacetKey k = keys[sel[f]];
+  int comp = phase ? phase[k.cf >> 2] : 0;   // weighted by phase / (1-phase) of the boundary cell (DmriFemLib.py:143)
+  uint32_t v[3] = {k.a, k.b, k.c};
+  for (int m = 0; m < 3; ++m) {
+    bf_verts[f * 3 + m] = (int32_t)v[m];
+    bf_dofs[f * 3 + m] = vc2dof[2 * (int64_t)v[m] + comp];
+  }
+}
+
+// ------------------------------------------------------------------------------------ pattern
+
+// contribution id -> (row, col).  ids: [0,16nc) cells, then 36 per interface facet, then 9 per boundary facet
+__device__ inline void src_to_rc(uint32_t s, uint32_t ncell16, uint32_t nif36, const int32_t* cell_dofs,
+                                 const int32_t* if_dofs, const int32_t* bf_dofs, int32_t& r, int32_t& c) {
+  if (s < ncell16) {
+    uint32_t t = s >> 4;
+    r = cell_dofs[t * 4 + ((s >> 2) & 3)];
+    c = cell_dofs[t * 4 + (s & 3)];
+  } else if (s < ncell16 + nif36) {
+    uint32_t q = s - ncell16;
+    uint32_t f = q / 36, k = q % 36;
+    uint32_t blk = k / 9, i = (k % 9) / 3, j = k % 3;
+    // blocks: (d0,d0) (d1,d1) (d0,d1) (d1,d0)
+    int rs = (blk == 1 || blk == 3) ? 3 : 0;
+    int cs = (blk == 1 || blk == 2) ? 3 : 0;
+    r = if_dofs[f * 6 + rs + i];
+    c = if_dofs[f * 6 + cs + j];
+  } else {
+    uint32_t q = s - ncell16 - nif36;
+    uint32_t f = q / 9, k = q % 9;
+    r = bf_dofs[f * 3 + k / 3];
+    c = bf_dofs[f * 3 + k % 3];
+  }
+}
+
+__global__ void k_gen_keys(int64_t nsrc, uint32_t ncell16, uint32_t nif36, const int32_t* __restrict__ cell_dofs,
+                           const int32_t* __restrict__ if_dofs, const int32_t* __restrict__ bf_dofs,
+                           uint64_t* __restrict__ keys, uint32_t* __restrict__ src) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nsrc) return;
+  int32_t r, c;
+  src_to_rc((uint32_t)i, ncell16, nif36, cell_dofs, if_dofs, bf_dofs, r, c);
+  keys[i] = ((uint64_t)(uint32_t)r << 32) | (uint32_t)c;
+  src[i] = (uint32_t)i;
+}
+
+__global__ void k_head_flags(int64_t n, const uint64_t* __restrict__ keys, int64_t* __restrict__ head) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+// pos = inclusive scan of head flags; entry p = pos-1 starts where head==1
+__global__ void k_scatter_unique(int64_t n, const uint64_t* __restrict__ keys, const int64_t* __restrict__ pos,
+                                 int32_t* __restrict__ rowidx, int32_t* __restrict__ colidx,
+                                 int64_t* __restrict__ seg, int64_t nnz) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool head = (i == 0) || (keys[i] != keys[i - 1]);
+  if (head) {
+    int64_t p = pos[i] - 1;
+    rowidx[p] = (int32_t)(keys[i] >> 32);
+    colidx[p] = (int32_t)(keys[i] & 0xffffffffu);
+    seg[p] = i;
+  }
+  if (i == n - 1) seg[nnz] = n;
+}
+
+__global__ void k_rowptr(int64_t ndof, int64_t nnz, const int32_t* __restrict__ rowidx, int32_t* __restrict__ rowptr) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r > ndof) return;
+  // lower_bound(rowidx, r)
+  int64_t lo = 0, hi = nnz;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (rowidx[mid] < (int32_t)r) lo = mid + 1; else hi = mid;
+  }
+  rowptr[r] = (int32_t)lo;
+}
+
+__global__ void k_diagpos(int64_t ndof, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                          int32_t* __restrict__ diagpos) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= ndof) return;
+  int lo = rowptr[r], hi = rowptr[r + 1];
+  int d = -1;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    int c = colidx[mid];
+    if (c == (int)r) { d = mid; break; }
+    if (c < (int)r) lo = mid + 1; else hi = mid;
+  }
+  diagpos[r] = d;
+}
+
+// ------------------------------------------------------------------------------------ assembly
+
+struct AsmArgs {
+  int64_t nnz;
+  uint32_t ncell16, nif36;
+  const int64_t* seg;
+  const uint32_t* src;
+  const int32_t* tets;
+  const double* xyz;
+  int dkind;
+  const double* D;
+  int t2kind;
+  const double* invT2;
+  const int32_t* if_verts;
+  const double* if_kappa;
+  const int32_t* bf_verts;
+  const double* bmark;
+  double *M, *S, *R, *Jx, *Jy, *Jz, *I, *B;
+};
+
+__device__ inline double tri_area(const double* xyz, int a, int b, int c) {
+  double ax = xyz[3 * b] - xyz[3 * a], ay = xyz[3 * b + 1] - xyz[3 * a + 1], az = xyz[3 * b + 2] - xyz[3 * a + 2];
+  double bx = xyz[3 * c] - xyz[3 * a], by = xyz[3 * c + 1] - xyz[3 * a + 1], bz = xyz[3 * c + 2] - xyz[3 * a + 2];
+  double cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx;
+  return 0.5 * sqrt(cx * cx + cy * cy + cz * cz);
+}
+
+// One thread per CSR nonzero; its contributions (cells, interface facets, boundary facets) are
+// visited in ascending contribution id (stable radix sort) -> fixed summation order.
+__global__ void __launch_bounds__(TPB) k_assemble(AsmArgs a) {
+  int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= a.nnz) return;
+  double m = 0, s = 0, r = 0, jx = 0, jy = 0, jz = 0, ii = 0, bb = 0;
+  for (int64_t q = a.seg[p]; q < a.seg[p + 1]; ++q) {
+    uint32_t sid = a.src[q];
+    if (sid < a.ncell16) {
+      uint32_t t = sid >> 4;
+      int i = (sid >> 2) & 3, j = sid & 3;
+      int4 tv = *reinterpret_cast<const int4*>(a.tets + 4 * (int64_t)t);
+      int vid[4] = {tv.x, tv.y, tv.z, tv.w};
+      double x[4][3];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        x[k][0] = a.xyz[3 * (int64_t)vid[k]];
+        x[k][1] = a.xyz[3 * (int64_t)vid[k] + 1];
+        x[k][2] = a.xyz[3 * (int64_t)vid[k] + 2];
+      }
+      // Jacobian columns e1,e2,e3 ; cofactors give the gradients of the barycentric functions
+      double e[3][3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        e[k][0] = x[k + 1][0] - x[0][0];
+        e[k][1] = x[k + 1][1] - x[0][1];
+        e[k][2] = x[k + 1][2] - x[0][2];
+      }
+      // c1 = e2 x e3, c2 = e3 x e1, c3 = e1 x e2 ; det = e1 . c1 ; grad(lambda_k) = c_k / det
+      double c[4][3];
+      c[1][0] = e[1][1] * e[2][2] - e[1][2] * e[2][1];
+      c[1][1] = e[1][2] * e[2][0] - e[1][0] * e[2][2];
+      c[1][2] = e[1][0] * e[2][1] - e[1][1] * e[2][0];
+      c[2][0] = e[2][1] * e[0][2] - e[2][2] * e[0][1];
+      c[2][1] = e[2][2] * e[0][0] - e[2][0] * e[0][2];
+      c[2][2] = e[2][0] * e[0][1] - e[2][1] * e[0][0];
+      c[3][0] = e[0][1] * e[1][2] - e[0][2] * e[1][1];
+      c[3][1] = e[0][2] * e[1][0] - e[0][0] * e[1][2];
+      c[3][2] = e[0][0] * e[1][1] - e[0][1] * e[1][0];
+      double det = e[0][0] * c[1][0] + e[0][1] * c[1][1] + e[0][2] * c[1][2];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) c[0][d] = -(c[1][d] + c[2][d] + c[3][d]);
+      double vol = fabs(det) / 6.0;
+      double inv = 1.0 / det;
+      double gi[3] = {c[i][0] * inv, c[i][1] * inv, c[i][2] * inv};
+      double gj[3] = {c[j][0] * inv, c[j][1] * inv, c[j][2] * inv};
+      double dg[3];
+      if (a.dkind == 0) {
+        double d0 = a.D[0];
+        dg[0] = d0 * gj[0]; dg[1] = d0 * gj[1]; dg[2] = d0 * gj[2];
+      } else if (a.dkind == 1) {
+        double d0 = a.D[t];
+        dg[0] = d0 * gj[0]; dg[1] = d0 * gj[1]; dg[2] = d0 * gj[2];
+      } else {
+        const double* Dt = a.D + 9 * (int64_t)t;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) dg[d] = Dt[3 * d] * gj[0] + Dt[3 * d + 1] * gj[1] + Dt[3 * d + 2] * gj[2];
+      }
+      double mij = vol * (i == j ? 2.0 : 1.0) / 20.0;
+      m += mij;
+      s += vol * (gi[0] * dg[0] + gi[1] * dg[1] + gi[2] * dg[2]);
+      r += (a.t2kind == 0 ? a.invT2[0] : a.invT2[t]) * mij;
+      double sx[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) sx[d] = x[0][d] + x[1][d] + x[2][d] + x[3][d];
+      if (i == j) {
+        jx += vol * (2.0 * sx[0] + 4.0 * x[i][0]) / 120.0;
+        jy += vol * (2.0 * sx[1] + 4.0 * x[i][1]) / 120.0;
+        jz += vol * (2.0 * sx[2] + 4.0 * x[i][2]) / 120.0;
+      } else {
+        jx += vol * (sx[0] + x[i][0] + x[j][0]) / 120.0;
+        jy += vol * (sx[1] + x[i][1] + x[j][1]) / 120.0;
+        jz += vol * (sx[2] + x[i][2] + x[j][2]) / 120.0;
+      }
+    } else if (sid < a.ncell16 + a.nif36) {
+      uint32_t q2 = sid - a.ncell16;
+      uint32_t f = q2 / 36, k = q2 % 36;
+      uint32_t blk = k / 9, i = (k % 9) / 3, j = k % 3;
+      double area = tri_area(a.xyz, a.if_verts[3 * f], a.if_verts[3 * f + 1], a.if_verts[3 * f + 2]);
+      double v = a.if_kappa[f] * area * (i == j ? 2.0 : 1.0) / 12.0;
+      ii += (blk < 2) ? v : -v;
+    } else {
+      uint32_t q2 = sid - a.ncell16 - a.nif36;
+      uint32_t f = q2 / 9, k = q2 % 9;
+      int i = k / 3, j = k % 3;
+      int va = a.bf_verts[3 * f], vb = a.bf_verts[3 * f + 1], vc = a.bf_verts[3 * f + 2];
+      double area = tri_area(a.xyz, va, vb, vc);
+      double kv[3] = {a.bmark[va], a.bmark[vb], a.bmark[vc]};
+      double sk = kv[0] + kv[1] + kv[2];
+      double w = (i == j) ? (2.0 * sk + 4.0 * kv[i]) : (sk + kv[i] + kv[j]);
+      bb += area * w / 60.0;
+    }
+  }
+  a.M[p] = m; a.S[p] = s; a.R[p] = r; a.Jx[p] = jx; a.Jy[p] = jy; a.Jz[p] = jz; a.I[p] = ii; a.B[p] = bb;
+}
+
+__global__ void k_lumped(int64_t ndof, const int32_t* __restrict__ rowptr, const double* __restrict__ M,
+                         double* __restrict__ lumped) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= ndof) return;
+  double s = 0;
+  for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) s += M[k];
+  lumped[r] = s;
+}
+
+}  // namespace
+
+// ===================================================================================== host side
+
+void bt_build_dofmap(btfem* h) {
+  const int64_t nv = h->nv, nc = h->nc;
+  std::vector<uint8_t> active(2 * nv, 0);
+  for (int64_t c = 0; c < nc; ++c) {
+    int ph = h->two_comp ? h->h_phase[c] : 0;
+    for (int k = 0; k < 4; ++k) active[2 * (int64_t)h->h_tets[4 * c + k] + ph] = 1;
+  }
+  std::vector<int32_t> vc2dof(2 * nv, -1);
+  h->h_dof_vertex.clear();
+  h->h_dof_comp.clear();
+  int32_t n = 0;
+  for (int64_t v = 0; v < nv; ++v)
+    for (int c = 0; c < 2; ++c)
+      if (active[2 * v + c]) {
+        vc2dof[2 * v + c] = n++;
+        h->h_dof_vertex.push_back((int32_t)v);
+        h->h_dof_comp.push_back(c);
+      }
+  h->ndof = n;
+  std::vector<int32_t> cell_dofs(4 * nc);
+  for (int64_t c = 0; c < nc; ++c) {
+    int ph = h->two_comp ? h->h_phase[c] : 0;
+    for (int k = 0; k < 4; ++k) cell_dofs[4 * c + k] = vc2dof[2 * (int64_t)h->h_tets[4 * c + k] + ph];
+  }
+  h->d_vc2dof.upload(vc2dof.data(), vc2dof.size(), h->stream);
+  h->d_cell_dofs.upload(cell_dofs.data(), cell_dofs.size(), h->stream);
+  h->d_dof_vertex.upload(h->h_dof_vertex.data(), h->h_dof_vertex.size(), h->stream);
+  h->d_dof_comp.upload(h->h_dof_comp.data(), h->h_dof_comp.size(), h->stream);
+  BT_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+void bt_build_facets(btfem* h) {
+  h->n_iface = 0;
+  h->n_bfacet = 0;
+  if (!h->two_comp && !h->periodic) return;
+  cudaStream_t st = h->stream;
+  const int64_t nf = 4 * h->nc;
+  // periodic marker kappa_e^h per vertex (DmriFemLib.py:601-610): kappa_e where the vertex lies within
+  // tol of a min/max face of a periodic direction
+  if (h->periodic) {
+    std::vector<double> bm(h->nv, 0.0);
+    for (int64_t v = 0; v < h->nv; ++v) {
+      bool on = false;
+      for (int d = 0; d < 3; ++d)
+        if (h->pdir[d]) {
+          double x = h->h_xyz[3 * v + d];
+          on = on || (x < h->lo[d] + h->ptol) || (x > h->hi[d] - h->ptol);
+        }
+      bm[v] = on ? h->kappa_e : 0.0;
+    }
+    h->d_bmark.upload(bm.data(), bm.size(), st);
+  } else {
+    h->d_bmark.release();
+  }
+  DevArray<FacetKey> keys;
+  keys.alloc(nf);
+  k_gen_facets<<<nblocks(nf), TPB, 0, st>>>(h->nc, h->d_tets.p, keys.p);
+  TempStorage tmp;
+  size_t bytes = 0;
+  BT_CUDA(cub::DeviceMergeSort::SortKeys(nullptr, bytes, keys.p, nf, FacetLess(), st));
+  tmp.reserve(bytes);
+  BT_CUDA(cub::DeviceMergeSort::SortKeys(tmp.p, bytes, keys.p, nf, FacetLess(), st));
+  DevArray<uint8_t> f_if, f_bd;
+  f_if.alloc(nf);
+  f_bd.alloc(nf);
+  k_flag_facets<<<nblocks(nf), TPB, 0, st>>>(nf, keys.p, h->two_comp ? h->d_phase.p : nullptr,
+                                             h->periodic ? h->d_bmark.p : nullptr, f_if.p, f_bd.p);
+  DevArray<int64_t> sel_if, sel_bd, nsel;
+  sel_if.alloc(nf);
+  sel_bd.alloc(nf);
+  nsel.alloc(2);
+  cub::CountingInputIterator<int64_t> idx(0);
+  bytes = 0;
+  BT_CUDA(cub::DeviceSelect::Flagged(nullptr, bytes, idx, f_if.p, sel_if.p, nsel.p, nf, st));
+  tmp.reserve(bytes);
+  BT_CUDA(cub::DeviceSelect::Flagged(tmp.p, bytes, idx, f_if.p, sel_if.p, nsel.p, nf, st));
+  BT_CUDA(cub::DeviceSelect::Flagged(tmp.p, bytes, idx, f_bd.p, sel_bd.p, nsel.p + 1, nf, st));
+  int64_t cnt[2];
+  nsel.download(cnt, st);
+  h->n_iface = cnt[0];
+  h->n_bfacet = cnt[1];
+  if (h->n_iface) {
+    h->d_if_verts.alloc(3 * h->n_iface);
+    h->d_if_dofs.alloc(6 * h->n_iface);
+    h->d_if_kappa.alloc(h->n_iface);
+    h->d_kappa_tab.upload(h->h_kappa.data(), h->h_kappa.size(), st);
+    if (h->kkind == 1) h->d_marker.upload(h->h_marker.data(), h->h_marker.size(), st);
+    k_fill_iface<<<nblocks(h->n_iface), TPB, 0, st>>>(h->n_iface, sel_if.p, keys.p, h->d_phase.p, h->d_vc2dof.p,
+                                                      h->kkind, h->d_kappa_tab.p, h->nmark,
+                                                      h->kkind == 1 ? h->d_marker.p : nullptr, h->d_if_verts.p,
+                                                      h->d_if_dofs.p, h->d_if_kappa.p);
+  }
+  if (h->n_bfacet) {
+    h->d_bf_verts.alloc(3 * h->n_bfacet);
+    h->d_bf_dofs.alloc(3 * h->n_bfacet);
+    k_fill_bfacet<<<nblocks(h->n_bfacet), TPB, 0, st>>>(h->n_bfacet, sel_bd.p, keys.p,
+                                                        h->two_comp ? h->d_phase.p : nullptr, h->d_vc2dof.p,
+                                                        h->d_bf_verts.p, h->d_bf_dofs.p);
+  }
+  BT_CUDA(cudaGetLastError());
+  BT_CUDA(cudaStreamSynchronize(st));
+}
+
+void bt_build_pattern(btfem* h) {
+  cudaStream_t st = h->stream;
+  const int64_t ncell16 = 16 * h->nc, nif36 = 36 * h->n_iface, nb9 = 9 * h->n_bfacet;
+  const int64_t nsrc = ncell16 + nif36 + nb9;
+  BT_REQUIRE(nsrc < (int64_t)0xffffffffLL, "mesh too large for 32-bit contribution ids");
+  h->nsrc = nsrc;
+  DevArray<uint64_t> keys_in, keys_out;
+  DevArray<uint32_t> src_in;
+  keys_in.alloc(nsrc);
+  keys_out.alloc(nsrc);
+  src_in.alloc(nsrc);
+  h->d_src.alloc(nsrc);
+  k_gen_keys<<<nblocks(nsrc), TPB, 0, st>>>(nsrc, (uint32_t)ncell16, (uint32_t)nif36, h->d_cell_dofs.p,
+                                            h->d_if_dofs.p, h->d_bf_dofs.p, keys_in.p, src_in.p);
+  int bits = 1;
+  while ((1LL << bits) < h->ndof) ++bits;
+  TempStorage tmp;
+  size_t bytes = 0;
+  BT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_in.p, keys_out.p, src_in.p, h->d_src.p, nsrc, 0,
+                                          32 + bits, st));
+  tmp.reserve(bytes);
+  BT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, keys_in.p, keys_out.p, src_in.p, h->d_src.p, nsrc, 0,
+                                          32 + bits, st));
+  keys_in.release();
+  src_in.release();
+  DevArray<int64_t> pos;
+  pos.alloc(nsrc);
+  k_head_flags<<<nblocks(nsrc), TPB, 0, st>>>(nsrc, keys_out.p, pos.p);
+  bytes = 0;
+  BT_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, pos.p, pos.p, nsrc, st));
+  tmp.reserve(bytes);
+  BT_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, bytes, pos.p, pos.p, nsrc, st));
+  int64_t nnz = 0;
+  BT_CUDA(cudaMemcpyAsync(&nnz, pos.p + (nsrc - 1), sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  BT_CUDA(cudaStreamSynchronize(st));
+  BT_REQUIRE(nnz < (int64_t)0x7fffffffLL, "nnz exceeds int32");
+  h->nnz = nnz;
+  h->d_rowidx.alloc(nnz);
+  h->d_colidx.alloc(nnz);
+  h->d_seg.alloc(nnz + 1);
+  k_scatter_unique<<<nblocks(nsrc), TPB, 0, st>>>(nsrc, keys_out.p, pos.p, h->d_rowidx.p, h->d_colidx.p,
+                                                  h->d_seg.p, nnz);
+  h->d_rowptr.alloc(h->ndof + 1);
+  k_rowptr<<<nblocks(h->ndof + 1), TPB, 0, st>>>(h->ndof, nnz, h->d_rowidx.p, h->d_rowptr.p);
+  h->d_diagpos.alloc(h->ndof);
+  k_diagpos<<<nblocks(h->ndof), TPB, 0, st>>>(h->ndof, h->d_rowptr.p, h->d_colidx.p, h->d_diagpos.p);
+  BT_CUDA(cudaGetLastError());
+  BT_CUDA(cudaStreamSynchronize(st));
+}
+
+void bt_assemble_values(btfem* h) {
+  cudaStream_t st = h->stream;
+  for (int k = 0; k < 8; ++k) h->d_vals[k].alloc(h->nnz);
+  h->d_D.upload(h->h_D.data(), h->h_D.size(), st);
+  h->d_invT2.upload(h->h_invT2.data(), h->h_invT2.size(), st);
+  AsmArgs a;
+  a.nnz = h->nnz;
+  a.ncell16 = (uint32_t)(16 * h->nc);
+  a.nif36 = (uint32_t)(36 * h->n_iface);
+  a.seg = h->d_seg.p;
+  a.src = h->d_src.p;
+  a.tets = h->d_tets.p;
+  a.xyz = h->d_xyz.p;
+  a.dkind = h->dkind;
+  a.D = h->d_D.p;
+  a.t2kind = h->t2kind;
+  a.invT2 = h->d_invT2.p;
+  a.if_verts = h->d_if_verts.p;
+  a.if_kappa = h->d_if_kappa.p;
+  a.bf_verts = h->d_bf_verts.p;
+  a.bmark = h->d_bmark.p;
+  a.M = h->d_vals[0].p; a.S = h->d_vals[1].p; a.R = h->d_vals[2].p; a.Jx = h->d_vals[3].p;
+  a.Jy = h->d_vals[4].p; a.Jz = h->d_vals[5].p; a.I = h->d_vals[6].p; a.B = h->d_vals[7].p;
+  k_assemble<<<nblocks(h->nnz), TPB, 0, st>>>(a);
+  h->d_lumped.alloc(h->ndof);
+  k_lumped<<<nblocks(h->ndof), TPB, 0, st>>>(h->ndof, h->d_rowptr.p, h->d_vals[0].p, h->d_lumped.p);
+  BT_CUDA(cudaGetLastError());
+  // initial condition on dofs + volumes (host reductions in a fixed order; ndof doubles, once)
+  std::vector<double> lumped(h->ndof);
+  h->d_lumped.download(lumped.data(), st);
+  std::vector<double> ic(h->ndof);
+  double vol = 0, voi = 0, vc[2] = {0, 0};
+  for (int64_t i = 0; i < h->ndof; ++i) {
+    double v = h->h_ic.empty() ? 1.0 : h->h_ic[h->h_dof_vertex[i]];
+    ic[i] = v;
+    vol += lumped[i];
+    voi += lumped[i] * v;
+    vc[h->h_dof_comp[i]] += lumped[i] * v;
+  }
+  h->whole_vol = vol;
+  h->voi = voi;
+  h->voi_comp[0] = vc[0];
+  h->voi_comp[1] = vc[1];
+  h->d_ic_dof.upload(ic.data(), ic.size(), st);
+  BT_CUDA(cudaStreamSynchronize(st));
+}
+
+void bt_build_periodic(btfem* h) {
+  // the gather operator of the weak pseudo-periodic BC is built in the Python host layer
+  // (geometry search, once per mesh) and handed over through btfem_set_periodic_gather
+  (void)h;
+}

@@ -1,0 +1,587 @@
+// The hot loop: fused complex SpMV + device-resident Jacobi-BiCGStab + theta stepping + signal.
+//
+// Reference behaviour being replaced (files under /root/reference):
+//   A = 1/k*M + assemble(F); b = assemble(L); linsolver.solve(A, u, b)     DmriFemLib.py:897-910
+//   comri pre-assembled form  A = MSI + f*g*J (dup / *= / +=)             comri/one-comp/hpc-fenics-cpp/main.cpp:296-328
+//   PETSc KSPSolve_BCGS + PCJACOBI + KSPConvergedDefault (third party, restated in oracle/bt_oracle.py)
+//
+// Design: the operator is never formed per step.  Two interleaved value arrays share the CSR pattern,
+//   PJ[k] = (P_k, Jg_k) / P_rr,   QJ[k] = (Q_k, Jg_k) / P_rr      (left Jacobi folded in, P_rr real)
+// and one kernel computes y = (V.x + i*c*V.y) x for either, c being a per-step scalar read from device
+// memory.  Every BiCGStab scalar lives in a device control block and every dot product is finished by the
+// last block of the kernel that produced its terms (fixed-order two-level reduction, no float atomics),
+// so one iteration is five kernels with constant arguments, replayed as a CUDA graph.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "btfem_internal.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr int NWARP = TPB / 32;
+
+enum { MODE_PLAIN = 0, MODE_RHS = 1, MODE_RESID = 2, MODE_V = 3, MODE_T = 4 };
+enum { TK_RHS = 0, TK_RESID = 1, TK_V = 2, TK_T = 3, TK_XR = 4, TK_SIG = 5 };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block partial -> partials[q][blockIdx.x]; the last block to arrive sums all partials in a fixed order.
+// Returns true in thread 0 of that last block with v[] = grand totals.
+template <int NV>
+__device__ bool reduce_finalize(double (&v)[NV], double* __restrict__ partials, unsigned int* ticket) {
+  __shared__ double sm[NV][NWARP];
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    double t = warp_sum(v[q]);
+    if (lane == 0) sm[q][warp] = t;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      double t = lane < NWARP ? sm[q][lane] : 0.0;
+      t = warp_sum(t);
+      if (lane == 0) partials[q * BT_MAX_PARTIALS + blockIdx.x] = t;
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  const volatile double* vp = partials;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    double acc = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += TPB) acc += vp[q * BT_MAX_PARTIALS + i];
+    double t = warp_sum(acc);
+    __syncthreads();
+    if (lane == 0) sm[q][warp] = t;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      double t = lane < NWARP ? sm[q][lane] : 0.0;
+      v[q] = warp_sum(t);
+    }
+  }
+  if (threadIdx.x == 0) *ticket = 0;
+  return threadIdx.x == 0;
+}
+
+// ------------------------------------------------------------------------------------ operator combination
+
+__global__ void k_pdiag(int n, const int32_t* __restrict__ diagpos, const double* __restrict__ M,
+                        const double* __restrict__ S, const double* __restrict__ R, const double* __restrict__ I,
+                        const double* __restrict__ B, double inv_dt, double theta, int pc, double* __restrict__ dinv) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int d = diagpos[r];
+  double p = M[d] * inv_dt + theta * (S[d] + R[d] + I[d] + B[d]);
+  dinv[r] = pc == BTFEM_PC_JACOBI ? 1.0 / p : 1.0;
+}
+
+__global__ void k_combine(int64_t nnz, const int32_t* __restrict__ rowidx, const double* __restrict__ M,
+                          const double* __restrict__ S, const double* __restrict__ R, const double* __restrict__ I,
+                          const double* __restrict__ B, const double* __restrict__ Jx, const double* __restrict__ Jy,
+                          const double* __restrict__ Jz, double inv_dt, double theta, double gx, double gy, double gz,
+                          const double* __restrict__ dinv, double2* __restrict__ PJ, double2* __restrict__ QJ,
+                          double* __restrict__ Bhat) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  double di = dinv[rowidx[k]];
+  double mk = M[k] * inv_dt;
+  double k0 = S[k] + R[k] + I[k];
+  double jg = (gx * Jx[k] + gy * Jy[k] + gz * Jz[k]) * di;
+  PJ[k] = make_double2((mk + theta * (k0 + B[k])) * di, jg);
+  QJ[k] = make_double2((mk - (1.0 - theta) * k0) * di, jg);
+  if (Bhat) Bhat[k] = B[k] * di;
+}
+
+// ------------------------------------------------------------------------------------ fused SpMV
+
+struct SpmvArgs {
+  int n;
+  const int32_t* rowptr;
+  const int32_t* colidx;
+  const double2* PJ;
+  const double2* QJ;
+  const double* cA;
+  const double* cb;
+  KrylovCtrl* ctrl;
+  double* partials;
+  // vectors
+  double2 *u, *r, *rp, *p, *v, *s, *t;
+  const double2* rhs_add;   // (1-theta) * Bhat * u_bc, or null
+  // MODE_PLAIN only
+  const double2* x_plain;
+  double2* y_plain;
+  double c_plain;
+};
+
+template <int LANES>
+__device__ __forceinline__ double2 row_product(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                               const double2* __restrict__ V, const double2* __restrict__ x, double c,
+                                               int row, bool valid, int lane) {
+  int s = 0, e = 0;
+  if (valid) {
+    s = __ldg(rowptr + row);
+    e = __ldg(rowptr + row + 1);
+  }
+  double ar = 0.0, ai = 0.0;
+#pragma unroll 2
+  for (int k = s + lane; k < e; k += LANES) {
+    const int col = __ldg(colidx + k);
+    const double2 pj = __ldg(V + k);
+    const double2 xv = __ldg(x + col);
+    const double a = pj.x, b = c * pj.y;   // (a + i b)(xr + i xi)
+    ar = fma(a, xv.x, ar);
+    ar = fma(-b, xv.y, ar);
+    ai = fma(a, xv.y, ai);
+    ai = fma(b, xv.x, ai);
+  }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) {
+    ar += __shfl_xor_sync(0xffffffffu, ar, o);
+    ai += __shfl_xor_sync(0xffffffffu, ai, o);
+  }
+  return make_double2(ar, ai);
+}
+
+template <int LANES, int MODE>
+__global__ void __launch_bounds__(TPB) k_spmv(SpmvArgs a) {
+  constexpr int RPB = TPB / LANES;
+  KrylovCtrl* ctrl = a.ctrl;
+  const double2* V;
+  const double2* x;
+  double c;
+  if (MODE == MODE_PLAIN) {
+    V = a.PJ; x = a.x_plain; c = a.c_plain;
+  } else if (MODE == MODE_RHS) {
+    V = a.QJ; x = a.u; c = ctrl->theta_cb_scale * a.cb[ctrl->step_next];
+  } else {
+    if (ctrl->done) return;
+    V = a.PJ; c = ctrl->theta_cA_scale * a.cA[ctrl->step];
+    x = (MODE == MODE_RESID) ? a.u : (MODE == MODE_V ? a.p : a.s);
+  }
+  const int lane = threadIdx.x % LANES;
+  const int grp = threadIdx.x / LANES;
+  double acc[2] = {0.0, 0.0};
+  const int ntiles = (a.n + RPB - 1) / RPB;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row = tile * RPB + grp;
+    const bool valid = row < a.n;
+    double2 y = row_product<LANES>(a.rowptr, a.colidx, V, x, c, row, valid, lane);
+    if (valid && lane == 0) {
+      if (MODE == MODE_PLAIN) {
+        a.y_plain[row] = y;
+      } else if (MODE == MODE_RHS) {
+        if (a.rhs_add) { double2 w = a.rhs_add[row]; y.x += w.x; y.y += w.y; }
+        if (ctrl->nonzero_guess) {
+          a.t[row] = y;                      // b^ kept for the residual kernel
+        } else {
+          a.r[row] = y; a.rp[row] = y;
+        }
+        a.p[row] = make_double2(0.0, 0.0);
+        a.v[row] = make_double2(0.0, 0.0);
+        acc[0] += y.x * y.x + y.y * y.y;
+      } else if (MODE == MODE_RESID) {
+        double2 b = a.t[row];
+        double2 rr = make_double2(b.x - y.x, b.y - y.y);
+        a.r[row] = rr; a.rp[row] = rr;
+        acc[0] += rr.x * rr.x + rr.y * rr.y;
+      } else if (MODE == MODE_V) {
+        a.v[row] = y;
+        double2 q = a.rp[row];
+        acc[0] += y.x * q.x + y.y * q.y;
+      } else {
+        a.t[row] = y;
+        double2 sv = a.s[row];
+        acc[0] += sv.x * y.x + sv.y * y.y;
+        acc[1] += y.x * y.x + y.y * y.y;
+      }
+    }
+  }
+  if (MODE == MODE_PLAIN) return;
+  if (MODE == MODE_RHS) {
+    double v1[1] = {acc[0]};
+    if (reduce_finalize<1>(v1, a.partials, &ctrl->ticket[TK_RHS])) {
+      double bn = sqrt(v1[0]);
+      ctrl->bnorm = bn;
+      ctrl->ttol = fmax(ctrl->rtol * bn, ctrl->atol);
+      ctrl->rho_old = 1.0; ctrl->alpha = 1.0; ctrl->omega = 1.0;
+      ctrl->iters = 0;
+      ctrl->step = ctrl->step_next;
+      ctrl->step_next = ctrl->step_next + 1;
+      ctrl->done = 0; ctrl->reason = 0;
+      if (!ctrl->nonzero_guess) {
+        ctrl->rho = v1[0];
+        ctrl->rnorm = bn;
+        if (!(bn == bn) || isinf(bn)) { ctrl->done = 1; ctrl->reason = BTFEM_ENAN; }
+        else if (bn <= ctrl->ttol) { ctrl->done = 1; ctrl->reason = bn < ctrl->atol ? 3 : 2; }
+      }
+    }
+  } else if (MODE == MODE_RESID) {
+    double v1[1] = {acc[0]};
+    if (reduce_finalize<1>(v1, a.partials, &ctrl->ticket[TK_RESID])) {
+      double rn = sqrt(v1[0]);
+      ctrl->rho = v1[0];
+      ctrl->rnorm = rn;
+      if (!(rn == rn) || isinf(rn)) { ctrl->done = 1; ctrl->reason = BTFEM_ENAN; }
+      else if (rn <= ctrl->ttol) { ctrl->done = 1; ctrl->reason = rn < ctrl->atol ? 3 : 2; }
+    }
+  } else if (MODE == MODE_V) {
+    double v1[1] = {acc[0]};
+    if (reduce_finalize<1>(v1, a.partials + 2 * BT_MAX_PARTIALS, &ctrl->ticket[TK_V])) {
+      if (v1[0] == 0.0) { ctrl->done = 1; ctrl->reason = BTFEM_EBREAKDOWN; ctrl->alpha = 0.0; }
+      else ctrl->alpha = ctrl->rho / v1[0];
+    }
+  } else {
+    double v2[2] = {acc[0], acc[1]};
+    if (reduce_finalize<2>(v2, a.partials + 3 * BT_MAX_PARTIALS, &ctrl->ticket[TK_T])) {
+      ctrl->omega = (v2[1] == 0.0) ? 0.0 : v2[0] / v2[1];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ vector kernels
+
+// p <- r - omega*beta*v + beta*p        (VecAXPBYPCZ in KSPSolve_BCGS)
+__global__ void __launch_bounds__(TPB) k_update_p(int n, KrylovCtrl* ctrl, const double2* __restrict__ r,
+                                                  const double2* __restrict__ v, double2* __restrict__ p) {
+  if (ctrl->done) return;
+  const double beta = (ctrl->rho / ctrl->rho_old) * (ctrl->alpha / ctrl->omega);
+  const double ob = ctrl->omega * beta;
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
+    double2 rr = r[i], vv = v[i], pp = p[i];
+    pp.x = rr.x - ob * vv.x + beta * pp.x;
+    pp.y = rr.y - ob * vv.y + beta * pp.y;
+    p[i] = pp;
+  }
+}
+
+// s <- r - alpha*v
+__global__ void __launch_bounds__(TPB) k_update_s(int n, KrylovCtrl* ctrl, const double2* __restrict__ r,
+                                                  const double2* __restrict__ v, double2* __restrict__ s) {
+  if (ctrl->done) return;
+  const double alpha = ctrl->alpha;
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
+    double2 rr = r[i], vv = v[i];
+    s[i] = make_double2(rr.x - alpha * vv.x, rr.y - alpha * vv.y);
+  }
+}
+
+// x <- x + alpha*p + omega*s ; r <- s - omega*t ; rho' = (r,rp) ; ||r|| ; convergence test
+__global__ void __launch_bounds__(TPB) k_update_xr(int n, KrylovCtrl* ctrl, double* partials, double2* __restrict__ x,
+                                                   const double2* __restrict__ p, const double2* __restrict__ s,
+                                                   const double2* __restrict__ t, const double2* __restrict__ rp,
+                                                   double2* __restrict__ r) {
+  if (ctrl->done) return;
+  const double alpha = ctrl->alpha, omega = ctrl->omega;
+  const bool fresh = (ctrl->iters == 0) && !ctrl->nonzero_guess;   // zero initial guess: x starts from 0
+  double acc[2] = {0.0, 0.0};
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
+    double2 pp = p[i], ss = s[i], tt = t[i], q = rp[i];
+    double2 xx = fresh ? make_double2(0.0, 0.0) : x[i];
+    xx.x += alpha * pp.x + omega * ss.x;
+    xx.y += alpha * pp.y + omega * ss.y;
+    x[i] = xx;
+    double2 rr = make_double2(ss.x - omega * tt.x, ss.y - omega * tt.y);
+    r[i] = rr;
+    acc[0] += rr.x * q.x + rr.y * q.y;
+    acc[1] += rr.x * rr.x + rr.y * rr.y;
+  }
+  if (reduce_finalize<2>(acc, partials + 5 * BT_MAX_PARTIALS, &ctrl->ticket[TK_XR])) {
+    const double rho_used = ctrl->rho;
+    ctrl->rho_old = rho_used;
+    ctrl->rho = acc[0];
+    const double dp = sqrt(acc[1]);
+    ctrl->rnorm = dp;
+    const int it = ctrl->iters + 1;
+    ctrl->iters = it;
+    if (!(dp == dp) || isinf(dp)) { ctrl->done = 1; ctrl->reason = BTFEM_ENAN; }
+    else if (dp <= ctrl->ttol) { ctrl->done = 1; ctrl->reason = dp < ctrl->atol ? 3 : 2; }
+    else if (dp >= ctrl->dtol * ctrl->bnorm) { ctrl->done = 1; ctrl->reason = BTFEM_EDTOL; }
+    else if (rho_used == 0.0 || omega == 0.0) { ctrl->done = 1; ctrl->reason = BTFEM_EBREAKDOWN; }
+    else if (it >= ctrl->maxit) { ctrl->done = 1; ctrl->reason = BTFEM_ENOTCONV; }
+  }
+}
+
+__global__ void k_set_ic(int n, const double* __restrict__ ic, double2* __restrict__ u) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) u[i] = make_double2(ic[i], 0.0);
+}
+
+// signal = sum_i lumped_i * Re u_i, split by compartment (DmriFemLib.py:926-931, 970-971)
+__global__ void __launch_bounds__(TPB) k_signal(int n, KrylovCtrl* ctrl, double* partials,
+                                                const double* __restrict__ lumped, const int32_t* __restrict__ comp,
+                                                const double2* __restrict__ u, double* __restrict__ out) {
+  double acc[2] = {0.0, 0.0};
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
+    double w = lumped[i] * u[i].x;
+    if (comp[i] == 0) acc[0] += w; else acc[1] += w;
+  }
+  if (reduce_finalize<2>(acc, partials + 6 * BT_MAX_PARTIALS, &ctrl->ticket[TK_SIG])) {
+    out[0] = acc[0];
+    out[1] = acc[1];
+  }
+}
+
+inline int vec_grid(int n) { return std::max(1, std::min((n + TPB - 1) / TPB, BT_NUM_SMS * 8)); }
+inline int spmv_grid(int n, int lanes) {
+  int rpb = TPB / lanes;
+  return std::max(1, std::min((n + rpb - 1) / rpb, BT_NUM_SMS * 16));
+}
+
+template <int MODE>
+void launch_spmv(int lanes, const SpmvArgs& a, cudaStream_t st) {
+  int g = spmv_grid(a.n, lanes);
+  switch (lanes) {
+    case 4: k_spmv<4, MODE><<<g, TPB, 0, st>>>(a); break;
+    case 8: k_spmv<8, MODE><<<g, TPB, 0, st>>>(a); break;
+    case 16: k_spmv<16, MODE><<<g, TPB, 0, st>>>(a); break;
+    case 32: k_spmv<32, MODE><<<g, TPB, 0, st>>>(a); break;
+    default: throw BtError{BTFEM_EINVAL, "lanes must be 4, 8, 16 or 32"};
+  }
+}
+
+SpmvArgs base_args(btfem* h) {
+  SpmvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = (int)h->ndof;
+  a.rowptr = h->d_rowptr.p;
+  a.colidx = h->d_colidx.p;
+  a.PJ = h->d_PJ.p;
+  a.QJ = h->d_QJ.p;
+  a.cA = h->d_cA.p;
+  a.cb = h->d_cb.p;
+  a.ctrl = h->d_ctrl.p;
+  a.partials = h->d_partials.p;
+  a.u = h->d_u.p; a.r = h->d_r.p; a.rp = h->d_rp.p; a.p = h->d_p.p; a.v = h->d_v.p; a.s = h->d_s.p; a.t = h->d_t.p;
+  return a;
+}
+
+void ensure_vectors(btfem* h) {
+  const size_t n = (size_t)h->ndof;
+  h->d_u.alloc(n); h->d_r.alloc(n); h->d_rp.alloc(n); h->d_p.alloc(n);
+  h->d_v.alloc(n); h->d_s.alloc(n); h->d_t.alloc(n);
+  h->d_partials.alloc(8 * BT_MAX_PARTIALS);
+  h->d_ctrl.alloc(1);
+  if (!h->h_ctrl) BT_CUDA(cudaMallocHost((void**)&h->h_ctrl, sizeof(KrylovCtrl)));
+}
+
+}  // namespace
+
+// ===================================================================================== host entry points
+
+void bt_combine(btfem* h, double dt, double theta, const double g[3], int pc) {
+  if (h->comb_dt == dt && h->comb_theta == theta && h->comb_pc == pc && h->comb_g[0] == g[0] &&
+      h->comb_g[1] == g[1] && h->comb_g[2] == g[2] && h->d_PJ.p)
+    return;
+  cudaStream_t st = h->stream;
+  const int n = (int)h->ndof;
+  h->d_PJ.alloc(h->nnz);
+  h->d_QJ.alloc(h->nnz);
+  h->d_dinv.alloc(n);
+  if (h->periodic) h->d_Bhat.alloc(h->nnz);
+  k_pdiag<<<(n + TPB - 1) / TPB, TPB, 0, st>>>(n, h->d_diagpos.p, h->d_vals[0].p, h->d_vals[1].p, h->d_vals[2].p,
+                                                h->d_vals[6].p, h->d_vals[7].p, 1.0 / dt, theta, pc, h->d_dinv.p);
+  k_combine<<<(int)((h->nnz + TPB - 1) / TPB), TPB, 0, st>>>(
+      h->nnz, h->d_rowidx.p, h->d_vals[0].p, h->d_vals[1].p, h->d_vals[2].p, h->d_vals[6].p, h->d_vals[7].p,
+      h->d_vals[3].p, h->d_vals[4].p, h->d_vals[5].p, 1.0 / dt, theta, g[0], g[1], g[2], h->d_dinv.p, h->d_PJ.p,
+      h->d_QJ.p, h->periodic ? h->d_Bhat.p : nullptr);
+  BT_CUDA(cudaGetLastError());
+  h->comb_dt = dt; h->comb_theta = theta; h->comb_pc = pc;
+  h->comb_g[0] = g[0]; h->comb_g[1] = g[1]; h->comb_g[2] = g[2];
+}
+
+void bt_spmv_host(btfem* h, double dt, double theta, double c, const double g[3], const double* x, double* y) {
+  cudaStream_t st = h->stream;
+  bt_combine(h, dt, theta, g, BTFEM_PC_NONE);
+  ensure_vectors(h);
+  DevArray<double2> dx, dy;
+  dx.upload(reinterpret_cast<const double2*>(x), h->ndof, st);
+  dy.alloc(h->ndof);
+  SpmvArgs a = base_args(h);
+  a.x_plain = dx.p;
+  a.y_plain = dy.p;
+  a.c_plain = theta * c;       // A = P + i*theta*c*Jg
+  launch_spmv<MODE_PLAIN>(h->lanes, a, st);
+  BT_CUDA(cudaGetLastError());
+  dy.download(reinterpret_cast<double2*>(y), st);
+}
+
+void bt_spmv_bench(btfem* h, double dt, double theta, double c, const double g[3], int lanes, int nrep, int flush_l2,
+                   double* ms) {
+  cudaStream_t st = h->stream;
+  bt_combine(h, dt, theta, g, BTFEM_PC_JACOBI);
+  ensure_vectors(h);
+  DevArray<double2> dx, dy;
+  dx.alloc(h->ndof);
+  dy.alloc(h->ndof);
+  k_set_ic<<<((int)h->ndof + TPB - 1) / TPB, TPB, 0, st>>>((int)h->ndof, h->d_ic_dof.p, dx.p);
+  DevArray<char> scratch;
+  const size_t flush_bytes = (size_t)512 << 20;
+  if (flush_l2) scratch.alloc(flush_bytes);
+  SpmvArgs a = base_args(h);
+  a.x_plain = dx.p;
+  a.y_plain = dy.p;
+  a.c_plain = theta * c;
+  cudaEvent_t e0, e1;
+  BT_CUDA(cudaEventCreate(&e0));
+  BT_CUDA(cudaEventCreate(&e1));
+  for (int w = 0; w < 3; ++w) launch_spmv<MODE_PLAIN>(lanes, a, st);
+  BT_CUDA(cudaStreamSynchronize(st));
+  double total = 0.0;
+  if (flush_l2) {
+    for (int i = 0; i < nrep; ++i) {
+      BT_CUDA(cudaMemsetAsync(scratch.p, i & 0xff, flush_bytes, st));
+      BT_CUDA(cudaEventRecord(e0, st));
+      launch_spmv<MODE_PLAIN>(lanes, a, st);
+      BT_CUDA(cudaEventRecord(e1, st));
+      BT_CUDA(cudaEventSynchronize(e1));
+      float t;
+      BT_CUDA(cudaEventElapsedTime(&t, e0, e1));
+      total += t;
+    }
+  } else {
+    BT_CUDA(cudaEventRecord(e0, st));
+    for (int i = 0; i < nrep; ++i) launch_spmv<MODE_PLAIN>(lanes, a, st);
+    BT_CUDA(cudaEventRecord(e1, st));
+    BT_CUDA(cudaEventSynchronize(e1));
+    float t;
+    BT_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    total = t;
+  }
+  BT_CUDA(cudaGetLastError());
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms = total / nrep;
+}
+
+void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_t* iters_per_step) {
+  BT_REQUIRE(sa->nsteps >= 0 && sa->dt > 0, "bad nsteps/dt");
+  BT_REQUIRE(sa->theta > 0 && sa->theta <= 1, "theta must be in (0,1]");
+  BT_REQUIRE(sa->ksp == BTFEM_KSP_BICGSTAB, "only BTFEM_KSP_BICGSTAB is implemented");
+  BT_REQUIRE(!h->periodic, "weak pseudo-periodic BC not implemented yet");
+  cudaStream_t st = h->stream;
+  const int n = (int)h->ndof;
+  cudaEvent_t e0, e1, e2;
+  BT_CUDA(cudaEventCreate(&e0));
+  BT_CUDA(cudaEventCreate(&e1));
+  BT_CUDA(cudaEventCreate(&e2));
+  BT_CUDA(cudaEventRecord(e0, st));
+  bt_combine(h, sa->dt, sa->theta, sa->gdir, (int)sa->pc);
+  ensure_vectors(h);
+  h->d_cA.upload(sa->cA, sa->nsteps, st);
+  h->d_cb.upload(sa->cb, sa->nsteps, st);
+  k_set_ic<<<(n + TPB - 1) / TPB, TPB, 0, st>>>(n, h->d_ic_dof.p, h->d_u.p);
+  KrylovCtrl c0;
+  memset(&c0, 0, sizeof(c0));
+  c0.rtol = sa->rtol; c0.atol = sa->atol; c0.dtol = 1e4;
+  c0.theta_cA_scale = sa->theta;
+  c0.theta_cb_scale = -(1.0 - sa->theta);
+  c0.maxit = (int)std::min<int64_t>(sa->maxit, 0x7fffffff);
+  c0.nonzero_guess = sa->nonzero_guess ? 1 : 0;
+  c0.done = 1;
+  *h->h_ctrl = c0;
+  BT_CUDA(cudaMemcpyAsync(h->d_ctrl.p, h->h_ctrl, sizeof(KrylovCtrl), cudaMemcpyHostToDevice, st));
+  BT_CUDA(cudaStreamSynchronize(st));   // h_ctrl is reused as the read-back buffer below
+
+  SpmvArgs a = base_args(h);
+  const int lanes = h->lanes;
+  const int vg = vec_grid(n);
+
+  // one BiCGStab iteration as a graph
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  BT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  k_update_p<<<vg, TPB, 0, st>>>(n, h->d_ctrl.p, h->d_r.p, h->d_v.p, h->d_p.p);
+  launch_spmv<MODE_V>(lanes, a, st);
+  k_update_s<<<vg, TPB, 0, st>>>(n, h->d_ctrl.p, h->d_r.p, h->d_v.p, h->d_s.p);
+  launch_spmv<MODE_T>(lanes, a, st);
+  k_update_xr<<<vg, TPB, 0, st>>>(n, h->d_ctrl.p, h->d_partials.p, h->d_u.p, h->d_p.p, h->d_s.p, h->d_t.p,
+                                  h->d_rp.p, h->d_r.p);
+  BT_CUDA(cudaStreamEndCapture(st, &graph));
+  BT_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+
+  BT_CUDA(cudaEventRecord(e1, st));
+  int64_t total_iters = 0, max_iters = 0, n_spmv = 0, n_kernels = 0;
+  int est = 4;
+  int last_reason = 0;
+  int fail = 0;
+  for (int64_t step = 0; step < sa->nsteps && !fail; ++step) {
+    launch_spmv<MODE_RHS>(lanes, a, st);
+    ++n_kernels;
+    if (sa->nonzero_guess) {
+      launch_spmv<MODE_RESID>(lanes, a, st);
+      ++n_kernels;
+    }
+    int launched = 0;
+    int chunk = std::max(1, est);
+    for (;;) {
+      for (int i = 0; i < chunk; ++i) BT_CUDA(cudaGraphLaunch(gexec, st));
+      launched += chunk;
+      BT_CUDA(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl.p, sizeof(KrylovCtrl), cudaMemcpyDeviceToHost, st));
+      BT_CUDA(cudaStreamSynchronize(st));
+      if (h->h_ctrl->done) break;
+      chunk = std::max(1, std::min(8, launched / 8));
+    }
+    n_kernels += 5 * (int64_t)launched;
+    const int it = h->h_ctrl->iters;
+    n_spmv += 1 + (sa->nonzero_guess ? 1 : 0) + 2 * (int64_t)it;
+    total_iters += it;
+    max_iters = std::max<int64_t>(max_iters, it);
+    if (iters_per_step) iters_per_step[step] = it;
+    est = it;
+    last_reason = h->h_ctrl->reason;
+    if (last_reason < 0) fail = last_reason;
+  }
+  BT_CUDA(cudaEventRecord(e2, st));
+  DevArray<double> d_sig;
+  d_sig.alloc(2);
+  k_signal<<<vg, TPB, 0, st>>>(n, h->d_ctrl.p, h->d_partials.p, h->d_lumped.p, h->d_dof_comp.p, h->d_u.p, d_sig.p);
+  BT_CUDA(cudaGetLastError());
+  double sig[2];
+  d_sig.download(sig, st);
+  float ms_setup = 0, ms_loop = 0;
+  BT_CUDA(cudaEventElapsedTime(&ms_setup, e0, e1));
+  BT_CUDA(cudaEventElapsedTime(&ms_loop, e1, e2));
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  cudaGraphExecDestroy(gexec);
+  cudaGraphDestroy(graph);
+  h->have_solution = true;
+  out->signal_comp[0] = sig[0];
+  out->signal_comp[1] = sig[1];
+  out->signal = sig[0] + sig[1];
+  out->voi = h->voi;
+  out->voi_comp[0] = h->voi_comp[0];
+  out->voi_comp[1] = h->voi_comp[1];
+  out->whole_vol = h->whole_vol;
+  out->loop_ms = ms_loop;
+  out->setup_ms = ms_setup;
+  out->total_iters = total_iters;
+  out->max_iters = max_iters;
+  out->n_spmv = n_spmv;
+  out->n_kernels = n_kernels + 1;
+  out->last_reason = last_reason;
+  if (fail) {
+    const char* what = fail == BTFEM_ENOTCONV ? "maximum iterations reached"
+                       : fail == BTFEM_EBREAKDOWN ? "BiCGStab breakdown"
+                       : fail == BTFEM_ENAN ? "non-finite residual"
+                                            : "residual diverged (dtol)";
+    throw BtError{fail, std::string("Krylov solver did not converge: ") + what};
+  }
+}

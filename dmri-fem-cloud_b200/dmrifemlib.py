@@ -1,0 +1,350 @@
+"""Host-side mirror of the reference's operator interface for the Bloch-Torrey path.
+
+Same class / function names, attributes, argument meaning and error behaviour as
+/root/reference/DmriFemLib.py for everything on the path:
+
+    MRI_parameters   DmriFemLib.py:800-858   (sequence, b <-> q <-> g; sympy like the reference)
+    MyDomain         DmriFemLib.py:583-637   (mesh sizes, kappa_e, D, kappa, phase, PeriodicDir)
+    MRI_simulation   DmriFemLib.py:860-915   (.k, .theta, .nskip, .solve(mydomain, mri_para, linsolver, ic))
+    PostProcessing   DmriFemLib.py:917-988   (signal line, log.txt; the .pvd/plot part is out of scope)
+    KrylovSolver     DOLFIN's class as used at GCloudDmriSolver.py:219-222 (parameters dict)
+    convert_g2q/q2g  DmriFemLib.py:680-686
+
+The arithmetic (assemble / KSP / signal) happens in libbtfem.so through btfem.BTFem;
+nothing here computes on the CPU beyond scalars and mesh bookkeeping.  DOLFIN objects are
+replaced by plain containers: `Mesh` holds numpy arrays, DG0 "functions" are (nc,) arrays.
+"""
+import sys
+import time
+
+import numpy as np
+import sympy as sp
+
+from . import btfem as _bt
+
+
+class Mesh:
+    """Stand-in for dolfin.Mesh: coordinates (nv,3) and cells (nc,4)."""
+
+    def __init__(self, xyz, tets):
+        self.xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        self.tets = np.ascontiguousarray(tets, dtype=np.int32)
+
+    def coordinates(self):
+        return self.xyz
+
+    def cells(self):
+        return self.tets
+
+    def num_vertices(self):
+        return len(self.xyz)
+
+    def num_cells(self):
+        return len(self.tets)
+
+    def _edge_lengths(self):
+        x = self.xyz[self.tets]
+        return np.stack([np.linalg.norm(x[:, i] - x[:, j], axis=1) for i in range(4) for j in range(i + 1, 4)], axis=1)
+
+    def hmin(self):
+        # DOLFIN >= 2017: Cell::h() = largest vertex-to-vertex distance (third party)
+        return float(self._edge_lengths().max(axis=1).min())
+
+    def hmax(self):
+        return float(self._edge_lengths().max(axis=1).max())
+
+
+class Point:
+    def __init__(self, x=0.0, y=0.0, z=0.0):
+        self.v = np.array([x, y, z], dtype=float)
+
+    def x(self):
+        return float(self.v[0])
+
+    def y(self):
+        return float(self.v[1])
+
+    def z(self):
+        return float(self.v[2])
+
+    def norm(self):
+        return float(np.linalg.norm(self.v))
+
+    def array(self):
+        return self.v.copy()
+
+
+def convert_g2q(gvalue):
+    g_ratio = 2.675e8
+    return gvalue * g_ratio * 1e-12
+
+
+def convert_q2g(qvalue):
+    g_ratio = 2.675e8
+    return qvalue / g_ratio * 1e12
+
+
+class MRI_parameters():
+    def __init__(self):
+        self.bvalue = None
+        self.gvalue = None
+        self.gdir = [1, 0, 0]
+        self.nperiod = 0
+        self.T2 = 1e16
+        self.s = sp.Symbol('s')
+
+    def set_gradient_dir(self, mymesh, g0, g1, g2):
+        self.gdir = Point(g0, g1, g2)
+        if abs(self.gdir.norm()) > 1e-10:
+            self.gdir.v /= self.gdir.norm()
+        else:
+            print("|g|=0! Please check again the gradient directions!")
+            sys.exit()
+        self.g = self.gdir.array()
+
+    def integral_term_for_gb(self):
+        self.int4gb = float(sp.integrate(self.ifs_sym * self.ifs_sym, (self.s, 0, self.T)))
+
+    def itime_profile_sym(self):
+        u = sp.Symbol('u')
+        self.ifs_sym = sp.integrate(self.fs_sym.subs(self.s, u), (u, 0, self.s))
+
+    def time_profile(self, t):
+        return (float(self.fs_sym.subs(self.s, t)))
+
+    def itime_profile(self, t):
+        return (float(self.ifs_sym.subs(self.s, t)))
+
+    def convert_b2q(self):
+        self.qvalue = np.sqrt(self.bvalue) / np.sqrt(self.int4gb)
+        return self.qvalue
+
+    def convert_q2b(self):
+        self.bvalue = self.qvalue * self.qvalue * self.int4gb
+        return self.bvalue
+
+    def Apply(self):
+        self.itime_profile_sym()
+        self.integral_term_for_gb()
+        if not (self.bvalue is None):
+            self.qvalue = self.convert_b2q()
+            self.gvalue = convert_q2g(self.qvalue)
+        elif not (self.gvalue is None):
+            self.qvalue = convert_g2q(self.gvalue)
+            self.bvalue = self.convert_q2b()
+        else:
+            print("bvalue or gvalue need to be specified.")
+            sys.exit()
+
+    # --- not in the reference: evaluate f and F on the whole time grid at once.  The reference
+    # calls sympy .subs four times per step (DmriFemLib.py:901-902); the values are the same.
+    def profiles_on_grid(self, ts):
+        try:
+            f = sp.lambdify(self.s, self.fs_sym, "math")
+            F = sp.lambdify(self.s, self.ifs_sym, "math")
+            fv = np.array([float(f(float(t))) for t in ts])
+            Fv = np.array([float(F(float(t))) for t in ts])
+            # spot-check the compiled profile against the symbolic one
+            for i in (0, len(ts) // 2, len(ts) - 1):
+                if len(ts) and abs(fv[i] - self.time_profile(ts[i])) > 1e-12 * max(1.0, abs(fv[i])):
+                    raise ValueError
+            return fv, Fv
+        except Exception:
+            return (np.array([self.time_profile(t) for t in ts]), np.array([self.itime_profile(t) for t in ts]))
+
+
+class KrylovSolver:
+    """dolfin.KrylovSolver(method, preconditioner) as a parameter holder; DOLFIN's defaults."""
+
+    def __init__(self, method="bicgstab", preconditioner="jacobi"):
+        if method not in ("bicgstab", "gmres"):
+            raise RuntimeError("Unknown Krylov method \"%s\"" % method)
+        if preconditioner in ("default",):
+            preconditioner = "jacobi" if method == "bicgstab" else "none"
+        if preconditioner not in ("jacobi", "none"):
+            raise RuntimeError("Unknown preconditioner \"%s\" (libbtfem implements jacobi and none)" % preconditioner)
+        self.method = method
+        self.preconditioner = preconditioner
+        self.parameters = {"relative_tolerance": 1e-6, "absolute_tolerance": 1e-15, "maximum_iterations": 10000,
+                           "nonzero_initial_guess": False, "error_on_nonconvergence": True, "restart": 30}
+
+
+class MyDomain():
+    def __init__(self, mymesh, mri_para):
+        self.porder = 1
+        self.hmin = mymesh.hmin()
+        self.hmax = mymesh.hmax()
+        self.tol = 1e-2 * self.hmin
+        self.gdim = 3
+        self.tdim = 3
+        xyz = mymesh.coordinates()
+        self.xmin, self.ymin, self.zmin = (float(v) for v in xyz.min(axis=0))
+        self.xmax, self.ymax, self.zmax = (float(v) for v in xyz.max(axis=0))
+        print("Domain size: xmin=%f, ymin=%f, zmin=%f, xmax=%f, ymax=%f, zmax=%f" % (
+            self.xmin, self.ymin, self.zmin, self.xmax, self.ymax, self.zmax))
+        self.mymesh = mymesh
+        self.gdir = mri_para.gdir
+        self.qvalue = mri_para.qvalue
+        self.kappa_e_scalar = 3e-3 / self.hmin
+        # defaults of GCloudDmriSolver.py:52-55
+        self.phase = None
+        self.PeriodicDir = [0, 0, 0]
+        self.IsDomainPeriodic = False
+        self.IsDomainMultiple = False
+        self.kappa = 1e-5
+        self.kappa_marker = None   # with a (nmark,nmark) kappa table: cell markers (variable permeability)
+        self.D = None
+        self.T2_cell = None        # optional DG0 T2 (GCloudDmriSolver.py:165-169)
+        self.device = 0
+        self._fem = None
+
+    def ImposeDiffusionTensor(self, k00, k01, k02, k10, k11, k12, k20, k21, k22):
+        print("Impose Diffusion Tensor ...")
+        nc = self.mymesh.num_cells()
+        rows = [[k00, k01, k02], [k10, k11, k12], [k20, k21, k22]]
+        D = np.empty((nc, 3, 3))
+        for i in range(3):
+            for j in range(3):
+                D[:, i, j] = np.broadcast_to(np.asarray(rows[i][j], dtype=float), (nc,))
+        self.D = D
+
+    def Apply(self):
+        if self.IsDomainPeriodic and sum(self.PeriodicDir) > 0:
+            raise NotImplementedError("strongly imposed pseudo-periodic BC (FuncF_sBC, DmriFemLib.py:148-238) "
+                                      "is outside the accelerated path; use the weak form (IsDomainPeriodic=False)")
+        if self.IsDomainMultiple:
+            print("Function Space for Two-compartment Domains has 4 components")
+            print("(ur0, ui0, ur1, ur1): r-real, i-imaginary")
+        else:
+            print("Function Space for Single Domains has 2 components")
+            print("(ur, ui): r-real, i-imaginary")
+        if sum(self.PeriodicDir) > 0:
+            print("The pseudo-periodic BCS are weakly imposed.")
+            print("The mesh does not need to be periodic.")
+
+    # --- GPU problem object, (re)built when coefficients change
+    def fem(self, mri_para, ic=None):
+        fem = _bt.BTFem(self.device)
+        phase = None
+        if self.IsDomainMultiple:
+            if self.phase is None:
+                raise RuntimeError("IsDomainMultiple requires mydomain.phase")
+            phase = np.asarray(self.phase).astype(np.int32)
+        fem.set_mesh(self.mymesh.xyz, self.mymesh.tets, phase)
+        D = self.D if self.D is not None else getattr(self, "D0", None)
+        if D is None:
+            raise RuntimeError("mydomain.D is not set")
+        fem.set_diffusion(D)
+        T2 = self.T2_cell if self.T2_cell is not None else mri_para.T2
+        fem.set_relaxation(1.0 / np.asarray(T2, dtype=float))
+        if self.IsDomainMultiple:
+            if np.isscalar(self.kappa):
+                fem.set_permeability(float(self.kappa))
+            else:
+                fem.set_permeability(np.asarray(self.kappa, dtype=float), self.kappa_marker)
+        if sum(self.PeriodicDir) > 0:
+            fem.set_periodic(self.PeriodicDir, self.kappa_e_scalar, self.tol,
+                             [self.xmin, self.ymin, self.zmin], [self.xmax, self.ymax, self.zmax])
+        fem.set_initial(ic)
+        fem.assemble()
+        self._fem = fem
+        return fem
+
+
+class MRI_simulation():
+    def __init__(self):
+        self.nskip = 5
+        self.theta = 0.5
+        self.verbose = True
+
+    def InitialCondition(self, mydomain, Dirac_Delta):
+        """Vertex values of the initial condition (DmriFemLib.py:865-876): given `ic`, else
+        1 where |x|^2 < 1e6."""
+        if Dirac_Delta is None:
+            xyz = mydomain.mymesh.coordinates()
+            Dirac_Delta = ((xyz * xyz).sum(axis=1) < 1e6).astype(float)
+        return np.asarray(Dirac_Delta, dtype=float)
+
+    def time_grid(self, mri_para):
+        ts = []
+        t = 0
+        while t < mri_para.T + self.k:      # DmriFemLib.py:897, t accumulated like the reference
+            ts.append(t)
+            t += self.k
+        return np.array(ts, dtype=float)
+
+    def solve(self, mydomain, mri_para, linsolver, ic=None):
+        self.Dirac_Delta = self.InitialCondition(mydomain, ic)
+        fem = mydomain.fem(mri_para, self.Dirac_Delta)
+        ts = self.time_grid(mri_para)
+        ft, ift = mri_para.profiles_on_grid(ts)
+        tps = np.concatenate([[0.0], ts[:-1]])          # tp lags t (DmriFemLib.py:886, 909)
+        ftp, iftp = mri_para.profiles_on_grid(tps)
+        q = mri_para.qvalue
+        par = linsolver.parameters
+        start_time = time.time()
+        if self.verbose:
+            for n in range(0, len(ts), self.nskip):
+                print('t: %6.2f ' % ts[n], 'T: %6.2f' % mri_para.T, 'dt: %.1f' % self.k, 'qvalue: %e' % q,
+                      'Completed %3.2f%%' % (float(ts[n]) / float(mri_para.T + self.k) * 100.0))
+        g = mri_para.gdir.array() if hasattr(mri_para.gdir, "array") else np.asarray(mri_para.gdir, dtype=float)
+        try:
+            self.stats = fem.solve(self.k, self.theta, q * ft, q * ftp, g, q=q, Fb=iftp,
+                                   ksp=linsolver.method, pc=linsolver.preconditioner,
+                                   rtol=par["relative_tolerance"], atol=par["absolute_tolerance"],
+                                   maxit=par["maximum_iterations"], nonzero_guess=par["nonzero_initial_guess"],
+                                   restart=par.get("restart", 30))
+        except _bt.BTFemError as e:
+            if e.code in (-3, -4, -5, -6) and not par.get("error_on_nonconvergence", True):
+                self.stats = None
+            else:
+                raise RuntimeError("*** Error: Unable to solve linear system using PETSc Krylov solver. "
+                                   "Reason: %s" % e)
+        self.t = float(ts[-1] + self.k) if len(ts) else 0.0
+        self.fem = fem
+        self.elapsed_time = time.time() - start_time
+        print("Successfully Completed! Elapsed time: %f seconds" % self.elapsed_time)
+
+    @property
+    def u_0(self):
+        """Solution in the reference's blocked layout (u0r,u0i[,u1r,u1i]) x N_vert, inactive dofs 0."""
+        fem = self.fem
+        u = fem.solution()
+        dv, dc = fem.dofmap()
+        ncomp = 2 if fem.two_comp else 1
+        out = np.zeros((2 * ncomp, fem.nv))
+        out[2 * dc, dv] = u.real
+        out[2 * dc + 1, dv] = u.imag
+        return out
+
+
+def PostProcessing(mydomain, mri_para, mri_simu, plt=None, ms=''):
+    st = mri_simu.stats
+    whole_vol, voi, signal = st["whole_vol"], st["voi"], st["signal"]
+    if mydomain.IsDomainMultiple == True:
+        initial0, initial1 = st["voi_comp"]
+        signal0, signal1 = st["signal_comp"]
+        if np.isscalar(mydomain.kappa) == True:
+            out_text = 'b: %.3f, g: %.3f, q: %.3e, Signal: %.3e, Normalized signal: %.6e, kappa: %.3e, dt: %.3f, hmin: %.3e, hmax: %.3e, whole_vol: %.3f, vol_of_interest: %.3f, elasped time %.3f (s)\n' % (
+                mri_para.bvalue, mri_para.gvalue, mri_para.qvalue, signal, signal / voi, mydomain.kappa, mri_simu.k,
+                mydomain.hmin, mydomain.hmax, whole_vol, voi, mri_simu.elapsed_time)
+        else:
+            out_text = 'b: %.3f, g: %.3f, q: %.3e, Signal: %.3e, Normalized signal: %.6e, dt: %.3f, hmin: %.3e, hmax: %.3e, whole_vol: %.3f, vol_of_interest: %.3f, elasped time %.3f (s)\n' % (
+                mri_para.bvalue, mri_para.gvalue, mri_para.qvalue, signal, signal / voi, mri_simu.k, mydomain.hmin,
+                mydomain.hmax, whole_vol, voi, mri_simu.elapsed_time)
+        print('Signal on each compartment')
+        print('Sum initial0: %.3e, Signal0: %.3e' % (initial0, signal0))
+        print('Sum initial1: %.3e, Signal1: %.3e' % (initial1, signal1))
+        print(out_text)
+    else:
+        out_text = 'b: %.3f, g: %.3f, q: %.3e, Signal: %.3e, Normalized signal: %.6e, dt: %.3f, hmin: %.3e, hmax: %.3e, whole_vol: %.3f, vol_of_interest: %.3f, elasped time %.3f (s)\n' % (
+            mri_para.bvalue, mri_para.gvalue, mri_para.qvalue, signal, signal / voi, mri_simu.k, mydomain.hmin,
+            mydomain.hmax, whole_vol, voi, mri_simu.elapsed_time)
+        print(out_text)
+    print("save to log.txt")
+    outfile = open('log.txt', 'a')
+    if not (ms == ''):
+        outfile.write('%' + ms + '\n')
+    outfile.write(out_text)
+    outfile.close()
+    return out_text

@@ -1,0 +1,156 @@
+/* btfem.h -- C-ABI of libbtfem.so, the B200 (sm_100a) Bloch-Torrey theta-scheme stepper.
+ *
+ * The reference (van-dang/DMRI-FEM-Cloud) has no FFI: its seam is the Python call
+ *   MRI_simulation.solve(mydomain, mri_para, linsolver)        DmriFemLib.py:878-915
+ *   PostProcessing(mydomain, mri_para, mri_simu, ...)          DmriFemLib.py:917-988
+ * underneath which DOLFIN `assemble` and PETSc `KSPSolve` do all arithmetic.  This header
+ * is what a ctypes stub in DmriFemLib.py would bind to replace that arithmetic; each entry
+ * point cites the reference lines it stands for.  See INTEGRATION.md for the stub.
+ *
+ * Conventions: plain pointers and sizes only; every array is caller-owned, contiguous,
+ * host memory, copied inside the call.  The handle is library-owned, bound to ONE GPU and
+ * not thread-safe.  Every function returns 0 on success or a negative BTFEM_E* code;
+ * btfem_last_error() then describes it.  No exception crosses the boundary.  There is no
+ * CPU fallback: without a usable CUDA device btfem_create fails.
+ *
+ * Unknown numbering: one complex number per ACTIVE (vertex, compartment) pair, numbered
+ * vertex-major ("dofs").  One compartment: dof == vertex.  Complex vectors are interleaved
+ * (re, im) doubles.  All matrices are real, fp64, and share one CSR pattern with sorted
+ * int32 columns.
+ */
+#ifndef BTFEM_H
+#define BTFEM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct btfem btfem_t;
+
+enum {
+  BTFEM_OK = 0,
+  BTFEM_EINVAL = -1,     /* bad argument / call order */
+  BTFEM_ECUDA = -2,      /* CUDA runtime error */
+  BTFEM_ENOTCONV = -3,   /* Krylov: maximum iterations reached (KSP_DIVERGED_ITS) */
+  BTFEM_EBREAKDOWN = -4, /* Krylov: rho == 0 or (v,r^) == 0 (KSP_DIVERGED_BREAKDOWN) */
+  BTFEM_ENAN = -5,       /* Krylov: non-finite residual (KSP_DIVERGED_NANORINF) */
+  BTFEM_EDTOL = -6,      /* Krylov: residual grew by dtol (KSP_DIVERGED_DTOL) */
+  BTFEM_ENOMEM = -7
+};
+
+/* which matrix btfem_get_values returns */
+enum { BTFEM_MAT_M = 0, BTFEM_MAT_S = 1, BTFEM_MAT_R = 2, BTFEM_MAT_JX = 3, BTFEM_MAT_JY = 4,
+       BTFEM_MAT_JZ = 5, BTFEM_MAT_I = 6, BTFEM_MAT_B = 7 };
+
+enum { BTFEM_KSP_BICGSTAB = 0, BTFEM_KSP_GMRES = 1 };
+enum { BTFEM_PC_JACOBI = 0, BTFEM_PC_NONE = 1 };
+
+/* ---- lifetime ----------------------------------------------------------------------- */
+int btfem_create(int device, btfem_t** out);
+void btfem_destroy(btfem_t* h);
+const char* btfem_last_error(btfem_t* h);   /* valid until the next call on h */
+int btfem_version(void);
+
+/* ---- problem definition ---------------------------------------------------------------
+ * Mesh + phase function: replaces Mesh/HDF5File.read + `phase` DG0 function
+ * (GCloudDmriSolver.py:150-177; phase = marker % 2, DmriFemLib.py:764).
+ * phase == NULL: one compartment (-M 0).  Otherwise phase[c] in {0,1} (-M 1). */
+int btfem_set_mesh(btfem_t* h, int64_t nv, const double* xyz /*[nv*3]*/, int64_t nc,
+                   const int32_t* tets /*[nc*4]*/, const int32_t* phase /*[nc] or NULL*/);
+
+/* Diffusion: kind 0 = scalar D0 (`-K`, GCloudDmriSolver.py:212-215), 1 = per-cell scalar [nc],
+ * 2 = per-cell full tensor [nc*9] row-major d00..d22 (ImposeDiffusionTensor, DmriFemLib.py:611-616). */
+int btfem_set_diffusion(btfem_t* h, int kind, const double* D);
+/* 1/T2: kind 0 = scalar, 1 = per-cell [nc] (DG0 `T2` function; FuncF_wBC, DmriFemLib.py:43-44). */
+int btfem_set_relaxation(btfem_t* h, int kind, const double* inv_t2);
+/* Membrane permeability kappa (`-p`; icondition_wBC, DmriFemLib.py:47-50): kind 0 = scalar,
+ * 1 = table by cell-marker pair: kappa[(min(ma,mb))*nmark + max(ma,mb)], markers from
+ * `marker` [nc] (variable permeability, MultilayeredDiskVariablePermeability.ipynb cell 10). */
+int btfem_set_permeability(btfem_t* h, int kind, const double* kappa, int32_t nmark,
+                           const int32_t* marker /*[nc] or NULL*/);
+/* Weak pseudo-periodic BC (`-pdir`; DmriFemLib.py:58-77,79-93,256-324,599-610).
+ * kappa_e: artificial permeability (reference: 3e-3/hmin); tol: face tolerance (1e-2*hmin);
+ * bbox lo/hi as printed by MyDomain (DmriFemLib.py:593). */
+int btfem_set_periodic(btfem_t* h, const int32_t pdir[3], double kappa_e, double tol,
+                       const double lo[3], const double hi[3]);
+/* Initial condition per vertex (Dirac_Delta interpolant, DmriFemLib.py:865-876); NULL = 1. */
+int btfem_set_initial(btfem_t* h, const double* ic /*[nv] or NULL*/);
+
+/* ---- assembly (once) -------------------------------------------------------------------
+ * Replaces assemble(F), assemble(L), MassMatrix (DmriFemLib.py:240-254, 904-905) and the
+ * comri pre-assembly of M, S, J[, I] (comri/one-comp/hpc-fenics-cpp/main.cpp:263-281):
+ * builds the dof map, the CSR pattern (GPU sort/unique) and M,S,R,Jx,Jy,Jz,I,B. */
+int btfem_assemble(btfem_t* h);
+
+/* sizes after assemble: ndof, nnz, number of interface facets, number of boundary facets in B */
+int btfem_get_sizes(btfem_t* h, int64_t* ndof, int64_t* nnz, int64_t* n_iface, int64_t* n_bfacet);
+/* parity hooks */
+int btfem_get_pattern(btfem_t* h, int32_t* rowptr /*[ndof+1]*/, int32_t* colidx /*[nnz]*/);
+int btfem_get_dofmap(btfem_t* h, int32_t* dof_vertex /*[ndof]*/, int32_t* dof_comp /*[ndof]*/);
+int btfem_get_values(btfem_t* h, int which, double* out /*[nnz]*/);
+int btfem_get_lumped_mass(btfem_t* h, double* out /*[ndof]*/);   /* 1^T M: signal weights */
+
+/* y = (P + i*c*Jg) x on host vectors, P = M/dt + theta*(S+R+I+B), Jg = g.J (g as given).
+ * The product of `A = 1/k*M + assemble(F)` with a vector (DmriFemLib.py:904). */
+int btfem_spmv(btfem_t* h, double dt, double theta, double c, const double gdir[3],
+               const double* x /*[2*ndof]*/, double* y /*[2*ndof]*/);
+/* Time `nrep` launches of the fused SpMV kernel on device-resident data (bench hook).
+ * lanes: threads per row (4, 8, 16 or 32).  flush_l2 != 0: a 512 MiB memset precedes every launch and
+ * each launch is timed on its own; otherwise the nrep launches are timed back to back.
+ * Returns average ms per launch. */
+int btfem_spmv_bench(btfem_t* h, double dt, double theta, double c, const double gdir[3],
+                     int32_t lanes, int32_t nrep, int32_t flush_l2, double* ms_per_launch);
+/* threads per row used by the solver's fused SpMV (default 8) */
+int btfem_set_lanes(btfem_t* h, int32_t lanes);
+
+/* ---- the theta loop ---------------------------------------------------------------------
+ * MRI_simulation.solve (DmriFemLib.py:878-915): for n in 0..nsteps-1
+ *   (P + i*theta*cA[n]*Jg) u^{n+1} = (Q - i*(1-theta)*cb[n]*Jg) u^n + (1-theta)*B*u_bc(u^n, Fb[n])
+ * with cA[n] = q*f(t_n), cb[n] = q*f(t_{n-1}) (lagged, DmriFemLib.py:901-902,909), solved by
+ * KrylovSolver("bicgstab","jacobi") semantics (GCloudDmriSolver.py:219-222; PETSc KSPBCGS,
+ * left PCJACOBI, preconditioned-residual test max(rtol*||K^-1 b||, atol)).
+ * All fields are 8 bytes wide so that the struct has no padding. */
+typedef struct {
+  int64_t nsteps;
+  double dt;
+  double theta;
+  const double* cA;   /* [nsteps] */
+  const double* cb;   /* [nsteps] */
+  const double* Fb;   /* [nsteps] or NULL (only read with periodic BC) */
+  double gdir[3];     /* unit gradient direction (set_gradient_dir normalises, DmriFemLib.py:819-821) */
+  double q;           /* q-value, enters the periodic phase only */
+  int64_t ksp;        /* BTFEM_KSP_* */
+  int64_t pc;         /* BTFEM_PC_*  */
+  double rtol;
+  double atol;
+  int64_t maxit;
+  int64_t nonzero_guess;   /* parameters["krylov_solver"]["nonzero_initial_guess"] */
+  int64_t restart;         /* GMRES restart (PETSc default 30) */
+} btfem_solve_args;
+
+typedef struct {
+  double signal;          /* assemble(ur*dx) | assemble((phase*u1r+(1-phase)*u0r)*dx), DmriFemLib.py:931,971 */
+  double signal_comp[2];  /* signal0, signal1 (DmriFemLib.py:928,930) */
+  double voi;             /* assemble(Dirac_Delta*dx), DmriFemLib.py:924 */
+  double voi_comp[2];     /* initial0, initial1 (DmriFemLib.py:927,929) */
+  double whole_vol;       /* assemble(1*dx), DmriFemLib.py:923 */
+  double loop_ms;         /* device time of the time loop (CUDA events) */
+  double setup_ms;        /* device time of the per-solve operator combination */
+  int64_t total_iters;    /* Krylov iterations summed over steps */
+  int64_t max_iters;      /* largest per-step count */
+  int64_t n_spmv;         /* fused-SpMV launches that did work */
+  int64_t n_kernels;      /* all kernel launches inside the loop */
+  int64_t last_reason;    /* >0 converged (2 = rtol, 3 = atol) */
+} btfem_solve_out;
+
+int btfem_solve(btfem_t* h, const btfem_solve_args* args, btfem_solve_out* out,
+                int32_t* iters_per_step /*[nsteps] or NULL*/);
+/* solution after the last solve, dof numbering, interleaved (re,im) */
+int btfem_get_solution(btfem_t* h, double* u /*[2*ndof]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BTFEM_H */

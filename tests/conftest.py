@@ -1,0 +1,33 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import __graft_entry__ as entry  # noqa: E402
+
+entry.load_package()
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    return entry.load_package()
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """libbtfem.so, built if missing (nvcc cross-compiles without a GPU)."""
+    entry.build_library()
+    from dmri_fem_cloud_b200 import btfem
+    return btfem.load_library()
+
+
+REF_MESH_DIR = "/root/reference/comri/meshes"
+GOLDEN = os.path.join(ROOT, "tests", "golden")

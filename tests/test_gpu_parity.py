@@ -1,0 +1,198 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the oracle on the same
+seeded inputs.  Integer pattern bit-exact; matrix values <= 1e-12 relative (north star);
+SpMV <= 1e-13; final signals <= 1e-8 relative (north star) -- tolerances written at each assert."""
+import os
+
+import numpy as np
+import pytest
+
+import bt_oracle as orc
+from conftest import GOLDEN
+from dmri_fem_cloud_b200 import btfem, meshes
+
+pytestmark = pytest.mark.gpu
+
+
+def _relmax(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def _cases():
+    rng = np.random.default_rng(7)
+    xyz, tets = meshes.box_mesh((-2.5,) * 3, (2.5,) * 3, 5, 4, 3)
+    xyz = xyz + 0.05 * rng.standard_normal(xyz.shape)          # break the symmetry
+    yield "box_1c", xyz, tets, None, dict(D=2e-3)
+    xyz2, tets2 = meshes.cylinder(3.0, 10.0, nr=3, nsec=10, nz=6)
+    xyz2, tets2 = meshes.shuffle_vertices(xyz2, tets2, seed=1)
+    yield "cyl_1c_tensorD_T2", xyz2, tets2, None, dict(
+        D=np.broadcast_to(np.array([[3e-3, 1e-4, 0], [1e-4, 2e-3, 0], [0, 0, 1e-3]]), (len(tets2), 3, 3)).copy(),
+        invT2=rng.uniform(1e-5, 1e-4, len(tets2)))
+    xyz3, tets3, marker = meshes.layered_cylinder((5.0, 7.5, 10.0), 5.0, (3, 2, 2), 12, 2)
+    yield "layered_2c", xyz3, tets3, (marker % 2).astype(np.int32), dict(
+        D=np.array([3e-3, 1e-3, 3e-3])[marker], kappa=1e-5)
+    xyz4, tets4, ph4 = meshes.box_with_sphere(10.0, 6, 5.0)
+    yield "sphere_in_box_2c", xyz4, tets4, ph4, dict(D=3e-3, kappa=5e-5, invT2=1.0 / 4e4)
+
+
+CASES = list(_cases())
+
+
+def _setup(fem, xyz, tets, phase, co):
+    fem.set_mesh(xyz, tets, phase)
+    fem.set_diffusion(co.get("D", 1.0))
+    fem.set_relaxation(co.get("invT2", 0.0))
+    if phase is not None:
+        fem.set_permeability(co.get("kappa", 0.0))
+    fem.assemble()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_pattern_and_values(case):
+    _, xyz, tets, phase, co = case
+    ops = orc.assemble(xyz, tets, phase, D=co.get("D", 1.0), invT2=co.get("invT2", 0.0), kappa=co.get("kappa", 0.0))
+    with btfem.BTFem(0) as fem:
+        _setup(fem, xyz, tets, phase, co)
+        assert fem.ndof == ops.ndof and fem.nnz == ops.nnz
+        rp, ci = fem.pattern()
+        assert np.array_equal(rp, ops.rowptr)            # bit-exact
+        assert np.array_equal(ci, ops.colidx)            # bit-exact
+        dv, dc = fem.dofmap()
+        assert np.array_equal(dv, ops.dof_vertex) and np.array_equal(dc, ops.dof_comp)
+        if phase is None:                                 # one compartment: the reference's scalar P1 pattern
+            rps, cis = orc.scalar_pattern(len(xyz), tets)
+            assert np.array_equal(rp, rps) and np.array_equal(ci, cis)
+        for name in ("M", "S", "R", "Jx", "Jy", "Jz", "I"):
+            got, want = fem.values(name), getattr(ops, name).data
+            if np.max(np.abs(want)) == 0:
+                assert np.max(np.abs(got)) == 0, name
+            else:
+                assert _relmax(got, want) <= 1e-12, (name, _relmax(got, want))
+        assert _relmax(fem.lumped_mass(), ops.lumped) <= 1e-13
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_fused_spmv(case):
+    _, xyz, tets, phase, co = case
+    ops = orc.assemble(xyz, tets, phase, D=co.get("D", 1.0), invT2=co.get("invT2", 0.0), kappa=co.get("kappa", 0.0))
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(ops.ndof) + 1j * rng.standard_normal(ops.ndof)
+    g = np.array([0.3, -0.5, 0.8])
+    g /= np.linalg.norm(g)
+    dt, theta, c = 200.0, 0.5, 1.5e-5
+    P = ops.M / dt + theta * (ops.S + ops.R + ops.I + ops.B)
+    Jg = g[0] * ops.Jx + g[1] * ops.Jy + g[2] * ops.Jz
+    want = P @ x + 1j * theta * c * (Jg @ x)
+    with btfem.BTFem(0) as fem:
+        _setup(fem, xyz, tets, phase, co)
+        for lanes in (4, 8, 16, 32):
+            fem.set_lanes(lanes)
+            got = fem.spmv(dt, theta, c, g, x)
+            assert _relmax(got, want) <= 1e-13, (lanes, _relmax(got, want))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_theta_loop_signal(case):
+    """Whole path: GPU Jacobi-BiCGStab at tight tolerance vs the oracle's exact (LU) time stepping."""
+    _, xyz, tets, phase, co = case
+    ops = orc.assemble(xyz, tets, phase, D=co.get("D", 1.0), invT2=co.get("invT2", 0.0), kappa=co.get("kappa", 0.0))
+    seq = orc.pgse(2000.0, 6000.0)
+    q = seq.q_from_b(1000.0)
+    k = 200.0
+    g = np.array([0.0, 1.0, 0.0])
+    ref = orc.theta_solve(ops, seq, q, g, k, solver="lu")
+    ts = orc.time_grid(seq.T, k)
+    f = np.array([seq.f(t) for t in ts])
+    fp = np.concatenate([[f[0]], f[:-1]])
+    with btfem.BTFem(0) as fem:
+        _setup(fem, xyz, tets, phase, co)
+        res = fem.solve(k, 0.5, q * f, q * fp, g, rtol=1e-13, atol=1e-16, want_iters=True)
+        u = fem.solution()
+    assert res["n_steps"] == ref["n_steps"]
+    assert abs(res["voi"] - ref["voi"]) <= 1e-12 * abs(ref["voi"])
+    assert abs(res["signal"] - ref["signal"]) <= 1e-8 * abs(ref["signal"])      # north-star tolerance
+    assert _relmax(u, ref["u"]) <= 1e-8
+    assert res["total_iters"] > 0 and res["last_reason"] > 0
+
+
+def test_bicgstab_matches_petsc_restatement():
+    """Same Krylov: iteration counts of the GPU solver equal the oracle's PETSc-BCGS restatement
+    at the CLI tolerances (GCloudDmriSolver.py:219-222), and the signals agree to 1e-8."""
+    _, xyz, tets, phase, co = CASES[0]
+    ops = orc.assemble(xyz, tets, phase, D=co["D"])
+    seq = orc.pgse(2000.0, 6000.0)
+    q = seq.q_from_b(1000.0)
+    k = 200.0
+    g = np.array([1.0, 0.0, 0.0])
+    ref = orc.theta_solve(ops, seq, q, g, k, solver="bicgstab", rtol=1e-9, atol=1e-10)
+    ts = orc.time_grid(seq.T, k)
+    f = np.array([seq.f(t) for t in ts])
+    fp = np.concatenate([[f[0]], f[:-1]])
+    with btfem.BTFem(0) as fem:
+        _setup(fem, xyz, tets, phase, co)
+        res = fem.solve(k, 0.5, q * f, q * fp, g, rtol=1e-9, atol=1e-10, want_iters=True)
+    assert abs(res["signal"] - ref["signal"]) <= 1e-8 * abs(ref["signal"])
+    # identical recurrence; rounding may shift an iteration here and there
+    assert np.max(np.abs(res["iters"].astype(int) - ref["iters"].astype(int))) <= 1
+    assert np.mean(res["iters"] == ref["iters"]) > 0.8
+
+
+def test_golden_convergence_box():
+    """Reference-recorded output: ConvergenceTest.ipynb cell 10, BoxMesh n=16 -> 8.440078e-01
+    (loop `t < T`, 1100 steps, dt=10, D=2e-3, delta=1000, Delta=10000, g=z, b=1000)."""
+    xyz, tets = meshes.box_mesh((-2.5,) * 3, (2.5,) * 3, 16, 16, 16)
+    seq = orc.pgse(1000.0, 10000.0)
+    q = seq.q_from_b(1000.0)
+    k = 10.0
+    ts = orc.time_grid(seq.T, k, closed=False)
+    assert len(ts) == 1100
+    f = np.array([seq.f(t) for t in ts])
+    fp = np.concatenate([[f[0]], f[:-1]])
+    with btfem.BTFem(0) as fem:
+        fem.set_mesh(xyz, tets)
+        fem.set_diffusion(2e-3)
+        fem.assemble()
+        res = fem.solve(k, 0.5, q * f, q * fp, [0, 0, 1.0], rtol=1e-12, atol=1e-15)
+    s = res["signal"] / res["voi"]
+    assert "%.6e" % s == "8.440078e-01"
+    gold = np.load(os.path.join(GOLDEN, "convergence_box_n16.npz"))
+    assert abs(s - float(gold["normalized_signal_lu"])) <= 1e-8 * s
+
+
+def test_errors_are_reported():
+    with btfem.BTFem(0) as fem:
+        with pytest.raises(btfem.BTFemError):
+            fem.assemble()                                   # no mesh yet
+        xyz, tets = meshes.box_mesh((0,) * 3, (1,) * 3, 2, 2, 2)
+        bad = tets.copy()
+        bad[0, 0] = 10 ** 6
+        with pytest.raises(btfem.BTFemError):
+            fem.set_mesh(xyz, bad)
+        fem.set_mesh(xyz, tets)
+        fem.set_diffusion(1e-3)
+        fem.assemble()
+        with pytest.raises(btfem.BTFemError) as ei:
+            fem.solve(1.0, 0.5, np.ones(5) * 1e-3, np.ones(5) * 1e-3, [1, 0, 0], rtol=1e-30, atol=0.0, maxit=3)
+        assert ei.value.code == -3                           # KSP_DIVERGED_ITS
+
+
+def test_full_size_properties():
+    """At bench size the oracle is too slow; use size-independent properties: q=0 reduces the
+    path to pure diffusion with Neumann BC, which conserves total magnetisation (signal == voi),
+    and the SpMV is linear."""
+    xyz, tets = meshes.box_mesh((-5,) * 3, (5,) * 3, 40, 40, 40)
+    with btfem.BTFem(0) as fem:
+        fem.set_mesh(xyz, tets)
+        fem.set_diffusion(3e-3)
+        fem.assemble()
+        n = 50
+        res = fem.solve(200.0, 0.5, np.zeros(n), np.zeros(n), [1, 0, 0], rtol=1e-12, atol=1e-15)
+        assert abs(res["signal"] - res["voi"]) <= 1e-9 * res["voi"]
+        assert abs(res["whole_vol"] - 1000.0) <= 1e-9 * 1000.0
+        rng = np.random.default_rng(0)
+        x = rng.standard_normal(fem.ndof) + 1j * rng.standard_normal(fem.ndof)
+        y = rng.standard_normal(fem.ndof) + 1j * rng.standard_normal(fem.ndof)
+        g = [0, 0, 1.0]
+        a = fem.spmv(200.0, 0.5, 2e-5, g, x)
+        b = fem.spmv(200.0, 0.5, 2e-5, g, y)
+        ab = fem.spmv(200.0, 0.5, 2e-5, g, 2.0 * x - 3.0 * y)
+        assert _relmax(ab, 2.0 * a - 3.0 * b) <= 1e-13
