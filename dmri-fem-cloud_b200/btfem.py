@@ -139,11 +139,11 @@ class BTFem:
         self.h2d_bytes = xyz.nbytes + tets.nbytes + (0 if ph is None else ph.nbytes)
 
     def set_diffusion(self, D):
-        D = np.ascontiguousarray(D, dtype=np.float64)
+        D = np.asarray(D, dtype=np.float64)
         if D.ndim == 0:
-            kind, D = 0, D.reshape(1)
+            kind, D = 0, D.reshape(1).copy()
         elif D.ndim == 1:
-            kind = 1
+            kind, D = 1, np.ascontiguousarray(D)
             assert len(D) == self.nc
         else:
             D = np.ascontiguousarray(np.broadcast_to(D, (self.nc, 3, 3)))
@@ -151,16 +151,18 @@ class BTFem:
         self._ck(self.lib.btfem_set_diffusion(self.h, kind, _dp(D)))
 
     def set_relaxation(self, inv_t2):
-        a = np.ascontiguousarray(inv_t2, dtype=np.float64)
+        a = np.asarray(inv_t2, dtype=np.float64)
         kind = 0 if a.ndim == 0 else 1
-        a = a.reshape(1) if kind == 0 else a
+        a = a.reshape(1).copy() if kind == 0 else np.ascontiguousarray(a)
         self._ck(self.lib.btfem_set_relaxation(self.h, kind, _dp(a)))
 
     def set_permeability(self, kappa, marker=None):
-        k = np.ascontiguousarray(kappa, dtype=np.float64)
+        k = np.asarray(kappa, dtype=np.float64)
         if k.ndim == 0:
-            self._ck(self.lib.btfem_set_permeability(self.h, 0, _dp(k.reshape(1)), 0, None))
+            k = k.reshape(1).copy()
+            self._ck(self.lib.btfem_set_permeability(self.h, 0, _dp(k), 0, None))
         else:
+            k = np.ascontiguousarray(k)
             m = np.ascontiguousarray(marker, dtype=np.int32)
             assert k.ndim == 2 and k.shape[0] == k.shape[1]
             self._ck(self.lib.btfem_set_permeability(self.h, 1, _dp(k), k.shape[0], _ip(m)))
