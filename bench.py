@@ -1,0 +1,340 @@
+#!/usr/bin/env python3
+"""Benchmark of the Bloch-Torrey theta-scheme path (BASELINE.json metric: DOF-steps/s).
+
+Workload (config.workload): BASELINE.json configs[1], the two-compartment permeable PGSE solve
+`-M 1 -b 1000 -p 1e-5 -k 200 -gdir 0 1 0` (delta/Delta = 10600/43100 -> 270 theta steps,
+D = 3e-3, BiCGStab+Jacobi rtol 1e-9 atol 1e-10, GCloudDmriSolver.py:52-55,219-222) on the
+synthetic cell-in-box mesh (sphere R=5 in a [-10,10]^3 Kuhn box) sized to ~1 M real DOFs.
+
+One bench "step" = one complete solve (IC -> 270 theta steps -> signal).  DOFs = 2 x active
+complex unknowns (the reference would count W.dim() = 4 x N_vert = 2x more for two compartments).
+
+  value    throughput of btfem_solve with mesh + operators resident in HBM (wall clock around
+           K solves, each ending in a stream sync; device event time reported beside it)
+  e2e      same metric through the reference-facing API (MyDomain / MRI_simulation.solve /
+           PostProcessing) from HOST numpy buffers: mesh upload, dof map, pattern, assembly,
+           solve, signal read-back all inside the timed region
+  roofline fused complex SpMV kernel: algorithmic bytes 20*nnz + 36*n per launch over the
+           CUDA-event time of one launch with L2 flushed before it
+  cpu_baseline  the oracle's C/OpenMP restatement on a bounded sample of the same workload
+
+N > 1 (torchrun): independent gradient directions shard one per rank, no data-path collective
+(weak scaling); torch.distributed is used for the barrier and the max-over-ranks only.
+`--impl reference` times the CPU restatement (the reference itself cannot run here: no
+DOLFIN/PETSc/MPI in the image).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+METRIC = "Bloch-Torrey DOF-steps/s"
+UNIT = "DOF-steps/s"
+
+
+def workload(n_box):
+    entry.load_package()
+    from dmri_fem_cloud_b200 import meshes
+    xyz, tets, phase = meshes.box_with_sphere(10.0, n_box, 5.0)
+    return xyz, tets, phase
+
+
+def sequence(delta=10600.0, Delta=43100.0, k=200.0, b=1000.0):
+    """PGSE scalars exactly as GCloudDmriSolver.py:184-193 + DmriFemLib.py:826-858 produce them."""
+    entry.load_package()
+    from dmri_fem_cloud_b200 import dmrifemlib as dl
+    import sympy as sp
+    mp = dl.MRI_parameters()
+    mp.bvalue = b
+    mp.delta, mp.Delta = delta, Delta
+    mp.T = Delta + delta
+    mp.fs_sym = sp.Piecewise((1., mp.s < delta), (0., mp.s < Delta), (-1., mp.s < mp.T), (0., True))
+    mp.Apply()
+    sim = dl.MRI_simulation()
+    sim.k = k
+    ts = sim.time_grid(mp)
+    f, _ = mp.profiles_on_grid(ts)
+    fp = np.concatenate([[f[0]], f[:-1]])
+    return mp, ts, f, fp
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for name, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_restatement(xyz, tets, phase, mp, f, fp, k, sample_steps, mode=0):
+    """Time the oracle's C/OpenMP time loop on the first `sample_steps` theta steps."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import bt_cpu
+    import bt_oracle as orc
+    ops = orc.assemble(xyz, tets, phase, D=3e-3, invT2=1e-16, kappa=1e-5)
+    q = mp.qvalue
+    t0 = time.perf_counter()
+    u, iters = bt_cpu.theta_loop(ops, [0, 1, 0], k, 0.5, q * f[:sample_steps], q * fp[:sample_steps], mode=mode)
+    dt = time.perf_counter() - t0
+    return {"seconds": dt, "ndof_real": 2 * ops.ndof, "steps": sample_steps, "iters": int(iters.sum()),
+            "cores": bt_cpu.num_threads(), "signal": float(ops.lumped @ u.real)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="btfem", choices=["btfem", "reference"])
+    ap.add_argument("--n-box", type=int, default=78, help="cubes per edge of the cell-in-box mesh (78 -> ~1 M DOFs)")
+    ap.add_argument("--cpu-sample-steps", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--lanes", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    k = 200.0
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        entry.build_oracle()
+        xyz, tets, phase = workload(args.n_box)
+        mp, ts, f, fp = sequence(k=k)
+        sample = args.cpu_sample_steps
+        res = None
+        for _ in range(max(1, args.warmup > 0)):       # one untimed pass pages everything in
+            res = cpu_restatement(xyz, tets, phase, mp, f, fp, k, 1)
+        tsum, steps = 0.0, 0
+        for _ in range(args.steps):
+            res = cpu_restatement(xyz, tets, phase, mp, f, fp, k, sample, mode=1)
+            tsum += res["seconds"]
+            steps += sample
+        v = res["ndof_real"] * steps / tsum
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tsum / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "configs[1] two-compartment permeable PGSE, cell-in-box n_box=%d" % args.n_box,
+                           "ndof_real": res["ndof_real"], "theta_steps_per_solve": len(ts)},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": res["cores"], "kind": "port",
+                                 "sample": "first %d of %d theta steps per bench step, C/OpenMP restatement "
+                                           "re-forming P,Q and the Jacobi diagonal every step (reference work "
+                                           "pattern); FEniCS/PETSc itself is not installable here" % (sample, len(ts))},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ GPU arm
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    entry.load_package()
+    from dmri_fem_cloud_b200 import btfem, dmrifemlib as dl, meshes
+
+    xyz, tets, phase = workload(args.n_box)
+    mp, ts, f, fp = sequence(k=k)
+    q = mp.qvalue
+    # sweep sharding: rank r takes direction r of a fixed set (rank 0: the CLI's -gdir 0 1 0)
+    dirs = np.vstack([[0.0, 1.0, 0.0], meshes.fibonacci_hemisphere(max(world, 2))])
+    g = dirs[rank % len(dirs)]
+    g = g / np.linalg.norm(g)
+
+    fem = btfem.BTFem(local_rank)
+    if args.lanes:
+        fem.set_lanes(args.lanes)
+    fem.set_mesh(xyz, tets, phase)
+    fem.set_diffusion(3e-3)
+    fem.set_relaxation(1e-16)
+    fem.set_permeability(1e-5)
+    t0 = time.perf_counter()
+    fem.assemble()
+    assemble_s = time.perf_counter() - t0
+    ndof_real = 2 * fem.ndof
+    nsteps = len(ts)
+
+    def one_solve():
+        return fem.solve(k, 0.5, q * f, q * fp, g, rtol=1e-9, atol=1e-10, maxit=100000)
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        res = one_solve()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    kernels = 0
+    for _ in range(args.steps):
+        res = one_solve()                       # returns after a stream sync
+        dev_ms += res["loop_ms"] + res["setup_ms"]
+        kernels += res["n_kernels"] + 3
+    barrier()
+    elapsed = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e through the reference-facing API, host buffers -> signal
+    def e2e_once():
+        mesh = dl.Mesh(xyz, tets)
+        md = dl.MyDomain(mesh, mp)
+        md.device = local_rank
+        md.phase = phase
+        md.IsDomainMultiple = True
+        md.kappa = 1e-5
+        md.Apply()
+        md.D0 = 3e-3
+        md.D = md.D0
+        ls = dl.KrylovSolver("bicgstab", "jacobi")
+        ls.parameters["relative_tolerance"] = 1e-9
+        ls.parameters["absolute_tolerance"] = 1e-10
+        ls.parameters["maximum_iterations"] = 100000
+        sim = dl.MRI_simulation()
+        sim.k = k
+        sim.verbose = False
+        sim.solve(md, mp, ls)
+        s = sim.stats["signal"] / sim.stats["voi"]
+        sim.fem.close()
+        return s
+
+    import contextlib
+    import io
+    e2e_steps = max(1, min(args.steps, 2))
+    with contextlib.redirect_stdout(io.StringIO()):
+        mp.set_gradient_dir(None, *g)
+        e2e_once()
+        barrier()
+        t1 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_sig = e2e_once()
+        barrier()
+        e2e_elapsed = time.perf_counter() - t1
+
+    tmax, e2e_max = elapsed, e2e_elapsed
+    if dist is not None:
+        import torch
+        tt = torch.tensor([elapsed, e2e_elapsed], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tmax, e2e_max = float(tt[0]), float(tt[1])
+
+    if rank == 0:
+        value = world * ndof_real * nsteps * args.steps / tmax
+        e2e_value = world * ndof_real * nsteps * e2e_steps / e2e_max
+        # roofline of the dominant kernel, measured live (CUDA events inside libbtfem on its stream)
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak, peak_src = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        lanes = args.lanes
+        alg_bytes = 20.0 * fem.nnz + 36.0 * fem.ndof
+        ms_cold = fem.spmv_bench(k, 0.5, q, g, lanes=lanes, nrep=20, flush_l2=True)
+        ms_warm = fem.spmv_bench(k, 0.5, q, g, lanes=lanes, nrep=50, flush_l2=False)
+        achieved = alg_bytes / (ms_cold * 1e-3) / 1e9
+        spmv_share = res["n_spmv"] * ms_warm / max(res["loop_ms"], 1e-9)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * tmax / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "configs[1] two-compartment permeable PGSE (-M 1 -b 1000 -p 1e-5 -k 200 "
+                                       "-gdir 0 1 0), cell-in-box n_box=%d" % args.n_box,
+                           "ndof_real": ndof_real, "n_vertices": int(len(xyz)), "n_tets": int(len(tets)),
+                           "nnz": fem.nnz, "n_interface_facets": fem.n_iface, "theta_steps_per_solve": nsteps,
+                           "krylov": "bicgstab+jacobi rtol 1e-9 atol 1e-10", "iters_per_solve": res["total_iters"],
+                           "l2_policy": "working set (matrix %.0f MB + 8 vectors %.0f MB) larger than L2; "
+                                        "roofline launch timed after an explicit 512 MiB L2 flush" % (
+                                            (20.0 * fem.nnz) / 1e6, 8 * 16.0 * fem.ndof / 1e6),
+                           "parallelism": "sweep-sharded x%d (one gradient direction per GPU)" % world,
+                           "spmv_lanes_per_row": lanes},
+                "device_ms_per_step": dev_ms / args.steps, "assemble_s": assemble_s,
+                "normalized_signal": res["signal"] / res["voi"],
+                "gpu_launches": int(kernels),
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(fem.h2d_bytes + 3 * 8 * nsteps),
+                        "d2h_bytes_per_step": int(8 * 8 + 4 * 8), "seconds_per_solve": e2e_max / e2e_steps,
+                        "normalized_signal": e2e_sig,
+                        "api": "dmrifemlib.MyDomain/MRI_simulation.solve (host numpy mesh -> signal)"},
+                "roofline": {"bound": "hbm", "kernel": ("k_spmv_stream<MODE_V|MODE_T>" if lanes == 0 else "k_spmv<%d,MODE_V|MODE_T>" % lanes) + " fused complex SpMV",
+                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "peak_source": peak_src, "traffic": None,
+                             "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch_l2_flushed": ms_cold,
+                             "ms_per_launch_back_to_back": ms_warm,
+                             "achieved_back_to_back": alg_bytes / (ms_warm * 1e-3) / 1e9,
+                             "share_of_loop": spmv_share}}
+        if not args.no_cpu and world == 1:
+            entry.build_oracle()
+            cpu = cpu_restatement(xyz, tets, phase, mp, f, fp, k, args.cpu_sample_steps, mode=0)
+            line["cpu_baseline"] = {"value": cpu["ndof_real"] * cpu["steps"] / cpu["seconds"], "unit": UNIT,
+                                    "cores": cpu["cores"], "kind": "port",
+                                    "sample": "first %d of %d theta steps, oracle C/OpenMP restatement with "
+                                              "pre-combined operators (%.1f s)" % (cpu["steps"], nsteps,
+                                                                                    cpu["seconds"])}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    fem.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -499,6 +499,27 @@ void bt_build_pattern(btfem* h) {
   k_diagpos<<<nblocks(h->ndof), TPB, 0, st>>>(h->ndof, h->d_rowptr.p, h->d_colidx.p, h->d_diagpos.p);
   BT_CUDA(cudaGetLastError());
   BT_CUDA(cudaStreamSynchronize(st));
+  // row blocks of the stream SpMV: greedy, contiguous, <= BT_STREAM_NNZ nonzeros and <= BT_STREAM_ROWS rows
+  std::vector<int32_t> rp(h->ndof + 1);
+  h->d_rowptr.download(rp.data(), st);
+  std::vector<int32_t> blk;
+  blk.push_back(0);
+  bool fits = true;
+  for (int64_t r = 0; r < h->ndof;) {
+    int64_t e = r;
+    while (e < h->ndof && e - r < BT_STREAM_ROWS && rp[e + 1] - rp[r] <= BT_STREAM_NNZ) ++e;
+    if (e == r) { fits = false; break; }   // a single row longer than a block: use the lanes variant
+    blk.push_back((int32_t)e);
+    r = e;
+  }
+  if (fits) {
+    h->n_rowblk = (int64_t)blk.size() - 1;
+    h->d_blk_row.upload(blk.data(), blk.size(), st);
+  } else {
+    h->n_rowblk = 0;
+    if (h->lanes == 0) h->lanes = 8;
+  }
+  BT_CUDA(cudaStreamSynchronize(st));
 }
 
 void bt_assemble_values(btfem* h) {

@@ -114,6 +114,8 @@ __global__ void k_combine(int64_t nnz, const int32_t* __restrict__ rowidx, const
 
 struct SpmvArgs {
   int n;
+  int nblk;                  // stream variant: number of row blocks
+  const int32_t* blk_row;    // [nblk+1] first row of each block
   const int32_t* rowptr;
   const int32_t* colidx;
   const double2* PJ;
@@ -131,89 +133,70 @@ struct SpmvArgs {
   double c_plain;
 };
 
-template <int LANES>
-__device__ __forceinline__ double2 row_product(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
-                                               const double2* __restrict__ V, const double2* __restrict__ x, double c,
-                                               int row, bool valid, int lane) {
-  int s = 0, e = 0;
-  if (valid) {
-    s = __ldg(rowptr + row);
-    e = __ldg(rowptr + row + 1);
-  }
-  double ar = 0.0, ai = 0.0;
-#pragma unroll 2
-  for (int k = s + lane; k < e; k += LANES) {
-    const int col = __ldg(colidx + k);
-    const double2 pj = __ldg(V + k);
-    const double2 xv = __ldg(x + col);
-    const double a = pj.x, b = c * pj.y;   // (a + i b)(xr + i xi)
-    ar = fma(a, xv.x, ar);
-    ar = fma(-b, xv.y, ar);
-    ai = fma(a, xv.y, ai);
-    ai = fma(b, xv.x, ai);
-  }
-#pragma unroll
-  for (int o = LANES / 2; o > 0; o >>= 1) {
-    ar += __shfl_xor_sync(0xffffffffu, ar, o);
-    ai += __shfl_xor_sync(0xffffffffu, ai, o);
-  }
-  return make_double2(ar, ai);
-}
+// streaming loads for the matrix (read once per SpMV; keeps the Krylov vectors in the 126 MB L2)
+__device__ __forceinline__ int ld_stream(const int32_t* p) { return __ldcs(p); }
+__device__ __forceinline__ double2 ld_stream(const double2* p) { return __ldcs(p); }
 
-template <int LANES, int MODE>
-__global__ void __launch_bounds__(TPB) k_spmv(SpmvArgs a) {
-  constexpr int RPB = TPB / LANES;
-  KrylovCtrl* ctrl = a.ctrl;
+struct ModeSetup {
   const double2* V;
   const double2* x;
   double c;
+  bool skip;
+};
+
+template <int MODE>
+__device__ __forceinline__ ModeSetup mode_setup(const SpmvArgs& a) {
+  ModeSetup m;
+  m.skip = false;
+  const KrylovCtrl* ctrl = a.ctrl;
   if (MODE == MODE_PLAIN) {
-    V = a.PJ; x = a.x_plain; c = a.c_plain;
+    m.V = a.PJ; m.x = a.x_plain; m.c = a.c_plain;
   } else if (MODE == MODE_RHS) {
-    V = a.QJ; x = a.u; c = ctrl->theta_cb_scale * a.cb[ctrl->step_next];
+    m.V = a.QJ; m.x = a.u; m.c = ctrl->theta_cb_scale * a.cb[ctrl->step_next];
   } else {
-    if (ctrl->done) return;
-    V = a.PJ; c = ctrl->theta_cA_scale * a.cA[ctrl->step];
-    x = (MODE == MODE_RESID) ? a.u : (MODE == MODE_V ? a.p : a.s);
+    m.skip = ctrl->done != 0;
+    m.V = a.PJ; m.c = ctrl->theta_cA_scale * a.cA[ctrl->step];
+    m.x = (MODE == MODE_RESID) ? a.u : (MODE == MODE_V ? a.p : a.s);
   }
-  const int lane = threadIdx.x % LANES;
-  const int grp = threadIdx.x / LANES;
-  double acc[2] = {0.0, 0.0};
-  const int ntiles = (a.n + RPB - 1) / RPB;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int row = tile * RPB + grp;
-    const bool valid = row < a.n;
-    double2 y = row_product<LANES>(a.rowptr, a.colidx, V, x, c, row, valid, lane);
-    if (valid && lane == 0) {
-      if (MODE == MODE_PLAIN) {
-        a.y_plain[row] = y;
-      } else if (MODE == MODE_RHS) {
-        if (a.rhs_add) { double2 w = a.rhs_add[row]; y.x += w.x; y.y += w.y; }
-        if (ctrl->nonzero_guess) {
-          a.t[row] = y;                      // b^ kept for the residual kernel
-        } else {
-          a.r[row] = y; a.rp[row] = y;
-        }
-        a.p[row] = make_double2(0.0, 0.0);
-        a.v[row] = make_double2(0.0, 0.0);
-        acc[0] += y.x * y.x + y.y * y.y;
-      } else if (MODE == MODE_RESID) {
-        double2 b = a.t[row];
-        double2 rr = make_double2(b.x - y.x, b.y - y.y);
-        a.r[row] = rr; a.rp[row] = rr;
-        acc[0] += rr.x * rr.x + rr.y * rr.y;
-      } else if (MODE == MODE_V) {
-        a.v[row] = y;
-        double2 q = a.rp[row];
-        acc[0] += y.x * q.x + y.y * q.y;
-      } else {
-        a.t[row] = y;
-        double2 sv = a.s[row];
-        acc[0] += sv.x * y.x + sv.y * y.y;
-        acc[1] += y.x * y.x + y.y * y.y;
-      }
+  return m;
+}
+
+// what happens to one finished row y_row = (A x)_row, and which dot-product terms it contributes
+template <int MODE>
+__device__ __forceinline__ void row_epilogue(const SpmvArgs& a, int row, double2 y, double (&acc)[2]) {
+  if (MODE == MODE_PLAIN) {
+    a.y_plain[row] = y;
+  } else if (MODE == MODE_RHS) {
+    if (a.rhs_add) { double2 w = a.rhs_add[row]; y.x += w.x; y.y += w.y; }
+    if (a.ctrl->nonzero_guess) {
+      a.t[row] = y;                      // b^ kept for the residual kernel
+    } else {
+      a.r[row] = y; a.rp[row] = y;
     }
+    a.p[row] = make_double2(0.0, 0.0);
+    a.v[row] = make_double2(0.0, 0.0);
+    acc[0] += y.x * y.x + y.y * y.y;
+  } else if (MODE == MODE_RESID) {
+    double2 b = a.t[row];
+    double2 rr = make_double2(b.x - y.x, b.y - y.y);
+    a.r[row] = rr; a.rp[row] = rr;
+    acc[0] += rr.x * rr.x + rr.y * rr.y;
+  } else if (MODE == MODE_V) {
+    a.v[row] = y;
+    double2 q = a.rp[row];
+    acc[0] += y.x * q.x + y.y * q.y;
+  } else {
+    a.t[row] = y;
+    double2 sv = a.s[row];
+    acc[0] += sv.x * y.x + sv.y * y.y;
+    acc[1] += y.x * y.x + y.y * y.y;
   }
+}
+
+// grid-wide completion of the dot products + the scalar recurrences that depend on them
+template <int MODE>
+__device__ __forceinline__ void mode_finalize(const SpmvArgs& a, double (&acc)[2]) {
+  KrylovCtrl* ctrl = a.ctrl;
   if (MODE == MODE_PLAIN) return;
   if (MODE == MODE_RHS) {
     double v1[1] = {acc[0]};
@@ -254,6 +237,117 @@ __global__ void __launch_bounds__(TPB) k_spmv(SpmvArgs a) {
       ctrl->omega = (v2[1] == 0.0) ? 0.0 : v2[0] / v2[1];
     }
   }
+}
+
+// ---- variant A: LANES threads per row (short rows; kept for the sweep and as the fallback)
+template <int LANES>
+__device__ __forceinline__ double2 row_product(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                               const double2* __restrict__ V, const double2* __restrict__ x, double c,
+                                               int row, bool valid, int lane) {
+  int s = 0, e = 0;
+  if (valid) {
+    s = __ldg(rowptr + row);
+    e = __ldg(rowptr + row + 1);
+  }
+  double ar = 0.0, ai = 0.0;
+#pragma unroll 2
+  for (int k = s + lane; k < e; k += LANES) {
+    const int col = ld_stream(colidx + k);
+    const double2 pj = ld_stream(V + k);
+    const double2 xv = __ldg(x + col);
+    const double a = pj.x, b = c * pj.y;   // (a + i b)(xr + i xi)
+    ar = fma(a, xv.x, ar);
+    ar = fma(-b, xv.y, ar);
+    ai = fma(a, xv.y, ai);
+    ai = fma(b, xv.x, ai);
+  }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) {
+    ar += __shfl_xor_sync(0xffffffffu, ar, o);
+    ai += __shfl_xor_sync(0xffffffffu, ai, o);
+  }
+  return make_double2(ar, ai);
+}
+
+template <int LANES, int MODE>
+__global__ void __launch_bounds__(TPB) k_spmv(SpmvArgs a) {
+  constexpr int RPB = TPB / LANES;
+  const ModeSetup m = mode_setup<MODE>(a);
+  if (m.skip) return;
+  const int lane = threadIdx.x % LANES;
+  const int grp = threadIdx.x / LANES;
+  double acc[2] = {0.0, 0.0};
+  const int ntiles = (a.n + RPB - 1) / RPB;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row = tile * RPB + grp;
+    const bool valid = row < a.n;
+    double2 y = row_product<LANES>(a.rowptr, a.colidx, m.V, m.x, m.c, row, valid, lane);
+    if (valid && lane == 0) row_epilogue<MODE>(a, row, y, acc);
+  }
+  mode_finalize<MODE>(a, acc);
+}
+
+// ---- variant B ("stream"): a block owns a contiguous row range holding <= STREAM_NNZ nonzeros.
+// Phase 1: all threads stream the range's (col, value) pairs fully coalesced, EPT independent loads per
+// thread in flight, gather x, and park the complex products in shared memory.  Phase 2: one thread per row
+// sums its products.  Row ranges are fixed at setup (pattern is static), so summation order is fixed too.
+constexpr int STREAM_EPT = 8;
+constexpr int STREAM_NNZ = TPB * STREAM_EPT;   // 2048 products = 32 KB shared
+
+template <int MODE>
+__global__ void __launch_bounds__(TPB, 3) k_spmv_stream(SpmvArgs a) {
+  __shared__ double s_re[STREAM_NNZ];
+  __shared__ double s_im[STREAM_NNZ];
+  const ModeSetup m = mode_setup<MODE>(a);
+  if (m.skip) return;
+  const int tid = threadIdx.x;
+  double acc[2] = {0.0, 0.0};
+  for (int b = blockIdx.x; b < a.nblk; b += gridDim.x) {
+    const int r0 = __ldg(a.blk_row + b), r1 = __ldg(a.blk_row + b + 1);
+    const int k0 = __ldg(a.rowptr + r0), k1 = __ldg(a.rowptr + r1);
+    const int row = r0 + tid;
+    int rs = 0, re = 0;
+    if (row < r1) {
+      rs = __ldg(a.rowptr + row) - k0;
+      re = __ldg(a.rowptr + row + 1) - k0;
+    }
+    int col[STREAM_EPT];
+    double2 val[STREAM_EPT];
+#pragma unroll
+    for (int j = 0; j < STREAM_EPT; ++j) {
+      const int k = k0 + j * TPB + tid;
+      col[j] = -1;
+      if (k < k1) {
+        col[j] = ld_stream(a.colidx + k);
+        val[j] = ld_stream(m.V + k);
+      }
+    }
+    double2 xv[STREAM_EPT];
+#pragma unroll
+    for (int j = 0; j < STREAM_EPT; ++j) {
+      xv[j] = make_double2(0.0, 0.0);
+      if (col[j] >= 0) xv[j] = __ldg(m.x + col[j]);      // EPT independent gathers in flight
+    }
+#pragma unroll
+    for (int j = 0; j < STREAM_EPT; ++j) {
+      if (col[j] >= 0) {
+        const double pa = val[j].x, pb = m.c * val[j].y;
+        s_re[j * TPB + tid] = fma(pa, xv[j].x, -pb * xv[j].y);
+        s_im[j * TPB + tid] = fma(pa, xv[j].y, pb * xv[j].x);
+      }
+    }
+    __syncthreads();
+    if (row < r1) {
+      double ar = 0.0, ai = 0.0;
+      for (int k = rs; k < re; ++k) {
+        ar += s_re[k];
+        ai += s_im[k];
+      }
+      row_epilogue<MODE>(a, row, make_double2(ar, ai), acc);
+    }
+    __syncthreads();
+  }
+  mode_finalize<MODE>(a, acc);
 }
 
 // ------------------------------------------------------------------------------------ vector kernels
@@ -347,13 +441,18 @@ inline int spmv_grid(int n, int lanes) {
 
 template <int MODE>
 void launch_spmv(int lanes, const SpmvArgs& a, cudaStream_t st) {
+  if (lanes == 0) {   // stream variant
+    int g = std::max(1, std::min(a.nblk, BT_NUM_SMS * 16));
+    k_spmv_stream<MODE><<<g, TPB, 0, st>>>(a);
+    return;
+  }
   int g = spmv_grid(a.n, lanes);
   switch (lanes) {
     case 4: k_spmv<4, MODE><<<g, TPB, 0, st>>>(a); break;
     case 8: k_spmv<8, MODE><<<g, TPB, 0, st>>>(a); break;
     case 16: k_spmv<16, MODE><<<g, TPB, 0, st>>>(a); break;
     case 32: k_spmv<32, MODE><<<g, TPB, 0, st>>>(a); break;
-    default: throw BtError{BTFEM_EINVAL, "lanes must be 4, 8, 16 or 32"};
+    default: throw BtError{BTFEM_EINVAL, "lanes must be 0 (stream), 4, 8, 16 or 32"};
   }
 }
 
@@ -363,6 +462,8 @@ SpmvArgs base_args(btfem* h) {
   a.n = (int)h->ndof;
   a.rowptr = h->d_rowptr.p;
   a.colidx = h->d_colidx.p;
+  a.nblk = (int)h->n_rowblk;
+  a.blk_row = h->d_blk_row.p;
   a.PJ = h->d_PJ.p;
   a.QJ = h->d_QJ.p;
   a.cA = h->d_cA.p;
@@ -547,6 +648,8 @@ void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_
     if (iters_per_step) iters_per_step[step] = it;
     est = it;
     last_reason = h->h_ctrl->reason;
+    // converged before the first iteration with a zero initial guess: PETSc returns x = 0
+    if (it == 0 && !sa->nonzero_guess && last_reason > 0) h->d_u.zero(st);
     if (last_reason < 0) fail = last_reason;
   }
   BT_CUDA(cudaEventRecord(e2, st));

@@ -84,7 +84,7 @@ def test_fused_spmv(case):
     want = P @ x + 1j * theta * c * (Jg @ x)
     with btfem.BTFem(0) as fem:
         _setup(fem, xyz, tets, phase, co)
-        for lanes in (4, 8, 16, 32):
+        for lanes in (0, 4, 8, 16, 32):          # 0 = stream variant (default)
             fem.set_lanes(lanes)
             got = fem.spmv(dt, theta, c, g, x)
             assert _relmax(got, want) <= 1e-13, (lanes, _relmax(got, want))
