@@ -300,7 +300,7 @@ def main():
                            "nnz": fem.nnz, "n_interface_facets": fem.n_iface, "theta_steps_per_solve": nsteps,
                            "krylov": "bicgstab+jacobi rtol 1e-9 atol 1e-10", "iters_per_solve": res["total_iters"],
                            "l2_policy": "working set (matrix %.0f MB + 8 vectors %.0f MB) larger than L2; "
-                                        "roofline launch timed after an explicit 512 MiB L2 flush" % (
+                                        "roofline launch timed after reading a 512 MiB scratch buffer (L2 flush)" % (
                                             (20.0 * fem.nnz) / 1e6, 8 * 16.0 * fem.ndof / 1e6),
                            "parallelism": "sweep-sharded x%d (one gradient direction per GPU)" % world,
                            "spmv_lanes_per_row": lanes},
@@ -312,7 +312,7 @@ def main():
                         "d2h_bytes_per_step": int(8 * 8 + 4 * 8), "seconds_per_solve": e2e_max / e2e_steps,
                         "normalized_signal": e2e_sig,
                         "api": "dmrifemlib.MyDomain/MRI_simulation.solve (host numpy mesh -> signal)"},
-                "roofline": {"bound": "hbm", "kernel": ("k_spmv_stream<MODE_V|MODE_T>" if lanes == 0 else "k_spmv<%d,MODE_V|MODE_T>" % lanes) + " fused complex SpMV",
+                "roofline": {"bound": "hbm", "kernel": ("k_spmv_sell<MODE_V|MODE_T>" if lanes == 0 else "k_spmv<%d,MODE_V|MODE_T>" % lanes) + " fused complex SpMV",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "peak_source": peak_src, "traffic": None,
                              "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch_l2_flushed": ms_cold,

@@ -204,8 +204,7 @@ int btfem_get_lumped_mass(btfem_t* h, double* out) {
 int btfem_set_lanes(btfem_t* h, int32_t lanes) {
   return guarded(h, [&] {
     BT_REQUIRE(lanes == 0 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32,
-               "lanes must be 0 (stream), 4, 8, 16 or 32");
-    BT_REQUIRE(lanes != 0 || !h->assembled || h->n_rowblk > 0, "stream variant unavailable: a row exceeds the block size");
+               "lanes must be 0 (SELL-32), 4, 8, 16 or 32");
     h->lanes = lanes;
   });
 }

@@ -11,8 +11,7 @@
 
 #define BT_NUM_SMS 148          // B200: 2 dies x 74 SMs
 #define BT_MAX_PARTIALS 4096
-#define BT_STREAM_NNZ 2048      // nonzeros per row block of the stream SpMV (solve.cu: TPB * STREAM_EPT)
-#define BT_STREAM_ROWS 256    // upper bound on the grid of any reducing kernel
+#define BT_SELL_SIGMA 1024      // sorting window (rows) of the SELL-32 layout    // upper bound on the grid of any reducing kernel
 
 struct BtError {
   int code;
@@ -130,8 +129,13 @@ struct btfem {
   bool assembled = false;
   int64_t ndof = 0, nnz = 0, nsrc = 0;
   DevArray<int32_t> d_rowptr, d_colidx, d_rowidx, d_diagpos;
-  int64_t n_rowblk = 0;            // row blocks of the stream SpMV (<= BT_STREAM_NNZ nonzeros, <= 256 rows each)
-  DevArray<int32_t> d_blk_row;     // [n_rowblk+1]
+  // SELL-32 copy of the pattern for the fused SpMV (rows sorted by length inside windows of BT_SELL_SIGMA)
+  int64_t n_slice = 0, nnz_sell = 0;
+  DevArray<int32_t> d_slice_ptr;   // [n_slice+1]
+  DevArray<int32_t> d_sell_row;    // [n_slice*32] slot -> row (-1 = padding slot)
+  DevArray<int32_t> d_sell_slot;   // [ndof] row -> slot
+  DevArray<int32_t> d_sell_col;    // [nnz_sell]
+  DevArray<double2> d_PJs, d_QJs;  // [nnz_sell] per-solve operator values in SELL order
   DevArray<uint32_t> d_src;        // contribution ids sorted by (row,col), stable
   DevArray<int64_t> d_seg;         // [nnz+1] segment offsets into d_src
   DevArray<double> d_vals[8];      // M,S,R,Jx,Jy,Jz,I,B
@@ -149,7 +153,7 @@ struct btfem {
   double comb_dt = -1, comb_theta = -1, comb_g[3] = {0, 0, 0};
   int comb_pc = -1;
   bool have_solution = false;
-  int lanes = 0;                   // fused SpMV variant: 0 = stream (row blocks), else threads per row
+  int lanes = 0;                   // fused SpMV variant: 0 = SELL-32 (default), else CSR with `lanes` threads per row
 
   // periodic gather operator G: u_bc[b] = phase * sum_k w[b][k] * u[idx[b][k]]
   int64_t n_pb = 0;

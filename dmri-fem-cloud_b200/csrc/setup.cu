@@ -212,6 +212,23 @@ __global__ void k_diagpos(int64_t ndof, const int32_t* __restrict__ rowptr, cons
   diagpos[r] = d;
 }
 
+// SELL-32 column indices: slot (slice, lane) copies its row's columns to slice-column-major order;
+// padding entries point at the row itself (a valid address; their values are zero).
+__global__ void k_sell_columns(int64_t nslice, const int32_t* __restrict__ slice_ptr,
+                               const int32_t* __restrict__ sell_row, const int32_t* __restrict__ rowptr,
+                               const int32_t* __restrict__ colidx, int32_t* __restrict__ sell_col) {
+  int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (slot >= nslice * 32) return;
+  const int64_t s = slot >> 5;
+  const int lane = (int)(slot & 31);
+  const int base = slice_ptr[s];
+  const int width = (slice_ptr[s + 1] - base) >> 5;
+  const int row = sell_row[slot];
+  const int k0 = row >= 0 ? rowptr[row] : 0;
+  const int len = row >= 0 ? rowptr[row + 1] - k0 : 0;
+  for (int j = 0; j < width; ++j) sell_col[base + j * 32 + lane] = j < len ? colidx[k0 + j] : (row >= 0 ? row : 0);
+}
+
 // ------------------------------------------------------------------------------------ assembly
 
 struct AsmArgs {
@@ -499,26 +516,46 @@ void bt_build_pattern(btfem* h) {
   k_diagpos<<<nblocks(h->ndof), TPB, 0, st>>>(h->ndof, h->d_rowptr.p, h->d_colidx.p, h->d_diagpos.p);
   BT_CUDA(cudaGetLastError());
   BT_CUDA(cudaStreamSynchronize(st));
-  // row blocks of the stream SpMV: greedy, contiguous, <= BT_STREAM_NNZ nonzeros and <= BT_STREAM_ROWS rows
+  // SELL-32 layout: sort rows by descending length inside windows of BT_SELL_SIGMA rows (stable, so the
+  // result is deterministic), cut into slices of 32 slots, slice width = longest row of the slice.
   std::vector<int32_t> rp(h->ndof + 1);
   h->d_rowptr.download(rp.data(), st);
-  std::vector<int32_t> blk;
-  blk.push_back(0);
-  bool fits = true;
-  for (int64_t r = 0; r < h->ndof;) {
-    int64_t e = r;
-    while (e < h->ndof && e - r < BT_STREAM_ROWS && rp[e + 1] - rp[r] <= BT_STREAM_NNZ) ++e;
-    if (e == r) { fits = false; break; }   // a single row longer than a block: use the lanes variant
-    blk.push_back((int32_t)e);
-    r = e;
+  const int64_t n = h->ndof;
+  const int64_t nslice = (n + 31) / 32;
+  std::vector<int32_t> sell_row(nslice * 32, -1), sell_slot(n), slice_ptr(nslice + 1, 0);
+  for (int64_t i = 0; i < n; ++i) sell_row[i] = (int32_t)i;
+  for (int64_t w0 = 0; w0 < n; w0 += BT_SELL_SIGMA) {
+    const int64_t w1 = std::min<int64_t>(n, w0 + BT_SELL_SIGMA);
+    std::stable_sort(sell_row.begin() + w0, sell_row.begin() + w1, [&](int32_t x, int32_t y) {
+      return rp[x + 1] - rp[x] > rp[y + 1] - rp[y];
+    });
   }
-  if (fits) {
-    h->n_rowblk = (int64_t)blk.size() - 1;
-    h->d_blk_row.upload(blk.data(), blk.size(), st);
-  } else {
-    h->n_rowblk = 0;
-    if (h->lanes == 0) h->lanes = 8;
+  int64_t tot = 0;
+  for (int64_t s = 0; s < nslice; ++s) {
+    int wmax = 0;
+    for (int l = 0; l < 32; ++l) {
+      const int32_t r = sell_row[s * 32 + l];
+      if (r >= 0) {
+        sell_slot[r] = (int32_t)(s * 32 + l);
+        wmax = std::max(wmax, rp[r + 1] - rp[r]);
+      }
+    }
+    slice_ptr[s] = (int32_t)tot;
+    tot += (int64_t)wmax * 32;
+    BT_REQUIRE(tot < (int64_t)0x7fffffffLL, "SELL storage exceeds int32");
   }
+  slice_ptr[nslice] = (int32_t)tot;
+  h->n_slice = nslice;
+  h->nnz_sell = tot;
+  h->d_slice_ptr.upload(slice_ptr.data(), slice_ptr.size(), st);
+  h->d_sell_row.upload(sell_row.data(), sell_row.size(), st);
+  h->d_sell_slot.upload(sell_slot.data(), sell_slot.size(), st);
+  h->d_sell_col.alloc(tot);
+  k_sell_columns<<<nblocks(nslice * 32), TPB, 0, st>>>(nslice, h->d_slice_ptr.p, h->d_sell_row.p, h->d_rowptr.p,
+                                                      h->d_colidx.p, h->d_sell_col.p);
+  h->d_PJs.release();
+  h->d_QJs.release();
+  BT_CUDA(cudaGetLastError());
   BT_CUDA(cudaStreamSynchronize(st));
 }
 

@@ -98,24 +98,40 @@ __global__ void k_combine(int64_t nnz, const int32_t* __restrict__ rowidx, const
                           const double* __restrict__ B, const double* __restrict__ Jx, const double* __restrict__ Jy,
                           const double* __restrict__ Jz, double inv_dt, double theta, double gx, double gy, double gz,
                           const double* __restrict__ dinv, double2* __restrict__ PJ, double2* __restrict__ QJ,
-                          double* __restrict__ Bhat) {
+                          double* __restrict__ Bhat, const int32_t* __restrict__ rowptr,
+                          const int32_t* __restrict__ sell_slot, const int32_t* __restrict__ slice_ptr,
+                          double2* __restrict__ PJs, double2* __restrict__ QJs) {
   int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (k >= nnz) return;
   double di = dinv[rowidx[k]];
   double mk = M[k] * inv_dt;
   double k0 = S[k] + R[k] + I[k];
   double jg = (gx * Jx[k] + gy * Jy[k] + gz * Jz[k]) * di;
-  PJ[k] = make_double2((mk + theta * (k0 + B[k])) * di, jg);
-  QJ[k] = make_double2((mk - (1.0 - theta) * k0) * di, jg);
+  const double2 pj = make_double2((mk + theta * (k0 + B[k])) * di, jg);
+  const double2 qj = make_double2((mk - (1.0 - theta) * k0) * di, jg);
+  PJ[k] = pj;
+  QJ[k] = qj;
   if (Bhat) Bhat[k] = B[k] * di;
+  if (PJs) {   // same entry in the SELL-32 layout: slice base + (position in row)*32 + slot lane
+    const int row = rowidx[k];
+    const int slot = sell_slot[row];
+    const int pos = slice_ptr[slot >> 5] + (int)(k - rowptr[row]) * 32 + (slot & 31);
+    PJs[pos] = pj;
+    QJs[pos] = qj;
+  }
 }
 
 // ------------------------------------------------------------------------------------ fused SpMV
 
 struct SpmvArgs {
   int n;
-  int nblk;                  // stream variant: number of row blocks
-  const int32_t* blk_row;    // [nblk+1] first row of each block
+  int nslice;                // SELL-32: number of 32-row slices
+  const int32_t* slice_ptr;  // [nslice+1] offset of each slice in the SELL arrays (multiple of 32)
+  const int32_t* sell_row;   // [nslice*32] row owned by each slot (-1 = padding)
+  const int32_t* sell_col;   // [nnz_sell] column indices, slice-column-major (padding: the row itself)
+  const double2* PJs;        // SELL copies of PJ / QJ
+  const double2* QJs;
+  int use_sell;
   const int32_t* rowptr;
   const int32_t* colidx;
   const double2* PJ;
@@ -150,12 +166,12 @@ __device__ __forceinline__ ModeSetup mode_setup(const SpmvArgs& a) {
   m.skip = false;
   const KrylovCtrl* ctrl = a.ctrl;
   if (MODE == MODE_PLAIN) {
-    m.V = a.PJ; m.x = a.x_plain; m.c = a.c_plain;
+    m.V = a.use_sell ? a.PJs : a.PJ; m.x = a.x_plain; m.c = a.c_plain;
   } else if (MODE == MODE_RHS) {
-    m.V = a.QJ; m.x = a.u; m.c = ctrl->theta_cb_scale * a.cb[ctrl->step_next];
+    m.V = a.use_sell ? a.QJs : a.QJ; m.x = a.u; m.c = ctrl->theta_cb_scale * a.cb[ctrl->step_next];
   } else {
     m.skip = ctrl->done != 0;
-    m.V = a.PJ; m.c = ctrl->theta_cA_scale * a.cA[ctrl->step];
+    m.V = a.use_sell ? a.PJs : a.PJ; m.c = ctrl->theta_cA_scale * a.cA[ctrl->step];
     m.x = (MODE == MODE_RESID) ? a.u : (MODE == MODE_V ? a.p : a.s);
   }
   return m;
@@ -287,65 +303,77 @@ __global__ void __launch_bounds__(TPB) k_spmv(SpmvArgs a) {
   mode_finalize<MODE>(a, acc);
 }
 
-// ---- variant B ("stream"): a block owns a contiguous row range holding <= STREAM_NNZ nonzeros.
-// Phase 1: all threads stream the range's (col, value) pairs fully coalesced, EPT independent loads per
-// thread in flight, gather x, and park the complex products in shared memory.  Phase 2: one thread per row
-// sums its products.  Row ranges are fixed at setup (pattern is static), so summation order is fixed too.
-constexpr int STREAM_EPT = 8;
-constexpr int STREAM_NNZ = TPB * STREAM_EPT;   // 2048 products = 32 KB shared
+// Ordered loads: `asm volatile` keeps the issue order, so all UNR matrix loads and then all UNR gathers are
+// in flight together (ptxas otherwise sinks each load next to its use to save registers, which serialises
+// the memory latency -- the kernel is latency-bound, not register-bound).
+__device__ __forceinline__ int ldv_stream_i32(const int32_t* p) {
+  int v;
+  asm volatile("ld.global.cs.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ldv_stream_f64x2(const double2* p) {
+  double2 v;
+  asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ldv_gather_f64x2(const double2* p) {
+  double2 v;
+  asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
 
-template <int MODE>
-__global__ void __launch_bounds__(TPB, 3) k_spmv_stream(SpmvArgs a) {
-  __shared__ double s_re[STREAM_NNZ];
-  __shared__ double s_im[STREAM_NNZ];
+// ---- variant C (default): SELL-32.  Rows are grouped in slices of 32 (after sorting by length inside
+// windows of BT_SELL_SIGMA rows to bound padding); a slice is stored column-major, so lane l of a warp owns
+// row-slot l and every warp-wide load of (column, value pair) is one fully coalesced 128 B / 512 B request.
+// No cross-lane reduction, no shared memory, warp-uniform trip counts; UNR independent (col, value) loads
+// and UNR independent x gathers are in flight per thread.  Within a row the products are summed in
+// ascending column order (the CSR order), so the result does not depend on the launch shape.
+// MINB (resident blocks per SM the register allocation aims at) and SELL_UNR set the loads in flight.
+template <int MODE, int SELL_UNR, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_spmv_sell(SpmvArgs a) {
   const ModeSetup m = mode_setup<MODE>(a);
   if (m.skip) return;
-  const int tid = threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int wpb = TPB / 32;
   double acc[2] = {0.0, 0.0};
-  for (int b = blockIdx.x; b < a.nblk; b += gridDim.x) {
-    const int r0 = __ldg(a.blk_row + b), r1 = __ldg(a.blk_row + b + 1);
-    const int k0 = __ldg(a.rowptr + r0), k1 = __ldg(a.rowptr + r1);
-    const int row = r0 + tid;
-    int rs = 0, re = 0;
-    if (row < r1) {
-      rs = __ldg(a.rowptr + row) - k0;
-      re = __ldg(a.rowptr + row + 1) - k0;
-    }
-    int col[STREAM_EPT];
-    double2 val[STREAM_EPT];
+  for (int slice = blockIdx.x * wpb + (threadIdx.x >> 5); slice < a.nslice; slice += gridDim.x * wpb) {
+    const int base = __ldg(a.slice_ptr + slice);
+    const int width = (__ldg(a.slice_ptr + slice + 1) - base) >> 5;
+    const int row = __ldg(a.sell_row + slice * 32 + lane);       // -1: padding slot past the last row
+    const int32_t* cp = a.sell_col + base + lane;
+    const double2* vp = m.V + base + lane;
+    double ar = 0.0, ai = 0.0;
+    int j = 0;
+    for (; j + SELL_UNR <= width; j += SELL_UNR) {
+      int col[SELL_UNR];
+      double2 val[SELL_UNR], xv[SELL_UNR];
 #pragma unroll
-    for (int j = 0; j < STREAM_EPT; ++j) {
-      const int k = k0 + j * TPB + tid;
-      col[j] = -1;
-      if (k < k1) {
-        col[j] = ld_stream(a.colidx + k);
-        val[j] = ld_stream(m.V + k);
+      for (int u = 0; u < SELL_UNR; ++u) {
+        col[u] = ldv_stream_i32(cp + (j + u) * 32);
+        val[u] = ldv_stream_f64x2(vp + (j + u) * 32);
+      }
+#pragma unroll
+      for (int u = 0; u < SELL_UNR; ++u) xv[u] = ldv_gather_f64x2(m.x + col[u]);
+#pragma unroll
+      for (int u = 0; u < SELL_UNR; ++u) {
+        const double pa = val[u].x, pb = m.c * val[u].y;
+        ar = fma(pa, xv[u].x, ar);
+        ar = fma(-pb, xv[u].y, ar);
+        ai = fma(pa, xv[u].y, ai);
+        ai = fma(pb, xv[u].x, ai);
       }
     }
-    double2 xv[STREAM_EPT];
-#pragma unroll
-    for (int j = 0; j < STREAM_EPT; ++j) {
-      xv[j] = make_double2(0.0, 0.0);
-      if (col[j] >= 0) xv[j] = __ldg(m.x + col[j]);      // EPT independent gathers in flight
+    for (; j < width; ++j) {
+      const int col = ld_stream(cp + j * 32);
+      const double2 val = ld_stream(vp + j * 32);
+      const double2 xv = __ldg(m.x + col);
+      const double pa = val.x, pb = m.c * val.y;
+      ar = fma(pa, xv.x, ar);
+      ar = fma(-pb, xv.y, ar);
+      ai = fma(pa, xv.y, ai);
+      ai = fma(pb, xv.x, ai);
     }
-#pragma unroll
-    for (int j = 0; j < STREAM_EPT; ++j) {
-      if (col[j] >= 0) {
-        const double pa = val[j].x, pb = m.c * val[j].y;
-        s_re[j * TPB + tid] = fma(pa, xv[j].x, -pb * xv[j].y);
-        s_im[j * TPB + tid] = fma(pa, xv[j].y, pb * xv[j].x);
-      }
-    }
-    __syncthreads();
-    if (row < r1) {
-      double ar = 0.0, ai = 0.0;
-      for (int k = rs; k < re; ++k) {
-        ar += s_re[k];
-        ai += s_im[k];
-      }
-      row_epilogue<MODE>(a, row, make_double2(ar, ai), acc);
-    }
-    __syncthreads();
+    if (row >= 0) row_epilogue<MODE>(a, row, make_double2(ar, ai), acc);
   }
   mode_finalize<MODE>(a, acc);
 }
@@ -413,6 +441,13 @@ __global__ void __launch_bounds__(TPB) k_update_xr(int n, KrylovCtrl* ctrl, doub
   }
 }
 
+// evicts L2 with clean lines (a memset would leave dirty lines whose write-back overlaps the timed kernel)
+__global__ void k_flush_l2(const double2* __restrict__ p, size_t n, double* sink) {
+  double acc = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc += p[i].x;
+  if (acc == 1.2345e300) *sink = acc;
+}
+
 __global__ void k_set_ic(int n, const double* __restrict__ ic, double2* __restrict__ u) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) u[i] = make_double2(ic[i], 0.0);
@@ -439,12 +474,34 @@ inline int spmv_grid(int n, int lanes) {
   return std::max(1, std::min((n + rpb - 1) / rpb, BT_NUM_SMS * 16));
 }
 
+constexpr int SELL_UNR_DEFAULT = 4;
+constexpr int SELL_MINB_DEFAULT = 3;
+
 template <int MODE>
-void launch_spmv(int lanes, const SpmvArgs& a, cudaStream_t st) {
-  if (lanes == 0) {   // stream variant
-    int g = std::max(1, std::min(a.nblk, BT_NUM_SMS * 16));
-    k_spmv_stream<MODE><<<g, TPB, 0, st>>>(a);
+void launch_spmv(int lanes, SpmvArgs a, cudaStream_t st) {
+  a.use_sell = lanes == 0 || lanes >= 100;
+  if (lanes == 0) {   // SELL-32
+    int g = std::max(1, std::min((a.nslice + TPB / 32 - 1) / (TPB / 32), BT_NUM_SMS * SELL_MINB_DEFAULT));
+    k_spmv_sell<MODE, SELL_UNR_DEFAULT, SELL_MINB_DEFAULT><<<g, TPB, 0, st>>>(a);
     return;
+  }
+  if (MODE == MODE_PLAIN && lanes >= 100) {   // tuning variants, bench hook only: lanes = 100*UNR/4 + MINB
+    const int nb = (a.nslice + TPB / 32 - 1) / (TPB / 32);
+#define SELL_CASE(code, unr, minb)                                                         \
+  case code:                                                                               \
+    k_spmv_sell<MODE_PLAIN, unr, minb><<<std::max(1, std::min(nb, BT_NUM_SMS * minb)), TPB, 0, st>>>(a); \
+    return;
+    switch (lanes) {
+      SELL_CASE(102, 4, 2)
+      SELL_CASE(103, 4, 3)
+      SELL_CASE(104, 4, 4)
+      SELL_CASE(106, 4, 6)
+      SELL_CASE(202, 8, 2)
+      SELL_CASE(203, 8, 3)
+      SELL_CASE(204, 8, 4)
+      default: throw BtError{BTFEM_EINVAL, "unknown SELL tuning variant"};
+    }
+#undef SELL_CASE
   }
   int g = spmv_grid(a.n, lanes);
   switch (lanes) {
@@ -452,7 +509,7 @@ void launch_spmv(int lanes, const SpmvArgs& a, cudaStream_t st) {
     case 8: k_spmv<8, MODE><<<g, TPB, 0, st>>>(a); break;
     case 16: k_spmv<16, MODE><<<g, TPB, 0, st>>>(a); break;
     case 32: k_spmv<32, MODE><<<g, TPB, 0, st>>>(a); break;
-    default: throw BtError{BTFEM_EINVAL, "lanes must be 0 (stream), 4, 8, 16 or 32"};
+    default: throw BtError{BTFEM_EINVAL, "lanes must be 0 (SELL-32), 4, 8, 16 or 32"};
   }
 }
 
@@ -462,8 +519,12 @@ SpmvArgs base_args(btfem* h) {
   a.n = (int)h->ndof;
   a.rowptr = h->d_rowptr.p;
   a.colidx = h->d_colidx.p;
-  a.nblk = (int)h->n_rowblk;
-  a.blk_row = h->d_blk_row.p;
+  a.nslice = (int)h->n_slice;
+  a.slice_ptr = h->d_slice_ptr.p;
+  a.sell_row = h->d_sell_row.p;
+  a.sell_col = h->d_sell_col.p;
+  a.PJs = h->d_PJs.p;
+  a.QJs = h->d_QJs.p;
   a.PJ = h->d_PJ.p;
   a.QJ = h->d_QJ.p;
   a.cA = h->d_cA.p;
@@ -497,12 +558,21 @@ void bt_combine(btfem* h, double dt, double theta, const double g[3], int pc) {
   h->d_QJ.alloc(h->nnz);
   h->d_dinv.alloc(n);
   if (h->periodic) h->d_Bhat.alloc(h->nnz);
+  if (h->n_slice) {   // padding entries stay (0,0)
+    if (h->d_PJs.n != (size_t)h->nnz_sell) {
+      h->d_PJs.alloc(h->nnz_sell);
+      h->d_QJs.alloc(h->nnz_sell);
+      h->d_PJs.zero(st);
+      h->d_QJs.zero(st);
+    }
+  }
   k_pdiag<<<(n + TPB - 1) / TPB, TPB, 0, st>>>(n, h->d_diagpos.p, h->d_vals[0].p, h->d_vals[1].p, h->d_vals[2].p,
                                                 h->d_vals[6].p, h->d_vals[7].p, 1.0 / dt, theta, pc, h->d_dinv.p);
   k_combine<<<(int)((h->nnz + TPB - 1) / TPB), TPB, 0, st>>>(
       h->nnz, h->d_rowidx.p, h->d_vals[0].p, h->d_vals[1].p, h->d_vals[2].p, h->d_vals[6].p, h->d_vals[7].p,
       h->d_vals[3].p, h->d_vals[4].p, h->d_vals[5].p, 1.0 / dt, theta, g[0], g[1], g[2], h->d_dinv.p, h->d_PJ.p,
-      h->d_QJ.p, h->periodic ? h->d_Bhat.p : nullptr);
+      h->d_QJ.p, h->periodic ? h->d_Bhat.p : nullptr, h->d_rowptr.p, h->d_sell_slot.p, h->d_slice_ptr.p,
+      h->n_slice ? h->d_PJs.p : nullptr, h->n_slice ? h->d_QJs.p : nullptr);
   BT_CUDA(cudaGetLastError());
   h->comb_dt = dt; h->comb_theta = theta; h->comb_pc = pc;
   h->comb_g[0] = g[0]; h->comb_g[1] = g[1]; h->comb_g[2] = g[2];
@@ -533,9 +603,12 @@ void bt_spmv_bench(btfem* h, double dt, double theta, double c, const double g[3
   dx.alloc(h->ndof);
   dy.alloc(h->ndof);
   k_set_ic<<<((int)h->ndof + TPB - 1) / TPB, TPB, 0, st>>>((int)h->ndof, h->d_ic_dof.p, dx.p);
-  DevArray<char> scratch;
-  const size_t flush_bytes = (size_t)512 << 20;
-  if (flush_l2) scratch.alloc(flush_bytes);
+  DevArray<double2> scratch;
+  const size_t flush_n = ((size_t)512 << 20) / sizeof(double2);
+  if (flush_l2) {
+    scratch.alloc(flush_n);
+    scratch.zero(st);
+  }
   SpmvArgs a = base_args(h);
   a.x_plain = dx.p;
   a.y_plain = dy.p;
@@ -548,7 +621,7 @@ void bt_spmv_bench(btfem* h, double dt, double theta, double c, const double g[3
   double total = 0.0;
   if (flush_l2) {
     for (int i = 0; i < nrep; ++i) {
-      BT_CUDA(cudaMemsetAsync(scratch.p, i & 0xff, flush_bytes, st));
+      k_flush_l2<<<BT_NUM_SMS * 8, TPB, 0, st>>>(scratch.p, flush_n, h->d_partials.p);
       BT_CUDA(cudaEventRecord(e0, st));
       launch_spmv<MODE_PLAIN>(lanes, a, st);
       BT_CUDA(cudaEventRecord(e1, st));

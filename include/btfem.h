@@ -97,13 +97,13 @@ int btfem_get_lumped_mass(btfem_t* h, double* out /*[ndof]*/);   /* 1^T M: signa
 int btfem_spmv(btfem_t* h, double dt, double theta, double c, const double gdir[3],
                const double* x /*[2*ndof]*/, double* y /*[2*ndof]*/);
 /* Time `nrep` launches of the fused SpMV kernel on device-resident data (bench hook).
- * lanes: 0 = stream variant (row blocks staged through shared memory), or threads per row (4, 8, 16, 32).
- * flush_l2 != 0: a 512 MiB memset precedes every launch and
+ * lanes: 0 = SELL-32 layout (default), or CSR with that many threads per row (4, 8, 16, 32).
+ * flush_l2 != 0: a kernel reading a 512 MiB scratch buffer precedes every launch (evicts L2) and
  * each launch is timed on its own; otherwise the nrep launches are timed back to back.
  * Returns average ms per launch. */
 int btfem_spmv_bench(btfem_t* h, double dt, double theta, double c, const double gdir[3],
                      int32_t lanes, int32_t nrep, int32_t flush_l2, double* ms_per_launch);
-/* SpMV variant used by the solver: 0 = stream (default), else threads per row */
+/* SpMV variant used by the solver: 0 = SELL-32 (default), else CSR with `lanes` threads per row */
 int btfem_set_lanes(btfem_t* h, int32_t lanes);
 
 /* ---- the theta loop ---------------------------------------------------------------------

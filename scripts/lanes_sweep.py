@@ -17,7 +17,7 @@ fem.set_permeability(1e-5)
 fem.assemble()
 b = 20.0 * fem.nnz + 36.0 * fem.ndof
 print("ndof", fem.ndof, "nnz", fem.nnz, "nnz/row %.2f" % (fem.nnz / fem.ndof), "alg MB %.1f" % (b / 1e6))
-for lanes in (0, 4, 8, 16):
+for lanes in (0, 102, 103, 104, 106, 202, 203, 204, 4, 8):
     for fl in (True, False):
         ms = fem.spmv_bench(200.0, 0.5, 1.5e-5, [0, 1, 0], lanes=lanes, nrep=30, flush_l2=fl)
-        print("lanes %2d flush %-5s ms %.4f GB/s %.0f" % (lanes, fl, ms, b / ms / 1e6))
+        print("lanes %3d flush %-5s ms %.4f GB/s %.0f" % (lanes, fl, ms, b / ms / 1e6))
