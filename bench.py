@@ -236,8 +236,8 @@ def main():
     # ---- e2e through the reference-facing API, host buffers -> signal
     def e2e_once():
         mesh = dl.Mesh(xyz, tets)
+        mesh.device = local_rank
         md = dl.MyDomain(mesh, mp)
-        md.device = local_rank
         md.phase = phase
         md.IsDomainMultiple = True
         md.kappa = 1e-5

@@ -59,6 +59,8 @@ def load_library(path=None):
         "btfem_last_error": (C.c_char_p, [H]),
         "btfem_version": (C.c_int, []),
         "btfem_set_mesh": (C.c_int, [H, C.c_int64, _c_double_p, C.c_int64, _c_int32_p, _c_int32_p]),
+        "btfem_set_phase": (C.c_int, [H, _c_int32_p]),
+        "btfem_get_mesh_stats": (C.c_int, [H, _c_double_p, _c_double_p]),
         "btfem_set_diffusion": (C.c_int, [H, C.c_int, _c_double_p]),
         "btfem_set_relaxation": (C.c_int, [H, C.c_int, _c_double_p]),
         "btfem_set_permeability": (C.c_int, [H, C.c_int, _c_double_p, C.c_int32, _c_int32_p]),
@@ -137,6 +139,19 @@ class BTFem:
         self.two_comp = ph is not None
         self._ck(self.lib.btfem_set_mesh(self.h, self.nv, _dp(xyz), self.nc, _ip(tets), None if ph is None else _ip(ph)))
         self.h2d_bytes = xyz.nbytes + tets.nbytes + (0 if ph is None else ph.nbytes)
+
+    def set_phase(self, phase=None):
+        ph = None if phase is None else np.ascontiguousarray(phase, dtype=np.int32)
+        if ph is not None:
+            assert len(ph) == self.nc
+        self.two_comp = ph is not None
+        self._ck(self.lib.btfem_set_phase(self.h, None if ph is None else _ip(ph)))
+        self.h2d_bytes += 0 if ph is None else ph.nbytes
+
+    def mesh_stats(self):
+        lo, hi = C.c_double(), C.c_double()
+        self._ck(self.lib.btfem_get_mesh_stats(self.h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
 
     def set_diffusion(self, D):
         D = np.asarray(D, dtype=np.float64)

@@ -83,6 +83,31 @@ int btfem_set_mesh(btfem_t* h, int64_t nv, const double* xyz, int64_t nc, const 
   });
 }
 
+int btfem_set_phase(btfem_t* h, const int32_t* phase) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->nc > 0, "set the mesh first");
+    if (phase)
+      for (int64_t i = 0; i < h->nc; ++i) BT_REQUIRE(phase[i] == 0 || phase[i] == 1, "phase must be 0 or 1");
+    invalidate(h);
+    h->two_comp = phase != nullptr;
+    if (phase) {
+      h->h_phase.assign(phase, phase + h->nc);
+      h->d_phase.upload(phase, h->nc, h->stream);
+      BT_CUDA(cudaStreamSynchronize(h->stream));
+    } else {
+      h->h_phase.clear();
+      h->d_phase.release();
+    }
+  });
+}
+
+int btfem_get_mesh_stats(btfem_t* h, double* hmin, double* hmax) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->nc > 0 && hmin && hmax, "set the mesh first");
+    bt_mesh_stats(h, hmin, hmax);
+  });
+}
+
 int btfem_set_diffusion(btfem_t* h, int kind, const double* D) {
   return guarded(h, [&] {
     BT_REQUIRE(h->nc > 0, "set the mesh first");

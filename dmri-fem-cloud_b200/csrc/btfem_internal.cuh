@@ -164,6 +164,7 @@ struct btfem {
 };
 
 // setup.cu
+void bt_mesh_stats(btfem* h, double* hmin, double* hmax);
 void bt_build_dofmap(btfem* h);
 void bt_build_facets(btfem* h);
 void bt_build_pattern(btfem* h);

@@ -35,6 +35,47 @@ struct TempStorage {
   }
 };
 
+// ------------------------------------------------------------------------------------ mesh statistics
+
+// per-block min / max over cells of the longest edge (exact: min/max are order independent)
+__global__ void __launch_bounds__(TPB) k_cell_sizes(int64_t nc, const int32_t* __restrict__ tets,
+                                                    const double* __restrict__ xyz, double* __restrict__ out) {
+  __shared__ double s_min[TPB / 32], s_max[TPB / 32];
+  double lo = 1e300, hi = 0.0;
+  for (int64_t c = blockIdx.x * (int64_t)TPB + threadIdx.x; c < nc; c += (int64_t)gridDim.x * TPB) {
+    int4 t = *reinterpret_cast<const int4*>(tets + 4 * c);
+    int v[4] = {t.x, t.y, t.z, t.w};
+    double x[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) x[k][d] = xyz[3 * (int64_t)v[k] + d];
+    double h2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = i + 1; j < 4; ++j) {
+        double dx = x[i][0] - x[j][0], dy = x[i][1] - x[j][1], dz = x[i][2] - x[j][2];
+        h2 = fmax(h2, dx * dx + dy * dy + dz * dz);
+      }
+    double hc = sqrt(h2);
+    lo = fmin(lo, hc);
+    hi = fmax(hi, hc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = lo; s_max[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < TPB / 32; ++w) { lo = fmin(lo, s_min[w]); hi = fmax(hi, s_max[w]); }
+    out[2 * blockIdx.x] = lo;
+    out[2 * blockIdx.x + 1] = hi;
+  }
+}
+
 // ------------------------------------------------------------------------------------ facets
 
 __global__ void k_gen_facets(int64_t nc, const int32_t* __restrict__ tets, FacetKey* __restrict__ keys) {
@@ -364,6 +405,23 @@ __global__ void k_lumped(int64_t ndof, const int32_t* __restrict__ rowptr, const
 }  // namespace
 
 // ===================================================================================== host side
+
+void bt_mesh_stats(btfem* h, double* hmin, double* hmax) {
+  const int grid = (int)std::min<int64_t>(nblocks(h->nc), BT_NUM_SMS * 8);
+  DevArray<double> part;
+  part.alloc(2 * grid);
+  k_cell_sizes<<<grid, TPB, 0, h->stream>>>(h->nc, h->d_tets.p, h->d_xyz.p, part.p);
+  BT_CUDA(cudaGetLastError());
+  std::vector<double> hp(2 * grid);
+  part.download(hp.data(), h->stream);
+  double lo = 1e300, hi = 0.0;
+  for (int i = 0; i < grid; ++i) {
+    lo = std::min(lo, hp[2 * i]);
+    hi = std::max(hi, hp[2 * i + 1]);
+  }
+  *hmin = lo;
+  *hmax = hi;
+}
 
 void bt_build_dofmap(btfem* h) {
   const int64_t nv = h->nv, nc = h->nc;

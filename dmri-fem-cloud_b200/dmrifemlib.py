@@ -172,8 +172,12 @@ class KrylovSolver:
 class MyDomain():
     def __init__(self, mymesh, mri_para):
         self.porder = 1
-        self.hmin = mymesh.hmin()
-        self.hmax = mymesh.hmax()
+        # the mesh goes to the GPU here; hmin/hmax (MPI.min/max of mesh.hmin()/hmax(), DmriFemLib.py:588-589)
+        # are reductions over the cells and are computed there
+        self.device = getattr(mymesh, "device", 0)
+        self._fem = _bt.BTFem(self.device)
+        self._fem.set_mesh(mymesh.xyz, mymesh.tets, None)
+        self.hmin, self.hmax = self._fem.mesh_stats()
         self.tol = 1e-2 * self.hmin
         self.gdim = 3
         self.tdim = 3
@@ -195,8 +199,6 @@ class MyDomain():
         self.kappa_marker = None   # with a (nmark,nmark) kappa table: cell markers (variable permeability)
         self.D = None
         self.T2_cell = None        # optional DG0 T2 (GCloudDmriSolver.py:165-169)
-        self.device = 0
-        self._fem = None
 
     def ImposeDiffusionTensor(self, k00, k01, k02, k10, k11, k12, k20, k21, k22):
         print("Impose Diffusion Tensor ...")
@@ -224,13 +226,13 @@ class MyDomain():
 
     # --- GPU problem object, (re)built when coefficients change
     def fem(self, mri_para, ic=None):
-        fem = _bt.BTFem(self.device)
+        fem = self._fem
         phase = None
         if self.IsDomainMultiple:
             if self.phase is None:
                 raise RuntimeError("IsDomainMultiple requires mydomain.phase")
             phase = np.asarray(self.phase).astype(np.int32)
-        fem.set_mesh(self.mymesh.xyz, self.mymesh.tets, phase)
+        fem.set_phase(phase)
         D = self.D if self.D is not None else getattr(self, "D0", None)
         if D is None:
             raise RuntimeError("mydomain.D is not set")
@@ -247,7 +249,6 @@ class MyDomain():
                              [self.xmin, self.ymin, self.zmin], [self.xmax, self.ymax, self.zmax])
         fem.set_initial(ic)
         fem.assemble()
-        self._fem = fem
         return fem
 
 

@@ -60,6 +60,12 @@ int btfem_version(void);
 int btfem_set_mesh(btfem_t* h, int64_t nv, const double* xyz /*[nv*3]*/, int64_t nc,
                    const int32_t* tets /*[nc*4]*/, const int32_t* phase /*[nc] or NULL*/);
 
+/* Replace only the phase function of the current mesh (NULL = one compartment). */
+int btfem_set_phase(btfem_t* h, const int32_t* phase /*[nc] or NULL*/);
+/* mesh.hmin()/hmax() as used by MyDomain (DmriFemLib.py:588-589): min / max over cells of the cell size,
+ * cell size = longest edge (DOLFIN >= 2017 Cell::h, third party).  Computed on the GPU. */
+int btfem_get_mesh_stats(btfem_t* h, double* hmin, double* hmax);
+
 /* Diffusion: kind 0 = scalar D0 (`-K`, GCloudDmriSolver.py:212-215), 1 = per-cell scalar [nc],
  * 2 = per-cell full tensor [nc*9] row-major d00..d22 (ImposeDiffusionTensor, DmriFemLib.py:611-616). */
 int btfem_set_diffusion(btfem_t* h, int kind, const double* D);

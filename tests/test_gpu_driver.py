@@ -1,0 +1,93 @@
+"""GPU tests of the reference-facing layer: the DmriFemLib mirror and the GCloudDmriSolver CLI."""
+import os
+
+import numpy as np
+import pytest
+import sympy as sp
+
+import bt_oracle as orc
+from conftest import REF_MESH_DIR
+from dmri_fem_cloud_b200 import cli, dmrifemlib as dl, meshes
+
+pytestmark = pytest.mark.gpu
+
+
+def test_mesh_stats_match_numpy():
+    rng = np.random.default_rng(0)
+    xyz, tets = meshes.cylinder(3.0, 10.0, nr=3, nsec=10, nz=6)
+    xyz = xyz + 0.02 * rng.standard_normal(xyz.shape)
+    m = dl.Mesh(xyz, tets)
+    mp = dl.MRI_parameters()
+    mp.qvalue = 0.0
+    md = dl.MyDomain(m, mp)
+    assert md.hmin == m.hmin() and md.hmax == m.hmax()          # same fp64 operations, exact
+
+
+def _pgse(mp, delta, Delta):
+    mp.delta, mp.Delta = delta, Delta
+    mp.T = Delta + delta
+    mp.fs_sym = sp.Piecewise((1., mp.s < delta), (0., mp.s < Delta), (-1., mp.s < mp.T), (0., True))
+
+
+def test_driver_two_compartment_matches_oracle(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    xyz, tets, marker = meshes.layered_cylinder((5.0, 7.5, 10.0), 5.0, (3, 2, 2), 12, 2)
+    phase = (marker % 2).astype(np.int32)
+    mesh = dl.Mesh(xyz, tets)
+    mp = dl.MRI_parameters()
+    mp.bvalue = 1000
+    _pgse(mp, 2000.0, 6000.0)
+    mp.set_gradient_dir(mesh, 0, 1, 0)
+    mp.Apply()
+    sim = dl.MRI_simulation()
+    sim.k = 200
+    md = dl.MyDomain(mesh, mp)
+    md.phase, md.IsDomainMultiple, md.kappa = phase, True, 1e-5
+    md.Apply()
+    md.D0 = 3e-3
+    md.D = md.D0
+    ls = dl.KrylovSolver("bicgstab", "jacobi")
+    ls.parameters["relative_tolerance"] = 1e-12
+    ls.parameters["absolute_tolerance"] = 1e-15
+    sim.solve(md, mp, ls)
+    text = dl.PostProcessing(md, mp, sim, None, '')
+    ops = orc.assemble(xyz, tets, phase, D=3e-3, invT2=1e-16, kappa=1e-5)
+    seq = orc.pgse(2000.0, 6000.0)
+    ref = orc.theta_solve(ops, seq, seq.q_from_b(1000.0), [0, 1, 0], 200.0, solver="lu")
+    assert abs(mp.qvalue - seq.q_from_b(1000.0)) <= 1e-15 * mp.qvalue
+    assert abs(sim.stats["signal"] - ref["signal"]) <= 1e-8 * abs(ref["signal"])
+    assert "Normalized signal: %.6e" % (ref["signal"] / ref["voi"]) in text
+    assert os.path.exists("log.txt")
+    # solution in the reference's blocked layout
+    want = orc.expand_to_reference_layout(ops, ref["u"]).reshape(4, -1)
+    assert np.max(np.abs(sim.u_0 - want)) <= 1e-8 * np.max(np.abs(want))
+
+
+def test_cli_config0_npz(tmp_path, monkeypatch, capsys):
+    """BASELINE configs[0]: -M 0 -b 1000 -d 10600 -D 43100 -k 200 -K 3e-3 -gdir 1 0 0 on a small cylinder."""
+    monkeypatch.chdir(tmp_path)
+    xyz, tets = meshes.cylinder(3.0, 25.0, nr=2, nsec=8, nz=8)
+    np.savez("cyl.npz", xyz=xyz, tets=tets)
+    text = cli.main(["prog", "-f", "cyl.npz", "-M", "0", "-b", "1000", "-d", "10600", "-D", "43100", "-k", "200",
+                     "-K", "3e-3", "-gdir", "1", "0", "0"])
+    ops = orc.assemble(xyz, tets, D=3e-3, invT2=1e-16)
+    seq = orc.pgse(10600.0, 43100.0)
+    ref = orc.theta_solve(ops, seq, seq.q_from_b(1000.0), [1, 0, 0], 200.0, solver="lu")
+    assert ref["n_steps"] == 270
+    got = float(text.split("Normalized signal: ")[1].split(",")[0])
+    assert abs(got - ref["signal"] / ref["voi"]) <= 2e-6 * got      # CLI tolerances (rtol 1e-9) + %.6e print
+    assert "b: 1000.000, g: 0.056, q: 1.500e-05" in text            # ExplicitImplementation.ipynb cell 10 prints q=1.499786e-05
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_MESH_DIR), reason="reference meshes not present on this box")
+def test_cli_reference_msh_fixture(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    path = os.path.join(REF_MESH_DIR, "cyl6_r_3E_6_vol.msh.zip")
+    text = cli.main(["prog", "-f", path, "-M", "0", "-b", "1000", "-k", "200", "-K", "3e-3", "-gdir", "1", "0", "0"])
+    xyz, tets, _ = meshes.read_gmsh2(path)
+    assert len(xyz) == 54 and len(tets) == 123
+    ops = orc.assemble(xyz, tets, D=3e-3, invT2=1e-16)
+    seq = orc.pgse(10600.0, 43100.0)
+    ref = orc.theta_solve(ops, seq, seq.q_from_b(1000.0), [1, 0, 0], 200.0, solver="lu")
+    got = float(text.split("Normalized signal: ")[1].split(",")[0])
+    assert abs(got - ref["signal"] / ref["voi"]) <= 2e-6 * got
