@@ -145,7 +145,20 @@ struct btfem {
   // ---- per-solve state
   DevArray<double2> d_PJ, d_QJ;
   DevArray<double> d_Bhat, d_dinv;
-  DevArray<double2> d_u, d_r, d_rp, d_p, d_v, d_s, d_t;
+  // the seven Krylov vectors live in ONE slab so that a single L2 access-policy window can pin them:
+  // 7 x 8 MB at 1 M DOFs fits the 126 MB L2 while the matrix streams past with evict-first loads
+  DevArray<double2> d_vecs;
+  struct VecView {
+    double2* p = nullptr;
+    size_t n = 0;
+    void zero(cudaStream_t s) { if (n) BT_CUDA(cudaMemsetAsync(p, 0, n * sizeof(double2), s)); }
+    void download(double2* dst, cudaStream_t s) const {
+      if (n) BT_CUDA(cudaMemcpyAsync(dst, p, n * sizeof(double2), cudaMemcpyDeviceToHost, s));
+      BT_CUDA(cudaStreamSynchronize(s));
+    }
+  } d_u, d_r, d_rp, d_p, d_v, d_s, d_t;
+  bool l2_window_set = false;
+  cudaAccessPolicyWindow l2_window{};
   DevArray<double> d_cA, d_cb, d_Fb;
   DevArray<double> d_partials;     // [8][BT_MAX_PARTIALS]
   DevArray<KrylovCtrl> d_ctrl;

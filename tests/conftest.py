@@ -14,6 +14,7 @@ entry.load_package()
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: long CPU test, excluded by default (run with --runslow)")
 
 
 @pytest.fixture(scope="session")
@@ -31,3 +32,16 @@ def built_lib():
 
 REF_MESH_DIR = "/root/reference/comri/meshes"
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_addoption(parser):
+    parser.addoption("--runslow", action="store_true", default=False)
+
+
+def pytest_collection_modifyitems(config, items):
+    if config.getoption("--runslow"):
+        return
+    skip = pytest.mark.skip(reason="slow: pass --runslow")
+    for item in items:
+        if "slow" in item.keywords:
+            item.add_marker(skip)
