@@ -65,6 +65,7 @@ def load_library(path=None):
         "btfem_set_relaxation": (C.c_int, [H, C.c_int, _c_double_p]),
         "btfem_set_permeability": (C.c_int, [H, C.c_int, _c_double_p, C.c_int32, _c_int32_p]),
         "btfem_set_periodic": (C.c_int, [H, _c_int32_p, C.c_double, C.c_double, _c_double_p, _c_double_p]),
+        "btfem_set_periodic_gather": (C.c_int, [H, C.c_int64, _c_int32_p, _c_int32_p, _c_double_p, _c_double_p]),
         "btfem_set_initial": (C.c_int, [H, _c_double_p]),
         "btfem_assemble": (C.c_int, [H]),
         "btfem_get_sizes": (C.c_int, [H, _c_int64_p, _c_int64_p, _c_int64_p, _c_int64_p]),
@@ -187,6 +188,13 @@ class BTFem:
         lo = np.ascontiguousarray(lo, dtype=np.float64)
         hi = np.ascontiguousarray(hi, dtype=np.float64)
         self._ck(self.lib.btfem_set_periodic(self.h, _ip(p), float(kappa_e), float(tol), _dp(lo), _dp(hi)))
+
+    def set_periodic_gather(self, dof, src, w, dx):
+        dof = np.ascontiguousarray(dof, dtype=np.int32)
+        src = np.ascontiguousarray(src, dtype=np.int32)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        dx = np.ascontiguousarray(dx, dtype=np.float64)
+        self._ck(self.lib.btfem_set_periodic_gather(self.h, len(dof), _ip(dof), _ip(src), _dp(w), _dp(dx)))
 
     def set_initial(self, ic=None):
         if ic is None:

@@ -24,6 +24,7 @@ int guarded(btfem* h, F&& f) {
 
 void invalidate(btfem* h) {
   h->assembled = false;
+  h->n_pb = 0;
   h->comb_dt = -1;
   h->have_solution = false;
 }
@@ -165,6 +166,24 @@ int btfem_set_periodic(btfem_t* h, const int32_t pdir[3], double kappa_e, double
   });
 }
 
+int btfem_set_periodic_gather(btfem_t* h, int64_t nb, const int32_t* dof, const int32_t* src, const double* w,
+                              const double* dx) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->assembled, "call btfem_assemble first");
+    BT_REQUIRE(nb >= 0 && (nb == 0 || (dof && src && w && dx)), "null argument");
+    for (int64_t i = 0; i < nb; ++i) {
+      BT_REQUIRE(dof[i] >= 0 && dof[i] < h->ndof, "periodic gather: dof out of range");
+      for (int k = 0; k < 3; ++k) BT_REQUIRE(src[3 * i + k] < h->ndof, "periodic gather: source out of range");
+    }
+    h->n_pb = nb;
+    h->d_pb_dof.upload(dof, nb, h->stream);
+    h->d_pb_src.upload(src, 3 * nb, h->stream);
+    h->d_pb_w.upload(w, 3 * nb, h->stream);
+    h->d_pb_dx.upload(dx, 3 * nb, h->stream);
+    BT_CUDA(cudaStreamSynchronize(h->stream));
+  });
+}
+
 int btfem_set_initial(btfem_t* h, const double* ic) {
   return guarded(h, [&] {
     BT_REQUIRE(h->nv > 0, "set the mesh first");
@@ -181,6 +200,7 @@ int btfem_assemble(btfem_t* h) {
     bt_build_facets(h);
     bt_build_pattern(h);
     bt_assemble_values(h);
+    bt_build_periodic(h);
     h->assembled = true;
   });
 }

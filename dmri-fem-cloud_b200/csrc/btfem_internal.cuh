@@ -168,12 +168,13 @@ struct btfem {
   bool have_solution = false;
   int lanes = 0;                   // fused SpMV variant: 0 = SELL-32 (default), else CSR with `lanes` threads per row
 
-  // periodic gather operator G: u_bc[b] = phase * sum_k w[b][k] * u[idx[b][k]]
+  // weak pseudo-periodic BC: gather operator (per boundary dof: 3 sources, weights, displacement)
   int64_t n_pb = 0;
   DevArray<int32_t> d_pb_dof, d_pb_src;   // [n_pb], [n_pb*3]
-  DevArray<double> d_pb_w, d_pb_gdx;      // [n_pb*3], [n_pb] (g . dx premultiplied per direction at solve)
-  DevArray<double> d_pb_dx;               // [n_pb*3] displacement to the mirrored point
-  DevArray<double2> d_ubc;                // [ndof] (zero off the periodic faces)
+  DevArray<double> d_pb_w, d_pb_dx;       // [n_pb*3], [n_pb*3]
+  DevArray<int32_t> d_pb_rows;            // rows with a nonzero in B (they receive (1-theta)*B*u_bc)
+  int64_t n_pb_rows = 0;
+  DevArray<double2> d_ubc, d_rhs_add;     // [ndof] dense, zero off the boundary
 };
 
 // setup.cu

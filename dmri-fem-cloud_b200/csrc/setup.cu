@@ -664,8 +664,15 @@ void bt_assemble_values(btfem* h) {
   BT_CUDA(cudaStreamSynchronize(st));
 }
 
+// rows that have a nonzero in B: only they receive the (1-theta)*B*u_bc term of the weak periodic BC
 void bt_build_periodic(btfem* h) {
-  // the gather operator of the weak pseudo-periodic BC is built in the Python host layer
-  // (geometry search, once per mesh) and handed over through btfem_set_periodic_gather
-  (void)h;
+  h->n_pb_rows = 0;
+  if (!h->periodic || h->n_bfacet == 0) return;
+  std::vector<int32_t> bd(3 * h->n_bfacet);
+  h->d_bf_dofs.download(bd.data(), h->stream);
+  std::sort(bd.begin(), bd.end());
+  bd.erase(std::unique(bd.begin(), bd.end()), bd.end());
+  h->n_pb_rows = (int64_t)bd.size();
+  h->d_pb_rows.upload(bd.data(), bd.size(), h->stream);
+  BT_CUDA(cudaStreamSynchronize(h->stream));
 }

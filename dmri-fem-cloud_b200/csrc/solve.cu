@@ -453,6 +453,49 @@ __global__ void k_flush_l2(const double2* __restrict__ p, size_t n, double* sink
   if (acc == 1.2345e300) *sink = acc;
 }
 
+// weak pseudo-periodic BC, per time step (WeakPseudoPeriodic_*.eval, DmriFemLib.py:270-321):
+// u_bc[dof] = exp(i*q*(g.dx)*F(t_p)) * sum_k w_k u[src_k]
+__global__ void k_periodic_ubc(int nb, const KrylovCtrl* ctrl, const double* __restrict__ Fb, double q, double gx,
+                               double gy, double gz, const int32_t* __restrict__ dof, const int32_t* __restrict__ src,
+                               const double* __restrict__ w, const double* __restrict__ dx,
+                               const double2* __restrict__ u, double2* __restrict__ ubc) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  double ar = 0.0, ai = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    int s = src[3 * b + k];
+    if (s >= 0) {
+      double2 uv = u[s];
+      ar += w[3 * b + k] * uv.x;
+      ai += w[3 * b + k] * uv.y;
+    }
+  }
+  const double th = q * (gx * dx[3 * b] + gy * dx[3 * b + 1] + gz * dx[3 * b + 2]) * Fb[ctrl->step_next];
+  double sn, cs;
+  sincos(th, &sn, &cs);
+  ubc[dof[b]] = make_double2(ar * cs - ai * sn, ar * sn + ai * cs);
+}
+
+// rhs_add[row] = scale * sum_k Bhat[k] * u_bc[col[k]] for the rows that touch B
+__global__ void k_periodic_rhs(int nrows, const int32_t* __restrict__ rows, const int32_t* __restrict__ rowptr,
+                               const int32_t* __restrict__ colidx, const double* __restrict__ Bhat, double scale,
+                               const double2* __restrict__ ubc, double2* __restrict__ rhs_add) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  const int r = rows[i];
+  double ar = 0.0, ai = 0.0;
+  for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+    const double bv = Bhat[k];
+    if (bv != 0.0) {
+      const double2 v = ubc[colidx[k]];
+      ar += bv * v.x;
+      ai += bv * v.y;
+    }
+  }
+  rhs_add[r] = make_double2(scale * ar, scale * ai);
+}
+
 __global__ void k_set_ic(int n, const double* __restrict__ ic, double2* __restrict__ u) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) u[i] = make_double2(ic[i], 0.0);
@@ -684,7 +727,11 @@ void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_
   BT_REQUIRE(sa->nsteps >= 0 && sa->dt > 0, "bad nsteps/dt");
   BT_REQUIRE(sa->theta > 0 && sa->theta <= 1, "theta must be in (0,1]");
   BT_REQUIRE(sa->ksp == BTFEM_KSP_BICGSTAB, "only BTFEM_KSP_BICGSTAB is implemented");
-  BT_REQUIRE(!h->periodic, "weak pseudo-periodic BC not implemented yet");
+  const bool periodic = h->periodic && h->n_pb_rows > 0;
+  if (periodic) {
+    BT_REQUIRE(sa->Fb != nullptr, "periodic BC needs Fb (F(t_{n-1}) per step)");
+    BT_REQUIRE(h->n_pb > 0, "periodic BC: call btfem_set_periodic_gather after btfem_assemble");
+  }
   cudaStream_t st = h->stream;
   const int n = (int)h->ndof;
   cudaEvent_t e0, e1, e2;
@@ -696,6 +743,13 @@ void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_
   ensure_vectors(h);
   h->d_cA.upload(sa->cA, sa->nsteps, st);
   h->d_cb.upload(sa->cb, sa->nsteps, st);
+  if (periodic) {
+    h->d_Fb.upload(sa->Fb, sa->nsteps, st);
+    h->d_ubc.alloc(n);
+    h->d_rhs_add.alloc(n);
+    h->d_ubc.zero(st);
+    h->d_rhs_add.zero(st);
+  }
   k_set_ic<<<(n + TPB - 1) / TPB, TPB, 0, st>>>(n, h->d_ic_dof.p, h->d_u.p);
   KrylovCtrl c0;
   memset(&c0, 0, sizeof(c0));
@@ -710,6 +764,7 @@ void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_
   BT_CUDA(cudaStreamSynchronize(st));   // h_ctrl is reused as the read-back buffer below
 
   SpmvArgs a = base_args(h);
+  if (periodic) a.rhs_add = h->d_rhs_add.p;
   const int lanes = h->lanes;
   const int vg = vec_grid(n);
 
@@ -747,6 +802,15 @@ void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_
   int last_reason = 0;
   int fail = 0;
   for (int64_t step = 0; step < sa->nsteps && !fail; ++step) {
+    if (periodic) {
+      k_periodic_ubc<<<((int)h->n_pb + TPB - 1) / TPB, TPB, 0, st>>>(
+          (int)h->n_pb, h->d_ctrl.p, h->d_Fb.p, sa->q, sa->gdir[0], sa->gdir[1], sa->gdir[2], h->d_pb_dof.p,
+          h->d_pb_src.p, h->d_pb_w.p, h->d_pb_dx.p, h->d_u.p, h->d_ubc.p);
+      k_periodic_rhs<<<((int)h->n_pb_rows + TPB - 1) / TPB, TPB, 0, st>>>(
+          (int)h->n_pb_rows, h->d_pb_rows.p, h->d_rowptr.p, h->d_colidx.p, h->d_Bhat.p, 1.0 - sa->theta,
+          h->d_ubc.p, h->d_rhs_add.p);
+      n_kernels += 2;
+    }
     launch_spmv<MODE_RHS>(lanes, a, st);
     ++n_kernels;
     if (sa->nonzero_guess) {

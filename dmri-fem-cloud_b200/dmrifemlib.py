@@ -249,6 +249,12 @@ class MyDomain():
                              [self.xmin, self.ymin, self.zmin], [self.xmax, self.ymax, self.zmax])
         fem.set_initial(ic)
         fem.assemble()
+        if sum(self.PeriodicDir) > 0:
+            from . import periodic
+            dv, dc = fem.dofmap()
+            fem.set_periodic_gather(*periodic.build_gather(
+                self.mymesh.xyz, self.mymesh.tets, phase, self.PeriodicDir,
+                [self.xmin, self.ymin, self.zmin], [self.xmax, self.ymax, self.zmax], dv, dc))
         return fem
 
 

@@ -1,0 +1,110 @@
+"""Weak pseudo-periodic boundary condition: the gather operator behind `WeakPseudoPeriodic_1c/_2c`
+(DmriFemLib.py:256-324, 386-450).
+
+For a vertex x on the min/max face of a periodic direction the reference evaluates the previous
+solution at the mirrored point x' (that coordinate replaced by the opposite face's value) by P1 point
+evaluation with extrapolation allowed, and rotates it by exp(i*q*(g.(x'-x))*F(t_p)).  If several
+directions match, the LAST one in x, y, z order wins (the assignments overwrite, :276-313).  The
+face test is |x - face| <= 1e-7 (:271).
+
+This is mesh bookkeeping done once per mesh on the host: it produces, per boundary dof, up to three
+source dofs with barycentric weights and the displacement x'-x.  The per-step arithmetic
+(u_bc = phase * sum w u, then (1-theta) * B * u_bc) runs on the GPU (csrc/solve.cu)."""
+import numpy as np
+
+FACE_TOL = 1e-7
+
+
+def _boundary_triangles(tets):
+    faces = np.array([[1, 2, 3], [0, 2, 3], [0, 1, 3], [0, 1, 2]])
+    f = np.sort(tets[:, faces], axis=2).reshape(-1, 3)
+    cell = np.repeat(np.arange(len(tets)), 4)
+    order = np.lexsort((f[:, 2], f[:, 1], f[:, 0]))
+    f, cell = f[order], cell[order]
+    same_next = np.zeros(len(f), dtype=bool)
+    same_next[:-1] = np.all(f[1:] == f[:-1], axis=1)
+    same_prev = np.zeros(len(f), dtype=bool)
+    same_prev[1:] = same_next[:-1]
+    ext = ~(same_next | same_prev)
+    return f[ext], cell[ext]
+
+
+def _locate(points2, tri_xy):
+    """For each 2-D point: containing triangle (or the closest one: extrapolation) and barycentric weights."""
+    a, b, c = tri_xy[:, 0], tri_xy[:, 1], tri_xy[:, 2]
+    d = (b[:, 1] - c[:, 1]) * (a[:, 0] - c[:, 0]) + (c[:, 0] - b[:, 0]) * (a[:, 1] - c[:, 1])
+    cen = tri_xy.mean(axis=1)
+    out_t = np.empty(len(points2), dtype=np.int64)
+    out_w = np.empty((len(points2), 3))
+    for i, p in enumerate(points2):
+        # candidates: the 16 triangles with the nearest centroids
+        k = min(16, len(cen))
+        cand = np.argpartition(((cen - p) ** 2).sum(axis=1), k - 1)[:k]
+        w0 = ((b[cand, 1] - c[cand, 1]) * (p[0] - c[cand, 0]) + (c[cand, 0] - b[cand, 0]) * (p[1] - c[cand, 1])) / d[cand]
+        w1 = ((c[cand, 1] - a[cand, 1]) * (p[0] - c[cand, 0]) + (a[cand, 0] - c[cand, 0]) * (p[1] - c[cand, 1])) / d[cand]
+        w2 = 1.0 - w0 - w1
+        W = np.stack([w0, w1, w2], axis=1)
+        best = np.argmax(W.min(axis=1))                  # inside: min weight >= 0; else least outside
+        out_t[i] = cand[best]
+        out_w[i] = W[best]
+    return out_t, out_w
+
+
+def build_gather(xyz, tets, phase, pdir, lo, hi, dof_vertex, dof_comp):
+    """Returns dof (nb,), src (nb,3) dof ids or -1, w (nb,3), dx (nb,3).
+
+    dof_vertex/dof_comp: the library's dof map (btfem_get_dofmap).  Field `comp` evaluated at a vertex
+    where that compartment is inactive is 0 (the reference's pinned dofs), i.e. src = -1."""
+    xyz = np.asarray(xyz, dtype=float)
+    nv = len(xyz)
+    vc2dof = -np.ones((nv, 2), dtype=np.int64)
+    vc2dof[dof_vertex, dof_comp] = np.arange(len(dof_vertex))
+    bf, _ = _boundary_triangles(np.asarray(tets))
+    # per vertex: (direction, side) of the LAST matching periodic direction
+    vdir = -np.ones(nv, dtype=np.int64)
+    vside = np.zeros(nv, dtype=np.int64)
+    for d in range(3):
+        if pdir[d]:
+            on_lo = np.abs(xyz[:, d] - lo[d]) <= FACE_TOL
+            on_hi = np.abs(xyz[:, d] - hi[d]) <= FACE_TOL
+            vdir[on_lo] = d
+            vside[on_lo] = 0
+            vdir[on_hi] = d                                # max face is tested second (:284, :299, :311)
+            vside[on_hi] = 1
+    src_v = -np.ones((nv, 3), dtype=np.int64)
+    wts = np.zeros((nv, 3))
+    dxs = np.zeros((nv, 3))
+    for d in range(3):
+        if not pdir[d]:
+            continue
+        other = [a for a in range(3) if a != d]
+        for side in (0, 1):
+            vs = np.nonzero((vdir == d) & (vside == side))[0]
+            if len(vs) == 0:
+                continue
+            target = hi[d] if side == 0 else lo[d]         # mirrored onto the opposite face
+            tri = bf[np.all(np.abs(xyz[bf][:, :, d] - target) <= FACE_TOL, axis=1)]
+            if len(tri) == 0:
+                continue
+            t_idx, W = _locate(xyz[vs][:, other], xyz[tri][:, :, other])
+            src_v[vs] = tri[t_idx]
+            wts[vs] = W
+            dxs[vs, d] = target - xyz[vs, d]
+    rows = np.nonzero(vdir >= 0)[0]
+    dof, src, w, dx = [], [], [], []
+    for comp in (0, 1):
+        act = rows[vc2dof[rows, comp] >= 0]
+        if len(act) == 0:
+            continue
+        dof.append(vc2dof[act, comp])
+        s = vc2dof[src_v[act], comp]
+        s[src_v[act] < 0] = -1
+        src.append(s)
+        w.append(wts[act])
+        dx.append(dxs[act])
+    if not dof:
+        return (np.zeros(0, np.int32), np.zeros((0, 3), np.int32), np.zeros((0, 3)), np.zeros((0, 3)))
+    dof = np.concatenate(dof)
+    order = np.argsort(dof, kind="stable")
+    return (dof[order].astype(np.int32), np.concatenate(src)[order].astype(np.int32),
+            np.concatenate(w)[order], np.concatenate(dx)[order])

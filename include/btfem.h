@@ -81,6 +81,11 @@ int btfem_set_permeability(btfem_t* h, int kind, const double* kappa, int32_t nm
  * bbox lo/hi as printed by MyDomain (DmriFemLib.py:593). */
 int btfem_set_periodic(btfem_t* h, const int32_t pdir[3], double kappa_e, double tol,
                        const double lo[3], const double hi[3]);
+/* Gather operator of the weak pseudo-periodic BC (WeakPseudoPeriodic_*.eval, DmriFemLib.py:270-321): for
+ * boundary dof `dof[b]`:  u_bc = exp(i*q*(g . dx[b])*F(t_p)) * sum_k w[b][k] * u[src[b][k]]   (src < 0: term is 0).
+ * Built once per mesh by the host layer (periodic.build_gather); call after btfem_assemble. */
+int btfem_set_periodic_gather(btfem_t* h, int64_t nb, const int32_t* dof /*[nb]*/, const int32_t* src /*[nb*3]*/,
+                              const double* w /*[nb*3]*/, const double* dx /*[nb*3]*/);
 /* Initial condition per vertex (Dirac_Delta interpolant, DmriFemLib.py:865-876); NULL = 1. */
 int btfem_set_initial(btfem_t* h, const double* ic /*[nv] or NULL*/);
 

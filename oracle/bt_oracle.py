@@ -417,6 +417,56 @@ def periodic_marker(xyz, pdir, lo, hi, hmin):
     return (3e-3 / hmin) * m.astype(float)
 
 
+def periodic_term(xyz, tets, ops, pdir, lo, hi, q, gdir, theta):
+    """Returns the callable (u, F_prev) -> (1-theta) * B * u_bc of ThetaMethodL_wBC*c
+    (DmriFemLib.py:71-76, 115-121) with u_bc from WeakPseudoPeriodic_*.eval (:270-321, 401-448):
+    P1 evaluation of the previous solution at the mirrored point (brute-force search over the
+    boundary triangles of the opposite face; closest triangle if none contains it, as
+    allow_extrapolation does), rotated by exp(i q (g.(x'-x)) F(t_p)); last matching direction wins."""
+    g = np.asarray(gdir, dtype=float)
+    g = g / np.linalg.norm(g)
+    bf, _ = boundary_facets(np.asarray(tets))
+    nv = len(xyz)
+    rows = []          # (dof, [(src dof or -1, weight)]*3, g.dx)
+    for v in range(nv):
+        hit = None
+        for d in range(3):
+            if pdir[d]:
+                if abs(xyz[v, d] - lo[d]) <= 1e-7:
+                    hit = (d, hi[d])
+                if abs(xyz[v, d] - hi[d]) <= 1e-7:
+                    hit = (d, lo[d])
+        if hit is None:
+            continue
+        d, target = hit
+        other = [a for a in range(3) if a != d]
+        tri = bf[np.all(np.abs(xyz[bf][:, :, d] - target) <= 1e-7, axis=1)]
+        p = xyz[v, other]
+        best, bw = None, None
+        for t in tri:
+            a, b, c = xyz[t][:, other]
+            den = (b[1] - c[1]) * (a[0] - c[0]) + (c[0] - b[0]) * (a[1] - c[1])
+            w0 = ((b[1] - c[1]) * (p[0] - c[0]) + (c[0] - b[0]) * (p[1] - c[1])) / den
+            w1 = ((c[1] - a[1]) * (p[0] - c[0]) + (a[0] - c[0]) * (p[1] - c[1])) / den
+            w = np.array([w0, w1, 1 - w0 - w1])
+            if best is None or w.min() > bw.min():
+                best, bw = t, w
+        gdx = g[d] * (target - xyz[v, d])
+        for comp in (0, 1):
+            dof = ops.vc2dof[v, comp]
+            if dof >= 0:
+                rows.append((dof, [(ops.vc2dof[t, comp], wt) for t, wt in zip(best, bw)], gdx))
+
+    def term(u, F_prev):
+        ubc = np.zeros(ops.ndof, dtype=complex)
+        for dof, srcs, gdx in rows:
+            val = sum(wt * u[s] for s, wt in srcs if s >= 0)
+            ubc[dof] = val * np.exp(1j * q * gdx * F_prev)
+        return (1.0 - theta) * (ops.B @ ubc)
+
+    return term
+
+
 # --------------------------------------------------------------------------- the theta loop
 
 

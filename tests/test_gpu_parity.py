@@ -196,3 +196,61 @@ def test_full_size_properties():
         b = fem.spmv(200.0, 0.5, 2e-5, g, y)
         ab = fem.spmv(200.0, 0.5, 2e-5, g, 2.0 * x - 3.0 * y)
         assert _relmax(ab, 2.0 * a - 3.0 * b) <= 1e-13
+
+
+def _periodic_cases():
+    rng = np.random.default_rng(11)
+    xyz, tets = meshes.box_mesh((-5, -2, -2), (5, 2, 2), 10, 4, 4)
+    yield "box_1c_px", xyz, tets, None, [1, 0, 0]
+    # opposite x-faces made non-matching: tangential jitter of the vertices on the max face only
+    xyz2 = xyz.copy()
+    on = np.abs(xyz2[:, 0] - 5.0) < 1e-12
+    inner = on & (np.abs(xyz2[:, 1]) < 1.9) & (np.abs(xyz2[:, 2]) < 1.9)
+    xyz2[inner, 1:] += 0.15 * rng.standard_normal((inner.sum(), 2))
+    yield "box_1c_px_nonmatching", xyz2, tets, None, [1, 0, 0]
+    xyz3, tets3, ph3 = meshes.ecs_slab(12, 12, 2, lx=12.0, ly=12.0, lz=1.0, ncyl=4, rmin=2.0, rmax=3.0, seed=3)
+    yield "ecs_2c_pxy", xyz3, tets3, ph3, [1, 1, 0]
+
+
+PCASES = list(_periodic_cases())
+
+
+@pytest.mark.parametrize("case", PCASES, ids=[c[0] for c in PCASES])
+def test_weak_pseudo_periodic(case):
+    """-pdir: artificial-permeability boundary matrix B and the lagged u_bc term (DmriFemLib.py:58-93,
+    256-324) against the oracle's independent restatement."""
+    from dmri_fem_cloud_b200 import periodic
+    _, xyz, tets, phase, pdir = case
+    lo, hi, hmin, hmax = orc.domain_sizes(xyz, tets)
+    kappa_e, tol = 3e-3 / hmin, 1e-2 * hmin
+    bm = orc.periodic_marker(xyz, pdir, lo, hi, hmin)
+    ops = orc.assemble(xyz, tets, phase, D=2e-3, kappa=1e-5, bnd_kappa_vertex=bm)
+    seq = orc.pgse(2000.0, 5000.0)
+    q = seq.q_from_b(800.0)
+    g = np.array([1.0, 0.5, 0.0])
+    g /= np.linalg.norm(g)
+    k = 200.0
+    per = orc.periodic_term(xyz, tets, ops, pdir, lo, hi, q, g, 0.5)
+    ref = orc.theta_solve(ops, seq, q, g, k, solver="lu", periodic=per)
+    ts = orc.time_grid(seq.T, k)
+    f = np.array([seq.f(t) for t in ts])
+    fp = np.concatenate([[f[0]], f[:-1]])
+    Fp = np.concatenate([[seq.F(0.0)], [seq.F(t) for t in ts[:-1]]])
+    with btfem.BTFem(0) as fem:
+        fem.set_mesh(xyz, tets, phase)
+        fem.set_diffusion(2e-3)
+        if phase is not None:
+            fem.set_permeability(1e-5)
+        fem.set_periodic(pdir, kappa_e, tol, lo, hi)
+        fem.assemble()
+        assert np.array_equal(fem.pattern()[1], ops.colidx)
+        assert _relmax(fem.values("B"), ops.B.data) <= 1e-12
+        dv, dc = fem.dofmap()
+        fem.set_periodic_gather(*periodic.build_gather(xyz, tets, phase, pdir, lo, hi, dv, dc))
+        res = fem.solve(k, 0.5, q * f, q * fp, g, q=q, Fb=Fp, rtol=1e-13, atol=1e-16)
+        u = fem.solution()
+    assert abs(res["signal"] - ref["signal"]) <= 1e-8 * abs(ref["signal"])
+    assert _relmax(u, ref["u"]) <= 1e-8
+    # the BC does something: the Neumann answer is different
+    neu = orc.theta_solve(orc.assemble(xyz, tets, phase, D=2e-3, kappa=1e-5), seq, q, g, k, solver="lu")
+    assert abs(neu["signal"] - ref["signal"]) > 1e-3 * abs(ref["signal"])
