@@ -56,6 +56,7 @@ void btfem_destroy(btfem_t* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+  if (h->h_gm) cudaFreeHost(h->h_gm);
   cudaStream_t st = h->stream;
   delete h;   // frees device arrays
   if (st) cudaStreamDestroy(st);

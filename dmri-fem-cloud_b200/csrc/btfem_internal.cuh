@@ -157,6 +157,9 @@ struct btfem {
       BT_CUDA(cudaStreamSynchronize(s));
     }
   } d_u, d_r, d_rp, d_p, d_v, d_s, d_t;
+  DevArray<double2> d_gm_V;        // GMRES basis, (restart+1) vectors
+  DevArray<double> d_gm_h;
+  double* h_gm = nullptr;          // pinned
   bool l2_window_set = false;
   cudaAccessPolicyWindow l2_window{};
   DevArray<double> d_cA, d_cb, d_Fb;

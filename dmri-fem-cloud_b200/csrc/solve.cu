@@ -516,6 +516,119 @@ __global__ void __launch_bounds__(TPB) k_signal(int n, KrylovCtrl* ctrl, double*
   }
 }
 
+// ------------------------------------------------------------------------------------ GMRES(m) kernels
+// PETSc KSPGMRES semantics on the (re,im)-split REAL system: real inner products, classical Gram-Schmidt
+// (no refinement, PETSc's default), left preconditioning (folded into the operator values), Givens rotations
+// on the host.  Secondary solver (the reference's GMRES notebooks); host-driven, one sync per iteration.
+constexpr int GM_MAXK = 64;   // restart <= 63
+
+struct GmVecs {
+  const double2* v[GM_MAXK];
+};
+
+// h_i = (w, v_i), i < k  (all k dot products in one pass over w)
+__global__ void __launch_bounds__(TPB) k_gm_dots(int n, int k, GmVecs V, const double2* __restrict__ w,
+                                                 double* __restrict__ partials, unsigned int* ticket,
+                                                 double* __restrict__ hout) {
+  __shared__ double sm[NWARP];
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = 0; i < k; ++i) {
+    const double2* __restrict__ vi = V.v[i];
+    double acc = 0.0;
+    for (int e = blockIdx.x * TPB + threadIdx.x; e < n; e += gridDim.x * TPB) {
+      const double2 a = w[e], b = vi[e];
+      acc += a.x * b.x + a.y * b.y;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sm[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+      double t = lane < NWARP ? sm[lane] : 0.0;
+      t = warp_sum(t);
+      if (lane == 0) partials[(size_t)i * BT_MAX_PARTIALS + blockIdx.x] = t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const volatile double* vp = partials;
+  for (int i = 0; i < k; ++i) {
+    double acc = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += TPB) acc += vp[(size_t)i * BT_MAX_PARTIALS + b];
+    acc = warp_sum(acc);
+    __syncthreads();
+    if (lane == 0) sm[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int q = 0; q < NWARP; ++q) t += sm[q];
+      hout[i] = t;
+    }
+  }
+  if (threadIdx.x == 0) *ticket = 0;
+}
+
+// w -= sum_i h_i v_i ; hout[k] = ||w||^2
+__global__ void __launch_bounds__(TPB) k_gm_update(int n, int k, GmVecs V, double2* __restrict__ w,
+                                                   double* __restrict__ partials, unsigned int* ticket,
+                                                   double* __restrict__ hout) {
+  double acc[1] = {0.0};
+  for (int e = blockIdx.x * TPB + threadIdx.x; e < n; e += gridDim.x * TPB) {
+    double2 a = w[e];
+    for (int i = 0; i < k; ++i) {
+      const double hi = hout[i];
+      const double2 b = V.v[i][e];
+      a.x -= hi * b.x;
+      a.y -= hi * b.y;
+    }
+    w[e] = a;
+    acc[0] += a.x * a.x + a.y * a.y;
+  }
+  if (reduce_finalize<1>(acc, partials, ticket)) hout[k] = acc[0];
+}
+
+// dst = alpha * src
+__global__ void k_gm_scale(int n, double alpha, const double2* __restrict__ src, double2* __restrict__ dst) {
+  for (int e = blockIdx.x * TPB + threadIdx.x; e < n; e += gridDim.x * TPB) {
+    const double2 a = src[e];
+    dst[e] = make_double2(alpha * a.x, alpha * a.y);
+  }
+}
+
+// x += sum_i y_i v_i
+__global__ void k_gm_axpy(int n, int k, GmVecs V, const double* __restrict__ y, double2* __restrict__ x) {
+  for (int e = blockIdx.x * TPB + threadIdx.x; e < n; e += gridDim.x * TPB) {
+    double2 a = x[e];
+    for (int i = 0; i < k; ++i) {
+      const double yi = y[i];
+      const double2 b = V.v[i][e];
+      a.x += yi * b.x;
+      a.y += yi * b.y;
+    }
+    x[e] = a;
+  }
+}
+
+// r = b - ax ; out[0] = ||r||^2
+__global__ void __launch_bounds__(TPB) k_gm_resid(int n, const double2* __restrict__ b, const double2* __restrict__ ax,
+                                                  double2* __restrict__ r, double* __restrict__ partials,
+                                                  unsigned int* ticket, double* __restrict__ out) {
+  double acc[1] = {0.0};
+  for (int e = blockIdx.x * TPB + threadIdx.x; e < n; e += gridDim.x * TPB) {
+    const double2 bb = b[e], aa = ax[e];
+    const double2 rr = make_double2(bb.x - aa.x, bb.y - aa.y);
+    r[e] = rr;
+    acc[0] += rr.x * rr.x + rr.y * rr.y;
+  }
+  if (reduce_finalize<1>(acc, partials, ticket)) out[0] = acc[0];
+}
+
 inline int vec_grid(int n) { return std::max(1, std::min((n + TPB - 1) / TPB, BT_NUM_SMS * 8)); }
 inline int spmv_grid(int n, int lanes) {
   int rpb = TPB / lanes;
@@ -617,9 +730,115 @@ void ensure_vectors(btfem* h) {
       cudaGetLastError();   // persistence is an optimisation: never fail the solve over it
     }
   }
-  h->d_partials.alloc(8 * BT_MAX_PARTIALS);
+  h->d_partials.alloc((size_t)(GM_MAXK + 8) * BT_MAX_PARTIALS);
   h->d_ctrl.alloc(1);
   if (!h->h_ctrl) BT_CUDA(cudaMallocHost((void**)&h->h_ctrl, sizeof(KrylovCtrl)));
+}
+
+// One linear solve with restarted GMRES, host-driven.  On entry the RHS kernel(s) have run: r = K^-1(b - A x0),
+// b^ is in t when the guess is non-zero.  Returns the iteration count; reason in *reason.
+int gmres_solve_step(btfem* h, const btfem_solve_args* sa, SpmvArgs a, double cA_step, int64_t* n_spmv,
+                     int64_t* n_kernels, int* reason) {
+  cudaStream_t st = h->stream;
+  const int n = (int)h->ndof;
+  const int m = (int)std::max<int64_t>(1, std::min<int64_t>(sa->restart > 0 ? sa->restart : 30, GM_MAXK - 1));
+  const size_t npad = ((size_t)n + 15) & ~(size_t)15;
+  const int vg = vec_grid(n);
+  const int lanes = h->lanes;
+  h->d_gm_V.alloc((size_t)(m + 1) * npad);
+  h->d_gm_h.alloc(GM_MAXK + 2);
+  if (!h->h_gm) BT_CUDA(cudaMallocHost((void**)&h->h_gm, sizeof(double) * (GM_MAXK + 2)));
+  GmVecs V;
+  for (int i = 0; i < GM_MAXK; ++i) V.v[i] = h->d_gm_V.p + (size_t)std::min(i, m) * npad;
+  unsigned int* tk1 = &h->d_ctrl.p->ticket[6];
+  unsigned int* tk2 = &h->d_ctrl.p->ticket[7];
+  double* part = h->d_partials.p;   // [GM_MAXK][BT_MAX_PARTIALS] needed by k_gm_dots
+
+  BT_CUDA(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl.p, sizeof(KrylovCtrl), cudaMemcpyDeviceToHost, st));
+  BT_CUDA(cudaStreamSynchronize(st));
+  const double bnorm = h->h_ctrl->bnorm, ttol = h->h_ctrl->ttol;
+  double res = h->h_ctrl->rnorm;
+  *reason = h->h_ctrl->reason;
+  if (h->h_ctrl->done) return 0;
+  if (!sa->nonzero_guess) {
+    BT_CUDA(cudaMemcpyAsync(h->d_t.p, h->d_r.p, sizeof(double2) * n, cudaMemcpyDeviceToDevice, st));   // keep b^
+    h->d_u.zero(st);
+  }
+  a.c_plain = sa->theta * cA_step;
+  int its = 0;
+  std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m, 0.0), sn(m, 0.0), rs(m + 1, 0.0), y(m, 0.0);
+  for (;;) {
+    k_gm_scale<<<vg, TPB, 0, st>>>(n, 1.0 / res, h->d_r.p, h->d_gm_V.p);
+    ++*n_kernels;
+    std::fill(rs.begin(), rs.end(), 0.0);
+    rs[0] = res;
+    int j = 0;
+    bool stop = false;
+    for (; j < m && !stop; ++j) {
+      double2* w = h->d_gm_V.p + (size_t)(j + 1) * npad;
+      a.x_plain = h->d_gm_V.p + (size_t)j * npad;
+      a.y_plain = w;
+      launch_spmv<MODE_PLAIN>(lanes, a, st);
+      k_gm_dots<<<vg, TPB, 0, st>>>(n, j + 1, V, w, part, tk1, h->d_gm_h.p);
+      k_gm_update<<<vg, TPB, 0, st>>>(n, j + 1, V, w, part, tk2, h->d_gm_h.p);
+      *n_kernels += 3;
+      ++*n_spmv;
+      BT_CUDA(cudaMemcpyAsync(h->h_gm, h->d_gm_h.p, sizeof(double) * (j + 2), cudaMemcpyDeviceToHost, st));
+      BT_CUDA(cudaStreamSynchronize(st));
+      double* hh = &H[(size_t)j * (m + 1)];
+      for (int i = 0; i <= j; ++i) hh[i] = h->h_gm[i];
+      const double tt = std::sqrt(h->h_gm[j + 1]);
+      hh[j + 1] = tt;
+      for (int i = 0; i < j; ++i) {   // previous rotations
+        const double t0 = hh[i];
+        hh[i] = cs[i] * t0 + sn[i] * hh[i + 1];
+        hh[i + 1] = -sn[i] * t0 + cs[i] * hh[i + 1];
+      }
+      const double den = std::sqrt(hh[j] * hh[j] + hh[j + 1] * hh[j + 1]);
+      if (den == 0.0) { *reason = BTFEM_EBREAKDOWN; break; }
+      cs[j] = hh[j] / den;
+      sn[j] = hh[j + 1] / den;
+      rs[j + 1] = -sn[j] * rs[j];
+      rs[j] = cs[j] * rs[j];
+      hh[j] = cs[j] * hh[j] + sn[j] * hh[j + 1];
+      res = std::fabs(rs[j + 1]);
+      ++its;
+      if (!(res == res) || std::isinf(res)) { *reason = BTFEM_ENAN; stop = true; }
+      else if (res <= ttol) { *reason = res < sa->atol ? 3 : 2; stop = true; }
+      else if (res >= 1e4 * bnorm) { *reason = BTFEM_EDTOL; stop = true; }
+      else if (its >= sa->maxit) { *reason = BTFEM_ENOTCONV; stop = true; }
+      else if (tt == 0.0) { *reason = BTFEM_EBREAKDOWN; stop = true; }
+      if (!stop && j + 1 < m) {
+        k_gm_scale<<<vg, TPB, 0, st>>>(n, 1.0 / tt, w, w);
+        ++*n_kernels;
+      }
+    }
+    const int kk = j;   // columns built
+    for (int i = kk - 1; i >= 0; --i) {   // back substitution R y = rs
+      double t0 = rs[i];
+      for (int l = i + 1; l < kk; ++l) t0 -= H[(size_t)l * (m + 1) + i] * y[l];
+      y[i] = t0 / H[(size_t)i * (m + 1) + i];
+    }
+    if (kk > 0) {
+      BT_CUDA(cudaMemcpyAsync(h->d_gm_h.p, y.data(), sizeof(double) * kk, cudaMemcpyHostToDevice, st));
+      k_gm_axpy<<<vg, TPB, 0, st>>>(n, kk, V, h->d_gm_h.p, h->d_u.p);
+      ++*n_kernels;
+      BT_CUDA(cudaStreamSynchronize(st));   // y is a host temporary
+    }
+    if (*reason != 0) break;
+    // restart: true preconditioned residual r = b^ - A^ x
+    a.x_plain = h->d_u.p;
+    a.y_plain = h->d_s.p;
+    launch_spmv<MODE_PLAIN>(lanes, a, st);
+    k_gm_resid<<<vg, TPB, 0, st>>>(n, h->d_t.p, h->d_s.p, h->d_r.p, part, tk2, h->d_gm_h.p);
+    *n_kernels += 2;
+    ++*n_spmv;
+    BT_CUDA(cudaMemcpyAsync(h->h_gm, h->d_gm_h.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    BT_CUDA(cudaStreamSynchronize(st));
+    res = std::sqrt(h->h_gm[0]);
+    if (res <= ttol) { *reason = res < sa->atol ? 3 : 2; break; }
+  }
+  return its;
 }
 
 }  // namespace
@@ -726,7 +945,8 @@ void bt_spmv_bench(btfem* h, double dt, double theta, double c, const double g[3
 void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_t* iters_per_step) {
   BT_REQUIRE(sa->nsteps >= 0 && sa->dt > 0, "bad nsteps/dt");
   BT_REQUIRE(sa->theta > 0 && sa->theta <= 1, "theta must be in (0,1]");
-  BT_REQUIRE(sa->ksp == BTFEM_KSP_BICGSTAB, "only BTFEM_KSP_BICGSTAB is implemented");
+  BT_REQUIRE(sa->ksp == BTFEM_KSP_BICGSTAB || sa->ksp == BTFEM_KSP_GMRES, "unknown Krylov method");
+  const bool gmres = sa->ksp == BTFEM_KSP_GMRES;
   const bool periodic = h->periodic && h->n_pb_rows > 0;
   if (periodic) {
     BT_REQUIRE(sa->Fb != nullptr, "periodic BC needs Fb (F(t_{n-1}) per step)");
@@ -816,6 +1036,17 @@ void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_
     if (sa->nonzero_guess) {
       launch_spmv<MODE_RESID>(lanes, a, st);
       ++n_kernels;
+    }
+    if (gmres) {
+      int reason = 0;
+      const int it = gmres_solve_step(h, sa, a, sa->cA[step], &n_spmv, &n_kernels, &reason);
+      n_spmv += 1 + (sa->nonzero_guess ? 1 : 0);
+      total_iters += it;
+      max_iters = std::max<int64_t>(max_iters, it);
+      if (iters_per_step) iters_per_step[step] = it;
+      last_reason = reason;
+      if (reason < 0) fail = reason;
+      continue;
     }
     int launched = 0;
     int chunk = std::max(1, est);

@@ -394,6 +394,84 @@ def bicgstab_petsc(matvec, b, diag, rtol=1e-9, atol=1e-10, maxit=100000, x0=None
     return x, i, dp, -3
 
 
+def gmres_petsc(matvec, b, diag, rtol=1e-6, atol=1e-15, maxit=10000, restart=30, x0=None, dtol=1e4):
+    """PETSc 3.7 KSPGMRES restated: restart 30, classical Gram-Schmidt without refinement, left PCJACOBI
+    (diag=None: no preconditioner), Givens rotations, default convergence test on the preconditioned
+    residual estimate.  REAL inner products on complex storage == GMRES on the reference's real
+    (re,im)-split system.  Returns x, iterations, residual norm, reason."""
+    rdot = lambda a, c: float(np.dot(a.real, c.real) + np.dot(a.imag, c.imag))
+    Kinv = 1.0 if diag is None else 1.0 / diag
+    n = len(b)
+    kb = Kinv * b
+    bnorm = np.sqrt(rdot(kb, kb))
+    if x0 is None:
+        x = np.zeros(n, dtype=complex)
+        r = kb.copy()
+    else:
+        x = x0.astype(complex).copy()
+        r = Kinv * (b - matvec(x))
+    res = np.sqrt(rdot(r, r))
+    ttol = max(rtol * bnorm, atol)
+    if res <= ttol:
+        return x, 0, res, 2
+    its = 0
+    m = restart
+    while True:
+        V = [r / res]
+        H = np.zeros((m + 1, m))
+        cs, sn, rs = np.zeros(m), np.zeros(m), np.zeros(m + 1)
+        rs[0] = res
+        reason = 0
+        k = 0
+        for j in range(m):
+            w = Kinv * matvec(V[j])
+            hcol = np.array([rdot(w, V[i]) for i in range(j + 1)])       # classical GS: all dots first
+            for i in range(j + 1):
+                w = w - hcol[i] * V[i]
+            tt = np.sqrt(rdot(w, w))
+            H[:j + 1, j] = hcol
+            H[j + 1, j] = tt
+            for i in range(j):
+                t0 = H[i, j]
+                H[i, j] = cs[i] * t0 + sn[i] * H[i + 1, j]
+                H[i + 1, j] = -sn[i] * t0 + cs[i] * H[i + 1, j]
+            den = np.hypot(H[j, j], H[j + 1, j])
+            if den == 0.0:
+                reason = -5
+                break
+            cs[j], sn[j] = H[j, j] / den, H[j + 1, j] / den
+            rs[j + 1] = -sn[j] * rs[j]
+            rs[j] = cs[j] * rs[j]
+            H[j, j] = cs[j] * H[j, j] + sn[j] * H[j + 1, j]
+            res = abs(rs[j + 1])
+            its += 1
+            k = j + 1
+            if not np.isfinite(res):
+                reason = -9
+            elif res <= ttol:
+                reason = 2
+            elif res >= dtol * bnorm:
+                reason = -4
+            elif its >= maxit:
+                reason = -3
+            elif tt == 0.0:
+                reason = -5
+            if reason:
+                break
+            V.append(w / tt)
+        y = np.zeros(k)
+        for i in range(k - 1, -1, -1):
+            y[i] = (rs[i] - H[i, i + 1:k] @ y[i + 1:k]) / H[i, i]
+        for i in range(k):
+            x = x + y[i] * V[i]
+        if reason:
+            return x, its, res, reason
+        r = kb - Kinv * matvec(x)
+        res = np.sqrt(rdot(r, r))
+        if res <= ttol:
+            return x, its, res, 2
+
+
 # --------------------------------------------------------------------------- weak pseudo-periodic
 
 
@@ -472,7 +550,7 @@ def periodic_term(xyz, tets, ops, pdir, lo, hi, q, gdir, theta):
 
 def theta_solve(ops, seq, q, gdir, k, theta=0.5, solver="lu", rtol=1e-9, atol=1e-10, maxit=100000,
                 closed=True, ic=None, nonzero_guess=False, rhs_uses_current_f=False,
-                periodic=None, return_history=False):
+                periodic=None, return_history=False, restart=30):
     """MRI_simulation.solve (DmriFemLib.py:878-915) on the pre-assembled operators.
 
     A_n uses f(t_n); b_n uses f(t_{n-1}), t_{-1}=0 (DmriFemLib.py:901-902, 909); the comri
@@ -509,8 +587,12 @@ def theta_solve(ops, seq, q, gdir, k, theta=0.5, solver="lu", rtol=1e-9, atol=1e
             iters.append(0)
         else:
             mv = lambda x, cA=cA: P @ x + 1j * theta * cA * (Jg @ x)
-            u, it, dp, reason = bicgstab_petsc(mv, b, diag, rtol, atol, maxit,
-                                               x0=u if nonzero_guess else None)
+            if solver.startswith("gmres"):
+                u, it, dp, reason = gmres_petsc(mv, b, None if solver == "gmres_none" else diag, rtol, atol, maxit,
+                                                restart, x0=u if nonzero_guess else None)
+            else:
+                u, it, dp, reason = bicgstab_petsc(mv, b, diag if solver != "bicgstab_none" else np.ones_like(diag),
+                                                   rtol, atol, maxit, x0=u if nonzero_guess else None)
             if reason < 0:
                 raise RuntimeError("Krylov solver did not converge: reason %d" % reason)
             iters.append(it)

@@ -254,3 +254,51 @@ def test_weak_pseudo_periodic(case):
     # the BC does something: the Neumann answer is different
     neu = orc.theta_solve(orc.assemble(xyz, tets, phase, D=2e-3, kappa=1e-5), seq, q, g, k, solver="lu")
     assert abs(neu["signal"] - ref["signal"]) > 1e-3 * abs(ref["signal"])
+
+
+@pytest.mark.parametrize("ksp,pc,nz", [("gmres", "jacobi", False), ("gmres", "none", False), ("gmres", "jacobi", True),
+                                       ("bicgstab", "none", False), ("bicgstab", "jacobi", True)])
+def test_other_krylov_choices(ksp, pc, nz):
+    """The reference's other solver settings: GMRES(30) (RealNeurons*.ipynb, rtol 1e-4,
+    nonzero initial guess), BiCGStab without PC (comri multilayer main.cpp:237).  Iteration counts follow
+    the oracle's PETSc restatement; signals agree with the exact (LU) stepping within the solver tolerance."""
+    _, xyz, tets, phase, co = CASES[3]
+    ops = orc.assemble(xyz, tets, phase, D=co["D"], invT2=co["invT2"], kappa=co["kappa"])
+    seq = orc.pgse(2000.0, 6000.0)
+    q = seq.q_from_b(1000.0)
+    k = 200.0
+    g = np.array([0.0, 0.6, 0.8])
+    name = ksp + ("_none" if pc == "none" else "")
+    ref = orc.theta_solve(ops, seq, q, g, k, solver=name, rtol=1e-10, atol=1e-14, nonzero_guess=nz, restart=30)
+    lu = orc.theta_solve(ops, seq, q, g, k, solver="lu")
+    ts = orc.time_grid(seq.T, k)
+    f = np.array([seq.f(t) for t in ts])
+    fp = np.concatenate([[f[0]], f[:-1]])
+    with btfem.BTFem(0) as fem:
+        _setup(fem, xyz, tets, phase, co)
+        res = fem.solve(k, 0.5, q * f, q * fp, g, ksp=ksp, pc=pc, rtol=1e-10, atol=1e-14, nonzero_guess=nz,
+                        restart=30, want_iters=True)
+    assert abs(res["signal"] - lu["signal"]) <= 1e-8 * abs(lu["signal"])
+    assert abs(res["signal"] - ref["signal"]) <= 1e-8 * abs(ref["signal"])
+    assert np.max(np.abs(res["iters"].astype(int) - ref["iters"].astype(int))) <= 2
+    assert np.mean(np.abs(res["iters"].astype(int) - ref["iters"].astype(int)) <= 1) > 0.9
+
+
+def test_gmres_restart_path():
+    """Small restart forces several GMRES cycles (true-residual recomputation at each restart)."""
+    _, xyz, tets, phase, co = CASES[0]
+    ops = orc.assemble(xyz, tets, phase, D=co["D"])
+    seq = orc.pgse(2000.0, 6000.0)
+    q = seq.q_from_b(1000.0)
+    k = 400.0
+    g = np.array([1.0, 0.0, 0.0])
+    ref = orc.theta_solve(ops, seq, q, g, k, solver="gmres", rtol=1e-11, atol=1e-15, restart=5)
+    ts = orc.time_grid(seq.T, k)
+    f = np.array([seq.f(t) for t in ts])
+    fp = np.concatenate([[f[0]], f[:-1]])
+    with btfem.BTFem(0) as fem:
+        _setup(fem, xyz, tets, phase, co)
+        res = fem.solve(k, 0.5, q * f, q * fp, g, ksp="gmres", rtol=1e-11, atol=1e-15, restart=5, want_iters=True)
+    assert ref["iters"].max() > 5
+    assert abs(res["signal"] - ref["signal"]) <= 1e-8 * abs(ref["signal"])
+    assert np.max(np.abs(res["iters"].astype(int) - ref["iters"].astype(int))) <= 2
