@@ -91,3 +91,55 @@ def test_cli_reference_msh_fixture(tmp_path, monkeypatch):
     ref = orc.theta_solve(ops, seq, seq.q_from_b(1000.0), [1, 0, 0], 200.0, solver="lu")
     got = float(text.split("Normalized signal: ")[1].split(",")[0])
     assert abs(got - ref["signal"] / ref["voi"]) <= 2e-6 * got
+
+
+def test_config3_layered_variable_kappa_T2_ogse(tmp_path, monkeypatch):
+    """BASELINE configs[2]: multilayered cylinder/disk, variable permeability (kappa_tensor by marker pair,
+    MultilayeredDiskVariablePermeability.ipynb cell 10), per-layer D through ImposeDiffusionTensor, per-layer
+    T2 (T2_Relaxation.ipynb cell 10), cos-OGSE profile (ArbitraryTimeSequence.ipynb cell 10, profile 3)."""
+    monkeypatch.chdir(tmp_path)
+    xyz, tets, marker = meshes.layered_cylinder((5.0, 7.5, 10.0), 5.0, (3, 2, 2), 12, 2)
+    phase = (marker % 2).astype(np.int32)
+    nc = len(tets)
+    mesh = dl.Mesh(xyz, tets)
+    mp = dl.MRI_parameters()
+    mp.bvalue = 1000
+    mp.delta, mp.Delta = 4000.0, 4000.0
+    t0, seq_ext = 100.0, 100.0
+    Dd = mp.Delta + mp.delta
+    mp.T = Dd + t0 + seq_ext
+    mp.nperiod = 1
+    omega = 2.0 * mp.nperiod * np.pi / mp.delta      # dolfin `pi` is a float (ArbitraryTimeSequence.ipynb)
+    tau = Dd / 2.0
+    mp.fs_sym = sp.Piecewise((0., mp.s < t0), (sp.cos(omega * (mp.s - t0)), mp.s <= mp.delta + t0),
+                             (0., mp.s <= tau + t0), (-sp.cos(omega * (mp.s - t0 - tau)), mp.s <= mp.delta + tau + t0),
+                             (0., True))
+    mp.set_gradient_dir(mesh, 1, 1, 0)
+    mp.Apply()
+    sim = dl.MRI_simulation()
+    sim.k = 100
+    md = dl.MyDomain(mesh, mp)
+    md.phase, md.IsDomainMultiple = phase, True
+    kt = np.zeros((3, 3))
+    kt[0, 1] = kt[1, 0] = 1e-4
+    kt[1, 2] = kt[2, 1] = 1e-5
+    md.kappa, md.kappa_marker = kt, marker
+    md.T2_cell = np.array([4e16, 4e4, 4e4])[marker]
+    md.Apply()
+    Dl = np.array([3e-3, 1e-3, 3e-3])[marker]
+    z = np.zeros(nc)
+    md.ImposeDiffusionTensor(Dl, z, z, z, Dl, z, z, z, Dl)
+    ls = dl.KrylovSolver("bicgstab", "jacobi")
+    ls.parameters["relative_tolerance"] = 1e-12
+    ls.parameters["absolute_tolerance"] = 1e-15
+    sim.solve(md, mp, ls)
+    text = dl.PostProcessing(md, mp, sim, None, '')
+    assert "kappa:" not in text                                  # non-scalar kappa: the line without kappa (:935)
+    ops = orc.assemble(xyz, tets, phase, D=Dl, invT2=1.0 / md.T2_cell,
+                       kappa_facet=lambda fv, c0, c1: kt[marker[c0], marker[c1]])
+    seq = orc.Sequence(mp.fs_sym, mp.T, mp.s)
+    assert abs(seq.q_from_b(1000.0) - mp.qvalue) <= 1e-14 * mp.qvalue
+    ref = orc.theta_solve(ops, seq, mp.qvalue, [1, 1, 0], 100.0, solver="lu")
+    assert abs(sim.stats["signal"] - ref["signal"]) <= 1e-8 * abs(ref["signal"])
+    assert abs(sim.stats["signal_comp"][1] - float(ops.lumped[ops.dof_comp == 1] @ ref["u"].real[ops.dof_comp == 1])) \
+        <= 1e-8 * abs(ref["signal"])
