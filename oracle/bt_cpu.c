@@ -33,6 +33,14 @@ int btcpu_num_threads(void) {
 #endif
 }
 
+void btcpu_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* y = Kinv .* (V + i*c*J) x */
 static void spmv(int n, const int* rp, const int* ci, const double* V, const double* J, double c,
                  const double* kinv, const cplx* x, cplx* y) {

@@ -23,6 +23,11 @@ def num_threads():
     return lib().btcpu_num_threads()
 
 
+def set_threads(n):
+    """Use n OpenMP threads (torchrun exports OMP_NUM_THREADS=1; the CPU arm wants every host core)."""
+    lib().btcpu_set_threads(C.c_int(int(n)))
+
+
 def theta_loop(ops, gdir, k, theta, cA, cb, rtol=1e-9, atol=1e-10, maxit=100000, mode=0, ic=None):
     """Run len(cA) theta steps from `ic` (default 1).  Returns u (complex), iters (per step)."""
     g = np.asarray(gdir, dtype=float)

@@ -1,0 +1,7 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=index,name --format=csv
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 1 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
+tail -c 1500 gpurun_out/bench_n2.json; tail -5 gpurun_out/bench_n2.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 1 --cpu-sample-steps 4 | tail -c 800
