@@ -78,6 +78,7 @@ def load_library(path=None):
                                        C.c_int32, _c_double_p]),
         "btfem_set_lanes": (C.c_int, [H, C.c_int32]),
         "btfem_solve": (C.c_int, [H, C.POINTER(SolveArgs), C.POINTER(SolveOut), _c_int32_p]),
+        "btfem_solve_batch": (C.c_int, [H, C.c_int32, C.POINTER(SolveArgs), C.POINTER(SolveOut)]),
         "btfem_get_solution": (C.c_int, [H, _c_double_p]),
     }
     for name, (res, args) in proto.items():
@@ -279,6 +280,33 @@ class BTFem:
         res["n_steps"] = len(cA)
         if want_iters:
             res["iters"] = iters
+        return res
+
+    def solve_batch(self, dt, theta, members, ksp="bicgstab", pc="jacobi", rtol=1e-9, atol=1e-10, maxit=100000):
+        """members: list of (cA, cb, gdir) -- independent solves advanced in lock step on the GPU."""
+        nb = len(members)
+        args = (SolveArgs * nb)()
+        outs = (SolveOut * nb)()
+        keep = []
+        for a, (cA, cb, g) in zip(args, members):
+            cA = np.ascontiguousarray(cA, dtype=np.float64)
+            cb = np.ascontiguousarray(cb, dtype=np.float64)
+            keep += [cA, cb]
+            a.nsteps = len(cA)
+            a.dt, a.theta = float(dt), float(theta)
+            a.cA, a.cb = _dp(cA), _dp(cb)
+            g = np.asarray(g, dtype=np.float64)
+            a.gdir[0], a.gdir[1], a.gdir[2] = g
+            a.ksp, a.pc = KSP_IDS[ksp], PC_IDS[pc]
+            a.rtol, a.atol, a.maxit = float(rtol), float(atol), int(maxit)
+            a.nonzero_guess, a.restart = 0, 30
+        self._ck(self.lib.btfem_solve_batch(self.h, nb, args, outs))
+        res = []
+        for o in outs:
+            d = {k: getattr(o, k) for k, _ in SolveOut._fields_ if k not in ("signal_comp", "voi_comp")}
+            d["signal_comp"] = (o.signal_comp[0], o.signal_comp[1])
+            d["voi_comp"] = (o.voi_comp[0], o.voi_comp[1])
+            res.append(d)
         return res
 
     def solution(self):

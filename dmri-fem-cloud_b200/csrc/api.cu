@@ -279,6 +279,16 @@ int btfem_solve(btfem_t* h, const btfem_solve_args* args, btfem_solve_out* out, 
   });
 }
 
+int btfem_solve_batch(btfem_t* h, int32_t members, const btfem_solve_args* args, btfem_solve_out* out) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->assembled, "call btfem_assemble first");
+    BT_REQUIRE(args && out && members >= 1, "null argument");
+    for (int b = 0; b < members; ++b) BT_REQUIRE(args[b].cA && args[b].cb, "null cA/cb");
+    memset(out, 0, sizeof(*out) * members);
+    bt_solve_batch(h, members, args, out);
+  });
+}
+
 int btfem_get_solution(btfem_t* h, double* u) {
   return guarded(h, [&] {
     BT_REQUIRE(h->have_solution && u, "no solution yet");

@@ -165,7 +165,11 @@ struct btfem {
   DevArray<double> d_cA, d_cb, d_Fb;
   DevArray<double> d_partials;     // [8][BT_MAX_PARTIALS]
   DevArray<KrylovCtrl> d_ctrl;
-  KrylovCtrl* h_ctrl = nullptr;    // pinned
+  KrylovCtrl* h_ctrl = nullptr;    // pinned, one per batch member
+  int h_ctrl_n = 0;
+  size_t vec_npad = 0;             // padded vector length (elements)
+  int64_t step_stride = 0;         // cA/cb stride between batch members
+  int comb_members = 0;
   double comb_dt = -1, comb_theta = -1, comb_g[3] = {0, 0, 0};
   int comb_pc = -1;
   bool have_solution = false;
@@ -189,8 +193,9 @@ void bt_assemble_values(btfem* h);
 void bt_build_periodic(btfem* h);
 
 // solve.cu
-void bt_combine(btfem* h, double dt, double theta, const double g[3], int pc);
+void bt_combine(btfem* h, double dt, double theta, const double g[3], int pc, int member = 0, int members = 1);
 void bt_spmv_host(btfem* h, double dt, double theta, double c, const double g[3], const double* x, double* y);
 void bt_spmv_bench(btfem* h, double dt, double theta, double c, const double g[3], int lanes, int nrep, int flush_l2,
                    double* ms);
 void bt_solve(btfem* h, const btfem_solve_args* a, btfem_solve_out* out, int32_t* iters_per_step);
+void bt_solve_batch(btfem* h, int members, const btfem_solve_args* a, btfem_solve_out* out);

@@ -149,7 +149,29 @@ struct SpmvArgs {
   const double2* x_plain;
   double2* y_plain;
   double c_plain;
+  // batch of independent solves on the same mesh (gridDim.y members; HARDI direction x b sweeps): element
+  // strides between consecutive members.  The pattern arrays are shared.
+  size_t mat_stride_csr, mat_stride_sell, vec_stride, part_stride, step_stride;
+  double* sig_out;           // k_signal: [members][2]
 };
+
+// arguments of batch member blockIdx.y
+__device__ __forceinline__ SpmvArgs member(SpmvArgs a) {
+  const size_t b = blockIdx.y;
+  if (b == 0) return a;
+  a.PJ += b * a.mat_stride_csr;
+  a.QJ += b * a.mat_stride_csr;
+  a.PJs += b * a.mat_stride_sell;
+  a.QJs += b * a.mat_stride_sell;
+  a.cA += b * a.step_stride;
+  a.cb += b * a.step_stride;
+  a.ctrl += b;
+  a.partials += b * a.part_stride;
+  a.u += b * a.vec_stride; a.r += b * a.vec_stride; a.rp += b * a.vec_stride; a.p += b * a.vec_stride;
+  a.v += b * a.vec_stride; a.s += b * a.vec_stride; a.t += b * a.vec_stride;
+  if (a.sig_out) a.sig_out += 2 * b;
+  return a;
+}
 
 // streaming loads for the matrix (read once per SpMV; keeps the Krylov vectors in the 126 MB L2)
 __device__ __forceinline__ int ld_stream(const int32_t* p) { return __ldcs(p); }
@@ -288,8 +310,9 @@ __device__ __forceinline__ double2 row_product(const int32_t* __restrict__ rowpt
 }
 
 template <int LANES, int MODE>
-__global__ void __launch_bounds__(TPB) k_spmv(SpmvArgs a) {
+__global__ void __launch_bounds__(TPB) k_spmv(SpmvArgs a_in) {
   constexpr int RPB = TPB / LANES;
+  const SpmvArgs a = member(a_in);
   const ModeSetup m = mode_setup<MODE>(a);
   if (m.skip) return;
   const int lane = threadIdx.x % LANES;
@@ -335,7 +358,8 @@ __device__ __forceinline__ double2 ldv_gather_f64x2(const double2* p) {
 // it sits at the practical one-pass streaming ceiling of ~5.4 TB/s for a 166 MB working set -- so plain int32
 // columns are kept.)
 template <int MODE, int SELL_UNR, int MINB>
-__global__ void __launch_bounds__(TPB, MINB) k_spmv_sell(SpmvArgs a) {
+__global__ void __launch_bounds__(TPB, MINB) k_spmv_sell(SpmvArgs a_in) {
+  const SpmvArgs a = member(a_in);
   const ModeSetup m = mode_setup<MODE>(a);
   if (m.skip) return;
   const int lane = threadIdx.x & 31;
@@ -386,12 +410,16 @@ __global__ void __launch_bounds__(TPB, MINB) k_spmv_sell(SpmvArgs a) {
 // ------------------------------------------------------------------------------------ vector kernels
 
 // p <- r - omega*beta*v + beta*p        (VecAXPBYPCZ in KSPSolve_BCGS)
-__global__ void __launch_bounds__(TPB) k_update_p(int n, KrylovCtrl* ctrl, const double2* __restrict__ r,
-                                                  const double2* __restrict__ v, double2* __restrict__ p) {
+__global__ void __launch_bounds__(TPB) k_update_p(SpmvArgs a_in) {
+  const SpmvArgs a = member(a_in);
+  const KrylovCtrl* ctrl = a.ctrl;
   if (ctrl->done) return;
   const double beta = (ctrl->rho / ctrl->rho_old) * (ctrl->alpha / ctrl->omega);
   const double ob = ctrl->omega * beta;
-  for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
+  const double2* __restrict__ r = a.r;
+  const double2* __restrict__ v = a.v;
+  double2* __restrict__ p = a.p;
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < a.n; i += gridDim.x * TPB) {
     double2 rr = r[i], vv = v[i], pp = p[i];
     pp.x = rr.x - ob * vv.x + beta * pp.x;
     pp.y = rr.y - ob * vv.y + beta * pp.y;
@@ -400,26 +428,34 @@ __global__ void __launch_bounds__(TPB) k_update_p(int n, KrylovCtrl* ctrl, const
 }
 
 // s <- r - alpha*v
-__global__ void __launch_bounds__(TPB) k_update_s(int n, KrylovCtrl* ctrl, const double2* __restrict__ r,
-                                                  const double2* __restrict__ v, double2* __restrict__ s) {
-  if (ctrl->done) return;
-  const double alpha = ctrl->alpha;
-  for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
+__global__ void __launch_bounds__(TPB) k_update_s(SpmvArgs a_in) {
+  const SpmvArgs a = member(a_in);
+  if (a.ctrl->done) return;
+  const double alpha = a.ctrl->alpha;
+  const double2* __restrict__ r = a.r;
+  const double2* __restrict__ v = a.v;
+  double2* __restrict__ s = a.s;
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < a.n; i += gridDim.x * TPB) {
     double2 rr = r[i], vv = v[i];
     s[i] = make_double2(rr.x - alpha * vv.x, rr.y - alpha * vv.y);
   }
 }
 
 // x <- x + alpha*p + omega*s ; r <- s - omega*t ; rho' = (r,rp) ; ||r|| ; convergence test
-__global__ void __launch_bounds__(TPB) k_update_xr(int n, KrylovCtrl* ctrl, double* partials, double2* __restrict__ x,
-                                                   const double2* __restrict__ p, const double2* __restrict__ s,
-                                                   const double2* __restrict__ t, const double2* __restrict__ rp,
-                                                   double2* __restrict__ r) {
+__global__ void __launch_bounds__(TPB) k_update_xr(SpmvArgs a_in) {
+  const SpmvArgs a = member(a_in);
+  KrylovCtrl* ctrl = a.ctrl;
   if (ctrl->done) return;
   const double alpha = ctrl->alpha, omega = ctrl->omega;
   const bool fresh = (ctrl->iters == 0) && !ctrl->nonzero_guess;   // zero initial guess: x starts from 0
+  double2* __restrict__ x = a.u;
+  const double2* __restrict__ p = a.p;
+  const double2* __restrict__ s = a.s;
+  const double2* __restrict__ t = a.t;
+  const double2* __restrict__ rp = a.rp;
+  double2* __restrict__ r = a.r;
   double acc[2] = {0.0, 0.0};
-  for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < a.n; i += gridDim.x * TPB) {
     double2 pp = p[i], ss = s[i], tt = t[i], q = rp[i];
     double2 xx = fresh ? make_double2(0.0, 0.0) : x[i];
     xx.x += alpha * pp.x + omega * ss.x;
@@ -430,7 +466,7 @@ __global__ void __launch_bounds__(TPB) k_update_xr(int n, KrylovCtrl* ctrl, doub
     acc[0] += rr.x * q.x + rr.y * q.y;
     acc[1] += rr.x * rr.x + rr.y * rr.y;
   }
-  if (reduce_finalize<2>(acc, partials + 5 * BT_MAX_PARTIALS, &ctrl->ticket[TK_XR])) {
+  if (reduce_finalize<2>(acc, a.partials + 5 * BT_MAX_PARTIALS, &ctrl->ticket[TK_XR])) {
     const double rho_used = ctrl->rho;
     ctrl->rho_old = rho_used;
     ctrl->rho = acc[0];
@@ -502,18 +538,24 @@ __global__ void k_set_ic(int n, const double* __restrict__ ic, double2* __restri
 }
 
 // signal = sum_i lumped_i * Re u_i, split by compartment (DmriFemLib.py:926-931, 970-971)
-__global__ void __launch_bounds__(TPB) k_signal(int n, KrylovCtrl* ctrl, double* partials,
-                                                const double* __restrict__ lumped, const int32_t* __restrict__ comp,
-                                                const double2* __restrict__ u, double* __restrict__ out) {
+__global__ void __launch_bounds__(TPB) k_signal(SpmvArgs a_in, const double* __restrict__ lumped,
+                                                const int32_t* __restrict__ comp) {
+  const SpmvArgs a = member(a_in);
+  const double2* __restrict__ u = a.u;
   double acc[2] = {0.0, 0.0};
-  for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) {
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < a.n; i += gridDim.x * TPB) {
     double w = lumped[i] * u[i].x;
     if (comp[i] == 0) acc[0] += w; else acc[1] += w;
   }
-  if (reduce_finalize<2>(acc, partials + 6 * BT_MAX_PARTIALS, &ctrl->ticket[TK_SIG])) {
-    out[0] = acc[0];
-    out[1] = acc[1];
+  if (reduce_finalize<2>(acc, a.partials + 6 * BT_MAX_PARTIALS, &a.ctrl->ticket[TK_SIG])) {
+    a.sig_out[0] = acc[0];
+    a.sig_out[1] = acc[1];
   }
+}
+
+__global__ void k_set_ic_batch(int n, size_t vec_stride, const double* __restrict__ ic, double2* __restrict__ u) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) u[blockIdx.y * vec_stride + i] = make_double2(ic[i], 0.0);
 }
 
 // ------------------------------------------------------------------------------------ GMRES(m) kernels
@@ -629,7 +671,15 @@ __global__ void __launch_bounds__(TPB) k_gm_resid(int n, const double2* __restri
   if (reduce_finalize<1>(acc, partials, ticket)) out[0] = acc[0];
 }
 
-inline int vec_grid(int n) { return std::max(1, std::min((n + TPB - 1) / TPB, BT_NUM_SMS * 8)); }
+inline int vec_blocks_per_sm() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BTFEM_VEC_BLOCKS");
+    v = e ? std::max(1, std::min(8, atoi(e))) : 8;
+  }
+  return v;
+}
+inline int vec_grid(int n) { return std::max(1, std::min((n + TPB - 1) / TPB, BT_NUM_SMS * vec_blocks_per_sm())); }
 inline int spmv_grid(int n, int lanes) {
   int rpb = TPB / lanes;
   return std::max(1, std::min((n + rpb - 1) / rpb, BT_NUM_SMS * 16));
@@ -639,11 +689,11 @@ constexpr int SELL_UNR_DEFAULT = 4;
 constexpr int SELL_MINB_DEFAULT = 3;
 
 template <int MODE>
-void launch_spmv(int lanes, SpmvArgs a, cudaStream_t st) {
+void launch_spmv(int lanes, SpmvArgs a, cudaStream_t st, int members = 1) {
   a.use_sell = lanes == 0 || lanes >= 100;
   if (lanes == 0) {   // SELL-32
     int g = std::max(1, std::min((a.nslice + TPB / 32 - 1) / (TPB / 32), BT_NUM_SMS * SELL_MINB_DEFAULT));
-    k_spmv_sell<MODE, SELL_UNR_DEFAULT, SELL_MINB_DEFAULT><<<g, TPB, 0, st>>>(a);
+    k_spmv_sell<MODE, SELL_UNR_DEFAULT, SELL_MINB_DEFAULT><<<dim3(g, members), TPB, 0, st>>>(a);
     return;
   }
   if (MODE == MODE_PLAIN && lanes >= 100) {   // tuning variants, bench hook only: lanes = 100*UNR/4 + MINB
@@ -664,7 +714,7 @@ void launch_spmv(int lanes, SpmvArgs a, cudaStream_t st) {
     }
 #undef SELL_CASE
   }
-  int g = spmv_grid(a.n, lanes);
+  dim3 g(spmv_grid(a.n, lanes), members);
   switch (lanes) {
     case 4: k_spmv<4, MODE><<<g, TPB, 0, st>>>(a); break;
     case 8: k_spmv<8, MODE><<<g, TPB, 0, st>>>(a); break;
@@ -693,14 +743,21 @@ SpmvArgs base_args(btfem* h) {
   a.ctrl = h->d_ctrl.p;
   a.partials = h->d_partials.p;
   a.u = h->d_u.p; a.r = h->d_r.p; a.rp = h->d_rp.p; a.p = h->d_p.p; a.v = h->d_v.p; a.s = h->d_s.p; a.t = h->d_t.p;
+  a.mat_stride_csr = (size_t)h->nnz;
+  a.mat_stride_sell = (size_t)h->nnz_sell;
+  a.vec_stride = 7 * h->vec_npad;
+  a.part_stride = (size_t)(GM_MAXK + 8) * BT_MAX_PARTIALS;
+  a.step_stride = (size_t)h->step_stride;
   return a;
 }
 
-void ensure_vectors(btfem* h) {
+// Krylov vectors of `members` independent solves: member b owns slab [b*7*npad, (b+1)*7*npad)
+void ensure_vectors(btfem* h, int members = 1) {
   const size_t n = (size_t)h->ndof;
   const size_t npad = (n + 15) & ~(size_t)15;           // keep every vector 256-byte aligned
-  if (h->d_vecs.n != 7 * npad) {
-    h->d_vecs.alloc(7 * npad);
+  h->vec_npad = npad;
+  if (h->d_vecs.n != (size_t)members * 7 * npad) {
+    h->d_vecs.alloc((size_t)members * 7 * npad);
     h->d_vecs.zero(h->stream);
     btfem::VecView* views[7] = {&h->d_u, &h->d_r, &h->d_rp, &h->d_p, &h->d_v, &h->d_s, &h->d_t};
     for (int i = 0; i < 7; ++i) {
@@ -712,7 +769,7 @@ void ensure_vectors(btfem* h) {
     if (!(env && env[0] == '0')) {
       cudaDeviceProp prop;
       BT_CUDA(cudaGetDeviceProperties(&prop, h->device));
-      const size_t bytes = 7 * npad * sizeof(double2);
+      const size_t bytes = (size_t)members * 7 * npad * sizeof(double2);
       const size_t persist = std::min<size_t>(bytes, (size_t)prop.persistingL2CacheMaxSize);
       const size_t window = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
       if (persist > 0 && window > 0 &&
@@ -730,9 +787,14 @@ void ensure_vectors(btfem* h) {
       cudaGetLastError();   // persistence is an optimisation: never fail the solve over it
     }
   }
-  h->d_partials.alloc((size_t)(GM_MAXK + 8) * BT_MAX_PARTIALS);
-  h->d_ctrl.alloc(1);
-  if (!h->h_ctrl) BT_CUDA(cudaMallocHost((void**)&h->h_ctrl, sizeof(KrylovCtrl)));
+  h->d_partials.alloc((size_t)members * (GM_MAXK + 8) * BT_MAX_PARTIALS);
+  h->d_ctrl.alloc(members);
+  if (h->h_ctrl_n < members) {
+    if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
+    h->h_ctrl = nullptr;
+    BT_CUDA(cudaMallocHost((void**)&h->h_ctrl, sizeof(KrylovCtrl) * members));
+    h->h_ctrl_n = members;
+  }
 }
 
 // One linear solve with restarted GMRES, host-driven.  On entry the RHS kernel(s) have run: r = K^-1(b - A x0),
@@ -845,20 +907,23 @@ int gmres_solve_step(btfem* h, const btfem_solve_args* sa, SpmvArgs a, double cA
 
 // ===================================================================================== host entry points
 
-void bt_combine(btfem* h, double dt, double theta, const double g[3], int pc) {
-  if (h->comb_dt == dt && h->comb_theta == theta && h->comb_pc == pc && h->comb_g[0] == g[0] &&
-      h->comb_g[1] == g[1] && h->comb_g[2] == g[2] && h->d_PJ.p)
+// Operator values of batch member `member` (of `members`): the value arrays hold `members` copies back to back.
+void bt_combine(btfem* h, double dt, double theta, const double g[3], int pc, int member, int members) {
+  const bool single = members == 1;
+  if (single && h->comb_members == 1 && h->comb_dt == dt && h->comb_theta == theta && h->comb_pc == pc &&
+      h->comb_g[0] == g[0] && h->comb_g[1] == g[1] && h->comb_g[2] == g[2] && h->d_PJ.p)
     return;
   cudaStream_t st = h->stream;
   const int n = (int)h->ndof;
-  h->d_PJ.alloc(h->nnz);
-  h->d_QJ.alloc(h->nnz);
+  const size_t nm = (size_t)members;
+  h->d_PJ.alloc(nm * h->nnz);
+  h->d_QJ.alloc(nm * h->nnz);
   h->d_dinv.alloc(n);
   if (h->periodic) h->d_Bhat.alloc(h->nnz);
   if (h->n_slice) {   // padding entries stay (0,0)
-    if (h->d_PJs.n != (size_t)h->nnz_sell) {
-      h->d_PJs.alloc(h->nnz_sell);
-      h->d_QJs.alloc(h->nnz_sell);
+    if (h->d_PJs.n != nm * (size_t)h->nnz_sell) {
+      h->d_PJs.alloc(nm * h->nnz_sell);
+      h->d_QJs.alloc(nm * h->nnz_sell);
       h->d_PJs.zero(st);
       h->d_QJs.zero(st);
     }
@@ -867,10 +932,13 @@ void bt_combine(btfem* h, double dt, double theta, const double g[3], int pc) {
                                                 h->d_vals[6].p, h->d_vals[7].p, 1.0 / dt, theta, pc, h->d_dinv.p);
   k_combine<<<(int)((h->nnz + TPB - 1) / TPB), TPB, 0, st>>>(
       h->nnz, h->d_rowidx.p, h->d_vals[0].p, h->d_vals[1].p, h->d_vals[2].p, h->d_vals[6].p, h->d_vals[7].p,
-      h->d_vals[3].p, h->d_vals[4].p, h->d_vals[5].p, 1.0 / dt, theta, g[0], g[1], g[2], h->d_dinv.p, h->d_PJ.p,
-      h->d_QJ.p, h->periodic ? h->d_Bhat.p : nullptr, h->d_rowptr.p, h->d_sell_slot.p, h->d_slice_ptr.p,
-      h->n_slice ? h->d_PJs.p : nullptr, h->n_slice ? h->d_QJs.p : nullptr);
+      h->d_vals[3].p, h->d_vals[4].p, h->d_vals[5].p, 1.0 / dt, theta, g[0], g[1], g[2], h->d_dinv.p,
+      h->d_PJ.p + (size_t)member * h->nnz, h->d_QJ.p + (size_t)member * h->nnz,
+      h->periodic ? h->d_Bhat.p : nullptr, h->d_rowptr.p, h->d_sell_slot.p, h->d_slice_ptr.p,
+      h->n_slice ? h->d_PJs.p + (size_t)member * h->nnz_sell : nullptr,
+      h->n_slice ? h->d_QJs.p + (size_t)member * h->nnz_sell : nullptr);
   BT_CUDA(cudaGetLastError());
+  h->comb_members = members;
   h->comb_dt = dt; h->comb_theta = theta; h->comb_pc = pc;
   h->comb_g[0] = g[0]; h->comb_g[1] = g[1]; h->comb_g[2] = g[2];
 }
@@ -942,7 +1010,13 @@ void bt_spmv_bench(btfem* h, double dt, double theta, double c, const double g[3
   *ms = total / nrep;
 }
 
-void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_t* iters_per_step) {
+// `members` independent solves on the same mesh advance in lock step (one kernel launch covers all of them,
+// member = blockIdx.y); a single solve is the batch of one.  All members share nsteps, dt, theta and the Krylov
+// settings of sa[0]; direction, q (through cA/cb) differ.
+static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem_solve_out* outv,
+                       int32_t* iters_per_step) {
+  const btfem_solve_args* sa = &sav[0];
+  BT_REQUIRE(members >= 1 && members <= 65535, "bad batch size");
   BT_REQUIRE(sa->nsteps >= 0 && sa->dt > 0, "bad nsteps/dt");
   BT_REQUIRE(sa->theta > 0 && sa->theta <= 1, "theta must be in (0,1]");
   BT_REQUIRE(sa->ksp == BTFEM_KSP_BICGSTAB || sa->ksp == BTFEM_KSP_GMRES, "unknown Krylov method");
@@ -952,6 +1026,10 @@ void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_
     BT_REQUIRE(sa->Fb != nullptr, "periodic BC needs Fb (F(t_{n-1}) per step)");
     BT_REQUIRE(h->n_pb > 0, "periodic BC: call btfem_set_periodic_gather after btfem_assemble");
   }
+  BT_REQUIRE(members == 1 || (!gmres && !periodic), "batched solves support BiCGStab without periodic BC");
+  for (int b = 1; b < members; ++b)
+    BT_REQUIRE(sav[b].nsteps == sa->nsteps && sav[b].dt == sa->dt && sav[b].theta == sa->theta && sav[b].cA &&
+                   sav[b].cb, "batch members must share nsteps, dt and theta");
   cudaStream_t st = h->stream;
   const int n = (int)h->ndof;
   cudaEvent_t e0, e1, e2;
@@ -959,10 +1037,19 @@ void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_
   BT_CUDA(cudaEventCreate(&e1));
   BT_CUDA(cudaEventCreate(&e2));
   BT_CUDA(cudaEventRecord(e0, st));
-  bt_combine(h, sa->dt, sa->theta, sa->gdir, (int)sa->pc);
-  ensure_vectors(h);
-  h->d_cA.upload(sa->cA, sa->nsteps, st);
-  h->d_cb.upload(sa->cb, sa->nsteps, st);
+  for (int b = 0; b < members; ++b) bt_combine(h, sa->dt, sa->theta, sav[b].gdir, (int)sa->pc, b, members);
+  ensure_vectors(h, members);
+  h->step_stride = sa->nsteps;
+  {
+    std::vector<double> cA((size_t)members * sa->nsteps), cb((size_t)members * sa->nsteps);
+    for (int b = 0; b < members; ++b) {
+      std::copy(sav[b].cA, sav[b].cA + sa->nsteps, cA.begin() + (size_t)b * sa->nsteps);
+      std::copy(sav[b].cb, sav[b].cb + sa->nsteps, cb.begin() + (size_t)b * sa->nsteps);
+    }
+    h->d_cA.upload(cA.data(), cA.size(), st);
+    h->d_cb.upload(cb.data(), cb.size(), st);
+    BT_CUDA(cudaStreamSynchronize(st));
+  }
   if (periodic) {
     h->d_Fb.upload(sa->Fb, sa->nsteps, st);
     h->d_ubc.alloc(n);
@@ -970,7 +1057,7 @@ void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_
     h->d_ubc.zero(st);
     h->d_rhs_add.zero(st);
   }
-  k_set_ic<<<(n + TPB - 1) / TPB, TPB, 0, st>>>(n, h->d_ic_dof.p, h->d_u.p);
+  k_set_ic_batch<<<dim3((n + TPB - 1) / TPB, members), TPB, 0, st>>>(n, 7 * h->vec_npad, h->d_ic_dof.p, h->d_u.p);
   KrylovCtrl c0;
   memset(&c0, 0, sizeof(c0));
   c0.rtol = sa->rtol; c0.atol = sa->atol; c0.dtol = 1e4;
@@ -979,25 +1066,26 @@ void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_
   c0.maxit = (int)std::min<int64_t>(sa->maxit, 0x7fffffff);
   c0.nonzero_guess = sa->nonzero_guess ? 1 : 0;
   c0.done = 1;
-  *h->h_ctrl = c0;
-  BT_CUDA(cudaMemcpyAsync(h->d_ctrl.p, h->h_ctrl, sizeof(KrylovCtrl), cudaMemcpyHostToDevice, st));
+  for (int b = 0; b < members; ++b) h->h_ctrl[b] = c0;
+  BT_CUDA(cudaMemcpyAsync(h->d_ctrl.p, h->h_ctrl, sizeof(KrylovCtrl) * members, cudaMemcpyHostToDevice, st));
   BT_CUDA(cudaStreamSynchronize(st));   // h_ctrl is reused as the read-back buffer below
 
   SpmvArgs a = base_args(h);
   if (periodic) a.rhs_add = h->d_rhs_add.p;
   const int lanes = h->lanes;
-  const int vg = vec_grid(n);
+  // keep the total block count near a few waves: the x-extent shrinks as the batch grows
+  const int vgx = std::max(1, std::min(vec_grid(n), std::max(BT_NUM_SMS, BT_NUM_SMS * 8 / members)));
+  const dim3 vg(vgx, members);
 
-  // one BiCGStab iteration as a graph
+  // one BiCGStab iteration (of every member) as a graph
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   BT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  k_update_p<<<vg, TPB, 0, st>>>(n, h->d_ctrl.p, h->d_r.p, h->d_v.p, h->d_p.p);
-  launch_spmv<MODE_V>(lanes, a, st);
-  k_update_s<<<vg, TPB, 0, st>>>(n, h->d_ctrl.p, h->d_r.p, h->d_v.p, h->d_s.p);
-  launch_spmv<MODE_T>(lanes, a, st);
-  k_update_xr<<<vg, TPB, 0, st>>>(n, h->d_ctrl.p, h->d_partials.p, h->d_u.p, h->d_p.p, h->d_s.p, h->d_t.p,
-                                  h->d_rp.p, h->d_r.p);
+  k_update_p<<<vg, TPB, 0, st>>>(a);
+  launch_spmv<MODE_V>(lanes, a, st, members);
+  k_update_s<<<vg, TPB, 0, st>>>(a);
+  launch_spmv<MODE_T>(lanes, a, st, members);
+  k_update_xr<<<vg, TPB, 0, st>>>(a);
   BT_CUDA(cudaStreamEndCapture(st, &graph));
   if (h->l2_window_set) {   // captured kernel nodes do not inherit the stream's access-policy window
     size_t nn = 0;
@@ -1017,9 +1105,10 @@ void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_
   BT_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
 
   BT_CUDA(cudaEventRecord(e1, st));
-  int64_t total_iters = 0, max_iters = 0, n_spmv = 0, n_kernels = 0;
+  std::vector<int64_t> total_iters(members, 0), max_iters(members, 0);
+  std::vector<int> last_reason(members, 0);
+  int64_t n_spmv = 0, n_kernels = 0;
   int est = 4;
-  int last_reason = 0;
   int fail = 0;
   for (int64_t step = 0; step < sa->nsteps && !fail; ++step) {
     if (periodic) {
@@ -1031,20 +1120,20 @@ void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_
           h->d_ubc.p, h->d_rhs_add.p);
       n_kernels += 2;
     }
-    launch_spmv<MODE_RHS>(lanes, a, st);
+    launch_spmv<MODE_RHS>(lanes, a, st, members);
     ++n_kernels;
     if (sa->nonzero_guess) {
-      launch_spmv<MODE_RESID>(lanes, a, st);
+      launch_spmv<MODE_RESID>(lanes, a, st, members);
       ++n_kernels;
     }
     if (gmres) {
       int reason = 0;
       const int it = gmres_solve_step(h, sa, a, sa->cA[step], &n_spmv, &n_kernels, &reason);
       n_spmv += 1 + (sa->nonzero_guess ? 1 : 0);
-      total_iters += it;
-      max_iters = std::max<int64_t>(max_iters, it);
+      total_iters[0] += it;
+      max_iters[0] = std::max<int64_t>(max_iters[0], it);
       if (iters_per_step) iters_per_step[step] = it;
-      last_reason = reason;
+      last_reason[0] = reason;
       if (reason < 0) fail = reason;
       continue;
     }
@@ -1053,30 +1142,37 @@ void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_
     for (;;) {
       for (int i = 0; i < chunk; ++i) BT_CUDA(cudaGraphLaunch(gexec, st));
       launched += chunk;
-      BT_CUDA(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl.p, sizeof(KrylovCtrl), cudaMemcpyDeviceToHost, st));
+      BT_CUDA(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl.p, sizeof(KrylovCtrl) * members, cudaMemcpyDeviceToHost, st));
       BT_CUDA(cudaStreamSynchronize(st));
-      if (h->h_ctrl->done) break;
+      bool all = true;
+      for (int b = 0; b < members; ++b) all = all && h->h_ctrl[b].done;
+      if (all) break;
       chunk = std::max(1, std::min(8, launched / 8));
     }
     n_kernels += 5 * (int64_t)launched;
-    const int it = h->h_ctrl->iters;
-    n_spmv += 1 + (sa->nonzero_guess ? 1 : 0) + 2 * (int64_t)it;
-    total_iters += it;
-    max_iters = std::max<int64_t>(max_iters, it);
-    if (iters_per_step) iters_per_step[step] = it;
-    est = it;
-    last_reason = h->h_ctrl->reason;
-    // converged before the first iteration with a zero initial guess: PETSc returns x = 0
-    if (it == 0 && !sa->nonzero_guess && last_reason > 0) h->d_u.zero(st);
-    if (last_reason < 0) fail = last_reason;
+    est = 0;
+    for (int b = 0; b < members; ++b) {
+      const int it = h->h_ctrl[b].iters;
+      n_spmv += 1 + (sa->nonzero_guess ? 1 : 0) + 2 * (int64_t)it;
+      total_iters[b] += it;
+      max_iters[b] = std::max<int64_t>(max_iters[b], it);
+      est = std::max(est, it);
+      last_reason[b] = h->h_ctrl[b].reason;
+      // converged before the first iteration with a zero initial guess: PETSc returns x = 0
+      if (it == 0 && !sa->nonzero_guess && last_reason[b] > 0)
+        BT_CUDA(cudaMemsetAsync(h->d_u.p + (size_t)b * 7 * h->vec_npad, 0, sizeof(double2) * n, st));
+      if (last_reason[b] < 0) fail = last_reason[b];
+    }
+    if (iters_per_step) iters_per_step[step] = h->h_ctrl[0].iters;
   }
   BT_CUDA(cudaEventRecord(e2, st));
   DevArray<double> d_sig;
-  d_sig.alloc(2);
-  k_signal<<<vg, TPB, 0, st>>>(n, h->d_ctrl.p, h->d_partials.p, h->d_lumped.p, h->d_dof_comp.p, h->d_u.p, d_sig.p);
+  d_sig.alloc(2 * (size_t)members);
+  a.sig_out = d_sig.p;
+  k_signal<<<vg, TPB, 0, st>>>(a, h->d_lumped.p, h->d_dof_comp.p);
   BT_CUDA(cudaGetLastError());
-  double sig[2];
-  d_sig.download(sig, st);
+  std::vector<double> sig(2 * (size_t)members);
+  d_sig.download(sig.data(), st);
   float ms_setup = 0, ms_loop = 0;
   BT_CUDA(cudaEventElapsedTime(&ms_setup, e0, e1));
   BT_CUDA(cudaEventElapsedTime(&ms_loop, e1, e2));
@@ -1084,20 +1180,23 @@ void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_
   cudaGraphExecDestroy(gexec);
   cudaGraphDestroy(graph);
   h->have_solution = true;
-  out->signal_comp[0] = sig[0];
-  out->signal_comp[1] = sig[1];
-  out->signal = sig[0] + sig[1];
-  out->voi = h->voi;
-  out->voi_comp[0] = h->voi_comp[0];
-  out->voi_comp[1] = h->voi_comp[1];
-  out->whole_vol = h->whole_vol;
-  out->loop_ms = ms_loop;
-  out->setup_ms = ms_setup;
-  out->total_iters = total_iters;
-  out->max_iters = max_iters;
-  out->n_spmv = n_spmv;
-  out->n_kernels = n_kernels + 1;
-  out->last_reason = last_reason;
+  for (int b = 0; b < members; ++b) {
+    btfem_solve_out* out = &outv[b];
+    out->signal_comp[0] = sig[2 * b];
+    out->signal_comp[1] = sig[2 * b + 1];
+    out->signal = sig[2 * b] + sig[2 * b + 1];
+    out->voi = h->voi;
+    out->voi_comp[0] = h->voi_comp[0];
+    out->voi_comp[1] = h->voi_comp[1];
+    out->whole_vol = h->whole_vol;
+    out->loop_ms = ms_loop;
+    out->setup_ms = ms_setup;
+    out->total_iters = total_iters[b];
+    out->max_iters = max_iters[b];
+    out->n_spmv = n_spmv;
+    out->n_kernels = n_kernels + 1;
+    out->last_reason = last_reason[b];
+  }
   if (fail) {
     const char* what = fail == BTFEM_ENOTCONV ? "maximum iterations reached"
                        : fail == BTFEM_EBREAKDOWN ? "BiCGStab breakdown"
@@ -1105,4 +1204,12 @@ void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_
                                             : "residual diverged (dtol)";
     throw BtError{fail, std::string("Krylov solver did not converge: ") + what};
   }
+}
+
+void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_t* iters_per_step) {
+  solve_impl(h, 1, sa, out, iters_per_step);
+}
+
+void bt_solve_batch(btfem* h, int members, const btfem_solve_args* sa, btfem_solve_out* out) {
+  solve_impl(h, members, sa, out, nullptr);
 }

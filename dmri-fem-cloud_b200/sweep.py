@@ -15,28 +15,45 @@ def shard_units(n_units, rank, world):
     return list(range(rank, n_units, world))
 
 
-def run_sweep(fem, mri_para, sim, directions, bvalues, linsolver_params, rank=0, world=1):
+def run_sweep(fem, mri_para, sim, directions, bvalues, linsolver_params, rank=0, world=1, batch=1):
     """Solve this rank's share.  Returns (unit ids, normalized signals).  `fem` is an assembled
-    btfem.BTFem, `mri_para` a dmrifemlib.MRI_parameters with fs_sym/T set (Apply() is re-run per b)."""
+    btfem.BTFem, `mri_para` a dmrifemlib.MRI_parameters with fs_sym/T set (Apply() is re-run per b).
+    batch > 1: that many units advance in lock step per kernel launch (btfem_solve_batch)."""
     units = sweep_units(directions, bvalues)
     mine = shard_units(len(units), rank, world)
     ts = sim.time_grid(mri_para)
     tps = np.concatenate([[0.0], ts[:-1]])
     out = []
     cache = {}
-    for u in mine:
-        i, j = units[u]
+
+    def scalars(j):
         if j not in cache:
             mri_para.bvalue, mri_para.gvalue = bvalues[j], None
             mri_para.Apply()
             f, _ = mri_para.profiles_on_grid(ts)
             fp, Fp = mri_para.profiles_on_grid(tps)
             cache[j] = (mri_para.qvalue, f, fp, Fp)
-        q, f, fp, Fp = cache[j]
+        return cache[j]
+
+    def unit_dir(i):
         g = np.asarray(directions[i], dtype=float)
-        g = g / np.linalg.norm(g)
-        res = fem.solve(sim.k, sim.theta, q * f, q * fp, g, q=q, Fb=Fp, **linsolver_params)
-        out.append(res["signal"] / res["voi"])
+        return g / np.linalg.norm(g)
+
+    if batch <= 1:
+        for u in mine:
+            i, j = units[u]
+            q, f, fp, Fp = scalars(j)
+            res = fem.solve(sim.k, sim.theta, q * f, q * fp, unit_dir(i), q=q, Fb=Fp, **linsolver_params)
+            out.append(res["signal"] / res["voi"])
+    else:
+        for k0 in range(0, len(mine), batch):
+            members = []
+            for u in mine[k0:k0 + batch]:
+                i, j = units[u]
+                q, f, fp, _ = scalars(j)
+                members.append((q * f, q * fp, unit_dir(i)))
+            for res in fem.solve_batch(sim.k, sim.theta, members, **linsolver_params):
+                out.append(res["signal"] / res["voi"])
     return mine, np.array(out)
 
 

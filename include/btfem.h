@@ -159,6 +159,12 @@ typedef struct {
 
 int btfem_solve(btfem_t* h, const btfem_solve_args* args, btfem_solve_out* out,
                 int32_t* iters_per_step /*[nsteps] or NULL*/);
+/* `members` independent solves on the same mesh in lock step (HARDI sweeps: the reference loops serially over
+ * directions and b-values, ExplicitImplementation.ipynb cell 10): args[m] differ in gdir and cA/cb (q); nsteps, dt,
+ * theta and the Krylov settings are taken from args[0].  One kernel launch covers all members, so small meshes
+ * stop being launch-latency bound.  BiCGStab, no periodic BC. */
+int btfem_solve_batch(btfem_t* h, int32_t members, const btfem_solve_args* args /*[members]*/,
+                      btfem_solve_out* out /*[members]*/);
 /* solution after the last solve, dof numbering, interleaved (re,im) */
 int btfem_get_solution(btfem_t* h, double* u /*[2*ndof]*/);
 
