@@ -39,6 +39,9 @@ import __graft_entry__ as entry  # noqa: E402
 
 METRIC = "Bloch-Torrey DOF-steps/s"
 UNIT = "DOF-steps/s"
+# DRAM bytes of one k_spmv_sell<MODE_V> launch on the default workload, from the committed
+# `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_spmv_sell_full.txt)
+NCU_TRAFFIC = {"n_box": 78, "bytes": 167.227136e6 + 3.839232e6}
 
 
 def workload(n_box):
@@ -124,7 +127,11 @@ def cpu_restatement(xyz, tets, phase, mp, f, fp, k, sample_steps, mode=0):
     ops = orc.assemble(xyz, tets, phase, D=3e-3, invT2=1e-16, kappa=1e-5)
     q = mp.qvalue
     t0 = time.perf_counter()
-    u, iters = bt_cpu.theta_loop(ops, [0, 1, 0], k, 0.5, q * f[:sample_steps], q * fp[:sample_steps], mode=mode)
+    if mode == 2:      # DmriFemLib.solve work pattern: A and b re-assembled from the elements every step
+        u, iters = bt_cpu.theta_loop_reassemble(ops, xyz, tets, [0, 1, 0], k, 0.5, q * f[:sample_steps],
+                                                q * fp[:sample_steps], 3e-3, 1e-16, 1e-5)
+    else:
+        u, iters = bt_cpu.theta_loop(ops, [0, 1, 0], k, 0.5, q * f[:sample_steps], q * fp[:sample_steps], mode=mode)
     dt = time.perf_counter() - t0
     return {"seconds": dt, "ndof_real": 2 * ops.ndof, "steps": sample_steps, "iters": int(iters.sum()),
             "cores": bt_cpu.num_threads(), "signal": float(ops.lumped @ u.real)}
@@ -159,7 +166,7 @@ def main():
             res = cpu_restatement(xyz, tets, phase, mp, f, fp, k, 1)
         tsum, steps = 0.0, 0
         for _ in range(args.steps):
-            res = cpu_restatement(xyz, tets, phase, mp, f, fp, k, sample, mode=1)
+            res = cpu_restatement(xyz, tets, phase, mp, f, fp, k, sample, mode=2)
             tsum += res["seconds"]
             steps += sample
         v = res["ndof_real"] * steps / tsum
@@ -170,9 +177,11 @@ def main():
                 "config": {"workload": "configs[1] two-compartment permeable PGSE, cell-in-box n_box=%d" % args.n_box,
                            "ndof_real": res["ndof_real"], "theta_steps_per_solve": len(ts)},
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": res["cores"], "kind": "port",
-                                 "sample": "first %d of %d theta steps per bench step, C/OpenMP restatement "
-                                           "re-forming P,Q and the Jacobi diagonal every step (reference work "
-                                           "pattern); FEniCS/PETSc itself is not installable here" % (sample, len(ts))},
+                                 "sample": "first %d of %d theta steps per bench step; C/OpenMP restatement of "
+                                           "DmriFemLib.solve: A and b re-assembled from element integrals every step "
+                                           "(closed forms, cheaper than the reference's FFC kernels) + Jacobi-BiCGStab "
+                                           "at the CLI tolerances; FEniCS/PETSc itself is not installable here" % (
+                                               sample, len(ts))},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -319,7 +328,8 @@ def main():
                         "api": "dmrifemlib.MyDomain/MRI_simulation.solve (host numpy mesh -> signal)"},
                 "roofline": {"bound": "hbm", "kernel": ("k_spmv_sell<MODE_V|MODE_T>" if lanes == 0 else "k_spmv<%d,MODE_V|MODE_T>" % lanes) + " fused complex SpMV",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "peak_source": peak_src, "traffic": None,
+                             "peak_source": peak_src,
+                             "traffic": NCU_TRAFFIC["bytes"] if args.n_box == NCU_TRAFFIC["n_box"] and lanes == 0 else None,
                              "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch_l2_flushed": ms_cold,
                              "ms_per_launch_back_to_back": ms_warm,
                              "achieved_back_to_back": alg_bytes / (ms_warm * 1e-3) / 1e9,

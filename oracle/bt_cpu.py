@@ -52,3 +52,39 @@ def theta_loop(ops, gdir, k, theta, cA, cb, rtol=1e-9, atol=1e-10, maxit=100000,
     if rc != 0:
         raise RuntimeError("bt_cpu: Krylov failure %d" % rc)
     return u, iters
+
+
+def theta_loop_reassemble(ops, xyz, tets, gdir, k, theta, cA, cb, D, invT2, kappa, rtol=1e-9, atol=1e-10,
+                          maxit=100000, ic=None):
+    """DmriFemLib.solve work pattern (re-assemble A and b every step).  Scalar D, 1/T2, kappa."""
+    import bt_oracle as orc
+    g = np.asarray(gdir, dtype=float)
+    g = np.ascontiguousarray(g / np.linalg.norm(g))
+    n = ops.ndof
+    u = np.zeros(n, dtype=np.complex128)
+    u[:] = 1.0 if ic is None else ic
+    cA = np.ascontiguousarray(cA, dtype=float)
+    cb = np.ascontiguousarray(cb, dtype=float)
+    iters = np.zeros(len(cA), dtype=np.int32)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    rp = np.ascontiguousarray(ops.rowptr, dtype=np.int32)
+    ci = np.ascontiguousarray(ops.colidx, dtype=np.int32)
+    xyz = np.ascontiguousarray(xyz, dtype=float)
+    tets = np.ascontiguousarray(tets, dtype=np.int32)
+    cd = np.ascontiguousarray(ops.cell_dofs, dtype=np.int32)
+    if ops.phase is not None and len(ops.iface[0]):
+        fv = ops.iface[0]
+        ifd = np.ascontiguousarray(np.concatenate([ops.vc2dof[fv, 0], ops.vc2dof[fv, 1]], axis=1), dtype=np.int32)
+        coef = np.ascontiguousarray(kappa * orc.tri_area(xyz, fv) / 12.0)
+    else:
+        ifd = np.zeros((0, 6), dtype=np.int32)
+        coef = np.zeros(0)
+    f = lib().btcpu_theta_loop_reassemble
+    f.restype = C.c_int
+    rc = f(C.c_int(n), ip(rp), ip(ci), C.c_int(len(tets)), dp(xyz), ip(tets), ip(cd), C.c_double(D), C.c_double(invT2),
+           C.c_int(len(ifd)), ip(ifd), dp(coef), dp(g), C.c_double(k), C.c_double(theta), C.c_int(len(cA)), dp(cA),
+           dp(cb), C.c_double(rtol), C.c_double(atol), C.c_int(maxit), dp(u), ip(iters))
+    if rc != 0:
+        raise RuntimeError("bt_cpu: Krylov failure %d" % rc)
+    return u, iters

@@ -43,6 +43,43 @@ def ufc_tensors():
     print("ufc tensors:", {k: np.shape(v) for k, v in out.items()})
 
 
+
+
+def fixture_meshes():
+    """Oracle signals on the reference's own small mesh fixtures (comri/meshes/*.zip), BASELINE configs[0]/[1]
+    parameters.  The meshes themselves (tiny) are stored with the signals so that the GPU box, which has no
+    /root/reference, can run the same cases."""
+    ref = "/root/reference/comri/meshes"
+    out = {}
+    seq = orc.pgse(10600.0, 43100.0)
+    q = seq.q_from_b(1000.0)
+    for name in ("cyl6_r_3E_6_vol", "cyl12_r_3E_6_vol"):
+        xyz, tets, marker = meshes.read_gmsh2(os.path.join(ref, name + ".msh.zip"))
+        ops = orc.assemble(xyz, tets, D=3e-3, invT2=1e-16)
+        r = orc.theta_solve(ops, seq, q, [1, 0, 0], 200.0, solver="lu")        # -M 0 ... -gdir 1 0 0
+        out[name + "_xyz"], out[name + "_tets"] = xyz, tets
+        out[name + "_signal"], out[name + "_voi"] = r["signal"], r["voi"]
+        print(name, len(xyz), len(tets), r["signal"] / r["voi"])
+    # two-compartment torus (phase from the compartment sub-mesh), -M 1 -b 1000 -p 1e-5 -k 200 -gdir 0 1 0
+    xyz, tets = meshes.read_dolfin_xml(os.path.join(ref, "multi_layer_torus.xml.zip"))
+    sx, st = meshes.read_dolfin_xml(os.path.join(ref, "multi_layer_torus_compt1.xml.zip"))
+    phase = meshes.phase_from_submesh(xyz, tets, sx, st)
+    ops = orc.assemble(xyz, tets, phase, D=3e-3, invT2=1e-16, kappa=1e-5)
+    r = orc.theta_solve(ops, seq, q, [0, 1, 0], 200.0, solver="lu")
+    out["torus_xyz"], out["torus_tets"], out["torus_phase"] = xyz.astype(np.float32).astype(np.float64), tets, phase
+    # (coordinates are stored exactly; float32 round trip only to check they are representable -- they are not
+    # in general, so store float64)
+    out["torus_xyz"] = xyz
+    out["torus_signal"], out["torus_voi"], out["torus_ndof"] = r["signal"], r["voi"], ops.ndof
+    print("torus", len(xyz), len(tets), int(phase.sum()), ops.ndof, r["signal"] / r["voi"])
+    np.savez_compressed(os.path.join(HERE, "fixture_meshes.npz"), **out)
+
+
 if __name__ == "__main__":
-    convergence_box()
-    ufc_tensors()
+    which = sys.argv[1:] or ["box", "ufc", "fixtures"]
+    if "box" in which:
+        convergence_box()
+    if "ufc" in which:
+        ufc_tensors()
+    if "fixtures" in which:
+        fixture_meshes()

@@ -326,3 +326,40 @@ def test_batched_solves_equal_individual_solves():
         assert s1["total_iters"] == sb["total_iters"]
     assert again["signal"] == single[1]["signal"]
     assert len({round(s["signal"], 6) for s in batch}) == len(batch)         # the members really differ
+
+
+FIX = np.load(os.path.join(GOLDEN, "fixture_meshes.npz"))
+
+
+@pytest.mark.parametrize("name,gdir,two", [("cyl6_r_3E_6_vol", [1, 0, 0], False), ("cyl12_r_3E_6_vol", [1, 0, 0], False),
+                                          ("torus", [0, 1, 0], True)])
+def test_reference_mesh_fixtures(name, gdir, two):
+    """The reference's own meshes (comri/meshes/*.zip, stored in tests/golden/fixture_meshes.npz with the
+    oracle's exact-stepping signals): BASELINE configs[0] (-M 0 ... -gdir 1 0 0) and configs[1]
+    (-M 1 -b 1000 -p 1e-5 -k 200 -gdir 0 1 0) at the CLI's Krylov tolerances."""
+    xyz, tets = FIX[name + "_xyz"], FIX[name + "_tets"]
+    phase = FIX[name + "_phase"] if two else None
+    seq = orc.pgse(10600.0, 43100.0)
+    q = seq.q_from_b(1000.0)
+    ts = orc.time_grid(seq.T, 200.0)
+    f = np.array([seq.f(t) for t in ts])
+    fp = np.concatenate([[f[0]], f[:-1]])
+    with btfem.BTFem(0) as fem:
+        fem.set_mesh(xyz, tets, phase)
+        fem.set_diffusion(3e-3)
+        fem.set_relaxation(1e-16)
+        if two:
+            fem.set_permeability(1e-5)
+        fem.assemble()
+        if two:
+            assert fem.ndof == int(FIX["torus_ndof"])
+        else:
+            rp, ci = fem.pattern()
+            rps, cis = orc.scalar_pattern(len(xyz), tets)
+            assert np.array_equal(rp, rps) and np.array_equal(ci, cis)
+        tight = fem.solve(200.0, 0.5, q * f, q * fp, gdir, rtol=1e-13, atol=1e-16)
+        cli = fem.solve(200.0, 0.5, q * f, q * fp, gdir, rtol=1e-9, atol=1e-10)      # GCloudDmriSolver.py:219-222
+    want = float(FIX[name + "_signal"])
+    assert abs(tight["voi"] - float(FIX[name + "_voi"])) <= 1e-12 * tight["voi"]
+    assert abs(tight["signal"] - want) <= 1e-8 * abs(want)
+    assert abs(cli["signal"] - want) <= 1e-6 * abs(want)

@@ -101,3 +101,15 @@ def test_inactive_dofs_and_reference_layout():
     assert np.count_nonzero(full[0]) + np.count_nonzero(full[2]) == ops.ndof
     # rows of M sum to the lumped mass; whole volume is the box volume
     assert abs(ops.lumped.sum() - 20.0 ** 3) <= 1e-9 * 8000
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/comri/meshes"), reason="reference meshes not present")
+def test_fixture_golden_is_current():
+    """tests/golden/fixture_meshes.npz holds the reference's cyl6 mesh and the oracle signal on it."""
+    fix = np.load(os.path.join(GOLDEN, "fixture_meshes.npz"))
+    xyz, tets, _ = meshes.read_gmsh2("/root/reference/comri/meshes/cyl6_r_3E_6_vol.msh.zip")
+    assert np.array_equal(xyz, fix["cyl6_r_3E_6_vol_xyz"]) and np.array_equal(tets, fix["cyl6_r_3E_6_vol_tets"])
+    seq = orc.pgse(10600.0, 43100.0)
+    ops = orc.assemble(xyz, tets, D=3e-3, invT2=1e-16)
+    r = orc.theta_solve(ops, seq, seq.q_from_b(1000.0), [1, 0, 0], 200.0, solver="lu")
+    assert abs(r["signal"] - float(fix["cyl6_r_3E_6_vol_signal"])) <= 1e-13 * abs(r["signal"])
