@@ -1,4 +1,5 @@
-"""Config 5 (HARDI sweep on a neuron-like mesh): signals/s on this rank's share of directions x b-values."""
+"""Config 5 (HARDI sweep on a neuron-like mesh, 46 k vertices ~ `25o_spindle17aFI`): 64 directions x 4 b-values,
+sharded round-robin over ranks (torchrun), `batch` members per kernel launch.  Prints whole-job signals/s."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -7,7 +8,18 @@ import __graft_entry__ as e
 e.load_package()
 from dmri_fem_cloud_b200 import btfem, dmrifemlib as dl, meshes, sweep
 
-ndir = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+ndir = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+batch = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+rank = int(os.environ.get("RANK", "0"))
+local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+world = int(os.environ.get("WORLD_SIZE", "1"))
+dist = None
+if world > 1:
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
 xyz, tets = meshes.neuron_like(h=0.7)
 xyz, tets = meshes.rcm_order(*meshes.shuffle_vertices(xyz, tets, 0))
 mp = dl.MRI_parameters()
@@ -20,22 +32,27 @@ sim = dl.MRI_simulation()
 sim.k = 200.0
 dirs = meshes.fibonacci_hemisphere(ndir)
 bvals = [1000.0, 2000.0, 3000.0, 4000.0]
-fem = btfem.BTFem(0)
+fem = btfem.BTFem(local_rank)
 fem.set_mesh(xyz, tets)
 fem.set_diffusion(3e-3)
 fem.set_relaxation(1e-16)
 fem.assemble()
-print("mesh", len(xyz), len(tets), "nnz", fem.nnz)
 par = dict(rtol=1e-9, atol=1e-10, maxit=100000)
-sweep.run_sweep(fem, mp, sim, dirs[:1], bvals[:1], par)          # warm-up
+sweep.run_sweep(fem, mp, sim, dirs[:2], bvals[:2], par, batch=min(batch, 4))          # warm-up
+if dist is not None:
+    dist.barrier(); torch.cuda.synchronize()
 t0 = time.perf_counter()
-mine, sig = sweep.run_sweep(fem, mp, sim, dirs, bvals, par, batch=int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+mine, sig = sweep.run_sweep(fem, mp, sim, dirs, bvals, par, rank=rank, world=world, batch=batch)
+full = sweep.gather_signals(len(dirs) * len(bvals), mine, sig, dist)
+if dist is not None:
+    dist.barrier(); torch.cuda.synchronize()
 dt = time.perf_counter() - t0
-print("signals", len(sig), "seconds %.3f" % dt, "signals/s %.2f" % (len(sig) / dt), "ms/solve %.1f" % (1e3 * dt / len(sig)))
-r = fem.solve(200.0, 0.5, np.zeros(270), np.zeros(270), [1, 0, 0], **par)
-print("q=0 solve: iters", r["total_iters"], "loop_ms %.1f" % r["loop_ms"], "kernels", r["n_kernels"])
-mp.bvalue = 4000.0; mp.gvalue = None; mp.Apply()
-ts = sim.time_grid(mp); f, _ = mp.profiles_on_grid(ts); fp = np.concatenate([[f[0]], f[:-1]])
-r = fem.solve(200.0, 0.5, mp.qvalue * f, mp.qvalue * fp, dirs[0], **par)
-print("b=4000 solve: iters", r["total_iters"], "loop_ms %.1f" % r["loop_ms"], "us/iter %.1f" % (1e3 * r["loop_ms"] / r["total_iters"]), "signal", r["signal"] / r["voi"])
-print(sig[:8])
+if dist is not None:
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t[0])
+if rank == 0:
+    print("HARDI mesh %d verts %d tets | %d signals on %d GPU(s), batch %d: %.3f s -> %.2f signals/s | first %s | checksum %.12f"
+          % (len(xyz), len(tets), len(full), world, batch, dt, len(full) / dt, np.round(full[:4], 6), full.sum()))
+if dist is not None:
+    dist.destroy_process_group()
