@@ -65,6 +65,7 @@ def load_library(path=None):
         "btfem_set_relaxation": (C.c_int, [H, C.c_int, _c_double_p]),
         "btfem_set_permeability": (C.c_int, [H, C.c_int, _c_double_p, C.c_int32, _c_int32_p]),
         "btfem_set_periodic": (C.c_int, [H, _c_int32_p, C.c_double, C.c_double, _c_double_p, _c_double_p]),
+        "btfem_get_boundary_facets": (C.c_int, [H, _c_int32_p]),
         "btfem_set_periodic_gather": (C.c_int, [H, C.c_int64, _c_int32_p, _c_int32_p, _c_double_p, _c_double_p]),
         "btfem_set_initial": (C.c_int, [H, _c_double_p]),
         "btfem_assemble": (C.c_int, [H]),
@@ -189,6 +190,11 @@ class BTFem:
         lo = np.ascontiguousarray(lo, dtype=np.float64)
         hi = np.ascontiguousarray(hi, dtype=np.float64)
         self._ck(self.lib.btfem_set_periodic(self.h, _ip(p), float(kappa_e), float(tol), _dp(lo), _dp(hi)))
+
+    def boundary_facets(self):
+        out = np.empty((self.n_bfacet, 3), dtype=np.int32)
+        self._ck(self.lib.btfem_get_boundary_facets(self.h, _ip(out)))
+        return out
 
     def set_periodic_gather(self, dof, src, w, dx):
         dof = np.ascontiguousarray(dof, dtype=np.int32)

@@ -167,6 +167,13 @@ int btfem_set_periodic(btfem_t* h, const int32_t pdir[3], double kappa_e, double
   });
 }
 
+int btfem_get_boundary_facets(btfem_t* h, int32_t* verts) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->assembled && (verts || h->n_bfacet == 0), "call btfem_assemble first");
+    if (h->n_bfacet) h->d_bf_verts.download(verts, h->stream);
+  });
+}
+
 int btfem_set_periodic_gather(btfem_t* h, int64_t nb, const int32_t* dof, const int32_t* src, const double* w,
                               const double* dx) {
   return guarded(h, [&] {

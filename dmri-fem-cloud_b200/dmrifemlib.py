@@ -254,7 +254,8 @@ class MyDomain():
             dv, dc = fem.dofmap()
             fem.set_periodic_gather(*periodic.build_gather(
                 self.mymesh.xyz, self.mymesh.tets, phase, self.PeriodicDir,
-                [self.xmin, self.ymin, self.zmin], [self.xmax, self.ymax, self.zmax], dv, dc))
+                [self.xmin, self.ymin, self.zmin], [self.xmax, self.ymax, self.zmax], dv, dc,
+                bfacets=fem.boundary_facets()))
         return fem
 
 

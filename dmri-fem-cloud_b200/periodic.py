@@ -29,37 +29,38 @@ def _boundary_triangles(tets):
     return f[ext], cell[ext]
 
 
-def _locate(points2, tri_xy):
-    """For each 2-D point: containing triangle (or the closest one: extrapolation) and barycentric weights."""
+def _locate(points2, tri_xy, ncand=16):
+    """For each 2-D point: containing triangle (or the least-outside one among the `ncand` triangles with the
+    nearest centroids: extrapolation, like allow_extrapolation) and its barycentric weights.  Vectorised."""
+    from scipy.spatial import cKDTree
     a, b, c = tri_xy[:, 0], tri_xy[:, 1], tri_xy[:, 2]
     d = (b[:, 1] - c[:, 1]) * (a[:, 0] - c[:, 0]) + (c[:, 0] - b[:, 0]) * (a[:, 1] - c[:, 1])
     cen = tri_xy.mean(axis=1)
-    out_t = np.empty(len(points2), dtype=np.int64)
-    out_w = np.empty((len(points2), 3))
-    for i, p in enumerate(points2):
-        # candidates: the 16 triangles with the nearest centroids
-        k = min(16, len(cen))
-        cand = np.argpartition(((cen - p) ** 2).sum(axis=1), k - 1)[:k]
-        w0 = ((b[cand, 1] - c[cand, 1]) * (p[0] - c[cand, 0]) + (c[cand, 0] - b[cand, 0]) * (p[1] - c[cand, 1])) / d[cand]
-        w1 = ((c[cand, 1] - a[cand, 1]) * (p[0] - c[cand, 0]) + (a[cand, 0] - c[cand, 0]) * (p[1] - c[cand, 1])) / d[cand]
-        w2 = 1.0 - w0 - w1
-        W = np.stack([w0, w1, w2], axis=1)
-        best = np.argmax(W.min(axis=1))                  # inside: min weight >= 0; else least outside
-        out_t[i] = cand[best]
-        out_w[i] = W[best]
-    return out_t, out_w
+    k = min(ncand, len(cen))
+    _, cand = cKDTree(cen).query(points2, k=k)
+    cand = cand.reshape(len(points2), k)
+    px, py = points2[:, 0:1], points2[:, 1:2]
+    w0 = ((b[cand, 1] - c[cand, 1]) * (px - c[cand, 0]) + (c[cand, 0] - b[cand, 0]) * (py - c[cand, 1])) / d[cand]
+    w1 = ((c[cand, 1] - a[cand, 1]) * (px - c[cand, 0]) + (a[cand, 0] - c[cand, 0]) * (py - c[cand, 1])) / d[cand]
+    w2 = 1.0 - w0 - w1
+    W = np.stack([w0, w1, w2], axis=2)                    # (np, k, 3)
+    best = np.argmax(W.min(axis=2), axis=1)               # inside: min weight >= 0; else least outside
+    rows = np.arange(len(points2))
+    return cand[rows, best], W[rows, best]
 
 
-def build_gather(xyz, tets, phase, pdir, lo, hi, dof_vertex, dof_comp):
+def build_gather(xyz, tets, phase, pdir, lo, hi, dof_vertex, dof_comp, bfacets=None):
     """Returns dof (nb,), src (nb,3) dof ids or -1, w (nb,3), dx (nb,3).
 
+    bfacets: exterior facets touching the periodic faces (btfem_get_boundary_facets) -- found on the GPU during
+    assembly; None: search them here.
     dof_vertex/dof_comp: the library's dof map (btfem_get_dofmap).  Field `comp` evaluated at a vertex
     where that compartment is inactive is 0 (the reference's pinned dofs), i.e. src = -1."""
     xyz = np.asarray(xyz, dtype=float)
     nv = len(xyz)
     vc2dof = -np.ones((nv, 2), dtype=np.int64)
     vc2dof[dof_vertex, dof_comp] = np.arange(len(dof_vertex))
-    bf, _ = _boundary_triangles(np.asarray(tets))
+    bf = np.asarray(bfacets, dtype=np.int64) if bfacets is not None else _boundary_triangles(np.asarray(tets))[0]
     # per vertex: (direction, side) of the LAST matching periodic direction
     vdir = -np.ones(nv, dtype=np.int64)
     vside = np.zeros(nv, dtype=np.int64)

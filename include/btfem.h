@@ -81,6 +81,9 @@ int btfem_set_permeability(btfem_t* h, int kind, const double* kappa, int32_t nm
  * bbox lo/hi as printed by MyDomain (DmriFemLib.py:593). */
 int btfem_set_periodic(btfem_t* h, const int32_t pdir[3], double kappa_e, double tol,
                        const double lo[3], const double hi[3]);
+/* Exterior facets that touch the periodic marker (the facets B is assembled on), as sorted vertex triples;
+ * n_bfacet from btfem_get_sizes.  Lets the host build the periodic gather without its own facet search. */
+int btfem_get_boundary_facets(btfem_t* h, int32_t* verts /*[n_bfacet*3]*/);
 /* Gather operator of the weak pseudo-periodic BC (WeakPseudoPeriodic_*.eval, DmriFemLib.py:270-321): for
  * boundary dof `dof[b]`:  u_bc = exp(i*q*(g . dx[b])*F(t_p)) * sum_k w[b][k] * u[src[b][k]]   (src < 0: term is 0).
  * Built once per mesh by the host layer (periodic.build_gather); call after btfem_assemble. */

@@ -246,7 +246,11 @@ def test_weak_pseudo_periodic(case):
         assert np.array_equal(fem.pattern()[1], ops.colidx)
         assert _relmax(fem.values("B"), ops.B.data) <= 1e-12
         dv, dc = fem.dofmap()
-        fem.set_periodic_gather(*periodic.build_gather(xyz, tets, phase, pdir, lo, hi, dv, dc))
+        g_host = periodic.build_gather(xyz, tets, phase, pdir, lo, hi, dv, dc)
+        g_dev = periodic.build_gather(xyz, tets, phase, pdir, lo, hi, dv, dc, bfacets=fem.boundary_facets())
+        for x1, x2 in zip(g_host, g_dev):                    # GPU-found facets give the same operator
+            assert np.array_equal(x1, x2)
+        fem.set_periodic_gather(*g_dev)
         res = fem.solve(k, 0.5, q * f, q * fp, g, q=q, Fb=Fp, rtol=1e-13, atol=1e-16)
         u = fem.solution()
     assert abs(res["signal"] - ref["signal"]) <= 1e-8 * abs(ref["signal"])
@@ -363,3 +367,39 @@ def test_reference_mesh_fixtures(name, gdir, two):
     assert abs(tight["voi"] - float(FIX[name + "_voi"])) <= 1e-12 * tight["voi"]
     assert abs(tight["signal"] - want) <= 1e-8 * abs(want)
     assert abs(cli["signal"] - want) <= 1e-6 * abs(want)
+
+
+def test_edge_cases():
+    """Smallest and degenerate inputs: one tet; zero time steps; q = 0; an interface-free two-compartment mesh."""
+    xyz = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.0]])
+    tets = np.array([[0, 1, 2, 3]], dtype=np.int32)
+    ops = orc.assemble(xyz, tets, D=1e-3)
+    with btfem.BTFem(0) as fem:
+        fem.set_mesh(xyz, tets)
+        fem.set_diffusion(1e-3)
+        fem.assemble()
+        assert fem.ndof == 4 and fem.nnz == 16
+        assert _relmax(fem.values("S"), ops.S.data) <= 1e-13
+        res = fem.solve(10.0, 0.5, np.zeros(0), np.zeros(0), [1, 0, 0])           # no steps: u = IC
+        assert res["n_steps"] == 0 and abs(res["signal"] - 1.0 / 6.0) <= 1e-15
+        res = fem.solve(10.0, 0.5, np.full(5, 1e-3), np.full(5, 1e-3), [1, 0, 0], rtol=1e-13, atol=1e-18)
+        seq_c = 1e-3
+        u = np.ones(4, dtype=complex)
+        Jg = ops.Jx
+        for _ in range(5):
+            A = (ops.M / 10.0 + 0.5 * ops.S + 0.5j * seq_c * Jg).toarray()
+            b = (ops.M / 10.0 - 0.5 * ops.S - 0.5j * seq_c * Jg) @ u
+            u = np.linalg.solve(A, b)
+        assert abs(res["signal"] - float(ops.lumped @ u.real)) <= 1e-10 * abs(res["signal"])
+    # two "compartments" that never touch: all cells phase 1 -> no interface facets, compartment 0 empty
+    xyz2, tets2 = meshes.box_mesh((0,) * 3, (1,) * 3, 2, 2, 2)
+    ph = np.ones(len(tets2), dtype=np.int32)
+    ops2 = orc.assemble(xyz2, tets2, ph, D=1e-3, kappa=1e-5)
+    with btfem.BTFem(0) as fem:
+        fem.set_mesh(xyz2, tets2, ph)
+        fem.set_diffusion(1e-3)
+        fem.set_permeability(1e-5)
+        fem.assemble()
+        assert fem.n_iface == 0 and fem.ndof == ops2.ndof == len(xyz2)
+        res = fem.solve(10.0, 0.5, np.zeros(3), np.zeros(3), [0, 0, 1])
+        assert res["signal_comp"][0] == 0.0 and abs(res["signal_comp"][1] - 1.0) <= 1e-9      # default rtol 1e-9
