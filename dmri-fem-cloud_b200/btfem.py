@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbtfem.so")
 
 MAT_IDS = {"M": 0, "S": 1, "R": 2, "Jx": 3, "Jy": 4, "Jz": 5, "I": 6, "B": 7}
+DIST_BLOB_BYTES = 192   # BTFEM_DIST_BLOB_BYTES
 KSP_IDS = {"bicgstab": 0, "gmres": 1}
 PC_IDS = {"jacobi": 0, "none": 1}
 
@@ -81,6 +82,11 @@ def load_library(path=None):
         "btfem_solve": (C.c_int, [H, C.POINTER(SolveArgs), C.POINTER(SolveOut), _c_int32_p]),
         "btfem_solve_batch": (C.c_int, [H, C.c_int32, C.POINTER(SolveArgs), C.POINTER(SolveOut)]),
         "btfem_get_solution": (C.c_int, [H, _c_double_p]),
+        "btfem_set_partition": (C.c_int, [H, C.c_int64, C.c_int64]),
+        "btfem_get_partition": (C.c_int, [H, _c_int64_p, _c_int64_p, _c_int64_p]),
+        "btfem_dist_export": (C.c_int, [H, C.c_void_p]),
+        "btfem_dist_connect": (C.c_int, [H, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, _c_int32_p, _c_int32_p,
+                                         _c_int32_p, _c_int32_p]),
     }
     for name, (res, args) in proto.items():
         f = getattr(lib, name)
@@ -314,6 +320,31 @@ class BTFem:
             d["voi_comp"] = (o.voi_comp[0], o.voi_comp[1])
             res.append(d)
         return res
+
+    # ---- one mesh row-partitioned over several GPUs (host logic: partition.py)
+    def set_partition(self, nv_own, nv_interior):
+        self._ck(self.lib.btfem_set_partition(self.h, int(nv_own), int(nv_interior)))
+
+    def partition_sizes(self):
+        """(owned dofs, owned dofs no peer needs, element shift of halo dofs in the vectors)"""
+        s = [C.c_int64() for _ in range(3)]
+        self._ck(self.lib.btfem_get_partition(self.h, *[C.byref(x) for x in s]))
+        return tuple(int(x.value) for x in s)
+
+    def dist_export(self):
+        blob = np.zeros(DIST_BLOB_BYTES, dtype=np.uint8)
+        self._ck(self.lib.btfem_dist_export(self.h, blob.ctypes.data_as(C.c_void_p)))
+        return blob
+
+    def dist_connect(self, rank, world, blobs, src, dst_rank, dst_slot, recv_from):
+        blobs = np.ascontiguousarray(blobs, dtype=np.uint8).reshape(world, DIST_BLOB_BYTES)
+        src = np.ascontiguousarray(src, dtype=np.int32)
+        dst_rank = np.ascontiguousarray(dst_rank, dtype=np.int32)
+        dst_slot = np.ascontiguousarray(dst_slot, dtype=np.int32)
+        recv_from = np.ascontiguousarray(recv_from, dtype=np.int32)
+        assert len(src) == len(dst_rank) == len(dst_slot) and len(recv_from) == world
+        self._ck(self.lib.btfem_dist_connect(self.h, int(rank), int(world), blobs.ctypes.data_as(C.c_void_p),
+                                             len(src), _ip(src), _ip(dst_rank), _ip(dst_slot), _ip(recv_from)))
 
     def solution(self):
         u = np.empty(self.ndof, dtype=np.complex128)

@@ -27,6 +27,7 @@ void invalidate(btfem* h) {
   h->n_pb = 0;
   h->comb_dt = -1;
   h->have_solution = false;
+  bt_dist_close(h);   // the peers' halo maps describe the old numbering
 }
 
 }  // namespace
@@ -55,6 +56,7 @@ void btfem_destroy(btfem_t* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  bt_dist_close(h);
   if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
   if (h->h_gm) cudaFreeHost(h->h_gm);
   cudaStream_t st = h->stream;
@@ -299,7 +301,43 @@ int btfem_solve_batch(btfem_t* h, int32_t members, const btfem_solve_args* args,
 int btfem_get_solution(btfem_t* h, double* u) {
   return guarded(h, [&] {
     BT_REQUIRE(h->have_solution && u, "no solution yet");
+    if (h->nv_own >= 0) memset(u, 0, sizeof(double) * 2 * h->ndof);   // halo dofs belong to peers: reported as 0
     h->d_u.download(reinterpret_cast<double2*>(u), h->stream);
+  });
+}
+
+int btfem_set_partition(btfem_t* h, int64_t nv_own, int64_t nv_interior) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->nv > 0, "set the mesh first");
+    BT_REQUIRE(nv_own > 0 && nv_own <= h->nv && nv_interior >= 0 && nv_interior <= nv_own, "bad partition sizes");
+    h->nv_own = nv_own;
+    h->nv_int = nv_interior;
+    h->d_vecs.release();
+    invalidate(h);
+  });
+}
+
+int btfem_get_partition(btfem_t* h, int64_t* n_own, int64_t* n_interior, int64_t* halo_shift) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->assembled && h->nv_own >= 0, "partitioned, assembled handle required");
+    if (n_own) *n_own = h->n_own;
+    if (n_interior) *n_interior = h->n_int;
+    if (halo_shift) *halo_shift = h->halo_shift;
+  });
+}
+
+int btfem_dist_export(btfem_t* h, void* blob) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->assembled && blob, "call btfem_assemble first");
+    bt_dist_export(h, blob);
+  });
+}
+
+int btfem_dist_connect(btfem_t* h, int32_t rank, int32_t world, const void* blobs, int64_t nsend, const int32_t* src,
+                       const int32_t* dst_rank, const int32_t* dst_slot, const int32_t* recv_from) {
+  return guarded(h, [&] {
+    BT_REQUIRE(blobs && recv_from && nsend >= 0 && (nsend == 0 || (src && dst_rank && dst_slot)), "null argument");
+    bt_dist_connect(h, rank, world, blobs, nsend, src, dst_rank, dst_slot, recv_from);
   });
 }
 

@@ -84,6 +84,52 @@ struct KrylovCtrl {
   unsigned int ticket[8];
 };
 
+// ---- row partition of ONE mesh over several GPUs (one process per GPU, peer memory over NVLink) -------------
+#define BT_MAX_RANKS 8
+#define BT_COMM_ELEMS 64        // double2 elements reserved behind the vector slab for the DistComm block
+
+// Lives in the IPC-exported allocation of every rank; written by the PEERS with system-scope stores.
+struct DistComm {
+  unsigned long long halo_flag[BT_MAX_RANKS];     // [sender] = sequence number of the sender's last halo push
+  unsigned long long ar_flag[2][BT_MAX_RANKS];    // all-reduce: [buffer][sender] = sequence number
+  double ar_val[2][BT_MAX_RANKS][4];              // all-reduce payload
+};
+static_assert(sizeof(DistComm) <= BT_COMM_ELEMS * 16, "DistComm does not fit its reservation");
+
+// Device-resident description of the partition (local memory of each rank).
+struct DistDev {
+  int rank, world;
+  int n_send;                        // halo entries this rank pushes per exchange
+  int n_send_ranks, n_recv_ranks;
+  int send_ranks[BT_MAX_RANKS], recv_ranks[BT_MAX_RANKS];
+  int wait_slice;                    // SELL slices below this one never touch a halo column
+  int n_int;                         // owned rows [0,n_int) are not needed by any peer
+  int pad_;
+  DistComm* comm[BT_MAX_RANKS];      // comm block of every rank (own or peer-mapped)
+  double2* vecs[BT_MAX_RANKS];       // base of every rank's Krylov vector slab
+  long long npad[BT_MAX_RANKS];      // vector stride (elements) of every rank's slab
+  const int32_t* send_src;           // [n_send] local owned dof
+  const int32_t* send_rank;          // [n_send] destination rank
+  const int32_t* send_slot;          // [n_send] element index in the destination's vectors
+  // state (sequence numbers never reset: every rank runs the same sequence of exchanges)
+  unsigned long long push_seq, ar_seq;
+  unsigned long long timeout_ns;
+  unsigned int push_ticket;
+  int error;                         // a wait timed out: the solve is abandoned on every rank
+};
+
+// what the ranks exchange (through the host layer) before btfem_dist_connect
+struct DistBlob {
+  uint64_t magic;
+  int64_t pid;
+  uint64_t raw_ptr;
+  int64_t device;
+  int64_t npad, n_own, ndof;
+  cudaIpcMemHandle_t ipc;            // 64 bytes
+  char pad_[BTFEM_DIST_BLOB_BYTES - 7 * 8 - 64];
+};
+static_assert(sizeof(DistBlob) == BTFEM_DIST_BLOB_BYTES, "DistBlob size");
+
 struct FacetKey {
   uint32_t a, b, c;   // sorted vertex ids
   uint32_t cf;        // cell*4 + local facet
@@ -124,6 +170,17 @@ struct btfem {
   DevArray<double> d_if_kappa;     // [n_iface]
   DevArray<int32_t> d_bf_verts;    // [n_bfacet*3]
   DevArray<int32_t> d_bf_dofs;     // [n_bfacet*3]
+
+  // ---- row partition (nv_own < 0: the handle owns the whole mesh)
+  int64_t nv_own = -1, nv_int = -1;   // vertices [0,nv_own) owned, of which [0,nv_int) are not needed by peers
+  int64_t n_own = 0, n_int = 0;       // the same in dofs (set by the dof map)
+  int64_t halo_shift = 0;             // halo dof j sits at vector element j + halo_shift (128-byte aligned halo)
+  bool dist_connected = false, dist_failed = false;
+  int rank = 0, world = 1;
+  DevArray<DistDev> d_dist;
+  DevArray<int32_t> d_send_src, d_send_rank, d_send_slot;
+  void* peer_map[BT_MAX_RANKS] = {nullptr};   // cudaIpcOpenMemHandle mappings to close
+  int64_t n_rows() const { return nv_own >= 0 ? n_own : ndof; }
 
   // ---- pattern
   bool assembled = false;
@@ -199,3 +256,7 @@ void bt_spmv_bench(btfem* h, double dt, double theta, double c, const double g[3
                    double* ms);
 void bt_solve(btfem* h, const btfem_solve_args* a, btfem_solve_out* out, int32_t* iters_per_step);
 void bt_solve_batch(btfem* h, int members, const btfem_solve_args* a, btfem_solve_out* out);
+void bt_dist_export(btfem* h, void* blob);
+void bt_dist_connect(btfem* h, int rank, int world, const void* blobs, int64_t nsend, const int32_t* src,
+                     const int32_t* dst_rank, const int32_t* dst_slot, const int32_t* recv_from);
+void bt_dist_close(btfem* h);

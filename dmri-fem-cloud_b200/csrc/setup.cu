@@ -255,9 +255,11 @@ __global__ void k_diagpos(int64_t ndof, const int32_t* __restrict__ rowptr, cons
 
 // SELL-32 column indices: slot (slice, lane) copies its row's columns to slice-column-major order;
 // padding entries point at the row itself (a valid address; their values are zero).
+// Row-partitioned handles: columns >= n_own are halo dofs, stored as vector ELEMENT indices (col + halo_shift).
 __global__ void k_sell_columns(int64_t nslice, const int32_t* __restrict__ slice_ptr,
                                const int32_t* __restrict__ sell_row, const int32_t* __restrict__ rowptr,
-                               const int32_t* __restrict__ colidx, int32_t* __restrict__ sell_col) {
+                               const int32_t* __restrict__ colidx, int32_t* __restrict__ sell_col, int n_own,
+                               int halo_shift) {
   int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (slot >= nslice * 32) return;
   const int64_t s = slot >> 5;
@@ -267,7 +269,11 @@ __global__ void k_sell_columns(int64_t nslice, const int32_t* __restrict__ slice
   const int row = sell_row[slot];
   const int k0 = row >= 0 ? rowptr[row] : 0;
   const int len = row >= 0 ? rowptr[row + 1] - k0 : 0;
-  for (int j = 0; j < width; ++j) sell_col[base + j * 32 + lane] = j < len ? colidx[k0 + j] : (row >= 0 ? row : 0);
+  for (int j = 0; j < width; ++j) {
+    int c = j < len ? colidx[k0 + j] : (row >= 0 ? row : 0);
+    if (c >= n_own) c += halo_shift;
+    sell_col[base + j * 32 + lane] = c;
+  }
 }
 
 // ------------------------------------------------------------------------------------ assembly
@@ -442,6 +448,18 @@ void bt_build_dofmap(btfem* h) {
         h->h_dof_comp.push_back(c);
       }
   h->ndof = n;
+  // row partition: dofs are vertex-major, so the owned (and the peer-independent) dofs are prefixes
+  h->n_own = n;
+  h->n_int = n;
+  h->halo_shift = 0;
+  if (h->nv_own >= 0) {
+    BT_REQUIRE(h->nv_own <= nv && h->nv_int <= h->nv_own, "partition sizes exceed the local mesh");
+    h->n_own = std::lower_bound(h->h_dof_vertex.begin(), h->h_dof_vertex.end(), (int32_t)h->nv_own) -
+               h->h_dof_vertex.begin();
+    h->n_int = std::lower_bound(h->h_dof_vertex.begin(), h->h_dof_vertex.end(), (int32_t)h->nv_int) -
+               h->h_dof_vertex.begin();
+    h->halo_shift = ((h->n_own + 7) & ~(int64_t)7) - h->n_own;   // halo entries start on a 128-byte line
+  }
   std::vector<int32_t> cell_dofs(4 * nc);
   for (int64_t c = 0; c < nc; ++c) {
     int ph = h->two_comp ? h->h_phase[c] : 0;
@@ -578,9 +596,9 @@ void bt_build_pattern(btfem* h) {
   // result is deterministic), cut into slices of 32 slots, slice width = longest row of the slice.
   std::vector<int32_t> rp(h->ndof + 1);
   h->d_rowptr.download(rp.data(), st);
-  const int64_t n = h->ndof;
+  const int64_t n = h->n_rows();   // row-partitioned: only owned rows are ever multiplied
   const int64_t nslice = (n + 31) / 32;
-  std::vector<int32_t> sell_row(nslice * 32, -1), sell_slot(n), slice_ptr(nslice + 1, 0);
+  std::vector<int32_t> sell_row(nslice * 32, -1), sell_slot(h->ndof, -1), slice_ptr(nslice + 1, 0);
   for (int64_t i = 0; i < n; ++i) sell_row[i] = (int32_t)i;
   for (int64_t w0 = 0; w0 < n; w0 += BT_SELL_SIGMA) {
     const int64_t w1 = std::min<int64_t>(n, w0 + BT_SELL_SIGMA);
@@ -610,7 +628,8 @@ void bt_build_pattern(btfem* h) {
   h->d_sell_slot.upload(sell_slot.data(), sell_slot.size(), st);
   h->d_sell_col.alloc(tot);
   k_sell_columns<<<nblocks(nslice * 32), TPB, 0, st>>>(nslice, h->d_slice_ptr.p, h->d_sell_row.p, h->d_rowptr.p,
-                                                      h->d_colidx.p, h->d_sell_col.p);
+                                                      h->d_colidx.p, h->d_sell_col.p, (int)h->n_own,
+                                                      (int)h->halo_shift);
   h->d_PJs.release();
   h->d_QJs.release();
   BT_CUDA(cudaGetLastError());
@@ -652,6 +671,7 @@ void bt_assemble_values(btfem* h) {
   for (int64_t i = 0; i < h->ndof; ++i) {
     double v = h->h_ic.empty() ? 1.0 : h->h_ic[h->h_dof_vertex[i]];
     ic[i] = v;
+    if (i >= h->n_rows()) continue;   // halo rows are incomplete and belong to a peer
     vol += lumped[i];
     voi += lumped[i] * v;
     vc[h->h_dof_comp[i]] += lumped[i] * v;

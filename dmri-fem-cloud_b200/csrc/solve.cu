@@ -15,6 +15,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <unistd.h>
+
 #include <vector>
 
 #include "btfem_internal.cuh"
@@ -33,10 +35,83 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Block partial -> partials[q][blockIdx.x]; the last block to arrive sums all partials in a fixed order.
-// Returns true in thread 0 of that last block with v[] = grand totals.
+// ------------------------------------------------------------------------------------ peer-memory primitives
+// Row-partitioned solves (one rank per GPU): flags and payloads live in the peers' DistComm blocks and are
+// accessed with system-scope acquire/release; every wait is bounded so that a lost peer ends the solve with
+// BTFEM_ECOMM instead of hanging the GPU.
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __noinline__ bool spin_until(const unsigned long long* flag, unsigned long long seq,
+                                        unsigned long long timeout_ns) {
+  if (ld_acquire_sys(flag) >= seq) return true;
+  const unsigned long long t0 = global_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 32; ++i)
+      if (ld_acquire_sys(flag) >= seq) return true;
+    if (global_ns() - t0 > timeout_ns) return false;
+  }
+}
+
+// All-reduce of NV doubles over the ranks, called by the 32 lanes of ONE warp per rank (v identical in all
+// lanes).  Lane r stores this rank's terms into rank r's comm block, then publishes the sequence number;
+// lane r then waits for rank r's terms.  The sum runs in rank order, so every rank gets the same bits.
+// Two payload buffers alternate: a rank can be at most one all-reduce ahead of the slowest rank.
 template <int NV>
-__device__ bool reduce_finalize(double (&v)[NV], double* __restrict__ partials, unsigned int* ticket) {
+__device__ __forceinline__ void dist_allreduce(double (&v)[NV], DistDev* d) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long seq = d->ar_seq + 1;
+  const int buf = (int)(seq & 1);
+  const int rank = d->rank, world = d->world;
+  __syncwarp();
+  if (lane < world) {
+    DistComm* pc = d->comm[lane];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) *(volatile double*)&pc->ar_val[buf][rank][q] = v[q];
+    __threadfence_system();
+    st_release_sys(&pc->ar_flag[buf][rank], seq);
+  }
+  double mine[NV];
+  bool ok = true;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) mine[q] = 0.0;
+  if (lane < world) {
+    DistComm* me = d->comm[rank];
+    ok = spin_until(&me->ar_flag[buf][lane], seq, d->timeout_ns);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) mine[q] = *(volatile double*)&me->ar_val[buf][lane][q];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    double t = 0.0;
+    for (int r = 0; r < world; ++r) t += __shfl_sync(0xffffffffu, mine[q], r);
+    v[q] = t;
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  if (lane == 0) {
+    d->ar_seq = seq;
+    if (!ok) d->error = 1;
+  }
+  __syncwarp();
+}
+
+// Block partial -> partials[q][blockIdx.x]; the last block to arrive sums all partials in a fixed order.
+// Returns true in thread 0 of that last block with v[] = grand totals (over all ranks when `dist` is set).
+template <int NV>
+__device__ bool reduce_finalize(double (&v)[NV], double* __restrict__ partials, unsigned int* ticket,
+                                DistDev* dist = nullptr) {
   __shared__ double sm[NV][NWARP];
   __shared__ int s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -78,6 +153,7 @@ __device__ bool reduce_finalize(double (&v)[NV], double* __restrict__ partials, 
       double t = lane < NWARP ? sm[q][lane] : 0.0;
       v[q] = warp_sum(t);
     }
+    if (dist) dist_allreduce<NV>(v, dist);
   }
   if (threadIdx.x == 0) *ticket = 0;
   return threadIdx.x == 0;
@@ -117,6 +193,7 @@ __global__ void k_combine(int64_t nnz, const int32_t* __restrict__ rowidx, const
   if (PJs) {   // same entry in the SELL-32 layout: slice base + (position in row)*32 + slot lane
     const int row = rowidx[k];
     const int slot = sell_slot[row];
+    if (slot < 0) return;   // halo row of a row-partitioned handle
     const int pos = slice_ptr[slot >> 5] + (int)(k - rowptr[row]) * 32 + (slot & 31);
     PJs[pos] = pj;
     QJs[pos] = qj;
@@ -153,7 +230,13 @@ struct SpmvArgs {
   // strides between consecutive members.  The pattern arrays are shared.
   size_t mat_stride_csr, mat_stride_sell, vec_stride, part_stride, step_stride;
   double* sig_out;           // k_signal: [members][2]
+  DistDev* dist;             // row-partitioned solve: peers, halo send list, sequence numbers (else null)
 };
+
+// a lost peer ends the solve on every rank
+__device__ __forceinline__ void comm_check(const SpmvArgs& a) {
+  if (a.dist && a.dist->error) { a.ctrl->done = 1; a.ctrl->reason = BTFEM_ECOMM; }
+}
 
 // arguments of batch member blockIdx.y
 __device__ __forceinline__ SpmvArgs member(SpmvArgs a) {
@@ -240,7 +323,7 @@ __device__ __forceinline__ void mode_finalize(const SpmvArgs& a, double (&acc)[2
   if (MODE == MODE_PLAIN) return;
   if (MODE == MODE_RHS) {
     double v1[1] = {acc[0]};
-    if (reduce_finalize<1>(v1, a.partials, &ctrl->ticket[TK_RHS])) {
+    if (reduce_finalize<1>(v1, a.partials, &ctrl->ticket[TK_RHS], a.dist)) {
       double bn = sqrt(v1[0]);
       ctrl->bnorm = bn;
       ctrl->ttol = fmax(ctrl->rtol * bn, ctrl->atol);
@@ -255,26 +338,30 @@ __device__ __forceinline__ void mode_finalize(const SpmvArgs& a, double (&acc)[2
         if (!(bn == bn) || isinf(bn)) { ctrl->done = 1; ctrl->reason = BTFEM_ENAN; }
         else if (bn <= ctrl->ttol) { ctrl->done = 1; ctrl->reason = bn < ctrl->atol ? 3 : 2; }
       }
+      comm_check(a);
     }
   } else if (MODE == MODE_RESID) {
     double v1[1] = {acc[0]};
-    if (reduce_finalize<1>(v1, a.partials, &ctrl->ticket[TK_RESID])) {
+    if (reduce_finalize<1>(v1, a.partials, &ctrl->ticket[TK_RESID], a.dist)) {
       double rn = sqrt(v1[0]);
       ctrl->rho = v1[0];
       ctrl->rnorm = rn;
       if (!(rn == rn) || isinf(rn)) { ctrl->done = 1; ctrl->reason = BTFEM_ENAN; }
       else if (rn <= ctrl->ttol) { ctrl->done = 1; ctrl->reason = rn < ctrl->atol ? 3 : 2; }
+      comm_check(a);
     }
   } else if (MODE == MODE_V) {
     double v1[1] = {acc[0]};
-    if (reduce_finalize<1>(v1, a.partials + 2 * BT_MAX_PARTIALS, &ctrl->ticket[TK_V])) {
+    if (reduce_finalize<1>(v1, a.partials + 2 * BT_MAX_PARTIALS, &ctrl->ticket[TK_V], a.dist)) {
       if (v1[0] == 0.0) { ctrl->done = 1; ctrl->reason = BTFEM_EBREAKDOWN; ctrl->alpha = 0.0; }
       else ctrl->alpha = ctrl->rho / v1[0];
+      comm_check(a);
     }
   } else {
     double v2[2] = {acc[0], acc[1]};
-    if (reduce_finalize<2>(v2, a.partials + 3 * BT_MAX_PARTIALS, &ctrl->ticket[TK_T])) {
+    if (reduce_finalize<2>(v2, a.partials + 3 * BT_MAX_PARTIALS, &ctrl->ticket[TK_T], a.dist)) {
       ctrl->omega = (v2[1] == 0.0) ? 0.0 : v2[0] / v2[1];
+      comm_check(a);
     }
   }
 }
@@ -347,6 +434,46 @@ __device__ __forceinline__ double2 ldv_gather_f64x2(const double2* p) {
   return v;
 }
 
+// One warp waits until every peer that sends to this rank has published the current exchange.  The halo
+// region of x starts on its own 128-byte line, so no line holding halo entries is cached before this returns.
+__device__ __forceinline__ void halo_wait(DistDev* d) {
+  const int lane = threadIdx.x & 31;
+  if (lane < d->n_recv_ranks) {
+    if (!spin_until(&d->comm[d->rank]->halo_flag[d->recv_ranks[lane]], d->push_seq, d->timeout_ns)) d->error = 1;
+  }
+  __syncwarp();
+}
+
+// Halo push: entries of a freshly produced vector (WHICH: 0 = u, 1 = p, 2 = s) that peers need are stored
+// straight into the peers' vectors over NVLink; the last block then publishes the sequence number.
+template <int WHICH>
+__global__ void __launch_bounds__(TPB) k_halo_push(SpmvArgs a, int check_done) {
+  DistDev* d = a.dist;
+  if (check_done && a.ctrl->done) return;
+  __shared__ int s_last;
+  const double2* __restrict__ src = WHICH == 0 ? a.u : (WHICH == 1 ? a.p : a.s);
+  const int vi = WHICH == 0 ? 0 : (WHICH == 1 ? 3 : 5);   // slab order: u r rp p v s t
+  const int ns = d->n_send;
+  for (int e = blockIdx.x * TPB + threadIdx.x; e < ns; e += gridDim.x * TPB) {
+    const int r = d->send_rank[e];
+    const double2 v = src[d->send_src[e]];
+    d->vecs[r][(size_t)vi * d->npad[r] + d->send_slot[e]] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&d->push_ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  const unsigned long long seq = d->push_seq + 1;
+  __syncthreads();
+  if (threadIdx.x < d->n_send_ranks) st_release_sys(&d->comm[d->send_ranks[threadIdx.x]]->halo_flag[d->rank], seq);
+  if (threadIdx.x == 0) {
+    d->push_seq = seq;
+    d->push_ticket = 0;
+  }
+}
+
 // ---- variant C (default): SELL-32.  Rows are grouped in slices of 32 (after sorting by length inside
 // windows of BT_SELL_SIGMA rows to bound padding); a slice is stored column-major, so lane l of a warp owns
 // row-slot l and every warp-wide load of (column, value pair) is one fully coalesced 128 B / 512 B request.
@@ -365,7 +492,16 @@ __global__ void __launch_bounds__(TPB, MINB) k_spmv_sell(SpmvArgs a_in) {
   const int lane = threadIdx.x & 31;
   const int wpb = TPB / 32;
   double acc[2] = {0.0, 0.0};
+  // row-partitioned: slices below wait_slice hold rows without halo columns and start at once; the peers'
+  // halo entries of x are awaited (per warp, once) only when the first slice that may need them is reached
+  bool halo_ready = (MODE == MODE_PLAIN) || a.dist == nullptr;
   for (int slice = blockIdx.x * wpb + (threadIdx.x >> 5); slice < a.nslice; slice += gridDim.x * wpb) {
+    if (!halo_ready) {
+      if (slice >= a.dist->wait_slice) {
+        halo_wait(a.dist);
+        halo_ready = true;
+      }
+    }
     const int base = __ldg(a.slice_ptr + slice);
     const int width = (__ldg(a.slice_ptr + slice + 1) - base) >> 5;
     const int row = __ldg(a.sell_row + slice * 32 + lane);       // -1: padding slot past the last row
@@ -395,7 +531,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_spmv_sell(SpmvArgs a_in) {
     for (; j < width; ++j) {
       const int col = ld_stream(cp + j * 32);
       const double2 val = ld_stream(vp + j * 32);
-      const double2 xv = __ldg(m.x + col);
+      const double2 xv = ldv_gather_f64x2(m.x + col);   // not .nc: halo entries of x arrive during the kernel
       const double pa = val.x, pb = m.c * val.y;
       ar = fma(pa, xv.x, ar);
       ar = fma(-pb, xv.y, ar);
@@ -466,7 +602,7 @@ __global__ void __launch_bounds__(TPB) k_update_xr(SpmvArgs a_in) {
     acc[0] += rr.x * q.x + rr.y * q.y;
     acc[1] += rr.x * rr.x + rr.y * rr.y;
   }
-  if (reduce_finalize<2>(acc, a.partials + 5 * BT_MAX_PARTIALS, &ctrl->ticket[TK_XR])) {
+  if (reduce_finalize<2>(acc, a.partials + 5 * BT_MAX_PARTIALS, &ctrl->ticket[TK_XR], a.dist)) {
     const double rho_used = ctrl->rho;
     ctrl->rho_old = rho_used;
     ctrl->rho = acc[0];
@@ -479,6 +615,7 @@ __global__ void __launch_bounds__(TPB) k_update_xr(SpmvArgs a_in) {
     else if (dp >= ctrl->dtol * ctrl->bnorm) { ctrl->done = 1; ctrl->reason = BTFEM_EDTOL; }
     else if (rho_used == 0.0 || omega == 0.0) { ctrl->done = 1; ctrl->reason = BTFEM_EBREAKDOWN; }
     else if (it >= ctrl->maxit) { ctrl->done = 1; ctrl->reason = BTFEM_ENOTCONV; }
+    comm_check(a);
   }
 }
 
@@ -547,7 +684,7 @@ __global__ void __launch_bounds__(TPB) k_signal(SpmvArgs a_in, const double* __r
     double w = lumped[i] * u[i].x;
     if (comp[i] == 0) acc[0] += w; else acc[1] += w;
   }
-  if (reduce_finalize<2>(acc, a.partials + 6 * BT_MAX_PARTIALS, &a.ctrl->ticket[TK_SIG])) {
+  if (reduce_finalize<2>(acc, a.partials + 6 * BT_MAX_PARTIALS, &a.ctrl->ticket[TK_SIG], a.dist)) {
     a.sig_out[0] = acc[0];
     a.sig_out[1] = acc[1];
   }
@@ -727,7 +864,8 @@ void launch_spmv(int lanes, SpmvArgs a, cudaStream_t st, int members = 1) {
 SpmvArgs base_args(btfem* h) {
   SpmvArgs a;
   memset(&a, 0, sizeof(a));
-  a.n = (int)h->ndof;
+  a.n = (int)h->n_rows();
+  a.dist = h->dist_connected ? h->d_dist.p : nullptr;
   a.rowptr = h->d_rowptr.p;
   a.colidx = h->d_colidx.p;
   a.nslice = (int)h->n_slice;
@@ -753,16 +891,22 @@ SpmvArgs base_args(btfem* h) {
 
 // Krylov vectors of `members` independent solves: member b owns slab [b*7*npad, (b+1)*7*npad)
 void ensure_vectors(btfem* h, int members = 1) {
-  const size_t n = (size_t)h->ndof;
+  // row-partitioned: halo entries sit halo_shift elements further (own 128-byte line) and the DistComm block
+  // follows the seven vectors inside the same (IPC-exported) allocation
+  const bool part = h->nv_own >= 0;
+  BT_REQUIRE(!part || members == 1, "row-partitioned handles solve one system at a time");
+  const size_t n = (size_t)h->ndof + (size_t)h->halo_shift;
   const size_t npad = (n + 15) & ~(size_t)15;           // keep every vector 256-byte aligned
   h->vec_npad = npad;
-  if (h->d_vecs.n != (size_t)members * 7 * npad) {
-    h->d_vecs.alloc((size_t)members * 7 * npad);
+  const size_t total = (size_t)members * 7 * npad + (part ? BT_COMM_ELEMS : 0);
+  if (h->d_vecs.n != total) {
+    BT_REQUIRE(!h->dist_connected, "vector slab of a connected partition cannot be re-allocated");
+    h->d_vecs.alloc(total);
     h->d_vecs.zero(h->stream);
     btfem::VecView* views[7] = {&h->d_u, &h->d_r, &h->d_rp, &h->d_p, &h->d_v, &h->d_s, &h->d_t};
     for (int i = 0; i < 7; ++i) {
       views[i]->p = h->d_vecs.p + i * npad;
-      views[i]->n = n;
+      views[i]->n = (size_t)h->n_rows();
     }
     h->l2_window_set = false;
     const char* env = getenv("BTFEM_L2_PERSIST");
@@ -948,9 +1092,21 @@ void bt_spmv_host(btfem* h, double dt, double theta, double c, const double g[3]
   bt_combine(h, dt, theta, g, BTFEM_PC_NONE);
   ensure_vectors(h);
   DevArray<double2> dx, dy;
-  dx.upload(reinterpret_cast<const double2*>(x), h->ndof, st);
+  const double2* x2 = reinterpret_cast<const double2*>(x);
+  if (h->nv_own >= 0) {   // local rows of a partition: x holds owned + halo dofs, y only the owned rows
+    BT_REQUIRE(h->lanes == 0, "row-partitioned handles use the SELL-32 kernel");
+    dx.alloc(h->ndof + h->halo_shift);
+    BT_CUDA(cudaMemcpyAsync(dx.p, x2, sizeof(double2) * h->n_own, cudaMemcpyHostToDevice, st));
+    if (h->ndof > h->n_own)
+      BT_CUDA(cudaMemcpyAsync(dx.p + h->n_own + h->halo_shift, x2 + h->n_own, sizeof(double2) * (h->ndof - h->n_own),
+                              cudaMemcpyHostToDevice, st));
+  } else {
+    dx.upload(x2, h->ndof, st);
+  }
   dy.alloc(h->ndof);
+  dy.zero(st);
   SpmvArgs a = base_args(h);
+  a.dist = nullptr;
   a.x_plain = dx.p;
   a.y_plain = dy.p;
   a.c_plain = theta * c;       // A = P + i*theta*c*Jg
@@ -962,6 +1118,7 @@ void bt_spmv_host(btfem* h, double dt, double theta, double c, const double g[3]
 void bt_spmv_bench(btfem* h, double dt, double theta, double c, const double g[3], int lanes, int nrep, int flush_l2,
                    double* ms) {
   cudaStream_t st = h->stream;
+  BT_REQUIRE(h->nv_own < 0, "the SpMV bench hook works on whole-mesh handles");
   bt_combine(h, dt, theta, g, BTFEM_PC_JACOBI);
   ensure_vectors(h);
   DevArray<double2> dx, dy;
@@ -1027,11 +1184,18 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     BT_REQUIRE(h->n_pb > 0, "periodic BC: call btfem_set_periodic_gather after btfem_assemble");
   }
   BT_REQUIRE(members == 1 || (!gmres && !periodic), "batched solves support BiCGStab without periodic BC");
+  const bool part = h->nv_own >= 0;
+  if (part) {
+    BT_REQUIRE(h->dist_connected, "row-partitioned handle: call btfem_dist_connect before btfem_solve");
+    BT_REQUIRE(!h->dist_failed, "a previous row-partitioned solve lost a peer; rebuild the handles");
+    BT_REQUIRE(!gmres && !periodic && members == 1 && h->lanes == 0,
+               "row-partitioned solves support BiCGStab on the SELL-32 kernel, without periodic BC");
+  }
   for (int b = 1; b < members; ++b)
     BT_REQUIRE(sav[b].nsteps == sa->nsteps && sav[b].dt == sa->dt && sav[b].theta == sa->theta && sav[b].cA &&
                    sav[b].cb, "batch members must share nsteps, dt and theta");
   cudaStream_t st = h->stream;
-  const int n = (int)h->ndof;
+  const int n = (int)h->n_rows();
   cudaEvent_t e0, e1, e2;
   BT_CUDA(cudaEventCreate(&e0));
   BT_CUDA(cudaEventCreate(&e1));
@@ -1081,12 +1245,16 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
   BT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const int push_grid = part ? std::max(1, std::min(32, ((int)h->d_send_src.n + TPB - 1) / TPB)) : 0;
   k_update_p<<<vg, TPB, 0, st>>>(a);
+  if (part) k_halo_push<1><<<push_grid, TPB, 0, st>>>(a, 1);
   launch_spmv<MODE_V>(lanes, a, st, members);
   k_update_s<<<vg, TPB, 0, st>>>(a);
+  if (part) k_halo_push<2><<<push_grid, TPB, 0, st>>>(a, 1);
   launch_spmv<MODE_T>(lanes, a, st, members);
   k_update_xr<<<vg, TPB, 0, st>>>(a);
   BT_CUDA(cudaStreamEndCapture(st, &graph));
+  const int kernels_per_iter = part ? 7 : 5;
   if (h->l2_window_set) {   // captured kernel nodes do not inherit the stream's access-policy window
     size_t nn = 0;
     BT_CUDA(cudaGraphGetNodes(graph, nullptr, &nn));
@@ -1104,6 +1272,8 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   }
   BT_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
 
+  DevArray<double> d_sig;   // allocated before the loop: no allocation may sit between two collectives
+  d_sig.alloc(2 * (size_t)members);
   BT_CUDA(cudaEventRecord(e1, st));
   std::vector<int64_t> total_iters(members, 0), max_iters(members, 0);
   std::vector<int> last_reason(members, 0);
@@ -1119,6 +1289,10 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
           (int)h->n_pb_rows, h->d_pb_rows.p, h->d_rowptr.p, h->d_colidx.p, h->d_Bhat.p, 1.0 - sa->theta,
           h->d_ubc.p, h->d_rhs_add.p);
       n_kernels += 2;
+    }
+    if (part) {
+      k_halo_push<0><<<push_grid, TPB, 0, st>>>(a, 0);
+      ++n_kernels;
     }
     launch_spmv<MODE_RHS>(lanes, a, st, members);
     ++n_kernels;
@@ -1149,7 +1323,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
       if (all) break;
       chunk = std::max(1, std::min(8, launched / 8));
     }
-    n_kernels += 5 * (int64_t)launched;
+    n_kernels += kernels_per_iter * (int64_t)launched;
     est = 0;
     for (int b = 0; b < members; ++b) {
       const int it = h->h_ctrl[b].iters;
@@ -1163,11 +1337,17 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
         BT_CUDA(cudaMemsetAsync(h->d_u.p + (size_t)b * 7 * h->vec_npad, 0, sizeof(double2) * n, st));
       if (last_reason[b] < 0) fail = last_reason[b];
     }
+    if (fail == BTFEM_ECOMM) break;
     if (iters_per_step) iters_per_step[step] = h->h_ctrl[0].iters;
   }
   BT_CUDA(cudaEventRecord(e2, st));
-  DevArray<double> d_sig;
-  d_sig.alloc(2 * (size_t)members);
+  if (fail == BTFEM_ECOMM) {   // no further collective may be started: the peers are gone or out of step
+    h->dist_failed = true;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    cudaGraphExecDestroy(gexec);
+    cudaGraphDestroy(graph);
+    throw BtError{fail, "row-partitioned solve: a peer rank did not answer within the time limit"};
+  }
   a.sig_out = d_sig.p;
   k_signal<<<vg, TPB, 0, st>>>(a, h->d_lumped.p, h->d_dof_comp.p);
   BT_CUDA(cudaGetLastError());
@@ -1198,6 +1378,11 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     out->last_reason = last_reason[b];
   }
   if (fail) {
+    if (part && h->d_dist.p) {   // the signal all-reduce above may itself have timed out
+      DistDev dd;
+      BT_CUDA(cudaMemcpy(&dd, h->d_dist.p, sizeof(dd), cudaMemcpyDeviceToHost));
+      if (dd.error) h->dist_failed = true;
+    }
     const char* what = fail == BTFEM_ENOTCONV ? "maximum iterations reached"
                        : fail == BTFEM_EBREAKDOWN ? "BiCGStab breakdown"
                        : fail == BTFEM_ENAN ? "non-finite residual"
@@ -1212,4 +1397,101 @@ void bt_solve(btfem* h, const btfem_solve_args* sa, btfem_solve_out* out, int32_
 
 void bt_solve_batch(btfem* h, int members, const btfem_solve_args* sa, btfem_solve_out* out) {
   solve_impl(h, members, sa, out, nullptr);
+}
+
+// ===================================================================================== row partition: host side
+
+void bt_dist_export(btfem* h, void* blob_out) {
+  BT_REQUIRE(h->nv_own >= 0, "call btfem_set_partition before btfem_assemble");
+  BT_REQUIRE(h->n_own > 0, "a rank must own at least one dof");
+  ensure_vectors(h, 1);
+  BT_CUDA(cudaStreamSynchronize(h->stream));   // slab and comm block are zero before any peer can write
+  DistBlob b;
+  memset(&b, 0, sizeof(b));
+  b.magic = 0x4254464d44495354ULL;   // "BTFMDIST"
+  b.pid = (int64_t)getpid();
+  b.raw_ptr = (uint64_t)(uintptr_t)h->d_vecs.p;
+  b.device = h->device;
+  b.npad = (int64_t)h->vec_npad;
+  b.n_own = h->n_own;
+  b.ndof = h->ndof;
+  BT_CUDA(cudaIpcGetMemHandle(&b.ipc, h->d_vecs.p));
+  memcpy(blob_out, &b, sizeof(b));
+}
+
+void bt_dist_close(btfem* h) {
+  for (int r = 0; r < BT_MAX_RANKS; ++r)
+    if (h->peer_map[r]) {
+      cudaIpcCloseMemHandle(h->peer_map[r]);
+      h->peer_map[r] = nullptr;
+    }
+  h->dist_connected = false;
+}
+
+void bt_dist_connect(btfem* h, int rank, int world, const void* blobs, int64_t nsend, const int32_t* src,
+                     const int32_t* dst_rank, const int32_t* dst_slot, const int32_t* recv_from) {
+  BT_REQUIRE(h->nv_own >= 0 && h->assembled, "partitioned, assembled handle required");
+  BT_REQUIRE(world >= 1 && world <= BT_MAX_RANKS && rank >= 0 && rank < world, "bad rank / world size");
+  BT_REQUIRE(h->d_vecs.p != nullptr, "call btfem_dist_export first");
+  bt_dist_close(h);
+  const DistBlob* bl = reinterpret_cast<const DistBlob*>(blobs);
+  DistDev d;
+  memset(&d, 0, sizeof(d));
+  d.rank = rank;
+  d.world = world;
+  d.n_send = (int)nsend;
+  d.n_int = (int)h->n_int;
+  // rows are sorted by length inside windows of BT_SELL_SIGMA rows: the first window holding a row that may
+  // reference a halo column starts the waiting region
+  d.wait_slice = (int)((h->n_int / BT_SELL_SIGMA) * (BT_SELL_SIGMA / 32));
+  {
+    const char* e = getenv("BTFEM_COMM_TIMEOUT_MS");
+    const double ms = e ? atof(e) : 10000.0;
+    d.timeout_ns = (unsigned long long)(std::max(1.0, ms) * 1e6);
+  }
+  for (int r = 0; r < world; ++r) {
+    BT_REQUIRE(bl[r].magic == 0x4254464d44495354ULL, "bad partition blob");
+    void* base = nullptr;
+    if (r == rank) {
+      BT_REQUIRE((uint64_t)(uintptr_t)h->d_vecs.p == bl[r].raw_ptr, "own blob does not match this handle");
+      base = h->d_vecs.p;
+    } else if (bl[r].pid == (int64_t)getpid()) {   // ranks as threads of one process: plain peer access
+      if ((int)bl[r].device != h->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess((int)bl[r].device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) BT_CUDA(e);
+        cudaGetLastError();
+      }
+      base = (void*)(uintptr_t)bl[r].raw_ptr;
+    } else {
+      BT_CUDA(cudaIpcOpenMemHandle(&base, bl[r].ipc, cudaIpcMemLazyEnablePeerAccess));
+      h->peer_map[r] = base;
+    }
+    d.vecs[r] = reinterpret_cast<double2*>(base);
+    d.npad[r] = bl[r].npad;
+    d.comm[r] = reinterpret_cast<DistComm*>(reinterpret_cast<double2*>(base) + 7 * bl[r].npad);
+  }
+  std::vector<char> to(world, 0);
+  for (int64_t e = 0; e < nsend; ++e) {
+    BT_REQUIRE(src[e] >= 0 && src[e] < h->n_own, "send list: source is not an owned dof");
+    BT_REQUIRE(dst_rank[e] >= 0 && dst_rank[e] < world && dst_rank[e] != rank, "send list: bad destination rank");
+    const DistBlob& pb = bl[dst_rank[e]];
+    BT_REQUIRE(dst_slot[e] >= pb.n_own && dst_slot[e] < pb.npad, "send list: slot is not a halo element of the peer");
+    to[dst_rank[e]] = 1;
+  }
+  for (int r = 0; r < world; ++r) {
+    if (to[r]) d.send_ranks[d.n_send_ranks++] = r;
+    if (recv_from && recv_from[r] && r != rank) d.recv_ranks[d.n_recv_ranks++] = r;
+  }
+  h->d_send_src.upload(src, nsend, h->stream);
+  h->d_send_rank.upload(dst_rank, nsend, h->stream);
+  h->d_send_slot.upload(dst_slot, nsend, h->stream);
+  d.send_src = h->d_send_src.p;
+  d.send_rank = h->d_send_rank.p;
+  d.send_slot = h->d_send_slot.p;
+  h->d_dist.upload(&d, 1, h->stream);
+  BT_CUDA(cudaStreamSynchronize(h->stream));
+  h->rank = rank;
+  h->world = world;
+  h->dist_connected = true;
+  h->dist_failed = false;
 }

@@ -37,7 +37,8 @@ enum {
   BTFEM_EBREAKDOWN = -4, /* Krylov: rho == 0 or (v,r^) == 0 (KSP_DIVERGED_BREAKDOWN) */
   BTFEM_ENAN = -5,       /* Krylov: non-finite residual (KSP_DIVERGED_NANORINF) */
   BTFEM_EDTOL = -6,      /* Krylov: residual grew by dtol (KSP_DIVERGED_DTOL) */
-  BTFEM_ENOMEM = -7
+  BTFEM_ENOMEM = -7,
+  BTFEM_ECOMM = -8       /* row-partitioned solve: a peer did not answer in time (the solve is abandoned) */
 };
 
 /* which matrix btfem_get_values returns */
@@ -170,6 +171,33 @@ int btfem_solve_batch(btfem_t* h, int32_t members, const btfem_solve_args* args 
                       btfem_solve_out* out /*[members]*/);
 /* solution after the last solve, dof numbering, interleaved (re,im) */
 int btfem_get_solution(btfem_t* h, double* u /*[2*ndof]*/);
+
+/* ---- one mesh row-partitioned over several GPUs ---------------------------------------------
+ * Replaces the MPI domain decomposition that DOLFIN/PETSc do underneath `mpirun -n N python3 GCloudDmriSolver.py`
+ * (README.md:89-94; MatMult ghost scatter + MPI_Allreduce inside KSPSolve, third party).  One process (or
+ * thread) per GPU; every rank owns a contiguous block of vertices of a locality-ordered numbering and builds
+ * a handle on its LOCAL sub-mesh: all cells touching an owned vertex, vertices numbered
+ *   [ owned, not needed by peers | owned, needed by peers | halo (owned by peers) ].
+ * Rows of owned dofs are complete; rows of halo dofs are never used.  During the solve there is no exchange
+ * step: the kernel that produces a Krylov vector stores the entries peers need straight into the peers' halo
+ * slots (NVLink peer stores), the fused SpMV starts on rows that need no halo at once and waits for the peers'
+ * arrival flags only where it reaches the first row that does; the dot products are all-reduced by the last
+ * thread block of the producing kernel through peer memory (fixed rank order -> every rank holds bit-identical
+ * scalars, so all ranks take identical control decisions).  BiCGStab only.
+ * Call order: set_mesh / coefficients -> btfem_set_partition -> btfem_assemble -> btfem_dist_export ->
+ * (host layer all-gathers the blobs and the halo requests) -> btfem_dist_connect -> host barrier -> btfem_solve.
+ * btfem_solve then returns the GLOBAL signal on every rank; voi / whole_vol are sums over OWNED dofs (the
+ * host layer adds them up). */
+#define BTFEM_DIST_BLOB_BYTES 192
+int btfem_set_partition(btfem_t* h, int64_t nv_own, int64_t nv_interior /* <= nv_own */);
+/* after assemble: owned dofs, owned dofs not needed by peers, and the element shift of halo dofs in vectors */
+int btfem_get_partition(btfem_t* h, int64_t* n_own, int64_t* n_interior, int64_t* halo_shift);
+int btfem_dist_export(btfem_t* h, void* blob /*[BTFEM_DIST_BLOB_BYTES]*/);
+/* blobs: every rank's blob, rank-major.  Send list: owned dof src[e] goes to vector element dst_slot[e]
+ * (= peer-local dof + the peer's halo_shift) of rank dst_rank[e]; recv_from[r] != 0 if rank r sends to us. */
+int btfem_dist_connect(btfem_t* h, int32_t rank, int32_t world, const void* blobs, int64_t nsend,
+                       const int32_t* src, const int32_t* dst_rank, const int32_t* dst_slot,
+                       const int32_t* recv_from /*[world]*/);
 
 #ifdef __cplusplus
 }
