@@ -86,7 +86,7 @@ def load_library(path=None):
         "btfem_get_partition": (C.c_int, [H, _c_int64_p, _c_int64_p, _c_int64_p]),
         "btfem_dist_export": (C.c_int, [H, C.c_void_p]),
         "btfem_dist_connect": (C.c_int, [H, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, _c_int32_p, _c_int32_p,
-                                         _c_int32_p, _c_int32_p]),
+                                         _c_int32_p, C.c_int64, _c_int32_p, _c_int32_p, _c_int32_p, _c_int32_p]),
     }
     for name, (res, args) in proto.items():
         f = getattr(lib, name)
@@ -336,15 +336,17 @@ class BTFem:
         self._ck(self.lib.btfem_dist_export(self.h, blob.ctypes.data_as(C.c_void_p)))
         return blob
 
-    def dist_connect(self, rank, world, blobs, src, dst_rank, dst_slot, recv_from):
+    def dist_connect(self, rank, world, blobs, src, dst_rank, dst_slot, recv_from, u_only=None):
+        """u_only: optional (src, dst_rank, dst_index) of the entries that travel with u only (periodic sources)."""
         blobs = np.ascontiguousarray(blobs, dtype=np.uint8).reshape(world, DIST_BLOB_BYTES)
-        src = np.ascontiguousarray(src, dtype=np.int32)
-        dst_rank = np.ascontiguousarray(dst_rank, dtype=np.int32)
-        dst_slot = np.ascontiguousarray(dst_slot, dtype=np.int32)
-        recv_from = np.ascontiguousarray(recv_from, dtype=np.int32)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        src, dst_rank, dst_slot, recv_from = i32(src), i32(dst_rank), i32(dst_slot), i32(recv_from)
         assert len(src) == len(dst_rank) == len(dst_slot) and len(recv_from) == world
+        us, ur, ui = (i32(a) for a in (u_only if u_only is not None else ([], [], [])))
+        assert len(us) == len(ur) == len(ui)
         self._ck(self.lib.btfem_dist_connect(self.h, int(rank), int(world), blobs.ctypes.data_as(C.c_void_p),
-                                             len(src), _ip(src), _ip(dst_rank), _ip(dst_slot), _ip(recv_from)))
+                                             len(src), _ip(src), _ip(dst_rank), _ip(dst_slot), len(us), _ip(us),
+                                             _ip(ur), _ip(ui), _ip(recv_from)))
 
     def solution(self):
         u = np.empty(self.ndof, dtype=np.complex128)

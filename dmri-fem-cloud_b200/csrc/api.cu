@@ -1,5 +1,7 @@
 // extern "C" entry points of libbtfem.so: argument checking, error capture, call order.
+#include <algorithm>
 #include <cstring>
+#include <vector>
 
 #include "btfem_internal.cuh"
 
@@ -181,13 +183,34 @@ int btfem_set_periodic_gather(btfem_t* h, int64_t nb, const int32_t* dof, const 
   return guarded(h, [&] {
     BT_REQUIRE(h->assembled, "call btfem_assemble first");
     BT_REQUIRE(nb >= 0 && (nb == 0 || (dof && src && w && dx)), "null argument");
+    const bool part = h->nv_own >= 0;
+    BT_REQUIRE(!h->dist_connected, "periodic gather of a partition must be set before btfem_dist_export");
+    int64_t n_extra = 0;
     for (int64_t i = 0; i < nb; ++i) {
       BT_REQUIRE(dof[i] >= 0 && dof[i] < h->ndof, "periodic gather: dof out of range");
-      for (int k = 0; k < 3; ++k) BT_REQUIRE(src[3 * i + k] < h->ndof, "periodic gather: source out of range");
+      for (int k = 0; k < 3; ++k) {
+        const int32_t s = src[3 * i + k];
+        BT_REQUIRE(s < h->ndof && (part || s >= -1), "periodic gather: source out of range");
+        if (s <= -2) n_extra = std::max<int64_t>(n_extra, (int64_t)(-2 - s) + 1);
+      }
+    }
+    // sources become ELEMENT indices relative to u: local dof (+ halo shift), or the source buffer that sits
+    // behind the seven vectors and the DistComm block of a partitioned handle
+    std::vector<int32_t> elem(src, src + 3 * nb);
+    if (part) {
+      const int64_t n_el = h->ndof + h->halo_shift;
+      const int64_t tail = 7 * ((n_el + 15) & ~(int64_t)15) + BT_COMM_ELEMS;
+      BT_REQUIRE(tail + n_extra < (int64_t)0x7fffffffLL, "periodic source buffer exceeds int32 indexing");
+      for (auto& s : elem) {
+        if (s <= -2) s = (int32_t)(tail + (-2 - s));
+        else if (s >= h->n_own) s += (int32_t)h->halo_shift;
+      }
+      if (n_extra != h->n_extra) h->d_vecs.release();
+      h->n_extra = n_extra;
     }
     h->n_pb = nb;
     h->d_pb_dof.upload(dof, nb, h->stream);
-    h->d_pb_src.upload(src, 3 * nb, h->stream);
+    h->d_pb_src.upload(elem.data(), 3 * nb, h->stream);
     h->d_pb_w.upload(w, 3 * nb, h->stream);
     h->d_pb_dx.upload(dx, 3 * nb, h->stream);
     BT_CUDA(cudaStreamSynchronize(h->stream));
@@ -334,10 +357,13 @@ int btfem_dist_export(btfem_t* h, void* blob) {
 }
 
 int btfem_dist_connect(btfem_t* h, int32_t rank, int32_t world, const void* blobs, int64_t nsend, const int32_t* src,
-                       const int32_t* dst_rank, const int32_t* dst_slot, const int32_t* recv_from) {
+                       const int32_t* dst_rank, const int32_t* dst_slot, int64_t nsend_u, const int32_t* src_u,
+                       const int32_t* dst_rank_u, const int32_t* dst_index_u, const int32_t* recv_from) {
   return guarded(h, [&] {
     BT_REQUIRE(blobs && recv_from && nsend >= 0 && (nsend == 0 || (src && dst_rank && dst_slot)), "null argument");
-    bt_dist_connect(h, rank, world, blobs, nsend, src, dst_rank, dst_slot, recv_from);
+    BT_REQUIRE(nsend_u >= 0 && (nsend_u == 0 || (src_u && dst_rank_u && dst_index_u)), "null argument");
+    bt_dist_connect(h, rank, world, blobs, nsend, src, dst_rank, dst_slot, nsend_u, src_u, dst_rank_u, dst_index_u,
+                    recv_from);
   });
 }
 

@@ -100,11 +100,11 @@ static_assert(sizeof(DistComm) <= BT_COMM_ELEMS * 16, "DistComm does not fit its
 struct DistDev {
   int rank, world;
   int n_send;                        // halo entries this rank pushes per exchange
+  int n_send_u;                      // n_send + entries pushed only with u (sources of the periodic gather)
   int n_send_ranks, n_recv_ranks;
   int send_ranks[BT_MAX_RANKS], recv_ranks[BT_MAX_RANKS];
   int wait_slice;                    // SELL slices below this one never touch a halo column
   int n_int;                         // owned rows [0,n_int) are not needed by any peer
-  int pad_;
   DistComm* comm[BT_MAX_RANKS];      // comm block of every rank (own or peer-mapped)
   double2* vecs[BT_MAX_RANKS];       // base of every rank's Krylov vector slab
   long long npad[BT_MAX_RANKS];      // vector stride (elements) of every rank's slab
@@ -124,9 +124,9 @@ struct DistBlob {
   int64_t pid;
   uint64_t raw_ptr;
   int64_t device;
-  int64_t npad, n_own, ndof;
+  int64_t npad, n_own, ndof, n_extra;
   cudaIpcMemHandle_t ipc;            // 64 bytes
-  char pad_[BTFEM_DIST_BLOB_BYTES - 7 * 8 - 64];
+  char pad_[BTFEM_DIST_BLOB_BYTES - 8 * 8 - 64];
 };
 static_assert(sizeof(DistBlob) == BTFEM_DIST_BLOB_BYTES, "DistBlob size");
 
@@ -175,6 +175,7 @@ struct btfem {
   int64_t nv_own = -1, nv_int = -1;   // vertices [0,nv_own) owned, of which [0,nv_int) are not needed by peers
   int64_t n_own = 0, n_int = 0;       // the same in dofs (set by the dof map)
   int64_t halo_shift = 0;             // halo dof j sits at vector element j + halo_shift (128-byte aligned halo)
+  int64_t n_extra = 0;                // u values of periodic-gather sources owned by peers, behind the DistComm block
   bool dist_connected = false, dist_failed = false;
   int rank = 0, world = 1;
   DevArray<DistDev> d_dist;
@@ -258,5 +259,6 @@ void bt_solve(btfem* h, const btfem_solve_args* a, btfem_solve_out* out, int32_t
 void bt_solve_batch(btfem* h, int members, const btfem_solve_args* a, btfem_solve_out* out);
 void bt_dist_export(btfem* h, void* blob);
 void bt_dist_connect(btfem* h, int rank, int world, const void* blobs, int64_t nsend, const int32_t* src,
-                     const int32_t* dst_rank, const int32_t* dst_slot, const int32_t* recv_from);
+                     const int32_t* dst_rank, const int32_t* dst_slot, int64_t nsend_u, const int32_t* src_u,
+                     const int32_t* dst_rank_u, const int32_t* dst_index_u, const int32_t* recv_from);
 void bt_dist_close(btfem* h);

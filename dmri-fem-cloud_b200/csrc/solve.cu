@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(TPB) k_halo_push(SpmvArgs a, int check_done) {
   __shared__ int s_last;
   const double2* __restrict__ src = WHICH == 0 ? a.u : (WHICH == 1 ? a.p : a.s);
   const int vi = WHICH == 0 ? 0 : (WHICH == 1 ? 3 : 5);   // slab order: u r rp p v s t
-  const int ns = d->n_send;
+  const int ns = WHICH == 0 ? d->n_send_u : d->n_send;   // u also carries the periodic-gather sources
   for (int e = blockIdx.x * TPB + threadIdx.x; e < ns; e += gridDim.x * TPB) {
     const int r = d->send_rank[e];
     const double2 v = src[d->send_src[e]];
@@ -631,7 +631,8 @@ __global__ void k_flush_l2(const double2* __restrict__ p, size_t n, double* sink
 __global__ void k_periodic_ubc(int nb, const KrylovCtrl* ctrl, const double* __restrict__ Fb, double q, double gx,
                                double gy, double gz, const int32_t* __restrict__ dof, const int32_t* __restrict__ src,
                                const double* __restrict__ w, const double* __restrict__ dx,
-                               const double2* __restrict__ u, double2* __restrict__ ubc) {
+                               const double2* __restrict__ u, double2* __restrict__ ubc, DistDev* dist) {
+  if (dist) halo_wait(dist);   // sources may be halo entries or entries of the periodic source buffer
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
   double ar = 0.0, ai = 0.0;
@@ -898,7 +899,7 @@ void ensure_vectors(btfem* h, int members = 1) {
   const size_t n = (size_t)h->ndof + (size_t)h->halo_shift;
   const size_t npad = (n + 15) & ~(size_t)15;           // keep every vector 256-byte aligned
   h->vec_npad = npad;
-  const size_t total = (size_t)members * 7 * npad + (part ? BT_COMM_ELEMS : 0);
+  const size_t total = (size_t)members * 7 * npad + (part ? BT_COMM_ELEMS + (size_t)h->n_extra : 0);
   if (h->d_vecs.n != total) {
     BT_REQUIRE(!h->dist_connected, "vector slab of a connected partition cannot be re-allocated");
     h->d_vecs.alloc(total);
@@ -1188,8 +1189,8 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   if (part) {
     BT_REQUIRE(h->dist_connected, "row-partitioned handle: call btfem_dist_connect before btfem_solve");
     BT_REQUIRE(!h->dist_failed, "a previous row-partitioned solve lost a peer; rebuild the handles");
-    BT_REQUIRE(!gmres && !periodic && members == 1 && h->lanes == 0,
-               "row-partitioned solves support BiCGStab on the SELL-32 kernel, without periodic BC");
+    BT_REQUIRE(!gmres && members == 1 && h->lanes == 0,
+               "row-partitioned solves support BiCGStab on the SELL-32 kernel");
   }
   for (int b = 1; b < members; ++b)
     BT_REQUIRE(sav[b].nsteps == sa->nsteps && sav[b].dt == sa->dt && sav[b].theta == sa->theta && sav[b].cA &&
@@ -1281,18 +1282,18 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   int est = 4;
   int fail = 0;
   for (int64_t step = 0; step < sa->nsteps && !fail; ++step) {
+    if (part) {
+      k_halo_push<0><<<push_grid, TPB, 0, st>>>(a, 0);
+      ++n_kernels;
+    }
     if (periodic) {
       k_periodic_ubc<<<((int)h->n_pb + TPB - 1) / TPB, TPB, 0, st>>>(
           (int)h->n_pb, h->d_ctrl.p, h->d_Fb.p, sa->q, sa->gdir[0], sa->gdir[1], sa->gdir[2], h->d_pb_dof.p,
-          h->d_pb_src.p, h->d_pb_w.p, h->d_pb_dx.p, h->d_u.p, h->d_ubc.p);
+          h->d_pb_src.p, h->d_pb_w.p, h->d_pb_dx.p, h->d_u.p, h->d_ubc.p, a.dist);
       k_periodic_rhs<<<((int)h->n_pb_rows + TPB - 1) / TPB, TPB, 0, st>>>(
           (int)h->n_pb_rows, h->d_pb_rows.p, h->d_rowptr.p, h->d_colidx.p, h->d_Bhat.p, 1.0 - sa->theta,
           h->d_ubc.p, h->d_rhs_add.p);
       n_kernels += 2;
-    }
-    if (part) {
-      k_halo_push<0><<<push_grid, TPB, 0, st>>>(a, 0);
-      ++n_kernels;
     }
     launch_spmv<MODE_RHS>(lanes, a, st, members);
     ++n_kernels;
@@ -1415,6 +1416,7 @@ void bt_dist_export(btfem* h, void* blob_out) {
   b.npad = (int64_t)h->vec_npad;
   b.n_own = h->n_own;
   b.ndof = h->ndof;
+  b.n_extra = h->n_extra;
   BT_CUDA(cudaIpcGetMemHandle(&b.ipc, h->d_vecs.p));
   memcpy(blob_out, &b, sizeof(b));
 }
@@ -1429,7 +1431,8 @@ void bt_dist_close(btfem* h) {
 }
 
 void bt_dist_connect(btfem* h, int rank, int world, const void* blobs, int64_t nsend, const int32_t* src,
-                     const int32_t* dst_rank, const int32_t* dst_slot, const int32_t* recv_from) {
+                     const int32_t* dst_rank, const int32_t* dst_slot, int64_t nsend_u, const int32_t* src_u,
+                     const int32_t* dst_rank_u, const int32_t* dst_index_u, const int32_t* recv_from) {
   BT_REQUIRE(h->nv_own >= 0 && h->assembled, "partitioned, assembled handle required");
   BT_REQUIRE(world >= 1 && world <= BT_MAX_RANKS && rank >= 0 && rank < world, "bad rank / world size");
   BT_REQUIRE(h->d_vecs.p != nullptr, "call btfem_dist_export first");
@@ -1440,6 +1443,7 @@ void bt_dist_connect(btfem* h, int rank, int world, const void* blobs, int64_t n
   d.rank = rank;
   d.world = world;
   d.n_send = (int)nsend;
+  d.n_send_u = (int)(nsend + nsend_u);
   d.n_int = (int)h->n_int;
   // rows are sorted by length inside windows of BT_SELL_SIGMA rows: the first window holding a row that may
   // reference a halo column starts the waiting region
@@ -1478,13 +1482,25 @@ void bt_dist_connect(btfem* h, int rank, int world, const void* blobs, int64_t n
     BT_REQUIRE(dst_slot[e] >= pb.n_own && dst_slot[e] < pb.npad, "send list: slot is not a halo element of the peer");
     to[dst_rank[e]] = 1;
   }
+  std::vector<int32_t> all_src(src, src + nsend), all_rank(dst_rank, dst_rank + nsend),
+      all_slot(dst_slot, dst_slot + nsend);
+  for (int64_t e = 0; e < nsend_u; ++e) {   // entries of the peers' periodic source buffers, as element indices
+    BT_REQUIRE(src_u[e] >= 0 && src_u[e] < h->n_own, "send list (u): source is not an owned dof");
+    BT_REQUIRE(dst_rank_u[e] >= 0 && dst_rank_u[e] < world && dst_rank_u[e] != rank, "send list (u): bad rank");
+    const DistBlob& pb = bl[dst_rank_u[e]];
+    BT_REQUIRE(dst_index_u[e] >= 0 && dst_index_u[e] < pb.n_extra, "send list (u): index outside the peer's buffer");
+    all_src.push_back(src_u[e]);
+    all_rank.push_back(dst_rank_u[e]);
+    all_slot.push_back((int32_t)(7 * pb.npad + BT_COMM_ELEMS + dst_index_u[e]));
+    to[dst_rank_u[e]] = 1;
+  }
   for (int r = 0; r < world; ++r) {
     if (to[r]) d.send_ranks[d.n_send_ranks++] = r;
     if (recv_from && recv_from[r] && r != rank) d.recv_ranks[d.n_recv_ranks++] = r;
   }
-  h->d_send_src.upload(src, nsend, h->stream);
-  h->d_send_rank.upload(dst_rank, nsend, h->stream);
-  h->d_send_slot.upload(dst_slot, nsend, h->stream);
+  h->d_send_src.upload(all_src.data(), all_src.size(), h->stream);
+  h->d_send_rank.upload(all_rank.data(), all_rank.size(), h->stream);
+  h->d_send_slot.upload(all_slot.data(), all_slot.size(), h->stream);
   d.send_src = h->d_send_src.p;
   d.send_rank = h->d_send_rank.p;
   d.send_slot = h->d_send_slot.p;

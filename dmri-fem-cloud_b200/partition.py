@@ -20,6 +20,7 @@ import threading
 import numpy as np
 
 from . import btfem as _bt
+from . import periodic as _periodic
 
 
 # ------------------------------------------------------------------------------------------------ partition
@@ -116,6 +117,47 @@ def send_list(part, requests, dof_vertex, dof_comp, n_own):
     return cat(src), cat(dst_rank), cat(dst_slot), recv_from
 
 
+def global_dofmap(nv, tets, phase=None):
+    """The single-handle numbering of the whole mesh: active (vertex, compartment) pairs, vertex-major
+    (csrc/setup.cu:bt_build_dofmap).  Returns dof_vertex, dof_comp, vc2dof (nv,2)."""
+    tets = np.asarray(tets)
+    active = np.zeros((nv, 2), dtype=bool)
+    if phase is None:
+        active[np.unique(tets), 0] = True
+    else:
+        phase = np.asarray(phase)
+        for c in (0, 1):
+            active[np.unique(tets[phase == c]), c] = True
+    flat = active.ravel()
+    vc2dof = np.where(flat, np.cumsum(flat) - 1, -1).reshape(nv, 2).astype(np.int64)
+    dv, dc = np.nonzero(active)
+    return dv.astype(np.int64), dc.astype(np.int64), vc2dof
+
+
+def periodic_plan(part, bounds, gather, gvc2dof, gdof_vertex, gdof_comp, dof_vertex, dof_comp):
+    """Restrict the GLOBAL periodic gather (periodic.build_gather on the whole mesh, global dof ids) to the
+    boundary dofs this rank holds.  Sources held locally become local dofs; sources held only by a peer become
+    entry k of this rank's periodic source buffer (src = -2-k) and a request row (owner, vertex, comp, k)."""
+    dof_g, src_g, w, dx = gather
+    lg = gvc2dof[part.l2g[dof_vertex], dof_comp]            # global id of every local dof
+    g2l = np.full(len(gdof_vertex), -1, dtype=np.int64)
+    g2l[lg] = np.arange(len(lg))
+    sel = g2l[dof_g] >= 0
+    dof_l = g2l[dof_g[sel]]
+    sg = src_g[sel].astype(np.int64)
+    sl = np.where(sg >= 0, g2l[np.maximum(sg, 0)], -1)
+    missing = (sg >= 0) & (sl < 0)
+    need = np.unique(sg[missing])
+    k_of = np.full(len(gdof_vertex), -1, dtype=np.int64)
+    k_of[need] = np.arange(len(need))
+    sl[missing] = -2 - k_of[sg[missing]]
+    gv = gdof_vertex[need]
+    owner = np.searchsorted(bounds, gv, side="right") - 1
+    req = np.stack([owner, gv, gdof_comp[need], np.arange(len(need))], axis=1).astype(np.int64) if len(need) \
+        else np.zeros((0, 4), dtype=np.int64)
+    return (dof_l.astype(np.int32), sl.astype(np.int32), w[sel], dx[sel]), req
+
+
 # ------------------------------------------------------------------------------------------------ collectives
 
 class TorchComm:
@@ -140,6 +182,12 @@ class TorchComm:
         import torch
         t = torch.from_numpy(np.array(a, dtype=np.float64, copy=True))
         self.dist.all_reduce(t, group=self.group)
+        return t.numpy()
+
+    def max(self, a):
+        import torch
+        t = torch.from_numpy(np.array(a, dtype=np.float64, copy=True))
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
         return t.numpy()
 
 
@@ -177,6 +225,9 @@ class ThreadComm:
             tot = tot + p
         return tot
 
+    def max(self, a):
+        return np.max(np.stack(self.allgather(np.array(a, dtype=np.float64, copy=True))), axis=0)
+
 
 class SingleComm:
     rank, world = 0, 1
@@ -189,6 +240,8 @@ class SingleComm:
 
     def sum(self, a):
         return np.array(a, dtype=np.float64, copy=True)
+
+    max = sum
 
 
 # ------------------------------------------------------------------------------------------------ the object
@@ -211,6 +264,8 @@ class DistBTFem:
         self.two_comp = phase is not None
         self.fem.set_mesh(xyz[self.part.l2g], self.part.tets, ph)
         self.fem.set_partition(self.part.nv_own, self.part.nv_int)
+        self._global = (xyz, tets, None if phase is None else np.asarray(phase, dtype=np.int32))
+        self.pdir = None
 
     def close(self):
         self.fem.close()
@@ -229,6 +284,17 @@ class DistBTFem:
     def set_permeability(self, kappa, marker=None):
         self.fem.set_permeability(kappa, None if marker is None else self._cells(marker))
 
+    def set_periodic(self, pdir, kappa_e, tol, lo, hi):
+        """Weak pseudo-periodic BC; lo/hi: bounding box of the WHOLE mesh (MyDomain prints it, DmriFemLib.py:593)."""
+        self.pdir = [int(p) for p in pdir]
+        self.lo, self.hi = np.asarray(lo, dtype=float), np.asarray(hi, dtype=float)
+        self.fem.set_periodic(self.pdir, kappa_e, tol, self.lo, self.hi)
+
+    def mesh_stats(self):
+        """hmin / hmax of the whole mesh (cells are spread over the ranks; a cut cell is seen by several)."""
+        lo, hi = self.fem.mesh_stats()
+        return (-float(self.comm.max([-lo])[0]), float(self.comm.max([hi])[0]))
+
     def set_initial(self, ic=None):
         self.fem.set_initial(None if ic is None else np.asarray(ic, dtype=np.float64)[self.part.l2g])
 
@@ -238,13 +304,23 @@ class DistBTFem:
         self.n_own, self.n_int, self.halo_shift = fem.partition_sizes()
         self.dof_vertex, self.dof_comp = fem.dofmap()
         req = halo_requests(part, self.bounds, self.dof_vertex, self.dof_comp, self.n_own, self.halo_shift)
+        req_u = np.zeros((0, 4), dtype=np.int64)
+        if self.pdir is not None and sum(self.pdir) > 0:
+            xyz, tets, phase = self._global
+            gdv, gdc, gvc2dof = global_dofmap(len(xyz), tets, phase)
+            gather = _periodic.build_gather(xyz, tets, phase, self.pdir, self.lo, self.hi, gdv, gdc)
+            local_gather, req_u = periodic_plan(part, self.bounds, gather, gvc2dof, gdv, gdc, self.dof_vertex,
+                                                self.dof_comp)
+            fem.set_periodic_gather(*local_gather)       # before the export: it sizes the source buffer
         blob = fem.dist_export()
-        gathered = self.comm.allgather((req, blob))
+        gathered = self.comm.allgather((req, blob, req_u))
         src, dst_rank, dst_slot, recv_from = send_list(part, [g[0] for g in gathered], self.dof_vertex,
                                                        self.dof_comp, self.n_own)
+        usrc, urank, uidx, urecv = send_list(part, [g[2] for g in gathered], self.dof_vertex, self.dof_comp,
+                                             self.n_own)
         fem.dist_connect(self.rank, self.world, np.stack([g[1] for g in gathered]), src, dst_rank, dst_slot,
-                         recv_from)
-        self.n_send = len(src)
+                         np.maximum(recv_from, urecv), u_only=(usrc, urank, uidx))
+        self.n_send, self.n_send_u = len(src), len(usrc)
         self.ndof_global = int(self.comm.sum([self.n_own])[0])
         self.comm.barrier()      # every slab is allocated, zeroed and mapped before the first halo push
 

@@ -29,6 +29,22 @@ def _boundary_triangles(tets):
     return f[ext], cell[ext]
 
 
+def _plane_triangles(xyz, tets, d, target):
+    """Facets with all three vertices on the plane x_d = target.  The plane is a face of the bounding box, so
+    these facets are exterior: no facet sort over the whole mesh is needed (row-partitioned set-up, where no
+    single GPU sees the whole mesh)."""
+    on = np.abs(xyz[:, d] - target) <= FACE_TOL
+    ont = on[tets]
+    cand = np.nonzero(ont.sum(axis=1) >= 3)[0]
+    out = []
+    for lf in range(4):
+        keep = [k for k in range(4) if k != lf]
+        m = ont[cand][:, keep].all(axis=1)
+        out.append(np.sort(tets[cand[m]][:, keep], axis=1))
+    f = np.concatenate(out) if out else np.zeros((0, 3), dtype=np.int64)
+    return np.unique(f, axis=0) if len(f) else f.reshape(0, 3)
+
+
 def _locate(points2, tri_xy, ncand=16):
     """For each 2-D point: containing triangle (or the least-outside one among the `ncand` triangles with the
     nearest centroids: extrapolation, like allow_extrapolation) and its barycentric weights.  Vectorised."""
@@ -60,7 +76,8 @@ def build_gather(xyz, tets, phase, pdir, lo, hi, dof_vertex, dof_comp, bfacets=N
     nv = len(xyz)
     vc2dof = -np.ones((nv, 2), dtype=np.int64)
     vc2dof[dof_vertex, dof_comp] = np.arange(len(dof_vertex))
-    bf = np.asarray(bfacets, dtype=np.int64) if bfacets is not None else _boundary_triangles(np.asarray(tets))[0]
+    tets = np.asarray(tets)
+    bf = np.asarray(bfacets, dtype=np.int64) if bfacets is not None else None
     # per vertex: (direction, side) of the LAST matching periodic direction
     vdir = -np.ones(nv, dtype=np.int64)
     vside = np.zeros(nv, dtype=np.int64)
@@ -84,7 +101,10 @@ def build_gather(xyz, tets, phase, pdir, lo, hi, dof_vertex, dof_comp, bfacets=N
             if len(vs) == 0:
                 continue
             target = hi[d] if side == 0 else lo[d]         # mirrored onto the opposite face
-            tri = bf[np.all(np.abs(xyz[bf][:, :, d] - target) <= FACE_TOL, axis=1)]
+            if bf is not None:
+                tri = bf[np.all(np.abs(xyz[bf][:, :, d] - target) <= FACE_TOL, axis=1)]
+            else:
+                tri = _plane_triangles(xyz, tets, d, target).astype(np.int64)
             if len(tri) == 0:
                 continue
             t_idx, W = _locate(xyz[vs][:, other], xyz[tri][:, :, other])

@@ -86,8 +86,10 @@ int btfem_set_periodic(btfem_t* h, const int32_t pdir[3], double kappa_e, double
  * n_bfacet from btfem_get_sizes.  Lets the host build the periodic gather without its own facet search. */
 int btfem_get_boundary_facets(btfem_t* h, int32_t* verts /*[n_bfacet*3]*/);
 /* Gather operator of the weak pseudo-periodic BC (WeakPseudoPeriodic_*.eval, DmriFemLib.py:270-321): for
- * boundary dof `dof[b]`:  u_bc = exp(i*q*(g . dx[b])*F(t_p)) * sum_k w[b][k] * u[src[b][k]]   (src < 0: term is 0).
- * Built once per mesh by the host layer (periodic.build_gather); call after btfem_assemble. */
+ * boundary dof `dof[b]`:  u_bc = exp(i*q*(g . dx[b])*F(t_p)) * sum_k w[b][k] * u[src[b][k]]   (src == -1: term is 0).
+ * Built once per mesh by the host layer (periodic.build_gather); call after btfem_assemble.
+ * Row-partitioned handles: dof / src are LOCAL dofs; src = -2-k means entry k of the periodic source buffer, which
+ * the owning peer fills (btfem_dist_connect, `_u` list); call before btfem_dist_export. */
 int btfem_set_periodic_gather(btfem_t* h, int64_t nb, const int32_t* dof /*[nb]*/, const int32_t* src /*[nb*3]*/,
                               const double* w /*[nb*3]*/, const double* dx /*[nb*3]*/);
 /* Initial condition per vertex (Dirac_Delta interpolant, DmriFemLib.py:865-876); NULL = 1. */
@@ -183,7 +185,7 @@ int btfem_get_solution(btfem_t* h, double* u /*[2*ndof]*/);
  * slots (NVLink peer stores), the fused SpMV starts on rows that need no halo at once and waits for the peers'
  * arrival flags only where it reaches the first row that does; the dot products are all-reduced by the last
  * thread block of the producing kernel through peer memory (fixed rank order -> every rank holds bit-identical
- * scalars, so all ranks take identical control decisions).  BiCGStab only.
+ * scalars, so all ranks take identical control decisions).  BiCGStab only; Neumann or weak pseudo-periodic BC.
  * Call order: set_mesh / coefficients -> btfem_set_partition -> btfem_assemble -> btfem_dist_export ->
  * (host layer all-gathers the blobs and the halo requests) -> btfem_dist_connect -> host barrier -> btfem_solve.
  * btfem_solve then returns the GLOBAL signal on every rank; voi / whole_vol are sums over OWNED dofs (the
@@ -194,9 +196,13 @@ int btfem_set_partition(btfem_t* h, int64_t nv_own, int64_t nv_interior /* <= nv
 int btfem_get_partition(btfem_t* h, int64_t* n_own, int64_t* n_interior, int64_t* halo_shift);
 int btfem_dist_export(btfem_t* h, void* blob /*[BTFEM_DIST_BLOB_BYTES]*/);
 /* blobs: every rank's blob, rank-major.  Send list: owned dof src[e] goes to vector element dst_slot[e]
- * (= peer-local dof + the peer's halo_shift) of rank dst_rank[e]; recv_from[r] != 0 if rank r sends to us. */
+ * (= peer-local dof + the peer's halo_shift) of rank dst_rank[e] whenever u, p or s is exchanged.
+ * The `_u` list travels with u only (once per time step): owned dof src_u[e] goes to entry dst_index_u[e] of
+ * rank dst_rank_u[e]'s periodic source buffer -- the weak pseudo-periodic gather reads u at mirrored points,
+ * which a peer may own (btfem_set_periodic_gather: src <= -2).  recv_from[r] != 0 if rank r sends to us. */
 int btfem_dist_connect(btfem_t* h, int32_t rank, int32_t world, const void* blobs, int64_t nsend,
-                       const int32_t* src, const int32_t* dst_rank, const int32_t* dst_slot,
+                       const int32_t* src, const int32_t* dst_rank, const int32_t* dst_slot, int64_t nsend_u,
+                       const int32_t* src_u, const int32_t* dst_rank_u, const int32_t* dst_index_u,
                        const int32_t* recv_from /*[world]*/);
 
 #ifdef __cplusplus

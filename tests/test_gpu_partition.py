@@ -154,6 +154,69 @@ def test_nonzero_guess_partitioned(monkeypatch):
     assert abs(out[0][0]["signal"] - ref["signal"]) <= 1e-10 * abs(ref["signal"])
 
 
+@pytest.mark.parametrize("world,two_comp,pdir", [(2, False, [1, 0, 0]), (3, True, [1, 1, 0]), (2, True, [0, 1, 1])])
+def test_weak_periodic_partitioned(world, two_comp, pdir, monkeypatch):
+    """configs[3] shape: weak pseudo-periodic BC on a partitioned mesh -- the mirrored sources of the gather live
+    on other ranks and travel with the per-step u push."""
+    from dmri_fem_cloud_b200 import periodic
+    monkeypatch.setenv("BTFEM_COMM_TIMEOUT_MS", "5000")
+    xyz, tets, phase = _mesh(two_comp)
+    lo, hi = xyz.min(axis=0), xyz.max(axis=0)
+    seq = orc.pgse(2000.0, 5000.0)
+    k = 200.0
+    ts = orc.time_grid(seq.T, k)
+    q = seq.q_from_b(800.0)
+    f = np.array([seq.f(t) for t in ts])
+    fp = np.concatenate([[f[0]], f[:-1]])
+    Fp = np.concatenate([[seq.F(0.0)], [seq.F(t) for t in ts[:-1]]])
+    g = np.array([1.0, 0.5, 0.25])
+    g /= np.linalg.norm(g)
+    with btfem.BTFem(0) as fem:
+        fem.set_mesh(xyz, tets, phase)
+        hmin, _ = fem.mesh_stats()
+        kappa_e, tol = 3e-3 / hmin, 1e-2 * hmin
+        fem.set_diffusion(COEF["D"])
+        if two_comp:
+            fem.set_permeability(COEF["kappa"])
+        fem.set_periodic(pdir, kappa_e, tol, lo, hi)
+        fem.assemble()
+        dv, dc = fem.dofmap()
+        fem.set_periodic_gather(*periodic.build_gather(xyz, tets, phase, pdir, lo, hi, dv, dc))
+        ref = fem.solve(k, 0.5, q * f, q * fp, g, q=q, Fb=Fp)
+        uref = fem.solution()
+        neu_sig = None
+    comms = partition.ThreadComm.make(world)
+    out, err = [None] * world, [None] * world
+
+    def run(comm):
+        try:
+            d = partition.DistBTFem(xyz, tets, comm, device=0, phase=phase)
+            assert abs(d.mesh_stats()[0] - hmin) <= 1e-15 * hmin
+            d.set_diffusion(COEF["D"])
+            if two_comp:
+                d.set_permeability(COEF["kappa"])
+            d.set_periodic(pdir, kappa_e, tol, lo, hi)
+            d.assemble()
+            res = d.solve(k, 0.5, q * f, q * fp, g, q=q, Fb=Fp)
+            out[comm.rank] = (res, d.global_solution(), d.n_send_u)
+            comm.barrier()
+            d.close()
+        except Exception as e:   # noqa: BLE001
+            err[comm.rank] = e
+            comm.sh.barrier.abort()
+
+    th = [threading.Thread(target=run, args=(c,)) for c in comms]
+    [t.start() for t in th]
+    [t.join(300) for t in th]
+    for e in err:
+        if e is not None:
+            raise e
+    assert sum(o[2] for o in out) > 0, "the test mesh must put mirrored sources on other ranks"
+    for res, sol, _ in out:
+        assert abs(res["signal"] - ref["signal"]) <= 1e-10 * abs(ref["signal"])
+        assert np.max(np.abs(sol[2] - uref)) <= 1e-9 * np.max(np.abs(uref))
+
+
 def test_lost_peer_times_out(monkeypatch):
     """A rank whose peer never shows up must fail with BTFEM_ECOMM, not hang."""
     monkeypatch.setenv("BTFEM_COMM_TIMEOUT_MS", "300")
