@@ -87,6 +87,8 @@ def load_library(path=None):
         "btfem_dist_export": (C.c_int, [H, C.c_void_p]),
         "btfem_dist_connect": (C.c_int, [H, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, _c_int32_p, _c_int32_p,
                                          _c_int32_p, C.c_int64, _c_int32_p, _c_int32_p, _c_int32_p, _c_int32_p]),
+        "btfem_dist_trace": (C.c_int, [H, C.c_int64]),
+        "btfem_dist_get_trace": (C.c_int, [H, C.c_void_p, C.c_int64, _c_int64_p]),
     }
     for name, (res, args) in proto.items():
         f = getattr(lib, name)
@@ -347,6 +349,17 @@ class BTFem:
         self._ck(self.lib.btfem_dist_connect(self.h, int(rank), int(world), blobs.ctypes.data_as(C.c_void_p),
                                              len(src), _ip(src), _ip(dst_rank), _ip(dst_slot), len(us), _ip(us),
                                              _ip(ur), _ip(ui), _ip(recv_from)))
+
+    def dist_trace(self, max_entries):
+        self._trace_cap = int(max_entries)
+        self._ck(self.lib.btfem_dist_trace(self.h, int(max_entries)))
+
+    def dist_get_trace(self):
+        """(n,8) uint64: first block start, local work done, collective done, longest halo wait [ns], kind, 0, 0, 0."""
+        out = np.zeros((self._trace_cap, 8), dtype=np.uint64)
+        n = C.c_int64()
+        self._ck(self.lib.btfem_dist_get_trace(self.h, out.ctypes.data_as(C.c_void_p), self._trace_cap, C.byref(n)))
+        return out[:n.value]
 
     def solution(self):
         u = np.empty(self.ndof, dtype=np.complex128)

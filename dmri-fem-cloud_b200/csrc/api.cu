@@ -367,4 +367,19 @@ int btfem_dist_connect(btfem_t* h, int32_t rank, int32_t world, const void* blob
   });
 }
 
+int btfem_dist_trace(btfem_t* h, int64_t max_entries) {
+  return guarded(h, [&] {
+    BT_REQUIRE(max_entries >= 0 && max_entries < (1LL << 28), "bad trace size");
+    BT_REQUIRE(!h->dist_connected, "enable tracing before btfem_dist_connect");
+    h->trace_cap = max_entries;
+  });
+}
+
+int btfem_dist_get_trace(btfem_t* h, uint64_t* out, int64_t max_entries, int64_t* n_entries) {
+  return guarded(h, [&] {
+    BT_REQUIRE(out && n_entries && max_entries >= 0, "null argument");
+    *n_entries = bt_dist_get_trace(h, out, max_entries);
+  });
+}
+
 }  // extern "C"

@@ -80,19 +80,26 @@ struct KrylovCtrl {
   int step;        // time step the iteration kernels work on
   int step_next;   // time step the next RHS launch starts
   int nonzero_guess;
-  int pad_;
+  int failed;             // sticky: a step ended with a negative reason; the remaining steps are skipped
   unsigned int ticket[8];
+  // device-driven time loop (the whole step is one graph with a WHILE node): statistics kept on the device
+  long long total_iters;
+  int max_iters;
+  unsigned int member_ticket;
 };
 
 // ---- row partition of ONE mesh over several GPUs (one process per GPU, peer memory over NVLink) -------------
 #define BT_MAX_RANKS 8
-#define BT_COMM_ELEMS 64        // double2 elements reserved behind the vector slab for the DistComm block
+#define BT_COMM_ELEMS 128       // double2 elements reserved behind the vector slab for the DistComm block
 
 // Lives in the IPC-exported allocation of every rank; written by the PEERS with system-scope stores.
+// All-reduce payloads use the "LL" encoding: a double travels as two 8-byte words (sequence number << 32 | half of
+// the bits), stored with one 16-byte store; 8-byte stores are single-copy atomic, so a reader that sees the
+// expected sequence number in both words has the value -- no fence, no separate flag (measured on 2 x B200:
+// 1.0 us per exchange against 4.1 us for payload + __threadfence_system + flag; scripts/p2p_latency.cu).
 struct DistComm {
-  unsigned long long halo_flag[BT_MAX_RANKS];     // [sender] = sequence number of the sender's last halo push
-  unsigned long long ar_flag[2][BT_MAX_RANKS];    // all-reduce: [buffer][sender] = sequence number
-  double ar_val[2][BT_MAX_RANKS][4];              // all-reduce payload
+  unsigned long long halo_flag[BT_MAX_RANKS];        // [sender] = sequence number of the sender's last halo push
+  unsigned long long ar_ll[2][BT_MAX_RANKS][4][2];   // all-reduce: [buffer][sender][value][half]
 };
 static_assert(sizeof(DistComm) <= BT_COMM_ELEMS * 16, "DistComm does not fit its reservation");
 
@@ -111,10 +118,19 @@ struct DistDev {
   const int32_t* send_src;           // [n_send] local owned dof
   const int32_t* send_rank;          // [n_send] destination rank
   const int32_t* send_slot;          // [n_send] element index in the destination's vectors
+  // the same Krylov entries grouped by source row, for the update kernels that push while they produce:
+  // boundary row n_int + j sends entries [bsend_ptr[j], bsend_ptr[j+1])
+  const int32_t* bsend_ptr;
+  const int32_t* bsend_rank;
+  const int32_t* bsend_slot;
   // state (sequence numbers never reset: every rank runs the same sequence of exchanges)
   unsigned long long push_seq, ar_seq;
   unsigned long long timeout_ns;
   unsigned int push_ticket;
+  // optional timeline (btfem_dist_trace): entry k = {first block start, local work done, collective done,
+  // longest halo wait} in globaltimer ns, one entry per kernel that closes a collective
+  unsigned long long* trace;
+  unsigned int trace_cap, trace_pos;
   int error;                         // a wait timed out: the solve is abandoned on every rank
 };
 
@@ -179,7 +195,9 @@ struct btfem {
   bool dist_connected = false, dist_failed = false;
   int rank = 0, world = 1;
   DevArray<DistDev> d_dist;
-  DevArray<int32_t> d_send_src, d_send_rank, d_send_slot;
+  DevArray<unsigned long long> d_trace;
+  int64_t trace_cap = 0;
+  DevArray<int32_t> d_send_src, d_send_rank, d_send_slot, d_bsend_ptr, d_bsend_rank, d_bsend_slot;
   void* peer_map[BT_MAX_RANKS] = {nullptr};   // cudaIpcOpenMemHandle mappings to close
   int64_t n_rows() const { return nv_own >= 0 ? n_own : ndof; }
 
@@ -262,3 +280,4 @@ void bt_dist_connect(btfem* h, int rank, int world, const void* blobs, int64_t n
                      const int32_t* dst_rank, const int32_t* dst_slot, int64_t nsend_u, const int32_t* src_u,
                      const int32_t* dst_rank_u, const int32_t* dst_index_u, const int32_t* recv_from);
 void bt_dist_close(btfem* h);
+int64_t bt_dist_get_trace(btfem* h, uint64_t* out, int64_t max_entries);

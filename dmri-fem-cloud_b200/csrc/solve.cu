@@ -13,6 +13,7 @@
 // so one iteration is five kernels with constant arguments, replayed as a CUDA graph.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <unistd.h>
@@ -52,22 +53,74 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __noinline__ bool spin_until(const unsigned long long* flag, unsigned long long seq,
-                                        unsigned long long timeout_ns) {
-  if (ld_acquire_sys(flag) >= seq) return true;
-  const unsigned long long t0 = global_ns();
-  for (;;) {
-#pragma unroll 1
-    for (int i = 0; i < 32; ++i)
-      if (ld_acquire_sys(flag) >= seq) return true;
-    if (global_ns() - t0 > timeout_ns) return false;
+// timeline hooks (no-ops unless btfem_dist_trace enabled a buffer)
+__device__ __forceinline__ void trace_mark(DistDev* d, int field) {
+  if (d->trace && d->trace_pos < d->trace_cap) d->trace[8 * (size_t)d->trace_pos + field] = global_ns();
+}
+__device__ __forceinline__ void trace_start(DistDev* d, int kind) {
+  if (d && d->trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    trace_mark(d, 0);
+    if (d->trace_pos < d->trace_cap) d->trace[8 * (size_t)d->trace_pos + 4] = (unsigned long long)kind;
+  }
+}
+__device__ __forceinline__ void trace_close(DistDev* d) {   // one thread, after the kernel's collective
+  if (d->trace) {
+    trace_mark(d, 2);
+    d->trace_pos = d->trace_pos + 1;
   }
 }
 
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Polls with relaxed loads (an acquire load per poll costs ~1.3 us on B200) and fences once on success.
+__device__ __noinline__ bool spin_until(const unsigned long long* flag, unsigned long long seq,
+                                        unsigned long long timeout_ns) {
+  bool ok = ld_relaxed_sys(flag) >= seq;
+  if (!ok) {
+    const unsigned long long t0 = global_ns();
+    for (;;) {
+#pragma unroll 1
+      for (int i = 0; i < 64 && !ok; ++i) ok = ld_relaxed_sys(flag) >= seq;
+      if (ok || global_ns() - t0 > timeout_ns) break;
+    }
+  }
+  __threadfence_system();   // acquire: what the peer wrote before the flag is read after it
+  return ok;
+}
+// LL words: one double <-> two (sequence, half) words moved by a single 16-byte access
+__device__ __forceinline__ void st_ll(unsigned long long* p, double v, unsigned int seq32) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long hi = (unsigned long long)seq32 << 32;
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(hi | (b & 0xffffffffull)), "l"(hi | (b >> 32))
+               : "memory");
+}
+__device__ __noinline__ bool ld_ll(const unsigned long long* p, unsigned int seq32, unsigned long long timeout_ns,
+                                   double* out) {
+  unsigned long long w0, w1;
+  unsigned long long t0 = 0;
+  for (int it = 0;; ++it) {
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+    if ((unsigned int)(w0 >> 32) == seq32 && (unsigned int)(w1 >> 32) == seq32) break;
+    if ((it & 63) == 63) {
+      if (t0 == 0) t0 = global_ns();
+      else if (global_ns() - t0 > timeout_ns) return false;
+    }
+  }
+  *out = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+  return true;
+}
+
 // All-reduce of NV doubles over the ranks, called by the 32 lanes of ONE warp per rank (v identical in all
-// lanes).  Lane r stores this rank's terms into rank r's comm block, then publishes the sequence number;
-// lane r then waits for rank r's terms.  The sum runs in rank order, so every rank gets the same bits.
-// Two payload buffers alternate: a rank can be at most one all-reduce ahead of the slowest rank.
+// lanes).  Lane r stores this rank's terms into rank r's comm block (LL words: the sequence number travels with
+// the data); lane r then polls rank r's terms.  The sum runs in rank order, so every rank gets the same bits.
+// Two payload buffers alternate: a rank can be at most one all-reduce ahead of the slowest rank, and it has
+// consumed buffer b (the poll loop returned its values) before it contributes to the next all-reduce.
 template <int NV>
 __device__ __forceinline__ void dist_allreduce(double (&v)[NV], DistDev* d) {
   const int lane = threadIdx.x & 31;
@@ -75,22 +128,21 @@ __device__ __forceinline__ void dist_allreduce(double (&v)[NV], DistDev* d) {
   const int buf = (int)(seq & 1);
   const int rank = d->rank, world = d->world;
   __syncwarp();
+  const unsigned int seq32 = (unsigned int)seq;
+  if (lane == 0) trace_mark(d, 1);
   if (lane < world) {
     DistComm* pc = d->comm[lane];
 #pragma unroll
-    for (int q = 0; q < NV; ++q) *(volatile double*)&pc->ar_val[buf][rank][q] = v[q];
-    __threadfence_system();
-    st_release_sys(&pc->ar_flag[buf][rank], seq);
+    for (int q = 0; q < NV; ++q) st_ll(&pc->ar_ll[buf][rank][q][0], v[q], seq32);
   }
   double mine[NV];
-  bool ok = true;
+  bool ok = d->error == 0;
 #pragma unroll
   for (int q = 0; q < NV; ++q) mine[q] = 0.0;
-  if (lane < world) {
+  if (ok && lane < world) {
     DistComm* me = d->comm[rank];
-    ok = spin_until(&me->ar_flag[buf][lane], seq, d->timeout_ns);
 #pragma unroll
-    for (int q = 0; q < NV; ++q) mine[q] = *(volatile double*)&me->ar_val[buf][lane][q];
+    for (int q = 0; q < NV; ++q) ok = ld_ll(&me->ar_ll[buf][lane][q][0], seq32, d->timeout_ns, &mine[q]) && ok;
   }
   __syncwarp();
 #pragma unroll
@@ -103,6 +155,7 @@ __device__ __forceinline__ void dist_allreduce(double (&v)[NV], DistDev* d) {
   if (lane == 0) {
     d->ar_seq = seq;
     if (!ok) d->error = 1;
+    trace_close(d);
   }
   __syncwarp();
 }
@@ -231,11 +284,29 @@ struct SpmvArgs {
   size_t mat_stride_csr, mat_stride_sell, vec_stride, part_stride, step_stride;
   double* sig_out;           // k_signal: [members][2]
   DistDev* dist;             // row-partitioned solve: peers, halo send list, sequence numbers (else null)
+  // device-driven loop: the BiCGStab iteration is the body of a graph WHILE node whose condition the kernels set
+  cudaGraphConditionalHandle cond;
+  int use_cond;
+  KrylovCtrl* ctrl0;         // member 0 (a.ctrl is shifted per member)
+  int32_t* iters_out;        // [nsteps] iteration count of every step (member 0), or null
 };
 
 // a lost peer ends the solve on every rank
 __device__ __forceinline__ void comm_check(const SpmvArgs& a) {
   if (a.dist && a.dist->error) { a.ctrl->done = 1; a.ctrl->reason = BTFEM_ECOMM; }
+}
+
+// Device-driven loop: called by the one thread per member that just updated ctrl->done.  The WHILE node of the
+// step graph runs its body (one BiCGStab iteration of every member) again while any member is still working.
+// `done` only goes 0 -> 1 inside the loop, so "all done" is final; concurrent callers of different members may
+// leave a stale 1 behind, which costs one empty pass: k_update_xr calls this again on its skip path.
+__device__ __forceinline__ void loop_condition(const SpmvArgs& a) {
+  if (!a.use_cond) return;
+  const unsigned int members = gridDim.y;
+  if (members > 1) __threadfence();
+  unsigned int any = 0;
+  for (unsigned int b = 0; b < members; ++b) any |= (((volatile KrylovCtrl*)a.ctrl0)[b].done == 0);
+  cudaGraphSetConditional(a.cond, any);
 }
 
 // arguments of batch member blockIdx.y
@@ -275,6 +346,7 @@ __device__ __forceinline__ ModeSetup mode_setup(const SpmvArgs& a) {
   if (MODE == MODE_PLAIN) {
     m.V = a.use_sell ? a.PJs : a.PJ; m.x = a.x_plain; m.c = a.c_plain;
   } else if (MODE == MODE_RHS) {
+    m.skip = ctrl->failed != 0;      // device-driven loop: the steps queued behind a failure do nothing
     m.V = a.use_sell ? a.QJs : a.QJ; m.x = a.u; m.c = ctrl->theta_cb_scale * a.cb[ctrl->step_next];
   } else {
     m.skip = ctrl->done != 0;
@@ -339,6 +411,7 @@ __device__ __forceinline__ void mode_finalize(const SpmvArgs& a, double (&acc)[2
         else if (bn <= ctrl->ttol) { ctrl->done = 1; ctrl->reason = bn < ctrl->atol ? 3 : 2; }
       }
       comm_check(a);
+      loop_condition(a);
     }
   } else if (MODE == MODE_RESID) {
     double v1[1] = {acc[0]};
@@ -349,6 +422,7 @@ __device__ __forceinline__ void mode_finalize(const SpmvArgs& a, double (&acc)[2
       if (!(rn == rn) || isinf(rn)) { ctrl->done = 1; ctrl->reason = BTFEM_ENAN; }
       else if (rn <= ctrl->ttol) { ctrl->done = 1; ctrl->reason = rn < ctrl->atol ? 3 : 2; }
       comm_check(a);
+      loop_condition(a);
     }
   } else if (MODE == MODE_V) {
     double v1[1] = {acc[0]};
@@ -438,10 +512,60 @@ __device__ __forceinline__ double2 ldv_gather_f64x2(const double2* p) {
 // region of x starts on its own 128-byte line, so no line holding halo entries is cached before this returns.
 __device__ __forceinline__ void halo_wait(DistDev* d) {
   const int lane = threadIdx.x & 31;
+  if (d->error) return;   // a peer is lost: fail fast, every later wait would time out as well
   if (lane < d->n_recv_ranks) {
+    const unsigned long long t0 = d->trace ? global_ns() : 0;
     if (!spin_until(&d->comm[d->rank]->halo_flag[d->recv_ranks[lane]], d->push_seq, d->timeout_ns)) d->error = 1;
+    if (d->trace && d->trace_pos < d->trace_cap) atomicMax(&d->trace[8 * (size_t)d->trace_pos + 3], global_ns() - t0);
   }
   __syncwarp();
+}
+
+// Called by every thread of the `participants` blocks that stored halo entries into peer vectors: once all of
+// them have passed their system-scope fence, the last block publishes the next sequence number to the peers.
+__device__ __forceinline__ void halo_publish(DistDev* d, unsigned int participants) {
+  __shared__ int s_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&d->push_ticket, 1u) == participants - 1);
+  __syncthreads();
+  if (!s_last) return;
+  const unsigned long long seq = d->push_seq + 1;
+  __syncthreads();
+  if (threadIdx.x < d->n_send_ranks) {
+    __threadfence_system();
+    st_relaxed_sys(&d->comm[d->send_ranks[threadIdx.x]]->halo_flag[d->rank], seq);
+  }
+  if (threadIdx.x == 0) {
+    d->push_seq = seq;
+    d->push_ticket = 0;
+    trace_mark(d, 1);
+    trace_close(d);
+  }
+}
+
+// Row-partitioned vector update: the rows peers need ([n_int, n), grouped at the end of the owned rows) are
+// produced FIRST by the leading blocks, stored locally and straight into the peers' halo slots (vector `vi` of
+// the slab), and published; the remaining rows follow, so the transfer overlaps the rest of the update and the
+// halo-free part of the next SpMV.  F(i) computes row i.
+template <typename F>
+__device__ __forceinline__ int push_boundary_rows(DistDev* d, int n, int vi, double2* __restrict__ out, F&& f) {
+  const int n_int = d->n_int;
+  const int nb = n - n_int;
+  const unsigned int participants = (unsigned int)max(1, min((int)gridDim.x, (nb + TPB - 1) / TPB));
+  if (blockIdx.x < participants) {
+    for (int j = blockIdx.x * TPB + threadIdx.x; j < nb; j += participants * TPB) {
+      const int i = n_int + j;
+      const double2 val = f(i);
+      out[i] = val;
+      for (int e = d->bsend_ptr[j]; e < d->bsend_ptr[j + 1]; ++e) {
+        const int r = d->bsend_rank[e];
+        d->vecs[r][(size_t)vi * d->npad[r] + d->bsend_slot[e]] = val;
+      }
+    }
+    halo_publish(d, participants);
+  }
+  return n_int;
 }
 
 // Halo push: entries of a freshly produced vector (WHICH: 0 = u, 1 = p, 2 = s) that peers need are stored
@@ -450,7 +574,6 @@ template <int WHICH>
 __global__ void __launch_bounds__(TPB) k_halo_push(SpmvArgs a, int check_done) {
   DistDev* d = a.dist;
   if (check_done && a.ctrl->done) return;
-  __shared__ int s_last;
   const double2* __restrict__ src = WHICH == 0 ? a.u : (WHICH == 1 ? a.p : a.s);
   const int vi = WHICH == 0 ? 0 : (WHICH == 1 ? 3 : 5);   // slab order: u r rp p v s t
   const int ns = WHICH == 0 ? d->n_send_u : d->n_send;   // u also carries the periodic-gather sources
@@ -459,19 +582,7 @@ __global__ void __launch_bounds__(TPB) k_halo_push(SpmvArgs a, int check_done) {
     const double2 v = src[d->send_src[e]];
     d->vecs[r][(size_t)vi * d->npad[r] + d->send_slot[e]] = v;
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&d->push_ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence_system();
-  const unsigned long long seq = d->push_seq + 1;
-  __syncthreads();
-  if (threadIdx.x < d->n_send_ranks) st_release_sys(&d->comm[d->send_ranks[threadIdx.x]]->halo_flag[d->rank], seq);
-  if (threadIdx.x == 0) {
-    d->push_seq = seq;
-    d->push_ticket = 0;
-  }
+  halo_publish(d, gridDim.x);
 }
 
 // ---- variant C (default): SELL-32.  Rows are grouped in slices of 32 (after sorting by length inside
@@ -489,6 +600,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_spmv_sell(SpmvArgs a_in) {
   const SpmvArgs a = member(a_in);
   const ModeSetup m = mode_setup<MODE>(a);
   if (m.skip) return;
+  if (MODE != MODE_PLAIN) trace_start(a.dist, MODE);
   const int lane = threadIdx.x & 31;
   const int wpb = TPB / 32;
   double acc[2] = {0.0, 0.0};
@@ -550,38 +662,48 @@ __global__ void __launch_bounds__(TPB) k_update_p(SpmvArgs a_in) {
   const SpmvArgs a = member(a_in);
   const KrylovCtrl* ctrl = a.ctrl;
   if (ctrl->done) return;
+  trace_start(a.dist, 5);
   const double beta = (ctrl->rho / ctrl->rho_old) * (ctrl->alpha / ctrl->omega);
   const double ob = ctrl->omega * beta;
   const double2* __restrict__ r = a.r;
   const double2* __restrict__ v = a.v;
   double2* __restrict__ p = a.p;
-  for (int i = blockIdx.x * TPB + threadIdx.x; i < a.n; i += gridDim.x * TPB) {
+  auto row = [&](int i) {
     double2 rr = r[i], vv = v[i], pp = p[i];
     pp.x = rr.x - ob * vv.x + beta * pp.x;
     pp.y = rr.y - ob * vv.y + beta * pp.y;
-    p[i] = pp;
-  }
+    return pp;
+  };
+  const int n = a.dist ? push_boundary_rows(a.dist, a.n, 3, p, row) : a.n;
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) p[i] = row(i);
 }
 
 // s <- r - alpha*v
 __global__ void __launch_bounds__(TPB) k_update_s(SpmvArgs a_in) {
   const SpmvArgs a = member(a_in);
   if (a.ctrl->done) return;
+  trace_start(a.dist, 6);
   const double alpha = a.ctrl->alpha;
   const double2* __restrict__ r = a.r;
   const double2* __restrict__ v = a.v;
   double2* __restrict__ s = a.s;
-  for (int i = blockIdx.x * TPB + threadIdx.x; i < a.n; i += gridDim.x * TPB) {
+  auto row = [&](int i) {
     double2 rr = r[i], vv = v[i];
-    s[i] = make_double2(rr.x - alpha * vv.x, rr.y - alpha * vv.y);
-  }
+    return make_double2(rr.x - alpha * vv.x, rr.y - alpha * vv.y);
+  };
+  const int n = a.dist ? push_boundary_rows(a.dist, a.n, 5, s, row) : a.n;
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) s[i] = row(i);
 }
 
 // x <- x + alpha*p + omega*s ; r <- s - omega*t ; rho' = (r,rp) ; ||r|| ; convergence test
 __global__ void __launch_bounds__(TPB) k_update_xr(SpmvArgs a_in) {
   const SpmvArgs a = member(a_in);
   KrylovCtrl* ctrl = a.ctrl;
-  if (ctrl->done) return;
+  if (ctrl->done) {   // this member stopped earlier in the pass (or in an earlier pass): keep the loop condition current
+    if (blockIdx.x == 0 && threadIdx.x == 0) loop_condition(a);
+    return;
+  }
+  trace_start(a.dist, 7);
   const double alpha = ctrl->alpha, omega = ctrl->omega;
   const bool fresh = (ctrl->iters == 0) && !ctrl->nonzero_guess;   // zero initial guess: x starts from 0
   double2* __restrict__ x = a.u;
@@ -616,7 +738,36 @@ __global__ void __launch_bounds__(TPB) k_update_xr(SpmvArgs a_in) {
     else if (rho_used == 0.0 || omega == 0.0) { ctrl->done = 1; ctrl->reason = BTFEM_EBREAKDOWN; }
     else if (it >= ctrl->maxit) { ctrl->done = 1; ctrl->reason = BTFEM_ENOTCONV; }
     comm_check(a);
+    loop_condition(a);
   }
+}
+
+// End of a time step of the device-driven loop: statistics, the PETSc corner case "converged before the first
+// iteration with a zero initial guess returns x = 0", and the sticky failure flag.
+__global__ void __launch_bounds__(TPB) k_step_end(SpmvArgs a_in) {
+  const SpmvArgs a = member(a_in);
+  KrylovCtrl* ctrl = a.ctrl;
+  if (ctrl->failed) return;
+  const int it = ctrl->iters, reason = ctrl->reason;
+  if (it == 0 && !ctrl->nonzero_guess && reason > 0) {
+    double2* __restrict__ u = a.u;
+    for (int i = blockIdx.x * TPB + threadIdx.x; i < a.n; i += gridDim.x * TPB) u[i] = make_double2(0.0, 0.0);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ctrl->total_iters += it;
+    if (it > ctrl->max_iters) ctrl->max_iters = it;
+    if (a.iters_out && blockIdx.y == 0) a.iters_out[ctrl->step] = it;
+  }
+}
+
+// runs after k_step_end (same stream): a failure of any member stops every member
+__global__ void k_step_fail(KrylovCtrl* ctrl, int members) {
+  int bad = 0;
+  for (int b = 0; b < members; ++b)
+    if (!ctrl[b].failed && ctrl[b].reason < 0 && ctrl[b].done) bad = ctrl[b].reason;
+  if (bad)
+    for (int b = 0; b < members; ++b)
+      if (!ctrl[b].failed) ctrl[b].failed = bad;
 }
 
 // evicts L2 with clean lines (a memset would leave dirty lines whose write-back overlaps the timed kernel)
@@ -880,6 +1031,7 @@ SpmvArgs base_args(btfem* h) {
   a.cA = h->d_cA.p;
   a.cb = h->d_cb.p;
   a.ctrl = h->d_ctrl.p;
+  a.ctrl0 = h->d_ctrl.p;
   a.partials = h->d_partials.p;
   a.u = h->d_u.p; a.r = h->d_r.p; a.rp = h->d_rp.p; a.p = h->d_p.p; a.v = h->d_v.p; a.s = h->d_s.p; a.t = h->d_t.p;
   a.mat_stride_csr = (size_t)h->nnz;
@@ -1217,8 +1369,8 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   }
   if (periodic) {
     h->d_Fb.upload(sa->Fb, sa->nsteps, st);
-    h->d_ubc.alloc(n);
-    h->d_rhs_add.alloc(n);
+    h->d_ubc.alloc(h->ndof);       // indexed by local dof: halo boundary dofs are columns of owned rows of B
+    h->d_rhs_add.alloc(h->ndof);
     h->d_ubc.zero(st);
     h->d_rhs_add.zero(st);
   }
@@ -1242,34 +1394,103 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   const int vgx = std::max(1, std::min(vec_grid(n), std::max(BT_NUM_SMS, BT_NUM_SMS * 8 / members)));
   const dim3 vg(vgx, members);
 
-  // one BiCGStab iteration (of every member) as a graph
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t gexec = nullptr;
-  BT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  // The BiCGStab iteration (of every member) as a CUDA graph.  Default ("device" loop): one graph per TIME STEP
+  // -- u push / periodic terms / RHS, then a WHILE node whose body is the iteration and whose condition the
+  // kernels themselves set from ctrl->done -- so the host queues nsteps graph launches and never waits inside the
+  // solve.  BTFEM_LOOP=host (and GMRES): the iteration graph is re-launched by the host, which polls ctrl->done.
+  const char* loop_env = getenv("BTFEM_LOOP");
+  const bool dev_loop = !gmres && !(loop_env && loop_env[0] == 'h');
   const int push_grid = part ? std::max(1, std::min(32, ((int)h->d_send_src.n + TPB - 1) / TPB)) : 0;
-  k_update_p<<<vg, TPB, 0, st>>>(a);
-  if (part) k_halo_push<1><<<push_grid, TPB, 0, st>>>(a, 1);
-  launch_spmv<MODE_V>(lanes, a, st, members);
-  k_update_s<<<vg, TPB, 0, st>>>(a);
-  if (part) k_halo_push<2><<<push_grid, TPB, 0, st>>>(a, 1);
-  launch_spmv<MODE_T>(lanes, a, st, members);
-  k_update_xr<<<vg, TPB, 0, st>>>(a);
-  BT_CUDA(cudaStreamEndCapture(st, &graph));
-  const int kernels_per_iter = part ? 7 : 5;
-  if (h->l2_window_set) {   // captured kernel nodes do not inherit the stream's access-policy window
+  const int kernels_per_iter = 5;
+  int unroll = 6;
+  if (const char* e = getenv("BTFEM_UNROLL")) unroll = std::max(1, std::min(64, atoi(e)));
+  DevArray<int32_t> d_iters;
+  if (dev_loop && iters_per_step) {
+    d_iters.alloc(sa->nsteps);
+    d_iters.zero(st);
+    a.iters_out = d_iters.p;
+  }
+  auto capture_prologue = [&]() {
+    if (part) k_halo_push<0><<<push_grid, TPB, 0, st>>>(a, 0);
+    if (periodic) {
+      k_periodic_ubc<<<((int)h->n_pb + TPB - 1) / TPB, TPB, 0, st>>>(
+          (int)h->n_pb, h->d_ctrl.p, h->d_Fb.p, sa->q, sa->gdir[0], sa->gdir[1], sa->gdir[2], h->d_pb_dof.p,
+          h->d_pb_src.p, h->d_pb_w.p, h->d_pb_dx.p, h->d_u.p, h->d_ubc.p, a.dist);
+      k_periodic_rhs<<<((int)h->n_pb_rows + TPB - 1) / TPB, TPB, 0, st>>>(
+          (int)h->n_pb_rows, h->d_pb_rows.p, h->d_rowptr.p, h->d_colidx.p, h->d_Bhat.p, 1.0 - sa->theta,
+          h->d_ubc.p, h->d_rhs_add.p);
+    }
+    launch_spmv<MODE_RHS>(lanes, a, st, members);
+    if (sa->nonzero_guess) launch_spmv<MODE_RESID>(lanes, a, st, members);
+  };
+  const int prologue_kernels = (part ? 1 : 0) + (periodic ? 2 : 0) + 1 + (sa->nonzero_guess ? 1 : 0);
+  auto capture_iteration = [&]() {
+    k_update_p<<<vg, TPB, 0, st>>>(a);     // row-partitioned: also stores the rows peers need into their halos
+    launch_spmv<MODE_V>(lanes, a, st, members);
+    k_update_s<<<vg, TPB, 0, st>>>(a);     // ditto
+    launch_spmv<MODE_T>(lanes, a, st, members);
+    k_update_xr<<<vg, TPB, 0, st>>>(a);
+  };
+  auto pin_vectors = [&](cudaGraph_t g) {   // captured kernel nodes do not inherit the stream's access-policy window
+    if (!h->l2_window_set) return;
     size_t nn = 0;
-    BT_CUDA(cudaGraphGetNodes(graph, nullptr, &nn));
+    if (cudaGraphGetNodes(g, nullptr, &nn) != cudaSuccess || nn == 0) { cudaGetLastError(); return; }
     std::vector<cudaGraphNode_t> nodes(nn);
-    BT_CUDA(cudaGraphGetNodes(graph, nodes.data(), &nn));
+    if (cudaGraphGetNodes(g, nodes.data(), &nn) != cudaSuccess) { cudaGetLastError(); return; }
     cudaKernelNodeAttrValue av;
     av.accessPolicyWindow = h->l2_window;
-    for (size_t i = 0; i < nn; ++i) {
+    int pinned = 0;
+    for (size_t i = 0; i < nn; ++i) {   // persistence is an optimisation: a node that refuses the attribute is left alone
       cudaGraphNodeType ty;
-      BT_CUDA(cudaGraphNodeGetType(nodes[i], &ty));
-      if (ty == cudaGraphNodeTypeKernel)
-        cudaGraphKernelNodeSetAttribute(nodes[i], cudaKernelNodeAttributeAccessPolicyWindow, &av);
+      if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (ty == cudaGraphNodeTypeKernel &&
+          cudaGraphKernelNodeSetAttribute(nodes[i], cudaKernelNodeAttributeAccessPolicyWindow, &av) == cudaSuccess)
+        ++pinned;
     }
     cudaGetLastError();
+    if (getenv("BTFEM_DEBUG")) fprintf(stderr, "[btfem] graph %p: %zu nodes, %d kernel nodes pinned to the L2 window\n", (void*)g, nn, pinned);
+  };
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  if (dev_loop) {
+    BT_CUDA(cudaGraphCreate(&graph, 0));
+    cudaGraphConditionalHandle hc;
+    BT_CUDA(cudaGraphConditionalHandleCreate(&hc, graph, 0, cudaGraphCondAssignDefault));
+    a.cond = hc;
+    a.use_cond = 1;
+    BT_CUDA(cudaStreamBeginCaptureToGraph(st, graph, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    capture_prologue();
+    cudaStreamCaptureStatus cs;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t ndeps = 0;
+    BT_CUDA(cudaStreamGetCaptureInfo(st, &cs, nullptr, nullptr, &deps, &ndeps));
+    std::vector<cudaGraphNode_t> tail(deps, deps + ndeps);
+    cudaGraph_t same = nullptr;
+    BT_CUDA(cudaStreamEndCapture(st, &same));
+    cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+    cp.conditional.handle = hc;
+    cp.conditional.type = cudaGraphCondTypeWhile;
+    cp.conditional.size = 1;
+    cudaGraphNode_t wnode;
+    BT_CUDA(cudaGraphAddNode(&wnode, graph, tail.data(), tail.size(), &cp));
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    // One evaluation of the WHILE condition costs about as much as a small kernel chain (measured: ~12 us per
+    // pass against ~7 us for a host re-launch), so a pass holds several iterations; once ctrl->done is set the
+    // remaining kernels of the pass return at once (~2 us each).
+    BT_CUDA(cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    for (int u = 0; u < unroll; ++u) capture_iteration();
+    BT_CUDA(cudaStreamEndCapture(st, &same));
+    BT_CUDA(cudaStreamBeginCaptureToGraph(st, graph, &wnode, nullptr, 1, cudaStreamCaptureModeThreadLocal));
+    k_step_end<<<vg, TPB, 0, st>>>(a);
+    k_step_fail<<<1, 1, 0, st>>>(h->d_ctrl.p, members);
+    BT_CUDA(cudaStreamEndCapture(st, &same));
+    pin_vectors(graph);
+    pin_vectors(body);
+  } else {
+    BT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    capture_iteration();
+    BT_CUDA(cudaStreamEndCapture(st, &graph));
+    pin_vectors(graph);
   }
   BT_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
 
@@ -1281,7 +1502,22 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   int64_t n_spmv = 0, n_kernels = 0;
   int est = 4;
   int fail = 0;
-  for (int64_t step = 0; step < sa->nsteps && !fail; ++step) {
+  if (dev_loop) {
+    for (int64_t step = 0; step < sa->nsteps; ++step) BT_CUDA(cudaGraphLaunch(gexec, st));
+    BT_CUDA(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl.p, sizeof(KrylovCtrl) * members, cudaMemcpyDeviceToHost, st));
+    BT_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < members; ++b) {
+      total_iters[b] = h->h_ctrl[b].total_iters;
+      max_iters[b] = h->h_ctrl[b].max_iters;
+      last_reason[b] = h->h_ctrl[b].failed ? h->h_ctrl[b].failed : h->h_ctrl[b].reason;
+      if (h->h_ctrl[b].failed) fail = h->h_ctrl[b].failed;
+      n_spmv += (1 + (sa->nonzero_guess ? 1 : 0)) * sa->nsteps + 2 * total_iters[b];
+    }
+    const int64_t passes = *std::max_element(total_iters.begin(), total_iters.end());
+    n_kernels = (prologue_kernels + 2) * sa->nsteps + kernels_per_iter * passes;   // kernels that did work
+    if (iters_per_step) d_iters.download(iters_per_step, st);
+  }
+  for (int64_t step = 0; !dev_loop && step < sa->nsteps && !fail; ++step) {
     if (part) {
       k_halo_push<0><<<push_grid, TPB, 0, st>>>(a, 0);
       ++n_kernels;
@@ -1498,16 +1734,56 @@ void bt_dist_connect(btfem* h, int rank, int world, const void* blobs, int64_t n
     if (to[r]) d.send_ranks[d.n_send_ranks++] = r;
     if (recv_from && recv_from[r] && r != rank) d.recv_ranks[d.n_recv_ranks++] = r;
   }
+  {   // the Krylov entries grouped by boundary row (counting sort on src - n_int)
+    const int64_t nb = h->n_own - h->n_int;
+    std::vector<int32_t> ptr(nb + 1, 0), brank(nsend), bslot(nsend);
+    for (int64_t e = 0; e < nsend; ++e) {
+      BT_REQUIRE(src[e] >= h->n_int, "send list: an interior dof cannot be needed by a peer");
+      ++ptr[src[e] - h->n_int + 1];
+    }
+    for (int64_t j = 0; j < nb; ++j) ptr[j + 1] += ptr[j];
+    std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+    for (int64_t e = 0; e < nsend; ++e) {
+      const int32_t pos = fill[src[e] - h->n_int]++;
+      brank[pos] = dst_rank[e];
+      bslot[pos] = dst_slot[e];
+    }
+    h->d_bsend_ptr.upload(ptr.data(), ptr.size(), h->stream);
+    h->d_bsend_rank.upload(brank.data(), brank.size(), h->stream);
+    h->d_bsend_slot.upload(bslot.data(), bslot.size(), h->stream);
+    d.bsend_ptr = h->d_bsend_ptr.p;
+    d.bsend_rank = h->d_bsend_rank.p;
+    d.bsend_slot = h->d_bsend_slot.p;
+  }
   h->d_send_src.upload(all_src.data(), all_src.size(), h->stream);
   h->d_send_rank.upload(all_rank.data(), all_rank.size(), h->stream);
   h->d_send_slot.upload(all_slot.data(), all_slot.size(), h->stream);
   d.send_src = h->d_send_src.p;
   d.send_rank = h->d_send_rank.p;
   d.send_slot = h->d_send_slot.p;
+  if (h->trace_cap > 0) {
+    h->d_trace.alloc(8 * (size_t)h->trace_cap);
+    h->d_trace.zero(h->stream);
+    d.trace = h->d_trace.p;
+    d.trace_cap = (unsigned int)h->trace_cap;
+  }
   h->d_dist.upload(&d, 1, h->stream);
   BT_CUDA(cudaStreamSynchronize(h->stream));
   h->rank = rank;
   h->world = world;
   h->dist_connected = true;
   h->dist_failed = false;
+}
+
+// Timeline of the first trace_cap collective-closing kernels since btfem_dist_connect: 8 words per entry
+// {first block start, local work done, collective done, longest halo wait, kind, 0, 0, 0}, globaltimer ns;
+// kind: 1 RHS, 2 residual, 3 SpMV v=Ap, 4 SpMV t=As, 5 update p, 6 update s, 7 update x/r, 0 other (u push, signal).
+int64_t bt_dist_get_trace(btfem* h, uint64_t* out, int64_t max_entries) {
+  BT_REQUIRE(h->dist_connected && h->trace_cap > 0, "tracing is not enabled (btfem_dist_trace before btfem_dist_connect)");
+  BT_CUDA(cudaStreamSynchronize(h->stream));
+  DistDev dd;
+  BT_CUDA(cudaMemcpy(&dd, h->d_dist.p, sizeof(dd), cudaMemcpyDeviceToHost));
+  const int64_t n = std::min<int64_t>(std::min<int64_t>(dd.trace_pos, h->trace_cap), max_entries);
+  if (n > 0) BT_CUDA(cudaMemcpy(out, h->d_trace.p, sizeof(uint64_t) * 8 * n, cudaMemcpyDeviceToHost));
+  return n;
 }

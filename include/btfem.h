@@ -205,6 +205,14 @@ int btfem_dist_connect(btfem_t* h, int32_t rank, int32_t world, const void* blob
                        const int32_t* src_u, const int32_t* dst_rank_u, const int32_t* dst_index_u,
                        const int32_t* recv_from /*[world]*/);
 
+/* Optional device-side timeline of a row-partitioned solve (measurement aid): call btfem_dist_trace before
+ * btfem_dist_connect; every kernel that closes a collective (halo publish in the update kernels, all-reduce in the
+ * SpMV / update_xr / signal kernels) then logs 8 words {first block start, local work done, collective done, longest
+ * halo wait, kind, 0, 0, 0} (GPU globaltimer ns; kind: 1 RHS, 2 residual, 3 SpMV v=Ap, 4 SpMV t=As, 5 update p,
+ * 6 update s, 7 update x/r, 0 other), for the first max_entries such kernels. */
+int btfem_dist_trace(btfem_t* h, int64_t max_entries);
+int btfem_dist_get_trace(btfem_t* h, uint64_t* out /*[max_entries*8]*/, int64_t max_entries, int64_t* n_entries);
+
 #ifdef __cplusplus
 }
 #endif

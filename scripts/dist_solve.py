@@ -1,7 +1,7 @@
 """One mesh row-partitioned over the GPUs of a node, one process per GPU (run under torchrun):
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-      scripts/dist_solve.py --n 78 [--check] [--reps 2] [--ecs NX]
+      scripts/dist_solve.py --nbox 78 [--check] [--reps 2] [--ecs NX]
 
 Workload: bench.py's configs[1] cell-in-box PGSE solve (or, with --ecs, the two-compartment extracellular-space
 slab of configs[3] without its periodic BC).  The host side only needs python-object collectives (gloo); halo
@@ -24,11 +24,12 @@ import bench  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=78)
+    ap.add_argument("--nbox", type=int, default=78)
     ap.add_argument("--ecs", type=int, default=0, help="use the ECS slab with this many cells per edge instead")
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--bvalue", type=float, default=1000.0)
+    ap.add_argument("--trace", type=int, default=0, help="log the first N collective-closing kernels per rank")
     args = ap.parse_args()
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -45,10 +46,10 @@ def main():
         g = np.array([1.0, 1.0, 0.0]) / np.sqrt(2.0)
         D, kappa, name = 2e-3, 1e-5, "ECS slab %dx%dx2 (configs[3] geometry, Neumann)" % (args.ecs, args.ecs)
     else:
-        xyz, tets, phase = bench.workload(args.n)
+        xyz, tets, phase = bench.workload(args.nbox)
         mp, ts, f, fp = bench.sequence(k=200.0, b=args.bvalue)
         g = np.array([0.0, 1.0, 0.0])
-        D, kappa, name = 3e-3, 1e-5, "configs[1] cell-in-box n_box=%d" % args.n
+        D, kappa, name = 3e-3, 1e-5, "configs[1] cell-in-box n_box=%d" % args.nbox
     k, q = 200.0, mp.qvalue
     kw = dict(rtol=1e-9, atol=1e-10, maxit=100000)
 
@@ -57,9 +58,14 @@ def main():
     d.set_diffusion(D)
     d.set_relaxation(1e-16)
     d.set_permeability(kappa)
+    if args.trace:
+        d.fem.dist_trace(args.trace)
     d.assemble()
     setup_s = time.perf_counter() - t0
     res = d.solve(k, 0.5, q * f, q * fp, g, **kw)            # warm-up
+    if args.trace:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        np.save(os.path.join(ROOT, "gpurun_out", "trace_w%d_r%d.npy" % (world, rank)), d.fem.dist_get_trace())
     comm.barrier()
     loop_ms, wall = [], []
     for _ in range(args.reps):

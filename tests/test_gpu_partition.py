@@ -256,7 +256,7 @@ def _gpu_count():
 @pytest.mark.skipif(_gpu_count() < 2, reason="needs >= 2 GPUs (one process per GPU over CUDA IPC)")
 def test_two_processes_two_gpus():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29617", os.path.join(ROOT, "scripts", "dist_solve.py"), "--n", "12", "--check"]
+           "127.0.0.1", "--master-port", "29617", os.path.join(ROOT, "scripts", "dist_solve.py"), "--nbox", "12", "--check"]
     env = dict(os.environ, BTFEM_COMM_TIMEOUT_MS="10000")
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
