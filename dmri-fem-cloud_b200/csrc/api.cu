@@ -194,15 +194,15 @@ int btfem_set_periodic_gather(btfem_t* h, int64_t nb, const int32_t* dof, const 
         if (s <= -2) n_extra = std::max<int64_t>(n_extra, (int64_t)(-2 - s) + 1);
       }
     }
-    // sources become ELEMENT indices relative to u: local dof (+ halo shift), or the source buffer that sits
-    // behind the seven vectors and the DistComm block of a partitioned handle
+    // sources become ELEMENT indices relative to u.  Partitioned handle: halo dofs sit halo_shift elements
+    // further, and everything at or behind halo_begin = n_own + halo_shift is read from the LL buffer of u --
+    // the halo dofs first, then the mirrored sources the owning peers deliver (src = -2-k -> entry n_halo + k)
     std::vector<int32_t> elem(src, src + 3 * nb);
     if (part) {
-      const int64_t n_el = h->ndof + h->halo_shift;
-      const int64_t tail = 7 * ((n_el + 15) & ~(int64_t)15) + BT_COMM_ELEMS;
-      BT_REQUIRE(tail + n_extra < (int64_t)0x7fffffffLL, "periodic source buffer exceeds int32 indexing");
+      const int64_t halo_begin = h->n_own + h->halo_shift, n_halo = h->ndof - h->n_own;
+      BT_REQUIRE(halo_begin + n_halo + n_extra < (int64_t)0x7fffffffLL, "periodic source buffer exceeds int32 indexing");
       for (auto& s : elem) {
-        if (s <= -2) s = (int32_t)(tail + (-2 - s));
+        if (s <= -2) s = (int32_t)(halo_begin + n_halo + (-2 - s));
         else if (s >= h->n_own) s += (int32_t)h->halo_shift;
       }
       if (n_extra != h->n_extra) h->d_vecs.release();

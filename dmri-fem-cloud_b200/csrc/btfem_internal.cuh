@@ -90,48 +90,61 @@ struct KrylovCtrl {
 
 // ---- row partition of ONE mesh over several GPUs (one process per GPU, peer memory over NVLink) -------------
 #define BT_MAX_RANKS 8
-#define BT_COMM_ELEMS 128       // double2 elements reserved behind the vector slab for the DistComm block
+#define BT_COMM_ELEMS 64        // double2 elements reserved behind the vector slab for the DistComm block
 
 // Lives in the IPC-exported allocation of every rank; written by the PEERS with system-scope stores.
-// All-reduce payloads use the "LL" encoding: a double travels as two 8-byte words (sequence number << 32 | half of
-// the bits), stored with one 16-byte store; 8-byte stores are single-copy atomic, so a reader that sees the
-// expected sequence number in both words has the value -- no fence, no separate flag (measured on 2 x B200:
-// 1.0 us per exchange against 4.1 us for payload + __threadfence_system + flag; scripts/p2p_latency.cu).
+// Everything that crosses NVLink uses the "LL" encoding: a double travels as two 8-byte words (sequence number
+// << 32 | half of the bits) stored with one 16-byte store; 8-byte stores are single-copy atomic, so a reader that
+// sees the expected sequence number in both words has the value -- no fence, no separate flag, one NVLink flight
+// (measured on 2 x B200, scripts/p2p_latency.cu: 1.0 us per exchange against 4.1 us for payload +
+// __threadfence_system + flag, 7-11 us for a fenced bulk push).
 struct DistComm {
-  unsigned long long halo_flag[BT_MAX_RANKS];        // [sender] = sequence number of the sender's last halo push
   unsigned long long ar_ll[2][BT_MAX_RANKS][4][2];   // all-reduce: [buffer][sender][value][half]
 };
+
 static_assert(sizeof(DistComm) <= BT_COMM_ELEMS * 16, "DistComm does not fit its reservation");
 
-// Device-resident description of the partition (local memory of each rank).
+// Mutable state of a partitioned handle (device memory of the rank itself).
 struct DistDev {
+  unsigned long long gen[3];         // generation of the halo entries of u, p, s last published to the peers
+  unsigned long long ar_seq;         // all-reduces done (never reset: every rank runs the same sequence)
+  unsigned int tick[3];              // block tickets of the kernels that produce u (push), p, s
+  int error;                         // a wait timed out: the solve is abandoned on every rank
+  // optional timeline (btfem_dist_trace): 8 words per kernel that closes a collective
+  unsigned long long* trace;
+  unsigned int trace_cap, trace_pos;
+};
+
+// per-peer addresses (device memory, read-only after btfem_dist_connect; indexed by a run-time rank)
+struct PeerTab {
+  unsigned long long* ll[BT_MAX_RANKS];   // LL halo buffer of every rank (own or peer-mapped)
+  DistComm* comm[BT_MAX_RANKS];           // comm block of every rank
+  int n_ll[BT_MAX_RANKS];                 // LL entries per vector at every rank
+};
+
+// Immutable description of the partition, passed BY VALUE with the kernel arguments (scalars and pointers only,
+// so that it stays in the constant bank).
+struct DistView {
+  int on;                            // 0: whole-mesh handle
   int rank, world;
-  int n_send;                        // halo entries this rank pushes per exchange
-  int n_send_u;                      // n_send + entries pushed only with u (sources of the periodic gather)
-  int n_send_ranks, n_recv_ranks;
-  int send_ranks[BT_MAX_RANKS], recv_ranks[BT_MAX_RANKS];
+  int n_int;                         // owned rows [0,n_int) are not needed by any peer and reference no halo column
+  int halo_begin;                    // vector element index of the first halo dof (n_own rounded up to 8)
+  int n_ll;                          // LL entries per vector here: halo dofs, then periodic-gather sources
   int wait_slice;                    // SELL slices below this one never touch a halo column
-  int n_int;                         // owned rows [0,n_int) are not needed by any peer
-  DistComm* comm[BT_MAX_RANKS];      // comm block of every rank (own or peer-mapped)
-  double2* vecs[BT_MAX_RANKS];       // base of every rank's Krylov vector slab
-  long long npad[BT_MAX_RANKS];      // vector stride (elements) of every rank's slab
-  const int32_t* send_src;           // [n_send] local owned dof
-  const int32_t* send_rank;          // [n_send] destination rank
-  const int32_t* send_slot;          // [n_send] element index in the destination's vectors
-  // the same Krylov entries grouped by source row, for the update kernels that push while they produce:
+  int n_send_u;                      // entries of the per-step u push (halo dofs + periodic sources of the peers)
+  DistDev* st;
+  unsigned long long* ll;            // this rank's LL buffer [3][n_ll][4 words]
+  DistComm* comm;                    // this rank's comm block
+  const PeerTab* peers;
+  const int32_t* send_src;           // [n_send_u] local owned dof
+  const int32_t* send_rank;          // [n_send_u] destination rank
+  const int32_t* send_slot;          // [n_send_u] LL entry at the destination
+  // the Krylov entries grouped by source row, for the update kernels that push while they produce:
   // boundary row n_int + j sends entries [bsend_ptr[j], bsend_ptr[j+1])
   const int32_t* bsend_ptr;
   const int32_t* bsend_rank;
   const int32_t* bsend_slot;
-  // state (sequence numbers never reset: every rank runs the same sequence of exchanges)
-  unsigned long long push_seq, ar_seq;
   unsigned long long timeout_ns;
-  unsigned int push_ticket;
-  // optional timeline (btfem_dist_trace): entry k = {first block start, local work done, collective done,
-  // longest halo wait} in globaltimer ns, one entry per kernel that closes a collective
-  unsigned long long* trace;
-  unsigned int trace_cap, trace_pos;
-  int error;                         // a wait timed out: the solve is abandoned on every rank
 };
 
 // what the ranks exchange (through the host layer) before btfem_dist_connect
@@ -140,9 +153,9 @@ struct DistBlob {
   int64_t pid;
   uint64_t raw_ptr;
   int64_t device;
-  int64_t npad, n_own, ndof, n_extra;
+  int64_t npad, n_own, ndof, n_extra, halo_shift;
   cudaIpcMemHandle_t ipc;            // 64 bytes
-  char pad_[BTFEM_DIST_BLOB_BYTES - 8 * 8 - 64];
+  char pad_[BTFEM_DIST_BLOB_BYTES - 9 * 8 - 64];
 };
 static_assert(sizeof(DistBlob) == BTFEM_DIST_BLOB_BYTES, "DistBlob size");
 
@@ -195,6 +208,8 @@ struct btfem {
   bool dist_connected = false, dist_failed = false;
   int rank = 0, world = 1;
   DevArray<DistDev> d_dist;
+  DistView dview{};                   // filled by btfem_dist_connect
+  DevArray<PeerTab> d_peers;
   DevArray<unsigned long long> d_trace;
   int64_t trace_cap = 0;
   DevArray<int32_t> d_send_src, d_send_rank, d_send_slot, d_bsend_ptr, d_bsend_rank, d_bsend_slot;
@@ -208,6 +223,11 @@ struct btfem {
   // SELL-32 copy of the pattern for the fused SpMV (rows sorted by length inside windows of BT_SELL_SIGMA)
   int64_t n_slice = 0, nnz_sell = 0;
   DevArray<int32_t> d_slice_ptr;   // [n_slice+1]
+  // static warp schedule of the fused SpMV (setup.cu: list scheduling of the slices over the warps of the launch)
+  DevArray<int32_t> d_sched;       // [n_slice] slice ids, grouped by warp
+  DevArray<int32_t> d_sched_ptr;   // [2*sched_warps+1]: warp w runs sched[ptr[2w] .. ptr[2w+1]) with halo reads,
+                                   //                    then sched[ptr[2w+1] .. ptr[2w+2]) plain
+  int sched_grid = 0;              // blocks of the launch the schedule was built for
   DevArray<int32_t> d_sell_row;    // [n_slice*32] slot -> row (-1 = padding slot)
   DevArray<int32_t> d_sell_slot;   // [ndof] row -> slot
   DevArray<int32_t> d_sell_col;    // [nnz_sell]

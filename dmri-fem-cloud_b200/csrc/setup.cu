@@ -12,6 +12,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <functional>
+#include <queue>
 
 #include "btfem_internal.cuh"
 
@@ -632,6 +634,44 @@ void bt_build_pattern(btfem* h) {
                                                       (int)h->halo_shift);
   h->d_PJs.release();
   h->d_QJs.release();
+  // Static warp schedule.  A round-robin of slices over warps leaves a tail (some warps get one slice more, and in
+  // a row partition the halo-reading slices cost about twice a plain one); a dynamic queue would fix that but make
+  // the order of the dot-product partial sums depend on timing.  So the queue is SIMULATED here, once: slices are
+  // dealt in order -- halo-reading ones first, then ascending, which keeps all warps on neighbouring slices at any
+  // time -- each to the warp with the least estimated work so far.  Deterministic, and part of the handle.
+  {
+    const int wpb = 256 / 32;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nslice + wpb - 1) / wpb, BT_NUM_SMS * 3));
+    const int nw = grid * wpb;
+    const int64_t first_halo = h->nv_own >= 0 ? std::min<int64_t>(nslice, (h->n_int / BT_SELL_SIGMA) * (BT_SELL_SIGMA / 32))
+                                             : nslice;
+    std::vector<std::vector<int32_t>> lists(nw);
+    std::vector<int32_t> nhalo(nw, 0);
+    typedef std::pair<double, int> Load;   // (estimated work, warp): min-heap, ties -> lowest warp id
+    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+    for (int w = 0; w < nw; ++w) heap.push(Load(0.0, w));
+    auto deal = [&](int64_t s, double factor) {
+      Load l = heap.top();
+      heap.pop();
+      const double width = (slice_ptr[s + 1] - slice_ptr[s]) / 32.0;
+      lists[l.second].push_back((int32_t)s);
+      heap.push(Load(l.first + 3.0 + factor * width, l.second));
+      return l.second;
+    };
+    for (int64_t s = first_halo; s < nslice; ++s) ++nhalo[deal(s, 2.5)];
+    for (int64_t s = 0; s < first_halo; ++s) deal(s, 1.0);
+    std::vector<int32_t> sched, ptr(2 * nw + 1, 0);
+    sched.reserve(nslice);
+    for (int w = 0; w < nw; ++w) {
+      ptr[2 * w] = (int32_t)sched.size();
+      ptr[2 * w + 1] = ptr[2 * w] + nhalo[w];
+      sched.insert(sched.end(), lists[w].begin(), lists[w].end());
+    }
+    ptr[2 * nw] = (int32_t)sched.size();
+    h->d_sched.upload(sched.data(), sched.size(), st);
+    h->d_sched_ptr.upload(ptr.data(), ptr.size(), st);
+    h->sched_grid = grid;
+  }
   BT_CUDA(cudaGetLastError());
   BT_CUDA(cudaStreamSynchronize(st));
 }

@@ -37,17 +37,9 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ------------------------------------------------------------------------------------ peer-memory primitives
-// Row-partitioned solves (one rank per GPU): flags and payloads live in the peers' DistComm blocks and are
-// accessed with system-scope acquire/release; every wait is bounded so that a lost peer ends the solve with
-// BTFEM_ECOMM instead of hanging the GPU.
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
+// Row-partitioned solves (one rank per GPU).  Data crossing NVLink is LL-encoded (btfem_internal.cuh): the
+// sequence number travels inside every 8-byte word, so there are no flags and no fences; every poll is bounded
+// so that a lost peer ends the solve with BTFEM_ECOMM instead of hanging the GPU.
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -57,10 +49,10 @@ __device__ __forceinline__ unsigned long long global_ns() {
 __device__ __forceinline__ void trace_mark(DistDev* d, int field) {
   if (d->trace && d->trace_pos < d->trace_cap) d->trace[8 * (size_t)d->trace_pos + field] = global_ns();
 }
-__device__ __forceinline__ void trace_start(DistDev* d, int kind) {
-  if (d && d->trace && blockIdx.x == 0 && threadIdx.x == 0) {
-    trace_mark(d, 0);
-    if (d->trace_pos < d->trace_cap) d->trace[8 * (size_t)d->trace_pos + 4] = (unsigned long long)kind;
+__device__ __forceinline__ void trace_start(const DistView& dv, int kind) {
+  if (dv.on && dv.st->trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    trace_mark(dv.st, 0);
+    if (dv.st->trace_pos < dv.st->trace_cap) dv.st->trace[8 * (size_t)dv.st->trace_pos + 4] = (unsigned long long)kind;
   }
 }
 __device__ __forceinline__ void trace_close(DistDev* d) {   // one thread, after the kernel's collective
@@ -70,29 +62,6 @@ __device__ __forceinline__ void trace_close(DistDev* d) {   // one thread, after
   }
 }
 
-__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// Polls with relaxed loads (an acquire load per poll costs ~1.3 us on B200) and fences once on success.
-__device__ __noinline__ bool spin_until(const unsigned long long* flag, unsigned long long seq,
-                                        unsigned long long timeout_ns) {
-  bool ok = ld_relaxed_sys(flag) >= seq;
-  if (!ok) {
-    const unsigned long long t0 = global_ns();
-    for (;;) {
-#pragma unroll 1
-      for (int i = 0; i < 64 && !ok; ++i) ok = ld_relaxed_sys(flag) >= seq;
-      if (ok || global_ns() - t0 > timeout_ns) break;
-    }
-  }
-  __threadfence_system();   // acquire: what the peer wrote before the flag is read after it
-  return ok;
-}
 // LL words: one double <-> two (sequence, half) words moved by a single 16-byte access
 __device__ __forceinline__ void st_ll(unsigned long long* p, double v, unsigned int seq32) {
   const unsigned long long b = (unsigned long long)__double_as_longlong(v);
@@ -100,20 +69,45 @@ __device__ __forceinline__ void st_ll(unsigned long long* p, double v, unsigned 
   asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(hi | (b & 0xffffffffull)), "l"(hi | (b >> 32))
                : "memory");
 }
+__device__ __forceinline__ bool ld_ll_try(const unsigned long long* p, unsigned int seq32, double* out) {
+  unsigned long long w0, w1;
+  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+  *out = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+  return (unsigned int)(w0 >> 32) == seq32 && (unsigned int)(w1 >> 32) == seq32;
+}
 __device__ __noinline__ bool ld_ll(const unsigned long long* p, unsigned int seq32, unsigned long long timeout_ns,
                                    double* out) {
-  unsigned long long w0, w1;
   unsigned long long t0 = 0;
   for (int it = 0;; ++it) {
-    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
-    if ((unsigned int)(w0 >> 32) == seq32 && (unsigned int)(w1 >> 32) == seq32) break;
+    if (ld_ll_try(p, seq32, out)) return true;
     if ((it & 63) == 63) {
       if (t0 == 0) t0 = global_ns();
       else if (global_ns() - t0 > timeout_ns) return false;
     }
   }
-  *out = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
-  return true;
+}
+// one complex vector entry = two LL doubles (32 bytes)
+__device__ __forceinline__ void st_ll2(unsigned long long* p, double2 v, unsigned int seq32) {
+  st_ll(p, v.x, seq32);
+  st_ll(p + 2, v.y, seq32);
+}
+// One halo entry (4 LL words at p) of generation seq32, as stored by the owning peer.
+__device__ __noinline__ double2 ld_halo_slow(const unsigned long long* p, unsigned int seq32, DistDev* st,
+                                             unsigned long long timeout_ns) {
+  double2 v = make_double2(0.0, 0.0);
+  if (st->error) return v;   // a peer is lost: fail fast, later waits would time out as well
+  const unsigned long long t0 = global_ns();
+  const bool ok = ld_ll(p, seq32, timeout_ns, &v.x) && ld_ll(p + 2, seq32, timeout_ns, &v.y);
+  if (!ok) { st->error = 1; return make_double2(0.0, 0.0); }
+  if (st->trace && st->trace_pos < st->trace_cap) atomicMax(&st->trace[8 * (size_t)st->trace_pos + 3], global_ns() - t0);
+  return v;
+}
+// Halo entry k of vector `which` (0 = u, 1 = p, 2 = s).
+__device__ __forceinline__ double2 ld_halo(const DistView& dv, int which, int k, unsigned int seq32) {
+  const unsigned long long* p = dv.ll + ((size_t)which * dv.n_ll + k) * 4;
+  double2 v;
+  if (ld_ll_try(p, seq32, &v.x) && ld_ll_try(p + 2, seq32, &v.y)) return v;   // usually there already
+  return ld_halo_slow(p, seq32, dv.st, dv.timeout_ns);
 }
 
 // All-reduce of NV doubles over the ranks, called by the 32 lanes of ONE warp per rank (v identical in all
@@ -122,16 +116,17 @@ __device__ __noinline__ bool ld_ll(const unsigned long long* p, unsigned int seq
 // Two payload buffers alternate: a rank can be at most one all-reduce ahead of the slowest rank, and it has
 // consumed buffer b (the poll loop returned its values) before it contributes to the next all-reduce.
 template <int NV>
-__device__ __forceinline__ void dist_allreduce(double (&v)[NV], DistDev* d) {
+__device__ __forceinline__ void dist_allreduce(double (&v)[NV], const DistView& dv) {
+  DistDev* d = dv.st;
   const int lane = threadIdx.x & 31;
   const unsigned long long seq = d->ar_seq + 1;
   const int buf = (int)(seq & 1);
-  const int rank = d->rank, world = d->world;
+  const int rank = dv.rank, world = dv.world;
   __syncwarp();
   const unsigned int seq32 = (unsigned int)seq;
   if (lane == 0) trace_mark(d, 1);
   if (lane < world) {
-    DistComm* pc = d->comm[lane];
+    DistComm* pc = dv.peers->comm[lane];
 #pragma unroll
     for (int q = 0; q < NV; ++q) st_ll(&pc->ar_ll[buf][rank][q][0], v[q], seq32);
   }
@@ -140,9 +135,9 @@ __device__ __forceinline__ void dist_allreduce(double (&v)[NV], DistDev* d) {
 #pragma unroll
   for (int q = 0; q < NV; ++q) mine[q] = 0.0;
   if (ok && lane < world) {
-    DistComm* me = d->comm[rank];
+    DistComm* me = dv.comm;
 #pragma unroll
-    for (int q = 0; q < NV; ++q) ok = ld_ll(&me->ar_ll[buf][lane][q][0], seq32, d->timeout_ns, &mine[q]) && ok;
+    for (int q = 0; q < NV; ++q) ok = ld_ll(&me->ar_ll[buf][lane][q][0], seq32, dv.timeout_ns, &mine[q]) && ok;
   }
   __syncwarp();
 #pragma unroll
@@ -164,7 +159,7 @@ __device__ __forceinline__ void dist_allreduce(double (&v)[NV], DistDev* d) {
 // Returns true in thread 0 of that last block with v[] = grand totals (over all ranks when `dist` is set).
 template <int NV>
 __device__ bool reduce_finalize(double (&v)[NV], double* __restrict__ partials, unsigned int* ticket,
-                                DistDev* dist = nullptr) {
+                                const DistView* dist = nullptr) {
   __shared__ double sm[NV][NWARP];
   __shared__ int s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -206,7 +201,7 @@ __device__ bool reduce_finalize(double (&v)[NV], double* __restrict__ partials, 
       double t = lane < NWARP ? sm[q][lane] : 0.0;
       v[q] = warp_sum(t);
     }
-    if (dist) dist_allreduce<NV>(v, dist);
+    if (dist && dist->on) dist_allreduce<NV>(v, *dist);
   }
   if (threadIdx.x == 0) *ticket = 0;
   return threadIdx.x == 0;
@@ -259,6 +254,9 @@ struct SpmvArgs {
   int n;
   int nslice;                // SELL-32: number of 32-row slices
   const int32_t* slice_ptr;  // [nslice+1] offset of each slice in the SELL arrays (multiple of 32)
+  const int32_t* sched;      // static warp schedule (setup.cu), or null: round-robin
+  const int32_t* sched_ptr;
+  int sched_grid;
   const int32_t* sell_row;   // [nslice*32] row owned by each slot (-1 = padding)
   const int32_t* sell_col;   // [nnz_sell] column indices, slice-column-major (padding: the row itself)
   const double2* PJs;        // SELL copies of PJ / QJ
@@ -283,7 +281,7 @@ struct SpmvArgs {
   // strides between consecutive members.  The pattern arrays are shared.
   size_t mat_stride_csr, mat_stride_sell, vec_stride, part_stride, step_stride;
   double* sig_out;           // k_signal: [members][2]
-  DistDev* dist;             // row-partitioned solve: peers, halo send list, sequence numbers (else null)
+  DistView dist;             // row-partitioned solve: peers, LL buffers, send lists (dist.on == 0: whole mesh)
   // device-driven loop: the BiCGStab iteration is the body of a graph WHILE node whose condition the kernels set
   cudaGraphConditionalHandle cond;
   int use_cond;
@@ -293,7 +291,7 @@ struct SpmvArgs {
 
 // a lost peer ends the solve on every rank
 __device__ __forceinline__ void comm_check(const SpmvArgs& a) {
-  if (a.dist && a.dist->error) { a.ctrl->done = 1; a.ctrl->reason = BTFEM_ECOMM; }
+  if (a.dist.on && a.dist.st->error) { a.ctrl->done = 1; a.ctrl->reason = BTFEM_ECOMM; }
 }
 
 // Device-driven loop: called by the one thread per member that just updated ctrl->done.  The WHILE node of the
@@ -395,7 +393,7 @@ __device__ __forceinline__ void mode_finalize(const SpmvArgs& a, double (&acc)[2
   if (MODE == MODE_PLAIN) return;
   if (MODE == MODE_RHS) {
     double v1[1] = {acc[0]};
-    if (reduce_finalize<1>(v1, a.partials, &ctrl->ticket[TK_RHS], a.dist)) {
+    if (reduce_finalize<1>(v1, a.partials, &ctrl->ticket[TK_RHS], &a.dist)) {
       double bn = sqrt(v1[0]);
       ctrl->bnorm = bn;
       ctrl->ttol = fmax(ctrl->rtol * bn, ctrl->atol);
@@ -415,7 +413,7 @@ __device__ __forceinline__ void mode_finalize(const SpmvArgs& a, double (&acc)[2
     }
   } else if (MODE == MODE_RESID) {
     double v1[1] = {acc[0]};
-    if (reduce_finalize<1>(v1, a.partials, &ctrl->ticket[TK_RESID], a.dist)) {
+    if (reduce_finalize<1>(v1, a.partials, &ctrl->ticket[TK_RESID], &a.dist)) {
       double rn = sqrt(v1[0]);
       ctrl->rho = v1[0];
       ctrl->rnorm = rn;
@@ -426,14 +424,14 @@ __device__ __forceinline__ void mode_finalize(const SpmvArgs& a, double (&acc)[2
     }
   } else if (MODE == MODE_V) {
     double v1[1] = {acc[0]};
-    if (reduce_finalize<1>(v1, a.partials + 2 * BT_MAX_PARTIALS, &ctrl->ticket[TK_V], a.dist)) {
+    if (reduce_finalize<1>(v1, a.partials + 2 * BT_MAX_PARTIALS, &ctrl->ticket[TK_V], &a.dist)) {
       if (v1[0] == 0.0) { ctrl->done = 1; ctrl->reason = BTFEM_EBREAKDOWN; ctrl->alpha = 0.0; }
       else ctrl->alpha = ctrl->rho / v1[0];
       comm_check(a);
     }
   } else {
     double v2[2] = {acc[0], acc[1]};
-    if (reduce_finalize<2>(v2, a.partials + 3 * BT_MAX_PARTIALS, &ctrl->ticket[TK_T], a.dist)) {
+    if (reduce_finalize<2>(v2, a.partials + 3 * BT_MAX_PARTIALS, &ctrl->ticket[TK_T], &a.dist)) {
       ctrl->omega = (v2[1] == 0.0) ? 0.0 : v2[0] / v2[1];
       comm_check(a);
     }
@@ -508,81 +506,149 @@ __device__ __forceinline__ double2 ldv_gather_f64x2(const double2* p) {
   return v;
 }
 
-// One warp waits until every peer that sends to this rank has published the current exchange.  The halo
-// region of x starts on its own 128-byte line, so no line holding halo entries is cached before this returns.
-__device__ __forceinline__ void halo_wait(DistDev* d) {
-  const int lane = threadIdx.x & 31;
-  if (d->error) return;   // a peer is lost: fail fast, every later wait would time out as well
-  if (lane < d->n_recv_ranks) {
-    const unsigned long long t0 = d->trace ? global_ns() : 0;
-    if (!spin_until(&d->comm[d->rank]->halo_flag[d->recv_ranks[lane]], d->push_seq, d->timeout_ns)) d->error = 1;
-    if (d->trace && d->trace_pos < d->trace_cap) atomicMax(&d->trace[8 * (size_t)d->trace_pos + 3], global_ns() - t0);
-  }
-  __syncwarp();
-}
-
-// Called by every thread of the `participants` blocks that stored halo entries into peer vectors: once all of
-// them have passed their system-scope fence, the last block publishes the next sequence number to the peers.
-__device__ __forceinline__ void halo_publish(DistDev* d, unsigned int participants) {
-  __shared__ int s_last;
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&d->push_ticket, 1u) == participants - 1);
-  __syncthreads();
-  if (!s_last) return;
-  const unsigned long long seq = d->push_seq + 1;
-  __syncthreads();
-  if (threadIdx.x < d->n_send_ranks) {
-    __threadfence_system();
-    st_relaxed_sys(&d->comm[d->send_ranks[threadIdx.x]]->halo_flag[d->rank], seq);
-  }
-  if (threadIdx.x == 0) {
-    d->push_seq = seq;
-    d->push_ticket = 0;
-    trace_mark(d, 1);
-    trace_close(d);
-  }
-}
-
 // Row-partitioned vector update: the rows peers need ([n_int, n), grouped at the end of the owned rows) are
-// produced FIRST by the leading blocks, stored locally and straight into the peers' halo slots (vector `vi` of
-// the slab), and published; the remaining rows follow, so the transfer overlaps the rest of the update and the
-// halo-free part of the next SpMV.  F(i) computes row i.
+// produced FIRST by the leading blocks, stored locally and -- LL-encoded, generation gen+1 -- straight into the
+// peers' halo buffers over NVLink; the remaining rows follow, so the transfer overlaps the rest of the update
+// and the halo-free part of the next SpMV.  No fence, no flag: the consumer polls the words it needs.
+// `which`: 0 = u, 1 = p, 2 = s.  F(i) computes row i.  Returns the number of rows left for the plain loop.
 template <typename F>
-__device__ __forceinline__ int push_boundary_rows(DistDev* d, int n, int vi, double2* __restrict__ out, F&& f) {
-  const int n_int = d->n_int;
+__device__ __forceinline__ int push_boundary_rows(const DistView& dv, int which, int n, double2* __restrict__ out,
+                                                  F&& f) {
+  const int n_int = dv.n_int;
   const int nb = n - n_int;
-  const unsigned int participants = (unsigned int)max(1, min((int)gridDim.x, (nb + TPB - 1) / TPB));
-  if (blockIdx.x < participants) {
+  const unsigned int g32 = (unsigned int)(dv.st->gen[which] + 1);
+  const int participants = max(1, min((int)gridDim.x, (nb + TPB - 1) / TPB));
+  if ((int)blockIdx.x < participants) {
     for (int j = blockIdx.x * TPB + threadIdx.x; j < nb; j += participants * TPB) {
       const int i = n_int + j;
       const double2 val = f(i);
       out[i] = val;
-      for (int e = d->bsend_ptr[j]; e < d->bsend_ptr[j + 1]; ++e) {
-        const int r = d->bsend_rank[e];
-        d->vecs[r][(size_t)vi * d->npad[r] + d->bsend_slot[e]] = val;
+      for (int e = dv.bsend_ptr[j]; e < dv.bsend_ptr[j + 1]; ++e) {
+        const int r = dv.bsend_rank[e];
+        st_ll2(dv.peers->ll[r] + ((size_t)which * dv.peers->n_ll[r] + dv.bsend_slot[e]) * 4, val, g32);
       }
     }
-    halo_publish(d, participants);
   }
   return n_int;
 }
 
-// Halo push: entries of a freshly produced vector (WHICH: 0 = u, 1 = p, 2 = s) that peers need are stored
-// straight into the peers' vectors over NVLink; the last block then publishes the sequence number.
-template <int WHICH>
-__global__ void __launch_bounds__(TPB) k_halo_push(SpmvArgs a, int check_done) {
-  DistDev* d = a.dist;
-  if (check_done && a.ctrl->done) return;
-  const double2* __restrict__ src = WHICH == 0 ? a.u : (WHICH == 1 ? a.p : a.s);
-  const int vi = WHICH == 0 ? 0 : (WHICH == 1 ? 3 : 5);   // slab order: u r rp p v s t
-  const int ns = WHICH == 0 ? d->n_send_u : d->n_send;   // u also carries the periodic-gather sources
-  for (int e = blockIdx.x * TPB + threadIdx.x; e < ns; e += gridDim.x * TPB) {
-    const int r = d->send_rank[e];
-    const double2 v = src[d->send_src[e]];
-    d->vecs[r][(size_t)vi * d->npad[r] + d->send_slot[e]] = v;
+// Every block of a producing kernel calls this when it is done; the last one makes the new generation current.
+// All blocks have read gen[which] by then, and the consumers are later kernels on the same stream.
+__device__ __forceinline__ void bump_generation(const DistView& dv, int which) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    DistDev* st = dv.st;
+    if (atomicAdd(&st->tick[which], 1u) == gridDim.x - 1) {
+      st->tick[which] = 0;
+      st->gen[which] = st->gen[which] + 1;
+      trace_mark(st, 1);
+      trace_close(st);
+    }
   }
-  halo_publish(d, gridDim.x);
+}
+
+// Per time step: the entries of u that peers need (their halo dofs and the mirrored sources of their periodic
+// gather) go out the same way.
+__global__ void __launch_bounds__(TPB) k_halo_push_u(SpmvArgs a) {
+  const DistView dv = a.dist;
+  trace_start(dv, 0);
+  const unsigned int g32 = (unsigned int)(dv.st->gen[0] + 1);
+  const double2* __restrict__ u = a.u;
+  for (int e = blockIdx.x * TPB + threadIdx.x; e < dv.n_send_u; e += gridDim.x * TPB) {
+    const int r = dv.send_rank[e];
+    st_ll2(dv.peers->ll[r] + (size_t)dv.send_slot[e] * 4, u[dv.send_src[e]], g32);
+  }
+  bump_generation(dv, 0);
+}
+
+// y_row for one SELL slice, plain: every column is a local vector element.
+template <int SELL_UNR>
+__device__ __forceinline__ double2 slice_product(const int32_t* cp, const double2* vp, int width, const double2* x,
+                                                 double c) {
+  double ar = 0.0, ai = 0.0;
+  int j = 0;
+  for (; j + SELL_UNR <= width; j += SELL_UNR) {
+    int col[SELL_UNR];
+    double2 val[SELL_UNR], xv[SELL_UNR];
+#pragma unroll
+    for (int u = 0; u < SELL_UNR; ++u) {
+      col[u] = ldv_stream_i32(cp + (j + u) * 32);
+      val[u] = ldv_stream_f64x2(vp + (j + u) * 32);
+    }
+#pragma unroll
+    for (int u = 0; u < SELL_UNR; ++u) xv[u] = ldv_gather_f64x2(x + col[u]);
+#pragma unroll
+    for (int u = 0; u < SELL_UNR; ++u) {
+      const double pa = val[u].x, pb = c * val[u].y;
+      ar = fma(pa, xv[u].x, ar);
+      ar = fma(-pb, xv[u].y, ar);
+      ai = fma(pa, xv[u].y, ai);
+      ai = fma(pb, xv[u].x, ai);
+    }
+  }
+  for (; j < width; ++j) {
+    const int col = ld_stream(cp + j * 32);
+    const double2 val = ld_stream(vp + j * 32);
+    const double2 xv = ldv_gather_f64x2(x + col);
+    const double pa = val.x, pb = c * val.y;
+    ar = fma(pa, xv.x, ar);
+    ar = fma(-pb, xv.y, ar);
+    ai = fma(pa, xv.y, ai);
+    ai = fma(pb, xv.x, ai);
+  }
+  return make_double2(ar, ai);
+}
+
+// The same for a slice whose rows may reference halo dofs (columns >= halo_begin): those values are LL words in
+// this rank's halo buffer.  Both 16-byte loads of every entry of a batch are issued before any is examined (a
+// system-scope load is an L2 round trip; issued one after the other they would dominate the slice), and only an
+// entry that has not arrived yet falls back to the bounded poll.  Same summation order as the plain loop.
+template <int UNR>
+__device__ __forceinline__ double2 slice_product_halo(const int32_t* cp, const double2* vp, int width, const double2* x,
+                                                      double c, const DistView& dv, int which, unsigned int gen32) {
+  const unsigned long long* ll = dv.ll + (size_t)which * dv.n_ll * 4;
+  const int hb = dv.halo_begin;
+  double ar = 0.0, ai = 0.0;
+  for (int j = 0; j < width; j += UNR) {
+    int col[UNR];
+    double2 val[UNR], xv[UNR];
+    unsigned long long w[UNR][4];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const bool in = j + u < width;
+      col[u] = in ? ldv_stream_i32(cp + (j + u) * 32) : 0;
+      val[u] = in ? ldv_stream_f64x2(vp + (j + u) * 32) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (col[u] >= hb) {
+        const unsigned long long* p = ll + (size_t)(col[u] - hb) * 4;
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[u][0]), "=l"(w[u][1]) : "l"(p) : "memory");
+        asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[u][2]), "=l"(w[u][3]) : "l"(p + 2) : "memory");
+      } else {
+        xv[u] = ldv_gather_f64x2(x + col[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (col[u] >= hb) {
+        const bool ok = (unsigned int)(w[u][0] >> 32) == gen32 && (unsigned int)(w[u][1] >> 32) == gen32 &&
+                        (unsigned int)(w[u][2] >> 32) == gen32 && (unsigned int)(w[u][3] >> 32) == gen32;
+        if (ok) {
+          xv[u].x = __longlong_as_double((long long)((w[u][0] & 0xffffffffull) | (w[u][1] << 32)));
+          xv[u].y = __longlong_as_double((long long)((w[u][2] & 0xffffffffull) | (w[u][3] << 32)));
+        } else {
+          xv[u] = ld_halo_slow(ll + (size_t)(col[u] - hb) * 4, gen32, dv.st, dv.timeout_ns);
+        }
+      }
+      const double pa = val[u].x, pb = c * val[u].y;
+      ar = fma(pa, xv[u].x, ar);
+      ar = fma(-pb, xv[u].y, ar);
+      ai = fma(pa, xv[u].y, ai);
+      ai = fma(pb, xv[u].x, ai);
+    }
+  }
+  return make_double2(ar, ai);
 }
 
 // ---- variant C (default): SELL-32.  Rows are grouped in slices of 32 (after sorting by length inside
@@ -595,7 +661,8 @@ __global__ void __launch_bounds__(TPB) k_halo_push(SpmvArgs a, int check_done) {
 // (Measured on B200: 16-bit column offsets, 18 instead of 20 B per nonzero, do not make this kernel faster --
 // it sits at the practical one-pass streaming ceiling of ~5.4 TB/s for a 166 MB working set -- so plain int32
 // columns are kept.)
-template <int MODE, int SELL_UNR, int MINB>
+// PART: row-partitioned handle (separate instantiation: the whole-mesh kernel carries none of the halo code).
+template <int MODE, int SELL_UNR, int MINB, bool PART = false>
 __global__ void __launch_bounds__(TPB, MINB) k_spmv_sell(SpmvArgs a_in) {
   const SpmvArgs a = member(a_in);
   const ModeSetup m = mode_setup<MODE>(a);
@@ -604,53 +671,43 @@ __global__ void __launch_bounds__(TPB, MINB) k_spmv_sell(SpmvArgs a_in) {
   const int lane = threadIdx.x & 31;
   const int wpb = TPB / 32;
   double acc[2] = {0.0, 0.0};
-  // row-partitioned: slices below wait_slice hold rows without halo columns and start at once; the peers'
-  // halo entries of x are awaited (per warp, once) only when the first slice that may need them is reached
-  bool halo_ready = (MODE == MODE_PLAIN) || a.dist == nullptr;
-  for (int slice = blockIdx.x * wpb + (threadIdx.x >> 5); slice < a.nslice; slice += gridDim.x * wpb) {
-    if (!halo_ready) {
-      if (slice >= a.dist->wait_slice) {
-        halo_wait(a.dist);
-        halo_ready = true;
+  // Row-partitioned: slices below wait_slice hold rows without halo columns; the few slices behind it read the
+  // halo entries they need from the LL buffer (which the peers fill while the preceding update kernel and this
+  // kernel run).  Those slices go FIRST, in a loop of their own: their L2-latency-bound loads overlap the bulk
+  // instead of forming the tail, and the plain loop keeps the register allocation of the whole-mesh kernel.
+  if (a.sched) {   // static schedule: this warp's halo-reading slices, then its plain ones
+    const int w = blockIdx.x * wpb + (threadIdx.x >> 5);
+    int k = __ldg(a.sched_ptr + 2 * w);
+    const int kmid = __ldg(a.sched_ptr + 2 * w + 1), kend = __ldg(a.sched_ptr + 2 * w + 2);
+    if (PART && MODE != MODE_PLAIN && a.dist.on) {
+      const int which = MODE == MODE_V ? 1 : (MODE == MODE_T ? 2 : 0);
+      const unsigned int gen32 = (unsigned int)a.dist.st->gen[which];
+      for (; k < kmid; ++k) {
+        const int slice = __ldg(a.sched + k);
+        const int base = __ldg(a.slice_ptr + slice);
+        const int width = (__ldg(a.slice_ptr + slice + 1) - base) >> 5;
+        const int row = __ldg(a.sell_row + slice * 32 + lane);
+        const double2 y = slice_product_halo<2>(a.sell_col + base + lane, m.V + base + lane, width, m.x, m.c, a.dist,
+                                                which, gen32);
+        if (row >= 0) row_epilogue<MODE>(a, row, y, acc);
       }
     }
-    const int base = __ldg(a.slice_ptr + slice);
-    const int width = (__ldg(a.slice_ptr + slice + 1) - base) >> 5;
-    const int row = __ldg(a.sell_row + slice * 32 + lane);       // -1: padding slot past the last row
-    const int32_t* cp = a.sell_col + base + lane;
-    const double2* vp = m.V + base + lane;
-    double ar = 0.0, ai = 0.0;
-    int j = 0;
-    for (; j + SELL_UNR <= width; j += SELL_UNR) {
-      int col[SELL_UNR];
-      double2 val[SELL_UNR], xv[SELL_UNR];
-#pragma unroll
-      for (int u = 0; u < SELL_UNR; ++u) {
-        col[u] = ldv_stream_i32(cp + (j + u) * 32);
-        val[u] = ldv_stream_f64x2(vp + (j + u) * 32);
-      }
-#pragma unroll
-      for (int u = 0; u < SELL_UNR; ++u) xv[u] = ldv_gather_f64x2(m.x + col[u]);
-#pragma unroll
-      for (int u = 0; u < SELL_UNR; ++u) {
-        const double pa = val[u].x, pb = m.c * val[u].y;
-        ar = fma(pa, xv[u].x, ar);
-        ar = fma(-pb, xv[u].y, ar);
-        ai = fma(pa, xv[u].y, ai);
-        ai = fma(pb, xv[u].x, ai);
-      }
+    for (; k < kend; ++k) {
+      const int slice = __ldg(a.sched + k);
+      const int base = __ldg(a.slice_ptr + slice);
+      const int width = (__ldg(a.slice_ptr + slice + 1) - base) >> 5;
+      const int row = __ldg(a.sell_row + slice * 32 + lane);       // -1: padding slot past the last row
+      const double2 y = slice_product<SELL_UNR>(a.sell_col + base + lane, m.V + base + lane, width, m.x, m.c);
+      if (row >= 0) row_epilogue<MODE>(a, row, y, acc);
     }
-    for (; j < width; ++j) {
-      const int col = ld_stream(cp + j * 32);
-      const double2 val = ld_stream(vp + j * 32);
-      const double2 xv = ldv_gather_f64x2(m.x + col);   // not .nc: halo entries of x arrive during the kernel
-      const double pa = val.x, pb = m.c * val.y;
-      ar = fma(pa, xv.x, ar);
-      ar = fma(-pb, xv.y, ar);
-      ai = fma(pa, xv.y, ai);
-      ai = fma(pb, xv.x, ai);
+  } else {         // tuning variants with another launch shape
+    for (int slice = blockIdx.x * wpb + (threadIdx.x >> 5); slice < a.nslice; slice += gridDim.x * wpb) {
+      const int base = __ldg(a.slice_ptr + slice);
+      const int width = (__ldg(a.slice_ptr + slice + 1) - base) >> 5;
+      const int row = __ldg(a.sell_row + slice * 32 + lane);
+      const double2 y = slice_product<SELL_UNR>(a.sell_col + base + lane, m.V + base + lane, width, m.x, m.c);
+      if (row >= 0) row_epilogue<MODE>(a, row, y, acc);
     }
-    if (row >= 0) row_epilogue<MODE>(a, row, make_double2(ar, ai), acc);
   }
   mode_finalize<MODE>(a, acc);
 }
@@ -674,8 +731,9 @@ __global__ void __launch_bounds__(TPB) k_update_p(SpmvArgs a_in) {
     pp.y = rr.y - ob * vv.y + beta * pp.y;
     return pp;
   };
-  const int n = a.dist ? push_boundary_rows(a.dist, a.n, 3, p, row) : a.n;
+  const int n = a.dist.on ? push_boundary_rows(a.dist, 1, a.n, p, row) : a.n;
   for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) p[i] = row(i);
+  if (a.dist.on) bump_generation(a.dist, 1);
 }
 
 // s <- r - alpha*v
@@ -691,8 +749,9 @@ __global__ void __launch_bounds__(TPB) k_update_s(SpmvArgs a_in) {
     double2 rr = r[i], vv = v[i];
     return make_double2(rr.x - alpha * vv.x, rr.y - alpha * vv.y);
   };
-  const int n = a.dist ? push_boundary_rows(a.dist, a.n, 5, s, row) : a.n;
+  const int n = a.dist.on ? push_boundary_rows(a.dist, 2, a.n, s, row) : a.n;
   for (int i = blockIdx.x * TPB + threadIdx.x; i < n; i += gridDim.x * TPB) s[i] = row(i);
+  if (a.dist.on) bump_generation(a.dist, 2);
 }
 
 // x <- x + alpha*p + omega*s ; r <- s - omega*t ; rho' = (r,rp) ; ||r|| ; convergence test
@@ -724,7 +783,7 @@ __global__ void __launch_bounds__(TPB) k_update_xr(SpmvArgs a_in) {
     acc[0] += rr.x * q.x + rr.y * q.y;
     acc[1] += rr.x * rr.x + rr.y * rr.y;
   }
-  if (reduce_finalize<2>(acc, a.partials + 5 * BT_MAX_PARTIALS, &ctrl->ticket[TK_XR], a.dist)) {
+  if (reduce_finalize<2>(acc, a.partials + 5 * BT_MAX_PARTIALS, &ctrl->ticket[TK_XR], &a.dist)) {
     const double rho_used = ctrl->rho;
     ctrl->rho_old = rho_used;
     ctrl->rho = acc[0];
@@ -782,16 +841,18 @@ __global__ void k_flush_l2(const double2* __restrict__ p, size_t n, double* sink
 __global__ void k_periodic_ubc(int nb, const KrylovCtrl* ctrl, const double* __restrict__ Fb, double q, double gx,
                                double gy, double gz, const int32_t* __restrict__ dof, const int32_t* __restrict__ src,
                                const double* __restrict__ w, const double* __restrict__ dx,
-                               const double2* __restrict__ u, double2* __restrict__ ubc, DistDev* dist) {
-  if (dist) halo_wait(dist);   // sources may be halo entries or entries of the periodic source buffer
+                               const double2* __restrict__ u, double2* __restrict__ ubc, DistView dv) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
+  // row-partitioned: a source at or behind halo_begin is a halo dof or a mirrored source owned by a peer, both
+  // delivered through the LL buffer of u
+  const unsigned int gen32 = dv.on ? (unsigned int)dv.st->gen[0] : 0u;
   double ar = 0.0, ai = 0.0;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     int s = src[3 * b + k];
     if (s >= 0) {
-      double2 uv = u[s];
+      double2 uv = (dv.on && s >= dv.halo_begin) ? ld_halo(dv, 0, s - dv.halo_begin, gen32) : u[s];
       ar += w[3 * b + k] * uv.x;
       ai += w[3 * b + k] * uv.y;
     }
@@ -836,7 +897,7 @@ __global__ void __launch_bounds__(TPB) k_signal(SpmvArgs a_in, const double* __r
     double w = lumped[i] * u[i].x;
     if (comp[i] == 0) acc[0] += w; else acc[1] += w;
   }
-  if (reduce_finalize<2>(acc, a.partials + 6 * BT_MAX_PARTIALS, &a.ctrl->ticket[TK_SIG], a.dist)) {
+  if (reduce_finalize<2>(acc, a.partials + 6 * BT_MAX_PARTIALS, &a.ctrl->ticket[TK_SIG], &a.dist)) {
     a.sig_out[0] = acc[0];
     a.sig_out[1] = acc[1];
   }
@@ -982,10 +1043,15 @@ void launch_spmv(int lanes, SpmvArgs a, cudaStream_t st, int members = 1) {
   a.use_sell = lanes == 0 || lanes >= 100;
   if (lanes == 0) {   // SELL-32
     int g = std::max(1, std::min((a.nslice + TPB / 32 - 1) / (TPB / 32), BT_NUM_SMS * SELL_MINB_DEFAULT));
-    k_spmv_sell<MODE, SELL_UNR_DEFAULT, SELL_MINB_DEFAULT><<<dim3(g, members), TPB, 0, st>>>(a);
+    if (a.sched_grid != g) a.sched = nullptr;   // the schedule belongs to one launch shape
+    if (a.dist.on && MODE != MODE_PLAIN)
+      k_spmv_sell<MODE, SELL_UNR_DEFAULT, SELL_MINB_DEFAULT, true><<<dim3(g, members), TPB, 0, st>>>(a);
+    else
+      k_spmv_sell<MODE, SELL_UNR_DEFAULT, SELL_MINB_DEFAULT><<<dim3(g, members), TPB, 0, st>>>(a);
     return;
   }
   if (MODE == MODE_PLAIN && lanes >= 100) {   // tuning variants, bench hook only: lanes = 100*UNR/4 + MINB
+    a.sched = nullptr;
     const int nb = (a.nslice + TPB / 32 - 1) / (TPB / 32);
 #define SELL_CASE(code, unr, minb)                                                         \
   case code:                                                                               \
@@ -1017,11 +1083,14 @@ SpmvArgs base_args(btfem* h) {
   SpmvArgs a;
   memset(&a, 0, sizeof(a));
   a.n = (int)h->n_rows();
-  a.dist = h->dist_connected ? h->d_dist.p : nullptr;
+  if (h->dist_connected) a.dist = h->dview;   // memset above: dist.on == 0 otherwise
   a.rowptr = h->d_rowptr.p;
   a.colidx = h->d_colidx.p;
   a.nslice = (int)h->n_slice;
   a.slice_ptr = h->d_slice_ptr.p;
+  a.sched = getenv("BTFEM_NO_SCHED") ? nullptr : h->d_sched.p;
+  a.sched_ptr = h->d_sched_ptr.p;
+  a.sched_grid = h->sched_grid;
   a.sell_row = h->d_sell_row.p;
   a.sell_col = h->d_sell_col.p;
   a.PJs = h->d_PJs.p;
@@ -1051,7 +1120,9 @@ void ensure_vectors(btfem* h, int members = 1) {
   const size_t n = (size_t)h->ndof + (size_t)h->halo_shift;
   const size_t npad = (n + 15) & ~(size_t)15;           // keep every vector 256-byte aligned
   h->vec_npad = npad;
-  const size_t total = (size_t)members * 7 * npad + (part ? BT_COMM_ELEMS + (size_t)h->n_extra : 0);
+  // ... followed by the LL halo buffer: 3 vectors x (halo dofs + periodic sources) x 32 bytes
+  const size_t n_ll = part ? (size_t)(h->ndof - h->n_own + h->n_extra) : 0;
+  const size_t total = (size_t)members * 7 * npad + (part ? BT_COMM_ELEMS + 3 * n_ll * 2 : 0);
   if (h->d_vecs.n != total) {
     BT_REQUIRE(!h->dist_connected, "vector slab of a connected partition cannot be re-allocated");
     h->d_vecs.alloc(total);
@@ -1259,7 +1330,7 @@ void bt_spmv_host(btfem* h, double dt, double theta, double c, const double g[3]
   dy.alloc(h->ndof);
   dy.zero(st);
   SpmvArgs a = base_args(h);
-  a.dist = nullptr;
+  a.dist.on = 0;
   a.x_plain = dx.p;
   a.y_plain = dy.p;
   a.c_plain = theta * c;       // A = P + i*theta*c*Jg
@@ -1411,7 +1482,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     a.iters_out = d_iters.p;
   }
   auto capture_prologue = [&]() {
-    if (part) k_halo_push<0><<<push_grid, TPB, 0, st>>>(a, 0);
+    if (part) k_halo_push_u<<<push_grid, TPB, 0, st>>>(a);
     if (periodic) {
       k_periodic_ubc<<<((int)h->n_pb + TPB - 1) / TPB, TPB, 0, st>>>(
           (int)h->n_pb, h->d_ctrl.p, h->d_Fb.p, sa->q, sa->gdir[0], sa->gdir[1], sa->gdir[2], h->d_pb_dof.p,
@@ -1519,7 +1590,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   }
   for (int64_t step = 0; !dev_loop && step < sa->nsteps && !fail; ++step) {
     if (part) {
-      k_halo_push<0><<<push_grid, TPB, 0, st>>>(a, 0);
+      k_halo_push_u<<<push_grid, TPB, 0, st>>>(a);
       ++n_kernels;
     }
     if (periodic) {
@@ -1653,6 +1724,7 @@ void bt_dist_export(btfem* h, void* blob_out) {
   b.n_own = h->n_own;
   b.ndof = h->ndof;
   b.n_extra = h->n_extra;
+  b.halo_shift = h->halo_shift;
   BT_CUDA(cudaIpcGetMemHandle(&b.ipc, h->d_vecs.p));
   memcpy(blob_out, &b, sizeof(b));
 }
@@ -1674,21 +1746,25 @@ void bt_dist_connect(btfem* h, int rank, int world, const void* blobs, int64_t n
   BT_REQUIRE(h->d_vecs.p != nullptr, "call btfem_dist_export first");
   bt_dist_close(h);
   const DistBlob* bl = reinterpret_cast<const DistBlob*>(blobs);
-  DistDev d;
-  memset(&d, 0, sizeof(d));
-  d.rank = rank;
-  d.world = world;
-  d.n_send = (int)nsend;
-  d.n_send_u = (int)(nsend + nsend_u);
-  d.n_int = (int)h->n_int;
+  DistView v;
+  memset(&v, 0, sizeof(v));
+  v.on = 1;
+  v.rank = rank;
+  v.world = world;
+  v.n_int = (int)h->n_int;
+  v.halo_begin = (int)(h->n_own + h->halo_shift);
+  v.n_ll = (int)(h->ndof - h->n_own + h->n_extra);
   // rows are sorted by length inside windows of BT_SELL_SIGMA rows: the first window holding a row that may
-  // reference a halo column starts the waiting region
-  d.wait_slice = (int)((h->n_int / BT_SELL_SIGMA) * (BT_SELL_SIGMA / 32));
+  // reference a halo column starts the polling region
+  v.wait_slice = (int)((h->n_int / BT_SELL_SIGMA) * (BT_SELL_SIGMA / 32));
   {
     const char* e = getenv("BTFEM_COMM_TIMEOUT_MS");
     const double ms = e ? atof(e) : 10000.0;
-    d.timeout_ns = (unsigned long long)(std::max(1.0, ms) * 1e6);
+    v.timeout_ns = (unsigned long long)(std::max(1.0, ms) * 1e6);
   }
+  auto n_ll_of = [](const DistBlob& b) { return b.ndof - b.n_own + b.n_extra; };
+  PeerTab pt;
+  memset(&pt, 0, sizeof(pt));
   for (int r = 0; r < world; ++r) {
     BT_REQUIRE(bl[r].magic == 0x4254464d44495354ULL, "bad partition blob");
     void* base = nullptr;
@@ -1706,61 +1782,65 @@ void bt_dist_connect(btfem* h, int rank, int world, const void* blobs, int64_t n
       BT_CUDA(cudaIpcOpenMemHandle(&base, bl[r].ipc, cudaIpcMemLazyEnablePeerAccess));
       h->peer_map[r] = base;
     }
-    d.vecs[r] = reinterpret_cast<double2*>(base);
-    d.npad[r] = bl[r].npad;
-    d.comm[r] = reinterpret_cast<DistComm*>(reinterpret_cast<double2*>(base) + 7 * bl[r].npad);
+    double2* slab = reinterpret_cast<double2*>(base);
+    pt.comm[r] = reinterpret_cast<DistComm*>(slab + 7 * bl[r].npad);
+    pt.ll[r] = reinterpret_cast<unsigned long long*>(slab + 7 * bl[r].npad + BT_COMM_ELEMS);
+    pt.n_ll[r] = (int)n_ll_of(bl[r]);
   }
-  std::vector<char> to(world, 0);
+  v.ll = pt.ll[rank];
+  v.comm = pt.comm[rank];
+  h->d_peers.upload(&pt, 1, h->stream);
+  v.peers = h->d_peers.p;
+  // Krylov entries: the host layer names the peer's vector element (dof + the peer's halo shift); the LL entry
+  // is the halo index.  u-only entries (periodic sources) follow the peer's halo dofs in its LL buffer.
+  std::vector<int32_t> all_src, all_rank, all_slot;
   for (int64_t e = 0; e < nsend; ++e) {
-    BT_REQUIRE(src[e] >= 0 && src[e] < h->n_own, "send list: source is not an owned dof");
+    BT_REQUIRE(src[e] >= h->n_int && src[e] < h->n_own, "send list: source is not an owned dof that peers may need");
     BT_REQUIRE(dst_rank[e] >= 0 && dst_rank[e] < world && dst_rank[e] != rank, "send list: bad destination rank");
     const DistBlob& pb = bl[dst_rank[e]];
-    BT_REQUIRE(dst_slot[e] >= pb.n_own && dst_slot[e] < pb.npad, "send list: slot is not a halo element of the peer");
-    to[dst_rank[e]] = 1;
+    const int64_t k = dst_slot[e] - (pb.n_own + pb.halo_shift);
+    BT_REQUIRE(k >= 0 && k < pb.ndof - pb.n_own, "send list: slot is not a halo element of the peer");
+    all_src.push_back(src[e]);
+    all_rank.push_back(dst_rank[e]);
+    all_slot.push_back((int32_t)k);
   }
-  std::vector<int32_t> all_src(src, src + nsend), all_rank(dst_rank, dst_rank + nsend),
-      all_slot(dst_slot, dst_slot + nsend);
-  for (int64_t e = 0; e < nsend_u; ++e) {   // entries of the peers' periodic source buffers, as element indices
+  {   // the same entries grouped by boundary row (counting sort on src - n_int)
+    const int64_t nb = h->n_own - h->n_int;
+    std::vector<int32_t> ptr(nb + 1, 0), brank(nsend), bslot(nsend);
+    for (int64_t e = 0; e < nsend; ++e) ++ptr[src[e] - h->n_int + 1];
+    for (int64_t j = 0; j < nb; ++j) ptr[j + 1] += ptr[j];
+    std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+    for (int64_t e = 0; e < nsend; ++e) {
+      const int32_t pos = fill[src[e] - h->n_int]++;
+      brank[pos] = all_rank[e];
+      bslot[pos] = all_slot[e];
+    }
+    h->d_bsend_ptr.upload(ptr.data(), ptr.size(), h->stream);
+    h->d_bsend_rank.upload(brank.data(), brank.size(), h->stream);
+    h->d_bsend_slot.upload(bslot.data(), bslot.size(), h->stream);
+    v.bsend_ptr = h->d_bsend_ptr.p;
+    v.bsend_rank = h->d_bsend_rank.p;
+    v.bsend_slot = h->d_bsend_slot.p;
+  }
+  for (int64_t e = 0; e < nsend_u; ++e) {
     BT_REQUIRE(src_u[e] >= 0 && src_u[e] < h->n_own, "send list (u): source is not an owned dof");
     BT_REQUIRE(dst_rank_u[e] >= 0 && dst_rank_u[e] < world && dst_rank_u[e] != rank, "send list (u): bad rank");
     const DistBlob& pb = bl[dst_rank_u[e]];
     BT_REQUIRE(dst_index_u[e] >= 0 && dst_index_u[e] < pb.n_extra, "send list (u): index outside the peer's buffer");
     all_src.push_back(src_u[e]);
     all_rank.push_back(dst_rank_u[e]);
-    all_slot.push_back((int32_t)(7 * pb.npad + BT_COMM_ELEMS + dst_index_u[e]));
-    to[dst_rank_u[e]] = 1;
+    all_slot.push_back((int32_t)(pb.ndof - pb.n_own + dst_index_u[e]));
   }
-  for (int r = 0; r < world; ++r) {
-    if (to[r]) d.send_ranks[d.n_send_ranks++] = r;
-    if (recv_from && recv_from[r] && r != rank) d.recv_ranks[d.n_recv_ranks++] = r;
-  }
-  {   // the Krylov entries grouped by boundary row (counting sort on src - n_int)
-    const int64_t nb = h->n_own - h->n_int;
-    std::vector<int32_t> ptr(nb + 1, 0), brank(nsend), bslot(nsend);
-    for (int64_t e = 0; e < nsend; ++e) {
-      BT_REQUIRE(src[e] >= h->n_int, "send list: an interior dof cannot be needed by a peer");
-      ++ptr[src[e] - h->n_int + 1];
-    }
-    for (int64_t j = 0; j < nb; ++j) ptr[j + 1] += ptr[j];
-    std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
-    for (int64_t e = 0; e < nsend; ++e) {
-      const int32_t pos = fill[src[e] - h->n_int]++;
-      brank[pos] = dst_rank[e];
-      bslot[pos] = dst_slot[e];
-    }
-    h->d_bsend_ptr.upload(ptr.data(), ptr.size(), h->stream);
-    h->d_bsend_rank.upload(brank.data(), brank.size(), h->stream);
-    h->d_bsend_slot.upload(bslot.data(), bslot.size(), h->stream);
-    d.bsend_ptr = h->d_bsend_ptr.p;
-    d.bsend_rank = h->d_bsend_rank.p;
-    d.bsend_slot = h->d_bsend_slot.p;
-  }
+  (void)recv_from;   // LL entries carry their own sequence numbers: nobody waits on a per-peer flag
+  v.n_send_u = (int)all_src.size();
   h->d_send_src.upload(all_src.data(), all_src.size(), h->stream);
   h->d_send_rank.upload(all_rank.data(), all_rank.size(), h->stream);
   h->d_send_slot.upload(all_slot.data(), all_slot.size(), h->stream);
-  d.send_src = h->d_send_src.p;
-  d.send_rank = h->d_send_rank.p;
-  d.send_slot = h->d_send_slot.p;
+  v.send_src = h->d_send_src.p;
+  v.send_rank = h->d_send_rank.p;
+  v.send_slot = h->d_send_slot.p;
+  DistDev d;
+  memset(&d, 0, sizeof(d));
   if (h->trace_cap > 0) {
     h->d_trace.alloc(8 * (size_t)h->trace_cap);
     h->d_trace.zero(h->stream);
@@ -1769,6 +1849,8 @@ void bt_dist_connect(btfem* h, int rank, int world, const void* blobs, int64_t n
   }
   h->d_dist.upload(&d, 1, h->stream);
   BT_CUDA(cudaStreamSynchronize(h->stream));
+  v.st = h->d_dist.p;
+  h->dview = v;
   h->rank = rank;
   h->world = world;
   h->dist_connected = true;
