@@ -639,6 +639,7 @@ void bt_build_pattern(btfem* h) {
   // the order of the dot-product partial sums depend on timing.  So the queue is SIMULATED here, once: slices are
   // dealt in order -- halo-reading ones first, then ascending, which keeps all warps on neighbouring slices at any
   // time -- each to the warp with the least estimated work so far.  Deterministic, and part of the handle.
+  // ptr[2w] .. ptr[2w+2] is warp w's list (ptr[2w+1] = ptr[2w]: kept for the layout of the kernel argument).
   {
     const int wpb = 256 / 32;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nslice + wpb - 1) / wpb, BT_NUM_SMS * 3));
@@ -649,7 +650,13 @@ void bt_build_pattern(btfem* h) {
     std::vector<int32_t> nhalo(nw, 0);
     typedef std::pair<double, int> Load;   // (estimated work, warp): min-heap, ties -> lowest warp id
     std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
-    for (int w = 0; w < nw; ++w) heap.push(Load(0.0, w));
+    // halo-reading slices are not in the lists: block b takes slices first_halo + b, + grid, ... cooperatively
+    // (solve.cu), which every warp of that block pays for before it starts on its list
+    for (int w = 0; w < nw; ++w) {
+      const int64_t b = w / wpb, nh = nslice - first_halo;
+      const int64_t mine = nh > b ? (nh - b + grid - 1) / grid : 0;
+      heap.push(Load(9.0 * (double)mine, w));
+    }
     auto deal = [&](int64_t s, double factor) {
       Load l = heap.top();
       heap.pop();
@@ -658,7 +665,6 @@ void bt_build_pattern(btfem* h) {
       heap.push(Load(l.first + 3.0 + factor * width, l.second));
       return l.second;
     };
-    for (int64_t s = first_halo; s < nslice; ++s) ++nhalo[deal(s, 2.5)];
     for (int64_t s = 0; s < first_halo; ++s) deal(s, 1.0);
     std::vector<int32_t> sched, ptr(2 * nw + 1, 0);
     sched.reserve(nslice);

@@ -254,7 +254,8 @@ struct SpmvArgs {
   int n;
   int nslice;                // SELL-32: number of 32-row slices
   const int32_t* slice_ptr;  // [nslice+1] offset of each slice in the SELL arrays (multiple of 32)
-  const int32_t* sched;      // static warp schedule (setup.cu), or null: round-robin
+  const int32_t* sched;      // static warp schedule (setup.cu); may be empty (null) when every slice reads halos
+  int sched_on;              // 0: round-robin over the launch (tuning variants with another launch shape)
   const int32_t* sched_ptr;
   int sched_grid;
   const int32_t* sell_row;   // [nslice*32] row owned by each slot (-1 = padding)
@@ -602,22 +603,26 @@ __device__ __forceinline__ double2 slice_product(const int32_t* cp, const double
 // The same for a slice whose rows may reference halo dofs (columns >= halo_begin): those values are LL words in
 // this rank's halo buffer.  Both 16-byte loads of every entry of a batch are issued before any is examined (a
 // system-scope load is an L2 round trip; issued one after the other they would dominate the slice), and only an
-// entry that has not arrived yet falls back to the bounded poll.  Same summation order as the plain loop.
+// entry that has not arrived yet falls back to the bounded poll.
+// The columns of the slice are split over the warps of the block: this warp takes j0, j0 + jstride, ... (UNR of
+// them per batch), so the dependent chain of a slice is two L2 round trips instead of two per column group.
 template <int UNR>
 __device__ __forceinline__ double2 slice_product_halo(const int32_t* cp, const double2* vp, int width, const double2* x,
-                                                      double c, const DistView& dv, int which, unsigned int gen32) {
+                                                      double c, const DistView& dv, int which, unsigned int gen32,
+                                                      int j0, int jstride) {
   const unsigned long long* ll = dv.ll + (size_t)which * dv.n_ll * 4;
   const int hb = dv.halo_begin;
   double ar = 0.0, ai = 0.0;
-  for (int j = 0; j < width; j += UNR) {
+  for (int j = j0; j < width; j += UNR * jstride) {
     int col[UNR];
     double2 val[UNR], xv[UNR];
     unsigned long long w[UNR][4];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      const bool in = j + u < width;
-      col[u] = in ? ldv_stream_i32(cp + (j + u) * 32) : 0;
-      val[u] = in ? ldv_stream_f64x2(vp + (j + u) * 32) : make_double2(0.0, 0.0);
+      const int ju = j + u * jstride;
+      const bool in = ju < width;
+      col[u] = in ? ldv_stream_i32(cp + ju * 32) : 0;
+      val[u] = in ? ldv_stream_f64x2(vp + ju * 32) : make_double2(0.0, 0.0);
     }
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
@@ -675,21 +680,33 @@ __global__ void __launch_bounds__(TPB, MINB) k_spmv_sell(SpmvArgs a_in) {
   // halo entries they need from the LL buffer (which the peers fill while the preceding update kernel and this
   // kernel run).  Those slices go FIRST, in a loop of their own: their L2-latency-bound loads overlap the bulk
   // instead of forming the tail, and the plain loop keeps the register allocation of the whole-mesh kernel.
-  if (a.sched) {   // static schedule: this warp's halo-reading slices, then its plain ones
+  if (a.sched_on) {   // static schedule
     const int w = blockIdx.x * wpb + (threadIdx.x >> 5);
     int k = __ldg(a.sched_ptr + 2 * w);
-    const int kmid = __ldg(a.sched_ptr + 2 * w + 1), kend = __ldg(a.sched_ptr + 2 * w + 2);
+    const int kend = __ldg(a.sched_ptr + 2 * w + 2);
     if (PART && MODE != MODE_PLAIN && a.dist.on) {
+      // Halo-reading slices: taken block by block, FIRST (their loads overlap the bulk instead of forming the
+      // tail), the 8 warps of the block splitting the columns of one slice; the per-warp partial rows meet in
+      // shared memory and are added in warp order (fixed order -> reproducible).
+      __shared__ double2 s_part[TPB / 32][32];
       const int which = MODE == MODE_V ? 1 : (MODE == MODE_T ? 2 : 0);
       const unsigned int gen32 = (unsigned int)a.dist.st->gen[which];
-      for (; k < kmid; ++k) {
-        const int slice = __ldg(a.sched + k);
+      const int first = min(a.dist.wait_slice, a.nslice);
+      const int wl = threadIdx.x >> 5;
+      for (int slice = first + blockIdx.x; slice < a.nslice; slice += gridDim.x) {
         const int base = __ldg(a.slice_ptr + slice);
         const int width = (__ldg(a.slice_ptr + slice + 1) - base) >> 5;
-        const int row = __ldg(a.sell_row + slice * 32 + lane);
-        const double2 y = slice_product_halo<2>(a.sell_col + base + lane, m.V + base + lane, width, m.x, m.c, a.dist,
-                                                which, gen32);
-        if (row >= 0) row_epilogue<MODE>(a, row, y, acc);
+        s_part[wl][lane] = slice_product_halo<2>(a.sell_col + base + lane, m.V + base + lane, width, m.x, m.c, a.dist,
+                                                 which, gen32, wl, wpb);
+        __syncthreads();
+        if (wl == 0) {
+          double2 y = s_part[0][lane];
+#pragma unroll
+          for (int q = 1; q < TPB / 32; ++q) { y.x += s_part[q][lane].x; y.y += s_part[q][lane].y; }
+          const int row = __ldg(a.sell_row + slice * 32 + lane);
+          if (row >= 0) row_epilogue<MODE>(a, row, y, acc);
+        }
+        __syncthreads();
       }
     }
     for (; k < kend; ++k) {
@@ -1043,7 +1060,9 @@ void launch_spmv(int lanes, SpmvArgs a, cudaStream_t st, int members = 1) {
   a.use_sell = lanes == 0 || lanes >= 100;
   if (lanes == 0) {   // SELL-32
     int g = std::max(1, std::min((a.nslice + TPB / 32 - 1) / (TPB / 32), BT_NUM_SMS * SELL_MINB_DEFAULT));
-    if (a.sched_grid != g) a.sched = nullptr;   // the schedule belongs to one launch shape
+    if (a.sched_grid != g) a.sched_on = 0;   // the schedule belongs to one launch shape
+    if (a.dist.on && MODE != MODE_PLAIN && !a.sched_on)
+      throw BtError{BTFEM_EINVAL, "row-partitioned SpMV needs the static schedule of its launch shape"};
     if (a.dist.on && MODE != MODE_PLAIN)
       k_spmv_sell<MODE, SELL_UNR_DEFAULT, SELL_MINB_DEFAULT, true><<<dim3(g, members), TPB, 0, st>>>(a);
     else
@@ -1051,7 +1070,7 @@ void launch_spmv(int lanes, SpmvArgs a, cudaStream_t st, int members = 1) {
     return;
   }
   if (MODE == MODE_PLAIN && lanes >= 100) {   // tuning variants, bench hook only: lanes = 100*UNR/4 + MINB
-    a.sched = nullptr;
+    a.sched_on = 0;
     const int nb = (a.nslice + TPB / 32 - 1) / (TPB / 32);
 #define SELL_CASE(code, unr, minb)                                                         \
   case code:                                                                               \
@@ -1088,7 +1107,8 @@ SpmvArgs base_args(btfem* h) {
   a.colidx = h->d_colidx.p;
   a.nslice = (int)h->n_slice;
   a.slice_ptr = h->d_slice_ptr.p;
-  a.sched = getenv("BTFEM_NO_SCHED") ? nullptr : h->d_sched.p;
+  a.sched = h->d_sched.p;
+  a.sched_on = (getenv("BTFEM_NO_SCHED") && h->nv_own < 0) ? 0 : 1;
   a.sched_ptr = h->d_sched_ptr.p;
   a.sched_grid = h->sched_grid;
   a.sell_row = h->d_sell_row.p;
@@ -1331,6 +1351,7 @@ void bt_spmv_host(btfem* h, double dt, double theta, double c, const double g[3]
   dy.zero(st);
   SpmvArgs a = base_args(h);
   a.dist.on = 0;
+  if (h->nv_own >= 0) a.sched_on = 0;   // the schedule of a partition leaves the halo-reading slices to the LL path
   a.x_plain = dx.p;
   a.y_plain = dy.p;
   a.c_plain = theta * c;       // A = P + i*theta*c*Jg
