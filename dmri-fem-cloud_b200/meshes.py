@@ -263,6 +263,16 @@ def shuffle_vertices(xyz, tets, seed=0):
     return xyz[perm].copy(), inv[tets].astype(np.int32)
 
 
+def coordinate_order(xyz, tets, axes=(1, 2, 0), decimals=9):
+    """Renumber vertices lexicographically by coordinates, axes[0] slowest: contiguous vertex blocks are then slabs
+    normal to axes[0] (what the row partition over GPUs wants for slab-like domains such as the ECS)."""
+    key = np.round(xyz, decimals)
+    perm = np.lexsort(tuple(key[:, a] for a in reversed(axes)))
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(perm))
+    return xyz[perm].copy(), inv[tets].astype(np.int32)
+
+
 def rcm_order(xyz, tets):
     """Reverse Cuthill-McKee vertex renumbering for gather locality in the SpMV."""
     import scipy.sparse as sp

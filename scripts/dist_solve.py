@@ -40,11 +40,17 @@ def main():
     from dmri_fem_cloud_b200 import btfem, meshes, partition
     comm = partition.TorchComm(dist)
 
+    Fb = pdir = None
     if args.ecs:
+        # configs[3]: extracellular space of 226 cylinders, weak pseudo-periodic BC in x and y, g = (1,1,0)/sqrt2
         xyz, tets, phase = meshes.ecs_slab(args.ecs, args.ecs, 2)
+        xyz, tets = meshes.coordinate_order(xyz, tets, axes=(1, 2, 0))       # vertex blocks = slabs normal to y
         mp, ts, f, fp = bench.sequence(delta=10000.0, Delta=13000.0, k=200.0, b=args.bvalue)
+        tps = np.concatenate([[0.0], ts[:-1]])
+        _, Fb = mp.profiles_on_grid(tps)
         g = np.array([1.0, 1.0, 0.0]) / np.sqrt(2.0)
-        D, kappa, name = 2e-3, 1e-5, "ECS slab %dx%dx2 (configs[3] geometry, Neumann)" % (args.ecs, args.ecs)
+        pdir = [1, 1, 0]
+        D, kappa, name = 2e-3, 1e-5, "configs[3] ECS slab %dx%dx2, 226 cylinders, weak periodic x,y" % (args.ecs, args.ecs)
     else:
         xyz, tets, phase = bench.workload(args.nbox)
         mp, ts, f, fp = bench.sequence(k=200.0, b=args.bvalue)
@@ -52,12 +58,18 @@ def main():
         D, kappa, name = 3e-3, 1e-5, "configs[1] cell-in-box n_box=%d" % args.nbox
     k, q = 200.0, mp.qvalue
     kw = dict(rtol=1e-9, atol=1e-10, maxit=100000)
+    if pdir is not None:
+        kw.update(q=q, Fb=Fb)
+        lo, hi = xyz.min(axis=0), xyz.max(axis=0)
 
     t0 = time.perf_counter()
     d = partition.DistBTFem(xyz, tets, comm, device=local_rank, phase=phase)
     d.set_diffusion(D)
     d.set_relaxation(1e-16)
     d.set_permeability(kappa)
+    if pdir is not None:
+        hmin, _ = d.mesh_stats()
+        d.set_periodic(pdir, 3e-3 / hmin, 1e-2 * hmin, lo, hi)        # kappa_e, tol as MyDomain sets them
     if args.trace:
         d.fem.dist_trace(args.trace)
     d.assemble()
@@ -94,7 +106,14 @@ def main():
             fem.set_diffusion(D)
             fem.set_relaxation(1e-16)
             fem.set_permeability(kappa)
+            if pdir is not None:
+                fem.set_periodic(pdir, 3e-3 / hmin, 1e-2 * hmin, lo, hi)
             fem.assemble()
+            if pdir is not None:
+                from dmri_fem_cloud_b200 import periodic
+                dv, dc = fem.dofmap()
+                fem.set_periodic_gather(*periodic.build_gather(xyz, tets, phase, pdir, lo, hi, dv, dc,
+                                                               bfacets=fem.boundary_facets()))
             fem.solve(k, 0.5, q * f, q * fp, g, **kw)
             ref = fem.solve(k, 0.5, q * f, q * fp, g, **kw)
         out["single_gpu_loop_s"] = (ref["loop_ms"] + ref["setup_ms"]) * 1e-3
