@@ -1,7 +1,7 @@
 """Direction x b-value sweeps (HARDI): the reference just loops serially over b-values / directions
 (ExplicitImplementation.ipynb cell 10, Manifolds.ipynb cell 10).  Every (direction, b) solve is
-independent, so the units shard round-robin over ranks (one process per GPU) with no data-path
-collective; the only exchange is the final gather of the signals."""
+independent, so the units shard over ranks (one process per GPU: directions round-robin, all b-values of a
+direction on the same rank) with no data-path collective; the only exchange is the final gather of the signals."""
 import numpy as np
 
 
@@ -15,12 +15,20 @@ def shard_units(n_units, rank, world):
     return list(range(rank, n_units, world))
 
 
+def shard_balanced(n_dir, n_b, rank, world):
+    """This rank's units for a lock-step batched sweep: directions round-robin over ranks, every rank taking ALL
+    b-values of its directions (the iteration count of a solve grows with b, so every rank gets the same mix),
+    listed b-major so that consecutive batch members share a b-value and finish their time steps together.
+    Unit ids stay direction-major (i * n_b + j), like sweep_units."""
+    return [i * n_b + j for j in range(n_b) for i in range(rank, n_dir, world)]
+
+
 def run_sweep(fem, mri_para, sim, directions, bvalues, linsolver_params, rank=0, world=1, batch=1):
     """Solve this rank's share.  Returns (unit ids, normalized signals).  `fem` is an assembled
     btfem.BTFem, `mri_para` a dmrifemlib.MRI_parameters with fs_sym/T set (Apply() is re-run per b).
     batch > 1: that many units advance in lock step per kernel launch (btfem_solve_batch)."""
     units = sweep_units(directions, bvalues)
-    mine = shard_units(len(units), rank, world)
+    mine = shard_balanced(len(directions), len(bvalues), rank, world)
     ts = sim.time_grid(mri_para)
     tps = np.concatenate([[0.0], ts[:-1]])
     out = []
