@@ -232,6 +232,10 @@ struct btfem {
   DevArray<int32_t> d_sell_slot;   // [ndof] row -> slot
   DevArray<int32_t> d_sell_col;    // [nnz_sell]
   DevArray<double2> d_PJs, d_QJs;  // [nnz_sell] per-solve operator values in SELL order
+  // batched solves (btfem_solve_batch): ONE direction-independent copy of the operator serves all members --
+  // (P_k, Q_k)/P_rr, (Jx_k, Jy_k), Jz_k in SELL order; J_g is formed per member inside the SpMV
+  DevArray<double2> d_PQs, d_Jxys;
+  DevArray<double> d_Jzs, d_gdirs /*[members*3]*/;
   DevArray<uint32_t> d_src;        // contribution ids sorted by (row,col), stable
   DevArray<int64_t> d_seg;         // [nnz+1] segment offsets into d_src
   DevArray<double> d_vals[8];      // M,S,R,Jx,Jy,Jz,I,B

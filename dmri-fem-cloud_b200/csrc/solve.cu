@@ -219,6 +219,19 @@ __global__ void k_pdiag(int n, const int32_t* __restrict__ diagpos, const double
   dinv[r] = pc == BTFEM_PC_JACOBI ? 1.0 / p : 1.0;
 }
 
+// One operator entry, with the rounding pinned by intrinsics: the per-direction combine (k_combine) and the
+// shared-operator batch path (k_combine_shared + k_spmv_sell_batch, which forms J_g per member on the fly) must
+// produce the same bits, whatever the compiler would contract.
+__device__ __forceinline__ double comb_p(double mk, double k0, double b, double theta, double di) {
+  return __dmul_rn(__fma_rn(theta, __dadd_rn(k0, b), mk), di);
+}
+__device__ __forceinline__ double comb_q(double mk, double k0, double one_minus_theta, double di) {
+  return __dmul_rn(__fma_rn(-one_minus_theta, k0, mk), di);
+}
+__device__ __forceinline__ double comb_jg(double gx, double gy, double gz, double jx, double jy, double jz, double di) {
+  return __dmul_rn(__fma_rn(gz, jz, __fma_rn(gy, jy, __dmul_rn(gx, jx))), di);
+}
+
 __global__ void k_combine(int64_t nnz, const int32_t* __restrict__ rowidx, const double* __restrict__ M,
                           const double* __restrict__ S, const double* __restrict__ R, const double* __restrict__ I,
                           const double* __restrict__ B, const double* __restrict__ Jx, const double* __restrict__ Jy,
@@ -232,9 +245,9 @@ __global__ void k_combine(int64_t nnz, const int32_t* __restrict__ rowidx, const
   double di = dinv[rowidx[k]];
   double mk = M[k] * inv_dt;
   double k0 = S[k] + R[k] + I[k];
-  double jg = (gx * Jx[k] + gy * Jy[k] + gz * Jz[k]) * di;
-  const double2 pj = make_double2((mk + theta * (k0 + B[k])) * di, jg);
-  const double2 qj = make_double2((mk - (1.0 - theta) * k0) * di, jg);
+  double jg = comb_jg(gx, gy, gz, Jx[k], Jy[k], Jz[k], di);
+  const double2 pj = make_double2(comb_p(mk, k0, B[k], theta, di), jg);
+  const double2 qj = make_double2(comb_q(mk, k0, 1.0 - theta, di), jg);
   PJ[k] = pj;
   QJ[k] = qj;
   if (Bhat) Bhat[k] = B[k] * di;
@@ -246,6 +259,29 @@ __global__ void k_combine(int64_t nnz, const int32_t* __restrict__ rowidx, const
     PJs[pos] = pj;
     QJs[pos] = qj;
   }
+}
+
+// Direction-independent operator of a batch, SELL order only (padding entries stay zero).
+__global__ void k_combine_shared(int64_t nnz, const int32_t* __restrict__ rowidx, const double* __restrict__ M,
+                                 const double* __restrict__ S, const double* __restrict__ R,
+                                 const double* __restrict__ I, const double* __restrict__ B,
+                                 const double* __restrict__ Jx, const double* __restrict__ Jy,
+                                 const double* __restrict__ Jz, double inv_dt, double theta,
+                                 const double* __restrict__ dinv, const int32_t* __restrict__ rowptr,
+                                 const int32_t* __restrict__ sell_slot, const int32_t* __restrict__ slice_ptr,
+                                 double2* __restrict__ PQs, double2* __restrict__ Jxys, double* __restrict__ Jzs) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  const int row = rowidx[k];
+  const int slot = sell_slot[row];
+  if (slot < 0) return;
+  const double di = dinv[row];
+  const double mk = M[k] * inv_dt;
+  const double k0 = S[k] + R[k] + I[k];
+  const int pos = slice_ptr[slot >> 5] + (int)(k - rowptr[row]) * 32 + (slot & 31);
+  PQs[pos] = make_double2(comb_p(mk, k0, B[k], theta, di), comb_q(mk, k0, 1.0 - theta, di));
+  Jxys[pos] = make_double2(Jx[k], Jy[k]);
+  Jzs[pos] = Jz[k];
 }
 
 // ------------------------------------------------------------------------------------ fused SpMV
@@ -281,6 +317,13 @@ struct SpmvArgs {
   // batch of independent solves on the same mesh (gridDim.y members; HARDI direction x b sweeps): element
   // strides between consecutive members.  The pattern arrays are shared.
   size_t mat_stride_csr, mat_stride_sell, vec_stride, part_stride, step_stride;
+  int members;               // batch size (0/1: single solve)
+  // shared-operator batch kernel (k_spmv_sell_batch): direction-independent SELL arrays + per-member directions
+  const double2* PQs;        // (P_k, Q_k) / P_rr
+  const double2* Jxys;       // (Jx_k, Jy_k), unscaled
+  const double* Jzs;
+  const double* dinv;        // 1 / P_rr per row
+  const double* gdirs;       // [members][3]
   double* sig_out;           // k_signal: [members][2]
   DistView dist;             // row-partitioned solve: peers, LL buffers, send lists (dist.on == 0: whole mesh)
   // device-driven loop: the BiCGStab iteration is the body of a graph WHILE node whose condition the kernels set
@@ -301,16 +344,15 @@ __device__ __forceinline__ void comm_check(const SpmvArgs& a) {
 // leave a stale 1 behind, which costs one empty pass: k_update_xr calls this again on its skip path.
 __device__ __forceinline__ void loop_condition(const SpmvArgs& a) {
   if (!a.use_cond) return;
-  const unsigned int members = gridDim.y;
+  const unsigned int members = a.members > 0 ? (unsigned int)a.members : gridDim.y;   // gridDim.y counts member GROUPS in the shared-operator batch kernel
   if (members > 1) __threadfence();
   unsigned int any = 0;
   for (unsigned int b = 0; b < members; ++b) any |= (((volatile KrylovCtrl*)a.ctrl0)[b].done == 0);
   cudaGraphSetConditional(a.cond, any);
 }
 
-// arguments of batch member blockIdx.y
-__device__ __forceinline__ SpmvArgs member(SpmvArgs a) {
-  const size_t b = blockIdx.y;
+// arguments of batch member b
+__device__ __forceinline__ SpmvArgs member_at(SpmvArgs a, size_t b) {
   if (b == 0) return a;
   a.PJ += b * a.mat_stride_csr;
   a.QJ += b * a.mat_stride_csr;
@@ -325,6 +367,8 @@ __device__ __forceinline__ SpmvArgs member(SpmvArgs a) {
   if (a.sig_out) a.sig_out += 2 * b;
   return a;
 }
+// arguments of batch member blockIdx.y
+__device__ __forceinline__ SpmvArgs member(const SpmvArgs& a) { return member_at(a, blockIdx.y); }
 
 // streaming loads for the matrix (read once per SpMV; keeps the Krylov vectors in the 126 MB L2)
 __device__ __forceinline__ int ld_stream(const int32_t* p) { return __ldcs(p); }
@@ -729,6 +773,123 @@ __global__ void __launch_bounds__(TPB, MINB) k_spmv_sell(SpmvArgs a_in) {
   mode_finalize<MODE>(a, acc);
 }
 
+
+// ---- batched solves: the shared-operator SELL kernel.  The members of a batch (HARDI: directions x b-values on
+// one mesh) differ in the direction g and the scalar c only, so the matrix is read ONCE per slice for BM members:
+// (column, P|Q, Jx, Jy, Jz) = 44 bytes per nonzero for the whole group instead of 20 bytes per member, and it
+// stays in L2 from one SpMV to the next (31 MB at 46 k vertices, whatever the batch size).  Per member the
+// kernel forms J_g,k = (g.J_k)/P_rr with the rounding of k_combine and gathers x_m[col]; the row sums run in
+// ascending column order and the dot-product partials follow the static schedule of the single-solve kernel,
+// so every member gets the bits of its one-at-a-time solve.  Block = (slices of the schedule, member group).
+template <int MODE, int BM>
+__global__ void __launch_bounds__(TPB, 2) k_spmv_sell_batch(SpmvArgs a) {
+  __shared__ double s_g[BM][4];       // gx, gy, gz, c of the group's members
+  __shared__ unsigned int s_mask;     // members that still work
+  const int m0 = blockIdx.y * BM;
+  const int lane = threadIdx.x & 31;
+  const int wpb = TPB / 32;
+  if (threadIdx.x < 32) {
+    bool act = false;
+    if (lane < BM && m0 + lane < a.members) {
+      const int m = m0 + lane;
+      const KrylovCtrl* ctrl = a.ctrl + m;
+      double c;
+      if (MODE == MODE_RHS) {
+        act = ctrl->failed == 0;
+        c = ctrl->theta_cb_scale * a.cb[(size_t)m * a.step_stride + ctrl->step_next];
+      } else {
+        act = ctrl->done == 0;
+        c = ctrl->theta_cA_scale * a.cA[(size_t)m * a.step_stride + ctrl->step];
+      }
+      s_g[lane][0] = a.gdirs[3 * m];
+      s_g[lane][1] = a.gdirs[3 * m + 1];
+      s_g[lane][2] = a.gdirs[3 * m + 2];
+      s_g[lane][3] = c;
+    }
+    const unsigned int mask = __ballot_sync(0xffffffffu, act);
+    if (lane == 0) s_mask = mask;
+  }
+  __syncthreads();
+  const unsigned int mask = s_mask;
+  if (mask == 0) return;
+  const double2* __restrict__ x0 =
+      (MODE == MODE_RHS || MODE == MODE_RESID) ? a.u : (MODE == MODE_V ? a.p : a.s);
+  x0 += (size_t)m0 * a.vec_stride;
+  // per-thread dot-product partials of the BM members live in shared memory (registers go to the row sums)
+  __shared__ double s_acc[BM][2][TPB];
+#pragma unroll
+  for (int m = 0; m < BM; ++m) s_acc[m][0][threadIdx.x] = s_acc[m][1][threadIdx.x] = 0.0;
+  const int w = blockIdx.x * wpb + (threadIdx.x >> 5);
+  const int kend = __ldg(a.sched_ptr + 2 * w + 2);
+  for (int k = __ldg(a.sched_ptr + 2 * w); k < kend; ++k) {
+    const int slice = __ldg(a.sched + k);
+    const int base = __ldg(a.slice_ptr + slice);
+    const int width = (__ldg(a.slice_ptr + slice + 1) - base) >> 5;
+    const int row = __ldg(a.sell_row + slice * 32 + lane);       // -1: padding slot past the last row
+    const double di = row >= 0 ? __ldg(a.dinv + row) : 0.0;
+    const int32_t* cp = a.sell_col + base + lane;
+    const double2* pq = a.PQs + base + lane;
+    const double2* jxy = a.Jxys + base + lane;
+    const double* jz = a.Jzs + base + lane;
+    double yr[BM], yi[BM];
+#pragma unroll
+    for (int m = 0; m < BM; ++m) yr[m] = yi[m] = 0.0;
+    // software pipeline: the matrix entry of column j+1 is in flight while the BM gathers of column j are
+    int col_n = 0;
+    double2 pq_n = make_double2(0.0, 0.0), jv_n = pq_n;
+    double jz_n = 0.0;
+    if (width > 0) { col_n = __ldg(cp); pq_n = __ldg(pq); jv_n = __ldg(jxy); jz_n = __ldg(jz); }
+#pragma unroll 1
+    for (int j = 0; j < width; ++j) {
+      const int col = col_n;
+      const double2 pqv = pq_n, jv = jv_n;
+      const double jzv = jz_n;
+      if (j + 1 < width) {
+        col_n = __ldg(cp + (j + 1) * 32);
+        pq_n = __ldg(pq + (j + 1) * 32);
+        jv_n = __ldg(jxy + (j + 1) * 32);
+        jz_n = __ldg(jz + (j + 1) * 32);
+      }
+      const double pa = MODE == MODE_RHS ? pqv.y : pqv.x;
+      const double2* xc = x0 + col;
+#pragma unroll
+      for (int h0 = 0; h0 < BM; h0 += 4) {     // four gathers in flight at a time
+        double2 xv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (mask >> (h0 + q) & 1u) xv[q] = ldv_gather_f64x2(xc + (size_t)(h0 + q) * a.vec_stride);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int m = h0 + q;
+          if (mask >> m & 1u) {
+            const double pb = s_g[m][3] * comb_jg(s_g[m][0], s_g[m][1], s_g[m][2], jv.x, jv.y, jzv, di);
+            yr[m] = fma(pa, xv[q].x, yr[m]);
+            yr[m] = fma(-pb, xv[q].y, yr[m]);
+            yi[m] = fma(pa, xv[q].y, yi[m]);
+            yi[m] = fma(pb, xv[q].x, yi[m]);
+          }
+        }
+      }
+    }
+    if (row >= 0) {
+#pragma unroll
+      for (int m = 0; m < BM; ++m)
+        if (mask >> m & 1u) {
+          double t[2] = {s_acc[m][0][threadIdx.x], s_acc[m][1][threadIdx.x]};
+          row_epilogue<MODE>(member_at(a, m0 + m), row, make_double2(yr[m], yi[m]), t);
+          s_acc[m][0][threadIdx.x] = t[0];
+          s_acc[m][1][threadIdx.x] = t[1];
+        }
+    }
+  }
+#pragma unroll 1
+  for (int m = 0; m < BM; ++m)
+    if (mask >> m & 1u) {   // block-uniform: mask is shared
+      double t[2] = {s_acc[m][0][threadIdx.x], s_acc[m][1][threadIdx.x]};
+      mode_finalize<MODE>(member_at(a, m0 + m), t);
+    }
+}
+
 // ------------------------------------------------------------------------------------ vector kernels
 
 // p <- r - omega*beta*v + beta*p        (VecAXPBYPCZ in KSPSolve_BCGS)
@@ -1052,12 +1213,33 @@ inline int spmv_grid(int n, int lanes) {
   return std::max(1, std::min((n + rpb - 1) / rpb, BT_NUM_SMS * 16));
 }
 
+// members per block of the shared-operator batch kernel (BTFEM_BATCH_GROUP=4|8)
+inline int batch_group() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BTFEM_BATCH_GROUP");
+    v = (e && atoi(e) == 4) ? 4 : 8;
+  }
+  return v;
+}
+
 constexpr int SELL_UNR_DEFAULT = 4;
 constexpr int SELL_MINB_DEFAULT = 3;
 
 template <int MODE>
 void launch_spmv(int lanes, SpmvArgs a, cudaStream_t st, int members = 1) {
   a.use_sell = lanes == 0 || lanes >= 100;
+  a.members = members;
+  if constexpr (MODE != MODE_PLAIN) if (lanes == 0 && a.PQs) {   // batch on the shared operator: (schedule blocks, member groups)
+    const int g = std::max(1, std::min((a.nslice + TPB / 32 - 1) / (TPB / 32), BT_NUM_SMS * SELL_MINB_DEFAULT));
+    if (a.sched_grid != g || !a.sched_on)
+      throw BtError{BTFEM_EINVAL, "batched SpMV needs the static schedule of its launch shape"};
+    if (batch_group() == 4)
+      k_spmv_sell_batch<MODE, 4><<<dim3(g, (members + 3) / 4), TPB, 0, st>>>(a);
+    else
+      k_spmv_sell_batch<MODE, 8><<<dim3(g, (members + 7) / 8), TPB, 0, st>>>(a);
+    return;
+  }
   if (lanes == 0) {   // SELL-32
     int g = std::max(1, std::min((a.nslice + TPB / 32 - 1) / (TPB / 32), BT_NUM_SMS * SELL_MINB_DEFAULT));
     if (a.sched_grid != g) a.sched_on = 0;   // the schedule belongs to one launch shape
@@ -1446,7 +1628,42 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   BT_CUDA(cudaEventCreate(&e1));
   BT_CUDA(cudaEventCreate(&e2));
   BT_CUDA(cudaEventRecord(e0, st));
-  for (int b = 0; b < members; ++b) bt_combine(h, sa->dt, sa->theta, sav[b].gdir, (int)sa->pc, b, members);
+  // Batch layouts.  Default: one pre-combined copy of the operator per member, member = blockIdx.y of the
+  // single-solve kernel (members x more warps in flight).  BTFEM_BATCH_SHARED=1: one direction-independent
+  // operator for all members (k_spmv_sell_batch) -- 44 B per nonzero per GROUP instead of 20 B per member, same
+  // bits; measured on B200 on the 46 k-vertex HARDI mesh it is SLOWER (15.4 / 19.0 signals/s with groups of
+  // 8 / 4 against 24.0): that regime is bound by gather latency and by L2 traffic of the gathers and vectors,
+  // which the shared matrix does not reduce, and the group kernel has 8x fewer warps to hide latency with
+  // (profiles/r1e_batch_layouts.txt).  Kept for meshes whose per-member copies would not fit in memory.
+  const char* shared_env = getenv("BTFEM_BATCH_SHARED");
+  const bool shared_ops = members > 1 && h->lanes == 0 && h->n_slice > 0 && shared_env && shared_env[0] == '1';
+  if (shared_ops) {
+    const int nd = (int)h->ndof;
+    h->d_dinv.alloc(nd);
+    k_pdiag<<<(nd + TPB - 1) / TPB, TPB, 0, st>>>(nd, h->d_diagpos.p, h->d_vals[0].p, h->d_vals[1].p, h->d_vals[2].p,
+                                                  h->d_vals[6].p, h->d_vals[7].p, 1.0 / sa->dt, sa->theta, (int)sa->pc,
+                                                  h->d_dinv.p);
+    if (h->d_PQs.n != (size_t)h->nnz_sell) {
+      h->d_PQs.alloc(h->nnz_sell);
+      h->d_Jxys.alloc(h->nnz_sell);
+      h->d_Jzs.alloc(h->nnz_sell);
+      h->d_PQs.zero(st);      // padding entries stay zero
+      h->d_Jxys.zero(st);
+      h->d_Jzs.zero(st);
+    }
+    k_combine_shared<<<(int)((h->nnz + TPB - 1) / TPB), TPB, 0, st>>>(
+        h->nnz, h->d_rowidx.p, h->d_vals[0].p, h->d_vals[1].p, h->d_vals[2].p, h->d_vals[6].p, h->d_vals[7].p,
+        h->d_vals[3].p, h->d_vals[4].p, h->d_vals[5].p, 1.0 / sa->dt, sa->theta, h->d_dinv.p, h->d_rowptr.p,
+        h->d_sell_slot.p, h->d_slice_ptr.p, h->d_PQs.p, h->d_Jxys.p, h->d_Jzs.p);
+    BT_CUDA(cudaGetLastError());
+    std::vector<double> gd(3 * (size_t)members);
+    for (int b = 0; b < members; ++b)
+      for (int d = 0; d < 3; ++d) gd[3 * b + d] = sav[b].gdir[d];
+    h->d_gdirs.upload(gd.data(), gd.size(), st);
+    BT_CUDA(cudaStreamSynchronize(st));   // gd is a host temporary
+  } else {
+    for (int b = 0; b < members; ++b) bt_combine(h, sa->dt, sa->theta, sav[b].gdir, (int)sa->pc, b, members);
+  }
   ensure_vectors(h, members);
   h->step_stride = sa->nsteps;
   {
@@ -1481,6 +1698,9 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
 
   SpmvArgs a = base_args(h);
   if (periodic) a.rhs_add = h->d_rhs_add.p;
+  if (shared_ops) {
+    a.PQs = h->d_PQs.p; a.Jxys = h->d_Jxys.p; a.Jzs = h->d_Jzs.p; a.dinv = h->d_dinv.p; a.gdirs = h->d_gdirs.p;
+  }
   const int lanes = h->lanes;
   // keep the total block count near a few waves: the x-extent shrinks as the batch grows
   const int vgx = std::max(1, std::min(vec_grid(n), std::max(BT_NUM_SMS, BT_NUM_SMS * 8 / members)));

@@ -53,17 +53,48 @@ def tet_geometry(xyz, tets):
     return det, np.abs(det) / 6.0, g
 
 
+def tri_geometry(xyz, tris):
+    """Area and P1 gradients (nc,3,3) of triangles embedded in R^3 (gdim 2 meshes carry z = 0; manifolds keep
+    theirs): with e1 = x1-x0, e2 = x2-x0, n = e1 x e2 the gradients are the in-plane vectors
+    grad l1 = (e2 x n)/|n|^2, grad l2 = (n x e1)/|n|^2, grad l0 = -(grad l1 + grad l2)."""
+    x = xyz[tris]
+    e1, e2 = x[:, 1] - x[:, 0], x[:, 2] - x[:, 0]
+    n = np.cross(e1, e2)
+    n2 = (n * n).sum(axis=1)
+    g = np.empty((len(tris), 3, 3))
+    g[:, 1] = np.cross(e2, n) / n2[:, None]
+    g[:, 2] = np.cross(n, e1) / n2[:, None]
+    g[:, 0] = -(g[:, 1] + g[:, 2])
+    return 0.5 * np.sqrt(n2), g
+
+
+def as_xyz3(xyz):
+    """Coordinates as (nv,3): gdim-2 meshes get z = 0 (GdotX then reduces to x*g0 + y*g1, DmriFemLib.py:33-39)."""
+    xyz = np.asarray(xyz, dtype=float)
+    if xyz.shape[1] == 2:
+        xyz = np.hstack([xyz, np.zeros((len(xyz), 1))])
+    return xyz
+
+
 def element_matrices(xyz, tets, D=1.0, invT2=0.0):
     """Closed-form P1 element matrices.
 
     D: scalar, (nc,) per-cell scalar, or (nc,3,3) / (3,3) tensor (DmriFemLib.py:611-616).
     invT2: scalar or (nc,) per-cell 1/T2 (DmriFemLib.py:43-44).
-    Returns dict of (nc,4,4) arrays M,S,R,Jx,Jy,Jz and vol (nc,).
+    Returns dict of (nc,n,n) arrays M,S,R,Jx,Jy,Jz and vol (nc,), n = vertices per cell: 4 (tetrahedra) or
+    3 (triangles: 2-D meshes and surfaces in 3-D, DmriFemLib.py:34-38,591-592).  On a d-simplex
+    int phi_i phi_j = |T|(1+d_ij)/((d+1)(d+2)) and int x phi_i phi_j = |T| w_ij/((d+1)(d+2)(d+3)),
+    w_ij = sum_k x_k + x_i + x_j (i != j), 2 sum_k x_k + 4 x_i (i == j).
     """
     nc = len(tets)
-    _, vol, g = tet_geometry(xyz, tets)
-    I4 = np.eye(4)
-    M = vol[:, None, None] * (1.0 + I4)[None] / 20.0
+    nvc = np.asarray(tets).shape[1]
+    d = nvc - 1
+    if nvc == 4:
+        _, vol, g = tet_geometry(xyz, tets)
+    else:
+        vol, g = tri_geometry(xyz, tets)
+    I4 = np.eye(nvc)
+    M = vol[:, None, None] * (1.0 + I4)[None] / float((d + 1) * (d + 2))
     D = np.asarray(D, dtype=float)
     if D.ndim == 0:
         Dg = D * g
@@ -78,13 +109,14 @@ def element_matrices(xyz, tets, D=1.0, invT2=0.0):
     R = it2[:, None, None] * M
     x = xyz[tets]
     out = {"M": M, "S": S, "R": R, "vol": vol}
+    jden = float((d + 1) * (d + 2) * (d + 3))
     for d, name in enumerate(("Jx", "Jy", "Jz")):
-        xd = x[:, :, d]                              # (nc,4)
+        xd = x[:, :, d]                              # (nc,n)
         sx = xd.sum(axis=1)
         Jm = sx[:, None, None] + xd[:, :, None] + xd[:, None, :]          # i != j
         Jd = 2.0 * sx[:, None] + 4.0 * xd                                  # i == j
         Jm = Jm * (1 - I4)[None] + Jd[:, :, None] * I4[None]
-        out[name] = vol[:, None, None] * Jm / 120.0
+        out[name] = vol[:, None, None] * Jm / jden
     return out
 
 
@@ -117,13 +149,18 @@ def dof_map(nv, tets, phase=None):
 _FACES = np.array([[1, 2, 3], [0, 2, 3], [0, 1, 3], [0, 1, 2]])  # facet i is opposite vertex i (UFC)
 
 
+_EDGES = np.array([[1, 2], [0, 2], [0, 1]])
+
+
 def facets(tets):
-    """All (cell, local facet) sorted by vertex triple.  Returns key (nf,3), cell, lf."""
+    """All (cell, local facet) sorted by vertex tuple.  Returns key (nf,3) (tets) or (nf,2) (triangles), cell, lf."""
     nc = len(tets)
-    f = np.sort(tets[:, _FACES], axis=2).reshape(nc * 4, 3)
-    cell = np.repeat(np.arange(nc), 4)
-    lf = np.tile(np.arange(4), nc)
-    order = np.lexsort((f[:, 2], f[:, 1], f[:, 0]))
+    nvc = np.asarray(tets).shape[1]
+    loc = _FACES if nvc == 4 else _EDGES
+    f = np.sort(tets[:, loc], axis=2).reshape(nc * nvc, nvc - 1)
+    cell = np.repeat(np.arange(nc), nvc)
+    lf = np.tile(np.arange(nvc), nc)
+    order = np.lexsort(tuple(f[:, k] for k in range(nvc - 2, -1, -1)))
     return f[order], cell[order], lf[order]
 
 
@@ -156,6 +193,9 @@ def boundary_facets(tets):
 
 
 def tri_area(xyz, fv):
+    """Measure of facets: triangle area (fv (n,3)) or edge length (fv (n,2))."""
+    if fv.shape[1] == 2:
+        return np.linalg.norm(xyz[fv[:, 1]] - xyz[fv[:, 0]], axis=1)
     a = xyz[fv[:, 1]] - xyz[fv[:, 0]]
     b = xyz[fv[:, 2]] - xyz[fv[:, 0]]
     return 0.5 * np.linalg.norm(np.cross(a, b), axis=1)
@@ -165,8 +205,9 @@ def scalar_pattern(nv, tets):
     """The reference's scalar P1 sparsity in mesh-vertex numbering: row v couples to every
     w sharing a cell with v, diagonal included, columns sorted (UFC dofmap
     comri/one-comp/hpc-fenics-cpp/ufc/Bloch_Torrey3D.cpp:3869-3884 + PETSc sorted AIJ)."""
-    r = np.repeat(tets, 4, axis=1).ravel()
-    c = np.tile(tets, (1, 4)).ravel()
+    n = np.asarray(tets).shape[1]
+    r = np.repeat(tets, n, axis=1).ravel()
+    c = np.tile(tets, (1, n)).ravel()
     A = sp.coo_matrix((np.ones(len(r), dtype=np.int8), (r, c)), shape=(nv, nv)).tocsr()
     A.sort_indices()
     return A.indptr.astype(np.int32), A.indices.astype(np.int32)
@@ -191,13 +232,15 @@ def assemble(xyz, tets, phase=None, D=1.0, invT2=0.0, kappa=0.0, kappa_facet=Non
     bnd_kappa_vertex: optional (nv,) vertex values of the P1-interpolated artificial
     permeability marker kappa_e^h (DmriFemLib.py:601-610) -> boundary matrix B.
     """
-    xyz = np.asarray(xyz, dtype=float)
+    xyz = as_xyz3(xyz)
     tets = np.asarray(tets)
     nv = len(xyz)
+    nvc = tets.shape[1]                 # 4: tetrahedra, 3: triangles
+    nvf = nvc - 1                       # vertices per facet
     cell_dofs, ndof, dv, dc, vc2dof = dof_map(nv, tets, phase)
     em = element_matrices(xyz, tets, D, invT2)
-    rows = np.repeat(cell_dofs, 4, axis=1).ravel()
-    cols = np.tile(cell_dofs, (1, 4)).ravel()
+    rows = np.repeat(cell_dofs, nvc, axis=1).ravel()
+    cols = np.tile(cell_dofs, (1, nvc)).ravel()
     ops = Operators()
     ops.ndof, ops.nv, ops.cell_dofs, ops.dof_vertex, ops.dof_comp, ops.vc2dof = ndof, nv, cell_dofs, dv, dc, vc2dof
     ops.phase = None if phase is None else np.asarray(phase).astype(np.int32)
@@ -213,14 +256,14 @@ def assemble(xyz, tets, phase=None, D=1.0, invT2=0.0, kappa=0.0, kappa_facet=Non
             else:
                 kf = np.asarray(kappa_facet, dtype=float)
             area = tri_area(xyz, fv)
-            fm = (kf * area)[:, None, None] * (1.0 + np.eye(3))[None] / 12.0      # (ni,3,3)
+            fm = (kf * area)[:, None, None] * (1.0 + np.eye(nvf))[None] / float(nvf * (nvf + 1))   # facet mass
             d0 = vc2dof[fv, 0]
             d1 = vc2dof[fv, 1]
             assert (d0 >= 0).all() and (d1 >= 0).all()
             rr, cc, vv = [], [], []
             for (ra, ca, sgn) in ((d0, d0, 1.0), (d1, d1, 1.0), (d0, d1, -1.0), (d1, d0, -1.0)):
-                rr.append(np.repeat(ra, 3, axis=1).ravel())
-                cc.append(np.tile(ca, (1, 3)).ravel())
+                rr.append(np.repeat(ra, nvf, axis=1).ravel())
+                cc.append(np.tile(ca, (1, nvf)).ravel())
                 vv.append(sgn * fm.ravel())
             trip["I"] = (np.concatenate(rr), np.concatenate(cc), np.concatenate(vv))
         ops.iface = (fv, c0, c1)
@@ -231,15 +274,15 @@ def assemble(xyz, tets, phase=None, D=1.0, invT2=0.0, kappa=0.0, kappa_facet=Non
         keep = np.any(kv != 0.0, axis=1)
         bf, bcell, kv = bf[keep], bcell[keep], kv[keep]
         area = tri_area(xyz, bf)
-        # int phi_i phi_j phi_k = |F| * {1/10, 1/30, 1/60}
+        # int phi_i phi_j phi_k = |F| * {1/10, 1/30, 1/60} (triangle), |F| * {1/4, 1/12} (edge)
         sk = kv.sum(axis=1)
-        Bm = (sk[:, None, None] + kv[:, :, None] + kv[:, None, :])          # i != j  -> /60
-        Bd = 2.0 * sk[:, None] + 4.0 * kv                                   # i == j  -> /60
-        I3 = np.eye(3)
-        Bm = (Bm * (1 - I3)[None] + Bd[:, :, None] * I3[None]) * area[:, None, None] / 60.0
+        Bm = (sk[:, None, None] + kv[:, :, None] + kv[:, None, :])          # i != j
+        Bd = 2.0 * sk[:, None] + 4.0 * kv                                   # i == j
+        I3 = np.eye(nvf)
+        Bm = (Bm * (1 - I3)[None] + Bd[:, :, None] * I3[None]) * area[:, None, None] / float(nvf * (nvf + 1) * (nvf + 2))
         ph = np.zeros(len(tets), dtype=np.int32) if phase is None else ops.phase
         bd = vc2dof[bf, ph[bcell][:, None]]
-        trip["B"] = (np.repeat(bd, 3, axis=1).ravel(), np.tile(bd, (1, 3)).ravel(), Bm.ravel())
+        trip["B"] = (np.repeat(bd, nvf, axis=1).ravel(), np.tile(bd, (1, nvf)).ravel(), Bm.ravel())
         ops.bnd = (bf, bcell)
     # shared pattern = union of every structural entry (cell couplings + interface couplings)
     rr = np.concatenate([trip[k][0] for k in ("M", "I") if k in trip]).astype(np.int64)
@@ -479,7 +522,8 @@ def domain_sizes(xyz, tets):
     """bbox, hmin, hmax.  h of a cell = longest edge (DOLFIN >= 2017 `Cell::h`, third party;
     SURVEY Appendix C.17)."""
     x = xyz[tets]
-    e = [np.linalg.norm(x[:, i] - x[:, j], axis=1) for i in range(4) for j in range(i + 1, 4)]
+    n = np.asarray(tets).shape[1]
+    e = [np.linalg.norm(x[:, i] - x[:, j], axis=1) for i in range(n) for j in range(i + 1, n)]
     h = np.max(np.stack(e, axis=1), axis=1)
     return xyz.min(axis=0), xyz.max(axis=0), float(h.min()), float(h.max())
 
@@ -505,10 +549,11 @@ def periodic_term(xyz, tets, ops, pdir, lo, hi, q, gdir, theta):
     g = g / np.linalg.norm(g)
     bf, _ = boundary_facets(np.asarray(tets))
     nv = len(xyz)
+    planar = bf.shape[1] == 2          # triangle mesh in the x-y plane: boundary facets are edges
     rows = []          # (dof, [(src dof or -1, weight)]*3, g.dx)
     for v in range(nv):
         hit = None
-        for d in range(3):
+        for d in range(2 if planar else 3):
             if pdir[d]:
                 if abs(xyz[v, d] - lo[d]) <= 1e-7:
                     hit = (d, hi[d])
@@ -517,11 +562,17 @@ def periodic_term(xyz, tets, ops, pdir, lo, hi, q, gdir, theta):
         if hit is None:
             continue
         d, target = hit
-        other = [a for a in range(3) if a != d]
+        other = [a for a in range(2 if planar else 3) if a != d]
         tri = bf[np.all(np.abs(xyz[bf][:, :, d] - target) <= 1e-7, axis=1)]
         p = xyz[v, other]
         best, bw = None, None
-        for t in tri:
+        for t in (tri if planar else ()):          # P1 along the opposite boundary edge
+            a, b = xyz[t][:, other[0]]
+            w0 = (p[0] - b) / (a - b)
+            w = np.array([w0, 1.0 - w0])
+            if best is None or w.min() > bw.min():
+                best, bw = t, w
+        for t in (() if planar else tri):
             a, b, c = xyz[t][:, other]
             den = (b[1] - c[1]) * (a[0] - c[0]) + (c[0] - b[0]) * (a[1] - c[1])
             w0 = ((b[1] - c[1]) * (p[0] - c[0]) + (c[0] - b[0]) * (p[1] - c[1])) / den

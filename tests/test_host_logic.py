@@ -125,10 +125,10 @@ def test_sweep_sharding_covers_every_unit_once():
         assert owned == list(range(256))
         sizes = [len(sweep.shard_units(len(units), r, world)) for r in range(world)]
         assert max(sizes) - min(sizes) <= 1
-        # the batched sweep's sharding: same cover, every rank holds every b-value equally often, b-major order
+        # the batched sweep's sharding: same cover, every rank holds every b-value equally often
         shards = [sweep.shard_balanced(64, 4, r, world) for r in range(world)]
         assert sorted(u for s in shards for u in s) == list(range(256))
         for s in shards:
             bs = [units[u][1] for u in s]
-            assert bs == sorted(bs) and all(bs.count(j) == 64 // world for j in range(4))
+            assert s == sorted(s) and all(bs.count(j) == 64 // world for j in range(4))
     assert sorted(u for r in range(3) for u in sweep.shard_balanced(7, 2, r, 3)) == list(range(14))   # ragged

@@ -1,0 +1,136 @@
+"""CPU: the oracle on triangle meshes (gdim 2 and surfaces in 3-D; DmriFemLib.py:34-38, 591-592,
+ArbitraryTimeSequence.ipynb / T2_Relaxation.ipynb run 2-D disks, Manifolds.ipynb surfaces).  The reference has
+no generated 2-D kernels in the tree, so the closed forms are pinned against an independent quadrature here and
+the whole path against the published matrix-formalism values for the layered disk."""
+import numpy as np
+
+import bt_oracle as orc
+from dmri_fem_cloud_b200 import meshes
+
+# Dunavant degree-5 rule on the reference triangle (7 points; exact for the cubic integrands x*phi_i*phi_j)
+_A, _B = 0.470142064105115, 0.101286507323456
+_QP = np.array([[1 / 3, 1 / 3, 1 / 3], [_A, _A, 1 - 2 * _A], [_A, 1 - 2 * _A, _A], [1 - 2 * _A, _A, _A],
+                [_B, _B, 1 - 2 * _B], [_B, 1 - 2 * _B, _B], [1 - 2 * _B, _B, _B]])
+_QW = np.array([0.225] + [0.132394152788506] * 3 + [0.125939180544827] * 3)
+
+
+def _quadrature_tensors(x, D):
+    """M, S, Jd of ONE triangle (x: 3x3 vertex coordinates) by quadrature and a least-squares gradient."""
+    e = np.stack([x[1] - x[0], x[2] - x[0]])                   # 2x3
+    area = 0.5 * np.linalg.norm(np.cross(e[0], e[1]))
+    # in-plane gradient of lambda_k: minimum-norm solution of e @ g = d(lambda_k)/d(xi)
+    dl = np.array([[-1.0, -1.0], [1.0, 0.0], [0.0, 1.0]])
+    g = np.stack([np.linalg.lstsq(e, dl[k], rcond=None)[0] for k in range(3)])
+    M = np.zeros((3, 3))
+    J = np.zeros((3, 3, 3))
+    for lam, w in zip(_QP, _QW):
+        p = lam @ x
+        M += w * area * np.outer(lam, lam)
+        for d in range(3):
+            J[d] += w * area * p[d] * np.outer(lam, lam)
+    S = area * g @ D @ g.T
+    return M, S, J
+
+
+def test_triangle_closed_forms_match_quadrature():
+    rng = np.random.default_rng(11)
+    xyz = rng.normal(size=(30, 3)) * 3.0 + 5.0
+    tris = np.array([rng.choice(30, 3, replace=False) for _ in range(12)])
+    D = np.array([[2.0, 0.3, 0.1], [0.3, 1.0, 0.2], [0.1, 0.2, 1.5]]) * 1e-3
+    em = orc.element_matrices(xyz, tris, D=D, invT2=0.25)
+    for c, t in enumerate(tris):
+        M, S, J = _quadrature_tensors(xyz[t], D)
+        assert np.allclose(em["M"][c], M, rtol=1e-13, atol=0)
+        assert np.allclose(em["R"][c], 0.25 * M, rtol=1e-13, atol=0)
+        assert np.allclose(em["S"][c], S, rtol=1e-11, atol=1e-16)
+        for d, name in enumerate(("Jx", "Jy", "Jz")):
+            assert np.allclose(em[name][c], J[d], rtol=1e-12, atol=1e-14)
+
+
+def test_planar_mesh_operators():
+    """gdim-2 input (two coordinate columns): areas, partition of unity, the x moment, symmetric S with zero row sums,
+    and the scalar pattern = vertex adjacency."""
+    xy, tris, _ = meshes.disk_triangulation((5.0,), (6,), 32)
+    ops = orc.assemble(xy, tris, D=3e-3)
+    area = 0.5 * 32 * 5.0 ** 2 * np.sin(2 * np.pi / 32)
+    one = np.ones(ops.ndof)
+    assert abs(one @ (ops.M @ one) - area) <= 1e-12 * area
+    assert abs(one @ (ops.Jx @ one)) <= 1e-12 * area * 5.0         # centred disk
+    assert np.abs(ops.Jz.data).max() == 0.0
+    assert np.abs(ops.S @ one).max() <= 1e-16 * 1e3
+    assert abs(ops.S - ops.S.T).max() <= 1e-17
+    rp, ci = orc.scalar_pattern(len(xy), tris)
+    assert np.array_equal(rp, ops.rowptr) and np.array_equal(ci, ops.colidx)
+    lo, hi, hmin, hmax = orc.domain_sizes(orc.as_xyz3(xy), tris)
+    assert hmin > 0 and hmax < 5.0 / 6 + 2 * np.pi * 5.0 / 32 + 1e-9
+
+
+def test_two_compartment_edges_and_boundary_marker():
+    """Interface facets of a triangle mesh are edges: I = kappa * L * (1+delta)/6 blocks; B with a P1 weight."""
+    xy, tris, lay = meshes.disk_triangulation((5.0, 10.0), (3, 3), 24)
+    phase = (lay % 2).astype(np.int32)
+    kv = np.where(np.linalg.norm(xy, axis=1) > 10.0 - 1e-9, 2.0, 0.0)     # marker on the outer circle
+    ops = orc.assemble(xy, tris, phase, D=3e-3, kappa=1e-5, bnd_kappa_vertex=kv)
+    fv, c0, c1 = ops.iface
+    assert fv.shape == (24, 2) and np.allclose(np.linalg.norm(xy[fv], axis=2), 5.0)
+    assert ops.ndof == len(xy) + 24
+    one = np.ones(ops.ndof)
+    assert np.abs(ops.I @ one).max() <= 1e-18                       # kappa (u0-u1)(v0-v1) annihilates constants
+    jump = np.where(ops.dof_comp == 0, 1.0, 0.0)
+    circ = 24 * 2 * 5.0 * np.sin(np.pi / 24)
+    assert abs(jump @ (ops.I @ jump) - 1e-5 * circ) <= 1e-12 * circ * 1e-5
+    outer = 24 * 2 * 10.0 * np.sin(np.pi / 24)
+    assert abs(one @ (ops.B @ one) - 2.0 * outer) <= 1e-12 * outer
+
+
+def test_three_layer_disk_vs_matrix_formalism():
+    """T2_Relaxation.ipynb cell 12 (matrix formalism, 2-D three-layer disk R=[5,7.5,10], D=3e-3, kappa=1e-5,
+    delta=Delta=10000): b=1000 -> 0.4777, b=4000 -> 0.1784 -- on the 2-D mesh itself, as the notebook runs it."""
+    xy, tris, lay = meshes.disk_triangulation((5.0, 7.5, 10.0), (6, 3, 3), 48)
+    phase = (lay % 2).astype(np.int32)
+    ops = orc.assemble(xy, tris, phase, D=3e-3, kappa=1e-5)
+    seq = orc.pgse(10000.0, 10000.0)
+    for b, want in ((1000.0, 0.4777), (4000.0, 0.1784)):
+        r = orc.theta_solve(ops, seq, seq.q_from_b(b), [0, 1, 0], 50.0, solver="lu")
+        assert abs(r["signal"] / r["voi"] - want) <= 0.01 * want
+
+
+def test_surface_in_3d_equals_rotated_planar_mesh():
+    """A triangle mesh embedded in 3-D (Manifolds.ipynb) gives the signal of the planar mesh it is a rotation of,
+    with the gradient rotated along."""
+    xy, tris, _ = meshes.disk_triangulation((5.0,), (5,), 24)
+    seq = orc.pgse(2000.0, 6000.0)
+    q = seq.q_from_b(2000.0)
+    flat = orc.theta_solve(orc.assemble(xy, tris, D=3e-3), seq, q, [1.0, 0.5, 0.0], 100.0, solver="lu")
+    c, s = np.cos(0.7), np.sin(0.7)
+    Rm = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]]) @ np.array([[1, 0, 0], [0, c, -s], [0, s, c]])
+    xyz = orc.as_xyz3(xy) @ Rm.T        # (a translation would add a time-discretised global phase)
+    rot = orc.theta_solve(orc.assemble(xyz, tris, D=3e-3), seq, q, Rm @ np.array([1.0, 0.5, 0.0]), 100.0, solver="lu")
+    assert abs(rot["signal"] - flat["signal"]) <= 1e-10 * abs(flat["signal"])
+
+
+def test_planar_weak_periodic_term():
+    """Weak pseudo-periodic BC on a rectangle (boundary facets = edges): constant u and g along the periodic
+    direction give u_bc = exp(i q g L F) on the faces, and B u_bc integrates kappa_e over both faces."""
+    n = 6
+    xs = np.linspace(-2.0, 2.0, n + 1)
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    xy = np.column_stack([X.ravel(), Y.ravel()])
+    idx = np.arange((n + 1) ** 2).reshape(n + 1, n + 1)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[1:, :-1].ravel(), idx[1:, 1:].ravel(), idx[:-1, 1:].ravel()
+    tris = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d], 1)])
+    xyz = orc.as_xyz3(xy)
+    lo, hi, hmin, _ = orc.domain_sizes(xyz, tris)
+    pdir = [1, 0, 0]
+    kv = orc.periodic_marker(xyz, pdir, lo, hi, hmin)
+    ops = orc.assemble(xy, tris, D=3e-3, bnd_kappa_vertex=kv)
+    q, F = 0.3, 2.0
+    term = orc.periodic_term(xyz, tris, ops, pdir, lo, hi, q, [1.0, 0.0, 0.0], 0.5)
+    t = term(np.ones(ops.ndof, dtype=complex), F)
+    ke = 3e-3 / hmin
+    # x = lo face sees u(hi) rotated by exp(+i q L F), x = hi face by exp(-i q L F); the imaginary parts cancel.
+    # Column sums of B: kappa_e^h is the P1 interpolant of the vertex marker, so besides the two faces (length 4
+    # each) the four edges of the y-faces that touch a corner contribute int kappa_e phi_corner^2 = kappa_e h/3.
+    h = 4.0 / n
+    want = 0.5 * ke * (2 * 4.0 + 4 * h / 3.0) * np.cos(q * 4.0 * F)
+    assert abs(t.sum() - want) <= 1e-12 * abs(want)
