@@ -68,25 +68,37 @@ void btfem_destroy(btfem_t* h) {
 
 const char* btfem_last_error(btfem_t* h) { return h ? h->err.c_str() : "null handle"; }
 
+static void set_mesh_cells(btfem_t* h, int64_t nv, const double* xyz, int64_t nc, const int32_t* cells, int cell_nv,
+                           const int32_t* phase) {
+  BT_REQUIRE(nv > 0 && nc > 0 && xyz && cells, "empty mesh");
+  BT_REQUIRE(nv < (1LL << 30) && nc < (1LL << 27), "mesh too large for 32-bit indices");
+  for (int64_t i = 0; i < cell_nv * nc; ++i)
+    BT_REQUIRE(cells[i] >= 0 && cells[i] < nv, "cell vertex index out of range");
+  if (phase)
+    for (int64_t i = 0; i < nc; ++i) BT_REQUIRE(phase[i] == 0 || phase[i] == 1, "phase must be 0 or 1");
+  invalidate(h);
+  h->nv = nv;
+  h->nc = nc;
+  h->cell_nv = cell_nv;
+  h->two_comp = phase != nullptr;
+  h->h_xyz.assign(xyz, xyz + 3 * nv);
+  h->h_tets.assign(4 * nc, -1);   // triangles keep the 4-slot cell layout, 4th slot = -1
+  for (int64_t c = 0; c < nc; ++c)
+    for (int k = 0; k < cell_nv; ++k) h->h_tets[4 * c + k] = cells[cell_nv * c + k];
+  if (phase) h->h_phase.assign(phase, phase + nc); else h->h_phase.clear();
+  h->d_xyz.upload(xyz, 3 * nv, h->stream);
+  h->d_tets.upload(h->h_tets.data(), 4 * nc, h->stream);
+  if (phase) h->d_phase.upload(phase, nc, h->stream); else h->d_phase.release();
+  BT_CUDA(cudaStreamSynchronize(h->stream));
+}
+
 int btfem_set_mesh(btfem_t* h, int64_t nv, const double* xyz, int64_t nc, const int32_t* tets, const int32_t* phase) {
-  return guarded(h, [&] {
-    BT_REQUIRE(nv > 0 && nc > 0 && xyz && tets, "empty mesh");
-    BT_REQUIRE(nv < (1LL << 30) && nc < (1LL << 27), "mesh too large for 32-bit indices");
-    for (int64_t i = 0; i < 4 * nc; ++i) BT_REQUIRE(tets[i] >= 0 && tets[i] < nv, "tet vertex index out of range");
-    if (phase)
-      for (int64_t i = 0; i < nc; ++i) BT_REQUIRE(phase[i] == 0 || phase[i] == 1, "phase must be 0 or 1");
-    invalidate(h);
-    h->nv = nv;
-    h->nc = nc;
-    h->two_comp = phase != nullptr;
-    h->h_xyz.assign(xyz, xyz + 3 * nv);
-    h->h_tets.assign(tets, tets + 4 * nc);
-    if (phase) h->h_phase.assign(phase, phase + nc); else h->h_phase.clear();
-    h->d_xyz.upload(xyz, 3 * nv, h->stream);
-    h->d_tets.upload(tets, 4 * nc, h->stream);
-    if (phase) h->d_phase.upload(phase, nc, h->stream); else h->d_phase.release();
-    BT_CUDA(cudaStreamSynchronize(h->stream));
-  });
+  return guarded(h, [&] { set_mesh_cells(h, nv, xyz, nc, tets, 4, phase); });
+}
+
+int btfem_set_mesh_tri(btfem_t* h, int64_t nv, const double* xyz, int64_t nc, const int32_t* tris,
+                       const int32_t* phase) {
+  return guarded(h, [&] { set_mesh_cells(h, nv, xyz, nc, tris, 3, phase); });
 }
 
 int btfem_set_phase(btfem_t* h, const int32_t* phase) {
@@ -332,6 +344,7 @@ int btfem_get_solution(btfem_t* h, double* u) {
 int btfem_set_partition(btfem_t* h, int64_t nv_own, int64_t nv_interior) {
   return guarded(h, [&] {
     BT_REQUIRE(h->nv > 0, "set the mesh first");
+    BT_REQUIRE(h->cell_nv == 4, "row partitions are built on tetrahedral meshes");
     BT_REQUIRE(nv_own > 0 && nv_own <= h->nv && nv_interior >= 0 && nv_interior <= nv_own, "bad partition sizes");
     h->nv_own = nv_own;
     h->nv_int = nv_interior;

@@ -40,13 +40,13 @@ struct TempStorage {
 // ------------------------------------------------------------------------------------ mesh statistics
 
 // per-block min / max over cells of the longest edge (exact: min/max are order independent)
-__global__ void __launch_bounds__(TPB) k_cell_sizes(int64_t nc, const int32_t* __restrict__ tets,
+__global__ void __launch_bounds__(TPB) k_cell_sizes(int64_t nc, int cell_nv, const int32_t* __restrict__ tets,
                                                     const double* __restrict__ xyz, double* __restrict__ out) {
   __shared__ double s_min[TPB / 32], s_max[TPB / 32];
   double lo = 1e300, hi = 0.0;
   for (int64_t c = blockIdx.x * (int64_t)TPB + threadIdx.x; c < nc; c += (int64_t)gridDim.x * TPB) {
     int4 t = *reinterpret_cast<const int4*>(tets + 4 * c);
-    int v[4] = {t.x, t.y, t.z, t.w};
+    int v[4] = {t.x, t.y, t.z, cell_nv == 4 ? t.w : t.x};   // triangle: the 4th slot repeats a vertex (adds no edge)
     double x[4][3];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -80,14 +80,22 @@ __global__ void __launch_bounds__(TPB) k_cell_sizes(int64_t nc, const int32_t* _
 
 // ------------------------------------------------------------------------------------ facets
 
-__global__ void k_gen_facets(int64_t nc, const int32_t* __restrict__ tets, FacetKey* __restrict__ keys) {
+// Facet slots stay 4 per cell.  Triangle meshes: facet lf < 3 is the EDGE opposite vertex lf, keyed (a, b, NOV);
+// slot 3 does not exist and gets a key of its own (NOV, NOV, slot) that matches nothing and is never flagged.
+constexpr uint32_t NOV = 0xffffffffu;   // "no vertex"
+
+__global__ void k_gen_facets(int64_t nc, int cell_nv, const int32_t* __restrict__ tets, FacetKey* __restrict__ keys) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= nc * 4) return;
   int64_t c = i >> 2;
   int lf = (int)(i & 3);
-  uint32_t v[3];
+  if (lf >= cell_nv) {
+    keys[i] = FacetKey{NOV, NOV, (uint32_t)i, (uint32_t)i};
+    return;
+  }
+  uint32_t v[3] = {NOV, NOV, NOV};
   int m = 0;
-  for (int k = 0; k < 4; ++k)
+  for (int k = 0; k < cell_nv; ++k)
     if (k != lf) v[m++] = (uint32_t)tets[c * 4 + k];   // facet lf is opposite vertex lf (UFC)
   if (v[0] > v[1]) { uint32_t t = v[0]; v[0] = v[1]; v[1] = t; }
   if (v[1] > v[2]) { uint32_t t = v[1]; v[1] = v[2]; v[2] = t; }
@@ -116,6 +124,11 @@ __global__ void k_flag_facets(int64_t nf, const FacetKey* __restrict__ keys, con
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= nf) return;
   FacetKey k = keys[i];
+  if (k.a == NOV) {   // the non-existent 4th facet of a triangle
+    flag_if[i] = 0;
+    flag_bd[i] = 0;
+    return;
+  }
   bool next_same = (i + 1 < nf) && same_facet(k, keys[i + 1]);
   bool prev_same = (i > 0) && same_facet(k, keys[i - 1]);
   uint8_t fi = 0, fb = 0;
@@ -123,7 +136,7 @@ __global__ void k_flag_facets(int64_t nf, const FacetKey* __restrict__ keys, con
     fi = phase[k.cf >> 2] != phase[keys[i + 1].cf >> 2];
   }
   if (!next_same && !prev_same && bmark) {
-    fb = (bmark[k.a] != 0.0) || (bmark[k.b] != 0.0) || (bmark[k.c] != 0.0);
+    fb = (bmark[k.a] != 0.0) || (bmark[k.b] != 0.0) || (k.c != NOV && bmark[k.c] != 0.0);
   }
   flag_if[i] = fi;
   flag_bd[i] = fb;
@@ -140,9 +153,12 @@ __global__ void k_fill_iface(int64_t ni, const int64_t* __restrict__ sel, const 
   FacetKey k = keys[i];
   uint32_t v[3] = {k.a, k.b, k.c};
   for (int m = 0; m < 3; ++m) {
-    if_verts[f * 3 + m] = (int32_t)v[m];
-    if_dofs[f * 6 + m] = vc2dof[2 * (int64_t)v[m] + 0];
-    if_dofs[f * 6 + 3 + m] = vc2dof[2 * (int64_t)v[m] + 1];
+    // edge (triangle mesh): no third vertex; its dof slots repeat the first vertex, so that the (zero-valued)
+    // contributions of the missing vertex land on pattern entries that exist anyway
+    const uint32_t vm = v[m] == NOV ? v[0] : v[m];
+    if_verts[f * 3 + m] = v[m] == NOV ? -1 : (int32_t)v[m];
+    if_dofs[f * 6 + m] = vc2dof[2 * (int64_t)vm + 0];
+    if_dofs[f * 6 + 3 + m] = vc2dof[2 * (int64_t)vm + 1];
   }
   double kap;
   if (kkind == 0) {
@@ -164,8 +180,9 @@ __global__ void k_fill_bfacet(int64_t nb, const int64_t* __restrict__ sel, const
   int comp = phase ? phase[k.cf >> 2] : 0;   // weighted by phase / (1-phase) of the boundary cell (DmriFemLib.py:143)
   uint32_t v[3] = {k.a, k.b, k.c};
   for (int m = 0; m < 3; ++m) {
-    bf_verts[f * 3 + m] = (int32_t)v[m];
-    bf_dofs[f * 3 + m] = vc2dof[2 * (int64_t)v[m] + comp];
+    const uint32_t vm = v[m] == NOV ? v[0] : v[m];   // edge: see k_fill_iface
+    bf_verts[f * 3 + m] = v[m] == NOV ? -1 : (int32_t)v[m];
+    bf_dofs[f * 3 + m] = vc2dof[2 * (int64_t)vm + comp];
   }
 }
 
@@ -282,6 +299,7 @@ __global__ void k_sell_columns(int64_t nslice, const int32_t* __restrict__ slice
 
 struct AsmArgs {
   int64_t nnz;
+  int cell_nv;   // 4 tetrahedra, 3 triangles
   uint32_t ncell16, nif36;
   const int64_t* seg;
   const uint32_t* src;
@@ -305,6 +323,11 @@ __device__ inline double tri_area(const double* xyz, int a, int b, int c) {
   return 0.5 * sqrt(cx * cx + cy * cy + cz * cz);
 }
 
+__device__ inline double edge_len(const double* xyz, int a, int b) {
+  double dx = xyz[3 * b] - xyz[3 * a], dy = xyz[3 * b + 1] - xyz[3 * a + 1], dz = xyz[3 * b + 2] - xyz[3 * a + 2];
+  return sqrt(dx * dx + dy * dy + dz * dz);
+}
+
 // One thread per CSR nonzero; its contributions (cells, interface facets, boundary facets) are
 // visited in ascending contribution id (stable radix sort) -> fixed summation order.
 __global__ void __launch_bounds__(TPB) k_assemble(AsmArgs a) {
@@ -313,7 +336,68 @@ __global__ void __launch_bounds__(TPB) k_assemble(AsmArgs a) {
   double m = 0, s = 0, r = 0, jx = 0, jy = 0, jz = 0, ii = 0, bb = 0;
   for (int64_t q = a.seg[p]; q < a.seg[p + 1]; ++q) {
     uint32_t sid = a.src[q];
-    if (sid < a.ncell16) {
+    if (sid < a.ncell16 && a.cell_nv == 3) {
+      // P1 triangle, possibly embedded in 3-D: n = e1 x e2, |T| = |n|/2, grad l1 = (e2 x n)/|n|^2,
+      // grad l2 = (n x e1)/|n|^2, grad l0 = -(grad l1 + grad l2);  int phi_i phi_j = |T|(1+d_ij)/12,
+      // int x phi_i phi_j = |T| w_ij / 60.  Slots (i,3), (3,j) of the 16-per-cell list do not exist: zero.
+      uint32_t t = sid >> 4;
+      int i = (sid >> 2) & 3, j = sid & 3;
+      if (i == 3 || j == 3) continue;
+      int4 tv = *reinterpret_cast<const int4*>(a.tets + 4 * (int64_t)t);
+      int vid[3] = {tv.x, tv.y, tv.z};
+      double x[3][3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        x[k][0] = a.xyz[3 * (int64_t)vid[k]];
+        x[k][1] = a.xyz[3 * (int64_t)vid[k] + 1];
+        x[k][2] = a.xyz[3 * (int64_t)vid[k] + 2];
+      }
+      double e1[3], e2[3], nn[3], g[3][3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) { e1[d] = x[1][d] - x[0][d]; e2[d] = x[2][d] - x[0][d]; }
+      nn[0] = e1[1] * e2[2] - e1[2] * e2[1];
+      nn[1] = e1[2] * e2[0] - e1[0] * e2[2];
+      nn[2] = e1[0] * e2[1] - e1[1] * e2[0];
+      double n2 = nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2];
+      double area = 0.5 * sqrt(n2);
+      double inv = 1.0 / n2;
+      g[1][0] = (e2[1] * nn[2] - e2[2] * nn[1]) * inv;
+      g[1][1] = (e2[2] * nn[0] - e2[0] * nn[2]) * inv;
+      g[1][2] = (e2[0] * nn[1] - e2[1] * nn[0]) * inv;
+      g[2][0] = (nn[1] * e1[2] - nn[2] * e1[1]) * inv;
+      g[2][1] = (nn[2] * e1[0] - nn[0] * e1[2]) * inv;
+      g[2][2] = (nn[0] * e1[1] - nn[1] * e1[0]) * inv;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) g[0][d] = -(g[1][d] + g[2][d]);
+      double dg[3];
+      if (a.dkind == 0) {
+        double d0 = a.D[0];
+        dg[0] = d0 * g[j][0]; dg[1] = d0 * g[j][1]; dg[2] = d0 * g[j][2];
+      } else if (a.dkind == 1) {
+        double d0 = a.D[t];
+        dg[0] = d0 * g[j][0]; dg[1] = d0 * g[j][1]; dg[2] = d0 * g[j][2];
+      } else {
+        const double* Dt = a.D + 9 * (int64_t)t;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) dg[d] = Dt[3 * d] * g[j][0] + Dt[3 * d + 1] * g[j][1] + Dt[3 * d + 2] * g[j][2];
+      }
+      double mij = area * (i == j ? 2.0 : 1.0) / 12.0;
+      m += mij;
+      s += area * (g[i][0] * dg[0] + g[i][1] * dg[1] + g[i][2] * dg[2]);
+      r += (a.t2kind == 0 ? a.invT2[0] : a.invT2[t]) * mij;
+      double sx[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) sx[d] = x[0][d] + x[1][d] + x[2][d];
+      if (i == j) {
+        jx += area * (2.0 * sx[0] + 4.0 * x[i][0]) / 60.0;
+        jy += area * (2.0 * sx[1] + 4.0 * x[i][1]) / 60.0;
+        jz += area * (2.0 * sx[2] + 4.0 * x[i][2]) / 60.0;
+      } else {
+        jx += area * (sx[0] + x[i][0] + x[j][0]) / 60.0;
+        jy += area * (sx[1] + x[i][1] + x[j][1]) / 60.0;
+        jz += area * (sx[2] + x[i][2] + x[j][2]) / 60.0;
+      }
+    } else if (sid < a.ncell16) {
       uint32_t t = sid >> 4;
       int i = (sid >> 2) & 3, j = sid & 3;
       int4 tv = *reinterpret_cast<const int4*>(a.tets + 4 * (int64_t)t);
@@ -383,19 +467,35 @@ __global__ void __launch_bounds__(TPB) k_assemble(AsmArgs a) {
       uint32_t q2 = sid - a.ncell16;
       uint32_t f = q2 / 36, k = q2 % 36;
       uint32_t blk = k / 9, i = (k % 9) / 3, j = k % 3;
-      double area = tri_area(a.xyz, a.if_verts[3 * f], a.if_verts[3 * f + 1], a.if_verts[3 * f + 2]);
-      double v = a.if_kappa[f] * area * (i == j ? 2.0 : 1.0) / 12.0;
+      double v;
+      if (a.if_verts[3 * f + 2] < 0) {   // interface EDGE of a triangle mesh: kappa * L * (1+d_ij)/6 on its two vertices
+        v = (i == 2 || j == 2) ? 0.0
+                               : a.if_kappa[f] * edge_len(a.xyz, a.if_verts[3 * f], a.if_verts[3 * f + 1]) *
+                                     (i == j ? 2.0 : 1.0) / 6.0;
+      } else {
+        double area = tri_area(a.xyz, a.if_verts[3 * f], a.if_verts[3 * f + 1], a.if_verts[3 * f + 2]);
+        v = a.if_kappa[f] * area * (i == j ? 2.0 : 1.0) / 12.0;
+      }
       ii += (blk < 2) ? v : -v;
     } else {
       uint32_t q2 = sid - a.ncell16 - a.nif36;
       uint32_t f = q2 / 9, k = q2 % 9;
       int i = k / 3, j = k % 3;
       int va = a.bf_verts[3 * f], vb = a.bf_verts[3 * f + 1], vc = a.bf_verts[3 * f + 2];
-      double area = tri_area(a.xyz, va, vb, vc);
-      double kv[3] = {a.bmark[va], a.bmark[vb], a.bmark[vc]};
-      double sk = kv[0] + kv[1] + kv[2];
-      double w = (i == j) ? (2.0 * sk + 4.0 * kv[i]) : (sk + kv[i] + kv[j]);
-      bb += area * w / 60.0;
+      if (vc < 0) {   // boundary EDGE: int kappa_e^h phi_i phi_j = L w_ij / 24 (int phi^3 = L/4, int phi_i^2 phi_j = L/12)
+        if (i < 2 && j < 2) {
+          double kv[2] = {a.bmark[va], a.bmark[vb]};
+          double sk = kv[0] + kv[1];
+          double w = (i == j) ? (2.0 * sk + 4.0 * kv[i]) : (sk + kv[i] + kv[j]);
+          bb += edge_len(a.xyz, va, vb) * w / 24.0;
+        }
+      } else {
+        double area = tri_area(a.xyz, va, vb, vc);
+        double kv[3] = {a.bmark[va], a.bmark[vb], a.bmark[vc]};
+        double sk = kv[0] + kv[1] + kv[2];
+        double w = (i == j) ? (2.0 * sk + 4.0 * kv[i]) : (sk + kv[i] + kv[j]);
+        bb += area * w / 60.0;
+      }
     }
   }
   a.M[p] = m; a.S[p] = s; a.R[p] = r; a.Jx[p] = jx; a.Jy[p] = jy; a.Jz[p] = jz; a.I[p] = ii; a.B[p] = bb;
@@ -418,7 +518,7 @@ void bt_mesh_stats(btfem* h, double* hmin, double* hmax) {
   const int grid = (int)std::min<int64_t>(nblocks(h->nc), BT_NUM_SMS * 8);
   DevArray<double> part;
   part.alloc(2 * grid);
-  k_cell_sizes<<<grid, TPB, 0, h->stream>>>(h->nc, h->d_tets.p, h->d_xyz.p, part.p);
+  k_cell_sizes<<<grid, TPB, 0, h->stream>>>(h->nc, h->cell_nv, h->d_tets.p, h->d_xyz.p, part.p);
   BT_CUDA(cudaGetLastError());
   std::vector<double> hp(2 * grid);
   part.download(hp.data(), h->stream);
@@ -436,7 +536,7 @@ void bt_build_dofmap(btfem* h) {
   std::vector<uint8_t> active(2 * nv, 0);
   for (int64_t c = 0; c < nc; ++c) {
     int ph = h->two_comp ? h->h_phase[c] : 0;
-    for (int k = 0; k < 4; ++k) active[2 * (int64_t)h->h_tets[4 * c + k] + ph] = 1;
+    for (int k = 0; k < h->cell_nv; ++k) active[2 * (int64_t)h->h_tets[4 * c + k] + ph] = 1;
   }
   std::vector<int32_t> vc2dof(2 * nv, -1);
   h->h_dof_vertex.clear();
@@ -465,7 +565,10 @@ void bt_build_dofmap(btfem* h) {
   std::vector<int32_t> cell_dofs(4 * nc);
   for (int64_t c = 0; c < nc; ++c) {
     int ph = h->two_comp ? h->h_phase[c] : 0;
-    for (int k = 0; k < 4; ++k) cell_dofs[4 * c + k] = vc2dof[2 * (int64_t)h->h_tets[4 * c + k] + ph];
+    // triangle: the 4th dof slot repeats the first, so that the (zero-valued) contributions (i,3), (3,j) of the
+    // 16-per-cell contribution list land on pattern entries that exist anyway
+    for (int k = 0; k < 4; ++k)
+      cell_dofs[4 * c + k] = vc2dof[2 * (int64_t)h->h_tets[4 * c + (k < h->cell_nv ? k : 0)] + ph];
   }
   h->d_vc2dof.upload(vc2dof.data(), vc2dof.size(), h->stream);
   h->d_cell_dofs.upload(cell_dofs.data(), cell_dofs.size(), h->stream);
@@ -499,7 +602,7 @@ void bt_build_facets(btfem* h) {
   }
   DevArray<FacetKey> keys;
   keys.alloc(nf);
-  k_gen_facets<<<nblocks(nf), TPB, 0, st>>>(h->nc, h->d_tets.p, keys.p);
+  k_gen_facets<<<nblocks(nf), TPB, 0, st>>>(h->nc, h->cell_nv, h->d_tets.p, keys.p);
   TempStorage tmp;
   size_t bytes = 0;
   BT_CUDA(cub::DeviceMergeSort::SortKeys(nullptr, bytes, keys.p, nf, FacetLess(), st));
@@ -689,6 +792,7 @@ void bt_assemble_values(btfem* h) {
   h->d_invT2.upload(h->h_invT2.data(), h->h_invT2.size(), st);
   AsmArgs a;
   a.nnz = h->nnz;
+  a.cell_nv = h->cell_nv;
   a.ncell16 = (uint32_t)(16 * h->nc);
   a.nif36 = (uint32_t)(36 * h->n_iface);
   a.seg = h->d_seg.p;

@@ -23,12 +23,31 @@ import sympy as sp
 from . import btfem as _bt
 
 
+class _Dim:
+    def __init__(self, d):
+        self._d = d
+
+    def dim(self):
+        return self._d
+
+
 class Mesh:
-    """Stand-in for dolfin.Mesh: coordinates (nv,3) and cells (nc,4)."""
+    """Stand-in for dolfin.Mesh: coordinates (nv,gdim) and cells (nc,tdim+1) -- tetrahedra, or triangles in the
+    plane (gdim 2) or in space (a surface, gdim 3)."""
 
     def __init__(self, xyz, tets):
         self.xyz = np.ascontiguousarray(xyz, dtype=np.float64)
         self.tets = np.ascontiguousarray(tets, dtype=np.int32)
+        if self.tets.ndim != 2 or self.tets.shape[1] not in (3, 4):
+            raise RuntimeError("cells must be tetrahedra (nc,4) or triangles (nc,3)")
+        if self.xyz.ndim != 2 or self.xyz.shape[1] not in (2, 3) or self.xyz.shape[1] < self.tets.shape[1] - 1:
+            raise RuntimeError("coordinates must be (nv,2) or (nv,3) and gdim >= tdim")
+
+    def geometry(self):
+        return _Dim(self.xyz.shape[1])
+
+    def topology(self):
+        return _Dim(self.tets.shape[1] - 1)
 
     def coordinates(self):
         return self.xyz
@@ -44,7 +63,8 @@ class Mesh:
 
     def _edge_lengths(self):
         x = self.xyz[self.tets]
-        return np.stack([np.linalg.norm(x[:, i] - x[:, j], axis=1) for i in range(4) for j in range(i + 1, 4)], axis=1)
+        n = self.tets.shape[1]
+        return np.stack([np.linalg.norm(x[:, i] - x[:, j], axis=1) for i in range(n) for j in range(i + 1, n)], axis=1)
 
     def hmin(self):
         # DOLFIN >= 2017: Cell::h() = largest vertex-to-vertex distance (third party)
@@ -94,6 +114,8 @@ class MRI_parameters():
         self.s = sp.Symbol('s')
 
     def set_gradient_dir(self, mymesh, g0, g1, g2):
+        if mymesh is not None and hasattr(mymesh, "geometry") and mymesh.geometry().dim() == 2:
+            g2 = 0.0                                  # gdim 2: Point(g0, g1), DmriFemLib.py:813-814
         self.gdir = Point(g0, g1, g2)
         if abs(self.gdir.norm()) > 1e-10:
             self.gdir.v /= self.gdir.norm()
@@ -179,11 +201,14 @@ class MyDomain():
         self._fem.set_mesh(mymesh.xyz, mymesh.tets, None)
         self.hmin, self.hmax = self._fem.mesh_stats()
         self.tol = 1e-2 * self.hmin
-        self.gdim = 3
-        self.tdim = 3
+        self.gdim = mymesh.geometry().dim()
+        self.tdim = mymesh.topology().dim()
         xyz = mymesh.coordinates()
-        self.xmin, self.ymin, self.zmin = (float(v) for v in xyz.min(axis=0))
-        self.xmax, self.ymax, self.zmax = (float(v) for v in xyz.max(axis=0))
+        lo, hi = xyz.min(axis=0), xyz.max(axis=0)
+        if self.gdim == 2:                            # GetGlobalDomainSize: zmin = zmax = 0 (DmriFemLib.py:571)
+            lo, hi = np.append(lo, 0.0), np.append(hi, 0.0)
+        self.xmin, self.ymin, self.zmin = (float(v) for v in lo)
+        self.xmax, self.ymax, self.zmax = (float(v) for v in hi)
         print("Domain size: xmin=%f, ymin=%f, zmin=%f, xmax=%f, ymax=%f, zmax=%f" % (
             self.xmin, self.ymin, self.zmin, self.xmax, self.ymax, self.zmax))
         self.mymesh = mymesh
@@ -244,7 +269,11 @@ class MyDomain():
                 fem.set_permeability(float(self.kappa))
             else:
                 fem.set_permeability(np.asarray(self.kappa, dtype=float), self.kappa_marker)
+        if self.gdim == 2:
+            self.PeriodicDir = [self.PeriodicDir[0], self.PeriodicDir[1], 0]     # no z faces (DmriFemLib.py:602-605)
         if sum(self.PeriodicDir) > 0:
+            if self.tdim == 2 and self.gdim == 3:
+                raise NotImplementedError("weak pseudo-periodic BC on a surface mesh in 3-D")
             fem.set_periodic(self.PeriodicDir, self.kappa_e_scalar, self.tol,
                              [self.xmin, self.ymin, self.zmin], [self.xmax, self.ymax, self.zmax])
         fem.set_initial(ic)

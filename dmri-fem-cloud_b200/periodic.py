@@ -65,6 +65,28 @@ def _locate(points2, tri_xy, ncand=16):
     return cand[rows, best], W[rows, best]
 
 
+def _line_segments(xyz, tris, d, target):
+    """Triangle mesh in the x-y plane: edges with both vertices on the line x_d = target."""
+    on = np.abs(xyz[:, d] - target) <= FACE_TOL
+    out = []
+    for a, b in ((1, 2), (0, 2), (0, 1)):
+        m = on[tris[:, a]] & on[tris[:, b]]
+        out.append(np.sort(tris[m][:, [a, b]], axis=1))
+    f = np.concatenate(out)
+    return np.unique(f, axis=0) if len(f) else f.reshape(0, 2)
+
+
+def _locate_1d(p, seg_x):
+    """For each coordinate p along the opposite boundary line: the containing edge (or the least-outside one:
+    extrapolation) and its two P1 weights."""
+    a, b = seg_x[:, 0][None, :], seg_x[:, 1][None, :]
+    w0 = (p[:, None] - b) / (a - b)
+    W = np.stack([w0, 1.0 - w0], axis=2)                  # (np, ns, 2)
+    best = np.argmax(W.min(axis=2), axis=1)
+    rows = np.arange(len(p))
+    return best, W[rows, best]
+
+
 def build_gather(xyz, tets, phase, pdir, lo, hi, dof_vertex, dof_comp, bfacets=None):
     """Returns dof (nb,), src (nb,3) dof ids or -1, w (nb,3), dx (nb,3).
 
@@ -73,6 +95,12 @@ def build_gather(xyz, tets, phase, pdir, lo, hi, dof_vertex, dof_comp, bfacets=N
     dof_vertex/dof_comp: the library's dof map (btfem_get_dofmap).  Field `comp` evaluated at a vertex
     where that compartment is inactive is 0 (the reference's pinned dofs), i.e. src = -1."""
     xyz = np.asarray(xyz, dtype=float)
+    tets = np.asarray(tets)
+    planar = tets.shape[1] == 3          # triangle mesh in the x-y plane: boundary facets are edges (third vertex -1)
+    if xyz.shape[1] == 2:
+        xyz = np.hstack([xyz, np.zeros((len(xyz), 1))])
+    if planar:
+        pdir = [pdir[0], pdir[1], 0]
     nv = len(xyz)
     vc2dof = -np.ones((nv, 2), dtype=np.int64)
     vc2dof[dof_vertex, dof_comp] = np.arange(len(dof_vertex))
@@ -101,6 +129,17 @@ def build_gather(xyz, tets, phase, pdir, lo, hi, dof_vertex, dof_comp, bfacets=N
             if len(vs) == 0:
                 continue
             target = hi[d] if side == 0 else lo[d]         # mirrored onto the opposite face
+            if planar:
+                o = 1 - d
+                seg = bf[:, :2] if bf is not None else _line_segments(xyz, tets, d, target).astype(np.int64)
+                seg = seg[np.all(np.abs(xyz[seg][:, :, d] - target) <= FACE_TOL, axis=1)]
+                if len(seg) == 0:
+                    continue
+                s_idx, W = _locate_1d(xyz[vs, o], xyz[seg][:, :, o])
+                src_v[vs, :2] = seg[s_idx]
+                wts[vs, :2] = W
+                dxs[vs, d] = target - xyz[vs, d]
+                continue
             if bf is not None:
                 tri = bf[np.all(np.abs(xyz[bf][:, :, d] - target) <= FACE_TOL, axis=1)]
             else:

@@ -61,6 +61,14 @@ int btfem_version(void);
 int btfem_set_mesh(btfem_t* h, int64_t nv, const double* xyz /*[nv*3]*/, int64_t nc,
                    const int32_t* tets /*[nc*4]*/, const int32_t* phase /*[nc] or NULL*/);
 
+/* Triangle meshes: gdim-2 meshes (the 2-D disks of ArbitraryTimeSequence.ipynb / T2_Relaxation.ipynb; the caller
+ * passes z = 0 and GdotX reduces to x*g0 + y*g1, DmriFemLib.py:34-36) and surfaces embedded in 3-D
+ * (Manifolds.ipynb; tdim 2, gdim 3, DmriFemLib.py:591-592).  Same path afterwards: P1 element integrals on
+ * triangles, interface and boundary facets are edges.  btfem_get_boundary_facets then reports the third vertex
+ * of a facet as -1.  Whole-mesh handles only (no btfem_set_partition). */
+int btfem_set_mesh_tri(btfem_t* h, int64_t nv, const double* xyz /*[nv*3]*/, int64_t nc,
+                       const int32_t* tris /*[nc*3]*/, const int32_t* phase /*[nc] or NULL*/);
+
 /* Replace only the phase function of the current mesh (NULL = one compartment). */
 int btfem_set_phase(btfem_t* h, const int32_t* phase /*[nc] or NULL*/);
 /* mesh.hmin()/hmax() as used by MyDomain (DmriFemLib.py:588-589): min / max over cells of the cell size,
