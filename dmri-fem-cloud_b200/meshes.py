@@ -31,7 +31,9 @@ def _open_text(path):
 
 
 def read_gmsh2(path):
-    """Read a gmsh v2 ASCII tetrahedral mesh (optionally zipped)."""
+    """Read a gmsh v2 ASCII mesh (optionally zipped): the tetrahedra (element type 4), or, when the file has
+    none, the triangles (type 2) -- a 2-D mesh, returned with two coordinate columns when every z is 0
+    (dolfin-convert writes gdim 2 then), else a surface in 3-D."""
     with _open_text(path) as f:
         lines = f.read().split("\n")
     i = lines.index("$Nodes")
@@ -44,35 +46,66 @@ def read_gmsh2(path):
         coords[k] = (float(p[1]), float(p[2]), float(p[3]))
     j = lines.index("$Elements")
     ne = int(lines[j + 1])
-    tets, marks = [], []
+    cells = {4: ([], []), 2: ([], [])}
+    nvert = {4: 4, 2: 3}
     for k in range(ne):
         p = lines[j + 2 + k].split()
-        if int(p[1]) == 4:
+        et = int(p[1])
+        if et in cells:
             nt = int(p[2])
-            tets.append([int(a) for a in p[3 + nt:3 + nt + 4]])
-            marks.append(int(p[3]) if nt > 0 else 0)
-    tets = np.array(tets, dtype=np.int64)
+            cells[et][0].append([int(a) for a in p[3 + nt:3 + nt + nvert[et]]])
+            cells[et][1].append(int(p[3]) if nt > 0 else 0)
+    et = 4 if cells[4][0] else 2
+    tets = np.array(cells[et][0], dtype=np.int64).reshape(-1, nvert[et])
+    marks = cells[et][1]
     used = np.zeros(node_ids.max() + 1, dtype=bool)
     used[tets.ravel()] = True
     keep = used[node_ids]                       # file order of $Nodes, unused nodes dropped
     new_id = -np.ones(node_ids.max() + 1, dtype=np.int64)
     new_id[node_ids[keep]] = np.arange(int(keep.sum()))
-    return coords[keep].copy(), new_id[tets].astype(np.int32), np.array(marks, dtype=np.int32)
+    xyz = coords[keep].copy()
+    if et == 2 and not np.any(xyz[:, 2]):
+        xyz = xyz[:, :2].copy()
+    return xyz, new_id[tets].astype(np.int32), np.array(marks, dtype=np.int32)
 
 
 def read_dolfin_xml(path):
-    """Read a DOLFIN XML tetrahedral mesh (optionally zipped)."""
+    """Read a DOLFIN XML mesh (optionally zipped): celltype tetrahedron, or triangle (dim 2 or 3)."""
     with _open_text(path) as f:
         txt = f.read()
     nv = int(re.search(r'<vertices size="(\d+)"', txt).group(1))
     nc = int(re.search(r'<cells size="(\d+)"', txt).group(1))
+    head = re.search(r'<mesh celltype="(\w+)" dim="(\d+)"', txt)
+    celltype, gdim = (head.group(1), int(head.group(2))) if head else ("tetrahedron", 3)
     xyz = np.zeros((nv, 3))
     for m in re.finditer(r'<vertex index="(\d+)" x="([^"]+)" y="([^"]+)"(?: z="([^"]+)")?', txt):
         xyz[int(m.group(1))] = (float(m.group(2)), float(m.group(3)), float(m.group(4) or 0.0))
+    if celltype == "triangle":
+        tris = np.zeros((nc, 3), dtype=np.int32)
+        for m in re.finditer(r'<triangle index="(\d+)" v0="(\d+)" v1="(\d+)" v2="(\d+)"', txt):
+            tris[int(m.group(1))] = [int(m.group(k)) for k in (2, 3, 4)]
+        return (xyz[:, :2].copy() if gdim == 2 else xyz), tris
     tets = np.zeros((nc, 4), dtype=np.int32)
     for m in re.finditer(r'<tetrahedron index="(\d+)" v0="(\d+)" v1="(\d+)" v2="(\d+)" v3="(\d+)"', txt):
         tets[int(m.group(1))] = [int(m.group(k)) for k in (2, 3, 4, 5)]
     return xyz, tets
+
+
+def read_dolfin_markers(path):
+    """Cell markers from a DOLFIN XML <mesh_value_collection> / <mesh_function> file, as msh2xml writes them
+    (DmriFemLib.py:725-746: one <value cell_index=.. local_entity="0" value=..> per cell); phase = marker % 2."""
+    with _open_text(path) as f:
+        txt = f.read()
+    m = re.search(r'<mesh_value_collection[^>]*size="(\d+)"', txt)
+    vals = [(int(a), int(b)) for a, b in re.findall(r'<value cell_index="(\d+)"[^>]*value="(\d+)"', txt)]
+    if not vals:       # plain <mesh_function>: <entity index=.. value=..>
+        vals = [(int(a), int(b)) for a, b in re.findall(r'<entity index="(\d+)" value="(\d+)"', txt)]
+        m = re.search(r'<mesh_function[^>]*size="(\d+)"', txt)
+    n = int(m.group(1)) if m else (max(v[0] for v in vals) + 1)
+    out = np.zeros(n, dtype=np.int32)
+    for c, v in vals:
+        out[c] = v
+    return out
 
 
 def phase_from_submesh(xyz, tets, sub_xyz, sub_tets, decimals=9):

@@ -132,3 +132,62 @@ def test_sweep_sharding_covers_every_unit_once():
             bs = [units[u][1] for u in s]
             assert s == sorted(s) and all(bs.count(j) == 64 // world for j in range(4))
     assert sorted(u for r in range(3) for u in sweep.shard_balanced(7, 2, r, 3)) == list(range(14))   # ragged
+
+
+def test_readers_triangle_meshes_and_markers(tmp_path):
+    """gmsh v2 triangles (a 2-D mesh: dolfin-convert writes gdim 2), DOLFIN XML celltype triangle, and the cell
+    marker file msh2xml writes (DmriFemLib.py:725-746)."""
+    msh = tmp_path / "sq.msh"
+    msh.write_text("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n5\n1 0 0 0\n2 1 0 0\n3 1 1 0\n4 0 1 0\n5 9 9 0\n$EndNodes\n"
+                   "$Elements\n3\n1 1 2 7 7 1 2\n2 2 2 3 1 1 2 3\n3 2 2 4 2 1 3 4\n$EndElements\n")
+    xy, tris, mk = meshes.read_gmsh2(str(msh))
+    assert xy.shape == (4, 2) and tris.tolist() == [[0, 1, 2], [0, 2, 3]] and mk.tolist() == [3, 4]
+    xml = tmp_path / "sq.xml"
+    xml.write_text('<?xml version="1.0"?>\n<dolfin xmlns:dolfin="http://fenicsproject.org">\n'
+                   '  <mesh celltype="triangle" dim="2">\n    <vertices size="4">\n'
+                   '      <vertex index="0" x="0" y="0" />\n      <vertex index="1" x="1" y="0" />\n'
+                   '      <vertex index="2" x="1" y="1" />\n      <vertex index="3" x="0" y="1" />\n    </vertices>\n'
+                   '    <cells size="2">\n      <triangle index="0" v0="0" v1="1" v2="2" />\n'
+                   '      <triangle index="1" v0="0" v1="2" v2="3" />\n    </cells>\n  </mesh>\n</dolfin>\n')
+    xy2, tris2 = meshes.read_dolfin_xml(str(xml))
+    assert np.array_equal(xy2, xy) and np.array_equal(tris2, tris)
+    ops = orc.assemble(xy2, tris2, D=1.0)
+    assert abs(ops.lumped.sum() - 1.0) < 1e-15
+    pmk = tmp_path / "pmk_sq.xml"
+    pmk.write_text('<?xml version="1.0"?>\n<dolfin xmlns:dolfin="http://fenicsproject.org">\n  <mesh_function>\n'
+                   '    <mesh_value_collection type="uint" dim="2" size="2">\n'
+                   '      <value cell_index="0" local_entity="0" value="3" />\n'
+                   '      <value cell_index="1" local_entity="0" value="4" />\n'
+                   '    </mesh_value_collection>\n  </mesh_function>\n</dolfin>\n')
+    assert meshes.read_dolfin_markers(str(pmk)).tolist() == [3, 4]
+
+
+def test_planar_periodic_gather_matches_oracle():
+    """periodic.build_gather on a triangle mesh (boundary facets = edges) reproduces the oracle's independent
+    restatement of WeakPseudoPeriodic_*.eval on non-matching opposite faces, pdir = (1,1,0), two compartments."""
+    from dmri_fem_cloud_b200 import periodic
+    n = 6
+    xs, ys = np.linspace(-2, 2, n + 1), np.linspace(-1, 1.5, n + 1)
+    X, Y = np.meshgrid(xs, ys, indexing="ij")
+    xy = np.column_stack([X.ravel(), Y.ravel()])
+    idx = np.arange((n + 1) ** 2).reshape(n + 1, n + 1)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[1:, :-1].ravel(), idx[1:, 1:].ravel(), idx[:-1, 1:].ravel()
+    tris = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d], 1)])
+    on = np.abs(xy[:, 0] - 2) < 1e-9
+    inner = on & (np.abs(xy[:, 1] + 1) > 1e-9) & (np.abs(xy[:, 1] - 1.5) > 1e-9)
+    xy[inner, 1] += 0.07
+    xyz = orc.as_xyz3(xy)
+    lo, hi, hmin, _ = orc.domain_sizes(xyz, tris)
+    pdir = [1, 1, 0]
+    ph = (np.linalg.norm(xy[tris].mean(axis=1), axis=1) < 0.9).astype(np.int32)
+    ops = orc.assemble(xy, tris, ph, D=3e-3, kappa=1e-5, bnd_kappa_vertex=orc.periodic_marker(xyz, pdir, lo, hi, hmin))
+    q, F = 0.3, 2.0
+    g = np.array([0.6, 0.8, 0.0])
+    rng = np.random.default_rng(0)
+    u = rng.normal(size=ops.ndof) + 1j * rng.normal(size=ops.ndof)
+    want = orc.periodic_term(xyz, tris, ops, pdir, lo, hi, q, g, 0.5)(u, F)
+    dof, src, w, dx = periodic.build_gather(xy, tris, ph, pdir, lo, hi, ops.dof_vertex, ops.dof_comp)
+    ubc = np.zeros(ops.ndof, complex)
+    ubc[dof] = (np.where(src >= 0, u[np.maximum(src, 0)], 0) * w).sum(axis=1) * np.exp(1j * q * (dx @ g) * F)
+    got = 0.5 * (ops.B @ ubc)
+    assert np.abs(want).max() > 1e-4 and np.abs(got - want).max() <= 1e-15
