@@ -143,3 +143,29 @@ def test_config3_layered_variable_kappa_T2_ogse(tmp_path, monkeypatch):
     assert abs(sim.stats["signal"] - ref["signal"]) <= 1e-8 * abs(ref["signal"])
     assert abs(sim.stats["signal_comp"][1] - float(ops.lumped[ops.dof_comp == 1] @ ref["u"].real[ops.dof_comp == 1])) \
         <= 1e-8 * abs(ref["signal"])
+
+
+def test_lu_solver_stand_in(tmp_path, monkeypatch):
+    """`linsolver = PETScLUSolver("mumps")` (ConvergenceTest.ipynb / T2_Relaxation.ipynb cell 10): the stand-in
+    (BiCGStab to rounding level) reproduces the exact discrete solve of the oracle (sparse LU) to 1e-10."""
+    monkeypatch.chdir(tmp_path)
+    xyz, tets = meshes.box_mesh((-2.5,) * 3, (2.5,) * 3, 6, 6, 6)
+    mesh = dl.Mesh(xyz, tets)
+    mp = dl.MRI_parameters()
+    mp.bvalue = 1000
+    _pgse(mp, 1000.0, 3000.0)
+    mp.set_gradient_dir(mesh, 0, 0, 1)
+    mp.Apply()
+    sim = dl.MRI_simulation()
+    sim.k = 100
+    md = dl.MyDomain(mesh, mp)
+    md.Apply()
+    md.D0 = 2e-3
+    md.D = md.D0
+    sim.solve(md, mp, dl.PETScLUSolver("mumps"))
+    dl.PostProcessing(md, mp, sim, None, '')
+    ops = orc.assemble(xyz, tets, D=2e-3, invT2=1e-16)
+    seq = orc.pgse(1000.0, 3000.0)
+    ref = orc.theta_solve(ops, seq, seq.q_from_b(1000.0), [0, 0, 1], 100.0, solver="lu")
+    assert abs(sim.stats["signal"] - ref["signal"]) <= 1e-10 * abs(ref["signal"])
+    assert dl.LUSolver is dl.PETScLUSolver
