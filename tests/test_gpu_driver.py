@@ -169,3 +169,67 @@ def test_lu_solver_stand_in(tmp_path, monkeypatch):
     ref = orc.theta_solve(ops, seq, seq.q_from_b(1000.0), [0, 0, 1], 100.0, solver="lu")
     assert abs(sim.stats["signal"] - ref["signal"]) <= 1e-10 * abs(ref["signal"])
     assert dl.LUSolver is dl.PETScLUSolver
+
+
+def test_comri_drivers_match_oracle(tmp_path, monkeypatch):
+    """The comri mains on libbtfem (comri.py): f(t_n) on both sides, FT closed at Delta+delta, s/s0 -- against the
+    oracle in the same variant (rhs_uses_current_f), on the reference's own cylinder / torus meshes."""
+    import io
+    from conftest import GOLDEN
+    from dmri_fem_cloud_b200 import comri
+    fix = np.load(os.path.join(GOLDEN, "fixture_meshes.npz"))
+    monkeypatch.setattr(comri, "KRYLOV", {"rtol": 1e-11, "atol": 1e-16, "maxit": 100000})
+
+    class Seq:                                   # FT of the C++ drivers as an oracle sequence
+        def __init__(self, delta, Delta):
+            self.delta, self.Delta, self.T = delta, Delta, delta + Delta
+
+        def f(self, t):
+            return comri.FT(t, self.delta, self.Delta)
+
+        def F(self, t):
+            return 0.0
+
+    # one-comp: -m cyl12 -b 1000 -d 2000 -D 6000 -k 200 -v 1 0 0 -K 3e-3
+    xyz, tets = fix["cyl12_r_3E_6_vol_xyz"], fix["cyl12_r_3E_6_vol_tets"]
+    p = comri.parse("one-comp", ["demo", "-b", "1000", "-d", "2000", "-D", "6000", "-k", "200", "-v", "1", "0", "0",
+                                 "-K", "3e-3"])
+    p["mesh"] = (xyz, tets)
+    buf = io.StringIO()
+    r = comri.run("one-comp", p, out=buf)
+    ops = orc.assemble(xyz, tets, D=3e-3)
+    ref = orc.theta_solve(ops, Seq(2000.0, 6000.0), r["gnorm"], [1, 0, 0], 200.0, solver="lu", rhs_uses_current_f=True)
+    assert len(r["ts"]) == ref["n_steps"] == 41
+    assert abs(r["gnorm"] - np.sqrt(1000.0) / np.sqrt(2000.0 ** 2 * (6000.0 - 2000.0 / 3))) <= 1e-18
+    assert abs(r["s"] - ref["signal"] / ref["voi"]) <= 1e-8 * r["s"]
+    assert ("b: %f, gnorm: %f, q: %f, gdir: (%f, %f, %f), s: %f" % (1000.0, r["gnorm"], r["qvalue"], 1, 0, 0, r["s"])) \
+        in buf.getvalue()
+    # lagging the right-hand side (DmriFemLib) gives a different number: the variant matters
+    lag = orc.theta_solve(ops, Seq(2000.0, 6000.0), r["gnorm"], [1, 0, 0], 200.0, solver="lu")
+    assert abs(lag["signal"] - ref["signal"]) > 1e-6 * abs(ref["signal"])
+
+    # two-comp with the compartment given as a sub-mesh (-c): multi_layer_torus + its compt1 cells
+    xyz, tets, phase = fix["torus_xyz"], fix["torus_tets"], fix["torus_phase"]
+    sub_cells = tets[phase == 1]
+    used = np.unique(sub_cells)
+    remap = -np.ones(len(xyz), dtype=np.int64)
+    remap[used] = np.arange(len(used))
+    p = comri.parse("two-comp", ["demo", "-b", "1000", "-d", "2000", "-D", "6000", "-N", "20", "-v", "0", "1", "0",
+                                 "-p", "1e-5"])
+    p["mesh"], p["cell"] = (xyz, tets), (xyz[used], remap[sub_cells].astype(np.int32))
+    r = comri.run("two-comp", p, out=io.StringIO())
+    assert np.array_equal(r["phase"], phase) and r["dt"] == 400.0
+    ops = orc.assemble(xyz, tets, phase, D=3e-3, kappa=1e-5)
+    ref = orc.theta_solve(ops, Seq(2000.0, 6000.0), r["gnorm"], [0, 1, 0], 400.0, solver="lu", rhs_uses_current_f=True)
+    assert abs(r["s"] - ref["signal"] / ref["voi"]) <= 1e-8 * r["s"]
+
+    # multilayer: torus shells by formula, loop t < T, no preconditioner
+    p = comri.parse("multilayer", ["demo", "-b", "500", "-d", "1000", "-D", "3000", "-N", "16"])
+    p["mesh"] = (xyz, tets)
+    r = comri.run("multilayer", p, out=io.StringIO())
+    assert len(r["ts"]) == 16 and set(np.unique(r["phase"])) == {0, 1}
+    ops = orc.assemble(xyz, tets, r["phase"], D=3e-3, kappa=5e-5)
+    ref = orc.theta_solve(ops, Seq(1000.0, 3000.0), r["gnorm"], [0, 0, 1], 250.0, solver="lu", closed=False,
+                          rhs_uses_current_f=True)
+    assert ref["n_steps"] == 16
+    assert abs(r["s"] - ref["signal"] / ref["voi"]) <= 1e-8 * r["s"]

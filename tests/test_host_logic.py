@@ -191,3 +191,28 @@ def test_planar_periodic_gather_matches_oracle():
     ubc[dof] = (np.where(src >= 0, u[np.maximum(src, 0)], 0) * w).sum(axis=1) * np.exp(1j * q * (dx @ g) * F)
     got = 0.5 * (ops.B @ ubc)
     assert np.abs(want).max() > 1e-4 and np.abs(got - want).max() <= 1e-15
+
+
+def test_comri_cli_parsing_and_scheme_quirks():
+    """comri drivers (comri/*/hpc-fenics-cpp/main.cpp): flags, defaults, gnorm/qvalue, FT closed at Delta+delta,
+    loop `t < T + dt` vs `t < T`, shell phases."""
+    from dmri_fem_cloud_b200 import comri
+    p = comri.parse("one-comp", ["demo", "-m", "cyl.xml", "-b", "1000", "-d", "10600", "-D", "43100", "-k", "200",
+                                 "-v", "2", "0", "0", "-K", "3e-3", "-N", "50", "-j", "10"])
+    assert (p["mesh"], p["b"], p["delta"], p["Delta"], p["dt"], p["is_dt"], p["K"], p["N"], p["nskip"]) == \
+        ("cyl.xml", 1000.0, 10600.0, 43100.0, 200.0, True, 3e-3, 50, 10)
+    assert p["g"] == (1.0, 0.0, 0.0)                                   # normalised (main.cpp:176-177)
+    d = comri.parse("one-comp", ["demo"])
+    assert (d["b"], d["delta"], d["Delta"], d["K"], d["g"], d["is_dt"]) == (1000.0, 40000.0, 40000.0, 2.4e-3,
+                                                                           (0.0, 1.0, 0.0), False)
+    t2 = comri.parse("two-comp", ["demo", "-c", "cell.xml", "-p", "1e-5"])
+    assert (t2["cell"], t2["kappa"], t2["b"], t2["K"]) == ("cell.xml", 1e-5, 4000.0, 3e-3)
+    ml = comri.parse("multilayer", ["demo", "-k", "5", "-v", "1", "0", "0", "-p", "9"])
+    assert (ml["is_dt"], ml["g"], ml["kappa"]) == (False, (0.0, 0.0, 1.0), 5e-5)     # those flags do not exist there
+    assert comri.FT(0.0, 10.0, 30.0) == 1.0 and comri.FT(10.0, 10.0, 30.0) == 0.0
+    assert comri.FT(30.0, 10.0, 30.0) == -1.0 and comri.FT(40.0, 10.0, 30.0) == -1.0      # `t <= Delta + delta`
+    assert len(comri.time_grid(40.0, 10.0, "one-comp")) == 5 and len(comri.time_grid(40.0, 10.0, "multilayer")) == 4
+    mid = np.array([[0.5, 0, 0], [1.2, 0, 0], [1.7, 0, 0], [3.0, 0, 0]])
+    assert comri.shell_phase(mid, "two-comp").tolist() == [0, 1, 0, 0]
+    mid = np.array([[20.0, 0, 0], [26.0, 0, 0], [28.0, 0, 0], [40.0, 0, 0]])
+    assert comri.shell_phase(mid, "multilayer").tolist() == [0, 1, 0, 0]
