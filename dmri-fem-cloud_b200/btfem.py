@@ -61,6 +61,7 @@ def load_library(path=None):
         "btfem_version": (C.c_int, []),
         "btfem_set_mesh": (C.c_int, [H, C.c_int64, _c_double_p, C.c_int64, _c_int32_p, _c_int32_p]),
         "btfem_set_mesh_tri": (C.c_int, [H, C.c_int64, _c_double_p, C.c_int64, _c_int32_p, _c_int32_p]),
+        "btfem_set_mesh_seg": (C.c_int, [H, C.c_int64, _c_double_p, C.c_int64, _c_int32_p]),
         "btfem_set_phase": (C.c_int, [H, _c_int32_p]),
         "btfem_get_mesh_stats": (C.c_int, [H, _c_double_p, _c_double_p]),
         "btfem_set_diffusion": (C.c_int, [H, C.c_int, _c_double_p]),
@@ -144,7 +145,7 @@ class BTFem:
 
     # ---- problem definition
     def set_mesh(self, xyz, tets, phase=None):
-        """tets: (nc,4) tetrahedra or (nc,3) triangles; xyz: (nv,3), or (nv,2) for a gdim-2 mesh (z = 0)."""
+        """tets: (nc,4) tetrahedra, (nc,3) triangles or (nc,2) segments; xyz: (nv,3), or (nv,2) for a gdim-2 mesh."""
         xyz = np.asarray(xyz, dtype=np.float64)
         if xyz.ndim != 2 or xyz.shape[1] not in (2, 3):
             raise ValueError("xyz must be (nv,3) or (nv,2)")
@@ -152,14 +153,19 @@ class BTFem:
             xyz = np.hstack([xyz, np.zeros((len(xyz), 1))])
         xyz = np.ascontiguousarray(xyz)
         tets = np.ascontiguousarray(tets, dtype=np.int32)
-        if tets.ndim != 2 or tets.shape[1] not in (3, 4):
-            raise ValueError("cells must be (nc,4) tetrahedra or (nc,3) triangles")
+        if tets.ndim != 2 or tets.shape[1] not in (2, 3, 4):
+            raise ValueError("cells must be (nc,4) tetrahedra, (nc,3) triangles or (nc,2) segments")
+        if tets.shape[1] == 2 and phase is not None:
+            raise ValueError("segment meshes are one-compartment")
         ph = None if phase is None else np.ascontiguousarray(phase, dtype=np.int32)
         self.nv, self.nc = len(xyz), len(tets)
         self.two_comp = ph is not None
         self.cell_nv = tets.shape[1]
-        fn = self.lib.btfem_set_mesh if self.cell_nv == 4 else self.lib.btfem_set_mesh_tri
-        self._ck(fn(self.h, self.nv, _dp(xyz), self.nc, _ip(tets), None if ph is None else _ip(ph)))
+        if self.cell_nv == 2:
+            self._ck(self.lib.btfem_set_mesh_seg(self.h, self.nv, _dp(xyz), self.nc, _ip(tets)))
+        else:
+            fn = self.lib.btfem_set_mesh if self.cell_nv == 4 else self.lib.btfem_set_mesh_tri
+            self._ck(fn(self.h, self.nv, _dp(xyz), self.nc, _ip(tets), None if ph is None else _ip(ph)))
         self.h2d_bytes = xyz.nbytes + tets.nbytes + (0 if ph is None else ph.nbytes)
 
     def set_phase(self, phase=None):

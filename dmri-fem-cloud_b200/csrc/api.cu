@@ -82,7 +82,7 @@ static void set_mesh_cells(btfem_t* h, int64_t nv, const double* xyz, int64_t nc
   h->cell_nv = cell_nv;
   h->two_comp = phase != nullptr;
   h->h_xyz.assign(xyz, xyz + 3 * nv);
-  h->h_tets.assign(4 * nc, -1);   // triangles keep the 4-slot cell layout, 4th slot = -1
+  h->h_tets.assign(4 * nc, -1);   // triangles / segments keep the 4-slot cell layout, unused slots = -1
   for (int64_t c = 0; c < nc; ++c)
     for (int k = 0; k < cell_nv; ++k) h->h_tets[4 * c + k] = cells[cell_nv * c + k];
   if (phase) h->h_phase.assign(phase, phase + nc); else h->h_phase.clear();
@@ -101,9 +101,14 @@ int btfem_set_mesh_tri(btfem_t* h, int64_t nv, const double* xyz, int64_t nc, co
   return guarded(h, [&] { set_mesh_cells(h, nv, xyz, nc, tris, 3, phase); });
 }
 
+int btfem_set_mesh_seg(btfem_t* h, int64_t nv, const double* xyz, int64_t nc, const int32_t* segs) {
+  return guarded(h, [&] { set_mesh_cells(h, nv, xyz, nc, segs, 2, nullptr); });
+}
+
 int btfem_set_phase(btfem_t* h, const int32_t* phase) {
   return guarded(h, [&] {
     BT_REQUIRE(h->nc > 0, "set the mesh first");
+    BT_REQUIRE(!phase || h->cell_nv > 2, "segment meshes are one-compartment");
     if (phase)
       for (int64_t i = 0; i < h->nc; ++i) BT_REQUIRE(phase[i] == 0 || phase[i] == 1, "phase must be 0 or 1");
     invalidate(h);

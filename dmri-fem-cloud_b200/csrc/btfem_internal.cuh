@@ -171,7 +171,7 @@ struct btfem {
 
   // ---- inputs (host copies are kept: they are small next to the matrices and make setters order-free)
   int64_t nv = 0, nc = 0;
-  int cell_nv = 4;   // vertices per cell: 4 tetrahedra, 3 triangles (stored in 4 slots, the 4th = -1)
+  int cell_nv = 4;   // vertices per cell: 4 tetrahedra, 3 triangles, 2 segments (stored in 4 slots, unused = -1)
   bool two_comp = false;
   std::vector<double> h_xyz;
   std::vector<int32_t> h_tets, h_phase;

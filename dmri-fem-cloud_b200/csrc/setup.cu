@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(TPB) k_cell_sizes(int64_t nc, int cell_nv, con
   double lo = 1e300, hi = 0.0;
   for (int64_t c = blockIdx.x * (int64_t)TPB + threadIdx.x; c < nc; c += (int64_t)gridDim.x * TPB) {
     int4 t = *reinterpret_cast<const int4*>(tets + 4 * c);
-    int v[4] = {t.x, t.y, t.z, cell_nv == 4 ? t.w : t.x};   // triangle: the 4th slot repeats a vertex (adds no edge)
+    // triangle / segment: the unused slots repeat a vertex (add no edge)
+    int v[4] = {t.x, t.y, cell_nv >= 3 ? t.z : t.x, cell_nv == 4 ? t.w : t.x};
     double x[4][3];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -336,7 +337,55 @@ __global__ void __launch_bounds__(TPB) k_assemble(AsmArgs a) {
   double m = 0, s = 0, r = 0, jx = 0, jy = 0, jz = 0, ii = 0, bb = 0;
   for (int64_t q = a.seg[p]; q < a.seg[p + 1]; ++q) {
     uint32_t sid = a.src[q];
-    if (sid < a.ncell16 && a.cell_nv == 3) {
+    if (sid < a.ncell16 && a.cell_nv == 2) {
+      // P1 segment in 3-D: e = x1 - x0, |T| = |e|, grad l1 = e/|e|^2 = -grad l0; int phi_i phi_j = |T|(1+d_ij)/6,
+      // int x phi_i phi_j = |T| w_ij / 24.  Slots 2, 3 of the 16-per-cell list do not exist: zero.
+      uint32_t t = sid >> 4;
+      int i = (sid >> 2) & 3, j = sid & 3;
+      if (i >= 2 || j >= 2) continue;
+      const int v0 = a.tets[4 * (int64_t)t], v1 = a.tets[4 * (int64_t)t + 1];
+      double x[2][3], e[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        x[0][d] = a.xyz[3 * (int64_t)v0 + d];
+        x[1][d] = a.xyz[3 * (int64_t)v1 + d];
+        e[d] = x[1][d] - x[0][d];
+      }
+      double l2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+      double len = sqrt(l2);
+      double inv = 1.0 / l2;
+      double g1[3] = {e[0] * inv, e[1] * inv, e[2] * inv};
+      double si = i == 1 ? 1.0 : -1.0, sj = j == 1 ? 1.0 : -1.0;
+      double gj[3] = {sj * g1[0], sj * g1[1], sj * g1[2]};
+      double dg[3];
+      if (a.dkind == 0) {
+        double d0 = a.D[0];
+        dg[0] = d0 * gj[0]; dg[1] = d0 * gj[1]; dg[2] = d0 * gj[2];
+      } else if (a.dkind == 1) {
+        double d0 = a.D[t];
+        dg[0] = d0 * gj[0]; dg[1] = d0 * gj[1]; dg[2] = d0 * gj[2];
+      } else {
+        const double* Dt = a.D + 9 * (int64_t)t;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) dg[d] = Dt[3 * d] * gj[0] + Dt[3 * d + 1] * gj[1] + Dt[3 * d + 2] * gj[2];
+      }
+      double mij = len * (i == j ? 2.0 : 1.0) / 6.0;
+      m += mij;
+      s += len * si * (g1[0] * dg[0] + g1[1] * dg[1] + g1[2] * dg[2]);
+      r += (a.t2kind == 0 ? a.invT2[0] : a.invT2[t]) * mij;
+      double sx[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) sx[d] = x[0][d] + x[1][d];
+      if (i == j) {
+        jx += len * (2.0 * sx[0] + 4.0 * x[i][0]) / 24.0;
+        jy += len * (2.0 * sx[1] + 4.0 * x[i][1]) / 24.0;
+        jz += len * (2.0 * sx[2] + 4.0 * x[i][2]) / 24.0;
+      } else {
+        jx += len * (sx[0] + x[i][0] + x[j][0]) / 24.0;
+        jy += len * (sx[1] + x[i][1] + x[j][1]) / 24.0;
+        jz += len * (sx[2] + x[i][2] + x[j][2]) / 24.0;
+      }
+    } else if (sid < a.ncell16 && a.cell_nv == 3) {
       // P1 triangle, possibly embedded in 3-D: n = e1 x e2, |T| = |n|/2, grad l1 = (e2 x n)/|n|^2,
       // grad l2 = (n x e1)/|n|^2, grad l0 = -(grad l1 + grad l2);  int phi_i phi_j = |T|(1+d_ij)/12,
       // int x phi_i phi_j = |T| w_ij / 60.  Slots (i,3), (3,j) of the 16-per-cell list do not exist: zero.
@@ -581,6 +630,7 @@ void bt_build_facets(btfem* h) {
   h->n_iface = 0;
   h->n_bfacet = 0;
   if (!h->two_comp && !h->periodic) return;
+  BT_REQUIRE(h->cell_nv >= 3, "segment meshes: one compartment, no periodic BC");
   cudaStream_t st = h->stream;
   const int64_t nf = 4 * h->nc;
   // periodic marker kappa_e^h per vertex (DmriFemLib.py:601-610): kappa_e where the vertex lies within

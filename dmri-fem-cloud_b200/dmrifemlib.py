@@ -38,8 +38,8 @@ class Mesh:
     def __init__(self, xyz, tets):
         self.xyz = np.ascontiguousarray(xyz, dtype=np.float64)
         self.tets = np.ascontiguousarray(tets, dtype=np.int32)
-        if self.tets.ndim != 2 or self.tets.shape[1] not in (3, 4):
-            raise RuntimeError("cells must be tetrahedra (nc,4) or triangles (nc,3)")
+        if self.tets.ndim != 2 or self.tets.shape[1] not in (2, 3, 4):
+            raise RuntimeError("cells must be tetrahedra (nc,4), triangles (nc,3) or segments (nc,2)")
         if self.xyz.ndim != 2 or self.xyz.shape[1] not in (2, 3) or self.xyz.shape[1] < self.tets.shape[1] - 1:
             raise RuntimeError("coordinates must be (nv,2) or (nv,3) and gdim >= tdim")
 
@@ -292,8 +292,8 @@ class MyDomain():
         if self.gdim == 2:
             self.PeriodicDir = [self.PeriodicDir[0], self.PeriodicDir[1], 0]     # no z faces (DmriFemLib.py:602-605)
         if sum(self.PeriodicDir) > 0:
-            if self.tdim == 2 and self.gdim == 3:
-                raise NotImplementedError("weak pseudo-periodic BC on a surface mesh in 3-D")
+            if self.tdim < self.gdim:
+                raise NotImplementedError("weak pseudo-periodic BC on a manifold mesh (curve or surface in 3-D)")
             fem.set_periodic(self.PeriodicDir, self.kappa_e_scalar, self.tol,
                              [self.xmin, self.ymin, self.zmin], [self.xmax, self.ymax, self.zmax])
         fem.set_initial(ic)

@@ -70,7 +70,7 @@ def read_gmsh2(path):
 
 
 def read_dolfin_xml(path):
-    """Read a DOLFIN XML mesh (optionally zipped): celltype tetrahedron, or triangle (dim 2 or 3)."""
+    """Read a DOLFIN XML mesh (optionally zipped): celltype tetrahedron, triangle (dim 2 or 3) or interval."""
     with _open_text(path) as f:
         txt = f.read()
     nv = int(re.search(r'<vertices size="(\d+)"', txt).group(1))
@@ -80,6 +80,11 @@ def read_dolfin_xml(path):
     xyz = np.zeros((nv, 3))
     for m in re.finditer(r'<vertex index="(\d+)" x="([^"]+)" y="([^"]+)"(?: z="([^"]+)")?', txt):
         xyz[int(m.group(1))] = (float(m.group(2)), float(m.group(3)), float(m.group(4) or 0.0))
+    if celltype == "interval":      # curve in 3-D (neuron skeleton, Manifolds.ipynb)
+        segs = np.zeros((nc, 2), dtype=np.int32)
+        for m in re.finditer(r'<interval index="(\d+)" v0="(\d+)" v1="(\d+)"', txt):
+            segs[int(m.group(1))] = [int(m.group(2)), int(m.group(3))]
+        return (xyz[:, :gdim].copy() if gdim < 3 else xyz), segs
     if celltype == "triangle":
         tris = np.zeros((nc, 3), dtype=np.int32)
         for m in re.finditer(r'<triangle index="(\d+)" v0="(\d+)" v1="(\d+)" v2="(\d+)"', txt):

@@ -69,6 +69,11 @@ int btfem_set_mesh(btfem_t* h, int64_t nv, const double* xyz /*[nv*3]*/, int64_t
 int btfem_set_mesh_tri(btfem_t* h, int64_t nv, const double* xyz /*[nv*3]*/, int64_t nc,
                        const int32_t* tris /*[nc*3]*/, const int32_t* phase /*[nc] or NULL*/);
 
+/* Curves in 3-D (neuron skeletons: Manifolds.ipynb runs `fru_M_100383_1D.xml`, tdim 1, gdim 3): P1 segments,
+ * a vertex may join any number of them (branch points).  One compartment, Neumann ends. */
+int btfem_set_mesh_seg(btfem_t* h, int64_t nv, const double* xyz /*[nv*3]*/, int64_t nc,
+                       const int32_t* segs /*[nc*2]*/);
+
 /* Replace only the phase function of the current mesh (NULL = one compartment). */
 int btfem_set_phase(btfem_t* h, const int32_t* phase /*[nc] or NULL*/);
 /* mesh.hmin()/hmax() as used by MyDomain (DmriFemLib.py:588-589): min / max over cells of the cell size,

@@ -68,6 +68,17 @@ def tri_geometry(xyz, tris):
     return 0.5 * np.sqrt(n2), g
 
 
+def seg_geometry(xyz, segs):
+    """Length and P1 gradients (nc,2,3) of segments embedded in R^3 (neuron skeletons, Manifolds.ipynb: tdim 1,
+    gdim 3): grad l1 = e/|e|^2, grad l0 = -grad l1."""
+    e = xyz[segs[:, 1]] - xyz[segs[:, 0]]
+    l2 = (e * e).sum(axis=1)
+    g = np.empty((len(segs), 2, 3))
+    g[:, 1] = e / l2[:, None]
+    g[:, 0] = -g[:, 1]
+    return np.sqrt(l2), g
+
+
 def as_xyz3(xyz):
     """Coordinates as (nv,3): gdim-2 meshes get z = 0 (GdotX then reduces to x*g0 + y*g1, DmriFemLib.py:33-39)."""
     xyz = np.asarray(xyz, dtype=float)
@@ -82,7 +93,8 @@ def element_matrices(xyz, tets, D=1.0, invT2=0.0):
     D: scalar, (nc,) per-cell scalar, or (nc,3,3) / (3,3) tensor (DmriFemLib.py:611-616).
     invT2: scalar or (nc,) per-cell 1/T2 (DmriFemLib.py:43-44).
     Returns dict of (nc,n,n) arrays M,S,R,Jx,Jy,Jz and vol (nc,), n = vertices per cell: 4 (tetrahedra) or
-    3 (triangles: 2-D meshes and surfaces in 3-D, DmriFemLib.py:34-38,591-592).  On a d-simplex
+    3 (triangles: 2-D meshes and surfaces in 3-D, DmriFemLib.py:34-38,591-592) or 2 (segments: curves in 3-D,
+    Manifolds.ipynb).  On a d-simplex
     int phi_i phi_j = |T|(1+d_ij)/((d+1)(d+2)) and int x phi_i phi_j = |T| w_ij/((d+1)(d+2)(d+3)),
     w_ij = sum_k x_k + x_i + x_j (i != j), 2 sum_k x_k + 4 x_i (i == j).
     """
@@ -91,8 +103,10 @@ def element_matrices(xyz, tets, D=1.0, invT2=0.0):
     d = nvc - 1
     if nvc == 4:
         _, vol, g = tet_geometry(xyz, tets)
-    else:
+    elif nvc == 3:
         vol, g = tri_geometry(xyz, tets)
+    else:
+        vol, g = seg_geometry(xyz, tets)
     I4 = np.eye(nvc)
     M = vol[:, None, None] * (1.0 + I4)[None] / float((d + 1) * (d + 2))
     D = np.asarray(D, dtype=float)
@@ -235,8 +249,10 @@ def assemble(xyz, tets, phase=None, D=1.0, invT2=0.0, kappa=0.0, kappa_facet=Non
     xyz = as_xyz3(xyz)
     tets = np.asarray(tets)
     nv = len(xyz)
-    nvc = tets.shape[1]                 # 4: tetrahedra, 3: triangles
+    nvc = tets.shape[1]                 # 4: tetrahedra, 3: triangles, 2: segments
     nvf = nvc - 1                       # vertices per facet
+    if nvc == 2 and (phase is not None or bnd_kappa_vertex is not None):
+        raise ValueError("segment meshes: one compartment, Neumann ends")
     cell_dofs, ndof, dv, dc, vc2dof = dof_map(nv, tets, phase)
     em = element_matrices(xyz, tets, D, invT2)
     rows = np.repeat(cell_dofs, nvc, axis=1).ravel()

@@ -222,3 +222,51 @@ def test_triangle_meshes_refuse_row_partitions():
         fem.set_mesh(xy, tris)
         with pytest.raises(btfem.BTFemError):
             fem.set_partition(5, 3)
+
+
+def test_segment_mesh_in_3d(tmp_path, monkeypatch):
+    """Curves in 3-D (the neuron skeleton of Manifolds.ipynb: tdim 1, gdim 3) through btfem_set_mesh_seg and through
+    the driver: pattern bit-exact (branch points included), values 1e-12, signal 1e-8 against the oracle."""
+    from test_oracle_2d import _tree
+    monkeypatch.chdir(tmp_path)
+    xyz, segs = _tree(seed=9, nseg=300)
+    ops = orc.assemble(xyz, segs, D=3e-3, invT2=1e-5)
+    with btfem.BTFem(0) as fem:
+        fem.set_mesh(xyz, segs)
+        fem.set_diffusion(3e-3)
+        fem.set_relaxation(1e-5)
+        fem.assemble()
+        rp, ci = fem.pattern()
+        rps, cis = orc.scalar_pattern(len(xyz), segs)
+        assert np.array_equal(rp, rps) and np.array_equal(ci, cis)
+        for name in ("M", "S", "R", "Jx", "Jy", "Jz"):
+            assert _relmax(fem.values(name), getattr(ops, name).data) <= 1e-12, name
+        assert np.max(np.abs(fem.values("I"))) == 0
+        hmin, hmax = fem.mesh_stats()
+        L = np.linalg.norm(xyz[segs[:, 1]] - xyz[segs[:, 0]], axis=1)
+        assert abs(hmin - L.min()) <= 1e-14 * L.min() and abs(hmax - L.max()) <= 1e-14 * L.max()
+        with pytest.raises(btfem.BTFemError):
+            fem.set_phase(np.zeros(len(segs), dtype=np.int32))
+    mesh = dl.Mesh(xyz, segs)
+    assert (mesh.geometry().dim(), mesh.topology().dim()) == (3, 1)
+    mp = dl.MRI_parameters()
+    mp.bvalue = 2000
+    mp.delta, mp.Delta = 2000.0, 6000.0
+    mp.T = mp.delta + mp.Delta
+    mp.fs_sym = sp.Piecewise((1., mp.s < mp.delta), (0., mp.s < mp.Delta), (-1., mp.s < mp.T), (0., True))
+    mp.set_gradient_dir(mesh, 1, 1, 1)
+    mp.T2 = 1e5
+    mp.Apply()
+    sim = dl.MRI_simulation()
+    sim.k = 200
+    md = dl.MyDomain(mesh, mp)
+    md.Apply()
+    md.D0 = 3e-3
+    md.D = md.D0
+    ls = dl.KrylovSolver("bicgstab", "jacobi")
+    ls.parameters["relative_tolerance"] = 1e-13
+    ls.parameters["absolute_tolerance"] = 1e-16
+    sim.solve(md, mp, ls)
+    seq = orc.pgse(2000.0, 6000.0)
+    ref = orc.theta_solve(ops, seq, mp.qvalue, [1, 1, 1], 200.0, solver="lu")
+    assert abs(sim.stats["signal"] - ref["signal"]) <= 1e-8 * abs(ref["signal"])

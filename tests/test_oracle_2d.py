@@ -134,3 +134,57 @@ def test_planar_weak_periodic_term():
     h = 4.0 / n
     want = 0.5 * ke * (2 * 4.0 + 4 * h / 3.0) * np.cos(q * 4.0 * F)
     assert abs(t.sum() - want) <= 1e-12 * abs(want)
+
+
+def _tree(seed=4, nseg=40):
+    """A branching curve in 3-D: random walk with side branches (vertices joining three segments)."""
+    rng = np.random.default_rng(seed)
+    pts, segs = [np.zeros(3)], []
+    tips = [0]
+    while len(segs) < nseg:
+        t = tips[rng.integers(len(tips))]
+        step = rng.normal(size=3)
+        pts.append(pts[t] + (0.5 + rng.random()) * step / np.linalg.norm(step))
+        segs.append([t, len(pts) - 1])
+        tips.append(len(pts) - 1)
+    return np.array(pts), np.array(segs, dtype=np.int32)
+
+
+def test_segment_closed_forms_and_slab_limit():
+    """Curves in 3-D (Manifolds.ipynb, tdim 1 / gdim 3).  Closed forms against Gauss quadrature on random segments;
+    a straight interval of length 5 along g reproduces the analytic slab signal quoted in ConvergenceTest.ipynb
+    (0.84389487095614 for D=2e-3, delta=1000, Delta=10000, b=1000) with O(h^2 + dt^2) convergence."""
+    xyz, segs = _tree()
+    D = np.array([[2.0, 0.3, 0.1], [0.3, 1.0, 0.2], [0.1, 0.2, 1.5]]) * 1e-3
+    em = orc.element_matrices(xyz, segs, D=D)
+    gp = 0.5 + np.array([-1, 0, 1]) * np.sqrt(0.6) / 2          # 3-point Gauss on [0,1]: exact to degree 5
+    gw = np.array([5, 8, 5]) / 18.0
+    for c, (a, b) in enumerate(segs):
+        e = xyz[b] - xyz[a]
+        L = np.linalg.norm(e)
+        M = np.zeros((2, 2))
+        J = np.zeros((3, 2, 2))
+        for s_, w in zip(gp, gw):
+            lam = np.array([1 - s_, s_])
+            M += w * L * np.outer(lam, lam)
+            for d in range(3):
+                J[d] += w * L * (xyz[a] + s_ * e)[d] * np.outer(lam, lam)
+        t = e / L
+        S = (t @ D @ t) / L * np.array([[1.0, -1.0], [-1.0, 1.0]])
+        assert np.allclose(em["M"][c], M, rtol=1e-13) and np.allclose(em["S"][c], S, rtol=1e-12)
+        for d, name in enumerate(("Jx", "Jy", "Jz")):
+            assert np.allclose(em[name][c], J[d], rtol=1e-12, atol=1e-15)
+    ops = orc.assemble(xyz, segs, D=3e-3)
+    rp, ci = orc.scalar_pattern(len(xyz), segs)
+    assert np.array_equal(rp, ops.rowptr) and np.array_equal(ci, ops.colidx)
+    assert (np.diff(rp) == 4).any()                                  # a branch point: itself + three neighbours
+    err = []
+    for n, k in ((50, 10.0), (100, 5.0)):
+        z = np.linspace(-2.5, 2.5, n + 1)
+        line = np.column_stack([0 * z, 0 * z, z])
+        cells = np.column_stack([np.arange(n), np.arange(1, n + 1)])
+        seq = orc.pgse(1000.0, 10000.0)
+        r = orc.theta_solve(orc.assemble(line, cells, D=2e-3), seq, seq.q_from_b(1000.0), [0, 0, 1], k, solver="lu",
+                            closed=False)
+        err.append(abs(r["signal"] / r["voi"] - 0.84389487095614))
+    assert err[1] < 5e-6 and 3.5 < err[0] / err[1] < 4.5
