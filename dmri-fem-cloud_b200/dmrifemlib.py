@@ -180,13 +180,29 @@ class MRI_parameters():
 
 
 class KrylovSolver:
-    """dolfin.KrylovSolver(method, preconditioner) as a parameter holder; DOLFIN's defaults."""
+    """dolfin.KrylovSolver(method, preconditioner) as a parameter holder; DOLFIN's defaults.
 
-    def __init__(self, method="bicgstab", preconditioner="jacobi"):
+    libbtfem implements BiCGStab and GMRES(m) with Jacobi or no preconditioner (the CLI's choice,
+    GCloudDmriSolver.py:218).  The notebooks also pass `KrylovSolver("bicgstab")` (PETSc's default PC, ILU(0) in
+    serial) and `KrylovSolver("bicgstab", "petsc_amg")` (ECS_226Cylinders.ipynb, RealNeurons.ipynb cell 10): a
+    preconditioner changes how fast the Krylov iteration reaches the tolerance, not what it converges to, so
+    those names are accepted and run with Jacobi -- `requested_preconditioner` keeps what was asked for and a
+    note is printed once.  Iteration counts (not converged signals) then differ from PETSc's."""
+
+    SUBSTITUTED = ("default", "ilu", "icc", "sor", "amg", "petsc_amg", "hypre_amg", "hypre_euclid",
+                   "hypre_parasails", "bjacobi")
+
+    def __init__(self, method="bicgstab", preconditioner="default"):
+        if method == "default":
+            method = "gmres"                      # PETSc's default KSP
         if method not in ("bicgstab", "gmres"):
             raise RuntimeError("Unknown Krylov method \"%s\"" % method)
-        if preconditioner in ("default",):
-            preconditioner = "jacobi" if method == "bicgstab" else "none"
+        self.requested_preconditioner = preconditioner
+        if preconditioner in self.SUBSTITUTED:
+            if preconditioner != "default":
+                print("libbtfem: preconditioner \"%s\" is not available on the GPU path; using \"jacobi\" "
+                      "(same converged solution, different iteration counts)" % preconditioner)
+            preconditioner = "jacobi"
         if preconditioner not in ("jacobi", "none"):
             raise RuntimeError("Unknown preconditioner \"%s\" (libbtfem implements jacobi and none)" % preconditioner)
         self.method = method

@@ -79,6 +79,15 @@ def test_krylov_solver_defaults():
     assert ls.parameters["relative_tolerance"] == 1e-6 and ls.parameters["nonzero_initial_guess"] is False
     with pytest.raises(RuntimeError):
         dl.KrylovSolver("cg", "jacobi")
+    with pytest.raises(RuntimeError):
+        dl.KrylovSolver("bicgstab", "no_such_pc")
+    # the notebooks' other spellings run with Jacobi (ECS_226Cylinders.ipynb / RealNeurons.ipynb cell 10, ConvergenceTest)
+    for args in (("bicgstab",), ("bicgstab", "petsc_amg"), ("gmres", "ilu")):
+        ls = dl.KrylovSolver(*args)
+        assert ls.preconditioner == "jacobi" and ls.requested_preconditioner == (args[1] if len(args) > 1 else "default")
+    assert dl.KrylovSolver("gmres", "none").preconditioner == "none"
+    lu = dl.PETScLUSolver("mumps")
+    assert (lu.method, lu.preconditioner, lu.parameters["relative_tolerance"]) == ("bicgstab", "jacobi", 1e-13)
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_MESH_DIR), reason="reference meshes not present")
