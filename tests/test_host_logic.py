@@ -225,3 +225,36 @@ def test_comri_cli_parsing_and_scheme_quirks():
     assert comri.shell_phase(mid, "two-comp").tolist() == [0, 1, 0, 0]
     mid = np.array([[20.0, 0, 0], [26.0, 0, 0], [28.0, 0, 0], [40.0, 0, 0]])
     assert comri.shell_phase(mid, "multilayer").tolist() == [0, 1, 0, 0]
+
+
+def test_preprocess_phase_and_cell_fields(tmp_path):
+    """CreatePhaseFunc (DmriFemLib.py:748-799) + the DG0 fields of PreprocessingMultiCompt.py:118-152 -> .npz."""
+    from dmri_fem_cloud_b200 import preprocess
+    xyz, tets, lay = meshes.layered_cylinder((5.0, 7.5, 10.0), 2.0, (2, 1, 1), 8, 1)
+    ph, plist = preprocess.create_phase_func(xyz, tets, partition_marker=lay)
+    assert np.array_equal(ph, lay % 2) and sorted(plist) == [0, 1, 2]
+    sub = lambda k: (xyz, tets[lay == k])                 # a compartment as a cell subset of the mesh
+    ph2, plist2, pm2 = preprocess.create_phase_func(xyz, tets, evengroup=[sub(2)], oddgroup=[sub(1)])
+    assert np.array_equal(pm2[lay == 1], np.full((lay == 1).sum(), 1)) and set(pm2[lay == 2]) == {2} and set(pm2[lay == 0]) == {0}
+    assert np.array_equal(ph2, (lay == 1).astype(np.int32)) and plist2 == [0, 2, 1]
+    f = preprocess.cell_fields(pm2, [3e-3, 1e-3, 2e-3], [1e6, 4e4, 5e4], [1, 0, 1])
+    assert set(f["d11"][lay == 1]) == {1e-3} and set(f["T2"][lay == 2]) == {5e4} and not f["d01"].any()
+    assert set(f["ic"][lay == 1]) == {0.0}
+    # command line: marker file written the way msh2xml does, output readable by the solver CLI
+    np.savez(tmp_path / "m.npz", xyz=xyz, tets=tets)
+    pmk = tmp_path / "pmk.xml"
+    pmk.write_text('<dolfin><mesh_function><mesh_value_collection type="uint" dim="3" size="%d">\n' % len(tets) +
+                   "".join('<value cell_index="%d" local_entity="0" value="%d" />\n' % (c, v) for c, v in enumerate(lay)) +
+                   '</mesh_value_collection></mesh_function></dolfin>\n')
+    monkey_load = preprocess._load
+    preprocess._load = lambda p: (xyz, tets)
+    try:
+        rc = preprocess.main(["preprocess", "-m", "mesh.xml", "-pmk", str(pmk), "-D0", "3e-3", "1e-3", "3e-3", "-T2", "1e6",
+                              "4e4", "4e4", "-o", str(tmp_path / "files.h5")])
+    finally:
+        preprocess._load = monkey_load
+    z = np.load(tmp_path / "files.npz")
+    assert rc == 0 and np.array_equal(z["phase"], lay % 2) and set(z["d00"][lay == 1]) == {1e-3} and set(z["ic"]) == {1.0}
+    from dmri_fem_cloud_b200 import cli
+    data = cli.load_input(str(tmp_path / "files.npz"))
+    assert all(k in data for k in ("xyz", "tets", "phase", "T2", "ic", "d00", "d22"))
