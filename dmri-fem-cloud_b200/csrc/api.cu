@@ -1,5 +1,6 @@
 // extern "C" entry points of libbtfem.so: argument checking, error capture, call order.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -10,6 +11,12 @@ namespace {
 template <typename F>
 int guarded(btfem* h, F&& f) {
   if (!h) return BTFEM_EINVAL;
+  struct AllocScope {   // device arrays touched inside this call live on the handle's stream (btfem_internal.cuh)
+    cudaStream_t s0 = bt_alloc_stream;
+    bool p0 = bt_alloc_pooled;
+    explicit AllocScope(btfem* h) { bt_alloc_stream = h->stream; bt_alloc_pooled = h->pool_ok; }
+    ~AllocScope() { bt_alloc_stream = s0; bt_alloc_pooled = p0; }
+  } scope(h);
   try {
     BT_CUDA(cudaSetDevice(h->device));
     f();
@@ -50,6 +57,21 @@ int btfem_create(int device, btfem_t** out) {
     delete h;
     return BTFEM_ECUDA;
   }
+  // Stream-ordered pool for the handle's device arrays: freed blocks stay in the pool (no trim at synchronisation
+  // points), so tearing a problem down and building the next one re-uses them.  BTFEM_POOL=0: plain cudaMalloc.
+  {
+    const char* env = getenv("BTFEM_POOL");
+    int supported = 0;
+    cudaMemPool_t pool = nullptr;
+    if (!(env && env[0] == '0') &&
+        cudaDeviceGetAttribute(&supported, cudaDevAttrMemoryPoolsSupported, device) == cudaSuccess && supported &&
+        cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      h->pool_ok = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess;
+    }
+    cudaGetLastError();
+  }
+  h->d_vecs.plain = true;   // the vector slab of a row partition is exported to the peers (cudaIpcGetMemHandle)
   *out = h;
   return BTFEM_OK;
 }
