@@ -258,3 +258,38 @@ def test_preprocess_phase_and_cell_fields(tmp_path):
     from dmri_fem_cloud_b200 import cli
     data = cli.load_input(str(tmp_path / "files.npz"))
     assert all(k in data for k in ("xyz", "tets", "phase", "T2", "ic", "d00", "d22"))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) prints ONE JSON line with the
+    contract's keys; under torchrun only rank 0 prints.  Tiny workload, CPU only."""
+    import json
+    import subprocess
+    import sys as _sys
+    cmd = [_sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+           "--cpu-sample-steps", "2", "--n-box", "8"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, check=True).stdout
+    lines = [l for l in out.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "DOF-steps/s" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    silent = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=300, env=env)
+    assert silent.returncode == 0 and silent.stdout.strip() == ""
+
+
+def test_bench_loop_roofline_arithmetic():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    r = b.loop_roofline(nnz=1000, n=100, iters=10, nsteps=2, loop_ms=1.0, peak_gbs=1.0)
+    spmv = 20 * 1000 + 36 * 100
+    assert r["algorithmic_bytes_per_iteration"] == 2 * spmv + 224 * 100
+    assert r["algorithmic_bytes_per_solve"] == 10 * (2 * spmv + 224 * 100) + 2 * spmv
+    assert abs(r["achieved"] - r["algorithmic_bytes_per_solve"] / 1e-3 / 1e9) < 1e-12 and r["us_per_iteration"] == 100.0
