@@ -137,10 +137,13 @@ def element_matrices(xyz, tets, D=1.0, invT2=0.0):
 # --------------------------------------------------------------------------- dof map / pattern
 
 
-def dof_map(nv, tets, phase=None):
+def dof_map(nv, tets, phase=None, vmaster=None):
     """Number the active (vertex, compartment) pairs vertex-major.
 
     phase: None (one compartment) or (nc,) int in {0,1} = marker % 2 (DmriFemLib.py:764).
+    vmaster: None, or (nv,) the master vertex of every vertex (itself if it is not a periodic slave): strongly
+    imposed periodicity (`constrained_domain=PeriodicBD`, DmriFemLib.py:327-375, 478-483) -- a slave vertex
+    carries the dofs of its master, only masters are numbered.
     Returns cell_dofs (nc,4) int32, ndof, dof_vertex (ndof,), dof_comp (ndof,),
     vc2dof (nv,2) int32 (-1 where inactive).
     """
@@ -148,15 +151,17 @@ def dof_map(nv, tets, phase=None):
     if phase is None:
         phase = np.zeros(len(tets), dtype=np.int32)
     phase = np.asarray(phase).astype(np.int32)
+    vm = np.arange(nv) if vmaster is None else np.asarray(vmaster)
     active = np.zeros((nv, 2), dtype=bool)
     for c in (0, 1):
-        active[np.unique(tets[phase == c]), c] = True
+        active[vm[np.unique(tets[phase == c])], c] = True
     flat = active.ravel()
     ids = np.cumsum(flat) - 1
     vc2dof = np.where(flat, ids, -1).reshape(nv, 2).astype(np.int32)
     ndof = int(flat.sum())
-    cell_dofs = vc2dof[tets, phase[:, None]].astype(np.int32)
     dv, dc = np.nonzero(active)
+    vc2dof = vc2dof[vm]                       # slaves point at their master's dofs
+    cell_dofs = vc2dof[tets, phase[:, None]].astype(np.int32)
     return cell_dofs, ndof, dv.astype(np.int32), dc.astype(np.int32), vc2dof
 
 
@@ -238,7 +243,7 @@ class Operators:
 
 
 def assemble(xyz, tets, phase=None, D=1.0, invT2=0.0, kappa=0.0, kappa_facet=None,
-             bnd_kappa_vertex=None):
+             bnd_kappa_vertex=None, vmaster=None):
     """Assemble M,S,R,Jx,Jy,Jz,(I),(B) + lumped mass on the active-dof numbering.
 
     kappa: scalar membrane permeability (`-p`); kappa_facet: optional callable
@@ -253,13 +258,14 @@ def assemble(xyz, tets, phase=None, D=1.0, invT2=0.0, kappa=0.0, kappa_facet=Non
     nvf = nvc - 1                       # vertices per facet
     if nvc == 2 and (phase is not None or bnd_kappa_vertex is not None):
         raise ValueError("segment meshes: one compartment, Neumann ends")
-    cell_dofs, ndof, dv, dc, vc2dof = dof_map(nv, tets, phase)
+    cell_dofs, ndof, dv, dc, vc2dof = dof_map(nv, tets, phase, vmaster)
     em = element_matrices(xyz, tets, D, invT2)
     rows = np.repeat(cell_dofs, nvc, axis=1).ravel()
     cols = np.tile(cell_dofs, (1, nvc)).ravel()
     ops = Operators()
     ops.ndof, ops.nv, ops.cell_dofs, ops.dof_vertex, ops.dof_comp, ops.vc2dof = ndof, nv, cell_dofs, dv, dc, vc2dof
     ops.phase = None if phase is None else np.asarray(phase).astype(np.int32)
+    ops.xyz, ops.cells, ops.Dcoef = xyz, tets, D
     trip = {k: (rows, cols, em[k].ravel()) for k in ("M", "S", "R", "Jx", "Jy", "Jz")}
     # interface (DmriFemLib.py:47-50, 112, 139): kappa*(u0-u1)(v0-v1) on facets with |jump(phase)|=1
     if phase is not None:
@@ -610,6 +616,139 @@ def periodic_term(xyz, tets, ops, pdir, lo, hi, q, gdir, theta):
         return (1.0 - theta) * (ops.B @ ubc)
 
     return term
+
+
+# --------------------------------------------------------------------------- strongly imposed periodicity
+
+
+def periodic_vertex_map(xyz, pdir, lo, hi, tol):
+    """Master vertex of every vertex for `constrained_domain=PeriodicBD` (DmriFemLib.py:327-375): a vertex within
+    `tol` of the max face of a periodic direction is identified with the vertex at the same place on the min face
+    (PeriodicBD.map shifts by the box length; `inside` = the min faces are the masters).  Edges and corners of the
+    box wrap in every periodic direction they touch.  The mesh must be periodic: a slave without a partner raises.
+    (How DOLFIN resolves vertices that are slave in one direction and master in another is third party; wrapping
+    all directions is the periodic lattice.)"""
+    xyz = as_xyz3(xyz)
+    w = xyz.copy()
+    slave = np.zeros(len(xyz), dtype=bool)
+    for d in range(3):
+        if pdir[d]:
+            on = np.abs(xyz[:, d] - hi[d]) < tol
+            w[on, d] = lo[d]
+            slave |= on
+    key = np.round(w / tol).astype(np.int64)
+    order = np.lexsort((key[:, 2], key[:, 1], key[:, 0]))
+    ks = key[order]
+    first = np.ones(len(ks), dtype=bool)
+    first[1:] = np.any(ks[1:] != ks[:-1], axis=1)
+    group = np.cumsum(first) - 1
+    vm = np.arange(len(xyz))
+    # master of a group: its (unique) non-slave member
+    gid = np.empty(len(xyz), dtype=np.int64)
+    gid[order] = group
+    master_of_group = -np.ones(group[-1] + 1, dtype=np.int64)
+    ns = np.nonzero(~slave)[0]
+    if len(np.unique(gid[ns])) != len(ns):
+        raise ValueError("two distinct non-slave vertices coincide after wrapping: tol too large")
+    master_of_group[gid[ns]] = ns
+    vm = master_of_group[gid]
+    if (vm < 0).any():
+        raise ValueError("the mesh is not periodic: %d vertices on a max face have no partner on the min face"
+                         % int((vm < 0).sum()))
+    return vm
+
+
+def strong_operators(ops, gdir):
+    """The matrices the transformed (strongly periodic) equation adds (FuncF_sBC, outer_interface,
+    inner_interface, DmriFemLib.py:147-165), on the pattern of `ops` (built with the same vmaster):
+
+        W[i,j] = int (g.Dg) phi_i phi_j                       (from -q^2 F^2 (g.Dg) u v)
+        C[i,j] = int (g.D grad phi_j + grad phi_j . D g) phi_i (from -i q F (g.D grad u + grad u.Dg) v)
+        N[i,j] = sum over the facets bounding the compartment of the cell (exterior facets and interface facets,
+                 seen from either side) of (D g . n_out) int_facet phi_i phi_j
+                 (outer_interface: -i (qF + 1e-16)(Dg.n) u v ds; inner_interface reduces to the same expression
+                 per side once D0 = D1 = D is inserted, as every call site does; the 1e-16 guard is dropped)
+
+    so that with Phi = F(t):  F_s(Phi; u, v) = -[S + R + q^2 Phi^2 W] u v - i q Phi [C - N] u v (+ kappa jump terms).
+    Returns (W, G) with G = C - N, csr on ops' pattern."""
+    g = np.asarray(gdir, dtype=float)
+    g = g / np.linalg.norm(g)
+    xyz, cells = ops.xyz, np.asarray(ops.cells)
+    nc, nvc = cells.shape
+    d = nvc - 1
+    if nvc == 4:
+        _, vol, grad = tet_geometry(xyz, cells)
+    elif nvc == 3:
+        vol, grad = tri_geometry(xyz, cells)
+    else:
+        raise ValueError("strong periodic BC: tetrahedra or triangles")
+    D = np.asarray(ops.Dcoef, dtype=float)
+    if D.ndim == 0:
+        Dc = np.broadcast_to(D * np.eye(3), (nc, 3, 3))
+    elif D.ndim == 1:
+        Dc = D[:, None, None] * np.eye(3)[None]
+    elif D.ndim == 2:
+        Dc = np.broadcast_to(D, (nc, 3, 3))
+    else:
+        Dc = D
+    Dg = np.einsum("cab,b->ca", Dc, g)                    # D g
+    DTg = np.einsum("cba,b->ca", Dc, g)                   # D^T g
+    gDg = np.einsum("ca,a->c", Dg, g)
+    I = np.eye(nvc)
+    Wm = (gDg * vol)[:, None, None] * (1.0 + I)[None] / float((d + 1) * (d + 2))
+    # C[i,j] = |T|/(d+1) * ((D + D^T) g) . grad phi_j      (int phi_i = |T|/(d+1))
+    cj = np.einsum("ca,cja->cj", Dg + DTg, grad)
+    Cm = (vol / (d + 1.0))[:, None, None] * np.broadcast_to(cj[:, None, :], (nc, nvc, nvc))
+    rows = np.repeat(ops.cell_dofs, nvc, axis=1).ravel()
+    cols = np.tile(ops.cell_dofs, (1, nvc)).ravel()
+    n = ops.ndof
+    W = sp.coo_matrix((Wm.ravel(), (rows, cols)), shape=(n, n)).tocsr()
+    C = sp.coo_matrix((Cm.ravel(), (rows, cols)), shape=(n, n)).tocsr()
+    # facets bounding a compartment: exterior facets, and interface facets from both sides.  For the facet of
+    # cell T opposite its local vertex o:  n_out |F| = -d |T| grad(lambda_o), so
+    # (Dg.n_out) int_F phi_i phi_j = -d |T| (Dg.grad lambda_o) (1 + d_ij) / (d (d+1)) = -|T| (Dg.grad lambda_o)(1+d_ij)/(d+1)
+    f, cell, lf = facets(cells)
+    nf = len(f)
+    same_next = np.zeros(nf, dtype=bool)
+    same_next[:-1] = np.all(f[1:] == f[:-1], axis=1)
+    same_prev = np.zeros(nf, dtype=bool)
+    same_prev[1:] = same_next[:-1]
+    ph = np.zeros(nc, dtype=np.int32) if ops.phase is None else ops.phase
+    partner = np.where(same_next, np.roll(cell, -1), np.where(same_prev, np.roll(cell, 1), -1))
+    bounding = (partner < 0) | (ph[np.maximum(partner, 0)] != ph[cell])
+    fc, fl = cell[bounding], lf[bounding]
+    loc = (_FACES if nvc == 4 else _EDGES)[fl]                                   # local vertices of the facet
+    coef = -vol[fc] * np.einsum("fa,fa->f", Dg[fc], grad[fc, fl]) / (d + 1.0)
+    nvf = nvc - 1
+    Nm = coef[:, None, None] * (1.0 + np.eye(nvf))[None]
+    fd = ops.cell_dofs[fc[:, None], loc]                                         # dofs of the cell's own compartment
+    N = sp.coo_matrix((Nm.ravel(), (np.repeat(fd, nvf, axis=1).ravel(), np.tile(fd, (1, nvf)).ravel())),
+                      shape=(n, n)).tocsr()
+    return W, (C - N).tocsr()
+
+
+def theta_solve_strong(ops, seq, q, gdir, k, theta=0.5, closed=True, ic=None):
+    """MRI_simulation.solve with ThetaMethodF/L_sBC1c/2c (DmriFemLib.py:166-238, 878-915): the transformed equation on
+    a periodic function space.  The matrix uses F(t_n), the right-hand side F(t_{n-1}) (ift_f / ift_p_f, :901-902),
+    and BOTH carry theta (the linear form is written with `+theta*FuncF_sBC`, :183, :232-233 -- equal to (1-theta)
+    for the theta = 0.5 the class fixes).  Exact (sparse LU) stepping.
+    Returns dict(u, signal, voi, n_steps)."""
+    W, G = strong_operators(ops, gdir)
+    K0 = ops.S + ops.R + ops.I
+    ic = np.ones(ops.ndof) if ic is None else np.asarray(ic, dtype=float)
+    u = ic.astype(complex)
+    ts = time_grid(seq.T, k, closed)
+    tp = 0.0
+    lus = {}
+    for t in ts:
+        Fn, Fp = seq.F(t), seq.F(tp)
+        b = (ops.M / k - theta * (K0 + (q * Fp) ** 2 * W)) @ u - 1j * theta * q * Fp * (G @ u)
+        key = round(Fn, 300)
+        if key not in lus:
+            lus[key] = spla.splu((ops.M / k + theta * (K0 + (q * Fn) ** 2 * W) + 1j * theta * q * Fn * G).tocsc())
+        u = lus[key].solve(b)
+        tp = t
+    return dict(u=u, signal=float(ops.lumped @ u.real), voi=float(ops.lumped @ ic), n_steps=len(ts))
 
 
 # --------------------------------------------------------------------------- the theta loop

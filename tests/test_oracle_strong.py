@@ -1,0 +1,115 @@
+"""CPU: the oracle's restatement of the STRONGLY imposed pseudo-periodic BC (FuncF_sBC / outer_interface /
+inner_interface / PeriodicBD, DmriFemLib.py:147-238, 327-375): the equation for u~ = u exp(+i q F(t) g.x) on a
+periodic function space.  The reference tree holds no recorded output of this mode (no notebook runs
+`IsDomainPeriodic = True` with a periodic direction), so the restatement is pinned by what must hold exactly or in
+the limit: the uniform solution in a periodic box, equivalence with the untransformed equation as dt -> 0, and
+invariance under tiling the unit cell."""
+import numpy as np
+
+import bt_oracle as orc
+from dmri_fem_cloud_b200 import meshes
+
+
+def _tile_x(xyz, tets, ph, L):
+    x2 = xyz.copy()
+    x2[:, 0] += L
+    allx = np.vstack([xyz, x2])
+    t2 = np.vstack([tets, tets + len(xyz)])
+    key = np.round(allx * 1e6).astype(np.int64)
+    _, first, inv = np.unique(key, axis=0, return_index=True, return_inverse=True)
+    return allx[first], inv.ravel()[t2].astype(np.int32), np.concatenate([ph, ph])
+
+
+def test_periodic_vertex_map_wraps_faces_edges_and_corners():
+    xyz, tets = meshes.box_mesh((-2, -1.5, -1), (2, 1.5, 1), 4, 3, 2)
+    lo, hi, hmin, _ = orc.domain_sizes(xyz, tets)
+    vm = orc.periodic_vertex_map(xyz, [1, 1, 1], lo, hi, 1e-2 * hmin)
+    assert len(np.unique(vm)) == 4 * 3 * 2 and (vm[vm] == vm).all()
+    corners = np.nonzero((np.abs(np.abs(xyz) - hi) < 1e-12).all(axis=1))[0]
+    assert len(corners) == 8 and len(set(vm[corners])) == 1 and np.allclose(xyz[vm[corners[0]]], lo)
+    vm_x = orc.periodic_vertex_map(xyz, [1, 0, 0], lo, hi, 1e-2 * hmin)
+    assert len(np.unique(vm_x)) == 4 * 4 * 3 and np.allclose(xyz[vm_x][:, 1:], xyz[:, 1:])
+    bad = xyz.copy()
+    bad[np.argmax(bad[:, 0]), 1] += 0.2                     # a max-face vertex without a partner
+    try:
+        orc.periodic_vertex_map(bad, [1, 0, 0], lo, hi, 1e-2 * hmin)
+        assert False
+    except ValueError:
+        pass
+
+
+def test_uniform_solution_in_a_periodic_box_follows_the_scalar_recurrence():
+    """No barriers, all directions periodic: u~ stays uniform (C 1 = 0, the facet terms of merged faces cancel), so
+    every dof follows u <- u (1/k - theta D q^2 F_p^2) / (1/k + theta D q^2 F_n^2); the signal tends to exp(-bD)."""
+    xyz, tets = meshes.box_mesh((-2, -1.5, -1), (2, 1.5, 1), 5, 4, 3)
+    rng = np.random.default_rng(2)
+    inner = (np.abs(xyz) < np.array([1.9, 1.4, 0.9])).all(axis=1)
+    xyz[inner] += 0.05 * rng.standard_normal((inner.sum(), 3))
+    lo, hi, hmin, _ = orc.domain_sizes(xyz, tets)
+    ops = orc.assemble(xyz, tets, D=2e-3, vmaster=orc.periodic_vertex_map(xyz, [1, 1, 1], lo, hi, 1e-2 * hmin))
+    seq = orc.pgse(1000.0, 3000.0)
+    q, k = seq.q_from_b(1500.0), 100.0
+    g = np.array([0.3, -0.5, 0.8])
+    r = orc.theta_solve_strong(ops, seq, q, g, k)
+    u, tp = 1.0, 0.0
+    for t in orc.time_grid(seq.T, k):
+        u *= (1 / k - 0.5 * 2e-3 * (q * seq.F(tp)) ** 2) / (1 / k + 0.5 * 2e-3 * (q * seq.F(t)) ** 2)
+        tp = t
+    assert np.abs(r["u"] - u).max() <= 1e-13
+    assert abs(r["signal"] / r["voi"] - np.exp(-1500.0 * 2e-3)) <= 0.01 * np.exp(-3.0)
+
+
+def test_transformed_equation_equals_the_original_one_as_dt_goes_to_zero():
+    """Without identification the transformed problem IS the Neumann problem (u = u~ at t = T where F = 0): the two
+    discretisations differ by the time error of the lagged, discontinuous f (first order) and a small spatial
+    term.  Two compartments with different D: exercises the signs of C and of the facet terms on both sides."""
+    xy, tris, lay = meshes.disk_triangulation((2.0, 3.0), (6, 4), 32)
+    ph = (lay % 2).astype(np.int32)
+    ops = orc.assemble(xy, tris, ph, D=np.array([2e-3, 1e-3])[lay], kappa=5e-5)
+    seq = orc.pgse(1000.0, 3000.0)
+    q = seq.q_from_b(1000.0)
+    g = np.array([0.6, 0.8, 0.0])
+    diff = []
+    for k in (50.0, 12.5):
+        a = orc.theta_solve(ops, seq, q, g, k, solver="lu")
+        b = orc.theta_solve_strong(ops, seq, q, g, k)
+        diff.append(abs(b["signal"] - a["signal"]) / a["signal"])
+    assert diff[0] < 1e-2 and diff[1] < 2e-3 and diff[1] < 0.3 * diff[0]
+    # tetrahedra: the spatial part of the difference falls with h^2 (1.7e-2 at n = 6, 1.6e-3 at n = 12)
+    err = []
+    for n in (6, 12):
+        xyz, tets = meshes.box_mesh((-2, -1.5, -1), (2, 1.5, 1), n, n, n // 2)
+        ops = orc.assemble(xyz, tets, D=2e-3)
+        a = orc.theta_solve(ops, seq, q, g, 50.0, solver="lu")
+        b = orc.theta_solve_strong(ops, seq, q, g, 50.0)
+        err.append(abs(b["signal"] - a["signal"]) / a["signal"])
+    assert err[1] < 3e-3 and err[1] < 0.25 * err[0]
+
+
+def test_tiling_the_unit_cell_does_not_change_the_signal():
+    """Periodic lattice of permeable cells, D differs between the compartments, interior vertices jittered: the
+    solution on two unit cells glued together equals the solution on one -- to rounding, because the discrete
+    problem is translation invariant.  Pins the vertex identification and the facet terms on merged faces."""
+    xyz, tets, ph = meshes.box_with_sphere(4.0, 6, 2.5)
+    rng = np.random.default_rng(1)
+    inner = (np.abs(xyz) < 3.9).all(axis=1)
+    xyz = xyz.copy()
+    xyz[inner] += 0.05 * rng.standard_normal((inner.sum(), 3))
+    seq = orc.pgse(1000.0, 3000.0)
+    q, k = seq.q_from_b(1000.0), 100.0
+    g = np.array([1.0, 0.5, 0.2])
+    pdir = [1, 1, 0]
+
+    def run(x, t, p):
+        lo, hi, hmin, _ = orc.domain_sizes(x, t)
+        vm = orc.periodic_vertex_map(x, pdir, lo, hi, 1e-2 * hmin)
+        ops = orc.assemble(x, t, p, D=np.where(p == 1, 1e-3, 2e-3), kappa=5e-5, vmaster=vm)
+        return orc.theta_solve_strong(ops, seq, q, g, k), ops
+
+    r1, o1 = run(xyz, tets, ph)
+    r2, o2 = run(*_tile_x(xyz, tets, ph, 8.0))
+    assert o2.ndof == 2 * o1.ndof
+    assert abs(r1["signal"] / r1["voi"] - r2["signal"] / r2["voi"]) <= 1e-13
+    neu = orc.theta_solve(orc.assemble(xyz, tets, ph, D=np.where(ph == 1, 1e-3, 2e-3), kappa=5e-5), seq, q, g, k,
+                          solver="lu")
+    assert abs(neu["signal"] / neu["voi"] - r1["signal"] / r1["voi"]) > 0.05      # periodicity matters here
