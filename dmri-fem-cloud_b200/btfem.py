@@ -62,6 +62,8 @@ def load_library(path=None):
         "btfem_set_mesh": (C.c_int, [H, C.c_int64, _c_double_p, C.c_int64, _c_int32_p, _c_int32_p]),
         "btfem_set_mesh_tri": (C.c_int, [H, C.c_int64, _c_double_p, C.c_int64, _c_int32_p, _c_int32_p]),
         "btfem_set_mesh_seg": (C.c_int, [H, C.c_int64, _c_double_p, C.c_int64, _c_int32_p]),
+        "btfem_set_periodic_map": (C.c_int, [H, _c_int32_p]),
+        "btfem_get_strong_operators": (C.c_int, [H, _c_double_p, _c_double_p, _c_double_p]),
         "btfem_set_phase": (C.c_int, [H, _c_int32_p]),
         "btfem_get_mesh_stats": (C.c_int, [H, _c_double_p, _c_double_p]),
         "btfem_set_diffusion": (C.c_int, [H, C.c_int, _c_double_p]),
@@ -215,6 +217,22 @@ class BTFem:
         lo = np.ascontiguousarray(lo, dtype=np.float64)
         hi = np.ascontiguousarray(hi, dtype=np.float64)
         self._ck(self.lib.btfem_set_periodic(self.h, _ip(p), float(kappa_e), float(tol), _dp(lo), _dp(hi)))
+
+    def set_periodic_map(self, vmaster=None):
+        """Strongly imposed periodicity: vmaster[v] = master vertex of v (periodic.vertex_map); None switches it off.
+        btfem_solve then steps the transformed equation: pass cA = q*F(t_n), cb = q*F(t_{n-1})."""
+        if vmaster is None:
+            self._ck(self.lib.btfem_set_periodic_map(self.h, None))
+        else:
+            vm = np.ascontiguousarray(vmaster, dtype=np.int32)
+            assert len(vm) == self.nv
+            self._ck(self.lib.btfem_set_periodic_map(self.h, _ip(vm)))
+
+    def strong_operators(self, gdir):
+        g = np.ascontiguousarray(gdir, dtype=np.float64)
+        W, G = np.empty(self.nnz), np.empty(self.nnz)
+        self._ck(self.lib.btfem_get_strong_operators(self.h, _dp(g), _dp(W), _dp(G)))
+        return W, G
 
     def boundary_facets(self):
         out = np.empty((self.n_bfacet, 3), dtype=np.int32)

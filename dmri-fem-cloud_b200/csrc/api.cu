@@ -99,6 +99,7 @@ static void set_mesh_cells(btfem_t* h, int64_t nv, const double* xyz, int64_t nc
   if (phase)
     for (int64_t i = 0; i < nc; ++i) BT_REQUIRE(phase[i] == 0 || phase[i] == 1, "phase must be 0 or 1");
   invalidate(h);
+  h->h_vmaster.clear();
   h->nv = nv;
   h->nc = nc;
   h->cell_nv = cell_nv;
@@ -125,6 +126,31 @@ int btfem_set_mesh_tri(btfem_t* h, int64_t nv, const double* xyz, int64_t nc, co
 
 int btfem_set_mesh_seg(btfem_t* h, int64_t nv, const double* xyz, int64_t nc, const int32_t* segs) {
   return guarded(h, [&] { set_mesh_cells(h, nv, xyz, nc, segs, 2, nullptr); });
+}
+
+int btfem_set_periodic_map(btfem_t* h, const int32_t* vmaster) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->nv > 0, "set the mesh first");
+    BT_REQUIRE(h->nv_own < 0, "strong periodic BC: whole-mesh handles");
+    if (vmaster) {
+      BT_REQUIRE(h->cell_nv >= 3, "strong periodic BC: tetrahedral or triangle meshes");
+      for (int64_t v = 0; v < h->nv; ++v) {
+        BT_REQUIRE(vmaster[v] >= 0 && vmaster[v] < h->nv, "periodic map: master out of range");
+        BT_REQUIRE(vmaster[vmaster[v]] == vmaster[v], "periodic map: the master of a master must be itself");
+      }
+      h->h_vmaster.assign(vmaster, vmaster + h->nv);
+    } else {
+      h->h_vmaster.clear();
+    }
+    invalidate(h);
+  });
+}
+
+int btfem_get_strong_operators(btfem_t* h, const double gdir[3], double* W, double* G) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->assembled && gdir, "call btfem_assemble first");
+    bt_strong_get(h, gdir, W, G);
+  });
 }
 
 int btfem_set_phase(btfem_t* h, const int32_t* phase) {
@@ -372,6 +398,7 @@ int btfem_set_partition(btfem_t* h, int64_t nv_own, int64_t nv_interior) {
   return guarded(h, [&] {
     BT_REQUIRE(h->nv > 0, "set the mesh first");
     BT_REQUIRE(h->cell_nv == 4, "row partitions are built on tetrahedral meshes");
+    BT_REQUIRE(h->h_vmaster.empty(), "strong periodic BC: whole-mesh handles");
     BT_REQUIRE(nv_own > 0 && nv_own <= h->nv && nv_interior >= 0 && nv_interior <= nv_own, "bad partition sizes");
     h->nv_own = nv_own;
     h->nv_int = nv_interior;

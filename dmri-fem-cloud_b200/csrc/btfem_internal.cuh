@@ -208,6 +208,9 @@ struct btfem {
   int32_t pdir[3] = {0, 0, 0};
   double kappa_e = 0.0, ptol = 0.0, lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
   std::vector<double> h_ic;   // empty = all ones
+  // strongly imposed periodicity (btfem_set_periodic_map): master vertex of every vertex; empty = none.
+  // Non-empty also selects the transformed equation (strong.cu) in btfem_solve.
+  std::vector<int32_t> h_vmaster;
 
   // ---- device mesh
   DevArray<double> d_xyz, d_D, d_invT2, d_kappa_tab, d_bmark /*kappa_e^h per vertex*/;
@@ -267,6 +270,7 @@ struct btfem {
   // ---- per-solve state
   DevArray<double2> d_PJ, d_QJ;
   DevArray<double> d_Bhat, d_dinv;
+  DevArray<double> d_strongW, d_strongG;   // strong periodic BC: W and G = C - N of the current direction (strong.cu)
   // the seven Krylov vectors live in ONE slab so that a single L2 access-policy window can pin them:
   // 7 x 8 MB at 1 M DOFs fits the 126 MB L2 while the matrix streams past with evict-first loads
   DevArray<double2> d_vecs;
@@ -316,6 +320,9 @@ void bt_build_periodic(btfem* h);
 
 // solve.cu
 void bt_combine(btfem* h, double dt, double theta, const double g[3], int pc, int member = 0, int members = 1);
+void bt_strong_build(btfem* h, const double g[3]);
+void bt_strong_recombine(btfem* h, cudaStream_t st, double dt, double theta, int pc);
+void bt_strong_get(btfem* h, const double g[3], double* W, double* G);
 void bt_spmv_host(btfem* h, double dt, double theta, double c, const double g[3], const double* x, double* y);
 void bt_spmv_bench(btfem* h, double dt, double theta, double c, const double g[3], int lanes, int nrep, int flush_l2,
                    double* ms);

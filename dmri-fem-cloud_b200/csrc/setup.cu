@@ -582,10 +582,14 @@ void bt_mesh_stats(btfem* h, double* hmin, double* hmax) {
 
 void bt_build_dofmap(btfem* h) {
   const int64_t nv = h->nv, nc = h->nc;
+  // strongly imposed periodicity: a slave vertex carries the dofs of its master (constrained_domain = PeriodicBD,
+  // DmriFemLib.py:327-375, 478-483); only masters are numbered
+  const bool merged = !h->h_vmaster.empty();
+  auto vm = [&](int64_t v) -> int64_t { return merged ? (int64_t)h->h_vmaster[v] : v; };
   std::vector<uint8_t> active(2 * nv, 0);
   for (int64_t c = 0; c < nc; ++c) {
     int ph = h->two_comp ? h->h_phase[c] : 0;
-    for (int k = 0; k < h->cell_nv; ++k) active[2 * (int64_t)h->h_tets[4 * c + k] + ph] = 1;
+    for (int k = 0; k < h->cell_nv; ++k) active[2 * vm(h->h_tets[4 * c + k]) + ph] = 1;
   }
   std::vector<int32_t> vc2dof(2 * nv, -1);
   h->h_dof_vertex.clear();
@@ -599,6 +603,10 @@ void bt_build_dofmap(btfem* h) {
         h->h_dof_comp.push_back(c);
       }
   h->ndof = n;
+  if (merged)
+    for (int64_t v = 0; v < nv; ++v)
+      if (vm(v) != v)
+        for (int c = 0; c < 2; ++c) vc2dof[2 * v + c] = vc2dof[2 * vm(v) + c];
   // row partition: dofs are vertex-major, so the owned (and the peer-independent) dofs are prefixes
   h->n_own = n;
   h->n_int = n;

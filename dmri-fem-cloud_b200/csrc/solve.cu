@@ -1611,6 +1611,9 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     BT_REQUIRE(h->n_pb > 0, "periodic BC: call btfem_set_periodic_gather after btfem_assemble");
   }
   BT_REQUIRE(members == 1 || (!gmres && !periodic), "batched solves support BiCGStab without periodic BC");
+  const bool strong = !h->h_vmaster.empty();   // transformed equation on a periodic dof map (strong.cu)
+  BT_REQUIRE(!strong || (members == 1 && !gmres && !periodic && h->lanes == 0 && h->nv_own < 0),
+             "strong periodic BC: single BiCGStab solves on the SELL-32 kernel, no weak periodic marker");
   const bool part = h->nv_own >= 0;
   if (part) {
     BT_REQUIRE(h->dist_connected, "row-partitioned handle: call btfem_dist_connect before btfem_solve");
@@ -1664,6 +1667,10 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   } else {
     for (int b = 0; b < members; ++b) bt_combine(h, sa->dt, sa->theta, sav[b].gdir, (int)sa->pc, b, members);
   }
+  if (strong) {   // W, G of this direction; the SELL values are re-combined at the start of every time step
+    bt_strong_build(h, sa->gdir);
+    h->comb_dt = -1;   // PJs/QJs will not hold what bt_combine caches
+  }
   ensure_vectors(h, members);
   h->step_stride = sa->nsteps;
   {
@@ -1688,7 +1695,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   memset(&c0, 0, sizeof(c0));
   c0.rtol = sa->rtol; c0.atol = sa->atol; c0.dtol = 1e4;
   c0.theta_cA_scale = sa->theta;
-  c0.theta_cb_scale = -(1.0 - sa->theta);
+  c0.theta_cb_scale = strong ? -sa->theta : -(1.0 - sa->theta);   // the sBC linear forms carry theta (DmriFemLib.py:183)
   c0.maxit = (int)std::min<int64_t>(sa->maxit, 0x7fffffff);
   c0.nonzero_guess = sa->nonzero_guess ? 1 : 0;
   c0.done = 1;
@@ -1723,6 +1730,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     a.iters_out = d_iters.p;
   }
   auto capture_prologue = [&]() {
+    if (strong) bt_strong_recombine(h, st, sa->dt, sa->theta, (int)sa->pc);
     if (part) k_halo_push_u<<<push_grid, TPB, 0, st>>>(a);
     if (periodic) {
       k_periodic_ubc<<<((int)h->n_pb + TPB - 1) / TPB, TPB, 0, st>>>(
@@ -1735,7 +1743,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     launch_spmv<MODE_RHS>(lanes, a, st, members);
     if (sa->nonzero_guess) launch_spmv<MODE_RESID>(lanes, a, st, members);
   };
-  const int prologue_kernels = (part ? 1 : 0) + (periodic ? 2 : 0) + 1 + (sa->nonzero_guess ? 1 : 0);
+  const int prologue_kernels = (strong ? 1 : 0) + (part ? 1 : 0) + (periodic ? 2 : 0) + 1 + (sa->nonzero_guess ? 1 : 0);
   auto capture_iteration = [&]() {
     k_update_p<<<vg, TPB, 0, st>>>(a);     // row-partitioned: also stores the rows peers need into their halos
     launch_spmv<MODE_V>(lanes, a, st, members);
@@ -1830,6 +1838,10 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     if (iters_per_step) d_iters.download(iters_per_step, st);
   }
   for (int64_t step = 0; !dev_loop && step < sa->nsteps && !fail; ++step) {
+    if (strong) {
+      bt_strong_recombine(h, st, sa->dt, sa->theta, (int)sa->pc);
+      ++n_kernels;
+    }
     if (part) {
       k_halo_push_u<<<push_grid, TPB, 0, st>>>(a);
       ++n_kernels;

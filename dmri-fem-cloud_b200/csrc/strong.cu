@@ -1,0 +1,333 @@
+// Strongly imposed pseudo-periodic boundary conditions (IsDomainPeriodic = True with a periodic direction):
+// the transformed Bloch-Torrey equation for u~ = u exp(+i q F(t) g.x) on a periodic function space.
+//
+// Reference (files under /root/reference): FuncF_sBC, outer_interface, inner_interface, ThetaMethodF/L_sBC1c/2c
+// (DmriFemLib.py:147-238) and `constrained_domain = PeriodicBD` (:327-375, 478-483).  With Phi = F(t), per step
+//     A_n = M/k + theta (S + R + I + q^2 Phi_n^2 W) + i theta q Phi_n G
+//     b_n = [M/k - theta (S + R + I + q^2 Phi_p^2 W) - i theta q Phi_p G] u^n          (theta on BOTH sides, :183)
+//     W[i,j] = int (g.Dg) phi_i phi_j
+//     G = C - N,  C[i,j] = int ((D + D^T) g . grad phi_j) phi_i,
+//                 N[i,j] = sum over the facets bounding the compartment of the cell (exterior facets, and interface
+//                          facets from either side) of (D g . n_out) int_F phi_i phi_j   (the 1e-16 guard of
+//                          outer_interface is below fp64 resolution and dropped)
+// The periodic identification itself is a dof-map matter (setup.cu: bt_build_dofmap with h_vmaster): slave vertices
+// carry the dofs of their masters, so pattern, assembly, SpMV, Krylov and signal kernels run unchanged.
+//
+// What this file adds: W and G for the gradient direction of a solve (bt_strong_build; W and C by the gather of
+// the assembly, N from the bounding facets -- generated, sorted by (row, col) and summed per entry in a fixed
+// order, so the values are reproducible), and the per-step re-combination of the SELL operator values
+// (k_strong_recombine: the real part now changes with Phi(t); skipped while Phi does not change, i.e. between the
+// gradient pulses).  oracle/bt_oracle.py: strong_operators / theta_solve_strong restate the same thing on the CPU.
+//
+// STATUS: compiled for sm_100a and covered by the oracle's CPU pins; the GPU parity tests
+// (tests/test_gpu_strong.py) have not run on hardware yet -- they are opt-in (BTFEM_TEST_STRONG=1).
+#include <algorithm>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "btfem_internal.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr uint32_t NOV = 0xffffffffu;
+inline int nblocks(int64_t n) { return (int)std::max<int64_t>(1, (n + TPB - 1) / TPB); }
+
+struct Tmp {
+  void* p = nullptr;
+  size_t n = 0;
+  ~Tmp() { if (p) cudaFree(p); }
+  void reserve(size_t b) {
+    if (b <= n) return;
+    if (p) cudaFree(p);
+    BT_CUDA(cudaMalloc(&p, b));
+    n = b;
+  }
+};
+
+// measure |T| and the gradients of the barycentric functions of cell t (tetrahedron or triangle in R^3)
+__device__ inline double cell_geometry(const double* __restrict__ xyz, const int32_t* __restrict__ cells, int64_t t,
+                                       int cell_nv, double (&g)[4][3]) {
+  double x[4][3];
+  for (int k = 0; k < cell_nv; ++k)
+    for (int d = 0; d < 3; ++d) x[k][d] = xyz[3 * (int64_t)cells[4 * t + k] + d];
+  if (cell_nv == 4) {
+    double e[3][3];
+    for (int k = 0; k < 3; ++k)
+      for (int d = 0; d < 3; ++d) e[k][d] = x[k + 1][d] - x[0][d];
+    double c[4][3];
+    c[1][0] = e[1][1] * e[2][2] - e[1][2] * e[2][1];
+    c[1][1] = e[1][2] * e[2][0] - e[1][0] * e[2][2];
+    c[1][2] = e[1][0] * e[2][1] - e[1][1] * e[2][0];
+    c[2][0] = e[2][1] * e[0][2] - e[2][2] * e[0][1];
+    c[2][1] = e[2][2] * e[0][0] - e[2][0] * e[0][2];
+    c[2][2] = e[2][0] * e[0][1] - e[2][1] * e[0][0];
+    c[3][0] = e[0][1] * e[1][2] - e[0][2] * e[1][1];
+    c[3][1] = e[0][2] * e[1][0] - e[0][0] * e[1][2];
+    c[3][2] = e[0][0] * e[1][1] - e[0][1] * e[1][0];
+    const double det = e[0][0] * c[1][0] + e[0][1] * c[1][1] + e[0][2] * c[1][2];
+    const double inv = 1.0 / det;
+    for (int d = 0; d < 3; ++d) {
+      g[1][d] = c[1][d] * inv; g[2][d] = c[2][d] * inv; g[3][d] = c[3][d] * inv;
+      g[0][d] = -(g[1][d] + g[2][d] + g[3][d]);
+    }
+    return fabs(det) / 6.0;
+  }
+  double e1[3], e2[3], nn[3];
+  for (int d = 0; d < 3; ++d) { e1[d] = x[1][d] - x[0][d]; e2[d] = x[2][d] - x[0][d]; }
+  nn[0] = e1[1] * e2[2] - e1[2] * e2[1];
+  nn[1] = e1[2] * e2[0] - e1[0] * e2[2];
+  nn[2] = e1[0] * e2[1] - e1[1] * e2[0];
+  const double n2 = nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2];
+  const double inv = 1.0 / n2;
+  g[1][0] = (e2[1] * nn[2] - e2[2] * nn[1]) * inv;
+  g[1][1] = (e2[2] * nn[0] - e2[0] * nn[2]) * inv;
+  g[1][2] = (e2[0] * nn[1] - e2[1] * nn[0]) * inv;
+  g[2][0] = (nn[1] * e1[2] - nn[2] * e1[1]) * inv;
+  g[2][1] = (nn[2] * e1[0] - nn[0] * e1[2]) * inv;
+  g[2][2] = (nn[0] * e1[1] - nn[1] * e1[0]) * inv;
+  for (int d = 0; d < 3; ++d) { g[0][d] = -(g[1][d] + g[2][d]); g[3][d] = 0.0; }
+  return 0.5 * sqrt(n2);
+}
+
+// D g and D^T g of cell t
+__device__ inline void cell_Dg(int dkind, const double* __restrict__ D, int64_t t, const double gd[3], double (&Dg)[3],
+                               double (&DTg)[3]) {
+  if (dkind == 2) {
+    const double* Dt = D + 9 * t;
+    for (int a = 0; a < 3; ++a) {
+      Dg[a] = Dt[3 * a] * gd[0] + Dt[3 * a + 1] * gd[1] + Dt[3 * a + 2] * gd[2];
+      DTg[a] = Dt[a] * gd[0] + Dt[3 + a] * gd[1] + Dt[6 + a] * gd[2];
+    }
+  } else {
+    const double d0 = dkind == 0 ? D[0] : D[t];
+    for (int a = 0; a < 3; ++a) Dg[a] = DTg[a] = d0 * gd[a];
+  }
+}
+
+// W and C: one thread per CSR nonzero, cell contributions of its segment in ascending contribution id
+// (the same gather as k_assemble; facet contributions of the segment carry nothing here)
+__global__ void __launch_bounds__(TPB) k_strong_cells(int64_t nnz, int cell_nv, uint32_t ncell16,
+                                                      const int64_t* __restrict__ seg, const uint32_t* __restrict__ src,
+                                                      const int32_t* __restrict__ cells, const double* __restrict__ xyz,
+                                                      int dkind, const double* __restrict__ D, double gx, double gy,
+                                                      double gz, double* __restrict__ W, double* __restrict__ G) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= nnz) return;
+  const double gd[3] = {gx, gy, gz};
+  const double dm = (double)(cell_nv - 1);   // d
+  double w = 0.0, c = 0.0;
+  for (int64_t q = seg[p]; q < seg[p + 1]; ++q) {
+    const uint32_t sid = src[q];
+    if (sid >= ncell16) continue;
+    const int64_t t = sid >> 4;
+    const int i = (sid >> 2) & 3, j = sid & 3;
+    if (i >= cell_nv || j >= cell_nv) continue;
+    double g[4][3];
+    const double vol = cell_geometry(xyz, cells, t, cell_nv, g);
+    double Dg[3], DTg[3];
+    cell_Dg(dkind, D, t, gd, Dg, DTg);
+    const double gDg = gd[0] * Dg[0] + gd[1] * Dg[1] + gd[2] * Dg[2];
+    w += gDg * vol * (i == j ? 2.0 : 1.0) / ((dm + 1.0) * (dm + 2.0));
+    c += vol / (dm + 1.0) * ((Dg[0] + DTg[0]) * g[j][0] + (Dg[1] + DTg[1]) * g[j][1] + (Dg[2] + DTg[2]) * g[j][2]);
+  }
+  W[p] = w;
+  G[p] = c;
+}
+
+// ---- facets that bound a compartment
+__global__ void k_strong_facet_keys(int64_t nc, int cell_nv, const int32_t* __restrict__ cells, FacetKey* __restrict__ keys) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nc * 4) return;
+  const int64_t c = i >> 2;
+  const int lf = (int)(i & 3);
+  if (lf >= cell_nv) { keys[i] = FacetKey{NOV, NOV, (uint32_t)i, (uint32_t)i}; return; }
+  uint32_t v[3] = {NOV, NOV, NOV};
+  int m = 0;
+  for (int k = 0; k < cell_nv; ++k)
+    if (k != lf) v[m++] = (uint32_t)cells[c * 4 + k];
+  if (v[0] > v[1]) { uint32_t t = v[0]; v[0] = v[1]; v[1] = t; }
+  if (v[1] > v[2]) { uint32_t t = v[1]; v[1] = v[2]; v[2] = t; }
+  if (v[0] > v[1]) { uint32_t t = v[0]; v[0] = v[1]; v[1] = t; }
+  keys[i] = FacetKey{v[0], v[1], v[2], (uint32_t)i};
+}
+
+struct KeyLess {
+  __host__ __device__ bool operator()(const FacetKey& x, const FacetKey& y) const {
+    if (x.a != y.a) return x.a < y.a;
+    if (x.b != y.b) return x.b < y.b;
+    if (x.c != y.c) return x.c < y.c;
+    return x.cf < y.cf;
+  }
+};
+__device__ inline bool same_key(const FacetKey& x, const FacetKey& y) { return x.a == y.a && x.b == y.b && x.c == y.c; }
+
+// flag[i] = facet i (seen from its cell) bounds the compartment of that cell: exterior, or the neighbour across it
+// lies in the other compartment
+__global__ void k_strong_flag(int64_t nf, const FacetKey* __restrict__ keys, const int32_t* __restrict__ phase,
+                              uint8_t* __restrict__ flag) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nf) return;
+  const FacetKey k = keys[i];
+  if (k.a == NOV) { flag[i] = 0; return; }
+  int64_t other = -1;
+  if (i + 1 < nf && same_key(k, keys[i + 1])) other = i + 1;
+  else if (i > 0 && same_key(k, keys[i - 1])) other = i - 1;
+  uint8_t f = 1;
+  if (other >= 0) f = phase ? (phase[k.cf >> 2] != phase[keys[other].cf >> 2]) : 0;
+  flag[i] = f;
+}
+
+// (row, col, value) of every pair of facet vertices: N[i,j] += (Dg.n_out) int_F phi_i phi_j
+//   = -|T| (Dg . grad lambda_o) (1 + d_ij) / (d + 1),  o = the vertex opposite the facet
+__global__ void k_strong_facet_pairs(int64_t nsel, const int64_t* __restrict__ sel, const FacetKey* __restrict__ keys,
+                                     int cell_nv, const int32_t* __restrict__ cells, const int32_t* __restrict__ cell_dofs,
+                                     const double* __restrict__ xyz, int dkind, const double* __restrict__ D, double gx,
+                                     double gy, double gz, uint64_t* __restrict__ okey, double* __restrict__ oval) {
+  const int nvf = cell_nv - 1;
+  const int per = nvf * nvf;
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= nsel * per) return;
+  const int64_t f = e / per;
+  const int a = (int)(e % per) / nvf, b = (int)(e % per) % nvf;
+  const uint32_t cf = keys[sel[f]].cf;
+  const int64_t t = cf >> 2;
+  const int lf = (int)(cf & 3);
+  const int la = a < lf ? a : a + 1, lb = b < lf ? b : b + 1;   // local vertices of the facet: all but lf
+  double g[4][3];
+  const double vol = cell_geometry(xyz, cells, t, cell_nv, g);
+  const double gd[3] = {gx, gy, gz};
+  double Dg[3], DTg[3];
+  cell_Dg(dkind, D, t, gd, Dg, DTg);
+  const double coef = -vol * (Dg[0] * g[lf][0] + Dg[1] * g[lf][1] + Dg[2] * g[lf][2]) / (double)cell_nv;
+  const uint32_t r = (uint32_t)cell_dofs[4 * t + la], c = (uint32_t)cell_dofs[4 * t + lb];
+  okey[e] = ((uint64_t)r << 32) | c;
+  oval[e] = coef * (a == b ? 2.0 : 1.0);
+}
+
+// sorted (key, value) runs -> G[pos(row, col)] -= sum of the run (one thread per run head, sequential sum)
+__global__ void k_strong_scatter(int64_t n, const uint64_t* __restrict__ key, const double* __restrict__ val,
+                                 const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                                 double* __restrict__ G) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t k = key[i];
+  if (i > 0 && key[i - 1] == k) return;
+  double s = 0.0;
+  for (int64_t j = i; j < n && key[j] == k; ++j) s += val[j];
+  const int r = (int)(k >> 32), c = (int)(k & 0xffffffffu);
+  int lo = rowptr[r], hi = rowptr[r + 1];
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int cm = colidx[mid];
+    if (cm == c) { G[mid] -= s; return; }
+    if (cm < c) lo = mid + 1; else hi = mid;
+  }
+}
+
+// Per time step: SELL operator values for the step that is about to start (ctrl->step_next).
+//   PJs = ((P0 + aA W)/d, G/d),  QJs = ((Q0 - aP W)/d, G/d),  d = P0_rr + aA W_rr (Jacobi) or 1
+//   P0 = M/k + theta K0, Q0 = M/k - theta K0, K0 = S + R + I;  aA = theta cA[n]^2, aP = theta cb[n]^2
+//   (cA[n] = q F(t_n), cb[n] = q F(t_{n-1})).  Nothing to do while both scalars repeat the previous step's.
+__global__ void __launch_bounds__(TPB) k_strong_recombine(int64_t nnz, const KrylovCtrl* __restrict__ ctrl,
+                                                          const double* __restrict__ cA, const double* __restrict__ cb,
+                                                          const int32_t* __restrict__ rowidx,
+                                                          const int32_t* __restrict__ diagpos,
+                                                          const double* __restrict__ M, const double* __restrict__ S,
+                                                          const double* __restrict__ R, const double* __restrict__ I,
+                                                          const double* __restrict__ W, const double* __restrict__ G,
+                                                          double inv_dt, double theta, int jacobi,
+                                                          const int32_t* __restrict__ rowptr,
+                                                          const int32_t* __restrict__ sell_slot,
+                                                          const int32_t* __restrict__ slice_ptr,
+                                                          double2* __restrict__ PJs, double2* __restrict__ QJs) {
+  if (ctrl->failed) return;
+  const int n = ctrl->step_next;
+  const double aA = theta * cA[n] * cA[n], aP = theta * cb[n] * cb[n];
+  if (n > 0 && cA[n] * cA[n] == cA[n - 1] * cA[n - 1] && cb[n] * cb[n] == cb[n - 1] * cb[n - 1]) return;
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  const int row = rowidx[k];
+  const int slot = sell_slot[row];
+  if (slot < 0) return;
+  const int dp = diagpos[row];
+  const double pd = M[dp] * inv_dt + theta * (S[dp] + R[dp] + I[dp]) + aA * W[dp];
+  const double di = jacobi ? 1.0 / pd : 1.0;
+  const double mk = M[k] * inv_dt, k0 = theta * (S[k] + R[k] + I[k]);
+  const double gv = G[k] * di;
+  const int pos = slice_ptr[slot >> 5] + (int)(k - rowptr[row]) * 32 + (slot & 31);
+  PJs[pos] = make_double2((mk + k0 + aA * W[k]) * di, gv);
+  QJs[pos] = make_double2((mk - k0 - aP * W[k]) * di, gv);
+}
+
+}  // namespace
+
+// W and G = C - N for gradient direction g (unit), CSR order, into h->d_strongW / h->d_strongG
+void bt_strong_build(btfem* h, const double g[3]) {
+  cudaStream_t st = h->stream;
+  BT_REQUIRE(h->cell_nv >= 3, "strong periodic BC: tetrahedral or triangle meshes");
+  BT_REQUIRE(h->nv_own < 0, "strong periodic BC: whole-mesh handles");
+  h->d_strongW.alloc(h->nnz);
+  h->d_strongG.alloc(h->nnz);
+  h->d_D.upload(h->h_D.data(), h->h_D.size(), st);
+  k_strong_cells<<<nblocks(h->nnz), TPB, 0, st>>>(h->nnz, h->cell_nv, (uint32_t)(16 * h->nc), h->d_seg.p, h->d_src.p,
+                                                  h->d_tets.p, h->d_xyz.p, h->dkind, h->d_D.p, g[0], g[1], g[2],
+                                                  h->d_strongW.p, h->d_strongG.p);
+  BT_CUDA(cudaGetLastError());
+  // bounding facets
+  const int64_t nf = 4 * h->nc;
+  DevArray<FacetKey> keys;
+  keys.alloc(nf);
+  k_strong_facet_keys<<<nblocks(nf), TPB, 0, st>>>(h->nc, h->cell_nv, h->d_tets.p, keys.p);
+  Tmp tmp;
+  size_t bytes = 0;
+  BT_CUDA(cub::DeviceMergeSort::SortKeys(nullptr, bytes, keys.p, nf, KeyLess(), st));
+  tmp.reserve(bytes);
+  BT_CUDA(cub::DeviceMergeSort::SortKeys(tmp.p, bytes, keys.p, nf, KeyLess(), st));
+  DevArray<uint8_t> flag;
+  flag.alloc(nf);
+  k_strong_flag<<<nblocks(nf), TPB, 0, st>>>(nf, keys.p, h->two_comp ? h->d_phase.p : nullptr, flag.p);
+  DevArray<int64_t> sel, nsel;
+  sel.alloc(nf);
+  nsel.alloc(1);
+  cub::CountingInputIterator<int64_t> idx(0);
+  bytes = 0;
+  BT_CUDA(cub::DeviceSelect::Flagged(nullptr, bytes, idx, flag.p, sel.p, nsel.p, nf, st));
+  tmp.reserve(bytes);
+  BT_CUDA(cub::DeviceSelect::Flagged(tmp.p, bytes, idx, flag.p, sel.p, nsel.p, nf, st));
+  int64_t ns = 0;
+  nsel.download(&ns, st);
+  if (ns > 0) {
+    const int nvf = h->cell_nv - 1;
+    const int64_t ne = ns * nvf * nvf;
+    DevArray<uint64_t> k_in, k_out;
+    DevArray<double> v_in, v_out;
+    k_in.alloc(ne); k_out.alloc(ne); v_in.alloc(ne); v_out.alloc(ne);
+    k_strong_facet_pairs<<<nblocks(ne), TPB, 0, st>>>(ns, sel.p, keys.p, h->cell_nv, h->d_tets.p, h->d_cell_dofs.p,
+                                                      h->d_xyz.p, h->dkind, h->d_D.p, g[0], g[1], g[2], k_in.p, v_in.p);
+    int bits = 1;
+    while ((1LL << bits) < h->ndof) ++bits;
+    bytes = 0;
+    BT_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k_in.p, k_out.p, v_in.p, v_out.p, ne, 0, 32 + bits, st));
+    tmp.reserve(bytes);
+    BT_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, k_in.p, k_out.p, v_in.p, v_out.p, ne, 0, 32 + bits, st));
+    k_strong_scatter<<<nblocks(ne), TPB, 0, st>>>(ne, k_out.p, v_out.p, h->d_rowptr.p, h->d_colidx.p, h->d_strongG.p);
+  }
+  BT_CUDA(cudaGetLastError());
+  BT_CUDA(cudaStreamSynchronize(st));   // temporaries go out of scope
+}
+
+// queued (or captured) at the start of every time step, before the right-hand-side SpMV
+void bt_strong_recombine(btfem* h, cudaStream_t st, double dt, double theta, int pc) {
+  k_strong_recombine<<<nblocks(h->nnz), TPB, 0, st>>>(
+      h->nnz, h->d_ctrl.p, h->d_cA.p, h->d_cb.p, h->d_rowidx.p, h->d_diagpos.p, h->d_vals[0].p, h->d_vals[1].p,
+      h->d_vals[2].p, h->d_vals[6].p, h->d_strongW.p, h->d_strongG.p, 1.0 / dt, theta, pc == BTFEM_PC_JACOBI ? 1 : 0,
+      h->d_rowptr.p, h->d_sell_slot.p, h->d_slice_ptr.p, h->d_PJs.p, h->d_QJs.p);
+}
+
+void bt_strong_get(btfem* h, const double g[3], double* W, double* G) {
+  bt_strong_build(h, g);
+  if (W) h->d_strongW.download(W, h->stream);
+  if (G) h->d_strongG.download(G, h->stream);
+}

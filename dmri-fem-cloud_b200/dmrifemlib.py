@@ -271,17 +271,24 @@ class MyDomain():
                 D[:, i, j] = np.broadcast_to(np.asarray(rows[i][j], dtype=float), (nc,))
         self.D = D
 
+    def is_strongly_periodic(self):
+        """ThetaMethodF/L pick the sBC forms when IsDomainPeriodic and a periodic direction (DmriFemLib.py:622-650)."""
+        return bool(self.IsDomainPeriodic) and sum(self.PeriodicDir) > 0
+
     def Apply(self):
-        if self.IsDomainPeriodic and sum(self.PeriodicDir) > 0:
-            raise NotImplementedError("strongly imposed pseudo-periodic BC (FuncF_sBC, DmriFemLib.py:148-238) "
-                                      "is outside the accelerated path; use the weak form (IsDomainPeriodic=False)")
+        if self.is_strongly_periodic() and self.tdim < self.gdim:
+            raise NotImplementedError("strong pseudo-periodic BC on a manifold mesh")
         if self.IsDomainMultiple:
             print("Function Space for Two-compartment Domains has 4 components")
             print("(ur0, ui0, ur1, ur1): r-real, i-imaginary")
         else:
             print("Function Space for Single Domains has 2 components")
             print("(ur, ui): r-real, i-imaginary")
-        if sum(self.PeriodicDir) > 0:
+        if self.is_strongly_periodic():
+            print("Initialize peridodic function spaces.")           # sic (DmriFemLib.py:479)
+            print("The pseudo-periodic BCS are strongly imposed.")
+            print("The mesh needs to be periodic.")
+        elif sum(self.PeriodicDir) > 0:
             print("The pseudo-periodic BCS are weakly imposed.")
             print("The mesh does not need to be periodic.")
 
@@ -307,14 +314,20 @@ class MyDomain():
                 fem.set_permeability(np.asarray(self.kappa, dtype=float), self.kappa_marker)
         if self.gdim == 2:
             self.PeriodicDir = [self.PeriodicDir[0], self.PeriodicDir[1], 0]     # no z faces (DmriFemLib.py:602-605)
-        if sum(self.PeriodicDir) > 0:
+        lo, hi = [self.xmin, self.ymin, self.zmin], [self.xmax, self.ymax, self.zmax]
+        if self.is_strongly_periodic():
+            from . import periodic
+            fem.set_periodic_map(periodic.vertex_map(self.mymesh.xyz, self.PeriodicDir, lo, hi, self.tol))
+        else:
+            fem.set_periodic_map(None)
+        if sum(self.PeriodicDir) > 0 and not self.is_strongly_periodic():
             if self.tdim < self.gdim:
                 raise NotImplementedError("weak pseudo-periodic BC on a manifold mesh (curve or surface in 3-D)")
             fem.set_periodic(self.PeriodicDir, self.kappa_e_scalar, self.tol,
                              [self.xmin, self.ymin, self.zmin], [self.xmax, self.ymax, self.zmax])
         fem.set_initial(ic)
         fem.assemble()
-        if sum(self.PeriodicDir) > 0:
+        if sum(self.PeriodicDir) > 0 and not self.is_strongly_periodic():
             from . import periodic
             dv, dc = fem.dofmap()
             fem.set_periodic_gather(*periodic.build_gather(
@@ -361,6 +374,10 @@ class MRI_simulation():
                 print('t: %6.2f ' % ts[n], 'T: %6.2f' % mri_para.T, 'dt: %.1f' % self.k, 'qvalue: %e' % q,
                       'Completed %3.2f%%' % (float(ts[n]) / float(mri_para.T + self.k) * 100.0))
         g = mri_para.gdir.array() if hasattr(mri_para.gdir, "array") else np.asarray(mri_para.gdir, dtype=float)
+        if mydomain.is_strongly_periodic():
+            # transformed equation (FuncF_sBC): the forms read the INTEGRATED profile, ift at t for the matrix and
+            # at tp for the right-hand side (DmriFemLib.py:901-902 with :166-238)
+            ft, ftp = ift, iftp
         try:
             self.stats = fem.solve(self.k, self.theta, q * ft, q * ftp, g, q=q, Fb=iftp,
                                    ksp=linsolver.method, pc=linsolver.preconditioner,

@@ -87,6 +87,38 @@ def _locate_1d(p, seg_x):
     return best, W[rows, best]
 
 
+def vertex_map(xyz, pdir, lo, hi, tol):
+    """Strongly imposed periodicity (`constrained_domain = PeriodicBD`, DmriFemLib.py:327-375): the master vertex of
+    every vertex.  A vertex within `tol` of the max face of a periodic direction (PeriodicBD.map) is identified with
+    the vertex at the same place on the min face (PeriodicBD.inside: the min faces are the masters); vertices on
+    edges / corners of the box wrap in every periodic direction they touch.  The mesh has to be periodic: a max-face
+    vertex without a partner raises.  (PeriodicBD uses tol = 1e-2*hmin, :334.)"""
+    xyz = np.asarray(xyz, dtype=float)
+    if xyz.shape[1] == 2:
+        xyz = np.hstack([xyz, np.zeros((len(xyz), 1))])
+    nv = len(xyz)
+    wrapped = xyz.copy()
+    slave = np.zeros(nv, dtype=bool)
+    for d in range(3):
+        if pdir[d]:
+            on = np.abs(xyz[:, d] - hi[d]) < tol
+            wrapped[on, d] = lo[d]
+            slave |= on
+    cell = np.floor(wrapped / tol + 0.5).astype(np.int64)        # grid of spacing tol: coincident points share a cell
+    _, inv = np.unique(cell, axis=0, return_inverse=True)
+    inv = inv.ravel()
+    masters = np.nonzero(~slave)[0]
+    owner = -np.ones(inv.max() + 1, dtype=np.int64)
+    if len(np.unique(inv[masters])) != len(masters):
+        raise RuntimeError("periodic map: distinct vertices coincide within tol")
+    owner[inv[masters]] = masters
+    vm = owner[inv]
+    if (vm < 0).any():
+        raise RuntimeError("the mesh is not periodic: %d vertices on a max face have no partner on the min face"
+                           % int((vm < 0).sum()))
+    return vm.astype(np.int32)
+
+
 def build_gather(xyz, tets, phase, pdir, lo, hi, dof_vertex, dof_comp, bfacets=None):
     """Returns dof (nb,), src (nb,3) dof ids or -1, w (nb,3), dx (nb,3).
 

@@ -74,6 +74,19 @@ int btfem_set_mesh_tri(btfem_t* h, int64_t nv, const double* xyz /*[nv*3]*/, int
 int btfem_set_mesh_seg(btfem_t* h, int64_t nv, const double* xyz /*[nv*3]*/, int64_t nc,
                        const int32_t* segs /*[nc*2]*/);
 
+/* Strongly imposed pseudo-periodic BC (`IsDomainPeriodic = True` with a periodic direction: FuncF_sBC,
+ * outer_interface, inner_interface, ThetaMethodF/L_sBC1c/2c and `constrained_domain = PeriodicBD`,
+ * DmriFemLib.py:147-238, 327-375, 478-483).  vmaster[v] = the vertex on the min face that vertex v of a max face is
+ * identified with (v itself otherwise; host search: periodic.vertex_map).  Slave vertices then carry their
+ * master's dofs and btfem_solve steps the TRANSFORMED equation: pass cA[n] = q*F(t_n), cb[n] = q*F(t_{n-1}) (the
+ * integrated profile, DmriFemLib.py:901-902) instead of q*f.  NULL: back to the default.  Call before
+ * btfem_assemble.  BiCGStab, whole-mesh handles, tetrahedra or triangles.
+ * (Compiled and restated by the oracle; GPU parity tests pending -- see csrc/strong.cu.) */
+int btfem_set_periodic_map(btfem_t* h, const int32_t* vmaster /*[nv] or NULL*/);
+/* parity hook: W[i,j] = int (g.Dg) phi_i phi_j and G = C - N of the transformed equation, CSR order */
+int btfem_get_strong_operators(btfem_t* h, const double gdir[3], double* W /*[nnz] or NULL*/,
+                               double* G /*[nnz] or NULL*/);
+
 /* Replace only the phase function of the current mesh (NULL = one compartment). */
 int btfem_set_phase(btfem_t* h, const int32_t* phase /*[nc] or NULL*/);
 /* mesh.hmin()/hmax() as used by MyDomain (DmriFemLib.py:588-589): min / max over cells of the cell size,

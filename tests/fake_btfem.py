@@ -12,6 +12,7 @@ class FakeBTFem:
         self.device = device
         self.D, self.invT2, self.kappa, self.kmarker = 1.0, 0.0, 0.0, None
         self.periodic = None
+        self.vmaster = None
         self.ic = None
         self.h2d_bytes = 0
         self.calls = []
@@ -53,6 +54,9 @@ class FakeBTFem:
     def set_periodic(self, pdir, kappa_e, tol, lo, hi):
         self.periodic = (list(pdir), np.asarray(lo, float), np.asarray(hi, float))
 
+    def set_periodic_map(self, vmaster=None):
+        self.vmaster = None if vmaster is None else np.asarray(vmaster)
+
     def boundary_facets(self):
         return None
 
@@ -74,6 +78,8 @@ class FakeBTFem:
             pdir, lo, hi = self.periodic
             hmin, _ = self.mesh_stats()
             kw["bnd_kappa_vertex"] = orc.periodic_marker(orc.as_xyz3(self.xyz), pdir, lo, hi, hmin)
+        if self.vmaster is not None:
+            kw["vmaster"] = self.vmaster
         self.ops = orc.assemble(self.xyz, self.tets, self.phase, D=self.D, invT2=self.invT2, **kw)
         self.ndof, self.nnz = self.ops.ndof, self.ops.nnz
         self.calls.append("assemble")
@@ -96,6 +102,14 @@ class FakeBTFem:
         import scipy.sparse.linalg as spla
         u = ic.astype(complex)
         lus = {}
+        if self.vmaster is not None:          # transformed equation: cA = q F(t_n), cb = q F(t_{n-1}), theta on both sides
+            W, G = orc.strong_operators(ops, g)
+            for n in range(len(cA)):
+                b = (ops.M / dt - theta * (K0 + cb[n] ** 2 * W)) @ u - 1j * theta * cb[n] * (G @ u)
+                if cA[n] not in lus:
+                    lus[cA[n]] = spla.splu((ops.M / dt + theta * (K0 + cA[n] ** 2 * W) + 1j * theta * cA[n] * G).tocsc())
+                u = lus[cA[n]].solve(b)
+            cA = []
         for n in range(len(cA)):
             b = Q @ u - 1j * (1.0 - theta) * cb[n] * (Jg @ u)
             if per is not None:

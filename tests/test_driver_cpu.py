@@ -131,3 +131,44 @@ def test_sweep_batches_and_sharding(fake):
     ref = orc.theta_solve(fem.ops, seq, seq.q_from_b(2000.0), dirs[1], 200.0, solver="lu")
     assert abs(full[1 * 2 + 1] - ref["signal"] / ref["voi"]) <= 1e-10
     assert full[1] < full[0] < 1.0                      # higher b, lower signal
+
+
+def test_driver_strong_periodic_flow(tmp_path, monkeypatch, fake):
+    """IsDomainPeriodic = True with PeriodicDir = [1,1,0]: the driver identifies the vertices of opposite faces
+    (periodic.vertex_map == the oracle's), hands the INTEGRATED profile to the solver, and the result equals the
+    oracle's transformed-equation stepping."""
+    from dmri_fem_cloud_b200 import periodic
+    monkeypatch.chdir(tmp_path)
+    xyz, tets, ph = meshes.box_with_sphere(4.0, 5, 2.5)
+    lo, hi, hmin, _ = orc.domain_sizes(xyz, tets)
+    vm = periodic.vertex_map(xyz, [1, 1, 0], lo, hi, 1e-2 * hmin)
+    assert np.array_equal(vm, orc.periodic_vertex_map(xyz, [1, 1, 0], lo, hi, 1e-2 * hmin))
+    assert np.array_equal(periodic.vertex_map(xyz, [1, 1, 1], lo, hi, 1e-2 * hmin),
+                          orc.periodic_vertex_map(xyz, [1, 1, 1], lo, hi, 1e-2 * hmin))
+    with pytest.raises(RuntimeError):
+        bad = xyz.copy()
+        bad[np.argmax(bad[:, 0] + 1e-3 * bad[:, 1])] += [0.0, 0.3, 0.0]
+        periodic.vertex_map(bad, [1, 0, 0], lo, hi, 1e-2 * hmin)
+    mesh = dl.Mesh(xyz, tets)
+    mp = dl.MRI_parameters()
+    mp.bvalue = 1000
+    mp.delta, mp.Delta = 1000.0, 3000.0
+    mp.T = mp.delta + mp.Delta
+    mp.fs_sym = sp.Piecewise((1., mp.s < mp.delta), (0., mp.s < mp.Delta), (-1., mp.s < mp.T), (0., True))
+    mp.set_gradient_dir(mesh, 1, 0.5, 0)
+    mp.Apply()
+    sim = dl.MRI_simulation()
+    sim.k = 100
+    sim.verbose = False
+    md = dl.MyDomain(mesh, mp)
+    md.phase, md.IsDomainMultiple, md.kappa = ph, True, 5e-5
+    md.PeriodicDir, md.IsDomainPeriodic = [1, 1, 0], True
+    md.Apply()
+    md.D0 = 2e-3
+    md.D = md.D0
+    sim.solve(md, mp, dl.KrylovSolver("bicgstab", "jacobi"))
+    ops = orc.assemble(xyz, tets, ph, D=2e-3, invT2=1e-16, kappa=5e-5, vmaster=vm)
+    seq = orc.pgse(1000.0, 3000.0)
+    ref = orc.theta_solve_strong(ops, seq, mp.qvalue, [1, 0.5, 0], 100.0)
+    assert abs(sim.stats["signal"] - ref["signal"]) <= 1e-10 * abs(ref["signal"])
+    assert sim.fem.periodic is None and sim.fem.vmaster is not None      # no weak marker in this mode
