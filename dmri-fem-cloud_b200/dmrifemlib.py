@@ -318,8 +318,10 @@ class MyDomain():
         if self.is_strongly_periodic():
             from . import periodic
             fem.set_periodic_map(periodic.vertex_map(self.mymesh.xyz, self.PeriodicDir, lo, hi, self.tol))
-        else:
+            self._strong_map = True
+        elif getattr(self, "_strong_map", False):      # the handle is re-used: back to the default dof map
             fem.set_periodic_map(None)
+            self._strong_map = False
         if sum(self.PeriodicDir) > 0 and not self.is_strongly_periodic():
             if self.tdim < self.gdim:
                 raise NotImplementedError("weak pseudo-periodic BC on a manifold mesh (curve or surface in 3-D)")
