@@ -27,6 +27,7 @@
 #include <cub/cub.cuh>
 
 #include "btfem_internal.cuh"
+#include "strong_math.cuh"
 
 namespace {
 
@@ -46,66 +47,6 @@ struct Tmp {
   }
 };
 
-// measure |T| and the gradients of the barycentric functions of cell t (tetrahedron or triangle in R^3)
-__device__ inline double cell_geometry(const double* __restrict__ xyz, const int32_t* __restrict__ cells, int64_t t,
-                                       int cell_nv, double (&g)[4][3]) {
-  double x[4][3];
-  for (int k = 0; k < cell_nv; ++k)
-    for (int d = 0; d < 3; ++d) x[k][d] = xyz[3 * (int64_t)cells[4 * t + k] + d];
-  if (cell_nv == 4) {
-    double e[3][3];
-    for (int k = 0; k < 3; ++k)
-      for (int d = 0; d < 3; ++d) e[k][d] = x[k + 1][d] - x[0][d];
-    double c[4][3];
-    c[1][0] = e[1][1] * e[2][2] - e[1][2] * e[2][1];
-    c[1][1] = e[1][2] * e[2][0] - e[1][0] * e[2][2];
-    c[1][2] = e[1][0] * e[2][1] - e[1][1] * e[2][0];
-    c[2][0] = e[2][1] * e[0][2] - e[2][2] * e[0][1];
-    c[2][1] = e[2][2] * e[0][0] - e[2][0] * e[0][2];
-    c[2][2] = e[2][0] * e[0][1] - e[2][1] * e[0][0];
-    c[3][0] = e[0][1] * e[1][2] - e[0][2] * e[1][1];
-    c[3][1] = e[0][2] * e[1][0] - e[0][0] * e[1][2];
-    c[3][2] = e[0][0] * e[1][1] - e[0][1] * e[1][0];
-    const double det = e[0][0] * c[1][0] + e[0][1] * c[1][1] + e[0][2] * c[1][2];
-    const double inv = 1.0 / det;
-    for (int d = 0; d < 3; ++d) {
-      g[1][d] = c[1][d] * inv; g[2][d] = c[2][d] * inv; g[3][d] = c[3][d] * inv;
-      g[0][d] = -(g[1][d] + g[2][d] + g[3][d]);
-    }
-    return fabs(det) / 6.0;
-  }
-  double e1[3], e2[3], nn[3];
-  for (int d = 0; d < 3; ++d) { e1[d] = x[1][d] - x[0][d]; e2[d] = x[2][d] - x[0][d]; }
-  nn[0] = e1[1] * e2[2] - e1[2] * e2[1];
-  nn[1] = e1[2] * e2[0] - e1[0] * e2[2];
-  nn[2] = e1[0] * e2[1] - e1[1] * e2[0];
-  const double n2 = nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2];
-  const double inv = 1.0 / n2;
-  g[1][0] = (e2[1] * nn[2] - e2[2] * nn[1]) * inv;
-  g[1][1] = (e2[2] * nn[0] - e2[0] * nn[2]) * inv;
-  g[1][2] = (e2[0] * nn[1] - e2[1] * nn[0]) * inv;
-  g[2][0] = (nn[1] * e1[2] - nn[2] * e1[1]) * inv;
-  g[2][1] = (nn[2] * e1[0] - nn[0] * e1[2]) * inv;
-  g[2][2] = (nn[0] * e1[1] - nn[1] * e1[0]) * inv;
-  for (int d = 0; d < 3; ++d) { g[0][d] = -(g[1][d] + g[2][d]); g[3][d] = 0.0; }
-  return 0.5 * sqrt(n2);
-}
-
-// D g and D^T g of cell t
-__device__ inline void cell_Dg(int dkind, const double* __restrict__ D, int64_t t, const double gd[3], double (&Dg)[3],
-                               double (&DTg)[3]) {
-  if (dkind == 2) {
-    const double* Dt = D + 9 * t;
-    for (int a = 0; a < 3; ++a) {
-      Dg[a] = Dt[3 * a] * gd[0] + Dt[3 * a + 1] * gd[1] + Dt[3 * a + 2] * gd[2];
-      DTg[a] = Dt[a] * gd[0] + Dt[3 + a] * gd[1] + Dt[6 + a] * gd[2];
-    }
-  } else {
-    const double d0 = dkind == 0 ? D[0] : D[t];
-    for (int a = 0; a < 3; ++a) Dg[a] = DTg[a] = d0 * gd[a];
-  }
-}
-
 // W and C: one thread per CSR nonzero, cell contributions of its segment in ascending contribution id
 // (the same gather as k_assemble; facet contributions of the segment carry nothing here)
 __global__ void __launch_bounds__(TPB) k_strong_cells(int64_t nnz, int cell_nv, uint32_t ncell16,
@@ -116,7 +57,6 @@ __global__ void __launch_bounds__(TPB) k_strong_cells(int64_t nnz, int cell_nv, 
   const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (p >= nnz) return;
   const double gd[3] = {gx, gy, gz};
-  const double dm = (double)(cell_nv - 1);   // d
   double w = 0.0, c = 0.0;
   for (int64_t q = seg[p]; q < seg[p + 1]; ++q) {
     const uint32_t sid = src[q];
@@ -124,13 +64,10 @@ __global__ void __launch_bounds__(TPB) k_strong_cells(int64_t nnz, int cell_nv, 
     const int64_t t = sid >> 4;
     const int i = (sid >> 2) & 3, j = sid & 3;
     if (i >= cell_nv || j >= cell_nv) continue;
-    double g[4][3];
-    const double vol = cell_geometry(xyz, cells, t, cell_nv, g);
-    double Dg[3], DTg[3];
-    cell_Dg(dkind, D, t, gd, Dg, DTg);
-    const double gDg = gd[0] * Dg[0] + gd[1] * Dg[1] + gd[2] * Dg[2];
-    w += gDg * vol * (i == j ? 2.0 : 1.0) / ((dm + 1.0) * (dm + 2.0));
-    c += vol / (dm + 1.0) * ((Dg[0] + DTg[0]) * g[j][0] + (Dg[1] + DTg[1]) * g[j][1] + (Dg[2] + DTg[2]) * g[j][2]);
+    double wc, cc;
+    strong_cell_wc(xyz, cells, t, cell_nv, i, j, dkind, D, gd, &wc, &cc);
+    w += wc;
+    c += cc;
   }
   W[p] = w;
   G[p] = c;
@@ -195,12 +132,8 @@ __global__ void k_strong_facet_pairs(int64_t nsel, const int64_t* __restrict__ s
   const int64_t t = cf >> 2;
   const int lf = (int)(cf & 3);
   const int la = a < lf ? a : a + 1, lb = b < lf ? b : b + 1;   // local vertices of the facet: all but lf
-  double g[4][3];
-  const double vol = cell_geometry(xyz, cells, t, cell_nv, g);
   const double gd[3] = {gx, gy, gz};
-  double Dg[3], DTg[3];
-  cell_Dg(dkind, D, t, gd, Dg, DTg);
-  const double coef = -vol * (Dg[0] * g[lf][0] + Dg[1] * g[lf][1] + Dg[2] * g[lf][2]) / (double)cell_nv;
+  const double coef = strong_facet_coef(xyz, cells, t, cell_nv, lf, dkind, D, gd);
   const uint32_t r = (uint32_t)cell_dofs[4 * t + la], c = (uint32_t)cell_dofs[4 * t + lb];
   okey[e] = ((uint64_t)r << 32) | c;
   oval[e] = coef * (a == b ? 2.0 : 1.0);
@@ -255,10 +188,11 @@ __global__ void __launch_bounds__(TPB) k_strong_recombine(int64_t nnz, const Kry
   const double pd = M[dp] * inv_dt + theta * (S[dp] + R[dp] + I[dp]) + aA * W[dp];
   const double di = jacobi ? 1.0 / pd : 1.0;
   const double mk = M[k] * inv_dt, k0 = theta * (S[k] + R[k] + I[k]);
-  const double gv = G[k] * di;
+  double pv, qv, jv;
+  strong_combine_entry(mk, k0, W[k], G[k], aA, aP, di, &pv, &qv, &jv);
   const int pos = slice_ptr[slot >> 5] + (int)(k - rowptr[row]) * 32 + (slot & 31);
-  PJs[pos] = make_double2((mk + k0 + aA * W[k]) * di, gv);
-  QJs[pos] = make_double2((mk - k0 - aP * W[k]) * di, gv);
+  PJs[pos] = make_double2(pv, jv);
+  QJs[pos] = make_double2(qv, jv);
 }
 
 }  // namespace

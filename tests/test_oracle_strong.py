@@ -113,3 +113,77 @@ def test_tiling_the_unit_cell_does_not_change_the_signal():
     neu = orc.theta_solve(orc.assemble(xyz, tets, ph, D=np.where(ph == 1, 1e-3, 2e-3), kappa=5e-5), seq, q, g, k,
                           solver="lu")
     assert abs(neu["signal"] / neu["voi"] - r1["signal"] / r1["voi"]) > 0.05      # periodicity matters here
+
+
+def _host_harness(tmp_path):
+    """g++ build of tests/strong_host_check.cpp: the SAME header the CUDA kernels include (csrc/strong_math.cuh)."""
+    import ctypes
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = str(tmp_path / "libstronghost.so")
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", os.path.join(here, "strong_host_check.cpp"),
+                           "-o", so])
+    return ctypes.CDLL(so)
+
+
+def test_kernel_arithmetic_of_strong_mode_matches_oracle(tmp_path):
+    """csrc/strong_math.cuh (what k_strong_cells / k_strong_facet_pairs / k_strong_recombine evaluate), compiled for
+    the host, against oracle.strong_operators -- tetrahedra with a full tensor D per cell and a two-compartment
+    triangle mesh.  Covers the formulas and signs of W, C and the facet terms; the sort / scatter plumbing around
+    them is exercised by the (opt-in) GPU tests."""
+    import ctypes as C
+    import scipy.sparse as sps
+    lib = _host_harness(tmp_path)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    rng = np.random.default_rng(3)
+    xyz, tets, ph = meshes.box_with_sphere(2.0, 3, 1.2)
+    xyz = xyz + 0.05 * rng.standard_normal(xyz.shape)
+    A = rng.normal(size=(len(tets), 3, 3))
+    Dt = 1e-3 * (np.einsum("cab,cdb->cad", A, A) + 0.3 * rng.normal(size=(len(tets), 3, 3)))     # not symmetric
+    xy, tris, lay = meshes.disk_triangulation((2.0, 3.0), (2, 2), 10)
+    for x, cells, phase, D, dkind in ((xyz, tets, ph, Dt, 2), (orc.as_xyz3(xy), tris, (lay % 2).astype(np.int32),
+                                                               np.array([2e-3, 1e-3])[lay], 1)):
+        nc, nvc = cells.shape
+        g = np.array([0.3, -0.5, 0.8 if nvc == 4 else 0.0])
+        g /= np.linalg.norm(g)
+        ops = orc.assemble(x, cells, phase, D=D, kappa=1e-5)
+        Wo, Go = orc.strong_operators(ops, g)
+        cells4 = -np.ones((nc, 4), dtype=np.int32)
+        cells4[:, :nvc] = cells
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        Dc = np.ascontiguousarray(D, dtype=np.float64)
+        W = np.zeros((nc, 4, 4))
+        Cm = np.zeros((nc, 4, 4))
+        coef = np.zeros((nc, 4))
+        lib.strong_host_cells(C.c_int64(nc), nvc, dp(x), ip(cells4), dkind, dp(Dc), dp(g), dp(W), dp(Cm))
+        lib.strong_host_facets(C.c_int64(nc), nvc, dp(x), ip(cells4), dkind, dp(Dc), dp(g), dp(coef))
+        n = ops.ndof
+        rows = np.repeat(ops.cell_dofs, nvc, axis=1).ravel()
+        cols = np.tile(ops.cell_dofs, (1, nvc)).ravel()
+        Wk = sps.coo_matrix((W[:, :nvc, :nvc].ravel(), (rows, cols)), shape=(n, n)).tocsr()
+        Ck = sps.coo_matrix((Cm[:, :nvc, :nvc].ravel(), (rows, cols)), shape=(n, n)).tocsr()
+        # bounding facets the way k_strong_flag picks them: exterior, or the neighbour is in the other compartment
+        f, cell, lf = orc.facets(cells)
+        same_next = np.zeros(len(f), dtype=bool)
+        same_next[:-1] = np.all(f[1:] == f[:-1], axis=1)
+        same_prev = np.zeros(len(f), dtype=bool)
+        same_prev[1:] = same_next[:-1]
+        partner = np.where(same_next, np.roll(cell, -1), np.where(same_prev, np.roll(cell, 1), -1))
+        bnd = (partner < 0) | (phase[np.maximum(partner, 0)] != phase[cell])
+        rr, cc, vv = [], [], []
+        for t, l in zip(cell[bnd], lf[bnd]):
+            loc = [k for k in range(nvc) if k != l]                  # la = a < lf ? a : a + 1
+            for a_ in range(nvc - 1):
+                for b_ in range(nvc - 1):
+                    rr.append(ops.cell_dofs[t, loc[a_]])
+                    cc.append(ops.cell_dofs[t, loc[b_]])
+                    vv.append(coef[t, l] * (2.0 if a_ == b_ else 1.0))
+        Nk = sps.coo_matrix((vv, (rr, cc)), shape=(n, n)).tocsr()
+        assert abs(Wk - Wo).max() <= 1e-15 * abs(Wo).max()
+        assert abs((Ck - Nk) - Go).max() <= 1e-13 * abs(Go).max()
+    out = np.zeros(3)
+    lib.strong_host_combine(C.c_double(2.0), C.c_double(0.5), C.c_double(0.25), C.c_double(-0.75), C.c_double(4.0),
+                            C.c_double(8.0), C.c_double(0.1), dp(out))
+    assert np.allclose(out, [(2.0 + 0.5 + 4.0 * 0.25) * 0.1, (2.0 - 0.5 - 8.0 * 0.25) * 0.1, -0.075], rtol=1e-15)
