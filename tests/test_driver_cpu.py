@@ -139,6 +139,7 @@ def test_driver_strong_periodic_flow(tmp_path, monkeypatch, fake):
     oracle's transformed-equation stepping."""
     from dmri_fem_cloud_b200 import periodic
     monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("BTFEM_STRONG", "1")              # the mode is opt-in until it has run on hardware
     xyz, tets, ph = meshes.box_with_sphere(4.0, 5, 2.5)
     lo, hi, hmin, _ = orc.domain_sizes(xyz, tets)
     vm = periodic.vertex_map(xyz, [1, 1, 0], lo, hi, 1e-2 * hmin)
@@ -163,6 +164,10 @@ def test_driver_strong_periodic_flow(tmp_path, monkeypatch, fake):
     md = dl.MyDomain(mesh, mp)
     md.phase, md.IsDomainMultiple, md.kappa = ph, True, 5e-5
     md.PeriodicDir, md.IsDomainPeriodic = [1, 1, 0], True
+    monkeypatch.delenv("BTFEM_STRONG")
+    with pytest.raises(NotImplementedError):
+        md.Apply()
+    monkeypatch.setenv("BTFEM_STRONG", "1")
     md.Apply()
     md.D0 = 2e-3
     md.D = md.D0
