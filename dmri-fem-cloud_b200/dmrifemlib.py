@@ -323,6 +323,7 @@ class MyDomain():
         if self.is_strongly_periodic():
             from . import periodic
             fem.set_periodic_map(periodic.vertex_map(self.mymesh.xyz, self.PeriodicDir, lo, hi, self.tol))
+            fem.set_periodic([0, 0, 0], 0.0, 0.0, lo, hi)      # no artificial-permeability marker in this mode
             self._strong_map = True
         elif getattr(self, "_strong_map", False):      # the handle is re-used: back to the default dof map
             fem.set_periodic_map(None)
