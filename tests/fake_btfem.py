@@ -52,7 +52,7 @@ class FakeBTFem:
         self.kappa, self.kmarker = kappa, marker
 
     def set_periodic(self, pdir, kappa_e, tol, lo, hi):
-        self.periodic = (list(pdir), np.asarray(lo, float), np.asarray(hi, float))
+        self.periodic = (list(pdir), np.asarray(lo, float), np.asarray(hi, float)) if sum(pdir) > 0 else None
 
     def set_periodic_map(self, vmaster=None):
         self.vmaster = None if vmaster is None else np.asarray(vmaster)
