@@ -17,6 +17,9 @@ complex unknowns (the reference would count W.dim() = 4 x N_vert = 2x more for t
   roofline fused complex SpMV kernel: algorithmic bytes 20*nnz + 36*n per launch over the
            CUDA-event time of one launch with L2 flushed before it
   cpu_baseline  the oracle's C/OpenMP restatement on a bounded sample of the same workload
+  loop_roofline the whole Krylov loop (algorithmic bytes of all iterations over the device loop time)
+  hardi    BASELINE.json's third figure, dMRI signals/s: the 64 x 4 HARDI sweep of configs[4] sharded over the
+           N ranks (skip with --no-hardi); a failure there is reported in the key and never blocks the line
 
 N > 1 (torchrun): independent gradient directions shard one per rank, no data-path collective
 (weak scaling); torch.distributed is used for the barrier and the max-over-ranks only.
@@ -149,6 +152,33 @@ def loop_roofline(nnz, n, iters, nsteps, loop_ms, peak_gbs):
                     "never reaches HBM"}
 
 
+def hardi_sweep(local_rank, rank, world, batch=16, h=0.7, ndir=64):
+    """BASELINE.json's third figure: dMRI signals/s of the HARDI sweep (configs[4]: 64 directions x 4 b-values on a
+    46 k-vertex neuron-like mesh, PGSE 10600/43100, dt 200), sharded over the ranks with no collective in the loop
+    (sweep.shard_balanced) and `batch` members per kernel launch.  Returns this rank's wall time for its share (the
+    caller takes the max over ranks) and the number of signals of the whole job."""
+    entry.load_package()
+    from dmri_fem_cloud_b200 import btfem, dmrifemlib as dl, meshes, sweep
+    xyz, tets = meshes.neuron_like(h=h)
+    xyz, tets = meshes.rcm_order(*meshes.shuffle_vertices(xyz, tets, 0))
+    mp, _, _, _ = sequence(k=200.0)
+    sim = dl.MRI_simulation()
+    sim.k = 200.0
+    dirs = meshes.fibonacci_hemisphere(ndir)
+    bvals = [1000.0, 2000.0, 3000.0, 4000.0]
+    par = dict(rtol=1e-9, atol=1e-10, maxit=100000)
+    with btfem.BTFem(local_rank) as fem:
+        fem.set_mesh(xyz, tets)
+        fem.set_diffusion(3e-3)
+        fem.set_relaxation(1e-16)
+        fem.assemble()
+        sweep.run_sweep(fem, mp, sim, dirs[:2], bvals[:2], par, batch=4)          # warm-up
+        t0 = time.perf_counter()
+        mine, sig = sweep.run_sweep(fem, mp, sim, dirs, bvals, par, rank=rank, world=world, batch=batch)
+        dt = time.perf_counter() - t0                                           # solve_batch returns after a stream sync
+    return dt, len(dirs) * len(bvals), int(len(xyz)), float(np.sum(sig))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -159,6 +189,7 @@ def main():
     ap.add_argument("--cpu-sample-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--no-hardi", action="store_true", help="skip the HARDI signals/s figure")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -295,12 +326,24 @@ def main():
         for fobj in keep:
             fobj.close()
 
-    tmax, e2e_max = elapsed, e2e_elapsed
+    # ---- HARDI sweep (signals/s).  No collective inside: a rank that fails reports an infinite time, so the
+    # max over ranks below cannot hang on it.
+    hardi_dt, hardi_info = float("inf"), None
+    if not args.no_hardi:
+        try:
+            barrier()
+            with contextlib.redirect_stdout(io.StringIO()):
+                hardi_dt, n_sig, n_vert, checksum = hardi_sweep(local_rank, rank, world)
+            hardi_info = {"n_signals": n_sig, "n_vertices": n_vert, "batch": 16, "local_checksum": checksum}
+        except Exception as exc:      # the headline line must still be printed
+            hardi_dt, hardi_info = float("inf"), {"error": "%s: %s" % (type(exc).__name__, exc)}
+
+    tmax, e2e_max, hardi_max = elapsed, e2e_elapsed, hardi_dt
     if dist is not None:
         import torch
-        tt = torch.tensor([elapsed, e2e_elapsed], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([elapsed, e2e_elapsed, hardi_dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        tmax, e2e_max = float(tt[0]), float(tt[1])
+        tmax, e2e_max, hardi_max = float(tt[0]), float(tt[1]), float(tt[2])
 
     if rank == 0:
         value = world * ndof_real * nsteps * args.steps / tmax
@@ -348,6 +391,15 @@ def main():
                              "share_of_loop": spmv_share}}
         # the whole time loop against the same roofline: SURVEY 8(d) algorithmic bytes of a Jacobi-BiCGStab iteration
         # (2 SpMVs + 224 n of vector passes) and of the per-step right-hand side (1 SpMV), over the device loop time
+        if hardi_info is not None:
+            if np.isfinite(hardi_max) and "error" not in hardi_info:
+                hardi_info.update({"value": hardi_info["n_signals"] / hardi_max, "unit": "signals/s",
+                                   "seconds": hardi_max,
+                                   "workload": "configs[4] HARDI 64 directions x 4 b-values, neuron-like mesh, sharded over "
+                                               "%d GPU(s), no collective in the loop" % world})
+            elif "error" not in hardi_info:
+                hardi_info["error"] = "a rank failed"
+            line["hardi"] = hardi_info
         line["loop_roofline"] = loop_roofline(fem.nnz, fem.ndof, res["total_iters"], nsteps, res["loop_ms"], peak)
         if not args.no_cpu and world == 1:
             entry.build_oracle()

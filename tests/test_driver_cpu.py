@@ -177,3 +177,21 @@ def test_driver_strong_periodic_flow(tmp_path, monkeypatch, fake):
     ref = orc.theta_solve_strong(ops, seq, mp.qvalue, [1, 0.5, 0], 100.0)
     assert abs(sim.stats["signal"] - ref["signal"]) <= 1e-10 * abs(ref["signal"])
     assert sim.fem.periodic is None and sim.fem.vmaster is not None      # no weak marker in this mode
+
+
+def test_bench_hardi_sweep_helper(fake):
+    """bench.py's HARDI figure: the helper shards 4 directions x 4 b-values over two ranks and every unit is solved
+    once (tiny mesh, test double)."""
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    tot = 0.0
+    for rank in range(2):
+        dt, n_sig, n_vert, checksum = b.hardi_sweep(0, rank, 2, batch=3, h=4.0, ndir=4)
+        assert dt > 0 and n_sig == 16 and n_vert > 50 and 0 < checksum < 8
+        tot += checksum
+    one = b.hardi_sweep(0, 0, 1, batch=16, h=4.0, ndir=4)
+    assert abs(one[3] - tot) <= 1e-9 * tot
