@@ -104,18 +104,19 @@ def vertex_map(xyz, pdir, lo, hi, tol):
             on = np.abs(xyz[:, d] - hi[d]) < tol
             wrapped[on, d] = lo[d]
             slave |= on
-    cell = np.floor(wrapped / tol + 0.5).astype(np.int64)        # grid of spacing tol: coincident points share a cell
-    _, inv = np.unique(cell, axis=0, return_inverse=True)
-    inv = inv.ravel()
+    # every wrapped position must coincide (within tol) with a vertex that is on no max face: nearest-neighbour search
+    from scipy.spatial import cKDTree
+    vm = np.arange(nv, dtype=np.int64)
     masters = np.nonzero(~slave)[0]
-    owner = -np.ones(inv.max() + 1, dtype=np.int64)
-    if len(np.unique(inv[masters])) != len(masters):
-        raise RuntimeError("periodic map: distinct vertices coincide within tol")
-    owner[inv[masters]] = masters
-    vm = owner[inv]
-    if (vm < 0).any():
-        raise RuntimeError("the mesh is not periodic: %d vertices on a max face have no partner on the min face"
-                           % int((vm < 0).sum()))
+    sl = np.nonzero(slave)[0]
+    if len(sl):
+        if len(masters) == 0:
+            raise RuntimeError("periodic map: every vertex lies on a max face")
+        dist, idx = cKDTree(xyz[masters]).query(wrapped[sl], k=1)
+        if (dist >= tol).any():
+            raise RuntimeError("the mesh is not periodic: %d vertices on a max face have no partner on the min face"
+                               % int((dist >= tol).sum()))
+        vm[sl] = masters[idx]
     return vm.astype(np.int32)
 
 
