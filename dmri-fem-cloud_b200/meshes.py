@@ -207,6 +207,61 @@ def layered_cylinder(radii=(5.0, 7.5, 10.0), height=5.0, nr_per_layer=(6, 3, 3),
     return xyz, tets, marker
 
 
+def icosphere(level=2):
+    """Unit-sphere triangulation by `level` midpoint subdivisions of the icosahedron (20 * 4^level triangles)."""
+    t = (1.0 + np.sqrt(5.0)) / 2.0
+    v = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+                  [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], dtype=float)
+    v /= np.linalg.norm(v, axis=1)[:, None]
+    f = np.array([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2],
+                  [10, 7, 6], [7, 1, 8], [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5], [2, 4, 11],
+                  [6, 2, 10], [8, 6, 7], [9, 8, 1]])
+    verts = [tuple(p) for p in v]
+    for _ in range(level):
+        cache, nf = {}, []
+
+        def mid(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in cache:
+                m = np.asarray(verts[a]) + np.asarray(verts[b])
+                verts.append(tuple(m / np.linalg.norm(m)))
+                cache[key] = len(verts) - 1
+            return cache[key]
+
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [[a, ab, ca], [b, bc, ab], [c, ca, bc], [ab, bc, ca]]
+        f = np.array(nf)
+    return np.array(verts), f
+
+
+def layered_sphere(radii=(5.0, 7.5, 10.0), nr_per_layer=(4, 2, 2), level=2):
+    """Concentric-layer ball with conforming interfaces (the multilayered sphere of T2_Relaxation.ipynb /
+    MultilayeredStructures.ipynb cell 12): shells of an icosphere at increasing radii, the prisms between two
+    shells split into 3 tets by the smallest-index rule (like extrude_triangulation), the innermost shell coned to
+    the centre.  marker = layer index (phase = marker % 2)."""
+    sv, sf = icosphere(level)
+    rs, lay = [], []
+    r_prev = 0.0
+    for li, (R, n) in enumerate(zip(radii, nr_per_layer)):
+        for m in range(1, n + 1):
+            rs.append(r_prev + (R - r_prev) * m / n)
+            lay.append(li)
+        r_prev = R
+    ns = len(sv)
+    xyz = np.concatenate([np.zeros((1, 3))] + [r * sv for r in rs], axis=0)
+    shell = lambda m, idx: 1 + m * ns + idx
+    tets = [np.column_stack([np.zeros(len(sf), dtype=np.int64), shell(0, sf[:, 0]), shell(0, sf[:, 1]), shell(0, sf[:, 2])])]
+    marker = [np.full(len(sf), lay[0])]
+    tri = np.sort(sf, axis=1)
+    for m in range(1, len(rs)):
+        a, b, c = (shell(m - 1, tri[:, q]) for q in range(3))
+        A, B, C = (shell(m, tri[:, q]) for q in range(3))
+        tets += [np.stack([a, b, c, C], axis=1), np.stack([a, b, C, B], axis=1), np.stack([a, B, C, A], axis=1)]
+        marker += [np.full(len(sf), lay[m])] * 3
+    return xyz, np.concatenate(tets, axis=0).astype(np.int32), np.concatenate(marker).astype(np.int32)
+
+
 def cylinder(radius=3.0, length=25.0, nr=4, nsec=16, nz=20):
     """Single-compartment cylinder of the `cyl*_r_3E_6` shape (axis z)."""
     xyz, tets, _ = layered_cylinder((radius,), length, (nr,), nsec, nz)

@@ -113,3 +113,34 @@ def test_fixture_golden_is_current():
     ops = orc.assemble(xyz, tets, D=3e-3, invT2=1e-16)
     r = orc.theta_solve(ops, seq, seq.q_from_b(1000.0), [1, 0, 0], 200.0, solver="lu")
     assert abs(r["signal"] - float(fix["cyl6_r_3E_6_vol_signal"])) <= 1e-13 * abs(r["signal"])
+
+
+def _sphere_signals(level, nr):
+    xyz, tets, marker = meshes.layered_sphere((5.0, 7.5, 10.0), nr, level)
+    ops = orc.assemble(xyz, tets, (marker % 2).astype(np.int32), D=3e-3, kappa=5e-5)
+    seq = orc.pgse(40000.0, 40000.0)
+    out = []
+    for b in (1000.0, 3000.0):
+        r = orc.theta_solve(ops, seq, seq.q_from_b(b), [0, 0, 1], 400.0, solver="lu")
+        out.append(r["signal"] / r["voi"])
+    return out
+
+
+def test_three_layer_sphere_vs_matrix_formalism():
+    """T2_Relaxation.ipynb / MultilayeredStructures.ipynb cell 12, matrix formalism for the three-layer SPHERE
+    R=[5,7.5,10], D=3e-3, kappa=5e-5, delta=Delta=40000: b=1000 -> .7886, 3000 -> .4932.  A whole-path 3-D
+    two-compartment pin on curved, conforming interfaces (meshes.layered_sphere); coarse mesh here (0.9 % / 2.5 %),
+    the --runslow variant shows the convergence (0.2 % / 0.5 %)."""
+    s1, s3 = _sphere_signals(2, (4, 2, 2))
+    assert abs(s1 - .7886) <= 0.012 * .7886 and abs(s3 - .4932) <= 0.03 * .4932
+    xyz, tets, marker = meshes.layered_sphere((5.0, 7.5, 10.0), (2, 1, 1), 1)
+    f, _, _ = orc.facets(tets)
+    shared = np.all(f[1:] == f[:-1], axis=1).sum()
+    assert len(f) - 2 * shared == 20 * 4                               # conforming: only the outer sphere is boundary
+    assert orc.tet_geometry(xyz, tets)[1].min() > 0
+
+
+@pytest.mark.slow
+def test_three_layer_sphere_vs_matrix_formalism_fine():
+    s1, s3 = _sphere_signals(3, (6, 3, 3))
+    assert abs(s1 - .7886) <= 0.003 * .7886 and abs(s3 - .4932) <= 0.006 * .4932
