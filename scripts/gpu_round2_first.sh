@@ -8,6 +8,7 @@ mkdir -p gpurun_out
 BTFEM_TEST_STRONG=1 BTFEM_STRONG=1 timeout 300 python -m pytest tests/test_gpu_strong.py -m gpu -q 2>&1 | tail -40 | tee gpurun_out/r2_first_strong.txt
 BTFEM_TEST_STRONG=1 BTFEM_STRONG=1 timeout 300 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_strong.py -m gpu -q -k box_1c > gpurun_out/r2_first_strong_memcheck.txt 2>&1
 grep -h "=========" gpurun_out/r2_first_strong_memcheck.txt | grep -v "Host Frame\|^========= *$" | sort | uniq -c | sort -rn | head
+BTFEM_TEST_PENDING=1 timeout 300 python -m pytest tests/test_gpu_pending.py -m gpu -q 2>&1 | tail -20 | tee gpurun_out/r2_first_pending.txt
 timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -6 | tee gpurun_out/r2_first_pytest.txt
 timeout 600 python bench.py --cpu-sample-steps 8 > gpurun_out/r2_first_bench.json 2> gpurun_out/r2_first_bench.err
 tail -c 1200 gpurun_out/r2_first_bench.json; tail -3 gpurun_out/r2_first_bench.err
