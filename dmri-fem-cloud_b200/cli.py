@@ -6,12 +6,17 @@ Same flags, defaults and quirks as /root/reference/GCloudDmriSolver.py:52-133:
   -k dt  -T2 T2  -gdir gx gy gz  -pdir px py pz
 A parse error prints 'Something goes wrong with the inputs!' and continues with what was parsed.
 
-Input file: the reference reads a DOLFIN HDF5 container written by the pre-processing scripts
-(datasets mesh, T2, ic, phase, d00..d22; PreprocessingMultiCompt.py:148-152).  There is no HDF5
-library in this image, so the same datasets are taken from a NumPy `.npz` with keys
+T2 quirk, kept: the reference parses `-T2` and reads the `T2` dataset (GCloudDmriSolver.py:115-119, 167-171) but
+never assigns either to `mri_para.T2`, so its forms always run with T2 = 1e16 (DmriFemLib.py:807).  Identical
+flags give identical signals here: T2 is parsed, read and -- by default -- not applied.  `-applyT2 1` (an
+extension, not a reference flag) applies it: the per-cell `T2` dataset, or the `-T2` scalar.
+
+Input file: the DOLFIN HDF5 container the pre-processing scripts write (datasets mesh, T2, ic, phase, d00..d22;
+PreprocessingMultiCompt.py:148-152), read by hdf5io.py (pure Python: no libhdf5 in this image); the same datasets
+from a NumPy `.npz` with keys
   xyz (nv,3), tets (nc,4) [, phase (nc,), T2 (nc,), ic (nc,), d00 .. d22 (nc,)]
-or, mesh only, from gmsh v2 `.msh[.zip]` / DOLFIN `.xml[.zip]` (then -K and -T2 apply, like the
-reference's is_kcoeff_from_file = 0 path).
+or, mesh only, gmsh v2 `.msh[.zip]` / DOLFIN `.xml[.zip]` (then -K applies, like the reference's
+is_kcoeff_from_file = 0 path).
 """
 import sys
 
@@ -19,6 +24,7 @@ import numpy as np
 import sympy as sp
 
 from . import dmrifemlib as dl
+from . import hdf5io
 from . import meshes
 
 
@@ -27,6 +33,8 @@ def load_input(path):
     if path.endswith(".npz"):
         z = np.load(path)
         data = {k: z[k] for k in z.files}
+    elif path.endswith(".h5") or path.endswith(".hdf5"):
+        data = hdf5io.read_dolfin_h5(path)
     elif ".msh" in path:
         xyz, tets, marker = meshes.read_gmsh2(path)
         data = {"xyz": xyz, "tets": tets, "marker": marker}
@@ -55,6 +63,7 @@ def main(argv=None):
     IsDomainMultiple = False
     PeriodicDir = [0, 0, 0]
     ffile = None
+    apply_T2 = 0
     try:
         for i in range(0, len(argv)):
             arg = argv[i]
@@ -97,6 +106,9 @@ def main(argv=None):
                 is_T2_from_file = 0
                 T2 = float(argv[i + 1])
                 print('T2: ', T2)
+            if arg == '-applyT2':
+                apply_T2 = int(argv[i + 1])
+                print('apply T2 (extension; the reference never does):', apply_T2)
             if arg == '-gdir':
                 g0 = float(argv[i + 1])
                 g1 = float(argv[i + 2])
@@ -126,7 +138,9 @@ def main(argv=None):
     mri_para.T = mri_para.Delta + mri_para.delta
     mri_para.fs_sym = sp.Piecewise((1., mri_para.s < mri_para.delta), (0., mri_para.s < mri_para.Delta),
                                    (-1., mri_para.s < mri_para.T), (0., True))
-    if is_T2_from_file == 0:
+    if is_T2_from_file == 1:
+        print("Reading T2 from file: ", ffile)
+    if apply_T2 and is_T2_from_file == 0:
         mri_para.T2 = T2
     mri_para.Apply()
     mri_simu.k = k
@@ -143,7 +157,7 @@ def main(argv=None):
     mydomain.IsDomainPeriodic = IsDomainPeriodic
     mydomain.IsDomainMultiple = IsDomainMultiple
     mydomain.kappa = kappa
-    if is_T2_from_file == 1:
+    if apply_T2 and is_T2_from_file == 1:
         mydomain.T2_cell = np.asarray(data["T2"], dtype=float)
     mydomain.Apply()
     if is_kcoeff_from_file == 1:

@@ -279,10 +279,6 @@ class MyDomain():
     def Apply(self):
         if self.is_strongly_periodic() and self.tdim < self.gdim:
             raise NotImplementedError("strong pseudo-periodic BC on a manifold mesh")
-        if self.is_strongly_periodic() and os.environ.get("BTFEM_STRONG") != "1":
-            raise NotImplementedError("strongly imposed pseudo-periodic BC (FuncF_sBC, DmriFemLib.py:148-238): the GPU path "
-                                      "(csrc/strong.cu) is written and CPU-verified but has not been validated on hardware "
-                                      "yet; set BTFEM_STRONG=1 to use it, or impose the BC weakly (IsDomainPeriodic=False)")
         if self.IsDomainMultiple:
             print("Function Space for Two-compartment Domains has 4 components")
             print("(ur0, ui0, ur1, ur1): r-real, i-imaginary")

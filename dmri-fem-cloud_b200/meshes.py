@@ -69,6 +69,26 @@ def read_gmsh2(path):
     return xyz, new_id[tets].astype(np.int32), np.array(marks, dtype=np.int32)
 
 
+def write_gmsh2(path, xyz, cells, tags=None):
+    """Write a gmsh v2 ASCII mesh (`$MeshFormat 2.2 0 8`): tetrahedra (element type 4) or triangles (type 2), one
+    physical/elementary tag pair per element -- the format the reference's `.msh` fixtures come in
+    (comri/meshes/*.msh.zip) and read_gmsh2 / GetPartitionMarkers (DmriFemLib.py:703-742) parse."""
+    xyz = np.asarray(xyz, dtype=float)
+    cells = np.asarray(cells)
+    x3 = np.zeros((len(xyz), 3))
+    x3[:, :xyz.shape[1]] = xyz
+    et = {4: 4, 3: 2}[cells.shape[1]]
+    tags = np.zeros(len(cells), dtype=np.int64) if tags is None else np.asarray(tags)
+    with open(path, "w") as f:
+        f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % len(x3))
+        for i, p in enumerate(x3):
+            f.write("%d %.17g %.17g %.17g\n" % (i + 1, p[0], p[1], p[2]))
+        f.write("$EndNodes\n$Elements\n%d\n" % len(cells))
+        for i, c in enumerate(cells):
+            f.write("%d %d 2 %d %d %s\n" % (i + 1, et, tags[i], tags[i], " ".join(str(int(v) + 1) for v in c)))
+        f.write("$EndElements\n")
+
+
 def read_dolfin_xml(path):
     """Read a DOLFIN XML mesh (optionally zipped): celltype tetrahedron, triangle (dim 2 or 3) or interval."""
     with _open_text(path) as f:

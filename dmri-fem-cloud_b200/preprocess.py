@@ -1,16 +1,18 @@
 """Pre-processing of the solver input, the part of PreprocessingOneCompt.py / PreprocessingMultiCompt.py that is
 not mesh generation: phase function and partition markers from compartment sub-meshes or from a marker file
 (CreatePhaseFunc, DmriFemLib.py:748-799), per-compartment T2 / IC / diffusion tensor as cell (DG0) arrays
-(PreprocessingMultiCompt.py:118-146), written to the `.npz` side format of cli.py -- the datasets the reference
-writes to DOLFIN HDF5 (mesh, T2, ic, phase, d00..d22, PreprocessingMultiCompt.py:148-152).
+(PreprocessingMultiCompt.py:118-146), written -- like the reference -- to a DOLFIN HDF5 container `<name>.h5`
+(mesh, T2, ic, phase, d00..d22, PreprocessingMultiCompt.py:148-152; hdf5io.write_dolfin_h5), or to the `.npz` side
+format of cli.py when `-o` names a `.npz`.
 
   python -m ... preprocess  -m mesh.xml [-odd cmpt1.xml ...] [-even cmptA.xml ...] [-pmk pmk_mesh.xml]
-                            [-D0 3e-3 3e-3] [-T2 1e6 1e6] [-IC 1 1] -o files.npz
+                            [-D0 3e-3 3e-3] [-T2 1e6 1e6] [-IC 1 1] -o files.h5
 """
 import sys
 
 import numpy as np
 
+from . import hdf5io
 from . import meshes
 
 
@@ -73,7 +75,7 @@ def _load(path):
 
 def main(argv=None):
     argv = list(sys.argv if argv is None else argv)
-    mesh, odd, even, pmk, ofile = None, [], [], None, "files.npz"
+    mesh, odd, even, pmk, ofile = None, [], [], None, "files.h5"
     D0, T2, IC = None, None, None
 
     def floats(i):
@@ -112,9 +114,11 @@ def main(argv=None):
     print("Partition markers:", plist)
     n = int(np.max(marker)) + 1
     fields = cell_fields(marker, D0 or [3e-3] * n, T2 or [1e6] * n, IC or [1.0] * n)     # PreprocessingMultiCompt.py:122-125
-    if not ofile.endswith(".npz"):
-        ofile = ofile.rsplit(".", 1)[0] + ".npz"
-    np.savez(ofile, xyz=xyz, tets=cells, phase=phase, marker=marker, **fields)
+    if ofile.endswith(".npz"):
+        np.savez(ofile, xyz=xyz, tets=cells, phase=phase, marker=marker, **fields)
+    else:                                          # filename + '.h5' whatever the extension (PreprocessingMultiCompt.py:144-146)
+        ofile = (ofile.rsplit(".", 1)[0] if "." in ofile.rsplit("/", 1)[-1] else ofile) + ".h5"
+        hdf5io.write_dolfin_h5(ofile, xyz, cells, dict(phase=phase, **fields))
     print("Write to ", ofile)
     return 0
 

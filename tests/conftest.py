@@ -38,10 +38,25 @@ def pytest_addoption(parser):
     parser.addoption("--runslow", action="store_true", default=False)
 
 
+def _gpu_usable():
+    """A CUDA device the library can open?  (btfem_create(0) fails without one: the product has no CPU fallback.)"""
+    try:
+        entry.build_library()
+        from dmri_fem_cloud_b200 import btfem
+        btfem.BTFem(0).close()
+        return True
+    except Exception:
+        return False
+
+
 def pytest_collection_modifyitems(config, items):
-    if config.getoption("--runslow"):
-        return
-    skip = pytest.mark.skip(reason="slow: pass --runslow")
-    for item in items:
-        if "slow" in item.keywords:
-            item.add_marker(skip)
+    if not config.getoption("--runslow"):
+        skip = pytest.mark.skip(reason="slow: pass --runslow")
+        for item in items:
+            if "slow" in item.keywords:
+                item.add_marker(skip)
+    gpu_items = [item for item in items if "gpu" in item.keywords]
+    if gpu_items and not _gpu_usable():
+        skip_gpu = pytest.mark.skip(reason="no usable CUDA device / libbtfem.so on this box")
+        for item in gpu_items:
+            item.add_marker(skip_gpu)

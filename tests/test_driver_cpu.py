@@ -43,14 +43,21 @@ def test_cli_two_compartments_from_marker_and_tensor_file(tmp_path, monkeypatch,
     T2 = np.array([1e6, 4e4, 1e6])[marker]
     np.savez("in.npz", xyz=xyz, tets=tets, phase=(marker % 2), T2=T2, d00=Dl, d01=z, d02=z, d10=z, d11=Dl, d12=z,
              d20=z, d21=z, d22=Dl)
-    text = cli.main(["prog", "-f", "in.npz", "-M", "1", "-b", "2000", "-p", "5e-5", "-d", "2000", "-D", "6000", "-k", "200",
-                     "-gdir", "0", "1", "0"])
-    ops = orc.assemble(xyz, tets, (marker % 2).astype(np.int32), D=Dl, invT2=1.0 / T2, kappa=5e-5)
+    flags = ["prog", "-M", "1", "-b", "2000", "-p", "5e-5", "-d", "2000", "-D", "6000", "-k", "200", "-gdir", "0", "1", "0"]
     seq = orc.pgse(2000.0, 6000.0)
-    ref = orc.theta_solve(ops, seq, seq.q_from_b(2000.0), [0, 1, 0], 200.0, solver="lu")
-    got = float(text.split("Normalized signal: ")[1].split(",")[0])
-    assert abs(got - ref["signal"] / ref["voi"]) <= 1e-6 * got
-    assert "kappa: 5.000e-05" in text or "kappa:" in text
+    # the reference reads the T2 dataset but never applies it (GCloudDmriSolver.py:167-171 vs DmriFemLib.py:807):
+    # identical flags -> T2 = 1e16; `-applyT2 1` (extension) applies the per-cell values.  Same from `.npz` and `.h5`.
+    from dmri_fem_cloud_b200 import hdf5io
+    fields = dict(phase=(marker % 2), T2=T2, ic=np.ones(nc), d00=Dl, d01=z, d02=z, d10=z, d11=Dl, d12=z, d20=z, d21=z, d22=Dl)
+    hdf5io.write_dolfin_h5("in.h5", xyz, tets, fields)
+    for extra, invT2 in (([], 1e-16), (["-applyT2", "1"], 1.0 / T2)):
+        ops = orc.assemble(xyz, tets, (marker % 2).astype(np.int32), D=Dl, invT2=invT2, kappa=5e-5)
+        ref = orc.theta_solve(ops, seq, seq.q_from_b(2000.0), [0, 1, 0], 200.0, solver="lu")
+        for infile in ("in.npz", "in.h5"):
+            text = cli.main(flags + ["-f", infile] + extra)
+            got = float(text.split("Normalized signal: ")[1].split(",")[0])
+            assert abs(got - ref["signal"] / ref["voi"]) <= 1e-6 * got, (infile, extra)
+            assert "kappa: 5.000e-05" in text or "kappa:" in text
 
 
 def test_driver_weak_periodic_and_ogse(tmp_path, monkeypatch, fake):
@@ -139,7 +146,6 @@ def test_driver_strong_periodic_flow(tmp_path, monkeypatch, fake):
     oracle's transformed-equation stepping."""
     from dmri_fem_cloud_b200 import periodic
     monkeypatch.chdir(tmp_path)
-    monkeypatch.setenv("BTFEM_STRONG", "1")              # the mode is opt-in until it has run on hardware
     xyz, tets, ph = meshes.box_with_sphere(4.0, 5, 2.5)
     lo, hi, hmin, _ = orc.domain_sizes(xyz, tets)
     vm = periodic.vertex_map(xyz, [1, 1, 0], lo, hi, 1e-2 * hmin)
@@ -164,10 +170,6 @@ def test_driver_strong_periodic_flow(tmp_path, monkeypatch, fake):
     md = dl.MyDomain(mesh, mp)
     md.phase, md.IsDomainMultiple, md.kappa = ph, True, 5e-5
     md.PeriodicDir, md.IsDomainPeriodic = [1, 1, 0], True
-    monkeypatch.delenv("BTFEM_STRONG")
-    with pytest.raises(NotImplementedError):
-        md.Apply()
-    monkeypatch.setenv("BTFEM_STRONG", "1")
     md.Apply()
     md.D0 = 2e-3
     md.D = md.D0

@@ -1,20 +1,15 @@
 """GPU parity of the STRONGLY imposed pseudo-periodic BC (csrc/strong.cu, btfem_set_periodic_map) against the oracle's
 restatement (pinned on the CPU by tests/test_oracle_strong.py).
 
-OPT-IN: these tests have not run on hardware yet (the kernels were written after the round's GPU budget was
-spent); they run with BTFEM_TEST_STRONG=1 and are skipped otherwise, so that an unvalidated path cannot turn the
-suite red.  Bars as everywhere: merged pattern bit-exact, operator values 1e-12, signals 1e-8."""
-import os
-
+First run on hardware: round 2 (profiles/r2a_strong.txt, 3 passed).  Bars as everywhere: merged pattern bit-exact,
+operator values 1e-12, signals 1e-8; plus the limit the notebooks quote for this mode, exp(-b D0), through the driver."""
 import numpy as np
 import pytest
 
 import bt_oracle as orc
 from dmri_fem_cloud_b200 import btfem, meshes, periodic
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("BTFEM_TEST_STRONG") != "1",
-                                 reason="strong periodic BC: GPU validation pending (set BTFEM_TEST_STRONG=1)")]
+pytestmark = pytest.mark.gpu
 
 
 def _relmax(a, b):
@@ -97,3 +92,44 @@ def test_strong_periodic_operators_and_signal(case):
     assert again["signal"] == res["signal"]                                                  # reproducible
     neu = orc.theta_solve(orc.assemble(xyz, cells, ph, D=D, kappa=kappa), seq, q, g, k, solver="lu")
     assert abs(plain["signal"] - neu["signal"]) <= 1e-8 * abs(neu["signal"])
+
+
+def test_driver_periodic_along_the_axis_gives_free_diffusion():
+    """`mydomain.PeriodicDir = [1, 0, 0]: s=exp(-bvalue*D0)` (T2_Relaxation.ipynb / MultilayeredStructures.ipynb /
+    DiscontinuousInitialCondition.ipynb cell 12) through MyDomain / MRI_simulation.solve with IsDomainPeriodic = True:
+    layered cylinder, gradient and periodicity along its axis, membranes parallel to the gradient.  Same meshes and
+    tolerances as the oracle's pin (tests/test_oracle_strong.py); Neumann ends give the restricted value instead."""
+    import sympy as sp
+    from dmri_fem_cloud_b200 import dmrifemlib as dl
+    xyz, tets, marker = meshes.layered_cylinder((5.0, 7.5, 10.0), 5.0, (2, 1, 1), 12, 4)      # axis z
+    ph = (marker % 2).astype(np.int32)
+    mesh = dl.Mesh(xyz, tets)
+
+    def run(b, k, strong):
+        mp = dl.MRI_parameters()
+        mp.bvalue = b
+        mp.delta, mp.Delta = 10000.0, 10000.0
+        mp.T = mp.delta + mp.Delta
+        mp.fs_sym = sp.Piecewise((1., mp.s < mp.delta), (0., mp.s < mp.Delta), (-1., mp.s < mp.T), (0., True))
+        mp.set_gradient_dir(mesh, 0, 0, 1)
+        mp.Apply()
+        sim = dl.MRI_simulation()
+        sim.k = k
+        sim.verbose = False
+        md = dl.MyDomain(mesh, mp)
+        md.phase, md.IsDomainMultiple, md.kappa = ph, True, 1e-5
+        md.PeriodicDir, md.IsDomainPeriodic = ([0, 0, 1], True) if strong else ([0, 0, 0], False)
+        md.Apply()
+        md.D0 = 3e-3
+        md.D = md.D0
+        ls = dl.KrylovSolver("bicgstab", "jacobi")
+        ls.parameters["relative_tolerance"] = 1e-10
+        ls.parameters["absolute_tolerance"] = 1e-12
+        sim.solve(md, mp, ls)
+        s = sim.stats["signal"] / sim.stats["voi"]
+        sim.fem.close()
+        return s
+
+    for b, k, tol in ((1000.0, 200.0, 3e-3), (1000.0, 50.0, 3e-4), (3000.0, 50.0, 2e-3)):
+        assert abs(run(b, k, True) - np.exp(-b * 3e-3)) <= tol * np.exp(-b * 3e-3)
+    assert run(1000.0, 200.0, False) > 0.9
