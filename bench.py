@@ -20,6 +20,12 @@ complex unknowns (the reference would count W.dim() = 4 x N_vert = 2x more for t
   loop_roofline the whole Krylov loop (algorithmic bytes of all iterations over the device loop time)
   hardi    BASELINE.json's third figure, dMRI signals/s: the 64 x 4 HARDI sweep of configs[4] sharded over the
            N ranks (skip with --no-hardi); a failure there is reported in the key and never blocks the line
+  partitioned  N > 1 only: ONE mesh row-partitioned over the N GPUs (configs[3]: ECS of 226 cylinders, weak
+           pseudo-periodic BC, ~1 M and ~4 M DOFs; the reference's `mpirun -n N` mode, README.md:86-94) -- DOF-steps/s,
+           us per BiCGStab iteration, speed-up and relative signal difference against the same solve on one GPU
+  signal_check  N = 1 only: the oracle's C/OpenMP restatement runs ALL theta steps of the same problem at the same
+           Krylov tolerances on the host cores; the relative difference of the two final signals is printed
+           (north star: <= 1e-8) and the same run is the `cpu_baseline`
 
 N > 1 (torchrun): independent gradient directions shard one per rank, no data-path collective
 (weak scaling); torch.distributed is used for the barrier and the max-over-ranks only.
@@ -44,7 +50,8 @@ METRIC = "Bloch-Torrey DOF-steps/s"
 UNIT = "DOF-steps/s"
 # DRAM bytes of one k_spmv_sell<MODE_V> launch on the default workload, from the committed
 # `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_spmv_sell_full.txt)
-NCU_TRAFFIC = {"n_box": 78, "bytes": 167.227136e6 + 3.839232e6}
+NCU_TRAFFIC = {"n_box": 78,
+               "sell": {"bytes": 167.227136e6 + 3.839232e6, "file": "profiles/r1_ncu_spmv_sell_full.txt (ncu, round 1)"}}
 
 
 def workload(n_box):
@@ -121,13 +128,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_restatement(xyz, tets, phase, mp, f, fp, k, sample_steps, mode=0):
+def cpu_operators(xyz, tets, phase):
+    """The oracle's assembled operators of the bench workload (numpy; built once per process)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import bt_oracle as orc
+    return orc.assemble(xyz, tets, phase, D=3e-3, invT2=1e-16, kappa=1e-5)
+
+
+def cpu_restatement(xyz, tets, phase, mp, f, fp, k, sample_steps, mode=0, ops=None):
     """Time the oracle's C/OpenMP time loop on the first `sample_steps` theta steps."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import bt_cpu
-    import bt_oracle as orc
     bt_cpu.set_threads(len(os.sched_getaffinity(0)))      # all host cores, whatever OMP_NUM_THREADS says
-    ops = orc.assemble(xyz, tets, phase, D=3e-3, invT2=1e-16, kappa=1e-5)
+    if ops is None:
+        ops = cpu_operators(xyz, tets, phase)
     q = mp.qvalue
     t0 = time.perf_counter()
     if mode == 2:      # DmriFemLib.solve work pattern: A and b re-assembled from the elements every step
@@ -137,7 +151,20 @@ def cpu_restatement(xyz, tets, phase, mp, f, fp, k, sample_steps, mode=0):
         u, iters = bt_cpu.theta_loop(ops, [0, 1, 0], k, 0.5, q * f[:sample_steps], q * fp[:sample_steps], mode=mode)
     dt = time.perf_counter() - t0
     return {"seconds": dt, "ndof_real": 2 * ops.ndof, "steps": sample_steps, "iters": int(iters.sum()),
-            "cores": bt_cpu.num_threads(), "signal": float(ops.lumped @ u.real)}
+            "cores": bt_cpu.num_threads(), "signal": float(ops.lumped @ u.real), "voi": float(ops.lumped.sum()),
+            "nnz": int(ops.nnz)}
+
+
+def make_config(n_box, world, ndof_real, n_vertices, n_tets, nnz, nsteps):
+    """The workload description BOTH arms print (the driver compares the two dicts)."""
+    return {"workload": "configs[1] two-compartment permeable PGSE (-M 1 -b 1000 -p 1e-5 -k 200 -gdir 0 1 0), "
+                        "cell-in-box n_box=%d" % n_box,
+            "ndof_real": int(ndof_real), "n_vertices": int(n_vertices), "n_tets": int(n_tets), "nnz": int(nnz),
+            "theta_steps_per_solve": int(nsteps), "krylov": "bicgstab+jacobi rtol 1e-9 atol 1e-10",
+            "l2_policy": "working set (operator %.0f MB + 8 vectors %.0f MB) larger than L2; the roofline launch is "
+                         "timed after reading a 512 MiB scratch buffer (L2 flush)" % (20.0 * nnz / 1e6,
+                                                                                    8 * 8.0 * ndof_real / 1e6),
+            "parallelism": "sweep-sharded x%d (one gradient direction per GPU)" % world}
 
 
 def loop_roofline(nnz, n, iters, nsteps, loop_ms, peak_gbs):
@@ -179,6 +206,68 @@ def hardi_sweep(local_rank, rank, world, batch=16, h=0.7, ndir=64):
     return dt, len(dirs) * len(bvals), int(len(xyz)), float(np.sum(sig))
 
 
+def partitioned_solve(dist, local_rank, rank, world, ecs):
+    """BASELINE.json configs[3]: the extracellular space of 226 cylinders (two compartments, D = 2e-3, kappa = 1e-5,
+    delta/Delta = 10000/13000, dt 200, g = (1,1,0)/sqrt 2, b = 1000, weak pseudo-periodic BC in x and y) as ONE mesh
+    row-partitioned over the `world` GPUs (partition.DistBTFem: halo entries and dot products travel through peer
+    memory inside libbtfem's kernels), against the same solve on one GPU (rank 0).  All ranks call this; rank 0 gets
+    the figures.  Loop time is device time (CUDA events inside libbtfem), max over ranks."""
+    import datetime
+    entry.load_package()
+    from dmri_fem_cloud_b200 import btfem, meshes, partition, periodic
+    group = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=600))
+    comm = partition.TorchComm(dist, group=group)
+    xyz, tets, phase = meshes.ecs_slab(ecs, ecs, 2)
+    xyz, tets = meshes.coordinate_order(xyz, tets, axes=(1, 2, 0))       # vertex blocks = slabs normal to y
+    mp, ts, f, fp = sequence(delta=10000.0, Delta=13000.0, k=200.0, b=1000.0)
+    _, Fb = mp.profiles_on_grid(np.concatenate([[0.0], ts[:-1]]))
+    g = np.array([1.0, 1.0, 0.0]) / np.sqrt(2.0)
+    pdir, k, q = [1, 1, 0], 200.0, mp.qvalue
+    kw = dict(rtol=1e-9, atol=1e-10, maxit=100000, q=q, Fb=Fb)
+    lo, hi = xyz.min(axis=0), xyz.max(axis=0)
+    d = partition.DistBTFem(xyz, tets, comm, device=local_rank, phase=phase)
+    try:
+        d.set_diffusion(2e-3)
+        d.set_relaxation(1e-16)
+        d.set_permeability(1e-5)
+        hmin, _ = d.mesh_stats()
+        d.set_periodic(pdir, 3e-3 / hmin, 1e-2 * hmin, lo, hi)            # kappa_e, tol as MyDomain sets them
+        d.assemble()
+        d.solve(k, 0.5, q * f, q * fp, g, **kw)                           # warm-up
+        comm.barrier()
+        res = d.solve(k, 0.5, q * f, q * fp, g, **kw)
+        loop_s = float(comm.max([res["loop_ms"] + res["setup_ms"]])[0]) * 1e-3
+        ndof_real = 2 * d.ndof_global
+    finally:
+        d.close()
+    out = None
+    if rank == 0:
+        with btfem.BTFem(local_rank) as fem:
+            fem.set_mesh(xyz, tets, phase)
+            fem.set_diffusion(2e-3)
+            fem.set_relaxation(1e-16)
+            fem.set_permeability(1e-5)
+            fem.set_periodic(pdir, 3e-3 / hmin, 1e-2 * hmin, lo, hi)
+            fem.assemble()
+            dv, dc = fem.dofmap()
+            fem.set_periodic_gather(*periodic.build_gather(xyz, tets, phase, pdir, lo, hi, dv, dc,
+                                                           bfacets=fem.boundary_facets()))
+            fem.solve(k, 0.5, q * f, q * fp, g, **kw)
+            ref = fem.solve(k, 0.5, q * f, q * fp, g, **kw)
+        single_s = (ref["loop_ms"] + ref["setup_ms"]) * 1e-3
+        s_part, s_one = res["signal"] / res["voi"], ref["signal"] / ref["voi"]
+        out = {"workload": "configs[3] ECS slab %dx%dx2, 226 cylinders, weak periodic x,y, row-partitioned over %d GPUs"
+                           % (ecs, ecs, world),
+               "ndof_real": int(ndof_real), "theta_steps": len(ts), "iters": int(res["total_iters"]),
+               "loop_s": loop_s, "value": ndof_real * len(ts) / loop_s, "unit": UNIT,
+               "us_per_iteration": 1e6 * loop_s / max(1, int(res["total_iters"])),
+               "single_gpu_loop_s": single_s, "single_gpu_iters": int(ref["total_iters"]),
+               "speedup_vs_single_gpu": single_s / loop_s,
+               "rel_signal_err_vs_single_gpu": abs(s_part - s_one) / abs(s_one)}
+    comm.barrier()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -190,6 +279,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--no-hardi", action="store_true", help="skip the HARDI signals/s figure")
+    ap.add_argument("--no-full", action="store_true", help="skip the full-length CPU run (signal check / reference arm)")
+    ap.add_argument("--no-partitioned", action="store_true", help="N > 1: skip the row-partitioned single-mesh figure")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -204,27 +295,33 @@ def main():
         xyz, tets, phase = workload(args.n_box)
         mp, ts, f, fp = sequence(k=k)
         sample = args.cpu_sample_steps
+        ops = cpu_operators(xyz, tets, phase)          # numpy assembly of the pattern: once, outside the timed region
         res = None
         for _ in range(max(1, args.warmup > 0)):       # one untimed pass pages everything in
-            res = cpu_restatement(xyz, tets, phase, mp, f, fp, k, 1)
+            res = cpu_restatement(xyz, tets, phase, mp, f, fp, k, 1, mode=2, ops=ops)
         tsum, steps = 0.0, 0
         for _ in range(args.steps):
-            res = cpu_restatement(xyz, tets, phase, mp, f, fp, k, sample, mode=2)
+            res = cpu_restatement(xyz, tets, phase, mp, f, fp, k, sample, mode=2, ops=ops)
             tsum += res["seconds"]
             steps += sample
         v = res["ndof_real"] * steps / tsum
+        full = None
+        if not args.no_full:                           # one full-length solve beside the sampled steps
+            r = cpu_restatement(xyz, tets, phase, mp, f, fp, k, len(ts), mode=2, ops=ops)
+            full = {"theta_steps": len(ts), "seconds": r["seconds"], "value": r["ndof_real"] * len(ts) / r["seconds"],
+                    "iters": r["iters"], "normalized_signal": r["signal"] / r["voi"]}
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tsum / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": "configs[1] two-compartment permeable PGSE, cell-in-box n_box=%d" % args.n_box,
-                           "ndof_real": res["ndof_real"], "theta_steps_per_solve": len(ts)},
+                "config": make_config(args.n_box, args.gpus, res["ndof_real"], len(xyz), len(tets), res["nnz"], len(ts)),
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": res["cores"], "kind": "port",
                                  "sample": "first %d of %d theta steps per bench step; C/OpenMP restatement of "
                                            "DmriFemLib.solve: A and b re-assembled from element integrals every step "
                                            "(closed forms, cheaper than the reference's FFC kernels) + Jacobi-BiCGStab "
                                            "at the CLI tolerances; FEniCS/PETSc itself is not installable here" % (
-                                               sample, len(ts))},
+                                               sample, len(ts)),
+                                 "full_length_run": full},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -338,6 +435,20 @@ def main():
         except Exception as exc:      # the headline line must still be printed
             hardi_dt, hardi_info = float("inf"), {"error": "%s: %s" % (type(exc).__name__, exc)}
 
+    # ---- one mesh row-partitioned over the N GPUs (configs[3]); never blocks the headline line
+    part_info = None
+    if dist is not None and not args.no_partitioned:
+        part_info = {}
+        for ecs in (400, 800):
+            try:
+                barrier()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    r = partitioned_solve(dist, local_rank, rank, world, ecs)
+                part_info["ecs%d" % ecs] = r
+            except Exception as exc:
+                part_info["ecs%d" % ecs] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+                break
+
     tmax, e2e_max, hardi_max = elapsed, e2e_elapsed, hardi_dt
     if dist is not None:
         import torch
@@ -359,20 +470,22 @@ def main():
         ms_cold = fem.spmv_bench(k, 0.5, q, g, lanes=lanes, nrep=20, flush_l2=True)
         ms_warm = fem.spmv_bench(k, 0.5, q, g, lanes=lanes, nrep=50, flush_l2=False)
         achieved = alg_bytes / (ms_cold * 1e-3) / 1e9
+        stream = lanes == 0 and fem.stream_kernel
+        spmv_kernel = ("k_spmv_stream<MODE_V|MODE_T> (SELL-32 through per-warp TMA rings)" if stream else
+                       "k_spmv_sell<MODE_V|MODE_T>" if lanes == 0 else "k_spmv<%d,MODE_V|MODE_T>" % lanes)
+        # DRAM bytes per launch: from the committed `ncu --set full` capture of this kernel on this workload
+        # (profiles/, dram__bytes_read.sum + dram__bytes_write.sum); null when no capture matches the configuration
+        traffic, traffic_src = None, None
+        tkey = "stream" if stream else ("sell" if lanes == 0 else None)
+        if args.n_box == NCU_TRAFFIC["n_box"] and tkey in NCU_TRAFFIC:
+            traffic, traffic_src = NCU_TRAFFIC[tkey]["bytes"], NCU_TRAFFIC[tkey]["file"]
         spmv_share = res["n_spmv"] * ms_warm / max(res["loop_ms"], 1e-9)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * tmax / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "configs[1] two-compartment permeable PGSE (-M 1 -b 1000 -p 1e-5 -k 200 "
-                                       "-gdir 0 1 0), cell-in-box n_box=%d" % args.n_box,
-                           "ndof_real": ndof_real, "n_vertices": int(len(xyz)), "n_tets": int(len(tets)),
-                           "nnz": fem.nnz, "n_interface_facets": fem.n_iface, "theta_steps_per_solve": nsteps,
-                           "krylov": "bicgstab+jacobi rtol 1e-9 atol 1e-10", "iters_per_solve": res["total_iters"],
-                           "l2_policy": "working set (matrix %.0f MB + 8 vectors %.0f MB) larger than L2; "
-                                        "roofline launch timed after reading a 512 MiB scratch buffer (L2 flush)" % (
-                                            (20.0 * fem.nnz) / 1e6, 8 * 16.0 * fem.ndof / 1e6),
-                           "parallelism": "sweep-sharded x%d (one gradient direction per GPU)" % world,
-                           "spmv_lanes_per_row": lanes},
+                "config": make_config(args.n_box, world, ndof_real, len(xyz), len(tets), fem.nnz, nsteps),
+                "solve": {"n_interface_facets": fem.n_iface, "iters_per_solve": res["total_iters"],
+                          "spmv_lanes_per_row": lanes, "spmv_kernel": spmv_kernel},
                 "device_ms_per_step": dev_ms / args.steps, "assemble_s": assemble_s,
                 "normalized_signal": res["signal"] / res["voi"],
                 "gpu_launches": int(kernels),
@@ -381,10 +494,10 @@ def main():
                         "d2h_bytes_per_step": int(8 * 8 + 4 * 8), "seconds_per_solve": e2e_max / e2e_steps,
                         "normalized_signal": e2e_sig,
                         "api": "dmrifemlib.MyDomain/MRI_simulation.solve (host numpy mesh -> signal)"},
-                "roofline": {"bound": "hbm", "kernel": ("k_spmv_sell<MODE_V|MODE_T>" if lanes == 0 else "k_spmv<%d,MODE_V|MODE_T>" % lanes) + " fused complex SpMV",
+                "roofline": {"bound": "hbm", "kernel": spmv_kernel + " fused complex SpMV",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "peak_source": peak_src,
-                             "traffic": NCU_TRAFFIC["bytes"] if args.n_box == NCU_TRAFFIC["n_box"] and lanes == 0 else None,
+                             "traffic": traffic, "traffic_source": traffic_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch_l2_flushed": ms_cold,
                              "ms_per_launch_back_to_back": ms_warm,
                              "achieved_back_to_back": alg_bytes / (ms_warm * 1e-3) / 1e9,
@@ -403,14 +516,26 @@ def main():
         line["loop_roofline"] = loop_roofline(fem.nnz, fem.ndof, res["total_iters"], nsteps, res["loop_ms"], peak)
         if not args.no_cpu and world == 1:
             entry.build_oracle()
-            cpu = cpu_restatement(xyz, tets, phase, mp, f, fp, k, args.cpu_sample_steps, mode=0)
+            ops = cpu_operators(xyz, tets, phase)
+            cpu_steps = args.cpu_sample_steps if args.no_full else nsteps
+            cpu = cpu_restatement(xyz, tets, phase, mp, f, fp, k, cpu_steps, mode=0, ops=ops)
             line["cpu_baseline"] = {"value": cpu["ndof_real"] * cpu["steps"] / cpu["seconds"], "unit": UNIT,
                                     "cores": cpu["cores"], "kind": "port",
-                                    "sample": "first %d of %d theta steps, oracle C/OpenMP restatement with "
-                                              "pre-combined operators (%.1f s)" % (cpu["steps"], nsteps,
-                                                                                    cpu["seconds"])}
+                                    "sample": "%s %d of %d theta steps, oracle C/OpenMP restatement with "
+                                              "pre-combined operators (%.1f s)" % (
+                                                  "all" if cpu_steps == nsteps else "first", cpu["steps"], nsteps,
+                                                  cpu["seconds"])}
+            if cpu_steps == nsteps:      # same problem, same Krylov tolerances, all theta steps: the two final signals
+                s_cpu, s_gpu = cpu["signal"] / cpu["voi"], res["signal"] / res["voi"]
+                line["signal_check"] = {"signal_rel_err_vs_cpu": abs(s_gpu - s_cpu) / abs(s_cpu),
+                                        "normalized_signal_gpu": s_gpu, "normalized_signal_cpu": s_cpu,
+                                        "krylov_rtol": 1e-9, "krylov_atol": 1e-10, "theta_steps": nsteps,
+                                        "iters_gpu": int(res["total_iters"]), "iters_cpu": cpu["iters"],
+                                        "target": 1e-8}
         else:
             line["cpu_baseline"] = None
+        if part_info is not None:
+            line["partitioned"] = part_info
         print(json.dumps(line))
     fem.close()
     if dist is not None:

@@ -83,6 +83,7 @@ def load_library(path=None):
         "btfem_spmv_bench": (C.c_int, [H, C.c_double, C.c_double, C.c_double, _c_double_p, C.c_int32, C.c_int32,
                                        C.c_int32, _c_double_p]),
         "btfem_set_lanes": (C.c_int, [H, C.c_int32]),
+        "btfem_get_spmv_kernel": (C.c_int, [H, _c_int32_p]),
         "btfem_solve": (C.c_int, [H, C.POINTER(SolveArgs), C.POINTER(SolveOut), _c_int32_p]),
         "btfem_solve_batch": (C.c_int, [H, C.c_int32, C.POINTER(SolveArgs), C.POINTER(SolveOut)]),
         "btfem_get_solution": (C.c_int, [H, _c_double_p]),
@@ -256,6 +257,17 @@ class BTFem:
 
     def set_lanes(self, lanes):
         self._ck(self.lib.btfem_set_lanes(self.h, int(lanes)))
+
+    @property
+    def spmv_kernel(self):
+        """0 CSR / 1 SELL-32 register-staged / 2 SELL-32 through per-warp TMA rings (btfem_get_spmv_kernel)."""
+        kind = C.c_int32(0)
+        self._ck(self.lib.btfem_get_spmv_kernel(self.h, C.byref(kind)))
+        return int(kind.value)
+
+    @property
+    def stream_kernel(self):
+        return self.spmv_kernel == 2
 
     # ---- assembly + parity hooks
     def assemble(self):

@@ -100,6 +100,13 @@ static void set_mesh_cells(btfem_t* h, int64_t nv, const double* xyz, int64_t nc
     for (int64_t i = 0; i < nc; ++i) BT_REQUIRE(phase[i] == 0 || phase[i] == 1, "phase must be 0 or 1");
   invalidate(h);
   h->h_vmaster.clear();
+  if (nv != h->nv || nc != h->nc) {   // per-cell / per-vertex inputs of the previous mesh do not fit this one
+    if (h->dkind != 0) { h->dkind = 0; h->h_D.assign(1, 1.0); }
+    if (h->t2kind != 0) { h->t2kind = 0; h->h_invT2.assign(1, 0.0); }
+    if (h->kkind != 0) { h->kkind = 0; h->h_kappa.assign(1, 0.0); h->nmark = 0; }
+    h->h_marker.clear();
+    h->h_ic.clear();
+  }
   h->nv = nv;
   h->nc = nc;
   h->cell_nv = cell_nv;
@@ -349,6 +356,14 @@ int btfem_set_lanes(btfem_t* h, int32_t lanes) {
     BT_REQUIRE(lanes == 0 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32,
                "lanes must be 0 (SELL-32), 4, 8, 16 or 32");
     h->lanes = lanes;
+  });
+}
+
+int btfem_get_spmv_kernel(btfem_t* h, int32_t* kind) {
+  return guarded(h, [&] {
+    BT_REQUIRE(kind, "null argument");
+    BT_REQUIRE(h->assembled, "call btfem_assemble first");
+    *kind = h->lanes != 0 ? 0 : (bt_stream_kernel_usable(h) ? 2 : 1);
   });
 }
 

@@ -9,8 +9,41 @@
 
 #include "../../include/btfem.h"
 
-#define BT_NUM_SMS 148          // B200: 2 dies x 74 SMs
+// SM count of the current device (148 on B200: 2 dies x 74 SMs), read once per device from the runtime
+inline int bt_num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int v = 0;
+    cached[dev] = (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) ? v : 148;
+  }
+  return cached[dev];
+}
+#define BT_NUM_SMS bt_num_sms()
 #define BT_MAX_PARTIALS 4096
+// warp-stream layout of the operator for the TMA kernels (solve.cu): every warp of the launch owns a contiguous
+// byte stream of "pieces" (<= PS_W columns of one SELL slice: w x 32 int32 columns, then w x 32 value pairs, and --
+// behind the last piece of a slice -- the 32 row numbers of the slice), which it pulls through a ring of
+// shared-memory stages with cp.async.bulk + mbarrier.  Offsets are counted in units of 128 bytes.
+#define BT_PS_MAX_WARPS 16      // warps per block of the stream kernels: 8 (ring depth 4), 12 (3) or 16 (2)
+#define BT_PS_W 8               // columns per piece
+#define BT_PS_COLU 5            // 128-byte units per stream column: 32 lanes x (4 + 16) bytes
+#define BT_PS_STAGE ((BT_PS_W * BT_PS_COLU + 1) * 128)   // bytes of a ring stage: a full piece + the row block
+// byte offset of column j (< width) of a slice whose stream starts at unit u0: piece p = j / W starts at u0 + p W 5
+__host__ __device__ inline size_t bt_ps_col_off(int64_t u0, int j, int lane) {
+  const int p = j / BT_PS_W;
+  return (size_t)(u0 + (int64_t)p * BT_PS_W * BT_PS_COLU) * 128 + (size_t)(j - p * BT_PS_W) * 128 + (size_t)lane * 4;
+}
+__host__ __device__ inline size_t bt_ps_val_off(int64_t u0, int width, int j, int lane) {
+  const int p = j / BT_PS_W;
+  const int w = width - p * BT_PS_W < BT_PS_W ? width - p * BT_PS_W : BT_PS_W;
+  return (size_t)(u0 + (int64_t)p * BT_PS_W * BT_PS_COLU) * 128 + (size_t)w * 128 + (size_t)(j - p * BT_PS_W) * 512 +
+         (size_t)lane * 16;
+}
+__host__ __device__ inline size_t bt_ps_row_off(int64_t u0, int width, int lane) {   // behind the last piece
+  return (size_t)(u0 + (int64_t)(width > 0 ? width : 0) * BT_PS_COLU) * 128 + (size_t)lane * 4;
+}
 #define BT_SELL_SIGMA 1024      // sorting window (rows) of the SELL-32 layout    // upper bound on the grid of any reducing kernel
 
 struct BtError {
@@ -261,6 +294,15 @@ struct btfem {
   // (P_k, Q_k)/P_rr, (Jx_k, Jy_k), Jz_k in SELL order; J_g is formed per member inside the SpMV
   DevArray<double2> d_PQs, d_Jxys;
   DevArray<double> d_Jzs, d_gdirs /*[members*3]*/;
+  // warp-stream copy of the SELL operator (whole-mesh handles; built with the pattern, filled by bt_combine)
+  int ps_blocks = 0;               // blocks (= SMs) the layout was built for; 0 = none
+  int ps_warps = 8;                // warps per block the layout was built for
+  int64_t ps_units = 0;            // length of a stream in 128-byte units
+  int ps_max_pieces = 0;           // longest piece list of a warp
+  DevArray<int32_t> d_ps_ptr;      // [ps_blocks * ps_warps + 1] piece range of every warp
+  DevArray<int4> d_ps_piece;       // {stream offset (units), columns, slice, 1 = last piece of its slice}
+  DevArray<int32_t> d_ps_scol0;    // [n_slice] stream offset (units) of the first piece of the slice
+  DevArray<unsigned char> d_PJt, d_QJt;   // [ps_units * 128] per-solve operator values + columns + rows, stream order
   DevArray<uint32_t> d_src;        // contribution ids sorted by (row,col), stable
   DevArray<int64_t> d_seg;         // [nnz+1] segment offsets into d_src
   DevArray<double> d_vals[8];      // M,S,R,Jx,Jy,Jz,I,B
@@ -291,6 +333,7 @@ struct btfem {
   DevArray<double> d_cA, d_cb, d_Fb;
   DevArray<double> d_partials;     // [8][BT_MAX_PARTIALS]
   DevArray<KrylovCtrl> d_ctrl;
+  DevArray<unsigned int> d_gridbar;   // persistent BiCGStab kernel: [0] arrival counter, [32] its value at kernel start
   KrylovCtrl* h_ctrl = nullptr;    // pinned, one per batch member
   int h_ctrl_n = 0;
   size_t vec_npad = 0;             // padded vector length (elements)
@@ -319,6 +362,7 @@ void bt_assemble_values(btfem* h);
 void bt_build_periodic(btfem* h);
 
 // solve.cu
+bool bt_stream_kernel_usable(const btfem* h);   // warp-stream layout built for this device and not switched off
 void bt_combine(btfem* h, double dt, double theta, const double g[3], int pc, int member = 0, int members = 1);
 void bt_strong_build(btfem* h, const double g[3]);
 void bt_strong_recombine(btfem* h, cudaStream_t st, double dt, double theta, int pc);

@@ -296,6 +296,31 @@ __global__ void k_sell_columns(int64_t nslice, const int32_t* __restrict__ slice
   }
 }
 
+// Warp-stream layout: the column indices and the row numbers of every slice go to their place in BOTH operator
+// streams (PJt, QJt); the values follow per solve (solve.cu: k_combine).  Offsets: bt_ps_*_off (btfem_internal.cuh).
+__global__ void k_stream_columns(int64_t nslice, const int32_t* __restrict__ slice_ptr,
+                                 const int32_t* __restrict__ sell_col, const int32_t* __restrict__ sell_row,
+                                 const int32_t* __restrict__ scol0, unsigned char* __restrict__ PJt,
+                                 unsigned char* __restrict__ QJt) {
+  int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (slot >= nslice * 32) return;
+  const int64_t s = slot >> 5;
+  const int lane = (int)(slot & 31);
+  const int base = slice_ptr[s];
+  const int width = (slice_ptr[s + 1] - base) >> 5;
+  const int64_t u0 = scol0[s];
+  for (int j = 0; j < width; ++j) {
+    const size_t off = bt_ps_col_off(u0, j, lane);
+    const int c = sell_col[base + j * 32 + lane];
+    *reinterpret_cast<int32_t*>(PJt + off) = c;
+    *reinterpret_cast<int32_t*>(QJt + off) = c;
+  }
+  const size_t roff = bt_ps_row_off(u0, width, lane);
+  const int row = sell_row[slot];
+  *reinterpret_cast<int32_t*>(PJt + roff) = row;
+  *reinterpret_cast<int32_t*>(QJt + roff) = row;
+}
+
 // ------------------------------------------------------------------------------------ assembly
 
 struct AsmArgs {
@@ -838,6 +863,101 @@ void bt_build_pattern(btfem* h) {
     h->d_sched.upload(sched.data(), sched.size(), st);
     h->d_sched_ptr.upload(ptr.data(), ptr.size(), st);
     h->sched_grid = grid;
+  }
+  // Warp streams for the TMA kernels (whole-mesh handles): one block per SM, ps_warps warps each; slices are dealt
+  // in ascending order to the warp with the least work so far (same simulated queue as above), and every warp's
+  // pieces are stored back to back in the order it will consume them.
+  h->ps_blocks = 0;
+  h->d_PJt.release();
+  h->d_QJt.release();
+  if (h->nv_own < 0 && nslice > 0 && !getenv("BTFEM_NO_STREAM")) {
+    const char* w_env = getenv("BTFEM_PS_WARPS");   // warps per block of the stream kernels: 8, 12 or 16
+    const int wpb = (w_env && (atoi(w_env) == 12 || atoi(w_env) == 16)) ? atoi(w_env) : 8;
+    const int nb = BT_NUM_SMS, nw = nb * wpb;
+    h->ps_warps = wpb;
+    // Dealing: chunks of wpb consecutive slices stay together on one block (its warps work on neighbouring rows at
+    // the same time and share the gathered x lines in L1), but the chunks are dealt in a scrambled order, each to the
+    // block with the least work so far.  A plain round-robin resonates with the mesh: on a structured n^3 box
+    // warp w would always get the same in-plane position (slices w, w + nw, ...) and the blocks' pass times differ
+    // by +-12 %.  Inside a block the slices of a chunk go, longest first, to its least loaded warps.
+    std::vector<std::vector<int32_t>> lists(nw);
+    typedef std::pair<int64_t, int> Load;
+    const int64_t nchunk = (nslice + wpb - 1) / wpb;
+    std::vector<int64_t> order(nchunk);
+    for (int64_t i = 0; i < nchunk; ++i) order[i] = i;
+    if (!getenv("BTFEM_PS_NO_SCRAMBLE"))
+      std::sort(order.begin(), order.end(), [](int64_t x, int64_t y) {
+        const uint64_t hx = (uint64_t)(x + 1) * 0x9E3779B97F4A7C15ull, hy = (uint64_t)(y + 1) * 0x9E3779B97F4A7C15ull;
+        return hx != hy ? hx < hy : x < y;
+      });
+    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+    for (int b = 0; b < nb; ++b) heap.push(Load(0, b));
+    std::vector<int64_t> wload(nw, 0);
+    for (int64_t oc = 0; oc < nchunk; ++oc) {
+      const int64_t s0 = order[oc] * wpb, s1 = std::min<int64_t>(nslice, s0 + wpb);
+      Load l = heap.top();
+      heap.pop();
+      const int b = l.second;
+      std::vector<Load> sl;   // (cost, slice), longest first
+      int64_t add = 0;
+      for (int64_t s = s0; s < s1; ++s) {
+        const int width = (slice_ptr[s + 1] - slice_ptr[s]) / 32;
+        const int64_t cost = 2 + width + 3 * ((width + BT_PS_W - 1) / BT_PS_W);   // columns + per-piece overhead
+        sl.push_back(Load(cost, (int)s));
+        add += cost;
+      }
+      std::sort(sl.begin(), sl.end(), [](const Load& x, const Load& y) { return x.first != y.first ? x.first > y.first : x.second < y.second; });
+      std::vector<char> used(wpb, 0);
+      for (const Load& e : sl) {   // each slice of the chunk to a different warp: the least loaded one still free
+        int best = -1;
+        for (int w = 0; w < wpb; ++w)
+          if (!used[w] && (best < 0 || wload[(size_t)b * wpb + w] < wload[(size_t)b * wpb + best])) best = w;
+        used[best] = 1;
+        wload[(size_t)b * wpb + best] += e.first;
+        lists[(size_t)b * wpb + best].push_back(e.second);
+      }
+      heap.push(Load(l.first + add, b));
+    }
+    if (const char* rot = getenv("BTFEM_PS_ROTATE")) {   // experiment: block b takes the lists of block b + rot
+      const int k = ((atoi(rot) % nb) + nb) % nb * wpb;
+      std::rotate(lists.begin(), lists.begin() + k, lists.end());
+    }
+    std::vector<int32_t> ptr(nw + 1, 0), scol0(nslice, 0);
+    std::vector<int4> pieces;
+    int64_t unit = 0;
+    int maxp = 0;
+    for (int w = 0; w < nw; ++w) {
+      ptr[w] = (int32_t)pieces.size();
+      for (int32_t s : lists[w]) {
+        const int width = (slice_ptr[s + 1] - slice_ptr[s]) / 32;
+        scol0[s] = (int32_t)unit;
+        if (width == 0) pieces.push_back(make_int4((int)unit, 0, s, 1));   // rows without entries: the row block only
+        for (int j = 0; j < width; j += BT_PS_W) {
+          const int wd = std::min(BT_PS_W, width - j);
+          pieces.push_back(make_int4((int)unit, wd, s, j + wd >= width ? 1 : 0));
+          unit += wd * BT_PS_COLU;
+        }
+        unit += 1;   // the row block
+        BT_REQUIRE(unit < (int64_t)0x7fffffffLL, "warp-stream storage exceeds int32 units");
+      }
+      maxp = std::max(maxp, (int)pieces.size() - ptr[w]);
+    }
+    ptr[nw] = (int32_t)pieces.size();
+    BT_REQUIRE(unit == (tot / 32) * BT_PS_COLU + nslice, "warp-stream layout does not cover the SELL storage");
+    h->ps_blocks = nb;
+    h->ps_units = unit;
+    h->ps_max_pieces = maxp;
+    h->d_ps_ptr.upload(ptr.data(), ptr.size(), st);
+    h->d_ps_piece.upload(pieces.data(), pieces.size(), st);
+    h->d_ps_scol0.upload(scol0.data(), scol0.size(), st);
+    h->d_PJt.alloc((size_t)unit * 128 + 16);
+    h->d_QJt.alloc((size_t)unit * 128 + 16);
+    h->d_PJt.zero(st);
+    h->d_QJt.zero(st);
+    k_stream_columns<<<nblocks(nslice * 32), TPB, 0, st>>>(nslice, h->d_slice_ptr.p, h->d_sell_col.p, h->d_sell_row.p,
+                                                          h->d_ps_scol0.p, h->d_PJt.p, h->d_QJt.p);
+    BT_CUDA(cudaGetLastError());
+    BT_CUDA(cudaStreamSynchronize(st));   // host vectors above go out of scope
   }
   BT_CUDA(cudaGetLastError());
   BT_CUDA(cudaStreamSynchronize(st));

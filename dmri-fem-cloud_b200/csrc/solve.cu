@@ -25,9 +25,10 @@
 namespace {
 
 constexpr int TPB = 256;
-constexpr int NWARP = TPB / 32;
+constexpr int NWARP = TPB / 32;   // kernels of TPB threads (reduce_finalize / grid_reduce read blockDim.x)
 
-enum { MODE_PLAIN = 0, MODE_RHS = 1, MODE_RESID = 2, MODE_V = 3, MODE_T = 4 };
+enum { MODE_PLAIN = 0, MODE_RHS = 1, MODE_RESID = 2, MODE_V = 3, MODE_T = 4,
+       MODE_RHSP = 5 /* right-hand side inside the persistent kernel: r = r^ = y, no p / v reset */ };
 enum { TK_RHS = 0, TK_RESID = 1, TK_V = 2, TK_T = 3, TK_XR = 4, TK_SIG = 5 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -160,9 +161,10 @@ __device__ __forceinline__ void dist_allreduce(double (&v)[NV], const DistView& 
 template <int NV>
 __device__ bool reduce_finalize(double (&v)[NV], double* __restrict__ partials, unsigned int* ticket,
                                 const DistView* dist = nullptr) {
-  __shared__ double sm[NV][NWARP];
+  __shared__ double sm[NV][32];
   __shared__ int s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int NWARP = blockDim.x >> 5;
 #pragma unroll
   for (int q = 0; q < NV; ++q) {
     double t = warp_sum(v[q]);
@@ -189,7 +191,7 @@ __device__ bool reduce_finalize(double (&v)[NV], double* __restrict__ partials, 
 #pragma unroll
   for (int q = 0; q < NV; ++q) {
     double acc = 0.0;
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += TPB) acc += vp[q * BT_MAX_PARTIALS + i];
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) acc += vp[q * BT_MAX_PARTIALS + i];
     double t = warp_sum(acc);
     __syncthreads();
     if (lane == 0) sm[q][warp] = t;
@@ -239,7 +241,8 @@ __global__ void k_combine(int64_t nnz, const int32_t* __restrict__ rowidx, const
                           const double* __restrict__ dinv, double2* __restrict__ PJ, double2* __restrict__ QJ,
                           double* __restrict__ Bhat, const int32_t* __restrict__ rowptr,
                           const int32_t* __restrict__ sell_slot, const int32_t* __restrict__ slice_ptr,
-                          double2* __restrict__ PJs, double2* __restrict__ QJs) {
+                          double2* __restrict__ PJs, double2* __restrict__ QJs, const int32_t* __restrict__ scol0,
+                          unsigned char* __restrict__ PJt, unsigned char* __restrict__ QJt) {
   int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (k >= nnz) return;
   double di = dinv[rowidx[k]];
@@ -255,9 +258,17 @@ __global__ void k_combine(int64_t nnz, const int32_t* __restrict__ rowidx, const
     const int row = rowidx[k];
     const int slot = sell_slot[row];
     if (slot < 0) return;   // halo row of a row-partitioned handle
-    const int pos = slice_ptr[slot >> 5] + (int)(k - rowptr[row]) * 32 + (slot & 31);
+    const int j = (int)(k - rowptr[row]);
+    const int sbase = slice_ptr[slot >> 5];
+    const int pos = sbase + j * 32 + (slot & 31);
     PJs[pos] = pj;
     QJs[pos] = qj;
+    if (PJt) {   // and in the warp-stream layout (setup.cu: k_stream_columns)
+      const int width = (slice_ptr[(slot >> 5) + 1] - sbase) >> 5;
+      const size_t off = bt_ps_val_off(scol0[slot >> 5], width, j, slot & 31);
+      *reinterpret_cast<double2*>(PJt + off) = pj;
+      *reinterpret_cast<double2*>(QJt + off) = qj;
+    }
   }
 }
 
@@ -325,6 +336,16 @@ struct SpmvArgs {
   const double* dinv;        // 1 / P_rr per row
   const double* gdirs;       // [members][3]
   double* sig_out;           // k_signal: [members][2]
+  // warp-stream kernels (k_spmv_stream, persistent BiCGStab): see btfem_internal.cuh / setup.cu
+  int ps_blocks;             // 0: layout not usable for this solve
+  int ps_warps;              // warps per block of the layout
+  const int32_t* ps_ptr;     // [ps_blocks * BT_PS_WARPS + 1]
+  const int4* ps_piece;      // {stream column, columns, slice, last}
+  const unsigned char* PJt;
+  const unsigned char* QJt;
+  unsigned int* gridbar;     // persistent kernel: grid barrier words
+  unsigned long long* prof;  // persistent kernel: optional phase timers of block 0 (BTFEM_PROFILE_PERSIST), or null
+  int step_begin, step_end;  // persistent kernel: time steps of this launch
   DistView dist;             // row-partitioned solve: peers, LL buffers, send lists (dist.on == 0: whole mesh)
   // device-driven loop: the BiCGStab iteration is the body of a graph WHILE node whose condition the kernels set
   cudaGraphConditionalHandle cond;
@@ -399,13 +420,22 @@ __device__ __forceinline__ ModeSetup mode_setup(const SpmvArgs& a) {
   return m;
 }
 
-// what happens to one finished row y_row = (A x)_row, and which dot-product terms it contributes
+// what happens to one finished row y_row = (A x)_row, and which dot-product terms it contributes.
+// The one vector entry the epilogue reads (epilogue_operand) can be loaded ahead of the row sum.
 template <int MODE>
-__device__ __forceinline__ void row_epilogue(const SpmvArgs& a, int row, double2 y, double (&acc)[2]) {
+__device__ __forceinline__ double2 epilogue_operand(const SpmvArgs& a, int row) {
+  if (MODE == MODE_RHS || MODE == MODE_RHSP) return a.rhs_add ? a.rhs_add[row] : make_double2(0.0, 0.0);
+  if (MODE == MODE_RESID) return a.t[row];
+  if (MODE == MODE_V) return a.rp[row];
+  if (MODE == MODE_T) return a.s[row];
+  return make_double2(0.0, 0.0);
+}
+template <int MODE>
+__device__ __forceinline__ void row_epilogue_op(const SpmvArgs& a, int row, double2 y, const double2 op, double (&acc)[2]) {
   if (MODE == MODE_PLAIN) {
     a.y_plain[row] = y;
   } else if (MODE == MODE_RHS) {
-    if (a.rhs_add) { double2 w = a.rhs_add[row]; y.x += w.x; y.y += w.y; }
+    if (a.rhs_add) { y.x += op.x; y.y += op.y; }
     if (a.ctrl->nonzero_guess) {
       a.t[row] = y;                      // b^ kept for the residual kernel
     } else {
@@ -414,21 +444,26 @@ __device__ __forceinline__ void row_epilogue(const SpmvArgs& a, int row, double2
     a.p[row] = make_double2(0.0, 0.0);
     a.v[row] = make_double2(0.0, 0.0);
     acc[0] += y.x * y.x + y.y * y.y;
+  } else if (MODE == MODE_RHSP) {
+    if (a.rhs_add) { y.x += op.x; y.y += op.y; }
+    a.r[row] = y; a.rp[row] = y;
+    acc[0] += y.x * y.x + y.y * y.y;
   } else if (MODE == MODE_RESID) {
-    double2 b = a.t[row];
-    double2 rr = make_double2(b.x - y.x, b.y - y.y);
+    double2 rr = make_double2(op.x - y.x, op.y - y.y);
     a.r[row] = rr; a.rp[row] = rr;
     acc[0] += rr.x * rr.x + rr.y * rr.y;
   } else if (MODE == MODE_V) {
     a.v[row] = y;
-    double2 q = a.rp[row];
-    acc[0] += y.x * q.x + y.y * q.y;
+    acc[0] += y.x * op.x + y.y * op.y;
   } else {
     a.t[row] = y;
-    double2 sv = a.s[row];
-    acc[0] += sv.x * y.x + sv.y * y.y;
+    acc[0] += op.x * y.x + op.y * y.y;
     acc[1] += y.x * y.x + y.y * y.y;
   }
+}
+template <int MODE>
+__device__ __forceinline__ void row_epilogue(const SpmvArgs& a, int row, double2 y, double (&acc)[2]) {
+  row_epilogue_op<MODE>(a, row, y, epilogue_operand<MODE>(a, row), acc);
 }
 
 // grid-wide completion of the dot products + the scalar recurrences that depend on them
@@ -771,6 +806,547 @@ __global__ void __launch_bounds__(TPB, MINB) k_spmv_sell(SpmvArgs a_in) {
     }
   }
   mode_finalize<MODE>(a, acc);
+}
+
+
+// ---- variant D (default for whole-mesh single solves): SELL-32 through per-warp TMA rings.  The operator is stored a
+// second time in "warp-stream" order (setup.cu): every warp of the launch owns a contiguous byte stream of pieces
+// (<= BT_PS_W columns of a slice; int32 columns, then value pairs, then -- last piece of a slice -- the 32 row numbers)
+// which lane 0 pulls into a ring of D shared-memory stages with cp.async.bulk (SASS: UBLKCP), completion on one
+// mbarrier per stage (SYNCS).  No register is spent on staging the 20 B/nonzero stream, D - 1 pieces per warp are
+// always in flight whatever the consumer does, and the x gathers, the row numbers and the epilogue operands of piece
+// k+1 are issued before the arithmetic of piece k.  Row sums run in ascending column order exactly as in
+// k_spmv_sell, so a row gets the same bits from both kernels.
+constexpr int PS_STAGE = BT_PS_STAGE;
+constexpr int ps_smem(int NW, int D) { return NW * D * PS_STAGE + NW * D * 8; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// The ring of one warp.  Pieces are numbered by a counter that runs over the warp's list again and again (one
+// pass per SpMV); piece c sits in stage c % D and its barrier completes with parity (c / D) & 1.
+template <int D>
+struct WarpRing {
+  unsigned char* buf;     // D stages
+  uint32_t buf_s, bar_s;  // shared-window addresses of the stages / of the D barriers
+  const int4* pieces;     // this warp's list
+  int np;
+  unsigned long long l2_evict_first;
+
+  __device__ __forceinline__ void setup(unsigned char* smem, const int32_t* ps_ptr, const int4* ps_piece) {
+    const int wl = threadIdx.x >> 5;
+    buf = smem + (size_t)wl * D * PS_STAGE;
+    buf_s = smem_u32(buf);
+    const int nwarp = blockDim.x >> 5;
+    bar_s = smem_u32(smem + (size_t)nwarp * D * PS_STAGE + (size_t)wl * D * 8);
+    const int w = blockIdx.x * nwarp + wl;
+    const int p0 = __ldg(ps_ptr + w);
+    np = __ldg(ps_ptr + w + 1) - p0;
+    pieces = ps_piece + p0;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_evict_first));
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int s = 0; s < D; ++s) mbar_init(bar_s + 8 * s, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
+  // lane 0: fetch list entry `idx` of operator stream T as ring piece number c; the stage's barrier completes when
+  // the bytes have landed
+  __device__ __forceinline__ void fetch(const unsigned char* T, int idx, unsigned int c) const {
+    const int4 d = __ldg(pieces + idx);
+    const unsigned int st = c % D;
+    const uint32_t bytes = (uint32_t)(d.y * BT_PS_COLU + d.w) * 128u;
+    const uint32_t bar = bar_s + 8 * st;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    // the operator streams past once per SpMV: evict-first in L2, which keeps the Krylov vectors resident
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            buf_s + st * PS_STAGE),
+        "l"(T + (size_t)d.x * 128), "r"(bytes), "r"(bar), "l"(l2_evict_first)
+        : "memory");
+  }
+  __device__ __forceinline__ void wait(unsigned int c) const { mbar_wait(bar_s + 8 * (c % D), (c / D) & 1u); }
+  __device__ __forceinline__ const unsigned char* stage(unsigned int c) const { return buf + (c % D) * PS_STAGE; }
+};
+
+// what a warp holds of a piece between its gather step and its arithmetic step
+struct PieceRegs {
+  int4 d;
+  double2 xv[BT_PS_W];
+  int row;        // last piece of a slice: the row of this lane and the vector entry its epilogue reads
+  double2 op;
+};
+
+// the vector whose entry the epilogue of a row reads (epilogue_operand), for a mode known at run time
+__device__ __forceinline__ const double2* epilogue_vector(const SpmvArgs& a, int mode) {
+  return mode == MODE_RESID ? a.t : mode == MODE_V ? a.rp : mode == MODE_T ? a.s
+         : (mode == MODE_RHS || mode == MODE_RHSP) ? a.rhs_add : nullptr;
+}
+__device__ __forceinline__ void row_epilogue_rt(const SpmvArgs& a, int mode, int row, double2 y, const double2 op,
+                                                double (&acc)[2]) {
+  switch (mode) {   // warp-uniform
+    case MODE_PLAIN: row_epilogue_op<MODE_PLAIN>(a, row, y, op, acc); break;
+    case MODE_RHS: row_epilogue_op<MODE_RHS>(a, row, y, op, acc); break;
+    case MODE_RESID: row_epilogue_op<MODE_RESID>(a, row, y, op, acc); break;
+    case MODE_V: row_epilogue_op<MODE_V>(a, row, y, op, acc); break;
+    case MODE_T: row_epilogue_op<MODE_T>(a, row, y, op, acc); break;
+    default: row_epilogue_op<MODE_RHSP>(a, row, y, op, acc); break;
+  }
+}
+
+// gather step of ring piece c: wait for the bytes, read the columns, issue the x loads (and the epilogue loads)
+template <int D>
+__device__ __forceinline__ void piece_gather(const double2* opv, const WarpRing<D>& r, unsigned int c, int idx,
+                                             const double2* __restrict__ x, PieceRegs& q) {
+  q.d = __ldg(r.pieces + idx);
+  r.wait(c);
+  const unsigned char* sp = r.stage(c);
+  const int32_t* cs = reinterpret_cast<const int32_t*>(sp) + (threadIdx.x & 31);
+#pragma unroll
+  for (int j = 0; j < BT_PS_W; ++j)
+    if (j < q.d.y) q.xv[j] = ldv_gather_f64x2(x + cs[j * 32]);
+  if (q.d.w) {
+    q.row = cs[q.d.y * BT_PS_COLU * 32];
+    q.op = make_double2(0.0, 0.0);
+    if (q.row >= 0 && opv) q.op = opv[q.row];
+  }
+}
+// arithmetic step: (ar, ai) += sum_j (V.x + i c V.y) x_j in ascending column order
+template <int D>
+__device__ __forceinline__ void piece_fma(const WarpRing<D>& r, unsigned int c, double cc, const PieceRegs& q,
+                                          double& ar, double& ai) {
+  const double2* vs = reinterpret_cast<const double2*>(r.stage(c) + q.d.y * 128) + (threadIdx.x & 31);
+#pragma unroll
+  for (int j = 0; j < BT_PS_W; ++j)
+    if (j < q.d.y) {
+      const double2 val = vs[j * 32];
+      const double pa = val.x, pb = cc * val.y;
+      ar = fma(pa, q.xv[j].x, ar);
+      ar = fma(-pb, q.xv[j].y, ar);
+      ai = fma(pa, q.xv[j].y, ai);
+      ai = fma(pb, q.xv[j].x, ai);
+    }
+}
+
+// One SpMV pass of this warp over its list: ring pieces c0 .. c0 + np - 1, operator stream T; the first
+// min(D, np) pieces are already in flight (or landed).  Every ring counter value is fetched exactly once, in order:
+// when piece k is consumed its stage takes list entry k + D of T while that exists, then entry k + D - np of `Tnext`
+// (the stream of the pass that follows; null: nothing) up to its first min(D, np) entries; entries of the next pass
+// whose stages this pass never touches (np < D) are fetched at once.  Returns c0 + np.
+template <int D, int G>
+__device__ __forceinline__ unsigned int stream_pass(const SpmvArgs& a, int mode, const WarpRing<D>& r, unsigned int c0,
+                                                    const unsigned char* T, const unsigned char* Tnext,
+                                                    const double2* __restrict__ x, double cc, double (&acc)[2]) {
+  static_assert(G >= 2 && G <= D, "the pieces whose gathers are in flight must all sit in the ring");
+  const int lane = threadIdx.x & 31;
+  const int np = r.np;
+  const double2* opv = epilogue_vector(a, mode);
+  double ar = 0.0, ai = 0.0;
+  PieceRegs q[G];   // gathers of G - 1 pieces are in flight while one piece is multiplied
+  auto finish = [&](int k, const PieceRegs& qq) {   // piece k is done: epilogue of its slice, refill of its stage
+    if (qq.d.w) {
+      if (qq.row >= 0) row_epilogue_rt(a, mode, qq.row, make_double2(ar, ai), qq.op, acc);
+      ar = 0.0;
+      ai = 0.0;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const int nx = k + D;
+      if (nx < np) r.fetch(T, nx, c0 + nx);
+      else if (Tnext && nx - np < min(D, np)) r.fetch(Tnext, nx - np, c0 + nx);
+    }
+  };
+  if (Tnext && lane == 0)
+    for (int i = 0; i < np && np + i < D; ++i) r.fetch(Tnext, i, c0 + np + i);
+#pragma unroll
+  for (int g = 0; g < G - 1; ++g)
+    if (g < np) piece_gather(opv, r, c0 + g, g, x, q[g]);
+  for (int k0 = 0; k0 < np; k0 += G) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int k = k0 + g;
+      if (k < np) {
+        const int kn = k + G - 1;
+        if (kn < np) piece_gather(opv, r, c0 + kn, kn, x, q[(g + G - 1) % G]);
+        piece_fma(r, c0 + k, cc, q[g], ar, ai);
+        finish(k, q[g]);
+      }
+    }
+  }
+  return c0 + np;
+}
+
+template <int MODE, int NW, int D, int G>
+__global__ void __launch_bounds__(NW * 32, 1) k_spmv_stream(SpmvArgs a) {
+  extern __shared__ __align__(128) unsigned char ps_ring[];
+  const ModeSetup m = mode_setup<MODE>(a);
+  if (m.skip) return;
+  const unsigned char* T = MODE == MODE_RHS ? a.QJt : a.PJt;
+  WarpRing<D> r;
+  r.setup(ps_ring, a.ps_ptr, a.ps_piece);
+  if ((threadIdx.x & 31) == 0)
+    for (int i = 0; i < D && i < r.np; ++i) r.fetch(T, i, (unsigned int)i);
+  double acc[2] = {0.0, 0.0};
+  stream_pass<D, G>(a, MODE, r, 0u, T, nullptr, m.x, m.c, acc);
+  mode_finalize<MODE>(a, acc);
+}
+
+
+// ---- the whole Jacobi-BiCGStab time loop as ONE persistent kernel (whole-mesh single solves, zero initial guess).
+// One block per SM, launched cooperatively; per time step: RHS pass, then iterations of
+//     p-update | barrier | v = A p, (r^,v) | reduce | s-update | barrier | t = A s, (t,s),(t,t) | reduce | x,r-update, (r^,r),(r,r) | reduce
+// with the SpMV passes running on the per-warp TMA rings above.  What the persistent form buys:
+//  * the rings never drain: while the blocks sit in a barrier / reduction or run a vector phase, every warp's ring
+//    already holds the first pieces of the NEXT pass (stream_pass refills with `Tnext`), so a pass starts at full
+//    bandwidth instead of paying launch latency + ramp (5.7 us per launch on this part, profiles/r2a_membench2*);
+//  * every block finishes the reductions itself (fixed order over the block partials -> all blocks hold the same
+//    bits), so alpha / omega / rho never travel through global memory and there is no last-block serialisation;
+//  * no launch gaps, no WHILE-node evaluation.
+// The recurrences, the order of the convergence tests and the reason codes are those of the kernel chain
+// (k_update_p .. k_update_xr), i.e. PETSc's KSPSolve_BCGS + KSPConvergedDefault.
+struct GridSync {
+  unsigned int* count;     // arrivals, monotonic (wrap-safe comparison)
+  unsigned int target;     // value that completes the next barrier
+  __device__ __forceinline__ void arrive_wait() {   // thread 0 of every block, between two __syncthreads
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(count, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(count) : "memory");
+    } while ((int)(seen - target) < 0);
+    __threadfence();
+  }
+};
+
+__device__ __forceinline__ void grid_barrier(GridSync& g) {
+  __syncthreads();
+  if (threadIdx.x == 0) g.arrive_wait();
+  __syncthreads();
+}
+
+// Sum of NV per-thread terms over the whole grid, returned to EVERY thread of every block (same bits everywhere):
+// block partial -> partials[q][block] -> barrier -> every block adds the partials of all blocks in a fixed order.
+template <int NV>
+__device__ __forceinline__ void grid_reduce(double (&v)[NV], double* __restrict__ partials, GridSync& g) {
+  __shared__ double sm[NV][32];
+  __shared__ double tot[NV];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int NWARP = blockDim.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    const double t = warp_sum(v[q]);
+    if (lane == 0) sm[q][warp] = t;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      double t = lane < NWARP ? sm[q][lane] : 0.0;
+      t = warp_sum(t);
+      if (lane == 0) __stcg(partials + q * BT_MAX_PARTIALS + blockIdx.x, t);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) g.arrive_wait();
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      double t = 0.0;
+      for (unsigned int b = lane; b < gridDim.x; b += 32) t += __ldcg(partials + q * BT_MAX_PARTIALS + b);
+      t = warp_sum(t);
+      if (lane == 0) tot[q] = t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NV; ++q) v[q] = tot[q];
+}
+
+// Vector phases of the persistent kernel.  U rows per thread are loaded before any is used: with one block of 256
+// threads per SM the loops would otherwise pay one L2 round trip per row.  No __restrict__ / read-only loads: every
+// vector is rewritten by other blocks between two barriers.
+constexpr int PV_U = 8, PX_U = 4;
+__device__ __noinline__ void pv_update_p(int n, int gid, int gsz, bool first, double beta, double ob, const double2* rv,
+                                         const double2* v, double2* p) {
+  for (int i0 = gid; i0 < n; i0 += PV_U * gsz) {
+    double2 rr[PV_U], vv[PV_U], pp[PV_U];
+#pragma unroll
+    for (int u = 0; u < PV_U; ++u) {
+      const int i = i0 + u * gsz;
+      rr[u] = vv[u] = pp[u] = make_double2(0.0, 0.0);
+      if (i < n) {
+        rr[u] = rv[i];
+        if (!first) { vv[u] = v[i]; pp[u] = p[i]; }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PV_U; ++u) {
+      const int i = i0 + u * gsz;
+      if (i < n) {
+        if (first) {
+          p[i] = rr[u];   // p = r: what the kernel chain gets from p = v = 0
+        } else {
+          pp[u].x = rr[u].x - ob * vv[u].x + beta * pp[u].x;
+          pp[u].y = rr[u].y - ob * vv[u].y + beta * pp[u].y;
+          p[i] = pp[u];
+        }
+      }
+    }
+  }
+}
+__device__ __noinline__ void pv_update_s(int n, int gid, int gsz, double alpha, const double2* rv, const double2* v,
+                                         double2* sv) {
+  for (int i0 = gid; i0 < n; i0 += PV_U * gsz) {
+    double2 rr[PV_U], vv[PV_U];
+#pragma unroll
+    for (int u = 0; u < PV_U; ++u) {
+      const int i = i0 + u * gsz;
+      rr[u] = vv[u] = make_double2(0.0, 0.0);
+      if (i < n) { rr[u] = rv[i]; vv[u] = v[i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < PV_U; ++u) {
+      const int i = i0 + u * gsz;
+      if (i < n) sv[i] = make_double2(rr[u].x - alpha * vv[u].x, rr[u].y - alpha * vv[u].y);
+    }
+  }
+}
+__device__ __noinline__ void pv_update_xr(int n, int gid, int gsz, bool fresh, double alpha, double omega, const double2* p,
+                                          const double2* sv, const double2* t, const double2* rp, double2* x, double2* rv,
+                                          double* red) {
+  double a0 = 0.0, a1 = 0.0;
+  for (int i0 = gid; i0 < n; i0 += PX_U * gsz) {
+    double2 pp[PX_U], ss[PX_U], tt[PX_U], qq[PX_U], xx[PX_U];
+#pragma unroll
+    for (int u = 0; u < PX_U; ++u) {
+      const int i = i0 + u * gsz;
+      pp[u] = ss[u] = tt[u] = qq[u] = xx[u] = make_double2(0.0, 0.0);
+      if (i < n) {
+        pp[u] = p[i]; ss[u] = sv[i]; tt[u] = t[i]; qq[u] = rp[i];
+        if (!fresh) xx[u] = x[i];   // zero initial guess: x starts from 0
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PX_U; ++u) {
+      const int i = i0 + u * gsz;
+      if (i < n) {
+        xx[u].x += alpha * pp[u].x + omega * ss[u].x;
+        xx[u].y += alpha * pp[u].y + omega * ss[u].y;
+        x[i] = xx[u];
+        const double2 rr = make_double2(ss[u].x - omega * tt[u].x, ss[u].y - omega * tt[u].y);
+        rv[i] = rr;
+        a0 += rr.x * qq[u].x + rr.y * qq[u].y;
+        a1 += rr.x * rr.x + rr.y * rr.y;
+      }
+    }
+  }
+  red[0] = a0;
+  red[1] = a1;
+}
+
+// Krylov state of the persistent kernel, one copy per block in shared memory (every block holds the same bits):
+// thread 0 updates it between two __syncthreads, everybody reads it.  Registers stay free for the pass body.
+struct PersistState {
+  double bn, ttol, rho, rho_old, alpha, omega, rnorm, cA, cb;
+  long long total_iters;
+  unsigned long long tprev;
+  int it, max_iters, mode, step, reason;
+  unsigned int bar_target;
+};
+
+template <int NW, int D, int G>
+__global__ void __launch_bounds__(NW * 32, 1) k_bicgstab_persistent(SpmvArgs a) {
+  extern __shared__ __align__(128) unsigned char ps_ring[];
+  __shared__ PersistState S;
+  if (a.ctrl->failed) return;   // uniform: written by an earlier launch only
+  const int lane = threadIdx.x & 31;
+  const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
+  const int gsz = gridDim.x * NW * 32, gid = blockIdx.x * NW * 32 + threadIdx.x;
+  if (threadIdx.x == 0) {
+    S.mode = MODE_RHSP;
+    S.step = a.step_begin;
+    S.it = 0;
+    S.reason = 0;
+    S.total_iters = a.ctrl->total_iters;
+    S.max_iters = a.ctrl->max_iters;
+    S.bar_target = a.gridbar[32];   // arrivals before this launch (written at the end of the previous one)
+    S.tprev = a.prof ? global_ns() : 0ull;
+    if (a.step_begin < a.step_end) {
+      S.cb = a.ctrl->theta_cb_scale * a.cb[a.step_begin];
+      S.cA = a.ctrl->theta_cA_scale * a.cA[a.step_begin];
+    }
+  }
+  // optional phase timers (block 0, thread 0): prof[k] += time since the previous mark
+#define PROF(k)                                   \
+  if (a.prof && leader) {                         \
+    const unsigned long long tn_ = global_ns();   \
+    a.prof[k] += tn_ - S.tprev;                   \
+    S.tprev = tn_;                                \
+  }
+  WarpRing<D> r;
+  r.setup(ps_ring, a.ps_ptr, a.ps_piece);
+  const int nfl = min(D, r.np);   // pieces of the next pass that are in flight between two passes
+  unsigned int c = 0;             // ring piece counter of this warp
+  if (lane == 0)
+    for (int i = 0; i < nfl; ++i) r.fetch(a.QJt, i, (unsigned int)i);
+  __syncthreads();
+  GridSync gs;
+  gs.count = a.gridbar;
+
+  // A state machine over the SpMV passes (right-hand side -> v = A p -> t = A s -> v = A p ...), so that the pass
+  // body is instantiated ONCE; the mode only selects the operator stream, the gathered vector and the epilogue.
+  for (;;) {
+    const int mode = S.mode, step = S.step;
+    if (step >= a.step_end || S.reason < 0) break;
+    // ---- one pass: y = (V.x + i cc V.y) x over this warp's pieces
+    double acc[2] = {0.0, 0.0};
+    {
+      const unsigned long long tp0 = a.prof ? global_ns() : 0ull;
+      const unsigned char* T = mode == MODE_RHSP ? a.QJt : a.PJt;
+      const double2* xg = mode == MODE_RHSP ? a.u : (mode == MODE_V ? a.p : a.s);
+      c = stream_pass<D, G>(a, mode, r, c, T, a.PJt, xg, mode == MODE_RHSP ? S.cb : S.cA, acc);
+      if (a.prof && lane == 0) {   // per-warp pass time: a.prof[16 + warp of the grid]; the SM the block runs on
+        a.prof[16 + blockIdx.x * NW + (threadIdx.x >> 5)] += global_ns() - tp0;
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (threadIdx.x == 0) a.prof[16 + gridDim.x * NW + blockIdx.x] = smid;
+      }
+    }
+    PROF(mode == MODE_RHSP ? 0 : (mode == MODE_V ? 3 : 7));
+    gs.target = S.bar_target;
+    if (mode == MODE_V) {
+      // ---- alpha = rho / (r^, v) ; s = r - alpha v
+      double red1[1] = {acc[0]};
+      grid_reduce<1>(red1, a.partials + 2 * BT_MAX_PARTIALS, gs);
+      PROF(4);
+      if (threadIdx.x == 0) {
+        if (red1[0] == 0.0) S.reason = BTFEM_EBREAKDOWN;
+        else S.alpha = S.rho / red1[0];
+      }
+      __syncthreads();
+      if (S.reason == 0) {
+        pv_update_s(a.n, gid, gsz, S.alpha, a.r, a.v, a.s);
+        PROF(5);
+        grid_barrier(gs);
+        PROF(6);
+        if (threadIdx.x == 0) { S.mode = MODE_T; S.bar_target = gs.target; }
+        __syncthreads();
+        continue;
+      }
+    } else if (mode == MODE_T) {
+      // ---- omega = (t,s) / (t,t) ; x <- x + alpha p + omega s ; r <- s - omega t ; rho' = (r, r^) ; ||r||
+      double red2[2] = {acc[0], acc[1]};
+      grid_reduce<2>(red2, a.partials + 3 * BT_MAX_PARTIALS, gs);
+      PROF(8);
+      const double omega = (red2[1] == 0.0) ? 0.0 : red2[0] / red2[1];
+      pv_update_xr(a.n, gid, gsz, S.it == 0, S.alpha, omega, a.p, a.s, a.t, a.rp, a.u, a.r, red2);
+      PROF(9);
+      grid_reduce<2>(red2, a.partials + 5 * BT_MAX_PARTIALS, gs);
+      PROF(10);
+      if (threadIdx.x == 0) {
+        const double rho_used = S.rho, rnorm = sqrt(red2[1]);
+        const int it = S.it + 1;
+        S.omega = omega;
+        S.rho_old = rho_used;
+        S.rho = red2[0];
+        S.rnorm = rnorm;
+        S.it = it;
+        int reason = 0;
+        if (!(rnorm == rnorm) || isinf(rnorm)) reason = BTFEM_ENAN;
+        else if (rnorm <= S.ttol) reason = rnorm < a.ctrl->atol ? 3 : 2;
+        else if (rnorm >= a.ctrl->dtol * S.bn) reason = BTFEM_EDTOL;
+        else if (rho_used == 0.0 || omega == 0.0) reason = BTFEM_EBREAKDOWN;
+        else if (it >= a.ctrl->maxit) reason = BTFEM_ENOTCONV;
+        S.reason = reason;
+      }
+      __syncthreads();
+    } else {
+      // ---- ||r||, start of the Krylov solve of this step
+      double red1[1] = {acc[0]};
+      grid_reduce<1>(red1, a.partials, gs);
+      PROF(10);
+      if (threadIdx.x == 0) {
+        const double bn = sqrt(red1[0]), atol = a.ctrl->atol;
+        S.bn = bn;
+        S.ttol = fmax(a.ctrl->rtol * bn, atol);
+        S.rho = red1[0]; S.rho_old = 1.0; S.alpha = 1.0; S.omega = 1.0; S.rnorm = bn;
+        S.it = 0;
+        int reason = 0;
+        if (!(bn == bn) || isinf(bn)) reason = BTFEM_ENAN;
+        else if (bn <= S.ttol) reason = bn < atol ? 3 : 2;
+        S.reason = reason;
+      }
+      __syncthreads();
+    }
+    if (S.reason == 0) {
+      // ---- p <- r - omega*beta*v + beta*p   (first iteration: p = r), then v = A p
+      const bool first = S.it == 0;
+      const double beta = first ? 0.0 : (S.rho / S.rho_old) * (S.alpha / S.omega);
+      pv_update_p(a.n, gid, gsz, first, beta, S.omega * beta, a.r, a.v, a.p);
+      PROF(1);
+      grid_barrier(gs);
+      PROF(2);
+      if (threadIdx.x == 0) { S.mode = MODE_V; S.bar_target = gs.target; }
+      __syncthreads();
+      continue;
+    }
+    // ---- end of the time step (k_step_end / k_step_fail of the kernel chain)
+    if (S.it == 0 && S.reason > 0) {   // converged before the first iteration with a zero guess: PETSc returns x = 0
+      for (int i = gid; i < a.n; i += gsz) a.u[i] = make_double2(0.0, 0.0);
+      grid_barrier(gs);                // the next right-hand side gathers x
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int it = S.it, reason = S.reason;
+      S.total_iters += it;
+      S.max_iters = max(S.max_iters, it);
+      if (blockIdx.x == 0) {
+        KrylovCtrl* ctrl = a.ctrl;
+        if (a.iters_out) a.iters_out[step] = it;
+        ctrl->bnorm = S.bn; ctrl->ttol = S.ttol; ctrl->rnorm = S.rnorm;
+        ctrl->rho = S.rho; ctrl->rho_old = S.rho_old; ctrl->alpha = S.alpha; ctrl->omega = S.omega;
+        ctrl->iters = it; ctrl->reason = reason; ctrl->done = 1;
+        ctrl->step = step; ctrl->step_next = step + 1;
+        ctrl->total_iters = S.total_iters; ctrl->max_iters = S.max_iters;
+        if (reason < 0) ctrl->failed = reason;
+      }
+      S.bar_target = gs.target;
+      if (reason >= 0) {
+        S.reason = 0;
+        S.step = step + 1;
+        S.mode = MODE_RHSP;
+        if (step + 1 < a.step_end) {
+          S.cb = a.ctrl->theta_cb_scale * a.cb[step + 1];
+          S.cA = a.ctrl->theta_cA_scale * a.cA[step + 1];
+        }
+      }
+    }
+    __syncthreads();
+    // the ring holds the first pieces of P (a pass v = A p was expected): let them land, fetch those of Q instead
+    if (S.reason >= 0 && S.step < a.step_end) {
+      for (int i = 0; i < nfl; ++i) r.wait(c + i);
+      __syncwarp();
+      c += nfl;   // every counter value is fetched (and completes) exactly once, in order
+      if (lane == 0)
+        for (int i = 0; i < nfl; ++i) r.fetch(a.QJt, i, c + i);
+    }
+  }
+  // nothing may still be in flight into shared memory when the block retires
+  for (int i = 0; i < nfl; ++i) r.wait(c + i);
+  if (leader) a.gridbar[32] = S.bar_target;
+#undef PROF
 }
 
 
@@ -1226,6 +1802,12 @@ inline int batch_group() {
 constexpr int SELL_UNR_DEFAULT = 4;
 constexpr int SELL_MINB_DEFAULT = 3;
 
+// 8-warp stream kernels: ring depth 5 / gathers of two pieces in flight (BTFEM_PS_DEEP=0: depth 4 / one piece)
+inline bool ps_deep() {
+  static const bool v = !(getenv("BTFEM_PS_DEEP") && getenv("BTFEM_PS_DEEP")[0] == '0');
+  return v;
+}
+
 template <int MODE>
 void launch_spmv(int lanes, SpmvArgs a, cudaStream_t st, int members = 1) {
   a.use_sell = lanes == 0 || lanes >= 100;
@@ -1238,6 +1820,22 @@ void launch_spmv(int lanes, SpmvArgs a, cudaStream_t st, int members = 1) {
       k_spmv_sell_batch<MODE, 4><<<dim3(g, (members + 3) / 4), TPB, 0, st>>>(a);
     else
       k_spmv_sell_batch<MODE, 8><<<dim3(g, (members + 7) / 8), TPB, 0, st>>>(a);
+    return;
+  }
+  if (lanes == 0 && a.ps_blocks > 0 && members == 1 && !a.dist.on) {   // SELL-32 through per-warp TMA rings
+    // configurations (warps per block, ring depth, gather depth); ps_cfg: 0 = (8,4,2), 1 = (8,5,3), 2 = (12,3,2), 3 = (16,2,2)
+    static bool attr_set = false;   // per instantiation
+    if (!attr_set) {
+      BT_CUDA(cudaFuncSetAttribute(k_spmv_stream<MODE, 8, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps_smem(8, 4)));
+      BT_CUDA(cudaFuncSetAttribute(k_spmv_stream<MODE, 8, 5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps_smem(8, 5)));
+      BT_CUDA(cudaFuncSetAttribute(k_spmv_stream<MODE, 12, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps_smem(12, 3)));
+      BT_CUDA(cudaFuncSetAttribute(k_spmv_stream<MODE, 16, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps_smem(16, 2)));
+      attr_set = true;
+    }
+    if (a.ps_warps == 16) k_spmv_stream<MODE, 16, 2, 2><<<a.ps_blocks, 512, ps_smem(16, 2), st>>>(a);
+    else if (a.ps_warps == 12) k_spmv_stream<MODE, 12, 3, 2><<<a.ps_blocks, 384, ps_smem(12, 3), st>>>(a);
+    else if (ps_deep()) k_spmv_stream<MODE, 8, 5, 3><<<a.ps_blocks, 256, ps_smem(8, 5), st>>>(a);
+    else k_spmv_stream<MODE, 8, 4, 2><<<a.ps_blocks, 256, ps_smem(8, 4), st>>>(a);
     return;
   }
   if (lanes == 0) {   // SELL-32
@@ -1297,6 +1895,15 @@ SpmvArgs base_args(btfem* h) {
   a.sell_col = h->d_sell_col.p;
   a.PJs = h->d_PJs.p;
   a.QJs = h->d_QJs.p;
+  // warp-stream kernels: the layout exists and bt_combine filled it (single solve, not the strong-periodic recombination)
+  if (bt_stream_kernel_usable(h) && h->comb_members == 1 && h->comb_dt > 0) {
+    a.ps_blocks = h->ps_blocks;
+    a.ps_warps = h->ps_warps;
+    a.ps_ptr = h->d_ps_ptr.p;
+    a.ps_piece = h->d_ps_piece.p;
+    a.PJt = h->d_PJt.p;
+    a.QJt = h->d_QJt.p;
+  }
   a.PJ = h->d_PJ.p;
   a.QJ = h->d_QJ.p;
   a.cA = h->d_cA.p;
@@ -1477,6 +2084,11 @@ int gmres_solve_step(btfem* h, const btfem_solve_args* sa, SpmvArgs a, double cA
 
 // ===================================================================================== host entry points
 
+bool bt_stream_kernel_usable(const btfem* h) {
+  static const bool off = getenv("BTFEM_NO_STREAM_KERNEL") != nullptr;
+  return !off && h->nv_own < 0 && h->ps_blocks > 0 && h->ps_blocks == BT_NUM_SMS;
+}
+
 // Operator values of batch member `member` (of `members`): the value arrays hold `members` copies back to back.
 void bt_combine(btfem* h, double dt, double theta, const double g[3], int pc, int member, int members) {
   const bool single = members == 1;
@@ -1506,7 +2118,8 @@ void bt_combine(btfem* h, double dt, double theta, const double g[3], int pc, in
       h->d_PJ.p + (size_t)member * h->nnz, h->d_QJ.p + (size_t)member * h->nnz,
       h->periodic ? h->d_Bhat.p : nullptr, h->d_rowptr.p, h->d_sell_slot.p, h->d_slice_ptr.p,
       h->n_slice ? h->d_PJs.p + (size_t)member * h->nnz_sell : nullptr,
-      h->n_slice ? h->d_QJs.p + (size_t)member * h->nnz_sell : nullptr);
+      h->n_slice ? h->d_QJs.p + (size_t)member * h->nnz_sell : nullptr,
+      h->d_ps_scol0.p, (single && h->ps_blocks) ? h->d_PJt.p : nullptr, (single && h->ps_blocks) ? h->d_QJt.p : nullptr);
   BT_CUDA(cudaGetLastError());
   h->comb_members = members;
   h->comb_dt = dt; h->comb_theta = theta; h->comb_pc = pc;
@@ -1770,9 +2383,50 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     cudaGetLastError();
     if (getenv("BTFEM_DEBUG")) fprintf(stderr, "[btfem] graph %p: %zu nodes, %d kernel nodes pinned to the L2 window\n", (void*)g, nn, pinned);
   };
+  // Whole-mesh single BiCGStab solves from a zero guess run the time loop as ONE persistent cooperative kernel
+  // (k_bicgstab_persistent) -- one launch for all time steps, or one per step behind the periodic-BC kernels.
+  // BTFEM_PERSIST=0 falls back to the kernel chain in a WHILE graph.
+  const char* pers_env = getenv("BTFEM_PERSIST");
+  const bool persist = dev_loop && !part && !strong && members == 1 && lanes == 0 && !sa->nonzero_guess &&
+                       a.ps_blocks > 0 && a.ps_blocks == BT_NUM_SMS && !(pers_env && pers_env[0] == '0');
+  const void* pers_fn = a.ps_warps == 16   ? (const void*)k_bicgstab_persistent<16, 2, 2>
+                        : a.ps_warps == 12 ? (const void*)k_bicgstab_persistent<12, 3, 2>
+                        : ps_deep()        ? (const void*)k_bicgstab_persistent<8, 5, 3>
+                                           : (const void*)k_bicgstab_persistent<8, 4, 2>;
+  const int pers_smem = a.ps_warps == 16 ? ps_smem(16, 2) : a.ps_warps == 12 ? ps_smem(12, 3) : ps_deep() ? ps_smem(8, 5) : ps_smem(8, 4);
+  if (persist) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      BT_CUDA(cudaFuncSetAttribute(k_bicgstab_persistent<8, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps_smem(8, 4)));
+      BT_CUDA(cudaFuncSetAttribute(k_bicgstab_persistent<8, 5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps_smem(8, 5)));
+      BT_CUDA(cudaFuncSetAttribute(k_bicgstab_persistent<12, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps_smem(12, 3)));
+      BT_CUDA(cudaFuncSetAttribute(k_bicgstab_persistent<16, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ps_smem(16, 2)));
+      attr_set = true;
+    }
+    if (h->d_gridbar.n != 64) {
+      h->d_gridbar.alloc(64);
+      h->d_gridbar.zero(st);
+    }
+    a.gridbar = h->d_gridbar.p;
+  }
+  DevArray<unsigned long long> d_prof;
+  if (persist && getenv("BTFEM_PROFILE_PERSIST")) {
+    d_prof.alloc(16 + (size_t)a.ps_blocks * (a.ps_warps + 1));
+    d_prof.zero(st);
+    a.prof = d_prof.p;
+  }
+  auto launch_persistent = [&](int s0, int s1) {
+    SpmvArgs ap = a;
+    ap.step_begin = s0;
+    ap.step_end = s1;
+    void* kargs[] = {(void*)&ap};
+    BT_CUDA(cudaLaunchCooperativeKernel(pers_fn, dim3(a.ps_blocks), dim3(a.ps_warps * 32), kargs, (size_t)pers_smem, st));
+  };
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
-  if (dev_loop) {
+  if (persist) {
+    // nothing to capture
+  } else if (dev_loop) {
     BT_CUDA(cudaGraphCreate(&graph, 0));
     cudaGraphConditionalHandle hc;
     BT_CUDA(cudaGraphConditionalHandleCreate(&hc, graph, 0, cudaGraphCondAssignDefault));
@@ -1812,7 +2466,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     BT_CUDA(cudaStreamEndCapture(st, &graph));
     pin_vectors(graph);
   }
-  BT_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+  if (graph) BT_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
 
   DevArray<double> d_sig;   // allocated before the loop: no allocation may sit between two collectives
   d_sig.alloc(2 * (size_t)members);
@@ -1822,8 +2476,74 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   int64_t n_spmv = 0, n_kernels = 0;
   int est = 4;
   int fail = 0;
+  int64_t persistent_launches = 0;
+  if (persist) {
+    if (!periodic) {
+      launch_persistent(0, (int)sa->nsteps);
+      persistent_launches = 1;
+    } else {
+      for (int64_t step = 0; step < sa->nsteps; ++step) {
+        k_periodic_ubc<<<((int)h->n_pb + TPB - 1) / TPB, TPB, 0, st>>>(
+            (int)h->n_pb, h->d_ctrl.p, h->d_Fb.p, sa->q, sa->gdir[0], sa->gdir[1], sa->gdir[2], h->d_pb_dof.p,
+            h->d_pb_src.p, h->d_pb_w.p, h->d_pb_dx.p, h->d_u.p, h->d_ubc.p, a.dist);
+        k_periodic_rhs<<<((int)h->n_pb_rows + TPB - 1) / TPB, TPB, 0, st>>>(
+            (int)h->n_pb_rows, h->d_pb_rows.p, h->d_rowptr.p, h->d_colidx.p, h->d_Bhat.p, 1.0 - sa->theta,
+            h->d_ubc.p, h->d_rhs_add.p);
+        launch_persistent((int)step, (int)step + 1);
+        ++persistent_launches;
+      }
+    }
+  }
+  if (a.prof) {   // where block 0 spent the loop (us per iteration follow from total_iters)
+    unsigned long long pr[16];
+    BT_CUDA(cudaMemcpyAsync(pr, d_prof.p, sizeof(pr), cudaMemcpyDeviceToHost, st));
+    BT_CUDA(cudaStreamSynchronize(st));
+    static const char* names[11] = {"rhs pass", "p update", "barrier(p)", "pass v=Ap", "reduce(v)", "s update", "barrier(s)",
+                                    "pass t=As", "reduce(t)", "x,r update", "reduce(x,r) + rest"};
+    fprintf(stderr, "[btfem] persistent kernel, block 0, ms per phase:");
+    for (int k = 0; k < 11; ++k) fprintf(stderr, " %s %.2f |", names[k], 1e-6 * (double)pr[k]);
+    fprintf(stderr, "\n");
+    if (const char* path = getenv("BTFEM_PROFILE_PERSIST_FILE")) {   // per-warp time inside the passes, ns
+      std::vector<unsigned long long> w((size_t)a.ps_blocks * a.ps_warps);
+      BT_CUDA(cudaMemcpy(w.data(), d_prof.p + 16, sizeof(unsigned long long) * w.size(), cudaMemcpyDeviceToHost));
+      std::vector<int32_t> pp(w.size() + 1);
+      std::vector<int4> pc(h->d_ps_piece.n);
+      BT_CUDA(cudaMemcpy(pp.data(), h->d_ps_ptr.p, sizeof(int32_t) * pp.size(), cudaMemcpyDeviceToHost));
+      BT_CUDA(cudaMemcpy(pc.data(), h->d_ps_piece.p, sizeof(int4) * pc.size(), cudaMemcpyDeviceToHost));
+      std::vector<unsigned long long> sm((size_t)a.ps_blocks);
+      BT_CUDA(cudaMemcpy(sm.data(), d_prof.p + 16 + w.size(), sizeof(unsigned long long) * sm.size(), cudaMemcpyDeviceToHost));
+      // gather footprint of every slice: distinct 32-byte sectors / 128-byte lines of x touched per column, summed
+      std::vector<int32_t> sp(h->n_slice + 1), sc(h->nnz_sell);
+      BT_CUDA(cudaMemcpy(sp.data(), h->d_slice_ptr.p, sizeof(int32_t) * sp.size(), cudaMemcpyDeviceToHost));
+      BT_CUDA(cudaMemcpy(sc.data(), h->d_sell_col.p, sizeof(int32_t) * sc.size(), cudaMemcpyDeviceToHost));
+      std::vector<long long> sect(h->n_slice, 0), line(h->n_slice, 0);
+      for (int64_t sl = 0; sl < h->n_slice; ++sl)
+        for (int base = sp[sl]; base < sp[sl + 1]; base += 32) {
+          int v[32];
+          for (int l = 0; l < 32; ++l) v[l] = sc[base + l];
+          std::sort(v, v + 32);
+          for (int l = 0; l < 32; ++l) {
+            if (l == 0 || (v[l] >> 1) != (v[l - 1] >> 1)) ++sect[sl];
+            if (l == 0 || (v[l] >> 3) != (v[l - 1] >> 3)) ++line[sl];
+          }
+        }
+      if (FILE* f = fopen(path, "w")) {   // warp, ns in passes, pieces, columns, slices, SM of the block, sectors, lines
+        for (size_t i = 0; i < w.size(); ++i) {
+          long long cols = 0, slices = 0, se = 0, li = 0;
+          for (int k = pp[i]; k < pp[i + 1]; ++k) {
+            cols += pc[k].y;
+            slices += pc[k].w;
+            if (pc[k].w) { se += sect[pc[k].z]; li += line[pc[k].z]; }
+          }
+          fprintf(f, "%zu %llu %d %lld %lld %llu %lld %lld\n", i, w[i], pp[i + 1] - pp[i], cols, slices, sm[i / a.ps_warps],
+                  se, li);
+        }
+        fclose(f);
+      }
+    }
+  }
   if (dev_loop) {
-    for (int64_t step = 0; step < sa->nsteps; ++step) BT_CUDA(cudaGraphLaunch(gexec, st));
+    for (int64_t step = 0; !persist && step < sa->nsteps; ++step) BT_CUDA(cudaGraphLaunch(gexec, st));
     BT_CUDA(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl.p, sizeof(KrylovCtrl) * members, cudaMemcpyDeviceToHost, st));
     BT_CUDA(cudaStreamSynchronize(st));
     for (int b = 0; b < members; ++b) {
@@ -1835,6 +2555,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     }
     const int64_t passes = *std::max_element(total_iters.begin(), total_iters.end());
     n_kernels = (prologue_kernels + 2) * sa->nsteps + kernels_per_iter * passes;   // kernels that did work
+    if (persist) n_kernels = persistent_launches + (periodic ? 2 * sa->nsteps : 0);
     if (iters_per_step) d_iters.download(iters_per_step, st);
   }
   for (int64_t step = 0; !dev_loop && step < sa->nsteps && !fail; ++step) {
@@ -1905,8 +2626,8 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   if (fail == BTFEM_ECOMM) {   // no further collective may be started: the peers are gone or out of step
     h->dist_failed = true;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
-    cudaGraphExecDestroy(gexec);
-    cudaGraphDestroy(graph);
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
     throw BtError{fail, "row-partitioned solve: a peer rank did not answer within the time limit"};
   }
   a.sig_out = d_sig.p;
@@ -1918,8 +2639,8 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   BT_CUDA(cudaEventElapsedTime(&ms_setup, e0, e1));
   BT_CUDA(cudaEventElapsedTime(&ms_loop, e1, e2));
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
-  cudaGraphExecDestroy(gexec);
-  cudaGraphDestroy(graph);
+  if (gexec) cudaGraphExecDestroy(gexec);
+  if (graph) cudaGraphDestroy(graph);
   h->have_solution = true;
   for (int b = 0; b < members; ++b) {
     btfem_solve_out* out = &outv[b];

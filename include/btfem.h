@@ -148,6 +148,10 @@ int btfem_spmv_bench(btfem_t* h, double dt, double theta, double c, const double
                      int32_t lanes, int32_t nrep, int32_t flush_l2, double* ms_per_launch);
 /* SpMV variant used by the solver: 0 = SELL-32 (default), else CSR with `lanes` threads per row */
 int btfem_set_lanes(btfem_t* h, int32_t lanes);
+/* Which fused-SpMV kernel a single whole-mesh solve on this (assembled) handle runs: 0 = CSR, `lanes` threads per row;
+ * 1 = SELL-32, register-staged loads (k_spmv_sell); 2 = SELL-32 through per-warp TMA rings (k_spmv_stream:
+ * cp.async.bulk + mbarrier).  Bench / profiling hook; the reference has no counterpart (PETSc MatMult). */
+int btfem_get_spmv_kernel(btfem_t* h, int32_t* kind);
 
 /* ---- the theta loop ---------------------------------------------------------------------
  * MRI_simulation.solve (DmriFemLib.py:878-915): for n in 0..nsteps-1

@@ -309,8 +309,9 @@ def test_gmres_restart_path():
 
 
 def test_batched_solves_equal_individual_solves():
-    """btfem_solve_batch: members (different directions and q) advanced in lock step give exactly the
-    signals of the one-at-a-time solves (same kernels, same reduction order per member)."""
+    """btfem_solve_batch: members (different directions and q) advanced in lock step.  A member gets exactly the same
+    bits whatever batch it travels in (same kernels, same reduction order per member); the one-at-a-time solves run
+    the persistent kernel (other grouping of the dot-product partial sums), so they agree to solver tolerance."""
     _, xyz, tets, phase, co = CASES[3]
     seq = orc.pgse(2000.0, 6000.0)
     k = 200.0
@@ -324,11 +325,16 @@ def test_batched_solves_equal_individual_solves():
         _setup(fem, xyz, tets, phase, co)
         single = [fem.solve(k, 0.5, cA, cb, g, rtol=1e-10, atol=1e-14) for cA, cb, g in members]
         batch = fem.solve_batch(k, 0.5, members, rtol=1e-10, atol=1e-14)
+        split = fem.solve_batch(k, 0.5, members[:2], rtol=1e-10, atol=1e-14) + \
+            fem.solve_batch(k, 0.5, members[2:], rtol=1e-10, atol=1e-14)
         again = fem.solve(k, 0.5, *members[1], rtol=1e-10, atol=1e-14)      # back to a batch of one
+    for sb, ss in zip(batch, split):
+        assert sb["signal"] == ss["signal"]                                  # bit-identical
+        assert sb["total_iters"] == ss["total_iters"]
     for s1, sb in zip(single, batch):
-        assert s1["signal"] == sb["signal"]                                  # bit-identical
-        assert s1["total_iters"] == sb["total_iters"]
-    assert again["signal"] == single[1]["signal"]
+        assert abs(s1["signal"] - sb["signal"]) <= 1e-9 * abs(sb["signal"])
+        assert abs(s1["total_iters"] - sb["total_iters"]) <= max(3, 0.02 * sb["total_iters"])
+    assert again["signal"] == single[1]["signal"]                            # reproducible
     assert len({round(s["signal"], 6) for s in batch}) == len(batch)         # the members really differ
 
 
