@@ -253,11 +253,17 @@ def test_preprocess_phase_and_cell_fields(tmp_path):
                               "4e4", "4e4", "-o", str(tmp_path / "files.h5")])
     finally:
         preprocess._load = monkey_load
-    z = np.load(tmp_path / "files.npz")
-    assert rc == 0 and np.array_equal(z["phase"], lay % 2) and set(z["d00"][lay == 1]) == {1e-3} and set(z["ic"]) == {1.0}
     from dmri_fem_cloud_b200 import cli
+    z = cli.load_input(str(tmp_path / "files.h5"))         # DOLFIN HDF5 container, like the reference's output
+    assert rc == 0 and np.array_equal(z["phase"], lay % 2) and set(z["d00"][lay == 1]) == {1e-3} and set(z["ic"]) == {1.0}
+    assert all(k in z for k in ("xyz", "tets", "phase", "T2", "ic", "d00", "d22"))
+    preprocess._load = lambda p: (xyz, tets)
+    try:                                                   # `-o x.npz` keeps the NumPy side format
+        assert preprocess.main(["preprocess", "-m", "mesh.xml", "-pmk", str(pmk), "-o", str(tmp_path / "files.npz")]) == 0
+    finally:
+        preprocess._load = monkey_load
     data = cli.load_input(str(tmp_path / "files.npz"))
-    assert all(k in data for k in ("xyz", "tets", "phase", "T2", "ic", "d00", "d22"))
+    assert all(k in data for k in ("xyz", "tets", "phase", "T2", "ic", "d00", "d22")) and np.array_equal(data["phase"], z["phase"])
 
 
 def test_bench_reference_arm_contract():
