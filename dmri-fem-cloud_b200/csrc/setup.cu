@@ -11,6 +11,8 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <functional>
 #include <queue>
@@ -22,17 +24,14 @@ namespace {
 constexpr int TPB = 256;
 inline int nblocks(int64_t n, int tpb = TPB) { return (int)std::max<int64_t>(1, (n + tpb - 1) / tpb); }
 
-struct TempStorage {
+struct TempStorage {   // CUB scratch, from the handle's stream-ordered pool like every other device array
+  DevArray<unsigned char> buf;
   void* p = nullptr;
   size_t bytes = 0;
-  ~TempStorage() {
-    if (p) cudaFree(p);
-  }
   void reserve(size_t b) {
     if (b <= bytes) return;
-    if (p) cudaFree(p);
-    p = nullptr;
-    BT_CUDA(cudaMalloc(&p, b));
+    buf.alloc(b);
+    p = buf.p;
     bytes = b;
   }
 };
@@ -605,33 +604,89 @@ void bt_mesh_stats(btfem* h, double* hmin, double* hmax) {
   *hmax = hi;
 }
 
+// ---- dof map on the device: active (vertex, compartment) pairs are numbered vertex-major by a prefix sum
+// (DmriFemLib's 2 / 4 fields on every vertex + ident_zeros pinning, DmriFemLib.py:240-254, become active-dof numbering)
+__global__ void k_dofmap_mark(int64_t nc, int cell_nv, const int32_t* __restrict__ tets, const int32_t* __restrict__ phase,
+                              const int32_t* __restrict__ vmaster, int32_t* __restrict__ active) {
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int ph = phase ? phase[c] : 0;
+  for (int k = 0; k < cell_nv; ++k) {
+    int v = tets[4 * c + k];
+    if (vmaster) v = vmaster[v];
+    active[2 * (int64_t)v + ph] = 1;   // benign race: every writer stores 1
+  }
+}
+__global__ void k_dofmap_number(int64_t nv2, const int32_t* __restrict__ active, const int32_t* __restrict__ excl,
+                                int32_t* __restrict__ vc2dof, int32_t* __restrict__ dof_vertex,
+                                int32_t* __restrict__ dof_comp) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nv2) return;
+  if (active[i]) {
+    const int32_t d = excl[i];
+    vc2dof[i] = d;
+    dof_vertex[d] = (int32_t)(i >> 1);
+    dof_comp[d] = (int32_t)(i & 1);
+  } else {
+    vc2dof[i] = -1;
+  }
+}
+__global__ void k_dofmap_slaves(int64_t nv, const int32_t* __restrict__ vmaster, int32_t* __restrict__ vc2dof) {
+  const int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (v >= nv) return;
+  const int m = vmaster[v];
+  if (m != v) {   // masters are their own masters (checked in btfem_set_periodic_map): no chain to follow
+    vc2dof[2 * v] = vc2dof[2 * (int64_t)m];
+    vc2dof[2 * v + 1] = vc2dof[2 * (int64_t)m + 1];
+  }
+}
+__global__ void k_cell_dofs(int64_t nc, int cell_nv, const int32_t* __restrict__ tets, const int32_t* __restrict__ phase,
+                            const int32_t* __restrict__ vc2dof, int32_t* __restrict__ cell_dofs) {
+  const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int ph = phase ? phase[c] : 0;
+  // triangle / segment: the unused dof slots repeat the first, so that the (zero-valued) contributions of the
+  // 16-per-cell contribution list land on pattern entries that exist anyway
+  for (int k = 0; k < 4; ++k) cell_dofs[4 * c + k] = vc2dof[2 * (int64_t)tets[4 * c + (k < cell_nv ? k : 0)] + ph];
+}
+
 void bt_build_dofmap(btfem* h) {
   const int64_t nv = h->nv, nc = h->nc;
+  cudaStream_t st = h->stream;
   // strongly imposed periodicity: a slave vertex carries the dofs of its master (constrained_domain = PeriodicBD,
   // DmriFemLib.py:327-375, 478-483); only masters are numbered
   const bool merged = !h->h_vmaster.empty();
-  auto vm = [&](int64_t v) -> int64_t { return merged ? (int64_t)h->h_vmaster[v] : v; };
-  std::vector<uint8_t> active(2 * nv, 0);
-  for (int64_t c = 0; c < nc; ++c) {
-    int ph = h->two_comp ? h->h_phase[c] : 0;
-    for (int k = 0; k < h->cell_nv; ++k) active[2 * vm(h->h_tets[4 * c + k]) + ph] = 1;
-  }
-  std::vector<int32_t> vc2dof(2 * nv, -1);
-  h->h_dof_vertex.clear();
-  h->h_dof_comp.clear();
-  int32_t n = 0;
-  for (int64_t v = 0; v < nv; ++v)
-    for (int c = 0; c < 2; ++c)
-      if (active[2 * v + c]) {
-        vc2dof[2 * v + c] = n++;
-        h->h_dof_vertex.push_back((int32_t)v);
-        h->h_dof_comp.push_back(c);
-      }
+  DevArray<int32_t> d_vm, active, excl;
+  if (merged) d_vm.upload(h->h_vmaster.data(), h->h_vmaster.size(), st);
+  active.alloc(2 * nv);
+  excl.alloc(2 * nv);
+  active.zero(st);
+  const int32_t* ph = h->two_comp ? h->d_phase.p : nullptr;
+  k_dofmap_mark<<<nblocks(nc), TPB, 0, st>>>(nc, h->cell_nv, h->d_tets.p, ph, merged ? d_vm.p : nullptr, active.p);
+  TempStorage tmp;
+  size_t bytes = 0;
+  BT_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, active.p, excl.p, 2 * nv, st));
+  tmp.reserve(bytes);
+  BT_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, active.p, excl.p, 2 * nv, st));
+  int32_t last_excl = 0, last_act = 0;
+  BT_CUDA(cudaMemcpyAsync(&last_excl, excl.p + (2 * nv - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  BT_CUDA(cudaMemcpyAsync(&last_act, active.p + (2 * nv - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  BT_CUDA(cudaStreamSynchronize(st));
+  const int32_t n = last_excl + last_act;
   h->ndof = n;
-  if (merged)
-    for (int64_t v = 0; v < nv; ++v)
-      if (vm(v) != v)
-        for (int c = 0; c < 2; ++c) vc2dof[2 * v + c] = vc2dof[2 * vm(v) + c];
+  h->d_vc2dof.alloc(2 * nv);
+  h->d_dof_vertex.alloc(n);
+  h->d_dof_comp.alloc(n);
+  k_dofmap_number<<<nblocks(2 * nv), TPB, 0, st>>>(2 * nv, active.p, excl.p, h->d_vc2dof.p, h->d_dof_vertex.p,
+                                                  h->d_dof_comp.p);
+  if (merged) k_dofmap_slaves<<<nblocks(nv), TPB, 0, st>>>(nv, d_vm.p, h->d_vc2dof.p);
+  h->d_cell_dofs.alloc(4 * nc);
+  k_cell_dofs<<<nblocks(nc), TPB, 0, st>>>(nc, h->cell_nv, h->d_tets.p, ph, h->d_vc2dof.p, h->d_cell_dofs.p);
+  BT_CUDA(cudaGetLastError());
+  h->h_dof_vertex.resize(n);
+  h->h_dof_comp.resize(n);
+  h->d_dof_vertex.download(h->h_dof_vertex.data(), st);
+  h->d_dof_comp.download(h->h_dof_comp.data(), st);
   // row partition: dofs are vertex-major, so the owned (and the peer-independent) dofs are prefixes
   h->n_own = n;
   h->n_int = n;
@@ -644,19 +699,6 @@ void bt_build_dofmap(btfem* h) {
                h->h_dof_vertex.begin();
     h->halo_shift = ((h->n_own + 7) & ~(int64_t)7) - h->n_own;   // halo entries start on a 128-byte line
   }
-  std::vector<int32_t> cell_dofs(4 * nc);
-  for (int64_t c = 0; c < nc; ++c) {
-    int ph = h->two_comp ? h->h_phase[c] : 0;
-    // triangle: the 4th dof slot repeats the first, so that the (zero-valued) contributions (i,3), (3,j) of the
-    // 16-per-cell contribution list land on pattern entries that exist anyway
-    for (int k = 0; k < 4; ++k)
-      cell_dofs[4 * c + k] = vc2dof[2 * (int64_t)h->h_tets[4 * c + (k < h->cell_nv ? k : 0)] + ph];
-  }
-  h->d_vc2dof.upload(vc2dof.data(), vc2dof.size(), h->stream);
-  h->d_cell_dofs.upload(cell_dofs.data(), cell_dofs.size(), h->stream);
-  h->d_dof_vertex.upload(h->h_dof_vertex.data(), h->h_dof_vertex.size(), h->stream);
-  h->d_dof_comp.upload(h->h_dof_comp.data(), h->h_dof_comp.size(), h->stream);
-  BT_CUDA(cudaStreamSynchronize(h->stream));
 }
 
 void bt_build_facets(btfem* h) {
@@ -734,6 +776,15 @@ void bt_build_facets(btfem* h) {
 
 void bt_build_pattern(btfem* h) {
   cudaStream_t st = h->stream;
+  const bool timing = getenv("BTFEM_TIMING") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaStreamSynchronize(st);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[btfem]   pattern: %-14s %7.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  };
   const int64_t ncell16 = 16 * h->nc, nif36 = 36 * h->n_iface, nb9 = 9 * h->n_bfacet;
   const int64_t nsrc = ncell16 + nif36 + nb9;
   BT_REQUIRE(nsrc < (int64_t)0xffffffffLL, "mesh too large for 32-bit contribution ids");
@@ -780,6 +831,7 @@ void bt_build_pattern(btfem* h) {
   k_diagpos<<<nblocks(h->ndof), TPB, 0, st>>>(h->ndof, h->d_rowptr.p, h->d_colidx.p, h->d_diagpos.p);
   BT_CUDA(cudaGetLastError());
   BT_CUDA(cudaStreamSynchronize(st));
+  lap("sort + csr");
   // SELL-32 layout: sort rows by descending length inside windows of BT_SELL_SIGMA rows (stable, so the
   // result is deterministic), cut into slices of 32 slots, slice width = longest row of the slice.
   std::vector<int32_t> rp(h->ndof + 1);
@@ -820,6 +872,7 @@ void bt_build_pattern(btfem* h) {
                                                       (int)h->halo_shift);
   h->d_PJs.release();
   h->d_QJs.release();
+  lap("sell");
   // Static warp schedule.  A round-robin of slices over warps leaves a tail (some warps get one slice more, and in
   // a row partition the halo-reading slices cost about twice a plain one); a dynamic queue would fix that but make
   // the order of the dot-product partial sums depend on timing.  So the queue is SIMULATED here, once: slices are
@@ -864,6 +917,7 @@ void bt_build_pattern(btfem* h) {
     h->d_sched_ptr.upload(ptr.data(), ptr.size(), st);
     h->sched_grid = grid;
   }
+  lap("schedule");
   // Warp streams for the TMA kernels (whole-mesh handles): one block per SM, ps_warps warps each; slices are dealt
   // in ascending order to the warp with the least work so far (same simulated queue as above), and every warp's
   // pieces are stored back to back in the order it will consume them.
@@ -959,6 +1013,7 @@ void bt_build_pattern(btfem* h) {
     BT_CUDA(cudaGetLastError());
     BT_CUDA(cudaStreamSynchronize(st));   // host vectors above go out of scope
   }
+  lap("warp streams");
   BT_CUDA(cudaGetLastError());
   BT_CUDA(cudaStreamSynchronize(st));
 }

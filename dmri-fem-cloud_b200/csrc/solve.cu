@@ -1466,6 +1466,359 @@ __global__ void __launch_bounds__(TPB, 2) k_spmv_sell_batch(SpmvArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------ batched solves, member-interleaved
+// HARDI-type sweeps: many (direction, b) solves on ONE mesh.  Members travel in groups of HB = 8 whose Krylov vectors
+// are interleaved member-innermost, x[row][m]: the 8 entries of a row are one 128-byte line, so ONE gather serves 8
+// members, and the operator is read ONCE per group in its direction-independent form ((P|Q), Jx, Jy, Jz: 44 B per
+// nonzero, L2-resident for sweep-sized meshes) instead of 20 B per nonzero per member.  A block works on one SELL
+// slice at a time: 32 rows x 8 members = 256 threads, lane = (row & 3, member); the operator loads of a row are
+// broadcasts within its 8 lanes.  Every member keeps the arithmetic of its one-at-a-time solve on k_spmv_sell
+// (J_g formed with the rounding of k_combine, row sums in ascending column order) and its dot products are reduced in
+// a fixed order that does not depend on the batch, so a member gets the same bits in whatever batch it travels.
+constexpr int HB = 8;
+
+struct HbLane {
+  int m;            // member of this lane inside the group
+  int member;       // global member index
+  bool act;         // the member exists and still works
+  double gx, gy, gz, cc;
+};
+
+// per-member sums over the block -> partials[member][q][block]; the last block of the GROUP finishes all 8 members:
+// warp w adds member w's partials over the blocks in a fixed order and lane 0 calls fin(member, totals).
+template <int NV, typename F>
+__device__ __forceinline__ void hb_reduce(const SpmvArgs& a, int m0, double (&v)[NV], int slot, int tk, F&& fin) {
+  __shared__ double sm[NV][TPB / 32][HB];
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) {
+    double t = v[q];
+    t += __shfl_xor_sync(0xffffffffu, t, 8);
+    t += __shfl_xor_sync(0xffffffffu, t, 16);
+    if (lane < HB) sm[q][warp][lane] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < HB && m0 + (int)threadIdx.x < a.members) {
+    double* part = a.partials + (size_t)(m0 + threadIdx.x) * a.part_stride;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < TPB / 32; ++w) t += sm[q][w][threadIdx.x];
+      part[(slot + q) * BT_MAX_PARTIALS + blockIdx.x] = t;
+    }
+  }
+  unsigned int* ticket = &a.ctrl0[m0].ticket[tk];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int member = m0 + warp;   // 8 warps <-> 8 members
+  if (member < a.members) {
+    const volatile double* part = a.partials + (size_t)member * a.part_stride;
+    double tot[NV];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      double acc = 0.0;
+      for (unsigned int b = lane; b < gridDim.x; b += 32) acc += part[(slot + q) * BT_MAX_PARTIALS + b];
+      tot[q] = warp_sum(acc);
+    }
+    if (lane == 0) fin(member, tot);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *ticket = 0;
+}
+
+// The WHILE condition of the step graph, evaluated by ONE thread in a kernel of its own behind the kernels that
+// change ctrl->done (no race between the finishing blocks of different groups; ~2 us per pass).
+__global__ void k_hb_cond(SpmvArgs a) {
+  if (!a.use_cond) return;
+  unsigned int any = 0;
+  for (int b = 0; b < a.members; ++b) any |= (a.ctrl0[b].done == 0);
+  cudaGraphSetConditional(a.cond, any);
+}
+
+__global__ void k_hb_set_ic(int n, size_t group_stride, const double* __restrict__ ic, double2* __restrict__ u) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < (size_t)n * HB) u[blockIdx.y * group_stride + i] = make_double2(ic[i / HB], 0.0);
+}
+
+// vectors of group g: u, r, rp, p, v, s, t at k * npad * HB behind a.u + g * 7 * npad * HB (a.vec_stride = 7 * npad)
+struct HbVecs {
+  double2 *u, *r, *rp, *p, *v, *s, *t;
+};
+__device__ __forceinline__ HbVecs hb_vecs(const SpmvArgs& a, int g) {
+  const size_t npadHB = a.vec_stride / 7 * HB;
+  double2* base = a.u + (size_t)g * 7 * npadHB;
+  HbVecs w;
+  w.u = base; w.r = base + npadHB; w.rp = base + 2 * npadHB; w.p = base + 3 * npadHB; w.v = base + 4 * npadHB;
+  w.s = base + 5 * npadHB; w.t = base + 6 * npadHB;
+  return w;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k_hb_spmv(SpmvArgs a) {
+  const int g = blockIdx.y, m0 = g * HB;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  HbLane L;
+  L.m = lane & (HB - 1);
+  L.member = m0 + L.m;
+  L.act = false;
+  L.gx = L.gy = L.gz = L.cc = 0.0;
+  if (L.member < a.members) {
+    const KrylovCtrl* ctrl = a.ctrl0 + L.member;
+    if (MODE == MODE_RHS) {
+      L.act = ctrl->failed == 0;
+      L.cc = ctrl->theta_cb_scale * a.cb[(size_t)L.member * a.step_stride + ctrl->step_next];
+    } else {
+      L.act = ctrl->done == 0;
+      L.cc = ctrl->theta_cA_scale * a.cA[(size_t)L.member * a.step_stride + ctrl->step];
+    }
+    L.gx = a.gdirs[3 * L.member]; L.gy = a.gdirs[3 * L.member + 1]; L.gz = a.gdirs[3 * L.member + 2];
+  }
+  if (__syncthreads_or(L.act) == 0) return;   // the whole group has stopped
+  const HbVecs w = hb_vecs(a, g);
+  const double2* __restrict__ x = (MODE == MODE_RHS) ? w.u : (MODE == MODE_V ? w.p : w.s);
+  const int rslot = warp * 4 + (lane >> 3);   // row slot of this lane inside a slice
+  double acc[2] = {0.0, 0.0};
+  for (int slice = blockIdx.x; slice < a.nslice; slice += gridDim.x) {
+    const int base = __ldg(a.slice_ptr + slice);
+    const int width = (__ldg(a.slice_ptr + slice + 1) - base) >> 5;
+    const int row = __ldg(a.sell_row + slice * 32 + rslot);   // -1: padding slot past the last row
+    const double di = row >= 0 ? __ldg(a.dinv + row) : 0.0;
+    const int32_t* cp = a.sell_col + base + rslot;
+    const double2* pq = a.PQs + base + rslot;
+    const double2* jxy = a.Jxys + base + rslot;
+    const double* jz = a.Jzs + base + rslot;
+    double yr = 0.0, yi = 0.0;
+    constexpr int U = 4;
+    for (int j0 = 0; j0 < width; j0 += U) {
+      int col[U];
+      double pa[U], pb[U];
+      double2 xv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + u;
+        col[u] = j < width ? __ldg(cp + j * 32) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (col[u] >= 0) xv[u] = ldv_gather_f64x2(x + (size_t)col[u] * HB + L.m);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + u;
+        if (col[u] >= 0) {
+          const double2 pqv = __ldg(pq + j * 32), jv = __ldg(jxy + j * 32);
+          const double jzv = __ldg(jz + j * 32);
+          pa[u] = MODE == MODE_RHS ? pqv.y : pqv.x;
+          pb[u] = L.cc * comb_jg(L.gx, L.gy, L.gz, jv.x, jv.y, jzv, di);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (col[u] >= 0) {
+          yr = fma(pa[u], xv[u].x, yr);
+          yr = fma(-pb[u], xv[u].y, yr);
+          yi = fma(pa[u], xv[u].y, yi);
+          yi = fma(pb[u], xv[u].x, yi);
+        }
+    }
+    if (row >= 0 && L.act) {
+      const size_t e = (size_t)row * HB + L.m;
+      const double2 y = make_double2(yr, yi);
+      if (MODE == MODE_RHS) {
+        w.r[e] = y; w.rp[e] = y;
+        w.p[e] = make_double2(0.0, 0.0);
+        w.v[e] = make_double2(0.0, 0.0);
+        acc[0] += y.x * y.x + y.y * y.y;
+      } else if (MODE == MODE_V) {
+        w.v[e] = y;
+        const double2 q = w.rp[e];
+        acc[0] += y.x * q.x + y.y * q.y;
+      } else {
+        w.t[e] = y;
+        const double2 sv = w.s[e];
+        acc[0] += sv.x * y.x + sv.y * y.y;
+        acc[1] += y.x * y.x + y.y * y.y;
+      }
+    }
+  }
+  if (MODE == MODE_RHS) {
+    double v1[1] = {acc[0]};
+    hb_reduce<1>(a, m0, v1, 0, TK_RHS, [&](int member, const double (&tot)[1]) {
+      KrylovCtrl* ctrl = a.ctrl0 + member;
+      if (ctrl->failed) return;
+      const double bn = sqrt(tot[0]);
+      ctrl->bnorm = bn;
+      ctrl->ttol = fmax(ctrl->rtol * bn, ctrl->atol);
+      ctrl->rho_old = 1.0; ctrl->alpha = 1.0; ctrl->omega = 1.0;
+      ctrl->iters = 0;
+      ctrl->step = ctrl->step_next;
+      ctrl->step_next = ctrl->step_next + 1;
+      ctrl->done = 0; ctrl->reason = 0;
+      ctrl->rho = tot[0];
+      ctrl->rnorm = bn;
+      if (!(bn == bn) || isinf(bn)) { ctrl->done = 1; ctrl->reason = BTFEM_ENAN; }
+      else if (bn <= ctrl->ttol) { ctrl->done = 1; ctrl->reason = bn < ctrl->atol ? 3 : 2; }
+    });
+  } else if (MODE == MODE_V) {
+    double v1[1] = {acc[0]};
+    hb_reduce<1>(a, m0, v1, 2, TK_V, [&](int member, const double (&tot)[1]) {
+      KrylovCtrl* ctrl = a.ctrl0 + member;
+      if (ctrl->done) return;
+      if (tot[0] == 0.0) { ctrl->done = 1; ctrl->reason = BTFEM_EBREAKDOWN; ctrl->alpha = 0.0; }
+      else ctrl->alpha = ctrl->rho / tot[0];
+    });
+  } else {
+    double v2[2] = {acc[0], acc[1]};
+    hb_reduce<2>(a, m0, v2, 3, TK_T, [&](int member, const double (&tot)[2]) {
+      KrylovCtrl* ctrl = a.ctrl0 + member;
+      if (ctrl->done) return;
+      ctrl->omega = (tot[1] == 0.0) ? 0.0 : tot[0] / tot[1];
+    });
+  }
+}
+
+// per-thread member constants of the interleaved vector kernels (the grid stride is a multiple of HB)
+__device__ __forceinline__ int hb_member(const SpmvArgs& a) { return blockIdx.y * HB + (threadIdx.x & (HB - 1)); }
+
+// p <- r - omega*beta*v + beta*p
+__global__ void __launch_bounds__(TPB) k_hb_update_p(SpmvArgs a) {
+  const int member = hb_member(a);
+  bool act = false;
+  double beta = 0.0, ob = 0.0;
+  if (member < a.members) {
+    const KrylovCtrl* ctrl = a.ctrl0 + member;
+    act = ctrl->done == 0;
+    if (act) {
+      beta = (ctrl->rho / ctrl->rho_old) * (ctrl->alpha / ctrl->omega);
+      ob = ctrl->omega * beta;
+    }
+  }
+  if (__syncthreads_or(act) == 0) return;
+  const HbVecs w = hb_vecs(a, blockIdx.y);
+  const size_t ne = (size_t)a.n * HB;
+  if (act)
+    for (size_t i = blockIdx.x * (size_t)TPB + threadIdx.x; i < ne; i += (size_t)gridDim.x * TPB) {
+      const double2 rr = w.r[i], vv = w.v[i];
+      double2 pp = w.p[i];
+      pp.x = rr.x - ob * vv.x + beta * pp.x;
+      pp.y = rr.y - ob * vv.y + beta * pp.y;
+      w.p[i] = pp;
+    }
+}
+
+// s <- r - alpha*v
+__global__ void __launch_bounds__(TPB) k_hb_update_s(SpmvArgs a) {
+  const int member = hb_member(a);
+  bool act = false;
+  double alpha = 0.0;
+  if (member < a.members) {
+    const KrylovCtrl* ctrl = a.ctrl0 + member;
+    act = ctrl->done == 0;
+    alpha = ctrl->alpha;
+  }
+  if (__syncthreads_or(act) == 0) return;
+  const HbVecs w = hb_vecs(a, blockIdx.y);
+  const size_t ne = (size_t)a.n * HB;
+  if (act)
+    for (size_t i = blockIdx.x * (size_t)TPB + threadIdx.x; i < ne; i += (size_t)gridDim.x * TPB) {
+      const double2 rr = w.r[i], vv = w.v[i];
+      w.s[i] = make_double2(rr.x - alpha * vv.x, rr.y - alpha * vv.y);
+    }
+}
+
+// x <- x + alpha*p + omega*s ; r <- s - omega*t ; rho' = (r,rp) ; ||r|| ; convergence test   (per member)
+__global__ void __launch_bounds__(TPB) k_hb_update_xr(SpmvArgs a) {
+  const int member = hb_member(a);
+  bool act = false, fresh = false;
+  double alpha = 0.0, omega = 0.0;
+  if (member < a.members) {
+    const KrylovCtrl* ctrl = a.ctrl0 + member;
+    act = ctrl->done == 0;
+    alpha = ctrl->alpha;
+    omega = ctrl->omega;
+    fresh = ctrl->iters == 0;   // zero initial guess: x starts from 0
+  }
+  if (__syncthreads_or(act) == 0) return;
+  const HbVecs w = hb_vecs(a, blockIdx.y);
+  const size_t ne = (size_t)a.n * HB;
+  double acc[2] = {0.0, 0.0};
+  if (act)
+    for (size_t i = blockIdx.x * (size_t)TPB + threadIdx.x; i < ne; i += (size_t)gridDim.x * TPB) {
+      const double2 pp = w.p[i], ss = w.s[i], tt = w.t[i], q = w.rp[i];
+      double2 xx = fresh ? make_double2(0.0, 0.0) : w.u[i];
+      xx.x += alpha * pp.x + omega * ss.x;
+      xx.y += alpha * pp.y + omega * ss.y;
+      w.u[i] = xx;
+      const double2 rr = make_double2(ss.x - omega * tt.x, ss.y - omega * tt.y);
+      w.r[i] = rr;
+      acc[0] += rr.x * q.x + rr.y * q.y;
+      acc[1] += rr.x * rr.x + rr.y * rr.y;
+    }
+  hb_reduce<2>(a, blockIdx.y * HB, acc, 5, TK_XR, [&](int mb, const double (&tot)[2]) {
+    KrylovCtrl* ctrl = a.ctrl0 + mb;
+    if (ctrl->done) return;
+    const double rho_used = ctrl->rho, om = ctrl->omega;
+    ctrl->rho_old = rho_used;
+    ctrl->rho = tot[0];
+    const double dp = sqrt(tot[1]);
+    ctrl->rnorm = dp;
+    const int it = ctrl->iters + 1;
+    ctrl->iters = it;
+    if (!(dp == dp) || isinf(dp)) { ctrl->done = 1; ctrl->reason = BTFEM_ENAN; }
+    else if (dp <= ctrl->ttol) { ctrl->done = 1; ctrl->reason = dp < ctrl->atol ? 3 : 2; }
+    else if (dp >= ctrl->dtol * ctrl->bnorm) { ctrl->done = 1; ctrl->reason = BTFEM_EDTOL; }
+    else if (rho_used == 0.0 || om == 0.0) { ctrl->done = 1; ctrl->reason = BTFEM_EBREAKDOWN; }
+    else if (it >= ctrl->maxit) { ctrl->done = 1; ctrl->reason = BTFEM_ENOTCONV; }
+  });
+}
+
+// end of a time step: statistics; "converged before the first iteration with a zero guess returns x = 0"
+__global__ void __launch_bounds__(TPB) k_hb_step_end(SpmvArgs a) {
+  const int member = hb_member(a);
+  bool zero = false;
+  if (member < a.members) {
+    KrylovCtrl* ctrl = a.ctrl0 + member;
+    if (!ctrl->failed) {
+      const int it = ctrl->iters;
+      zero = it == 0 && ctrl->reason > 0;
+      if (blockIdx.x == 0 && threadIdx.x < HB) {
+        ctrl->total_iters += it;
+        if (it > ctrl->max_iters) ctrl->max_iters = it;
+      }
+    }
+  }
+  if (zero) {
+    const HbVecs w = hb_vecs(a, blockIdx.y);
+    const size_t ne = (size_t)a.n * HB;
+    for (size_t i = blockIdx.x * (size_t)TPB + threadIdx.x; i < ne; i += (size_t)gridDim.x * TPB)
+      w.u[i] = make_double2(0.0, 0.0);
+  }
+}
+
+// signal = sum_i lumped_i * Re u_i, split by compartment, per member
+__global__ void __launch_bounds__(TPB) k_hb_signal(SpmvArgs a, const double* __restrict__ lumped,
+                                                   const int32_t* __restrict__ comp) {
+  const HbVecs w = hb_vecs(a, blockIdx.y);
+  const size_t ne = (size_t)a.n * HB;
+  double acc[2] = {0.0, 0.0};
+  for (size_t i = blockIdx.x * (size_t)TPB + threadIdx.x; i < ne; i += (size_t)gridDim.x * TPB) {
+    const size_t row = i / HB;
+    const double v = lumped[row] * w.u[i].x;
+    if (comp[row] == 0) acc[0] += v; else acc[1] += v;
+  }
+  hb_reduce<2>(a, blockIdx.y * HB, acc, 6, TK_SIG, [&](int mb, const double (&tot)[2]) {
+    a.sig_out[2 * mb] = tot[0];
+    a.sig_out[2 * mb + 1] = tot[1];
+  });
+}
+
 // ------------------------------------------------------------------------------------ vector kernels
 
 // p <- r - omega*beta*v + beta*p        (VecAXPBYPCZ in KSPSolve_BCGS)
@@ -1802,9 +2155,11 @@ inline int batch_group() {
 constexpr int SELL_UNR_DEFAULT = 4;
 constexpr int SELL_MINB_DEFAULT = 3;
 
-// 8-warp stream kernels: ring depth 5 / gathers of two pieces in flight (BTFEM_PS_DEEP=0: depth 4 / one piece)
+// 8-warp stream kernels: ring depth 4 and the gathers of one piece in flight while another is multiplied.
+// BTFEM_PS_DEEP=1: depth 5 / two pieces -- measured SLOWER on B200 (profiles/r2i_deep.txt: 210 KB of rings leave 18 KB
+// of L1 for the x gathers, and the passes are bound by the memory system, not by gather latency).
 inline bool ps_deep() {
-  static const bool v = !(getenv("BTFEM_PS_DEEP") && getenv("BTFEM_PS_DEEP")[0] == '0');
+  static const bool v = getenv("BTFEM_PS_DEEP") && getenv("BTFEM_PS_DEEP")[0] == '1';
   return v;
 }
 
@@ -2244,15 +2599,22 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   BT_CUDA(cudaEventCreate(&e1));
   BT_CUDA(cudaEventCreate(&e2));
   BT_CUDA(cudaEventRecord(e0, st));
-  // Batch layouts.  Default: one pre-combined copy of the operator per member, member = blockIdx.y of the
-  // single-solve kernel (members x more warps in flight).  BTFEM_BATCH_SHARED=1: one direction-independent
-  // operator for all members (k_spmv_sell_batch) -- 44 B per nonzero per GROUP instead of 20 B per member, same
-  // bits; measured on B200 on the 46 k-vertex HARDI mesh it is SLOWER (15.4 / 19.0 signals/s with groups of
-  // 8 / 4 against 24.0): that regime is bound by gather latency and by L2 traffic of the gathers and vectors,
-  // which the shared matrix does not reduce, and the group kernel has 8x fewer warps to hide latency with
-  // (profiles/r1e_batch_layouts.txt).  Kept for meshes whose per-member copies would not fit in memory.
+  // Batch layouts (BTFEM_BATCH_LAYOUT):
+  //   "interleaved" (default when the batch qualifies): groups of 8 members, Krylov vectors member-innermost, ONE
+  //       direction-independent operator per batch (k_hb_*): one 128-byte gather serves 8 members and the operator is
+  //       read once per group (44 B per nonzero per 8 members instead of 20 B per member);
+  //   "member": one pre-combined copy of the operator per member, member = blockIdx.y of the single-solve kernels
+  //       (round 1's default; also what periodic / non-zero-guess batches fall back to);
+  //   "shared": round 1's shared-operator kernel with per-member vector slabs (k_spmv_sell_batch; slower than
+  //       "member" on the 46 k-vertex HARDI mesh, profiles/r1e_batch_layouts.txt).
+  const char* layout_env = getenv("BTFEM_BATCH_LAYOUT");
   const char* shared_env = getenv("BTFEM_BATCH_SHARED");
-  const bool shared_ops = members > 1 && h->lanes == 0 && h->n_slice > 0 && shared_env && shared_env[0] == '1';
+  const bool batch_ok = members > 1 && h->lanes == 0 && h->n_slice > 0;
+  const bool hb = batch_ok && !periodic && !gmres && !part && !strong && !sa->nonzero_guess &&
+                  !(layout_env && (layout_env[0] == 'm' || layout_env[0] == 's')) && !(shared_env && shared_env[0] == '1');
+  const bool shared_ops = hb || (batch_ok && ((shared_env && shared_env[0] == '1') || (layout_env && layout_env[0] == 's')));
+  const int groups = (members + HB - 1) / HB;
+  const int members_alloc = hb ? groups * HB : members;
   if (shared_ops) {
     const int nd = (int)h->ndof;
     h->d_dinv.alloc(nd);
@@ -2284,7 +2646,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     bt_strong_build(h, sa->gdir);
     h->comb_dt = -1;   // PJs/QJs will not hold what bt_combine caches
   }
-  ensure_vectors(h, members);
+  ensure_vectors(h, members_alloc);
   h->step_stride = sa->nsteps;
   {
     std::vector<double> cA((size_t)members * sa->nsteps), cb((size_t)members * sa->nsteps);
@@ -2303,7 +2665,11 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     h->d_ubc.zero(st);
     h->d_rhs_add.zero(st);
   }
-  k_set_ic_batch<<<dim3((n + TPB - 1) / TPB, members), TPB, 0, st>>>(n, 7 * h->vec_npad, h->d_ic_dof.p, h->d_u.p);
+  if (hb)
+    k_hb_set_ic<<<dim3((unsigned)(((size_t)n * HB + TPB - 1) / TPB), groups), TPB, 0, st>>>(
+        n, (size_t)7 * h->vec_npad * HB, h->d_ic_dof.p, h->d_u.p);
+  else
+    k_set_ic_batch<<<dim3((n + TPB - 1) / TPB, members), TPB, 0, st>>>(n, 7 * h->vec_npad, h->d_ic_dof.p, h->d_u.p);
   KrylovCtrl c0;
   memset(&c0, 0, sizeof(c0));
   c0.rtol = sa->rtol; c0.atol = sa->atol; c0.dtol = 1e4;
@@ -2312,8 +2678,8 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   c0.maxit = (int)std::min<int64_t>(sa->maxit, 0x7fffffff);
   c0.nonzero_guess = sa->nonzero_guess ? 1 : 0;
   c0.done = 1;
-  for (int b = 0; b < members; ++b) h->h_ctrl[b] = c0;
-  BT_CUDA(cudaMemcpyAsync(h->d_ctrl.p, h->h_ctrl, sizeof(KrylovCtrl) * members, cudaMemcpyHostToDevice, st));
+  for (int b = 0; b < members_alloc; ++b) h->h_ctrl[b] = c0;
+  BT_CUDA(cudaMemcpyAsync(h->d_ctrl.p, h->h_ctrl, sizeof(KrylovCtrl) * members_alloc, cudaMemcpyHostToDevice, st));
   BT_CUDA(cudaStreamSynchronize(st));   // h_ctrl is reused as the read-back buffer below
 
   SpmvArgs a = base_args(h);
@@ -2325,13 +2691,18 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   // keep the total block count near a few waves: the x-extent shrinks as the batch grows
   const int vgx = std::max(1, std::min(vec_grid(n), std::max(BT_NUM_SMS, BT_NUM_SMS * 8 / members)));
   const dim3 vg(vgx, members);
+  // member-interleaved batch: (blocks over the slices | the n x 8 vector entries, groups)
+  const dim3 hb_sg(std::max(1, std::min((int)h->n_slice, std::max(BT_NUM_SMS, BT_NUM_SMS * 8 / groups))), groups);
+  const dim3 hb_vg(std::max(1, std::min((int)(((size_t)n * HB + TPB - 1) / TPB), std::max(BT_NUM_SMS, BT_NUM_SMS * 8 / groups))),
+                   groups);
+  if (hb) a.members = members;
 
   // The BiCGStab iteration (of every member) as a CUDA graph.  Default ("device" loop): one graph per TIME STEP
   // -- u push / periodic terms / RHS, then a WHILE node whose body is the iteration and whose condition the
   // kernels themselves set from ctrl->done -- so the host queues nsteps graph launches and never waits inside the
   // solve.  BTFEM_LOOP=host (and GMRES): the iteration graph is re-launched by the host, which polls ctrl->done.
   const char* loop_env = getenv("BTFEM_LOOP");
-  const bool dev_loop = !gmres && !(loop_env && loop_env[0] == 'h');
+  const bool dev_loop = !gmres && (hb || !(loop_env && loop_env[0] == 'h'));
   const int push_grid = part ? std::max(1, std::min(32, ((int)h->d_send_src.n + TPB - 1) / TPB)) : 0;
   const int kernels_per_iter = 5;
   int unroll = 6;
@@ -2353,11 +2724,24 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
           (int)h->n_pb_rows, h->d_pb_rows.p, h->d_rowptr.p, h->d_colidx.p, h->d_Bhat.p, 1.0 - sa->theta,
           h->d_ubc.p, h->d_rhs_add.p);
     }
+    if (hb) {
+      k_hb_spmv<MODE_RHS><<<hb_sg, TPB, 0, st>>>(a);
+      k_hb_cond<<<1, 1, 0, st>>>(a);
+      return;
+    }
     launch_spmv<MODE_RHS>(lanes, a, st, members);
     if (sa->nonzero_guess) launch_spmv<MODE_RESID>(lanes, a, st, members);
   };
   const int prologue_kernels = (strong ? 1 : 0) + (part ? 1 : 0) + (periodic ? 2 : 0) + 1 + (sa->nonzero_guess ? 1 : 0);
   auto capture_iteration = [&]() {
+    if (hb) {
+      k_hb_update_p<<<hb_vg, TPB, 0, st>>>(a);
+      k_hb_spmv<MODE_V><<<hb_sg, TPB, 0, st>>>(a);
+      k_hb_update_s<<<hb_vg, TPB, 0, st>>>(a);
+      k_hb_spmv<MODE_T><<<hb_sg, TPB, 0, st>>>(a);
+      k_hb_update_xr<<<hb_vg, TPB, 0, st>>>(a);
+      return;
+    }
     k_update_p<<<vg, TPB, 0, st>>>(a);     // row-partitioned: also stores the rows peers need into their halos
     launch_spmv<MODE_V>(lanes, a, st, members);
     k_update_s<<<vg, TPB, 0, st>>>(a);     // ditto
@@ -2453,8 +2837,11 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     // remaining kernels of the pass return at once (~2 us each).
     BT_CUDA(cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
     for (int u = 0; u < unroll; ++u) capture_iteration();
+    if (hb) k_hb_cond<<<1, 1, 0, st>>>(a);   // the WHILE condition, once per pass
     BT_CUDA(cudaStreamEndCapture(st, &same));
     BT_CUDA(cudaStreamBeginCaptureToGraph(st, graph, &wnode, nullptr, 1, cudaStreamCaptureModeThreadLocal));
+    if (hb) k_hb_step_end<<<hb_vg, TPB, 0, st>>>(a);
+    else
     k_step_end<<<vg, TPB, 0, st>>>(a);
     k_step_fail<<<1, 1, 0, st>>>(h->d_ctrl.p, members);
     BT_CUDA(cudaStreamEndCapture(st, &same));
@@ -2631,6 +3018,8 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     throw BtError{fail, "row-partitioned solve: a peer rank did not answer within the time limit"};
   }
   a.sig_out = d_sig.p;
+  if (hb) k_hb_signal<<<hb_vg, TPB, 0, st>>>(a, h->d_lumped.p, h->d_dof_comp.p);
+  else
   k_signal<<<vg, TPB, 0, st>>>(a, h->d_lumped.p, h->d_dof_comp.p);
   BT_CUDA(cudaGetLastError());
   std::vector<double> sig(2 * (size_t)members);
@@ -2641,7 +3030,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
   if (gexec) cudaGraphExecDestroy(gexec);
   if (graph) cudaGraphDestroy(graph);
-  h->have_solution = true;
+  h->have_solution = !hb;   // btfem_get_solution reads member 0's slab, which the interleaved layout does not have
   for (int b = 0; b < members; ++b) {
     btfem_solve_out* out = &outv[b];
     out->signal_comp[0] = sig[2 * b];

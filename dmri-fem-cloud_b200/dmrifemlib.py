@@ -352,7 +352,7 @@ class MRI_simulation():
         1 where |x|^2 < 1e6."""
         if Dirac_Delta is None:
             xyz = mydomain.mymesh.coordinates()
-            Dirac_Delta = ((xyz * xyz).sum(axis=1) < 1e6).astype(float)
+            Dirac_Delta = (np.einsum("ij,ij->i", xyz, xyz) < 1e6).astype(float)
         return np.asarray(Dirac_Delta, dtype=float)
 
     def time_grid(self, mri_para):
@@ -373,10 +373,6 @@ class MRI_simulation():
         q = mri_para.qvalue
         par = linsolver.parameters
         start_time = time.time()
-        if self.verbose:
-            for n in range(0, len(ts), self.nskip):
-                print('t: %6.2f ' % ts[n], 'T: %6.2f' % mri_para.T, 'dt: %.1f' % self.k, 'qvalue: %e' % q,
-                      'Completed %3.2f%%' % (float(ts[n]) / float(mri_para.T + self.k) * 100.0))
         g = mri_para.gdir.array() if hasattr(mri_para.gdir, "array") else np.asarray(mri_para.gdir, dtype=float)
         if mydomain.is_strongly_periodic():
             # transformed equation (FuncF_sBC): the forms read the INTEGRATED profile, ift at t for the matrix and
@@ -394,6 +390,12 @@ class MRI_simulation():
             else:
                 raise RuntimeError("*** Error: Unable to solve linear system using PETSc Krylov solver. "
                                    "Reason: %s" % e)
+        if self.verbose and self.stats is not None:
+            # the reference prints one line every nskip steps while it steps (DmriFemLib.py:911-912); here the whole time
+            # loop is one device-resident kernel, so the same lines come out when it has returned
+            for n in range(0, len(ts), self.nskip):
+                print('t: %6.2f ' % ts[n], 'T: %6.2f' % mri_para.T, 'dt: %.1f' % self.k, 'qvalue: %e' % q,
+                      'Completed %3.2f%%' % (float(ts[n]) / float(mri_para.T + self.k) * 100.0))
         self.t = float(ts[-1] + self.k) if len(ts) else 0.0
         self.fem = fem
         self.elapsed_time = time.time() - start_time
