@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libbtfem.so")
 MAT_IDS = {"M": 0, "S": 1, "R": 2, "Jx": 3, "Jy": 4, "Jz": 5, "I": 6, "B": 7}
 DIST_BLOB_BYTES = 192   # BTFEM_DIST_BLOB_BYTES
 KSP_IDS = {"bicgstab": 0, "gmres": 1}
-PC_IDS = {"jacobi": 0, "none": 1}
+PC_IDS = {"jacobi": 0, "none": 1, "ilu": 2}
 
 _c_double_p = C.POINTER(C.c_double)
 _c_int32_p = C.POINTER(C.c_int32)
@@ -84,6 +84,7 @@ def load_library(path=None):
                                        C.c_int32, _c_double_p]),
         "btfem_set_lanes": (C.c_int, [H, C.c_int32]),
         "btfem_get_spmv_kernel": (C.c_int, [H, _c_int32_p]),
+        "btfem_get_ilu_factors": (C.c_int, [H, _c_double_p]),
         "btfem_solve": (C.c_int, [H, C.POINTER(SolveArgs), C.POINTER(SolveOut), _c_int32_p]),
         "btfem_solve_batch": (C.c_int, [H, C.c_int32, C.POINTER(SolveArgs), C.POINTER(SolveOut)]),
         "btfem_get_solution": (C.c_int, [H, _c_double_p]),
@@ -268,6 +269,12 @@ class BTFem:
     @property
     def stream_kernel(self):
         return self.spmv_kernel == 2
+
+    def ilu_factors(self):
+        """Complex ILU(0) factors of the last pc="ilu" solve, CSR order (btfem_get_ilu_factors)."""
+        out = np.zeros(2 * self.nnz)
+        self._ck(self.lib.btfem_get_ilu_factors(self.h, _dp(out)))
+        return out[0::2] + 1j * out[1::2]
 
     # ---- assembly + parity hooks
     def assemble(self):

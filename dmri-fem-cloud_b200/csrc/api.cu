@@ -38,6 +38,7 @@ void invalidate(btfem* h) {
   h->assembled = false;
   h->n_pb = 0;
   h->comb_dt = -1;
+  h->ilu_valid = false;
   h->have_solution = false;
   bt_dist_close(h);   // the peers' halo maps describe the old numbering
 }
@@ -405,6 +406,13 @@ int btfem_get_spmv_kernel(btfem_t* h, int32_t* kind) {
     BT_REQUIRE(kind, "null argument");
     BT_REQUIRE(h->assembled, "call btfem_assemble first");
     *kind = h->lanes != 0 ? 0 : (bt_stream_kernel_usable(h) ? 2 : 1);
+  });
+}
+
+int btfem_get_ilu_factors(btfem_t* h, double* out) {
+  return guarded(h, [&] {
+    BT_REQUIRE(out, "null argument");
+    bt_ilu_get(h, out);
   });
 }
 

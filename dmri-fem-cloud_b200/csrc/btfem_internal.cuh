@@ -327,12 +327,19 @@ struct btfem {
   } d_u, d_r, d_rp, d_p, d_v, d_s, d_t;
   DevArray<double2> d_gm_V;        // GMRES basis, (restart+1) vectors
   DevArray<double> d_gm_h;
+  DevArray<double> d_gm_state;     // sizeof(GmState) (solve.cu): device-resident Hessenberg / Givens / residual state
   double* h_gm = nullptr;          // pinned
   bool l2_window_set = false;
   cudaAccessPolicyWindow l2_window{};
   DevArray<double> d_cA, d_cb, d_Fb;
   DevArray<double> d_partials;     // [8][BT_MAX_PARTIALS]
   DevArray<KrylovCtrl> d_ctrl;
+  // ILU(0) preconditioner (ilu.cu): complex factors on the CSR pattern, scratch, ready flags with an epoch
+  DevArray<double2> d_ilu, d_ilu_y, d_ilu_tmp;
+  DevArray<unsigned int> d_ilu_flag;
+  unsigned int ilu_epoch = 0;
+  double ilu_c = 0.0;
+  bool ilu_valid = false;
   DevArray<unsigned int> d_gridbar;   // persistent BiCGStab kernel: [0] arrival counter, [32] its value at kernel start
   KrylovCtrl* h_ctrl = nullptr;    // pinned, one per batch member
   int h_ctrl_n = 0;
@@ -361,6 +368,10 @@ void bt_build_pattern(btfem* h);
 void bt_assemble_values(btfem* h);
 void bt_build_periodic(btfem* h);
 
+// ilu.cu
+void bt_ilu_factor(btfem* h, double c, cudaStream_t st);
+void bt_ilu_apply(btfem* h, const double2* in, double2* out, cudaStream_t st);
+void bt_ilu_get(btfem* h, double* out);
 // solve.cu
 bool bt_stream_kernel_usable(const btfem* h);   // warp-stream layout built for this device and not switched off
 void bt_combine(btfem* h, double dt, double theta, const double g[3], int pc, int member = 0, int members = 1);

@@ -339,6 +339,7 @@ struct SpmvArgs {
   // warp-stream kernels (k_spmv_stream, persistent BiCGStab): see btfem_internal.cuh / setup.cu
   int ps_blocks;             // 0: layout not usable for this solve
   int ps_warps;              // warps per block of the layout
+  int ps_l2ahead;            // persistent kernel: pieces per warp prefetched into L2 for the next pass when a pass ends
   const int32_t* ps_ptr;     // [ps_blocks * BT_PS_WARPS + 1]
   const int4* ps_piece;      // {stream column, columns, slice, last}
   const unsigned char* PJt;
@@ -874,6 +875,14 @@ struct WarpRing {
         "l"(T + (size_t)d.x * 128), "r"(bytes), "r"(bar), "l"(l2_evict_first)
         : "memory");
   }
+  // lane 0: pull list entries [i0, i1) of stream T into L2 (no shared-memory stage involved)
+  __device__ __forceinline__ void prefetch_l2(const unsigned char* T, int i0, int i1) const {
+    for (int i = i0; i < i1 && i < np; ++i) {
+      const int4 d = __ldg(pieces + i);
+      const uint32_t bytes = (uint32_t)(d.y * BT_PS_COLU + d.w) * 128u;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(T + (size_t)d.x * 128), "r"(bytes) : "memory");
+    }
+  }
   __device__ __forceinline__ void wait(unsigned int c) const { mbar_wait(bar_s + 8 * (c % D), (c / D) & 1u); }
   __device__ __forceinline__ const unsigned char* stage(unsigned int c) const { return buf + (c % D) * PS_STAGE; }
 };
@@ -983,6 +992,9 @@ __device__ __forceinline__ unsigned int stream_pass(const SpmvArgs& a, int mode,
       }
     }
   }
+  // This warp is done and will sit in a barrier until the slowest one is; the memory system would idle with it.
+  // Its next pieces of the following pass (behind the D already on their way into the ring) go to L2 meanwhile.
+  if (Tnext && lane == 0 && a.ps_l2ahead > 0) r.prefetch_l2(Tnext, D, D + a.ps_l2ahead);
   return c0 + np;
 }
 
@@ -1562,7 +1574,7 @@ __device__ __forceinline__ HbVecs hb_vecs(const SpmvArgs& a, int g) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(TPB) k_hb_spmv(SpmvArgs a) {
+__global__ void __launch_bounds__(TPB, 4) k_hb_spmv(SpmvArgs a) {
   const int g = blockIdx.y, m0 = g * HB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   HbLane L;
@@ -1586,7 +1598,11 @@ __global__ void __launch_bounds__(TPB) k_hb_spmv(SpmvArgs a) {
   const double2* __restrict__ x = (MODE == MODE_RHS) ? w.u : (MODE == MODE_V ? w.p : w.s);
   const int rslot = warp * 4 + (lane >> 3);   // row slot of this lane inside a slice
   double acc[2] = {0.0, 0.0};
-  for (int slice = blockIdx.x; slice < a.nslice; slice += gridDim.x) {
+  // a block takes a CONTIGUOUS range of slices: neighbouring rows gather the same x lines (128 bytes per row and
+  // group), which then come from this SM's L1 instead of L2
+  const int per = (a.nslice + gridDim.x - 1) / gridDim.x;
+  const int s_end = min(a.nslice, ((int)blockIdx.x + 1) * per);
+  for (int slice = blockIdx.x * per; slice < s_end; ++slice) {
     const int base = __ldg(a.slice_ptr + slice);
     const int width = (__ldg(a.slice_ptr + slice + 1) - base) >> 5;
     const int row = __ldg(a.sell_row + slice * 32 + rslot);   // -1: padding slot past the last row
@@ -2128,6 +2144,140 @@ __global__ void __launch_bounds__(TPB) k_gm_resid(int n, const double2* __restri
   if (reduce_finalize<1>(acc, partials, ticket)) out[0] = acc[0];
 }
 
+// ---- device-resident GMRES(m): the Hessenberg column, the Givens rotations, the residual estimate and the
+// convergence test live in a small device block (GmState) that single-thread kernels update right behind the
+// orthogonalisation kernels, so the host does not read anything back per iteration -- it looks at `stop` every
+// GM_CHECK iterations and once per restart cycle.  Arithmetic = the previous host loop = oracle gmres_petsc.
+constexpr int GM_CHECK = 5;
+struct GmState {
+  double H[(GM_MAXK + 1) * GM_MAXK];   // column j at H[j * (m + 1) ...], rotated in place
+  double cs[GM_MAXK], sn[GM_MAXK], rs[GM_MAXK + 1], y[GM_MAXK];
+  double res, ttol, bnorm, atol, inv;
+  int its, maxit, reason, stop, kk, m;
+};
+
+// start of a restart cycle: residual norm `res` is current
+__global__ void k_gm_begin(GmState* g) {
+  for (int i = 0; i <= g->m; ++i) g->rs[i] = 0.0;
+  g->rs[0] = g->res;
+  g->kk = 0;
+  g->inv = g->res != 0.0 ? 1.0 / g->res : 0.0;
+}
+// dst = (*alpha) * src unless the cycle has stopped
+__global__ void k_gm_scale_dev(int n, const GmState* g, const double2* __restrict__ src, double2* __restrict__ dst) {
+  if (g->stop) return;
+  const double alpha = g->inv;
+  for (int e = blockIdx.x * TPB + threadIdx.x; e < n; e += gridDim.x * TPB) {
+    const double2 v = src[e];
+    dst[e] = make_double2(alpha * v.x, alpha * v.y);
+  }
+}
+// column j of the Hessenberg matrix is in hcol[0..j], ||w||^2 in hcol[j+1]: rotations, residual, convergence test
+__global__ void k_gm_givens(GmState* g, int j, const double* __restrict__ hcol) {
+  if (g->stop) return;
+  const int m = g->m;
+  double* hh = g->H + (size_t)j * (m + 1);
+  for (int i = 0; i <= j; ++i) hh[i] = hcol[i];
+  const double tt = sqrt(hcol[j + 1]);
+  hh[j + 1] = tt;
+  for (int i = 0; i < j; ++i) {   // previous rotations
+    const double t0 = hh[i];
+    hh[i] = g->cs[i] * t0 + g->sn[i] * hh[i + 1];
+    hh[i + 1] = -g->sn[i] * t0 + g->cs[i] * hh[i + 1];
+  }
+  const double den = sqrt(hh[j] * hh[j] + hh[j + 1] * hh[j + 1]);
+  if (den == 0.0) { g->reason = BTFEM_EBREAKDOWN; g->stop = 1; return; }
+  g->cs[j] = hh[j] / den;
+  g->sn[j] = hh[j + 1] / den;
+  g->rs[j + 1] = -g->sn[j] * g->rs[j];
+  g->rs[j] = g->cs[j] * g->rs[j];
+  hh[j] = g->cs[j] * hh[j] + g->sn[j] * hh[j + 1];
+  const double res = fabs(g->rs[j + 1]);
+  g->res = res;
+  g->its = g->its + 1;
+  g->kk = j + 1;
+  g->inv = tt != 0.0 ? 1.0 / tt : 0.0;
+  if (!(res == res) || isinf(res)) { g->reason = BTFEM_ENAN; g->stop = 1; }
+  else if (res <= g->ttol) { g->reason = res < g->atol ? 3 : 2; g->stop = 1; }
+  else if (res >= 1e4 * g->bnorm) { g->reason = BTFEM_EDTOL; g->stop = 1; }
+  else if (g->its >= g->maxit) { g->reason = BTFEM_ENOTCONV; g->stop = 1; }
+  else if (tt == 0.0) { g->reason = BTFEM_EBREAKDOWN; g->stop = 1; }
+}
+// back substitution R y = rs over the kk columns built
+__global__ void k_gm_backsolve(GmState* g) {
+  const int kk = g->kk, m = g->m;
+  for (int i = kk - 1; i >= 0; --i) {
+    double t0 = g->rs[i];
+    for (int l = i + 1; l < kk; ++l) t0 -= g->H[(size_t)l * (m + 1) + i] * g->y[l];
+    g->y[i] = t0 / g->H[(size_t)i * (m + 1) + i];
+  }
+}
+// x += sum_{i < kk} y_i v_i
+__global__ void k_gm_axpy_dev(int n, const GmState* g, GmVecs V, double2* __restrict__ x) {
+  const int k = g->kk;
+  for (int e = blockIdx.x * TPB + threadIdx.x; e < n; e += gridDim.x * TPB) {
+    double2 a = x[e];
+    for (int i = 0; i < k; ++i) {
+      const double yi = g->y[i];
+      const double2 b = V.v[i][e];
+      a.x += yi * b.x;
+      a.y += yi * b.y;
+    }
+    x[e] = a;
+  }
+}
+// after the restart residual: res = sqrt(norm2[0]); converged?  else the next cycle may run
+__global__ void k_gm_setres(GmState* g, const double* __restrict__ norm2) {
+  if (g->reason != 0) return;
+  const double res = sqrt(norm2[0]);
+  g->res = res;
+  g->stop = 0;
+  if (res <= g->ttol) { g->reason = res < g->atol ? 3 : 2; g->stop = 1; }
+}
+
+// ---- left preconditioning by an explicit operator M^-1 (ILU(0), ilu.cu): the fused epilogues cannot be used
+// (the dot products need M^-1 A x, which exists only after two triangular solves), so the products are plain
+// SpMVs and these small kernels do what the epilogues of the Jacobi path do.
+// r = r^ = M^-1 b has just been formed in a.r: ||r||, start of the Krylov solve of this step (MODE_RHS's finalize
+// without the step counters, which the right-hand-side kernel has advanced already)
+__global__ void __launch_bounds__(TPB) k_pc_rhs(SpmvArgs a) {
+  KrylovCtrl* ctrl = a.ctrl;
+  if (ctrl->failed) return;
+  double acc[1] = {0.0};
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < a.n; i += gridDim.x * TPB) {
+    const double2 y = a.r[i];
+    a.rp[i] = y;
+    acc[0] += y.x * y.x + y.y * y.y;
+  }
+  if (reduce_finalize<1>(acc, a.partials, &ctrl->ticket[TK_RHS])) {
+    const double bn = sqrt(acc[0]);
+    ctrl->bnorm = bn;
+    ctrl->ttol = fmax(ctrl->rtol * bn, ctrl->atol);
+    ctrl->rho = acc[0];
+    ctrl->rnorm = bn;
+    ctrl->done = 0; ctrl->reason = 0;
+    if (!(bn == bn) || isinf(bn)) { ctrl->done = 1; ctrl->reason = BTFEM_ENAN; }
+    else if (bn <= ctrl->ttol) { ctrl->done = 1; ctrl->reason = bn < ctrl->atol ? 3 : 2; }
+  }
+}
+// the dot products of v = M^-1 A p (MODE_V) / t = M^-1 A s (MODE_T) and the scalar that follows
+template <int MODE>
+__global__ void __launch_bounds__(TPB) k_pc_dot(SpmvArgs a) {
+  if (a.ctrl->done) return;
+  double acc[2] = {0.0, 0.0};
+  for (int i = blockIdx.x * TPB + threadIdx.x; i < a.n; i += gridDim.x * TPB) {
+    if (MODE == MODE_V) {
+      const double2 y = a.v[i], q = a.rp[i];
+      acc[0] += y.x * q.x + y.y * q.y;
+    } else {
+      const double2 y = a.t[i], sv = a.s[i];
+      acc[0] += sv.x * y.x + sv.y * y.y;
+      acc[1] += y.x * y.x + y.y * y.y;
+    }
+  }
+  mode_finalize<MODE>(a, acc);
+}
+
 inline int vec_blocks_per_sm() {
   static int v = -1;
   if (v < 0) {
@@ -2254,6 +2404,10 @@ SpmvArgs base_args(btfem* h) {
   if (bt_stream_kernel_usable(h) && h->comb_members == 1 && h->comb_dt > 0) {
     a.ps_blocks = h->ps_blocks;
     a.ps_warps = h->ps_warps;
+    {
+      static const int ahead = getenv("BTFEM_PS_L2AHEAD") ? std::max(0, atoi(getenv("BTFEM_PS_L2AHEAD"))) : 0;
+      a.ps_l2ahead = ahead;
+    }
     a.ps_ptr = h->d_ps_ptr.p;
     a.ps_piece = h->d_ps_piece.p;
     a.PJt = h->d_PJt.p;
@@ -2329,9 +2483,18 @@ void ensure_vectors(btfem* h, int members = 1) {
   }
 }
 
-// One linear solve with restarted GMRES, host-driven.  On entry the RHS kernel(s) have run: r = K^-1(b - A x0),
-// b^ is in t when the guess is non-zero.  Returns the iteration count; reason in *reason.
-int gmres_solve_step(btfem* h, const btfem_solve_args* sa, SpmvArgs a, double cA_step, int64_t* n_spmv,
+// r <- M^-1 r in place (ILU(0)) and the start-of-solve scalars on the preconditioned residual
+void pc_fix_rhs(btfem* h, const SpmvArgs& a, cudaStream_t st) {
+  bt_ilu_apply(h, h->d_r.p, h->d_r.p, st);
+  k_pc_rhs<<<vec_grid(a.n), TPB, 0, st>>>(a);
+}
+
+// One linear solve with restarted GMRES(m), device-resident (GmState): the host launches the Arnoldi steps of a
+// restart cycle back to back and reads the state block every GM_CHECK iterations and at the end of the cycle.
+// On entry the RHS kernel(s) have run: r = K^-1(b - A x0), b^ is in t when the guess is non-zero.  `ilu`: K^-1 is
+// the ILU(0) operator applied behind every product (Jacobi is folded into the operator values).
+// Returns the iteration count; reason in *reason.
+int gmres_solve_step(btfem* h, const btfem_solve_args* sa, SpmvArgs a, double cA_step, bool ilu, int64_t* n_spmv,
                      int64_t* n_kernels, int* reason) {
   cudaStream_t st = h->stream;
   const int n = (int)h->ndof;
@@ -2341,7 +2504,10 @@ int gmres_solve_step(btfem* h, const btfem_solve_args* sa, SpmvArgs a, double cA
   const int lanes = h->lanes;
   h->d_gm_V.alloc((size_t)(m + 1) * npad);
   h->d_gm_h.alloc(GM_MAXK + 2);
-  if (!h->h_gm) BT_CUDA(cudaMallocHost((void**)&h->h_gm, sizeof(double) * (GM_MAXK + 2)));
+  h->d_gm_state.alloc((sizeof(GmState) + 7) / 8);
+  if (!h->h_gm) BT_CUDA(cudaMallocHost((void**)&h->h_gm, sizeof(GmState)));
+  GmState* hs = reinterpret_cast<GmState*>(h->h_gm);
+  GmState* ds = reinterpret_cast<GmState*>(h->d_gm_state.p);
   GmVecs V;
   for (int i = 0; i < GM_MAXK; ++i) V.v[i] = h->d_gm_V.p + (size_t)std::min(i, m) * npad;
   unsigned int* tk1 = &h->d_ctrl.p->ticket[6];
@@ -2350,8 +2516,6 @@ int gmres_solve_step(btfem* h, const btfem_solve_args* sa, SpmvArgs a, double cA
 
   BT_CUDA(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl.p, sizeof(KrylovCtrl), cudaMemcpyDeviceToHost, st));
   BT_CUDA(cudaStreamSynchronize(st));
-  const double bnorm = h->h_ctrl->bnorm, ttol = h->h_ctrl->ttol;
-  double res = h->h_ctrl->rnorm;
   *reason = h->h_ctrl->reason;
   if (h->h_ctrl->done) return 0;
   if (!sa->nonzero_guess) {
@@ -2359,80 +2523,62 @@ int gmres_solve_step(btfem* h, const btfem_solve_args* sa, SpmvArgs a, double cA
     h->d_u.zero(st);
   }
   a.c_plain = sa->theta * cA_step;
-  int its = 0;
-  std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m, 0.0), sn(m, 0.0), rs(m + 1, 0.0), y(m, 0.0);
-  for (;;) {
-    k_gm_scale<<<vg, TPB, 0, st>>>(n, 1.0 / res, h->d_r.p, h->d_gm_V.p);
+  memset(hs, 0, sizeof(GmState));
+  hs->res = h->h_ctrl->rnorm;
+  hs->ttol = h->h_ctrl->ttol;
+  hs->bnorm = h->h_ctrl->bnorm;
+  hs->atol = sa->atol;
+  hs->maxit = (int)std::min<int64_t>(sa->maxit, 0x7fffffff);
+  hs->m = m;
+  BT_CUDA(cudaMemcpyAsync(ds, hs, sizeof(GmState), cudaMemcpyHostToDevice, st));
+  auto read_state = [&]() {   // header fields only (behind the arrays)
+    BT_CUDA(cudaMemcpyAsync(&hs->res, &ds->res, sizeof(GmState) - offsetof(GmState, res), cudaMemcpyDeviceToHost, st));
+    BT_CUDA(cudaStreamSynchronize(st));
+  };
+  auto product = [&](const double2* x, double2* y) {   // y = K^-1 A x
+    a.x_plain = x;
+    a.y_plain = y;
+    launch_spmv<MODE_PLAIN>(lanes, a, st);
     ++*n_kernels;
-    std::fill(rs.begin(), rs.end(), 0.0);
-    rs[0] = res;
-    int j = 0;
-    bool stop = false;
-    for (; j < m && !stop; ++j) {
+    ++*n_spmv;
+    if (ilu) {
+      bt_ilu_apply(h, y, y, st);
+      *n_kernels += 2;
+    }
+  };
+  for (;;) {
+    k_gm_begin<<<1, 1, 0, st>>>(ds);
+    k_gm_scale_dev<<<vg, TPB, 0, st>>>(n, ds, h->d_r.p, h->d_gm_V.p);
+    *n_kernels += 2;
+    for (int j = 0; j < m; ++j) {
       double2* w = h->d_gm_V.p + (size_t)(j + 1) * npad;
-      a.x_plain = h->d_gm_V.p + (size_t)j * npad;
-      a.y_plain = w;
-      launch_spmv<MODE_PLAIN>(lanes, a, st);
+      product(h->d_gm_V.p + (size_t)j * npad, w);
       k_gm_dots<<<vg, TPB, 0, st>>>(n, j + 1, V, w, part, tk1, h->d_gm_h.p);
       k_gm_update<<<vg, TPB, 0, st>>>(n, j + 1, V, w, part, tk2, h->d_gm_h.p);
-      *n_kernels += 3;
-      ++*n_spmv;
-      BT_CUDA(cudaMemcpyAsync(h->h_gm, h->d_gm_h.p, sizeof(double) * (j + 2), cudaMemcpyDeviceToHost, st));
-      BT_CUDA(cudaStreamSynchronize(st));
-      double* hh = &H[(size_t)j * (m + 1)];
-      for (int i = 0; i <= j; ++i) hh[i] = h->h_gm[i];
-      const double tt = std::sqrt(h->h_gm[j + 1]);
-      hh[j + 1] = tt;
-      for (int i = 0; i < j; ++i) {   // previous rotations
-        const double t0 = hh[i];
-        hh[i] = cs[i] * t0 + sn[i] * hh[i + 1];
-        hh[i + 1] = -sn[i] * t0 + cs[i] * hh[i + 1];
-      }
-      const double den = std::sqrt(hh[j] * hh[j] + hh[j + 1] * hh[j + 1]);
-      if (den == 0.0) { *reason = BTFEM_EBREAKDOWN; break; }
-      cs[j] = hh[j] / den;
-      sn[j] = hh[j + 1] / den;
-      rs[j + 1] = -sn[j] * rs[j];
-      rs[j] = cs[j] * rs[j];
-      hh[j] = cs[j] * hh[j] + sn[j] * hh[j + 1];
-      res = std::fabs(rs[j + 1]);
-      ++its;
-      if (!(res == res) || std::isinf(res)) { *reason = BTFEM_ENAN; stop = true; }
-      else if (res <= ttol) { *reason = res < sa->atol ? 3 : 2; stop = true; }
-      else if (res >= 1e4 * bnorm) { *reason = BTFEM_EDTOL; stop = true; }
-      else if (its >= sa->maxit) { *reason = BTFEM_ENOTCONV; stop = true; }
-      else if (tt == 0.0) { *reason = BTFEM_EBREAKDOWN; stop = true; }
-      if (!stop && j + 1 < m) {
-        k_gm_scale<<<vg, TPB, 0, st>>>(n, 1.0 / tt, w, w);
-        ++*n_kernels;
+      k_gm_givens<<<1, 1, 0, st>>>(ds, j, h->d_gm_h.p);
+      if (j + 1 < m) k_gm_scale_dev<<<vg, TPB, 0, st>>>(n, ds, w, w);
+      *n_kernels += 4;
+      if ((j + 1) % GM_CHECK == 0 && j + 1 < m) {   // bounded overshoot: a stopped cycle runs at most GM_CHECK - 1 empty steps
+        read_state();
+        if (hs->stop) break;
       }
     }
-    const int kk = j;   // columns built
-    for (int i = kk - 1; i >= 0; --i) {   // back substitution R y = rs
-      double t0 = rs[i];
-      for (int l = i + 1; l < kk; ++l) t0 -= H[(size_t)l * (m + 1) + i] * y[l];
-      y[i] = t0 / H[(size_t)i * (m + 1) + i];
-    }
-    if (kk > 0) {
-      BT_CUDA(cudaMemcpyAsync(h->d_gm_h.p, y.data(), sizeof(double) * kk, cudaMemcpyHostToDevice, st));
-      k_gm_axpy<<<vg, TPB, 0, st>>>(n, kk, V, h->d_gm_h.p, h->d_u.p);
-      ++*n_kernels;
-      BT_CUDA(cudaStreamSynchronize(st));   // y is a host temporary
-    }
-    if (*reason != 0) break;
-    // restart: true preconditioned residual r = b^ - A^ x
-    a.x_plain = h->d_u.p;
-    a.y_plain = h->d_s.p;
-    launch_spmv<MODE_PLAIN>(lanes, a, st);
-    k_gm_resid<<<vg, TPB, 0, st>>>(n, h->d_t.p, h->d_s.p, h->d_r.p, part, tk2, h->d_gm_h.p);
+    k_gm_backsolve<<<1, 1, 0, st>>>(ds);
+    k_gm_axpy_dev<<<vg, TPB, 0, st>>>(n, ds, V, h->d_u.p);
     *n_kernels += 2;
-    ++*n_spmv;
-    BT_CUDA(cudaMemcpyAsync(h->h_gm, h->d_gm_h.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-    BT_CUDA(cudaStreamSynchronize(st));
-    res = std::sqrt(h->h_gm[0]);
-    if (res <= ttol) { *reason = res < sa->atol ? 3 : 2; break; }
+    read_state();
+    if (hs->reason != 0) break;
+    // restart: true preconditioned residual r = b^ - K^-1 A x
+    product(h->d_u.p, h->d_s.p);
+    k_gm_resid<<<vg, TPB, 0, st>>>(n, h->d_t.p, h->d_s.p, h->d_r.p, part, tk2, h->d_gm_h.p);
+    k_gm_setres<<<1, 1, 0, st>>>(ds, h->d_gm_h.p);
+    *n_kernels += 2;
+    read_state();
+    if (hs->reason != 0) break;
   }
-  return its;
+  BT_CUDA(cudaGetLastError());
+  *reason = hs->reason;
+  return hs->its;
 }
 
 }  // namespace
@@ -2453,6 +2599,7 @@ void bt_combine(btfem* h, double dt, double theta, const double g[3], int pc, in
   cudaStream_t st = h->stream;
   const int n = (int)h->ndof;
   const size_t nm = (size_t)members;
+  h->ilu_valid = false;   // factors belong to the operator values that are replaced below
   h->d_PJ.alloc(nm * h->nnz);
   h->d_QJ.alloc(nm * h->nnz);
   h->d_dinv.alloc(n);
@@ -2578,6 +2725,10 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     BT_REQUIRE(sa->Fb != nullptr, "periodic BC needs Fb (F(t_{n-1}) per step)");
     BT_REQUIRE(h->n_pb > 0, "periodic BC: call btfem_set_periodic_gather after btfem_assemble");
   }
+  BT_REQUIRE(sa->pc == BTFEM_PC_JACOBI || sa->pc == BTFEM_PC_NONE || sa->pc == BTFEM_PC_ILU, "unknown preconditioner");
+  const bool ilu = sa->pc == BTFEM_PC_ILU;
+  BT_REQUIRE(!ilu || (members == 1 && h->nv_own < 0 && h->h_vmaster.empty() && !sa->nonzero_guess),
+             "ILU(0): single whole-mesh solves from a zero initial guess (no strong periodic map)");
   BT_REQUIRE(members == 1 || (!gmres && !periodic), "batched solves support BiCGStab without periodic BC");
   const bool strong = !h->h_vmaster.empty();   // transformed equation on a periodic dof map (strong.cu)
   BT_REQUIRE(!strong || (members == 1 && !gmres && !periodic && h->lanes == 0 && h->nv_own < 0),
@@ -2600,18 +2751,21 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   BT_CUDA(cudaEventCreate(&e2));
   BT_CUDA(cudaEventRecord(e0, st));
   // Batch layouts (BTFEM_BATCH_LAYOUT):
-  //   "interleaved" (default when the batch qualifies): groups of 8 members, Krylov vectors member-innermost, ONE
-  //       direction-independent operator per batch (k_hb_*): one 128-byte gather serves 8 members and the operator is
-  //       read once per group (44 B per nonzero per 8 members instead of 20 B per member);
-  //   "member": one pre-combined copy of the operator per member, member = blockIdx.y of the single-solve kernels
-  //       (round 1's default; also what periodic / non-zero-guess batches fall back to);
-  //   "shared": round 1's shared-operator kernel with per-member vector slabs (k_spmv_sell_batch; slower than
-  //       "member" on the 46 k-vertex HARDI mesh, profiles/r1e_batch_layouts.txt).
+  //   "member" (default): one pre-combined copy of the operator per member, member = blockIdx.y of the single-solve
+  //       kernels -- fully coalesced streaming loads, members x more warps in flight; HBM-bound on the operator copies;
+  //   "interleaved": groups of 8 members, Krylov vectors member-innermost, ONE direction-independent operator per
+  //       batch (k_hb_*): one 128-byte gather serves 8 members and the operator is read once per group (44 B per
+  //       nonzero per 8 members instead of 20 B per member).  Same bits per member.  Moves 2.4x fewer bytes through
+  //       L2 but, measured on B200 on the 46 k-vertex HARDI mesh, is SLOWER (16.4 against 22-24 signals/s,
+  //       profiles/r2n_hardi_layouts.txt): with 8 x 7 vectors per group the working set leaves L2, nearly every load
+  //       batch then waits for a DRAM miss, and the 4-rows-x-8-members lane mapping has too few loads in flight;
+  //   "shared": round 1's shared-operator kernel with per-member vector slabs (k_spmv_sell_batch; also slower,
+  //       profiles/r1e_batch_layouts.txt).
   const char* layout_env = getenv("BTFEM_BATCH_LAYOUT");
   const char* shared_env = getenv("BTFEM_BATCH_SHARED");
   const bool batch_ok = members > 1 && h->lanes == 0 && h->n_slice > 0;
   const bool hb = batch_ok && !periodic && !gmres && !part && !strong && !sa->nonzero_guess &&
-                  !(layout_env && (layout_env[0] == 'm' || layout_env[0] == 's')) && !(shared_env && shared_env[0] == '1');
+                  layout_env && layout_env[0] == 'i';
   const bool shared_ops = hb || (batch_ok && ((shared_env && shared_env[0] == '1') || (layout_env && layout_env[0] == 's')));
   const int groups = (members + HB - 1) / HB;
   const int members_alloc = hb ? groups * HB : members;
@@ -2692,7 +2846,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   const int vgx = std::max(1, std::min(vec_grid(n), std::max(BT_NUM_SMS, BT_NUM_SMS * 8 / members)));
   const dim3 vg(vgx, members);
   // member-interleaved batch: (blocks over the slices | the n x 8 vector entries, groups)
-  const dim3 hb_sg(std::max(1, std::min((int)h->n_slice, std::max(BT_NUM_SMS, BT_NUM_SMS * 8 / groups))), groups);
+  const dim3 hb_sg(std::max(1, std::min((int)h->n_slice, std::max(BT_NUM_SMS, BT_NUM_SMS * 4 / groups))), groups);
   const dim3 hb_vg(std::max(1, std::min((int)(((size_t)n * HB + TPB - 1) / TPB), std::max(BT_NUM_SMS, BT_NUM_SMS * 8 / groups))),
                    groups);
   if (hb) a.members = members;
@@ -2702,7 +2856,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   // kernels themselves set from ctrl->done -- so the host queues nsteps graph launches and never waits inside the
   // solve.  BTFEM_LOOP=host (and GMRES): the iteration graph is re-launched by the host, which polls ctrl->done.
   const char* loop_env = getenv("BTFEM_LOOP");
-  const bool dev_loop = !gmres && (hb || !(loop_env && loop_env[0] == 'h'));
+  const bool dev_loop = !gmres && !ilu && !(loop_env && loop_env[0] == 'h');
   const int push_grid = part ? std::max(1, std::min(32, ((int)h->d_send_src.n + TPB - 1) / TPB)) : 0;
   const int kernels_per_iter = 5;
   int unroll = 6;
@@ -2847,12 +3001,30 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     BT_CUDA(cudaStreamEndCapture(st, &same));
     pin_vectors(graph);
     pin_vectors(body);
-  } else {
+  } else if (!ilu) {
     BT_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     capture_iteration();
     BT_CUDA(cudaStreamEndCapture(st, &graph));
     pin_vectors(graph);
   }
+  // BiCGStab with an explicit left preconditioner (ILU(0)): plain products + triangular solves + dot kernels
+  auto iteration_ilu = [&](double c_step) {
+    SpmvArgs ap = a;
+    ap.c_plain = sa->theta * c_step;
+    auto product = [&](const double2* x, double2* y) {
+      ap.x_plain = x;
+      ap.y_plain = y;
+      launch_spmv<MODE_PLAIN>(lanes, ap, st);
+      bt_ilu_apply(h, y, y, st);
+    };
+    k_update_p<<<vg, TPB, 0, st>>>(a);
+    product(h->d_p.p, h->d_v.p);
+    k_pc_dot<MODE_V><<<vg, TPB, 0, st>>>(a);
+    k_update_s<<<vg, TPB, 0, st>>>(a);
+    product(h->d_s.p, h->d_t.p);
+    k_pc_dot<MODE_T><<<vg, TPB, 0, st>>>(a);
+    k_update_xr<<<vg, TPB, 0, st>>>(a);
+  };
   if (graph) BT_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
 
   DevArray<double> d_sig;   // allocated before the loop: no allocation may sit between two collectives
@@ -2963,15 +3135,24 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
           h->d_ubc.p, h->d_rhs_add.p);
       n_kernels += 2;
     }
-    launch_spmv<MODE_RHS>(lanes, a, st, members);
+    if (hb) {
+      k_hb_spmv<MODE_RHS><<<hb_sg, TPB, 0, st>>>(a);
+    } else {
+      launch_spmv<MODE_RHS>(lanes, a, st, members);
+    }
     ++n_kernels;
     if (sa->nonzero_guess) {
       launch_spmv<MODE_RESID>(lanes, a, st, members);
       ++n_kernels;
     }
+    if (ilu) {   // renew the factors when the operator changed, then r = r^ = M^-1 b and the start-of-solve scalars
+      bt_ilu_factor(h, sa->theta * sa->cA[step], st);
+      pc_fix_rhs(h, a, st);
+      n_kernels += 5;
+    }
     if (gmres) {
       int reason = 0;
-      const int it = gmres_solve_step(h, sa, a, sa->cA[step], &n_spmv, &n_kernels, &reason);
+      const int it = gmres_solve_step(h, sa, a, sa->cA[step], ilu, &n_spmv, &n_kernels, &reason);
       n_spmv += 1 + (sa->nonzero_guess ? 1 : 0);
       total_iters[0] += it;
       max_iters[0] = std::max<int64_t>(max_iters[0], it);
@@ -2983,7 +3164,10 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     int launched = 0;
     int chunk = std::max(1, est);
     for (;;) {
-      for (int i = 0; i < chunk; ++i) BT_CUDA(cudaGraphLaunch(gexec, st));
+      for (int i = 0; i < chunk; ++i) {
+        if (ilu) iteration_ilu(sa->cA[step]);
+        else BT_CUDA(cudaGraphLaunch(gexec, st));
+      }
       launched += chunk;
       BT_CUDA(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl.p, sizeof(KrylovCtrl) * members, cudaMemcpyDeviceToHost, st));
       BT_CUDA(cudaStreamSynchronize(st));
@@ -2992,7 +3176,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
       if (all) break;
       chunk = std::max(1, std::min(8, launched / 8));
     }
-    n_kernels += kernels_per_iter * (int64_t)launched;
+    n_kernels += (ilu ? 11 : kernels_per_iter) * (int64_t)launched;
     est = 0;
     for (int b = 0; b < members; ++b) {
       const int it = h->h_ctrl[b].iters;
@@ -3002,8 +3186,10 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
       est = std::max(est, it);
       last_reason[b] = h->h_ctrl[b].reason;
       // converged before the first iteration with a zero initial guess: PETSc returns x = 0
-      if (it == 0 && !sa->nonzero_guess && last_reason[b] > 0)
+      if (it == 0 && !sa->nonzero_guess && last_reason[b] > 0) {
+        BT_REQUIRE(!hb, "interleaved batch: use the device-driven loop (unset BTFEM_LOOP)");
         BT_CUDA(cudaMemsetAsync(h->d_u.p + (size_t)b * 7 * h->vec_npad, 0, sizeof(double2) * n, st));
+      }
       if (last_reason[b] < 0) fail = last_reason[b];
     }
     if (fail == BTFEM_ECOMM) break;

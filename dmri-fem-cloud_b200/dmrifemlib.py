@@ -183,15 +183,20 @@ class MRI_parameters():
 class KrylovSolver:
     """dolfin.KrylovSolver(method, preconditioner) as a parameter holder; DOLFIN's defaults.
 
-    libbtfem implements BiCGStab and GMRES(m) with Jacobi or no preconditioner (the CLI's choice,
-    GCloudDmriSolver.py:218).  The notebooks also pass `KrylovSolver("bicgstab")` (PETSc's default PC, ILU(0) in
-    serial) and `KrylovSolver("bicgstab", "petsc_amg")` (ECS_226Cylinders.ipynb, RealNeurons.ipynb cell 10): a
-    preconditioner changes how fast the Krylov iteration reaches the tolerance, not what it converges to, so
-    those names are accepted and run with Jacobi -- `requested_preconditioner` keeps what was asked for and a
-    note is printed once.  Iteration counts (not converged signals) then differ from PETSc's."""
+    libbtfem implements BiCGStab and GMRES(m) with Jacobi, ILU(0) or no preconditioner:
+      "jacobi"   the CLI's choice (GCloudDmriSolver.py:218): fused into the operator values, the fast path;
+      "ilu"      KrylovSolver("gmres", "ilu") of the comri C++ demo (comri/one-comp/fenics-cpp/main.cpp:180-183):
+                 PETSc's PCILU defaults restated (ILU(0), natural ordering) in libbtfem's ilu.cu;
+      "default"  `KrylovSolver("bicgstab")` in the notebooks: PETSc's default preconditioner, which is ILU(0) on one
+                 process (block Jacobi + ILU(0) under mpirun) -> "ilu";
+      "none".
+    The algebraic-multigrid and other names the notebooks use (`KrylovSolver("bicgstab", "petsc_amg")`,
+    ECS_226Cylinders.ipynb / RealNeurons.ipynb cell 10) have no counterpart here: a preconditioner changes how fast
+    the Krylov iteration reaches the tolerance, not what it converges to, so they are accepted and run with Jacobi
+    -- LOUDLY: a Python warning and a printed line each time; `requested_preconditioner` keeps what was asked for.
+    Iteration counts (not converged signals) then differ from PETSc's."""
 
-    SUBSTITUTED = ("default", "ilu", "icc", "sor", "amg", "petsc_amg", "hypre_amg", "hypre_euclid",
-                   "hypre_parasails", "bjacobi")
+    SUBSTITUTED = ("icc", "sor", "amg", "petsc_amg", "hypre_amg", "hypre_euclid", "hypre_parasails", "bjacobi")
 
     def __init__(self, method="bicgstab", preconditioner="default"):
         if method == "default":
@@ -199,13 +204,17 @@ class KrylovSolver:
         if method not in ("bicgstab", "gmres"):
             raise RuntimeError("Unknown Krylov method \"%s\"" % method)
         self.requested_preconditioner = preconditioner
+        if preconditioner == "default":
+            preconditioner = "ilu"
         if preconditioner in self.SUBSTITUTED:
-            if preconditioner != "default":
-                print("libbtfem: preconditioner \"%s\" is not available on the GPU path; using \"jacobi\" "
-                      "(same converged solution, different iteration counts)" % preconditioner)
+            import warnings
+            msg = ("libbtfem: preconditioner \"%s\" is NOT available on the GPU path; running \"jacobi\" instead "
+                   "(same converged solution, different iteration counts)" % preconditioner)
+            warnings.warn(msg, RuntimeWarning, stacklevel=2)
+            print(msg)
             preconditioner = "jacobi"
-        if preconditioner not in ("jacobi", "none"):
-            raise RuntimeError("Unknown preconditioner \"%s\" (libbtfem implements jacobi and none)" % preconditioner)
+        if preconditioner not in ("jacobi", "none", "ilu"):
+            raise RuntimeError("Unknown preconditioner \"%s\" (libbtfem implements jacobi, ilu and none)" % preconditioner)
         self.method = method
         self.preconditioner = preconditioner
         self.parameters = {"relative_tolerance": 1e-6, "absolute_tolerance": 1e-15, "maximum_iterations": 10000,
@@ -329,6 +338,10 @@ class MyDomain():
                 raise NotImplementedError("weak pseudo-periodic BC on a manifold mesh (curve or surface in 3-D)")
             fem.set_periodic(self.PeriodicDir, self.kappa_e_scalar, self.tol,
                              [self.xmin, self.ymin, self.zmin], [self.xmax, self.ymax, self.zmax])
+            self._weak_periodic = True
+        elif getattr(self, "_weak_periodic", False):   # the handle is re-used with PeriodicDir back to [0,0,0]
+            fem.set_periodic([0, 0, 0], 0.0, 0.0, lo, hi)
+            self._weak_periodic = False
         fem.set_initial(ic)
         fem.assemble()
         if sum(self.PeriodicDir) > 0 and not self.is_strongly_periodic():
@@ -374,6 +387,10 @@ class MRI_simulation():
         par = linsolver.parameters
         start_time = time.time()
         g = mri_para.gdir.array() if hasattr(mri_para.gdir, "array") else np.asarray(mri_para.gdir, dtype=float)
+        if mydomain.is_strongly_periodic() and linsolver.method != "bicgstab":
+            raise NotImplementedError("strongly imposed pseudo-periodic BC (IsDomainPeriodic = True): libbtfem solves the "
+                                      "transformed equation with KrylovSolver(\"bicgstab\", ...) only, not \"%s\""
+                                      % linsolver.method)
         if mydomain.is_strongly_periodic():
             # transformed equation (FuncF_sBC): the forms read the INTEGRATED profile, ift at t for the matrix and
             # at tp for the right-hand side (DmriFemLib.py:901-902 with :166-238)

@@ -62,7 +62,22 @@ def _locate(points2, tri_xy, ncand=16):
     W = np.stack([w0, w1, w2], axis=2)                    # (np, k, 3)
     best = np.argmax(W.min(axis=2), axis=1)               # inside: min weight >= 0; else least outside
     rows = np.arange(len(points2))
-    return cand[rows, best], W[rows, best]
+    tri, w = cand[rows, best], W[rows, best]
+    # On anisotropic / strongly graded faces the containing triangle need not be among the `ncand` nearest centroids:
+    # points that ended up outside every candidate are searched again over ALL triangles (exhaustive, few points).
+    out = np.nonzero(w.min(axis=1) < -1e-9)[0]
+    for i0 in range(0, len(out), 256):
+        sel = out[i0:i0 + 256]
+        qx, qy = points2[sel, 0:1], points2[sel, 1:2]
+        v0 = ((b[:, 1] - c[:, 1]) * (qx - c[:, 0]) + (c[:, 0] - b[:, 0]) * (qy - c[:, 1])) / d
+        v1 = ((c[:, 1] - a[:, 1]) * (qx - c[:, 0]) + (a[:, 0] - c[:, 0]) * (qy - c[:, 1])) / d
+        V = np.stack([v0, v1, 1.0 - v0 - v1], axis=2)     # (points, triangles, 3)
+        bt = np.argmax(V.min(axis=2), axis=1)
+        r = np.arange(len(sel))
+        better = V[r, bt].min(axis=1) > w[sel].min(axis=1)
+        tri[sel[better]] = bt[better]
+        w[sel[better]] = V[r, bt][better]
+    return tri, w
 
 
 def _line_segments(xyz, tris, d, target):

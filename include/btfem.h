@@ -46,7 +46,10 @@ enum { BTFEM_MAT_M = 0, BTFEM_MAT_S = 1, BTFEM_MAT_R = 2, BTFEM_MAT_JX = 3, BTFE
        BTFEM_MAT_JZ = 5, BTFEM_MAT_I = 6, BTFEM_MAT_B = 7 };
 
 enum { BTFEM_KSP_BICGSTAB = 0, BTFEM_KSP_GMRES = 1 };
-enum { BTFEM_PC_JACOBI = 0, BTFEM_PC_NONE = 1 };
+/* BTFEM_PC_ILU: ILU(0) on the pattern of A (PETSc PCILU defaults: levels 0, natural ordering), the preconditioner of
+ * KrylovSolver("gmres","ilu") (comri/one-comp/fenics-cpp/main.cpp:180-183) and PETSc's serial default; single
+ * whole-mesh solves, zero initial guess.  The factorisation is renewed whenever theta*cA[step] changes. */
+enum { BTFEM_PC_JACOBI = 0, BTFEM_PC_NONE = 1, BTFEM_PC_ILU = 2 };
 
 /* ---- lifetime ----------------------------------------------------------------------- */
 int btfem_create(int device, btfem_t** out);
@@ -152,6 +155,9 @@ int btfem_set_lanes(btfem_t* h, int32_t lanes);
  * 1 = SELL-32, register-staged loads (k_spmv_sell); 2 = SELL-32 through per-warp TMA rings (k_spmv_stream:
  * cp.async.bulk + mbarrier).  Bench / profiling hook; the reference has no counterpart (PETSc MatMult). */
 int btfem_get_spmv_kernel(btfem_t* h, int32_t* kind);
+/* Parity hook: the ILU(0) factors of the last solve with BTFEM_PC_ILU, (re,im) per CSR nonzero (unit-lower L below the
+ * diagonal, U on and above it -- one array, like PETSc's factored AIJ matrix).  out[2*nnz]. */
+int btfem_get_ilu_factors(btfem_t* h, double* out);
 
 /* ---- the theta loop ---------------------------------------------------------------------
  * MRI_simulation.solve (DmriFemLib.py:878-915): for n in 0..nsteps-1

@@ -397,6 +397,58 @@ def time_grid(T, k, closed=True):
 # --------------------------------------------------------------------------- Krylov (PETSc restated)
 
 
+class _Pc:
+    """Left preconditioner K^-1 of the Krylov restatements, used as `Kinv * vector`: None (identity), the real Jacobi
+    diagonal (array), or any callable vector -> vector (ILU(0): ilu0_factor)."""
+
+    def __init__(self, spec):
+        self.spec = spec
+
+    def __mul__(self, v):
+        if self.spec is None:
+            return v
+        if callable(self.spec):
+            return self.spec(v)
+        return v / self.spec
+
+
+def ilu0_factor(A):
+    """PETSc PCILU with its defaults restated (third party, PETSc 3.7: MatILUFactorSymbolic/Numeric, levels = 0, natural
+    ordering, no shift): incomplete LU on the pattern of A, row by row (IKJ), no pivoting; L has a unit diagonal and is
+    stored with U in one array like PETSc's factored AIJ matrix.  A: complex CSR with sorted columns, i.e. the
+    reference's real (re,im)-split matrix with every 2x2 block [[a,-b],[b,a]] written as the complex number a + ib --
+    scalar ILU(0) on the split matrix drops no fill inside the (full) blocks, so both factorisations apply the same
+    operator when unknowns are ordered vertex by vertex.  Returns K^-1: v -> U^-1 L^-1 v."""
+    A = sp.csr_matrix(A).astype(complex)
+    A.sort_indices()
+    n = A.shape[0]
+    rp, ci, lu = A.indptr, A.indices, A.data.copy()
+    diag = np.full(n, -1, dtype=np.int64)
+    for i in range(n):
+        pos = {int(ci[k]): k for k in range(rp[i], rp[i + 1])}
+        for k in range(rp[i], rp[i + 1]):
+            c = int(ci[k])
+            if c >= i:
+                break
+            lu[k] = lu[k] / lu[diag[c]]                    # l_ic
+            lic = lu[k]
+            for kk in range(diag[c] + 1, rp[c + 1]):       # row i -= l_ic * (U part of row c), inside the pattern only
+                j = pos.get(int(ci[kk]))
+                if j is not None:
+                    lu[j] -= lic * lu[kk]
+        diag[i] = pos[i]
+    L = sp.csr_matrix((lu, ci, rp), shape=(n, n))
+    Lo = (sp.tril(L, -1) + sp.identity(n, dtype=complex)).tocsr()
+    Up = sp.triu(L, 0).tocsr()
+
+    def apply(v):
+        y = spla.spsolve_triangular(Lo, np.asarray(v, dtype=complex), lower=True, unit_diagonal=True)
+        return spla.spsolve_triangular(Up, y, lower=False)
+
+    apply.lu = lu
+    return apply
+
+
 def bicgstab_petsc(matvec, b, diag, rtol=1e-9, atol=1e-10, maxit=100000, x0=None, dtol=1e4):
     """PETSc 3.7 KSPSolve_BCGS with left PCJACOBI and the default convergence test
     (preconditioned residual 2-norm <= max(rtol*||K^-1 b||, atol)), on COMPLEX storage but
@@ -404,7 +456,7 @@ def bicgstab_petsc(matvec, b, diag, rtol=1e-9, atol=1e-10, maxit=100000, x0=None
     real (re,im)-split system.  `diag` is the real Jacobi diagonal P_ii.
     Returns x, iterations, final preconditioned residual norm, reason (>0 converged)."""
     rdot = lambda a, c: float(np.dot(a.real, c.real) + np.dot(a.imag, c.imag))
-    Kinv = 1.0 / diag
+    Kinv = _Pc(diag)
     n = len(b)
     if x0 is None:
         x = np.zeros(n, dtype=complex)
@@ -465,7 +517,7 @@ def gmres_petsc(matvec, b, diag, rtol=1e-6, atol=1e-15, maxit=10000, restart=30,
     residual estimate.  REAL inner products on complex storage == GMRES on the reference's real
     (re,im)-split system.  Returns x, iterations, residual norm, reason."""
     rdot = lambda a, c: float(np.dot(a.real, c.real) + np.dot(a.imag, c.imag))
-    Kinv = 1.0 if diag is None else 1.0 / diag
+    Kinv = _Pc(diag)
     n = len(b)
     kb = Kinv * b
     bnorm = np.sqrt(rdot(kb, kb))
@@ -793,12 +845,18 @@ def theta_solve(ops, seq, q, gdir, k, theta=0.5, solver="lu", rtol=1e-9, atol=1e
             iters.append(0)
         else:
             mv = lambda x, cA=cA: P @ x + 1j * theta * cA * (Jg @ x)
+            pc = diag
+            if solver.endswith("_none"):
+                pc = None
+            elif solver.endswith("_ilu"):                   # KrylovSolver("gmres", "ilu"), fenics-cpp/main.cpp:180-183
+                key = round(cA, 300)
+                if key not in lus:
+                    lus[key] = ilu0_factor(P + 1j * theta * cA * Jg)
+                pc = lus[key]
             if solver.startswith("gmres"):
-                u, it, dp, reason = gmres_petsc(mv, b, None if solver == "gmres_none" else diag, rtol, atol, maxit,
-                                                restart, x0=u if nonzero_guess else None)
+                u, it, dp, reason = gmres_petsc(mv, b, pc, rtol, atol, maxit, restart, x0=u if nonzero_guess else None)
             else:
-                u, it, dp, reason = bicgstab_petsc(mv, b, diag if solver != "bicgstab_none" else np.ones_like(diag),
-                                                   rtol, atol, maxit, x0=u if nonzero_guess else None)
+                u, it, dp, reason = bicgstab_petsc(mv, b, pc, rtol, atol, maxit, x0=u if nonzero_guess else None)
             if reason < 0:
                 raise RuntimeError("Krylov solver did not converge: reason %d" % reason)
             iters.append(it)

@@ -451,3 +451,30 @@ def test_layered_sphere_parity_and_matrix_formalism():
             q = seq.q_from_b(b)
             res = fem.solve(200.0, 0.5, q * f, q * fp, [0, 0, 1], rtol=1e-10, atol=1e-12)
             assert abs(res["signal"] / res["voi"] - want) <= 3e-3 * want
+
+
+def test_interleaved_batch_layout(monkeypatch):
+    """BTFEM_BATCH_LAYOUT=interleaved (k_hb_*: groups of 8 members, member-innermost vectors, one shared
+    direction-independent operator): a member gets the same bits whatever batch it travels in -- also across a group
+    boundary (9 members = 2 groups) -- and agrees with the default layout to solver tolerance."""
+    _, xyz, tets, phase, co = CASES[3]
+    seq = orc.pgse(2000.0, 6000.0)
+    k = 200.0
+    ts = orc.time_grid(seq.T, k)
+    f = np.array([seq.f(t) for t in ts])
+    fp = np.concatenate([[f[0]], f[:-1]])
+    dirs = meshes.fibonacci_hemisphere(3)
+    qs = [seq.q_from_b(b) for b in (500.0, 1500.0, 3000.0)]
+    members = [(q * f, q * fp, d) for d in dirs for q in qs]           # 9 members
+    with btfem.BTFem(0) as fem:
+        _setup(fem, xyz, tets, phase, co)
+        default = fem.solve_batch(k, 0.5, members, rtol=1e-10, atol=1e-14)
+        monkeypatch.setenv("BTFEM_BATCH_LAYOUT", "interleaved")
+        inter = fem.solve_batch(k, 0.5, members, rtol=1e-10, atol=1e-14)
+        split = fem.solve_batch(k, 0.5, members[:2], rtol=1e-10, atol=1e-14) + \
+            fem.solve_batch(k, 0.5, members[2:], rtol=1e-10, atol=1e-14)
+    for a, b in zip(inter, split):
+        assert a["signal"] == b["signal"] and a["total_iters"] == b["total_iters"]      # bit-identical
+    for a, d in zip(inter, default):
+        assert abs(a["signal"] - d["signal"]) <= 1e-9 * abs(d["signal"])
+        assert abs(a["total_iters"] - d["total_iters"]) <= max(3, 0.02 * d["total_iters"])

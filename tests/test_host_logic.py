@@ -81,10 +81,13 @@ def test_krylov_solver_defaults():
         dl.KrylovSolver("cg", "jacobi")
     with pytest.raises(RuntimeError):
         dl.KrylovSolver("bicgstab", "no_such_pc")
-    # the notebooks' other spellings run with Jacobi (ECS_226Cylinders.ipynb / RealNeurons.ipynb cell 10, ConvergenceTest)
-    for args in (("bicgstab",), ("bicgstab", "petsc_amg"), ("gmres", "ilu")):
-        ls = dl.KrylovSolver(*args)
-        assert ls.preconditioner == "jacobi" and ls.requested_preconditioner == (args[1] if len(args) > 1 else "default")
+    # PETSc's default preconditioner is ILU(0) on one process; "ilu" is implemented (comri fenics-cpp main.cpp:180-183)
+    assert dl.KrylovSolver("bicgstab").preconditioner == "ilu" and dl.KrylovSolver("bicgstab").requested_preconditioner == "default"
+    assert dl.KrylovSolver("gmres", "ilu").preconditioner == "ilu"
+    # multigrid & co. (ECS_226Cylinders.ipynb / RealNeurons.ipynb cell 10) run with Jacobi -- loudly
+    with pytest.warns(RuntimeWarning, match="NOT available"):
+        ls = dl.KrylovSolver("bicgstab", "petsc_amg")
+    assert ls.preconditioner == "jacobi" and ls.requested_preconditioner == "petsc_amg"
     assert dl.KrylovSolver("gmres", "none").preconditioner == "none"
     lu = dl.PETScLUSolver("mumps")
     assert (lu.method, lu.preconditioner, lu.parameters["relative_tolerance"]) == ("bicgstab", "jacobi", 1e-13)
@@ -299,3 +302,21 @@ def test_bench_loop_roofline_arithmetic():
     assert r["algorithmic_bytes_per_iteration"] == 2 * spmv + 224 * 100
     assert r["algorithmic_bytes_per_solve"] == 10 * (2 * spmv + 224 * 100) + 2 * spmv
     assert abs(r["achieved"] - r["algorithmic_bytes_per_solve"] / 1e-3 / 1e9) < 1e-12 and r["us_per_iteration"] == 100.0
+
+
+def test_periodic_locate_falls_back_to_exhaustive_search():
+    """periodic._locate: on a strongly graded face the containing triangle is not among the nearest centroids; the
+    point must still get its true triangle and weights (the reference evaluates in the containing cell)."""
+    from dmri_fem_cloud_b200 import periodic
+    big = [[(0.0, 0.0), (100.0, 0.0), (0.0, 1.0)], [(100.0, 0.0), (100.0, 1.0), (0.0, 1.0)]]
+    rng = np.random.default_rng(3)
+    small = []
+    for _ in range(40):                      # a cloud of tiny triangles next to the query point, none containing it
+        c = np.array([90.0, 3.0]) + rng.uniform(-0.5, 0.5, 2)
+        small.append([tuple(c), tuple(c + [0.05, 0.0]), tuple(c + [0.0, 0.05])])
+    tri_xy = np.array(big + small)
+    pts = np.array([[90.0, 0.05], [10.0, 0.95]])
+    tri, w = periodic._locate(pts, tri_xy, ncand=16)
+    assert tri.tolist() == [0, 1]
+    assert (w >= -1e-12).all() and np.allclose(w.sum(axis=1), 1.0)
+    assert np.allclose((w[:, :, None] * tri_xy[tri]).sum(axis=1), pts)
