@@ -51,7 +51,13 @@ UNIT = "DOF-steps/s"
 # DRAM bytes of one k_spmv_sell<MODE_V> launch on the default workload, from the committed
 # `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_spmv_sell_full.txt)
 NCU_TRAFFIC = {"n_box": 78,
-               "sell": {"bytes": 167.227136e6 + 3.839232e6, "file": "profiles/r1_ncu_spmv_sell_full.txt (ncu, round 1)"}}
+               "sell": {"bytes": 167.227136e6 + 3.839232e6, "file": "profiles/r1_ncu_spmv_sell_full.txt (ncu, round 1)"},
+               "stream": {"bytes": 159.704576e6 + 7.045888e6,
+                          "file": "profiles/r2m_ncu_persistent_and_stream_full.txt (ncu, round 2)"},
+               # one launch = one whole solve of this workload (270 steps, 11 335 iterations when captured)
+               "persistent": {"bytes": 3.465271e12 + 30.187408e9,
+                              "file": "profiles/r2m_ncu_persistent_and_stream_full.txt (ncu, round 2; 0.69 x the algorithmic "
+                                      "bytes: the Krylov vectors stay in L2, HBM carries the operator stream)"}}
 
 
 def workload(n_box):

@@ -66,6 +66,7 @@ def load_library(path=None):
         "btfem_get_strong_operators": (C.c_int, [H, _c_double_p, _c_double_p, _c_double_p]),
         "btfem_set_phase": (C.c_int, [H, _c_int32_p]),
         "btfem_get_mesh_stats": (C.c_int, [H, _c_double_p, _c_double_p]),
+        "btfem_get_bbox": (C.c_int, [H, _c_double_p, _c_double_p]),
         "btfem_set_diffusion": (C.c_int, [H, C.c_int, _c_double_p]),
         "btfem_set_relaxation": (C.c_int, [H, C.c_int, _c_double_p]),
         "btfem_set_permeability": (C.c_int, [H, C.c_int, _c_double_p, C.c_int32, _c_int32_p]),
@@ -184,6 +185,12 @@ class BTFem:
         lo, hi = C.c_double(), C.c_double()
         self._ck(self.lib.btfem_get_mesh_stats(self.h, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
+
+    def bbox(self):
+        """Bounding box of the vertices (btfem_get_bbox): (lo[3], hi[3])."""
+        lo, hi = np.zeros(3), np.zeros(3)
+        self._ck(self.lib.btfem_get_bbox(self.h, _dp(lo), _dp(hi)))
+        return lo, hi
 
     def set_diffusion(self, D):
         D = np.asarray(D, dtype=np.float64)

@@ -122,9 +122,15 @@ static void set_mesh_cells(btfem_t* h, int64_t nv, const double* xyz, int64_t nc
     }
     if (phase)
       for (int64_t i = 0; i < nc; ++i) bad_phase |= phase[i] & ~1;
-    h->h_xyz.assign(xyz, xyz + 3 * nv);
-    if (phase) h->h_phase.assign(phase, phase + nc); else h->h_phase.clear();
-    if (cell_nv == 4) h->h_tets.assign(cells, cells + 4 * nc);
+    h->h_xyz.assign(xyz, xyz + 3 * nv);   // kept: the periodic marker is evaluated on the host (setup.cu)
+    double lo3[3] = {xyz[0], xyz[1], xyz[2]}, hi3[3] = {xyz[0], xyz[1], xyz[2]};
+    for (int64_t v = 0; v < nv; ++v)      // bounding box (GetGlobalDomainSize, DmriFemLib.py:560-581)
+      for (int d = 0; d < 3; ++d) {
+        const double x = xyz[3 * v + d];
+        lo3[d] = x < lo3[d] ? x : lo3[d];
+        hi3[d] = x > hi3[d] ? x : hi3[d];
+      }
+    for (int d = 0; d < 3; ++d) { h->bbox_lo[d] = lo3[d]; h->bbox_hi[d] = hi3[d]; }
   });
   struct Joiner {
     std::thread& t;
@@ -137,10 +143,11 @@ static void set_mesh_cells(btfem_t* h, int64_t nv, const double* xyz, int64_t nc
     helper.join();
   } else {
     helper.join();
-    h->h_tets.assign(4 * nc, -1);   // triangles / segments keep the 4-slot cell layout, unused slots = -1
+    std::vector<int32_t> slots(4 * nc, -1);   // triangles / segments keep the 4-slot cell layout, unused slots = -1
     for (int64_t c = 0; c < nc; ++c)
-      for (int k = 0; k < cell_nv; ++k) h->h_tets[4 * c + k] = cells[cell_nv * c + k];
-    h->d_tets.upload(h->h_tets.data(), 4 * nc, h->stream);
+      for (int k = 0; k < cell_nv; ++k) slots[4 * c + k] = cells[cell_nv * c + k];
+    h->d_tets.upload(slots.data(), 4 * nc, h->stream);
+    BT_CUDA(cudaStreamSynchronize(h->stream));   // `slots` is a temporary
   }
   BT_CUDA(cudaStreamSynchronize(h->stream));
   if (!(lo >= 0 && hi < nv) || bad_phase) {
@@ -197,11 +204,9 @@ int btfem_set_phase(btfem_t* h, const int32_t* phase) {
     invalidate(h);
     h->two_comp = phase != nullptr;
     if (phase) {
-      h->h_phase.assign(phase, phase + h->nc);
       h->d_phase.upload(phase, h->nc, h->stream);
       BT_CUDA(cudaStreamSynchronize(h->stream));
     } else {
-      h->h_phase.clear();
       h->d_phase.release();
     }
   });
@@ -211,6 +216,13 @@ int btfem_get_mesh_stats(btfem_t* h, double* hmin, double* hmax) {
   return guarded(h, [&] {
     BT_REQUIRE(h->nc > 0 && hmin && hmax, "set the mesh first");
     bt_mesh_stats(h, hmin, hmax);
+  });
+}
+
+int btfem_get_bbox(btfem_t* h, double lo[3], double hi[3]) {
+  return guarded(h, [&] {
+    BT_REQUIRE(h->nv > 0 && lo && hi, "set the mesh first");
+    for (int d = 0; d < 3; ++d) { lo[d] = h->bbox_lo[d]; hi[d] = h->bbox_hi[d]; }
   });
 }
 

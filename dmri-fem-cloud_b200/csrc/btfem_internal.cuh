@@ -228,7 +228,7 @@ struct btfem {
   int cell_nv = 4;   // vertices per cell: 4 tetrahedra, 3 triangles, 2 segments (stored in 4 slots, unused = -1)
   bool two_comp = false;
   std::vector<double> h_xyz;
-  std::vector<int32_t> h_tets, h_phase;
+  double bbox_lo[3] = {0, 0, 0}, bbox_hi[3] = {0, 0, 0};   // bounding box of the vertices (btfem_get_bbox)
   int dkind = 0;
   std::vector<double> h_D{1.0};
   int t2kind = 0;

@@ -980,8 +980,15 @@ void bt_build_pattern(btfem* h) {
     std::vector<int4> pieces;
     int64_t unit = 0;
     int maxp = 0;
+    const int pad_max = getenv("BTFEM_PS_PAD") ? std::max(0, atoi(getenv("BTFEM_PS_PAD"))) : 0;   // experiment: units of 128 B
+    int64_t pad_total = 0;
     for (int w = 0; w < nw; ++w) {
       ptr[w] = (int32_t)pieces.size();
+      if (pad_max > 0) {   // de-correlate the start addresses of the warp streams (they are ~equally long)
+        const int64_t pad = (int64_t)(((uint32_t)w * 2654435761u) >> 16) % pad_max;
+        unit += pad;
+        pad_total += pad;
+      }
       for (int32_t s : lists[w]) {
         const int width = (slice_ptr[s + 1] - slice_ptr[s]) / 32;
         scol0[s] = (int32_t)unit;
@@ -997,7 +1004,7 @@ void bt_build_pattern(btfem* h) {
       maxp = std::max(maxp, (int)pieces.size() - ptr[w]);
     }
     ptr[nw] = (int32_t)pieces.size();
-    BT_REQUIRE(unit == (tot / 32) * BT_PS_COLU + nslice, "warp-stream layout does not cover the SELL storage");
+    BT_REQUIRE(unit - pad_total == (tot / 32) * BT_PS_COLU + nslice, "warp-stream layout does not cover the SELL storage");
     h->ps_blocks = nb;
     h->ps_units = unit;
     h->ps_max_pieces = maxp;

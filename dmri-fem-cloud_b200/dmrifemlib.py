@@ -249,10 +249,7 @@ class MyDomain():
         self.tol = 1e-2 * self.hmin
         self.gdim = mymesh.geometry().dim()
         self.tdim = mymesh.topology().dim()
-        xyz = mymesh.coordinates()
-        lo, hi = xyz.min(axis=0), xyz.max(axis=0)
-        if self.gdim == 2:                            # GetGlobalDomainSize: zmin = zmax = 0 (DmriFemLib.py:571)
-            lo, hi = np.append(lo, 0.0), np.append(hi, 0.0)
+        lo, hi = self._fem.bbox()                     # GetGlobalDomainSize (gdim 2: z = 0 was appended by set_mesh)
         self.xmin, self.ymin, self.zmin = (float(v) for v in lo)
         self.xmax, self.ymax, self.zmax = (float(v) for v in hi)
         print("Domain size: xmin=%f, ymin=%f, zmin=%f, xmax=%f, ymax=%f, zmax=%f" % (

@@ -95,6 +95,8 @@ int btfem_set_phase(btfem_t* h, const int32_t* phase /*[nc] or NULL*/);
 /* mesh.hmin()/hmax() as used by MyDomain (DmriFemLib.py:588-589): min / max over cells of the cell size,
  * cell size = longest edge (DOLFIN >= 2017 Cell::h, third party).  Computed on the GPU. */
 int btfem_get_mesh_stats(btfem_t* h, double* hmin, double* hmax);
+/* Bounding box of the vertices: GetGlobalDomainSize (DmriFemLib.py:560-581; MPI.min / MPI.max of the coordinates). */
+int btfem_get_bbox(btfem_t* h, double lo[3], double hi[3]);
 
 /* Diffusion: kind 0 = scalar D0 (`-K`, GCloudDmriSolver.py:212-215), 1 = per-cell scalar [nc],
  * 2 = per-cell full tensor [nc*9] row-major d00..d22 (ImposeDiffusionTensor, DmriFemLib.py:611-616). */

@@ -42,6 +42,10 @@ class FakeBTFem:
         _, _, hmin, hmax = orc.domain_sizes(orc.as_xyz3(self.xyz), self.tets)
         return hmin, hmax
 
+    def bbox(self):
+        x3 = orc.as_xyz3(self.xyz)
+        return x3.min(axis=0), x3.max(axis=0)
+
     def set_diffusion(self, D):
         self.D = D
 
