@@ -115,7 +115,16 @@ static void set_mesh_cells(btfem_t* h, int64_t nv, const double* xyz, int64_t nc
   // 11 M indices and 70 MB to upload).  Device kernels never see the mesh before the checks have passed: the handle
   // stays un-assembled and the error is raised below.
   int32_t lo = 0, hi = 0, bad_phase = 0;
+  const bool timing = getenv("BTFEM_TIMING") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[btfem] set_mesh: %-18s %7.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  };
   std::thread helper([&] {
+    auto h0 = std::chrono::steady_clock::now();
     for (int64_t i = 0; i < cell_nv * nc; ++i) {   // branch-free min/max passes: they vectorise
       lo = cells[i] < lo ? cells[i] : lo;
       hi = cells[i] > hi ? cells[i] : hi;
@@ -131,6 +140,9 @@ static void set_mesh_cells(btfem_t* h, int64_t nv, const double* xyz, int64_t nc
         hi3[d] = x > hi3[d] ? x : hi3[d];
       }
     for (int d = 0; d < 3; ++d) { h->bbox_lo[d] = lo3[d]; h->bbox_hi[d] = hi3[d]; }
+    if (timing)
+      fprintf(stderr, "[btfem] set_mesh: helper thread      %7.2f ms\n",
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
   });
   struct Joiner {
     std::thread& t;
@@ -138,9 +150,12 @@ static void set_mesh_cells(btfem_t* h, int64_t nv, const double* xyz, int64_t nc
   } joiner{helper};
   h->d_xyz.upload(xyz, 3 * nv, h->stream);
   if (phase) h->d_phase.upload(phase, nc, h->stream); else h->d_phase.release();
+  lap("xyz/phase enqueue");
   if (cell_nv == 4) {
     h->d_tets.upload(cells, 4 * nc, h->stream);
+    lap("tets enqueue");
     helper.join();
+    lap("join helper");
   } else {
     helper.join();
     std::vector<int32_t> slots(4 * nc, -1);   // triangles / segments keep the 4-slot cell layout, unused slots = -1
@@ -150,6 +165,7 @@ static void set_mesh_cells(btfem_t* h, int64_t nv, const double* xyz, int64_t nc
     BT_CUDA(cudaStreamSynchronize(h->stream));   // `slots` is a temporary
   }
   BT_CUDA(cudaStreamSynchronize(h->stream));
+  lap("stream sync");
   if (!(lo >= 0 && hi < nv) || bad_phase) {
     h->nv = h->nc = 0;   // nothing usable was set
     BT_REQUIRE(lo >= 0 && hi < nv, "cell vertex index out of range");

@@ -21,30 +21,34 @@ inline int bt_num_sms() {
   return cached[dev];
 }
 #define BT_NUM_SMS bt_num_sms()
-#define BT_MAX_PARTIALS 4096
+#define BT_MAX_PARTIALS 4096      // upper bound on the grid of any reducing kernel
+#define BT_SELL_SIGMA 1024        // sorting window (rows) of the SELL-32 layout
 // warp-stream layout of the operator for the TMA kernels (solve.cu): every warp of the launch owns a contiguous
-// byte stream of "pieces" (<= PS_W columns of one SELL slice: w x 32 int32 columns, then w x 32 value pairs, and --
-// behind the last piece of a slice -- the 32 row numbers of the slice), which it pulls through a ring of
-// shared-memory stages with cp.async.bulk + mbarrier.  Offsets are counted in units of 128 bytes.
+// byte stream of "pieces" (<= PS_W columns of one SELL slice: w x 32 column indices, then w x 32 value pairs, and --
+// behind the last piece of a slice -- the 32 row numbers), which it pulls through a ring of shared-memory stages with
+// cp.async.bulk + mbarrier.  Column indices are 16-bit offsets from a per-piece reference column (18 bytes per
+// nonzero) when every piece spans fewer than 65 536 columns -- the passes are bandwidth-bound -- else int32 (20 bytes).
+// Offsets are counted in units of 64 bytes.
 #define BT_PS_MAX_WARPS 16      // warps per block of the stream kernels: 8 (ring depth 4), 12 (3) or 16 (2)
 #define BT_PS_W 8               // columns per piece
-#define BT_PS_COLU 5            // 128-byte units per stream column: 32 lanes x (4 + 16) bytes
-#define BT_PS_STAGE ((BT_PS_W * BT_PS_COLU + 1) * 128)   // bytes of a ring stage: a full piece + the row block
-// byte offset of column j (< width) of a slice whose stream starts at unit u0: piece p = j / W starts at u0 + p W 5
-__host__ __device__ inline size_t bt_ps_col_off(int64_t u0, int j, int lane) {
+#define BT_PS_STAGE ((BT_PS_W * 10 + 2) * 64)   // bytes of a ring stage: a full int32 piece + the row block
+// 64-byte units per stream column: 32 lanes x (2 | 4 bytes of column + 16 bytes of values)
+__host__ __device__ inline int bt_ps_colu(bool c16) { return c16 ? 9 : 10; }
+// byte offset of column j (< width) of a slice whose stream starts at unit u0: piece p = j / W starts at u0 + p W colu
+__host__ __device__ inline size_t bt_ps_col_off(int64_t u0, int j, int lane, bool c16) {
   const int p = j / BT_PS_W;
-  return (size_t)(u0 + (int64_t)p * BT_PS_W * BT_PS_COLU) * 128 + (size_t)(j - p * BT_PS_W) * 128 + (size_t)lane * 4;
+  return (size_t)(u0 + (int64_t)p * BT_PS_W * bt_ps_colu(c16)) * 64 + (size_t)(j - p * BT_PS_W) * (c16 ? 64 : 128) +
+         (size_t)lane * (c16 ? 2 : 4);
 }
-__host__ __device__ inline size_t bt_ps_val_off(int64_t u0, int width, int j, int lane) {
+__host__ __device__ inline size_t bt_ps_val_off(int64_t u0, int width, int j, int lane, bool c16) {
   const int p = j / BT_PS_W;
   const int w = width - p * BT_PS_W < BT_PS_W ? width - p * BT_PS_W : BT_PS_W;
-  return (size_t)(u0 + (int64_t)p * BT_PS_W * BT_PS_COLU) * 128 + (size_t)w * 128 + (size_t)(j - p * BT_PS_W) * 512 +
-         (size_t)lane * 16;
+  return (size_t)(u0 + (int64_t)p * BT_PS_W * bt_ps_colu(c16)) * 64 + (size_t)w * (c16 ? 64 : 128) +
+         (size_t)(j - p * BT_PS_W) * 512 + (size_t)lane * 16;
 }
-__host__ __device__ inline size_t bt_ps_row_off(int64_t u0, int width, int lane) {   // behind the last piece
-  return (size_t)(u0 + (int64_t)(width > 0 ? width : 0) * BT_PS_COLU) * 128 + (size_t)lane * 4;
+__host__ __device__ inline size_t bt_ps_row_off(int64_t u0, int width, int lane, bool c16) {   // behind the last piece
+  return (size_t)(u0 + (int64_t)(width > 0 ? width : 0) * bt_ps_colu(c16)) * 64 + (size_t)lane * 4;
 }
-#define BT_SELL_SIGMA 1024      // sorting window (rows) of the SELL-32 layout    // upper bound on the grid of any reducing kernel
 
 struct BtError {
   int code;
@@ -297,12 +301,14 @@ struct btfem {
   // warp-stream copy of the SELL operator (whole-mesh handles; built with the pattern, filled by bt_combine)
   int ps_blocks = 0;               // blocks (= SMs) the layout was built for; 0 = none
   int ps_warps = 8;                // warps per block the layout was built for
-  int64_t ps_units = 0;            // length of a stream in 128-byte units
+  int64_t ps_units = 0;            // length of a stream in 64-byte units
+  bool ps_col16 = false;           // 16-bit column offsets from a per-piece reference column
   int ps_max_pieces = 0;           // longest piece list of a warp
   DevArray<int32_t> d_ps_ptr;      // [ps_blocks * ps_warps + 1] piece range of every warp
-  DevArray<int4> d_ps_piece;       // {stream offset (units), columns, slice, 1 = last piece of its slice}
+  DevArray<int4> d_ps_piece;       // {stream offset (units), columns, slice, reference column << 1 | last piece of its slice}
   DevArray<int32_t> d_ps_scol0;    // [n_slice] stream offset (units) of the first piece of the slice
-  DevArray<unsigned char> d_PJt, d_QJt;   // [ps_units * 128] per-solve operator values + columns + rows, stream order
+  DevArray<int32_t> d_ps_first;    // [n_slice] index of the slice's first piece in d_ps_piece
+  DevArray<unsigned char> d_PJt, d_QJt;   // [ps_units * 64] per-solve operator values + columns + rows, stream order
   DevArray<uint32_t> d_src;        // contribution ids sorted by (row,col), stable
   DevArray<int64_t> d_seg;         // [nnz+1] segment offsets into d_src
   DevArray<double> d_vals[8];      // M,S,R,Jx,Jy,Jz,I,B

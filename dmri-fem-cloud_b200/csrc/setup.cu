@@ -288,18 +288,45 @@ __global__ void k_sell_columns(int64_t nslice, const int32_t* __restrict__ slice
   const int row = sell_row[slot];
   const int k0 = row >= 0 ? rowptr[row] : 0;
   const int len = row >= 0 ? rowptr[row + 1] - k0 : 0;
+  const int pad_col = row >= 0 ? row : max(sell_row[s * 32], 0);   // empty slots point at a row of their own slice
   for (int j = 0; j < width; ++j) {
-    int c = j < len ? colidx[k0 + j] : (row >= 0 ? row : 0);
+    int c = j < len ? colidx[k0 + j] : pad_col;
     if (c >= n_own) c += halo_shift;
     sell_col[base + j * 32 + lane] = c;
   }
 }
 
-// Warp-stream layout: the column indices and the row numbers of every slice go to their place in BOTH operator
-// streams (PJt, QJt); the values follow per solve (solve.cu: k_combine).  Offsets: bt_ps_*_off (btfem_internal.cuh).
+// Warp-stream layout.  Largest column spread of a piece (<= BT_PS_W columns x 32 rows of a slice): decides whether
+// 16-bit column offsets fit.  One warp per slice.
+__global__ void k_stream_spread(int64_t nslice, const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ sell_col,
+                                int32_t* __restrict__ max_spread) {
+  const int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= nslice) return;
+  const int base = slice_ptr[s];
+  const int width = (slice_ptr[s + 1] - base) >> 5;
+  int worst = 0;
+  for (int j0 = 0; j0 < width; j0 += BT_PS_W) {
+    int lo = 0x7fffffff, hi = 0;
+    for (int j = j0; j < min(width, j0 + BT_PS_W); ++j) {
+      const int c = sell_col[base + j * 32 + lane];
+      lo = min(lo, c);
+      hi = max(hi, c);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    worst = max(worst, hi - lo);
+  }
+  if (lane == 0) atomicMax(max_spread, worst);
+}
+
+// The column indices and the row numbers of every slice go to their place in BOTH operator streams (PJt, QJt); the
+// values follow per solve (solve.cu: k_combine).  Offsets: bt_ps_*_off (btfem_internal.cuh).  One warp per slice; with
+// 16-bit columns the reference column of a piece (its smallest column) goes into the piece descriptor.
 __global__ void k_stream_columns(int64_t nslice, const int32_t* __restrict__ slice_ptr,
                                  const int32_t* __restrict__ sell_col, const int32_t* __restrict__ sell_row,
-                                 const int32_t* __restrict__ scol0, unsigned char* __restrict__ PJt,
+                                 const int32_t* __restrict__ scol0, const int32_t* __restrict__ first_piece, int c16,
+                                 int4* __restrict__ pieces, unsigned char* __restrict__ PJt,
                                  unsigned char* __restrict__ QJt) {
   int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (slot >= nslice * 32) return;
@@ -308,13 +335,31 @@ __global__ void k_stream_columns(int64_t nslice, const int32_t* __restrict__ sli
   const int base = slice_ptr[s];
   const int width = (slice_ptr[s + 1] - base) >> 5;
   const int64_t u0 = scol0[s];
-  for (int j = 0; j < width; ++j) {
-    const size_t off = bt_ps_col_off(u0, j, lane);
-    const int c = sell_col[base + j * 32 + lane];
-    *reinterpret_cast<int32_t*>(PJt + off) = c;
-    *reinterpret_cast<int32_t*>(QJt + off) = c;
+  for (int j0 = 0, p = 0; j0 < width; j0 += BT_PS_W, ++p) {
+    const int j1 = min(width, j0 + BT_PS_W);
+    int ref = 0;
+    if (c16) {
+      int lo = 0x7fffffff;
+      for (int j = j0; j < j1; ++j) lo = min(lo, sell_col[base + j * 32 + lane]);
+      ref = __reduce_min_sync(0xffffffffu, lo);
+      if (lane == 0) {
+        int4* d = pieces + first_piece[s] + p;
+        d->w = (ref << 1) | (d->w & 1);
+      }
+    }
+    for (int j = j0; j < j1; ++j) {
+      const size_t off = bt_ps_col_off(u0, j, lane, c16 != 0);
+      const int c = sell_col[base + j * 32 + lane];
+      if (c16) {
+        *reinterpret_cast<uint16_t*>(PJt + off) = (uint16_t)(c - ref);
+        *reinterpret_cast<uint16_t*>(QJt + off) = (uint16_t)(c - ref);
+      } else {
+        *reinterpret_cast<int32_t*>(PJt + off) = c;
+        *reinterpret_cast<int32_t*>(QJt + off) = c;
+      }
+    }
   }
-  const size_t roff = bt_ps_row_off(u0, width, lane);
+  const size_t roff = bt_ps_row_off(u0, width, lane, c16 != 0);
   const int row = sell_row[slot];
   *reinterpret_cast<int32_t*>(PJt + roff) = row;
   *reinterpret_cast<int32_t*>(QJt + roff) = row;
@@ -978,45 +1023,56 @@ void bt_build_pattern(btfem* h) {
     }
     std::vector<int32_t> ptr(nw + 1, 0), scol0(nslice, 0);
     std::vector<int4> pieces;
+    // 16-bit column offsets (18 instead of 20 bytes per nonzero) when no piece spans 65 536 columns or more
+    bool c16 = false;
+    if (!getenv("BTFEM_PS_COL32")) {
+      DevArray<int32_t> d_spread;
+      d_spread.alloc(1);
+      d_spread.zero(st);
+      k_stream_spread<<<nblocks(nslice * 32), TPB, 0, st>>>(nslice, h->d_slice_ptr.p, h->d_sell_col.p, d_spread.p);
+      int32_t spread = 0;
+      d_spread.download(&spread, st);
+      c16 = spread < 65536;
+      if (timing) fprintf(stderr, "[btfem]   warp streams: widest piece spans %d columns -> %d-bit column entries\n", spread, c16 ? 16 : 32);
+    }
+    const int colu = bt_ps_colu(c16);
+    std::vector<int32_t> first(nslice, 0);
     int64_t unit = 0;
     int maxp = 0;
-    const int pad_max = getenv("BTFEM_PS_PAD") ? std::max(0, atoi(getenv("BTFEM_PS_PAD"))) : 0;   // experiment: units of 128 B
-    int64_t pad_total = 0;
     for (int w = 0; w < nw; ++w) {
       ptr[w] = (int32_t)pieces.size();
-      if (pad_max > 0) {   // de-correlate the start addresses of the warp streams (they are ~equally long)
-        const int64_t pad = (int64_t)(((uint32_t)w * 2654435761u) >> 16) % pad_max;
-        unit += pad;
-        pad_total += pad;
-      }
       for (int32_t s : lists[w]) {
         const int width = (slice_ptr[s + 1] - slice_ptr[s]) / 32;
         scol0[s] = (int32_t)unit;
+        first[s] = (int32_t)pieces.size();
         if (width == 0) pieces.push_back(make_int4((int)unit, 0, s, 1));   // rows without entries: the row block only
         for (int j = 0; j < width; j += BT_PS_W) {
           const int wd = std::min(BT_PS_W, width - j);
-          pieces.push_back(make_int4((int)unit, wd, s, j + wd >= width ? 1 : 0));
-          unit += wd * BT_PS_COLU;
+          pieces.push_back(make_int4((int)unit, wd, s, j + wd >= width ? 1 : 0));   // .w: reference column << 1 | last
+          unit += wd * colu;
         }
-        unit += 1;   // the row block
+        unit += 2;   // the row block (128 bytes)
         BT_REQUIRE(unit < (int64_t)0x7fffffffLL, "warp-stream storage exceeds int32 units");
       }
       maxp = std::max(maxp, (int)pieces.size() - ptr[w]);
     }
     ptr[nw] = (int32_t)pieces.size();
-    BT_REQUIRE(unit - pad_total == (tot / 32) * BT_PS_COLU + nslice, "warp-stream layout does not cover the SELL storage");
+    BT_REQUIRE(unit == (tot / 32) * colu + 2 * nslice, "warp-stream layout does not cover the SELL storage");
     h->ps_blocks = nb;
     h->ps_units = unit;
+    h->ps_col16 = c16;
     h->ps_max_pieces = maxp;
     h->d_ps_ptr.upload(ptr.data(), ptr.size(), st);
     h->d_ps_piece.upload(pieces.data(), pieces.size(), st);
     h->d_ps_scol0.upload(scol0.data(), scol0.size(), st);
-    h->d_PJt.alloc((size_t)unit * 128 + 16);
-    h->d_QJt.alloc((size_t)unit * 128 + 16);
+    h->d_ps_first.upload(first.data(), first.size(), st);
+    h->d_PJt.alloc((size_t)unit * 64 + 16);
+    h->d_QJt.alloc((size_t)unit * 64 + 16);
     h->d_PJt.zero(st);
     h->d_QJt.zero(st);
     k_stream_columns<<<nblocks(nslice * 32), TPB, 0, st>>>(nslice, h->d_slice_ptr.p, h->d_sell_col.p, h->d_sell_row.p,
-                                                          h->d_ps_scol0.p, h->d_PJt.p, h->d_QJt.p);
+                                                          h->d_ps_scol0.p, h->d_ps_first.p, c16 ? 1 : 0, h->d_ps_piece.p,
+                                                          h->d_PJt.p, h->d_QJt.p);
     BT_CUDA(cudaGetLastError());
     BT_CUDA(cudaStreamSynchronize(st));   // host vectors above go out of scope
   }

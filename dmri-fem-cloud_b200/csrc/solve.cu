@@ -242,7 +242,7 @@ __global__ void k_combine(int64_t nnz, const int32_t* __restrict__ rowidx, const
                           double* __restrict__ Bhat, const int32_t* __restrict__ rowptr,
                           const int32_t* __restrict__ sell_slot, const int32_t* __restrict__ slice_ptr,
                           double2* __restrict__ PJs, double2* __restrict__ QJs, const int32_t* __restrict__ scol0,
-                          unsigned char* __restrict__ PJt, unsigned char* __restrict__ QJt) {
+                          unsigned char* __restrict__ PJt, unsigned char* __restrict__ QJt, int c16) {
   int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (k >= nnz) return;
   double di = dinv[rowidx[k]];
@@ -265,7 +265,7 @@ __global__ void k_combine(int64_t nnz, const int32_t* __restrict__ rowidx, const
     QJs[pos] = qj;
     if (PJt) {   // and in the warp-stream layout (setup.cu: k_stream_columns)
       const int width = (slice_ptr[(slot >> 5) + 1] - sbase) >> 5;
-      const size_t off = bt_ps_val_off(scol0[slot >> 5], width, j, slot & 31);
+      const size_t off = bt_ps_val_off(scol0[slot >> 5], width, j, slot & 31, c16 != 0);
       *reinterpret_cast<double2*>(PJt + off) = pj;
       *reinterpret_cast<double2*>(QJt + off) = qj;
     }
@@ -339,6 +339,7 @@ struct SpmvArgs {
   // warp-stream kernels (k_spmv_stream, persistent BiCGStab): see btfem_internal.cuh / setup.cu
   int ps_blocks;             // 0: layout not usable for this solve
   int ps_warps;              // warps per block of the layout
+  int ps_c16;                // 16-bit column offsets from the piece's reference column
   int ps_l2ahead;            // persistent kernel: pieces per warp prefetched into L2 for the next pass when a pass ends
   const int32_t* ps_ptr;     // [ps_blocks * BT_PS_WARPS + 1]
   const int4* ps_piece;      // {stream column, columns, slice, last}
@@ -840,9 +841,11 @@ struct WarpRing {
   uint32_t buf_s, bar_s;  // shared-window addresses of the stages / of the D barriers
   const int4* pieces;     // this warp's list
   int np;
+  int colu;               // 64-byte units per stream column: 9 (16-bit columns) or 10
   unsigned long long l2_evict_first;
 
-  __device__ __forceinline__ void setup(unsigned char* smem, const int32_t* ps_ptr, const int4* ps_piece) {
+  __device__ __forceinline__ void setup(unsigned char* smem, const int32_t* ps_ptr, const int4* ps_piece, int c16) {
+    colu = bt_ps_colu(c16 != 0);
     const int wl = threadIdx.x >> 5;
     buf = smem + (size_t)wl * D * PS_STAGE;
     buf_s = smem_u32(buf);
@@ -865,22 +868,22 @@ struct WarpRing {
   __device__ __forceinline__ void fetch(const unsigned char* T, int idx, unsigned int c) const {
     const int4 d = __ldg(pieces + idx);
     const unsigned int st = c % D;
-    const uint32_t bytes = (uint32_t)(d.y * BT_PS_COLU + d.w) * 128u;
+    const uint32_t bytes = (uint32_t)(d.y * colu + 2 * (d.w & 1)) * 64u;
     const uint32_t bar = bar_s + 8 * st;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
     // the operator streams past once per SpMV: evict-first in L2, which keeps the Krylov vectors resident
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
             buf_s + st * PS_STAGE),
-        "l"(T + (size_t)d.x * 128), "r"(bytes), "r"(bar), "l"(l2_evict_first)
+        "l"(T + (size_t)d.x * 64), "r"(bytes), "r"(bar), "l"(l2_evict_first)
         : "memory");
   }
   // lane 0: pull list entries [i0, i1) of stream T into L2 (no shared-memory stage involved)
   __device__ __forceinline__ void prefetch_l2(const unsigned char* T, int i0, int i1) const {
     for (int i = i0; i < i1 && i < np; ++i) {
       const int4 d = __ldg(pieces + i);
-      const uint32_t bytes = (uint32_t)(d.y * BT_PS_COLU + d.w) * 128u;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(T + (size_t)d.x * 128), "r"(bytes) : "memory");
+      const uint32_t bytes = (uint32_t)(d.y * colu + 2 * (d.w & 1)) * 64u;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(T + (size_t)d.x * 64), "r"(bytes) : "memory");
     }
   }
   __device__ __forceinline__ void wait(unsigned int c) const { mbar_wait(bar_s + 8 * (c % D), (c / D) & 1u); }
@@ -919,12 +922,21 @@ __device__ __forceinline__ void piece_gather(const double2* opv, const WarpRing<
   q.d = __ldg(r.pieces + idx);
   r.wait(c);
   const unsigned char* sp = r.stage(c);
-  const int32_t* cs = reinterpret_cast<const int32_t*>(sp) + (threadIdx.x & 31);
+  const int lane = threadIdx.x & 31;
+  if (r.colu == 9) {   // 16-bit offsets from the reference column of the piece
+    const uint16_t* cs = reinterpret_cast<const uint16_t*>(sp) + lane;
+    const int ref = q.d.w >> 1;
 #pragma unroll
-  for (int j = 0; j < BT_PS_W; ++j)
-    if (j < q.d.y) q.xv[j] = ldv_gather_f64x2(x + cs[j * 32]);
-  if (q.d.w) {
-    q.row = cs[q.d.y * BT_PS_COLU * 32];
+    for (int j = 0; j < BT_PS_W; ++j)
+      if (j < q.d.y) q.xv[j] = ldv_gather_f64x2(x + (ref + (int)cs[j * 32]));
+  } else {
+    const int32_t* cs = reinterpret_cast<const int32_t*>(sp) + lane;
+#pragma unroll
+    for (int j = 0; j < BT_PS_W; ++j)
+      if (j < q.d.y) q.xv[j] = ldv_gather_f64x2(x + cs[j * 32]);
+  }
+  if (q.d.w & 1) {
+    q.row = reinterpret_cast<const int32_t*>(sp + (size_t)q.d.y * r.colu * 64)[lane];
     q.op = make_double2(0.0, 0.0);
     if (q.row >= 0 && opv) q.op = opv[q.row];
   }
@@ -933,7 +945,7 @@ __device__ __forceinline__ void piece_gather(const double2* opv, const WarpRing<
 template <int D>
 __device__ __forceinline__ void piece_fma(const WarpRing<D>& r, unsigned int c, double cc, const PieceRegs& q,
                                           double& ar, double& ai) {
-  const double2* vs = reinterpret_cast<const double2*>(r.stage(c) + q.d.y * 128) + (threadIdx.x & 31);
+  const double2* vs = reinterpret_cast<const double2*>(r.stage(c) + q.d.y * (r.colu == 9 ? 64 : 128)) + (threadIdx.x & 31);
 #pragma unroll
   for (int j = 0; j < BT_PS_W; ++j)
     if (j < q.d.y) {
@@ -962,7 +974,7 @@ __device__ __forceinline__ unsigned int stream_pass(const SpmvArgs& a, int mode,
   double ar = 0.0, ai = 0.0;
   PieceRegs q[G];   // gathers of G - 1 pieces are in flight while one piece is multiplied
   auto finish = [&](int k, const PieceRegs& qq) {   // piece k is done: epilogue of its slice, refill of its stage
-    if (qq.d.w) {
+    if (qq.d.w & 1) {
       if (qq.row >= 0) row_epilogue_rt(a, mode, qq.row, make_double2(ar, ai), qq.op, acc);
       ar = 0.0;
       ai = 0.0;
@@ -1005,7 +1017,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_spmv_stream(SpmvArgs a) {
   if (m.skip) return;
   const unsigned char* T = MODE == MODE_RHS ? a.QJt : a.PJt;
   WarpRing<D> r;
-  r.setup(ps_ring, a.ps_ptr, a.ps_piece);
+  r.setup(ps_ring, a.ps_ptr, a.ps_piece, a.ps_c16);
   if ((threadIdx.x & 31) == 0)
     for (int i = 0; i < D && i < r.np; ++i) r.fetch(T, i, (unsigned int)i);
   double acc[2] = {0.0, 0.0};
@@ -1208,7 +1220,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_bicgstab_persistent(SpmvArgs a) 
     S.tprev = tn_;                                \
   }
   WarpRing<D> r;
-  r.setup(ps_ring, a.ps_ptr, a.ps_piece);
+  r.setup(ps_ring, a.ps_ptr, a.ps_piece, a.ps_c16);
   const int nfl = min(D, r.np);   // pieces of the next pass that are in flight between two passes
   unsigned int c = 0;             // ring piece counter of this warp
   if (lane == 0)
@@ -2404,6 +2416,7 @@ SpmvArgs base_args(btfem* h) {
   if (bt_stream_kernel_usable(h) && h->comb_members == 1 && h->comb_dt > 0) {
     a.ps_blocks = h->ps_blocks;
     a.ps_warps = h->ps_warps;
+    a.ps_c16 = h->ps_col16 ? 1 : 0;
     {
       static const int ahead = getenv("BTFEM_PS_L2AHEAD") ? std::max(0, atoi(getenv("BTFEM_PS_L2AHEAD"))) : 0;
       a.ps_l2ahead = ahead;
@@ -2621,7 +2634,8 @@ void bt_combine(btfem* h, double dt, double theta, const double g[3], int pc, in
       h->periodic ? h->d_Bhat.p : nullptr, h->d_rowptr.p, h->d_sell_slot.p, h->d_slice_ptr.p,
       h->n_slice ? h->d_PJs.p + (size_t)member * h->nnz_sell : nullptr,
       h->n_slice ? h->d_QJs.p + (size_t)member * h->nnz_sell : nullptr,
-      h->d_ps_scol0.p, (single && h->ps_blocks) ? h->d_PJt.p : nullptr, (single && h->ps_blocks) ? h->d_QJt.p : nullptr);
+      h->d_ps_scol0.p, (single && h->ps_blocks) ? h->d_PJt.p : nullptr, (single && h->ps_blocks) ? h->d_QJt.p : nullptr,
+      h->ps_col16 ? 1 : 0);
   BT_CUDA(cudaGetLastError());
   h->comb_members = members;
   h->comb_dt = dt; h->comb_theta = theta; h->comb_pc = pc;
@@ -3091,8 +3105,8 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
           long long cols = 0, slices = 0, se = 0, li = 0;
           for (int k = pp[i]; k < pp[i + 1]; ++k) {
             cols += pc[k].y;
-            slices += pc[k].w;
-            if (pc[k].w) { se += sect[pc[k].z]; li += line[pc[k].z]; }
+            slices += pc[k].w & 1;
+            if (pc[k].w & 1) { se += sect[pc[k].z]; li += line[pc[k].z]; }
           }
           fprintf(f, "%zu %llu %d %lld %lld %llu %lld %lld\n", i, w[i], pp[i + 1] - pp[i], cols, slices, sm[i / a.ps_warps],
                   se, li);
