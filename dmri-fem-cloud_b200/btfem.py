@@ -86,6 +86,7 @@ def load_library(path=None):
         "btfem_set_lanes": (C.c_int, [H, C.c_int32]),
         "btfem_get_spmv_kernel": (C.c_int, [H, _c_int32_p]),
         "btfem_get_ilu_factors": (C.c_int, [H, _c_double_p]),
+        "btfem_set_sm_partition": (C.c_int, [H, C.c_int32]),
         "btfem_solve": (C.c_int, [H, C.POINTER(SolveArgs), C.POINTER(SolveOut), _c_int32_p]),
         "btfem_solve_batch": (C.c_int, [H, C.c_int32, C.POINTER(SolveArgs), C.POINTER(SolveOut)]),
         "btfem_get_solution": (C.c_int, [H, _c_double_p]),
@@ -265,6 +266,11 @@ class BTFem:
 
     def set_lanes(self, lanes):
         self._ck(self.lib.btfem_set_lanes(self.h, int(lanes)))
+
+    def set_sm_partition(self, nblocks):
+        """The persistent kernel of this handle runs on `nblocks` SMs (0 = all): several handles with disjoint shares
+        solve concurrently on one GPU (btfem_set_sm_partition).  Call before assemble()."""
+        self._ck(self.lib.btfem_set_sm_partition(self.h, int(nblocks)))
 
     @property
     def spmv_kernel(self):

@@ -437,6 +437,16 @@ int btfem_get_spmv_kernel(btfem_t* h, int32_t* kind) {
   });
 }
 
+int btfem_set_sm_partition(btfem_t* h, int32_t nblocks) {
+  return guarded(h, [&] {
+    BT_REQUIRE(nblocks >= 0 && nblocks <= BT_NUM_SMS, "SM partition: 0 (all) .. number of SMs of the device");
+    if (nblocks != h->ps_req_blocks) {
+      h->ps_req_blocks = nblocks;
+      invalidate(h);   // the warp-stream layout belongs to one launch shape
+    }
+  });
+}
+
 int btfem_get_ilu_factors(btfem_t* h, double* out) {
   return guarded(h, [&] {
     BT_REQUIRE(out, "null argument");

@@ -299,6 +299,7 @@ struct btfem {
   DevArray<double2> d_PQs, d_Jxys;
   DevArray<double> d_Jzs, d_gdirs /*[members*3]*/;
   // warp-stream copy of the SELL operator (whole-mesh handles; built with the pattern, filled by bt_combine)
+  int ps_req_blocks = 0;           // btfem_set_sm_partition: blocks the stream kernels may use (0 = all SMs)
   int ps_blocks = 0;               // blocks (= SMs) the layout was built for; 0 = none
   int ps_warps = 8;                // warps per block the layout was built for
   int64_t ps_units = 0;            // length of a stream in 64-byte units

@@ -972,7 +972,7 @@ void bt_build_pattern(btfem* h) {
   if (h->nv_own < 0 && nslice > 0 && !getenv("BTFEM_NO_STREAM")) {
     const char* w_env = getenv("BTFEM_PS_WARPS");   // warps per block of the stream kernels: 8, 12 or 16
     const int wpb = (w_env && (atoi(w_env) == 12 || atoi(w_env) == 16)) ? atoi(w_env) : 8;
-    const int nb = BT_NUM_SMS, nw = nb * wpb;
+    const int nb = h->ps_req_blocks > 0 ? std::min(h->ps_req_blocks, (int)BT_NUM_SMS) : (int)BT_NUM_SMS, nw = nb * wpb;
     h->ps_warps = wpb;
     // Dealing: chunks of wpb consecutive slices stay together on one block (its warps work on neighbouring rows at
     // the same time and share the gathered x lines in L1), but the chunks are dealt in a scrambled order, each to the

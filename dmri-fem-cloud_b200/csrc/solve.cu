@@ -2600,7 +2600,8 @@ int gmres_solve_step(btfem* h, const btfem_solve_args* sa, SpmvArgs a, double cA
 
 bool bt_stream_kernel_usable(const btfem* h) {
   static const bool off = getenv("BTFEM_NO_STREAM_KERNEL") != nullptr;
-  return !off && h->nv_own < 0 && h->ps_blocks > 0 && h->ps_blocks == BT_NUM_SMS;
+  const int want = h->ps_req_blocks > 0 ? std::min(h->ps_req_blocks, (int)BT_NUM_SMS) : (int)BT_NUM_SMS;
+  return !off && h->nv_own < 0 && h->ps_blocks > 0 && h->ps_blocks == want;
 }
 
 // Operator values of batch member `member` (of `members`): the value arrays hold `members` copies back to back.
@@ -2940,7 +2941,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   // BTFEM_PERSIST=0 falls back to the kernel chain in a WHILE graph.
   const char* pers_env = getenv("BTFEM_PERSIST");
   const bool persist = dev_loop && !part && !strong && members == 1 && lanes == 0 && !sa->nonzero_guess &&
-                       a.ps_blocks > 0 && a.ps_blocks == BT_NUM_SMS && !(pers_env && pers_env[0] == '0');
+                       a.ps_blocks > 0 && a.ps_blocks <= BT_NUM_SMS && !(pers_env && pers_env[0] == '0');
   const void* pers_fn = a.ps_warps == 16   ? (const void*)k_bicgstab_persistent<16, 2, 2>
                         : a.ps_warps == 12 ? (const void*)k_bicgstab_persistent<12, 3, 2>
                         : ps_deep()        ? (const void*)k_bicgstab_persistent<8, 5, 3>

@@ -70,6 +70,83 @@ def run_sweep(fem, mri_para, sim, directions, bvalues, linsolver_params, rank=0,
     return mine, np.array(out)
 
 
+def make_concurrent_handles(make_fem, n_handles, n_sms=148):
+    """`n_handles` assembled btfem.BTFem objects on ONE GPU, each confined to its share of the SMs
+    (btfem_set_sm_partition): their persistent time-loop kernels run side by side, so that a sweep over a mesh too
+    small to fill the device keeps every SM and the whole memory system busy.  make_fem(fem) sets mesh and coefficients
+    on a fresh handle (not assemble)."""
+    from . import btfem as _bt
+    fems = []
+    share = max(1, n_sms // n_handles)
+    try:
+        for _ in range(n_handles):
+            fem = _bt.BTFem(make_fem.device if hasattr(make_fem, "device") else 0)
+            fems.append(fem)
+            fem.set_sm_partition(share)
+            make_fem(fem)
+            fem.assemble()
+    except Exception:
+        for fem in fems:
+            fem.close()
+        raise
+    return fems
+
+
+def run_sweep_concurrent(fems, mri_para, sim, directions, bvalues, linsolver_params, rank=0, world=1):
+    """Like run_sweep, with the rank's units solved CONCURRENTLY: one host thread per handle of `fems`
+    (make_concurrent_handles) takes the next unit from a shared queue (largest b first: those solves take the most
+    iterations) and runs it as one persistent-kernel launch on the handle's SM share.  Which handle solves a unit does
+    not change its bits (all handles have the same launch shape)."""
+    import queue
+    import threading
+    units = sweep_units(directions, bvalues)
+    mine = shard_balanced(len(directions), len(bvalues), rank, world)
+    ts = sim.time_grid(mri_para)
+    tps = np.concatenate([[0.0], ts[:-1]])
+    mri_para.bvalue, mri_para.gvalue = bvalues[0], None
+    mri_para.Apply()
+    f, _ = mri_para.profiles_on_grid(ts)
+    fp, Fp = mri_para.profiles_on_grid(tps)
+    qs = []
+    for b in bvalues:
+        mri_para.bvalue, mri_para.gvalue = b, None
+        qs.append(mri_para.convert_b2q())
+    order = sorted(range(len(mine)), key=lambda k: (-bvalues[units[mine[k]][1]], k))
+    todo = queue.Queue()
+    for k in order:
+        todo.put(k)
+    out = np.zeros(len(mine))
+    errors = []
+    stats = []            # (loop ms, set-up ms, iterations) per solve, for diagnostics: run_sweep_concurrent.last_stats
+
+    def worker(fem):
+        while True:
+            try:
+                k = todo.get_nowait()
+            except queue.Empty:
+                return
+            i, j = units[mine[k]]
+            g = np.asarray(directions[i], dtype=float)
+            try:
+                res = fem.solve(sim.k, sim.theta, qs[j] * f, qs[j] * fp, g / np.linalg.norm(g), q=qs[j], Fb=Fp,
+                                **linsolver_params)
+                out[k] = res["signal"] / res["voi"]
+                stats.append((res["loop_ms"], res["setup_ms"], res["total_iters"]))
+            except Exception as exc:          # keep the other workers going; report below
+                errors.append(exc)
+                return
+
+    threads = [threading.Thread(target=worker, args=(fem,)) for fem in fems]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    run_sweep_concurrent.last_stats = np.array(stats, dtype=float)
+    return mine, out
+
+
 def gather_signals(n_units, mine, signals, dist=None):
     """Assemble the full signal table on every rank.  dist: an initialised torch.distributed module
     (gloo or nccl) or None for a single process."""

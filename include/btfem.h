@@ -157,6 +157,12 @@ int btfem_set_lanes(btfem_t* h, int32_t lanes);
  * 1 = SELL-32, register-staged loads (k_spmv_sell); 2 = SELL-32 through per-warp TMA rings (k_spmv_stream:
  * cp.async.bulk + mbarrier).  Bench / profiling hook; the reference has no counterpart (PETSc MatMult). */
 int btfem_get_spmv_kernel(btfem_t* h, int32_t* kind);
+/* SM partition: the persistent time-loop kernel of this handle runs on `nblocks` SMs (one block each; 0 = all SMs of
+ * the device).  Several handles with disjoint shares -- e.g. 16 x 9 SMs of a B200 -- solve CONCURRENTLY on one GPU,
+ * each from its own host thread on its own stream: the serial loops over directions / b-values around `solve`
+ * (ExplicitImplementation.ipynb cell 10) on meshes too small to fill the device.  Set before btfem_assemble (the
+ * operator's warp-stream layout is built for this launch shape). */
+int btfem_set_sm_partition(btfem_t* h, int32_t nblocks);
 /* Parity hook: the ILU(0) factors of the last solve with BTFEM_PC_ILU, (re,im) per CSR nonzero (unit-lower L below the
  * diagonal, U on and above it -- one array, like PETSc's factored AIJ matrix).  out[2*nnz]. */
 int btfem_get_ilu_factors(btfem_t* h, double* out);

@@ -32,17 +32,32 @@ sim = dl.MRI_simulation()
 sim.k = 200.0
 dirs = meshes.fibonacci_hemisphere(ndir)
 bvals = [1000.0, 2000.0, 3000.0, 4000.0]
-fem = btfem.BTFem(local_rank)
-fem.set_mesh(xyz, tets)
-fem.set_diffusion(3e-3)
-fem.set_relaxation(1e-16)
-fem.assemble()
+concurrent = int(sys.argv[3]) if len(sys.argv) > 3 else 0      # > 0: that many handles, each on its share of the SMs
 par = dict(rtol=1e-9, atol=1e-10, maxit=100000)
-sweep.run_sweep(fem, mp, sim, dirs[:2], bvals[:2], par, batch=min(batch, 4))          # warm-up
+
+
+def make_fem(fem):
+    fem.set_mesh(xyz, tets)
+    fem.set_diffusion(3e-3)
+    fem.set_relaxation(1e-16)
+
+
+make_fem.device = local_rank
+if concurrent > 0:
+    fems = sweep.make_concurrent_handles(make_fem, concurrent)
+    sweep.run_sweep_concurrent(fems, mp, sim, dirs[:concurrent // 2 + 1], bvals[:2], par)      # warm-up
+else:
+    fem = btfem.BTFem(local_rank)
+    make_fem(fem)
+    fem.assemble()
+    sweep.run_sweep(fem, mp, sim, dirs[:2], bvals[:2], par, batch=min(batch, 4))          # warm-up
 if dist is not None:
     dist.barrier(); torch.cuda.synchronize()
 t0 = time.perf_counter()
-mine, sig = sweep.run_sweep(fem, mp, sim, dirs, bvals, par, rank=rank, world=world, batch=batch)
+if concurrent > 0:
+    mine, sig = sweep.run_sweep_concurrent(fems, mp, sim, dirs, bvals, par, rank=rank, world=world)
+else:
+    mine, sig = sweep.run_sweep(fem, mp, sim, dirs, bvals, par, rank=rank, world=world, batch=batch)
 full = sweep.gather_signals(len(dirs) * len(bvals), mine, sig, dist)
 if dist is not None:
     dist.barrier(); torch.cuda.synchronize()
@@ -53,6 +68,11 @@ if dist is not None:
     dt = float(t[0])
 if rank == 0:
     print("HARDI mesh %d verts %d tets | %d signals on %d GPU(s), batch %d: %.3f s -> %.2f signals/s | first %s | checksum %.12f"
-          % (len(xyz), len(tets), len(full), world, batch, dt, len(full) / dt, np.round(full[:4], 6), full.sum()))
+          % (len(xyz), len(tets), len(full), world, batch if concurrent == 0 else -concurrent, dt, len(full) / dt,
+             np.round(full[:4], 6), full.sum()))
+if concurrent > 0 and rank == 0:
+    st = sweep.run_sweep_concurrent.last_stats
+    print("  per solve: loop %.1f ms, set-up %.1f ms, %.0f iterations -> %.1f us per iteration inside the kernel" % (
+        st[:, 0].mean(), st[:, 1].mean(), st[:, 2].mean(), 1e3 * st[:, 0].sum() / st[:, 2].sum()))
 if dist is not None:
     dist.destroy_process_group()

@@ -37,12 +37,16 @@ def _cases():
 CASES = list(_cases())
 
 
-def _setup(fem, xyz, tets, phase, co):
+def _setup_inputs(fem, xyz, tets, phase, co):
     fem.set_mesh(xyz, tets, phase)
     fem.set_diffusion(co.get("D", 1.0))
     fem.set_relaxation(co.get("invT2", 0.0))
     if phase is not None:
         fem.set_permeability(co.get("kappa", 0.0))
+
+
+def _setup(fem, xyz, tets, phase, co):
+    _setup_inputs(fem, xyz, tets, phase, co)
     fem.assemble()
 
 
@@ -478,3 +482,41 @@ def test_interleaved_batch_layout(monkeypatch):
     for a, d in zip(inter, default):
         assert abs(a["signal"] - d["signal"]) <= 1e-9 * abs(d["signal"])
         assert abs(a["total_iters"] - d["total_iters"]) <= max(3, 0.02 * d["total_iters"])
+
+
+def test_sm_partition_concurrent_handles():
+    """btfem_set_sm_partition + sweep.run_sweep_concurrent: handles confined to disjoint SM shares solve concurrently
+    (one host thread and one persistent-kernel launch each); same bits whichever handle takes a unit, solver-tolerance
+    agreement with a full-device solve."""
+    import sympy as sp
+    from dmri_fem_cloud_b200 import dmrifemlib as dl, sweep
+    _, xyz, tets, phase, co = CASES[3]
+
+    def make_fem(fem):
+        _setup_inputs(fem, xyz, tets, phase, co)
+
+    mp = dl.MRI_parameters()
+    mp.delta, mp.Delta = 2000.0, 6000.0
+    mp.T = mp.delta + mp.Delta
+    mp.fs_sym = sp.Piecewise((1., mp.s < mp.delta), (0., mp.s < mp.Delta), (-1., mp.s < mp.T), (0., True))
+    mp.bvalue = 1000.0
+    mp.Apply()
+    sim = dl.MRI_simulation()
+    sim.k = 200.0
+    dirs = meshes.fibonacci_hemisphere(3)
+    bvals = [500.0, 3000.0]
+    par = dict(rtol=1e-10, atol=1e-14, maxit=100000)
+    fems = sweep.make_concurrent_handles(make_fem, 3, n_sms=12)          # 3 handles x 4 SMs
+    try:
+        assert all(f.spmv_kernel == 2 for f in fems)
+        mine, a = sweep.run_sweep_concurrent(fems, mp, sim, dirs, bvals, par)
+        _, b = sweep.run_sweep_concurrent(fems[::-1], mp, sim, dirs, bvals, par)
+    finally:
+        for f in fems:
+            f.close()
+    assert np.array_equal(a, b)                                          # bit-identical, whoever solved what
+    with btfem.BTFem(0) as fem:
+        make_fem(fem)
+        fem.assemble()
+        _, ref = sweep.run_sweep(fem, mp, sim, dirs, bvals, par)
+    assert mine == list(range(6)) and np.max(np.abs(a - ref) / np.abs(ref)) <= 1e-9
