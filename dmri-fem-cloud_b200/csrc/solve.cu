@@ -866,7 +866,10 @@ struct WarpRing {
   // lane 0: fetch list entry `idx` of operator stream T as ring piece number c; the stage's barrier completes when
   // the bytes have landed
   __device__ __forceinline__ void fetch(const unsigned char* T, int idx, unsigned int c) const {
-    const int4 d = __ldg(pieces + idx);
+    fetch_desc(T, __ldg(pieces + idx), c);
+  }
+  // the same with the list entry already in registers
+  __device__ __forceinline__ void fetch_desc(const unsigned char* T, const int4 d, unsigned int c) const {
     const unsigned int st = c % D;
     const uint32_t bytes = (uint32_t)(d.y * colu + 2 * (d.w & 1)) * 64u;
     const uint32_t bar = bar_s + 8 * st;
@@ -917,9 +920,9 @@ __device__ __forceinline__ void row_epilogue_rt(const SpmvArgs& a, int mode, int
 
 // gather step of ring piece c: wait for the bytes, read the columns, issue the x loads (and the epilogue loads)
 template <int D>
-__device__ __forceinline__ void piece_gather(const double2* opv, const WarpRing<D>& r, unsigned int c, int idx,
+__device__ __forceinline__ void piece_gather(const double2* opv, const WarpRing<D>& r, unsigned int c, const int4 desc,
                                              const double2* __restrict__ x, PieceRegs& q) {
-  q.d = __ldg(r.pieces + idx);
+  q.d = desc;
   r.wait(c);
   const unsigned char* sp = r.stage(c);
   const int lane = threadIdx.x & 31;
@@ -970,9 +973,17 @@ __device__ __forceinline__ unsigned int stream_pass(const SpmvArgs& a, int mode,
   static_assert(G >= 2 && G <= D, "the pieces whose gathers are in flight must all sit in the ring");
   const int lane = threadIdx.x & 31;
   const int np = r.np;
+  const int nnext = Tnext ? min(D, np) : 0;   // entries of the following pass that this pass puts into the ring
   const double2* opv = epilogue_vector(a, mode);
   double ar = 0.0, ai = 0.0;
   PieceRegs q[G];   // gathers of G - 1 pieces are in flight while one piece is multiplied
+  // List entries are read ONE STEP before they are needed (ncu: the entry's load latency sat on the critical path of
+  // every piece -- the address arithmetic on its width was the second-largest stall of the pass):
+  //   dg = entry of the piece whose gathers the next step issues, dr = entry the next step's refill fetches.
+  auto entry = [&](int i) {   // list entry of ring piece c0 + i: this pass, then the first entries of the next one
+    return __ldg(r.pieces + (i < np ? i : i - np));
+  };
+  int4 dg = make_int4(0, 0, 0, 0), dr = dg;
   auto finish = [&](int k, const PieceRegs& qq) {   // piece k is done: epilogue of its slice, refill of its stage
     if (qq.d.w & 1) {
       if (qq.row >= 0) row_epilogue_rt(a, mode, qq.row, make_double2(ar, ai), qq.op, acc);
@@ -980,32 +991,37 @@ __device__ __forceinline__ unsigned int stream_pass(const SpmvArgs& a, int mode,
       ai = 0.0;
     }
     __syncwarp();
-    if (lane == 0) {
+    const int nx = k + D;
+    const bool have = nx < np + nnext;
+    if (lane == 0 && have) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      const int nx = k + D;
-      if (nx < np) r.fetch(T, nx, c0 + nx);
-      else if (Tnext && nx - np < min(D, np)) r.fetch(Tnext, nx - np, c0 + nx);
+      r.fetch_desc(nx < np ? T : Tnext, dr, c0 + nx);
     }
+    if (nx + 1 < np + nnext) dr = entry(nx + 1);
   };
   if (Tnext && lane == 0)
     for (int i = 0; i < np && np + i < D; ++i) r.fetch(Tnext, i, c0 + np + i);
 #pragma unroll
   for (int g = 0; g < G - 1; ++g)
-    if (g < np) piece_gather(opv, r, c0 + g, g, x, q[g]);
+    if (g < np) piece_gather(opv, r, c0 + g, __ldg(r.pieces + g), x, q[g]);
+  if (G - 1 < np) dg = __ldg(r.pieces + G - 1);
+  if (D < np + nnext) dr = entry(D);
   for (int k0 = 0; k0 < np; k0 += G) {
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       const int k = k0 + g;
       if (k < np) {
         const int kn = k + G - 1;
-        if (kn < np) piece_gather(opv, r, c0 + kn, kn, x, q[(g + G - 1) % G]);
+        if (kn < np) {
+          piece_gather(opv, r, c0 + kn, dg, x, q[(g + G - 1) % G]);
+          if (kn + 1 < np) dg = __ldg(r.pieces + kn + 1);
+        }
         piece_fma(r, c0 + k, cc, q[g], ar, ai);
         finish(k, q[g]);
       }
     }
   }
-  // This warp is done and will sit in a barrier until the slowest one is; the memory system would idle with it.
-  // Its next pieces of the following pass (behind the D already on their way into the ring) go to L2 meanwhile.
+  // (profiles/r2o_*: prefetching further pieces of the next pass into L2 from here -- BTFEM_PS_L2AHEAD -- is slower)
   if (Tnext && lane == 0 && a.ps_l2ahead > 0) r.prefetch_l2(Tnext, D, D + a.ps_l2ahead);
   return c0 + np;
 }
