@@ -52,12 +52,11 @@ UNIT = "DOF-steps/s"
 # `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_ncu_spmv_sell_full.txt)
 NCU_TRAFFIC = {"n_box": 78,
                "sell": {"bytes": 167.227136e6 + 3.839232e6, "file": "profiles/r1_ncu_spmv_sell_full.txt (ncu, round 1)"},
-               "stream": {"bytes": 159.704576e6 + 7.045888e6,
-                          "file": "profiles/r2m_ncu_persistent_and_stream_full.txt (ncu, round 2)"},
-               # one launch = one whole solve of this workload (270 steps, 11 335 iterations when captured)
-               "persistent": {"bytes": 3.465271e12 + 30.187408e9,
-                              "file": "profiles/r2m_ncu_persistent_and_stream_full.txt (ncu, round 2; 0.69 x the algorithmic "
-                                      "bytes: the Krylov vectors stay in L2, HBM carries the operator stream)"}}
+               # one launch = one whole solve of this workload (270 steps, 11 335 iterations when captured; the final layout:
+               # 16-bit column offsets, 18 B per nonzero)
+               "persistent": {"bytes": 3.117732e12 + 95.638328e9,
+                              "file": "profiles/r2m_ncu_persistent_and_stream_full.txt (ncu, round 2, last capture; 0.63 x the "
+                                      "algorithmic bytes: the Krylov vectors stay in L2, HBM carries the operator stream)"}}
 
 
 def workload(n_box):
@@ -409,8 +408,8 @@ def main():
         sim.verbose = False
         sim.solve(md, mp, ls)
         s = sim.stats["signal"] / sim.stats["voi"]
-        keep.append(sim.fem)        # teardown (cudaFree of ~1 GB) is not part of the reference's timed region either
-        return s
+        keep.append(sim.fem)        # teardown is not part of the reference's timed region either (measured: closing inside
+        return s                    # the region costs 0.14 s per solve, cudaFree of the IPC-exportable vector slab + pinned frees)
 
     import contextlib
     import io
