@@ -340,6 +340,7 @@ struct SpmvArgs {
   int ps_blocks;             // 0: layout not usable for this solve
   int ps_warps;              // warps per block of the layout
   int ps_c16;                // 16-bit column offsets from the piece's reference column
+  int ps_fence;              // fence.proxy.async before every ring refill (debug switch)
   int ps_l2ahead;            // persistent kernel: pieces per warp prefetched into L2 for the next pass when a pass ends
   const int32_t* ps_ptr;     // [ps_blocks * BT_PS_WARPS + 1]
   const int4* ps_piece;      // {stream column, columns, slice, last}
@@ -993,8 +994,12 @@ __device__ __forceinline__ unsigned int stream_pass(const SpmvArgs& a, int mode,
     __syncwarp();
     const int nx = k + D;
     const bool have = nx < np + nnext;
+    // fence.proxy.async orders this warp's generic-proxy reads of the stage before the async-proxy refill.  Every
+    // lane's reads have in fact returned (their values fed arithmetic that has issued) and __syncwarp orders them before
+    // lane 0's copy, which is what TMA load pipelines rely on without a fence; the fence costs 0.3 us per iteration
+    // (profiles/r2af_*), so it stays as a margin.  BTFEM_PS_FENCE=0 drops it.
     if (lane == 0 && have) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (a.ps_fence) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       r.fetch_desc(nx < np ? T : Tnext, dr, c0 + nx);
     }
     if (nx + 1 < np + nnext) dr = entry(nx + 1);
@@ -2434,6 +2439,10 @@ SpmvArgs base_args(btfem* h) {
     a.ps_blocks = h->ps_blocks;
     a.ps_warps = h->ps_warps;
     a.ps_c16 = h->ps_col16 ? 1 : 0;
+    {
+      static const int fence = !(getenv("BTFEM_PS_FENCE") && getenv("BTFEM_PS_FENCE")[0] == '0');
+      a.ps_fence = fence;
+    }
     {
       static const int ahead = getenv("BTFEM_PS_L2AHEAD") ? std::max(0, atoi(getenv("BTFEM_PS_L2AHEAD"))) : 0;
       a.ps_l2ahead = ahead;
