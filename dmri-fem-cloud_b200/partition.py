@@ -229,6 +229,110 @@ class ThreadComm:
         return np.max(np.stack(self.allgather(np.array(a, dtype=np.float64, copy=True))), axis=0)
 
 
+class SocketComm:
+    """The same tiny collective interface over plain TCP sockets: one process per GPU WITHOUT torch in the host
+    plumbing (the data path never used it: halo entries and dot products travel through peer memory inside libbtfem's
+    kernels).  Rank 0 listens on (addr, port); every collective is an all-gather of pickled python objects through it.
+    Launch with any launcher that sets RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT (torchrun, mpirun wrappers, a
+    shell loop): `SocketComm.from_env()`."""
+
+    def __init__(self, rank, world, addr="127.0.0.1", port=29555, timeout=600.0):
+        import socket
+        self.rank, self.world = int(rank), int(world)
+        self._peers = []          # rank 0: sockets of ranks 1..world-1, in rank order
+        self._sock = None         # other ranks: socket to rank 0
+        if self.world == 1:
+            return
+        if self.rank == 0:
+            srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+            srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+            srv.bind((addr, int(port)))
+            srv.listen(self.world)
+            srv.settimeout(timeout)
+            got = {}
+            while len(got) < self.world - 1:
+                c, _ = srv.accept()
+                c.settimeout(timeout)
+                c.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+                got[self._recv(c)] = c
+            srv.close()
+            self._peers = [got[r] for r in range(1, self.world)]
+        else:
+            import time
+            deadline = time.time() + timeout
+            while True:
+                try:
+                    self._sock = socket.create_connection((addr, int(port)), timeout=timeout)
+                    break
+                except OSError:
+                    if time.time() > deadline:
+                        raise
+                    time.sleep(0.05)
+            self._sock.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+            self._send(self._sock, self.rank)
+
+    @classmethod
+    def from_env(cls, port_offset=17, **kw):
+        import os
+        return cls(os.environ.get("RANK", "0"), os.environ.get("WORLD_SIZE", "1"),
+                   os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("MASTER_PORT", "29538")) + port_offset, **kw)
+
+    @staticmethod
+    def _send(sock, obj):
+        import pickle
+        import struct
+        data = pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
+        sock.sendall(struct.pack("<Q", len(data)) + data)
+
+    @staticmethod
+    def _recv(sock):
+        import pickle
+        import struct
+
+        def exactly(n):
+            buf = bytearray()
+            while len(buf) < n:
+                part = sock.recv(min(1 << 20, n - len(buf)))
+                if not part:
+                    raise ConnectionError("peer closed the connection")
+                buf.extend(part)
+            return bytes(buf)
+
+        (n,) = struct.unpack("<Q", exactly(8))
+        return pickle.loads(exactly(n))
+
+    def allgather(self, obj):
+        if self.world == 1:
+            return [obj]
+        if self.rank == 0:
+            out = [obj] + [self._recv(c) for c in self._peers]
+            for c in self._peers:
+                self._send(c, out)
+            return out
+        self._send(self._sock, obj)
+        return self._recv(self._sock)
+
+    def barrier(self):
+        self.allgather(None)
+
+    def sum(self, a):
+        parts = self.allgather(np.array(a, dtype=np.float64, copy=True))
+        tot = parts[0].copy()
+        for p in parts[1:]:      # rank order: identical on every rank
+            tot = tot + p
+        return tot
+
+    def max(self, a):
+        return np.max(np.stack(self.allgather(np.array(a, dtype=np.float64, copy=True))), axis=0)
+
+    def close(self):
+        for c in self._peers:
+            c.close()
+        if self._sock is not None:
+            self._sock.close()
+        self._peers, self._sock = [], None
+
+
 class SingleComm:
     rank, world = 0, 1
 

@@ -30,15 +30,21 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--bvalue", type=float, default=1000.0)
     ap.add_argument("--trace", type=int, default=0, help="log the first N collective-closing kernels per rank")
+    ap.add_argument("--comm", default="torch", choices=["torch", "socket"],
+                    help="host plumbing of the set-up: torch.distributed (gloo) or the torch-free partition.SocketComm")
     args = ap.parse_args()
-    import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist.init_process_group("gloo")
     entry.load_package()
     from dmri_fem_cloud_b200 import btfem, meshes, partition
-    comm = partition.TorchComm(dist)
+    dist = None
+    if args.comm == "socket":
+        comm = partition.SocketComm.from_env()
+    else:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+        comm = partition.TorchComm(dist)
 
     Fb = pdir = None
     if args.ecs:
@@ -124,7 +130,10 @@ def main():
     if rank == 0:
         print(json.dumps(out))
     comm.barrier()
-    dist.destroy_process_group()
+    if dist is not None:
+        dist.destroy_process_group()
+    else:
+        comm.close()
     return 0
 
 

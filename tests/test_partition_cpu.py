@@ -107,12 +107,16 @@ def test_thread_comm_collectives():
         assert out[r] == ([("r", 0), ("r", 1), ("r", 2)], [6.0, 6.0])
 
 
-def _gloo_worker(rank, world, port, q):
-    import torch.distributed as dist
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    comm = partition.TorchComm(dist)
+def _gloo_worker(rank, world, port, q, kind="gloo"):
+    dist = None
+    if kind == "socket":      # the torch-free plumbing: plain TCP through rank 0
+        comm = partition.SocketComm(rank, world, "127.0.0.1", port)
+    else:
+        import torch.distributed as dist
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        comm = partition.TorchComm(dist)
     xyz, tets, phase = _mesh(True)
     gops = orc.assemble(xyz, tets, phase, D=2e-3, invT2=1e-3, kappa=1e-2)
     rng = np.random.default_rng(1)
@@ -135,18 +139,23 @@ def _gloo_worker(rank, world, port, q):
     tot = comm.sum([s["n_own"]])
     comm.barrier()
     q.put((rank, err, int(tot[0]), gops.ndof))
-    dist.destroy_process_group()
+    if dist is not None:
+        dist.destroy_process_group()
+    else:
+        comm.close()
 
 
-def test_two_rank_partition_gloo():
-    import torch.multiprocessing as mp
+@pytest.mark.parametrize("kind", ["gloo", "socket"])
+def test_two_rank_partition_gloo(kind):
+    """The N > 1 host plumbing on two CPU processes: torch.distributed (gloo) and the torch-free SocketComm."""
+    import multiprocessing as mp
     sk = socket.socket()
     sk.bind(("127.0.0.1", 0))
     port = sk.getsockname()[1]
     sk.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q, kind)) for r in range(2)]
     for p in procs:
         p.start()
     out = [q.get(timeout=180) for _ in range(2)]
