@@ -885,8 +885,12 @@ void bt_build_pattern(btfem* h) {
   const int64_t nslice = (n + 31) / 32;
   std::vector<int32_t> sell_row(nslice * 32, -1), sell_slot(h->ndof, -1), slice_ptr(nslice + 1, 0);
   for (int64_t i = 0; i < n; ++i) sell_row[i] = (int32_t)i;
-  for (int64_t w0 = 0; w0 < n; w0 += BT_SELL_SIGMA) {
-    const int64_t w1 = std::min<int64_t>(n, w0 + BT_SELL_SIGMA);
+  // whole-mesh handles: the window is tunable (BTFEM_SELL_SIGMA, a multiple of 32; 32 = rows stay in mesh order)
+  int64_t sigma = BT_SELL_SIGMA;
+  if (const char* e = getenv("BTFEM_SELL_SIGMA"))
+    if (h->nv_own < 0) sigma = std::max<int64_t>(32, (atoll(e) / 32) * 32);
+  for (int64_t w0 = 0; w0 < n; w0 += sigma) {
+    const int64_t w1 = std::min<int64_t>(n, w0 + sigma);
     std::stable_sort(sell_row.begin() + w0, sell_row.begin() + w1, [&](int32_t x, int32_t y) {
       return rp[x + 1] - rp[x] > rp[y + 1] - rp[y];
     });
@@ -908,6 +912,8 @@ void bt_build_pattern(btfem* h) {
   slice_ptr[nslice] = (int32_t)tot;
   h->n_slice = nslice;
   h->nnz_sell = tot;
+  if (timing) fprintf(stderr, "[btfem]   SELL-32: window %lld rows, %lld slots for %lld nonzeros (padding %.1f %%)\n", (long long)sigma,
+                      (long long)tot, (long long)rp[n], 100.0 * ((double)tot / std::max<double>(1.0, (double)rp[n]) - 1.0));
   h->d_slice_ptr.upload(slice_ptr.data(), slice_ptr.size(), st);
   h->d_sell_row.upload(sell_row.data(), sell_row.size(), st);
   h->d_sell_slot.upload(sell_slot.data(), sell_slot.size(), st);
@@ -969,6 +975,8 @@ void bt_build_pattern(btfem* h) {
   h->ps_blocks = 0;
   h->d_PJt.release();
   h->d_QJt.release();
+  h->d_PJt_b.release();
+  h->d_QJt_b.release();
   if (h->nv_own < 0 && nslice > 0 && !getenv("BTFEM_NO_STREAM")) {
     const char* w_env = getenv("BTFEM_PS_WARPS");   // warps per block of the stream kernels: 8, 12 or 16
     const int wpb = (w_env && (atoi(w_env) == 12 || atoi(w_env) == 16)) ? atoi(w_env) : 8;

@@ -251,18 +251,22 @@ __global__ void k_combine(int64_t nnz, const int32_t* __restrict__ rowidx, const
   double jg = comb_jg(gx, gy, gz, Jx[k], Jy[k], Jz[k], di);
   const double2 pj = make_double2(comb_p(mk, k0, B[k], theta, di), jg);
   const double2 qj = make_double2(comb_q(mk, k0, 1.0 - theta, di), jg);
-  PJ[k] = pj;
-  QJ[k] = qj;
+  if (PJ) {   // (null: only the warp streams of one direction of a persistent batch are wanted)
+    PJ[k] = pj;
+    QJ[k] = qj;
+  }
   if (Bhat) Bhat[k] = B[k] * di;
-  if (PJs) {   // same entry in the SELL-32 layout: slice base + (position in row)*32 + slot lane
+  if (PJs || PJt) {   // same entry in the SELL-32 layout: slice base + (position in row)*32 + slot lane
     const int row = rowidx[k];
     const int slot = sell_slot[row];
     if (slot < 0) return;   // halo row of a row-partitioned handle
     const int j = (int)(k - rowptr[row]);
     const int sbase = slice_ptr[slot >> 5];
     const int pos = sbase + j * 32 + (slot & 31);
-    PJs[pos] = pj;
-    QJs[pos] = qj;
+    if (PJs) {
+      PJs[pos] = pj;
+      QJs[pos] = qj;
+    }
     if (PJt) {   // and in the warp-stream layout (setup.cu: k_stream_columns)
       const int width = (slice_ptr[(slot >> 5) + 1] - sbase) >> 5;
       const size_t off = bt_ps_val_off(scol0[slot >> 5], width, j, slot & 31, c16 != 0);
@@ -296,6 +300,17 @@ __global__ void k_combine_shared(int64_t nnz, const int32_t* __restrict__ rowidx
 }
 
 // ------------------------------------------------------------------------------------ fused SpMV
+
+// Lock-step batch inside ONE persistent kernel (k_bicgstab_persistent_batch): members that share a gradient direction
+// form a pass group -- they read ONE operator stream (the direction's P|Q, J_g values; b only enters through the
+// scalar c) -- of at most PB_GM members.
+constexpr int PB_MAX = 16;   // members per launch
+constexpr int PB_GM = 4;     // members per pass group
+struct PbArgs {
+  int members, groups;
+  unsigned char g_m0[PB_MAX], g_nm[PB_MAX], g_dir[PB_MAX];   // per group: first member, members, direction (stream) index
+  size_t stream_stride;                                      // bytes between the operator streams of two directions
+};
 
 struct SpmvArgs {
   int n;
@@ -349,10 +364,12 @@ struct SpmvArgs {
   unsigned int* gridbar;     // persistent kernel: grid barrier words
   unsigned long long* prof;  // persistent kernel: optional phase timers of block 0 (BTFEM_PROFILE_PERSIST), or null
   int step_begin, step_end;  // persistent kernel: time steps of this launch
+  PbArgs pb;                 // batch form of the persistent kernel
   DistView dist;             // row-partitioned solve: peers, LL buffers, send lists (dist.on == 0: whole mesh)
   // device-driven loop: the BiCGStab iteration is the body of a graph WHILE node whose condition the kernels set
   cudaGraphConditionalHandle cond;
   int use_cond;
+  const int32_t* member_dir; // batch: operator copy of every member (members with one direction share a copy), or null
   KrylovCtrl* ctrl0;         // member 0 (a.ctrl is shifted per member)
   int32_t* iters_out;        // [nsteps] iteration count of every step (member 0), or null
 };
@@ -378,10 +395,11 @@ __device__ __forceinline__ void loop_condition(const SpmvArgs& a) {
 // arguments of batch member b
 __device__ __forceinline__ SpmvArgs member_at(SpmvArgs a, size_t b) {
   if (b == 0) return a;
-  a.PJ += b * a.mat_stride_csr;
-  a.QJ += b * a.mat_stride_csr;
-  a.PJs += b * a.mat_stride_sell;
-  a.QJs += b * a.mat_stride_sell;
+  const size_t mb = a.member_dir ? (size_t)__ldg(a.member_dir + b) : b;
+  a.PJ += mb * a.mat_stride_csr;
+  a.QJ += mb * a.mat_stride_csr;
+  a.PJs += mb * a.mat_stride_sell;
+  a.QJs += mb * a.mat_stride_sell;
   a.cA += b * a.step_stride;
   a.cb += b * a.step_stride;
   a.ctrl += b;
@@ -1396,6 +1414,961 @@ __global__ void __launch_bounds__(NW * 32, 1) k_bicgstab_persistent(SpmvArgs a) 
 }
 
 
+// ---- lock-step batches (HARDI sweeps: directions x b-values on one mesh) as ONE persistent kernel.
+// Same machinery as k_bicgstab_persistent -- per-warp TMA rings, grid barrier, every block finishes the reductions --
+// with every phase covering all members that still iterate, so that the barrier / reduction latency (15 us per
+// iteration, as much as the whole iteration of ONE member on a 46 k-vertex mesh) is paid once per batch iteration:
+//  * passes: members with the same gradient direction share one operator stream (A = P + i c J_g: b only enters
+//    through c).  A warp fetches a piece once and runs it for every member of the group ("units": the gathers of the
+//    next unit are in flight while one unit is multiplied), so the stream is read once per group and the per-piece
+//    costs (mbarrier wait, list entry, column decode) are spread over the group;
+//  * dot products: every thread keeps its per-member partial sums in shared memory, the block / grid reduction visits
+//    them in the order of the single-solve kernel -> a member gets the bits of its one-at-a-time persistent solve;
+//  * vector phases: one sweep over (member, row) with batched loads; thread -> row mapping of the single-solve kernel.
+// Members iterate in lock-step inside a time step (one common iteration counter); a member that has converged
+// drops out of the passes and phases until the next step starts.
+constexpr int PB_NW = 8, PB_D = 3;
+constexpr int pb_smem() { return ps_smem(PB_NW, PB_D) + 2 * PB_MAX * PB_NW * 32 * 8; }
+
+struct PbState {
+  double rho[PB_MAX], rho_old[PB_MAX], alpha[PB_MAX], omega[PB_MAX], beta[PB_MAX];
+  double bn[PB_MAX], ttol[PB_MAX], rnorm[PB_MAX], cA[PB_MAX], cb[PB_MAX];
+  double tot[2 * PB_MAX];
+  double wsum[2 * PB_MAX][PB_NW];
+  long long total_iters[PB_MAX];
+  int max_iters[PB_MAX], its[PB_MAX], reason[PB_MAX];
+  unsigned int active;                  // bit m: member m still iterates in this time step
+  unsigned char gmask[PB_MAX];          // per group: its active members (bit j: member g_m0 + j)
+  unsigned char unit[PB_MAX][PB_GM];    // per group: the member behind unit j (its j-th active member)
+  unsigned char act[PB_MAX];            // active members, ascending
+  int nact;
+  unsigned char actg[PB_MAX];           // member-interleaved form: groups of 8 members with an active member
+  int ngact;
+  double gd[PB_MAX][3];                 // member-interleaved form: gradient direction of every member
+  int it, mode, step, fail;
+  unsigned int bar_target;
+};
+
+// thread 0: the lists that follow from S.active
+__device__ __forceinline__ void pb_rebuild(PbState& S, const PbArgs& pb) {
+  int na = 0;
+  for (int g = 0; g < pb.groups; ++g) {
+    const int m0 = pb.g_m0[g], nm = pb.g_nm[g];
+    const unsigned int gm = (S.active >> m0) & ((1u << nm) - 1u);
+    S.gmask[g] = (unsigned char)gm;
+    int j = 0;
+    for (int k = 0; k < nm; ++k)
+      if ((gm >> k) & 1u) {
+        S.unit[g][j++] = (unsigned char)(m0 + k);
+        S.act[na++] = (unsigned char)(m0 + k);
+      }
+  }
+  S.nact = na;
+}
+__device__ __forceinline__ int pb_next_group(const PbState& S, const PbArgs& pb, int g) {
+  for (int k = g + 1; k < pb.groups; ++k)
+    if (S.gmask[k]) return k;
+  return -1;
+}
+
+// gather step of one unit: columns of ring piece c (landed), x of member `m`
+template <int D>
+__device__ __forceinline__ void pb_gather(const WarpRing<D>& r, unsigned int c, const int4 d, const double2* __restrict__ x,
+                                          const double2* __restrict__ opv, double2 (&xv)[BT_PS_W], double2& op) {
+  const unsigned char* sp = r.stage(c);
+  const int lane = threadIdx.x & 31;
+  if (r.colu == 9) {
+    const uint16_t* cs = reinterpret_cast<const uint16_t*>(sp) + lane;
+    const int ref = d.w >> 1;
+#pragma unroll
+    for (int j = 0; j < BT_PS_W; ++j)
+      if (j < d.y) xv[j] = ldv_gather_f64x2(x + (ref + (int)cs[j * 32]));
+  } else {
+    const int32_t* cs = reinterpret_cast<const int32_t*>(sp) + lane;
+#pragma unroll
+    for (int j = 0; j < BT_PS_W; ++j)
+      if (j < d.y) xv[j] = ldv_gather_f64x2(x + cs[j * 32]);
+  }
+  if (d.w & 1) {
+    const int row = reinterpret_cast<const int32_t*>(sp + (size_t)d.y * r.colu * 64)[lane];
+    op = make_double2(0.0, 0.0);
+    if (row >= 0 && opv) op = opv[row];
+  }
+}
+template <int D>
+__device__ __forceinline__ void pb_fma(const WarpRing<D>& r, unsigned int c, const int4 d, double cc,
+                                       const double2 (&xv)[BT_PS_W], double& ar, double& ai) {
+  const double2* vs = reinterpret_cast<const double2*>(r.stage(c) + d.y * (r.colu == 9 ? 64 : 128)) + (threadIdx.x & 31);
+#pragma unroll
+  for (int j = 0; j < BT_PS_W; ++j)
+    if (j < d.y) {
+      const double2 val = vs[j * 32];
+      const double pa = val.x, pb = cc * val.y;
+      ar = fma(pa, xv[j].x, ar);
+      ar = fma(-pb, xv[j].y, ar);
+      ai = fma(pa, xv[j].y, ai);
+      ai = fma(pb, xv[j].x, ai);
+    }
+}
+
+// One pass of this warp over its list for the `na` units (active members) of a group: ring pieces c0 .. c0 + np - 1 of
+// stream T, refilled like stream_pass (the first entries of `Tnext` follow those of T).  acc: this thread's column of
+// the per-member accumulators, acc[(2 m + q) * NT].
+template <int D, int NT>
+__device__ __forceinline__ unsigned int pb_stream_pass(const SpmvArgs& a, int mode, const WarpRing<D>& r, unsigned int c0,
+                                                       const unsigned char* T, const unsigned char* Tnext,
+                                                       const unsigned char* unit, int na, const double* ccs, double* acc) {
+  const int lane = threadIdx.x & 31;
+  const int np = r.np;
+  const int nnext = min(D, np);
+  if (lane == 0)
+    for (int i = 0; i < np && np + i < D; ++i) r.fetch(Tnext, i, c0 + np + i);
+  if (np == 0) return c0;
+  const double2* xbase = mode == MODE_RHSP ? a.u : (mode == MODE_V ? a.p : a.s);
+  const double2* opbase = mode == MODE_V ? a.rp : (mode == MODE_T ? a.s : nullptr);
+  const size_t vs = a.vec_stride;
+  auto entry = [&](int i) { return __ldg(r.pieces + (i < np ? i : i - np)); };
+  double ar[PB_GM], ai[PB_GM];
+#pragma unroll
+  for (int j = 0; j < PB_GM; ++j) ar[j] = ai[j] = 0.0;
+  double2 xv[2][BT_PS_W], op[2];
+  op[0] = op[1] = make_double2(0.0, 0.0);
+  int4 d = __ldg(r.pieces), dn = d, dr = make_int4(0, 0, 0, 0);
+  if (np > 1) dn = __ldg(r.pieces + 1);
+  if (D < np + nnext) dr = entry(D);
+  const bool even = (na & 1) == 0;
+  auto gather_unit = [&](unsigned int c, const int4 dd, int j, double2 (&xb)[BT_PS_W], double2& ob) {
+    const size_t off = (size_t)unit[j] * vs;
+    pb_gather(r, c, dd, xbase + off, opbase ? opbase + off : nullptr, xb, ob);
+  };
+  r.wait(c0);
+  gather_unit(c0, d, 0, xv[0], op[0]);
+  for (int k = 0; k < np; ++k) {
+    const unsigned int c = c0 + k;
+    const bool last = (d.w & 1) != 0;
+    int row = -1;
+    if (last) row = reinterpret_cast<const int32_t*>(r.stage(c) + (size_t)d.y * r.colu * 64)[lane];
+#pragma unroll
+    for (int j = 0; j < PB_GM; ++j)
+      if (j < na) {
+        // the next unit's loads go out before this unit's arithmetic: the next member on this piece, or (even unit
+        // counts: the register buffers then alternate across the piece boundary) the first member on the next piece
+        if (j + 1 < na) {
+          gather_unit(c, d, j + 1, xv[(j + 1) & 1], op[(j + 1) & 1]);
+        } else if (even && k + 1 < np) {
+          r.wait(c + 1);
+          gather_unit(c + 1, dn, 0, xv[0], op[0]);
+        }
+        const int m = unit[j];
+        pb_fma(r, c, d, ccs[m], xv[j & 1], ar[j], ai[j]);
+        if (last) {
+          if (row >= 0) {
+            const size_t off = (size_t)m * vs + row;
+            const double2 y = make_double2(ar[j], ai[j]), o = op[j & 1];
+            double* a0 = acc + (size_t)(2 * m) * NT;
+            if (mode == MODE_V) {
+              a.v[off] = y;
+              a0[0] += y.x * o.x + y.y * o.y;
+            } else if (mode == MODE_T) {
+              a.t[off] = y;
+              a0[0] += o.x * y.x + o.y * y.y;
+              a0[NT] += y.x * y.x + y.y * y.y;
+            } else {
+              a.r[off] = y;
+              a.rp[off] = y;
+              a0[0] += y.x * y.x + y.y * y.y;
+            }
+          }
+          ar[j] = 0.0;
+          ai[j] = 0.0;
+        }
+      }
+    // piece k is done for every unit: its stage takes the entry D pieces further (see stream_pass)
+    __syncwarp();
+    const int nx = k + D;
+    if (lane == 0 && nx < np + nnext) {
+      if (a.ps_fence) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      r.fetch_desc(nx < np ? T : Tnext, dr, c0 + nx);
+    }
+    if (nx + 1 < np + nnext) dr = entry(nx + 1);
+    if (!even && k + 1 < np) {
+      r.wait(c + 1);
+      gather_unit(c + 1, dn, 0, xv[0], op[0]);
+    }
+    d = dn;
+    if (k + 2 < np) dn = __ldg(r.pieces + k + 2);
+  }
+  return c0 + np;
+}
+
+// Sums of the per-thread accumulators acc_s[(2 m + q) * NT + thread], q < nq, of the active members over the whole
+// grid -> S.tot[2 m + q] in every block.  Order of the additions: that of grid_reduce.
+template <int NW>
+__device__ __forceinline__ void pb_grid_reduce(const SpmvArgs& a, PbState& S, const double* acc_s, int nq, int slot,
+                                               GridSync& g) {
+  constexpr int NT = NW * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nact = S.nact, nval = nact * nq;
+  for (int i = 0; i < nval; ++i) {
+    const int v = 2 * S.act[i / nq] + (i % nq);
+    const double t = warp_sum(acc_s[(size_t)v * NT + threadIdx.x]);
+    if (lane == 0) S.wsum[v][warp] = t;
+  }
+  __syncthreads();
+  for (int i = warp; i < nval; i += NW) {
+    const int m = S.act[i / nq], q = i % nq;
+    double t = lane < NW ? S.wsum[2 * m + q][lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) __stcg(a.partials + (size_t)m * a.part_stride + (size_t)(slot + q) * BT_MAX_PARTIALS + blockIdx.x, t);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) g.arrive_wait();
+  __syncthreads();
+  for (int i = warp; i < nval; i += NW) {
+    const int m = S.act[i / nq], q = i % nq;
+    const double* pp = a.partials + (size_t)m * a.part_stride + (size_t)(slot + q) * BT_MAX_PARTIALS;
+    double t = 0.0;
+    for (unsigned int b = lane; b < gridDim.x; b += 32) t += __ldcg(pp + b);
+    t = warp_sum(t);
+    if (lane == 0) S.tot[2 * m + q] = t;
+  }
+  __syncthreads();
+}
+
+// Vector phases over (active member, row): work item w of a thread = (member act[w / R], row gid + (w % R) * gsz),
+// R = rows per thread -- the thread -> row mapping of pv_update_*; PB_U items are loaded before any is used.
+constexpr int PB_U = 4, PB_UV = 8;
+__device__ __noinline__ void pb_update_p(int n, size_t vstride, const PbState& S, int gid, int gsz, bool first,
+                                         const double2* rv, const double2* v, double2* p) {
+  const int R = (n + gsz - 1) / gsz, items = S.nact * R;
+  for (int w0 = 0; w0 < items; w0 += PB_UV) {
+    double2 rr[PB_UV], vv[PB_UV], pp[PB_UV];
+    size_t idx[PB_UV];
+    int mm[PB_UV];
+#pragma unroll
+    for (int u = 0; u < PB_UV; ++u) {
+      const int w = w0 + u;
+      mm[u] = -1;
+      rr[u] = vv[u] = pp[u] = make_double2(0.0, 0.0);
+      if (w < items) {
+        const int m = S.act[w / R], row = gid + (w % R) * gsz;
+        if (row < n) {
+          mm[u] = m;
+          idx[u] = (size_t)m * vstride + row;
+          rr[u] = rv[idx[u]];
+          if (!first) { vv[u] = v[idx[u]]; pp[u] = p[idx[u]]; }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PB_UV; ++u)
+      if (mm[u] >= 0) {
+        if (first) {
+          p[idx[u]] = rr[u];
+        } else {
+          const double beta = S.beta[mm[u]], ob = S.omega[mm[u]] * beta;
+          pp[u].x = rr[u].x - ob * vv[u].x + beta * pp[u].x;
+          pp[u].y = rr[u].y - ob * vv[u].y + beta * pp[u].y;
+          p[idx[u]] = pp[u];
+        }
+      }
+  }
+}
+__device__ __noinline__ void pb_update_s(int n, size_t vstride, const PbState& S, int gid, int gsz, const double2* rv,
+                                         const double2* v, double2* sv) {
+  const int R = (n + gsz - 1) / gsz, items = S.nact * R;
+  for (int w0 = 0; w0 < items; w0 += PB_UV) {
+    double2 rr[PB_UV], vv[PB_UV];
+    size_t idx[PB_UV];
+    int mm[PB_UV];
+#pragma unroll
+    for (int u = 0; u < PB_UV; ++u) {
+      const int w = w0 + u;
+      mm[u] = -1;
+      rr[u] = vv[u] = make_double2(0.0, 0.0);
+      if (w < items) {
+        const int m = S.act[w / R], row = gid + (w % R) * gsz;
+        if (row < n) {
+          mm[u] = m;
+          idx[u] = (size_t)m * vstride + row;
+          rr[u] = rv[idx[u]];
+          vv[u] = v[idx[u]];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PB_UV; ++u)
+      if (mm[u] >= 0) {
+        const double alpha = S.alpha[mm[u]];
+        sv[idx[u]] = make_double2(rr[u].x - alpha * vv[u].x, rr[u].y - alpha * vv[u].y);
+      }
+  }
+}
+// x <- x + alpha p + omega s ; r <- s - omega t ; acc[2m] += (r, r^), acc[2m+1] += (r, r)   (acc zeroed by the caller)
+template <int NT>
+__device__ __noinline__ void pb_update_xr(int n, size_t vstride, const PbState& S, int gid, int gsz, bool fresh,
+                                          const double2* p, const double2* sv, const double2* t, const double2* rp,
+                                          double2* x, double2* rv, double* acc) {
+  const int R = (n + gsz - 1) / gsz, items = S.nact * R;
+  for (int w0 = 0; w0 < items; w0 += PB_U) {
+    double2 pp[PB_U], ss[PB_U], tt[PB_U], qq[PB_U], xx[PB_U];
+    size_t idx[PB_U];
+    int mm[PB_U];
+#pragma unroll
+    for (int u = 0; u < PB_U; ++u) {
+      const int w = w0 + u;
+      mm[u] = -1;
+      pp[u] = ss[u] = tt[u] = qq[u] = xx[u] = make_double2(0.0, 0.0);
+      if (w < items) {
+        const int m = S.act[w / R], row = gid + (w % R) * gsz;
+        if (row < n) {
+          mm[u] = m;
+          idx[u] = (size_t)m * vstride + row;
+          pp[u] = p[idx[u]]; ss[u] = sv[idx[u]]; tt[u] = t[idx[u]]; qq[u] = rp[idx[u]];
+          if (!fresh) xx[u] = x[idx[u]];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PB_U; ++u)
+      if (mm[u] >= 0) {
+        const double alpha = S.alpha[mm[u]], omega = S.omega[mm[u]];
+        xx[u].x += alpha * pp[u].x + omega * ss[u].x;
+        xx[u].y += alpha * pp[u].y + omega * ss[u].y;
+        x[idx[u]] = xx[u];
+        const double2 rr = make_double2(ss[u].x - omega * tt[u].x, ss[u].y - omega * tt[u].y);
+        rv[idx[u]] = rr;
+        double* a0 = acc + (size_t)(2 * mm[u]) * NT;
+        a0[0] += rr.x * qq[u].x + rr.y * qq[u].y;
+        a0[NT] += rr.x * rr.x + rr.y * rr.y;
+      }
+  }
+}
+
+template <int NW, int D>
+__global__ void __launch_bounds__(NW * 32, 1) k_bicgstab_persistent_batch(SpmvArgs a) {
+  extern __shared__ __align__(128) unsigned char ps_ring[];
+  __shared__ PbState S;
+  constexpr int NT = NW * 32;
+  constexpr int ring_bytes = NW * D * PS_STAGE + NW * D * 8;   // ps_smem(NW, D)
+  double* acc_s = reinterpret_cast<double*>(ps_ring + ring_bytes);
+  double* acc = acc_s + threadIdx.x;
+  const int M = a.pb.members;
+  for (int m = 0; m < M; ++m)
+    if (a.ctrl[m].failed) return;   // uniform: written by an earlier launch only
+  const int lane = threadIdx.x & 31;
+  const int gsz = gridDim.x * NT, gid = blockIdx.x * NT + threadIdx.x;
+  const unsigned int all = M >= 32 ? 0xffffffffu : (1u << M) - 1u;
+  auto load_step_scalars = [&](int step) {   // thread 0
+    for (int m = 0; m < M; ++m) {
+      S.cb[m] = a.ctrl->theta_cb_scale * a.cb[(size_t)m * a.step_stride + step];
+      S.cA[m] = a.ctrl->theta_cA_scale * a.cA[(size_t)m * a.step_stride + step];
+    }
+  };
+  if (threadIdx.x == 0) {
+    S.mode = MODE_RHSP;
+    S.step = a.step_begin;
+    S.it = 0;
+    S.fail = 0;
+    S.active = all;
+    for (int m = 0; m < M; ++m) {
+      S.total_iters[m] = a.ctrl[m].total_iters;
+      S.max_iters[m] = a.ctrl[m].max_iters;
+      S.reason[m] = 0;
+      S.its[m] = 0;
+      S.rho[m] = S.rho_old[m] = S.alpha[m] = S.omega[m] = 1.0;
+      S.beta[m] = 0.0;
+      S.bn[m] = S.ttol[m] = S.rnorm[m] = 0.0;
+    }
+    S.bar_target = a.gridbar[32];
+    if (a.step_begin < a.step_end) load_step_scalars(a.step_begin);
+    pb_rebuild(S, a.pb);
+  }
+  WarpRing<D> r;
+  r.setup(ps_ring, a.ps_ptr, a.ps_piece, a.ps_c16);
+  const int nfl = min(D, r.np);
+  unsigned int c = 0;
+  const size_t sstr = a.pb.stream_stride;
+  const unsigned char* inring = a.QJt + (size_t)a.pb.g_dir[0] * sstr;   // the stream whose first nfl pieces are in the ring
+  if (lane == 0)
+    for (int i = 0; i < nfl; ++i) r.fetch(inring, i, (unsigned int)i);
+  __syncthreads();
+  GridSync gs;
+  gs.count = a.gridbar;
+  gs.target = 0;
+  const bool prof_on = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  unsigned long long tprev = prof_on ? global_ns() : 0ull;
+#define PROF(k)                                   \
+  if (prof_on) {                                  \
+    const unsigned long long tn_ = global_ns();   \
+    a.prof[k] += tn_ - tprev;                     \
+    tprev = tn_;                                  \
+  }
+
+  for (;;) {
+    const int mode = S.mode, step = S.step;
+    if (step >= a.step_end || S.fail) break;
+    const int nact = S.nact;
+    for (int i = 0; i < nact; ++i) {
+      const int m = S.act[i];
+      acc[(size_t)(2 * m) * NT] = 0.0;
+      acc[(size_t)(2 * m + 1) * NT] = 0.0;
+    }
+    // ---- passes: one per group with active members
+    {
+      const unsigned char* base = mode == MODE_RHSP ? a.QJt : a.PJt;
+      const double* ccs = mode == MODE_RHSP ? S.cb : S.cA;
+      const int gfirst = pb_next_group(S, a.pb, -1);
+      int g = gfirst;
+      while (g >= 0) {
+        const int gn = pb_next_group(S, a.pb, g);
+        const unsigned char* T = base + (size_t)a.pb.g_dir[g] * sstr;
+        // after the last group: the first group's v = A p / t = A s pass follows unless the step ends or members drop out
+        const unsigned char* Tn = gn >= 0 ? base + (size_t)a.pb.g_dir[gn] * sstr : a.PJt + (size_t)a.pb.g_dir[gfirst] * sstr;
+        if (inring != T) {   // the ring holds pieces of another stream: let them land, fetch the right ones
+          for (int i = 0; i < nfl; ++i) r.wait(c + i);
+          __syncwarp();
+          c += nfl;
+          if (lane == 0)
+            for (int i = 0; i < nfl; ++i) r.fetch(T, i, c + i);
+        }
+        c = pb_stream_pass<D, NT>(a, mode, r, c, T, Tn, S.unit[g], __popc((unsigned int)S.gmask[g]), ccs, acc);
+        inring = Tn;
+        g = gn;
+      }
+    }
+    PROF(mode == MODE_RHSP ? 0 : (mode == MODE_V ? 3 : 7));
+    gs.target = S.bar_target;
+    if (mode == MODE_V) {
+      // ---- alpha = rho / (r^, v) ; s = r - alpha v
+      pb_grid_reduce<NW>(a, S, acc_s, 1, 2, gs);
+      PROF(4);
+      if (threadIdx.x < nact) {   // one lane per active member (nact <= PB_MAX <= 32)
+        const int m = S.act[threadIdx.x];
+        const double d = S.tot[2 * m];
+        if (d == 0.0) { S.reason[m] = BTFEM_EBREAKDOWN; S.its[m] = S.it; atomicMin(&S.fail, (int)BTFEM_EBREAKDOWN); }
+        else S.alpha[m] = S.rho[m] / d;
+      }
+      __syncthreads();
+      if (!S.fail) {
+        pb_update_s(a.n, a.vec_stride, S, gid, gsz, a.r, a.v, a.s);
+        PROF(5);
+        grid_barrier(gs);
+        PROF(6);
+        if (threadIdx.x == 0) { S.mode = MODE_T; S.bar_target = gs.target; }
+        __syncthreads();
+        continue;
+      }
+    } else if (mode == MODE_T) {
+      // ---- omega = (t,s) / (t,t) ; x <- x + alpha p + omega s ; r <- s - omega t ; rho' = (r, r^) ; ||r||
+      pb_grid_reduce<NW>(a, S, acc_s, 2, 3, gs);
+      PROF(8);
+      if (threadIdx.x < nact) {
+        const int m = S.act[threadIdx.x];
+        S.omega[m] = (S.tot[2 * m + 1] == 0.0) ? 0.0 : S.tot[2 * m] / S.tot[2 * m + 1];
+      }
+      for (int i = 0; i < nact; ++i) {
+        const int m = S.act[i];
+        acc[(size_t)(2 * m) * NT] = 0.0;
+        acc[(size_t)(2 * m + 1) * NT] = 0.0;
+      }
+      __syncthreads();
+      pb_update_xr<NT>(a.n, a.vec_stride, S, gid, gsz, S.it == 0, a.p, a.s, a.t, a.rp, a.u, a.r, acc);
+      PROF(9);
+      pb_grid_reduce<NW>(a, S, acc_s, 2, 5, gs);
+      PROF(10);
+      if (threadIdx.x < 32) {   // warp 0, one lane per active member: the convergence tests of KSPConvergedDefault
+        const int it = S.it + 1;
+        const unsigned int before = S.active;
+        __syncwarp();
+        if (lane < nact) {
+          const int m = S.act[lane];
+          const double rho_used = S.rho[m], omega = S.omega[m], rho_new = S.tot[2 * m], rnorm = sqrt(S.tot[2 * m + 1]);
+          S.rho_old[m] = rho_used;
+          S.rho[m] = rho_new;
+          S.rnorm[m] = rnorm;
+          int reason = 0;
+          if (!(rnorm == rnorm) || isinf(rnorm)) reason = BTFEM_ENAN;
+          else if (rnorm <= S.ttol[m]) reason = rnorm < a.ctrl->atol ? 3 : 2;
+          else if (rnorm >= a.ctrl->dtol * S.bn[m]) reason = BTFEM_EDTOL;
+          else if (rho_used == 0.0 || omega == 0.0) reason = BTFEM_EBREAKDOWN;
+          else if (it >= a.ctrl->maxit) reason = BTFEM_ENOTCONV;
+          if (reason != 0) {
+            S.reason[m] = reason;
+            S.its[m] = it;
+            atomicAnd(&S.active, ~(1u << m));
+            if (reason < 0) atomicMin(&S.fail, reason);
+          } else {
+            S.beta[m] = (rho_new / rho_used) * (S.alpha[m] / omega);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          S.it = it;
+          if (S.active != before) pb_rebuild(S, a.pb);
+        }
+      }
+      __syncthreads();
+    } else {
+      // ---- ||r|| of every member: start of the Krylov solves of this step
+      pb_grid_reduce<NW>(a, S, acc_s, 1, 0, gs);
+      PROF(10);
+      if (threadIdx.x < 32) {
+        const unsigned int before = S.active;
+        __syncwarp();
+        if (lane < nact) {
+          const int m = S.act[lane];
+          const double atol = a.ctrl->atol;
+          const double bn = sqrt(S.tot[2 * m]);
+          const double ttol = fmax(a.ctrl->rtol * bn, atol);
+          S.bn[m] = bn;
+          S.ttol[m] = ttol;
+          S.rho[m] = S.tot[2 * m]; S.rho_old[m] = 1.0; S.alpha[m] = 1.0; S.omega[m] = 1.0; S.rnorm[m] = bn;
+          int reason = 0;
+          if (!(bn == bn) || isinf(bn)) reason = BTFEM_ENAN;
+          else if (bn <= ttol) reason = bn < atol ? 3 : 2;
+          if (reason != 0) {
+            S.reason[m] = reason;
+            S.its[m] = 0;
+            atomicAnd(&S.active, ~(1u << m));
+            if (reason < 0) atomicMin(&S.fail, reason);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          S.it = 0;
+          if (S.active != before) pb_rebuild(S, a.pb);
+        }
+      }
+      __syncthreads();
+    }
+    if (!S.fail && S.active != 0u) {
+      // ---- p <- r - omega*beta*v + beta*p   (first iteration: p = r), then v = A p
+      pb_update_p(a.n, a.vec_stride, S, gid, gsz, S.it == 0, a.r, a.v, a.p);
+      PROF(1);
+      grid_barrier(gs);
+      PROF(2);
+      if (threadIdx.x == 0) { S.mode = MODE_V; S.bar_target = gs.target; }
+      __syncthreads();
+      continue;
+    }
+    // ---- every member has finished the time step (or one has failed, which ends the batch)
+    if (!S.fail) {
+      bool anyz = false;   // converged before the first iteration with a zero guess: PETSc returns x = 0
+      for (int m = 0; m < M; ++m)
+        if (S.its[m] == 0 && S.reason[m] > 0) {
+          anyz = true;
+          double2* u = a.u + (size_t)m * a.vec_stride;
+          for (int i = gid; i < a.n; i += gsz) u[i] = make_double2(0.0, 0.0);
+        }
+      if (anyz) grid_barrier(gs);   // the next right-hand sides gather x
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int fail = S.fail;
+      for (int m = 0; m < M; ++m) {
+        const int it = S.its[m];
+        S.total_iters[m] += it;
+        S.max_iters[m] = max(S.max_iters[m], it);
+        if (blockIdx.x == 0) {
+          KrylovCtrl* ctrl = a.ctrl + m;
+          ctrl->bnorm = S.bn[m]; ctrl->ttol = S.ttol[m]; ctrl->rnorm = S.rnorm[m];
+          ctrl->rho = S.rho[m]; ctrl->rho_old = S.rho_old[m]; ctrl->alpha = S.alpha[m]; ctrl->omega = S.omega[m];
+          ctrl->iters = it; ctrl->reason = S.reason[m]; ctrl->done = 1;
+          ctrl->step = step; ctrl->step_next = step + 1;
+          ctrl->total_iters = S.total_iters[m]; ctrl->max_iters = S.max_iters[m];
+          if (fail) ctrl->failed = fail;   // a failure of any member stops every member (k_step_fail)
+        }
+      }
+      S.bar_target = gs.target;
+      if (!fail) {
+        S.step = step + 1;
+        S.mode = MODE_RHSP;
+        S.it = 0;
+        S.active = all;
+        for (int m = 0; m < M; ++m) { S.reason[m] = 0; S.its[m] = 0; }
+        if (step + 1 < a.step_end) load_step_scalars(step + 1);
+        pb_rebuild(S, a.pb);
+      }
+    }
+    __syncthreads();
+  }
+  // nothing may still be in flight into shared memory when the block retires
+  for (int i = 0; i < nfl; ++i) r.wait(c + i);
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.gridbar[32] = S.bar_target;
+#undef PROF
+}
+
+
+// ---- lock-step batches on a SMALL mesh as one cooperative kernel with many warps ("coop" batch kernel, the default for
+// batches of up to PB_MAX members on whole-mesh handles).  ncu on the kernel chain (profiles/r2ai_*) shows where a
+// 16-member iteration on a 46 k-vertex mesh goes: 52 us per batched SpMV although neither the operator bytes (one copy
+// per direction changes nothing), nor the gather locality (the SELL window changes nothing) bound it -- every block
+// walks ctrl -> schedule -> slice -> columns -> gather -> epilogue -> ticket for ONE slice per warp, 6.5 waves of
+// blocks per launch.  Here the whole time loop is one launch of 1024-thread blocks (32 warps per SM, <= 64 registers):
+//  * passes: the (active member, slice) items of a phase, member-major, are cut into one contiguous chunk per block
+//    (<= 2 members per block); inside a block the 32 warps take 32 neighbouring slices at a time (they share gathered
+//    x lines in L1), the position rotating from round to round so that no warp always gets the longest rows of a
+//    sorting window.  One operator copy per direction (bt_combine: members of a direction share it), plain SELL loads;
+//  * vector phases: the (active member, row) space cut into one chunk per block, fully coalesced;
+//  * reductions: per-block partials for its <= 2 members, then every block adds the partials of all blocks in a fixed
+//    order (deterministic for a given batch; the grouping depends on which members are active, so a member's bits
+//    depend on the batch it travels in -- unlike the kernel chain).
+// The scalar recurrences, convergence tests and reason codes are those of k_bicgstab_persistent.
+constexpr int CB_NT = 1024;
+constexpr int CHB_U = 4;   // columns of a row in flight in k_bicgstab_coop_hb
+
+// thread 0: the list of active members
+__device__ __forceinline__ void cb_rebuild(PbState& S, int M) {
+  int na = 0;
+  for (int m = 0; m < M; ++m)
+    if ((S.active >> m) & 1u) S.act[na++] = (unsigned char)m;
+  S.nact = na;
+}
+
+// acc0 / acc1: this thread's terms for the block's first member (active index ai0) and the one after it; nq values each.
+template <int NT>
+__device__ __forceinline__ void cb_grid_reduce(const SpmvArgs& a, PbState& S, double (*wacc)[4], const double (&acc0)[2],
+                                               const double (&acc1)[2], int ai0, int nq, int slot, GridSync& g) {
+  constexpr int NWB = NT / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nact = S.nact, nval = nact * nq;
+  {
+    const double t0 = warp_sum(acc0[0]), t2 = warp_sum(acc1[0]);
+    double t1 = 0.0, t3 = 0.0;
+    if (nq == 2) { t1 = warp_sum(acc0[1]); t3 = warp_sum(acc1[1]); }
+    if (lane == 0) { wacc[warp][0] = t0; wacc[warp][1] = t1; wacc[warp][2] = t2; wacc[warp][3] = t3; }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nval) {   // block partial of value (ai, q): zero unless the block holds rows of that member
+    const int ai = threadIdx.x / nq, q = threadIdx.x % nq, m = S.act[ai];
+    double t = 0.0;
+    if (ai == ai0 || ai == ai0 + 1) {
+      const int c = (ai - ai0) * 2 + q;
+      for (int w = 0; w < NWB; ++w) t += wacc[w][c];
+    }
+    __stcg(a.partials + (size_t)m * a.part_stride + (size_t)(slot + q) * BT_MAX_PARTIALS + blockIdx.x, t);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) g.arrive_wait();
+  __syncthreads();
+  for (int i = warp; i < nval; i += NWB) {
+    const int m = S.act[i / nq], q = i % nq;
+    const double* pp = a.partials + (size_t)m * a.part_stride + (size_t)(slot + q) * BT_MAX_PARTIALS;
+    double t = 0.0;
+    for (unsigned int b = lane; b < gridDim.x; b += 32) t += __ldcg(pp + b);
+    t = warp_sum(t);
+    if (lane == 0) S.tot[2 * m + q] = t;
+  }
+  __syncthreads();
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) k_bicgstab_coop_batch(SpmvArgs a) {
+  __shared__ PbState S;
+  __shared__ double wacc[NT / 32][4];
+  __shared__ int sdir[PB_MAX];
+  constexpr int NWB = NT / 32;
+  const int M = a.pb.members;
+  for (int m = 0; m < M; ++m)
+    if (a.ctrl[m].failed) return;   // uniform: written by an earlier launch only
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int all = M >= 32 ? 0xffffffffu : (1u << M) - 1u;
+  const int n = a.n, NS = a.nslice, NB = gridDim.x;
+  const size_t vs = a.vec_stride;
+  auto load_step_scalars = [&](int step) {   // thread 0
+    for (int m = 0; m < M; ++m) {
+      S.cb[m] = a.ctrl->theta_cb_scale * a.cb[(size_t)m * a.step_stride + step];
+      S.cA[m] = a.ctrl->theta_cA_scale * a.cA[(size_t)m * a.step_stride + step];
+    }
+  };
+  if (threadIdx.x == 0) {
+    S.mode = MODE_RHSP;
+    S.step = a.step_begin;
+    S.it = 0;
+    S.fail = 0;
+    S.active = all;
+    for (int m = 0; m < M; ++m) {
+      S.total_iters[m] = a.ctrl[m].total_iters;
+      S.max_iters[m] = a.ctrl[m].max_iters;
+      S.reason[m] = 0;
+      S.its[m] = 0;
+      S.rho[m] = S.rho_old[m] = S.alpha[m] = S.omega[m] = 1.0;
+      S.beta[m] = 0.0;
+      S.bn[m] = S.ttol[m] = S.rnorm[m] = 0.0;
+    }
+    S.bar_target = a.gridbar[32];
+    if (a.step_begin < a.step_end) load_step_scalars(a.step_begin);
+    cb_rebuild(S, M);
+  }
+  if ((int)threadIdx.x < M) sdir[threadIdx.x] = a.member_dir ? a.member_dir[threadIdx.x] : (int)threadIdx.x;
+  __syncthreads();
+  GridSync gs;
+  gs.count = a.gridbar;
+  gs.target = 0;
+  const bool prof_on = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  unsigned long long tprev = prof_on ? global_ns() : 0ull;
+#define PROF(k)                                   \
+  if (prof_on) {                                  \
+    const unsigned long long tn_ = global_ns();   \
+    a.prof[k] += tn_ - tprev;                     \
+    tprev = tn_;                                  \
+  }
+
+  for (;;) {
+    const int mode = S.mode, step = S.step;
+    if (step >= a.step_end || S.fail) break;
+    const int nact = S.nact;
+    // chunk of this block in the (active member, row) space of the vector phases
+    const long long WV = (long long)nact * n;
+    const long long clo = WV * blockIdx.x / NB, chi = WV * (blockIdx.x + 1) / NB;
+    const int aiv0 = (int)(clo / n);
+    double acc0[2] = {0.0, 0.0}, acc1[2] = {0.0, 0.0};
+    int ai0;
+    const unsigned long long tp0 = a.prof ? global_ns() : 0ull;
+    // ---- pass: y_m = (V.x + i c_m V.y) x_m over this block's chunk of the (active member, slice) items
+    {
+      const long long W = (long long)nact * NS;
+      const int blo = (int)(W * blockIdx.x / NB), bhi = (int)(W * (blockIdx.x + 1) / NB);
+      ai0 = blo / NS;
+      const double2* Vb = mode == MODE_RHSP ? a.QJs : a.PJs;
+      const double2* xbase = mode == MODE_RHSP ? a.u : (mode == MODE_V ? a.p : a.s);
+      const double2* opbase = mode == MODE_V ? a.rp : (mode == MODE_T ? a.s : nullptr);
+      const double* ccs = mode == MODE_RHSP ? S.cb : S.cA;
+      int k = 0;
+      for (int i0 = blo; i0 < bhi; i0 += NWB, ++k) {
+        const int v = i0 + ((warp + 7 * k) & (NWB - 1));
+        if (v < bhi) {
+          const int ai = v / NS, s = v - ai * NS, m = S.act[ai];
+          const int base = __ldg(a.slice_ptr + s);
+          const int width = (__ldg(a.slice_ptr + s + 1) - base) >> 5;
+          const int row = __ldg(a.sell_row + s * 32 + lane);
+          const size_t off = (size_t)m * vs + (row >= 0 ? row : 0);
+          double2 op = make_double2(0.0, 0.0);
+          if (opbase && row >= 0) op = opbase[off];
+          const double2 y = slice_product<4>(a.sell_col + base + lane, Vb + (size_t)sdir[m] * a.mat_stride_sell + base + lane,
+                                             width, xbase + (size_t)m * vs, ccs[m]);
+          if (row >= 0) {
+            double t0, t1 = 0.0;
+            if (mode == MODE_V) {
+              a.v[off] = y;
+              t0 = y.x * op.x + y.y * op.y;
+            } else if (mode == MODE_T) {
+              a.t[off] = y;
+              t0 = op.x * y.x + op.y * y.y;
+              t1 = y.x * y.x + y.y * y.y;
+            } else {
+              a.r[off] = y;
+              a.rp[off] = y;
+              t0 = y.x * y.x + y.y * y.y;
+            }
+            if (ai == ai0) { acc0[0] += t0; acc0[1] += t1; }
+            else { acc1[0] += t0; acc1[1] += t1; }
+          }
+        }
+      }
+    }
+    if (a.prof && threadIdx.x == 0) a.prof[16 + blockIdx.x] += global_ns() - tp0;   // per-block time inside the passes
+    PROF(mode == MODE_RHSP ? 0 : (mode == MODE_V ? 3 : 7));
+    gs.target = S.bar_target;
+    if (mode == MODE_V) {
+      // ---- alpha = rho / (r^, v) ; s = r - alpha v
+      cb_grid_reduce<NT>(a, S, wacc, acc0, acc1, ai0, 1, 2, gs);
+      PROF(4);
+      if ((int)threadIdx.x < nact) {
+        const int m = S.act[threadIdx.x];
+        const double d = S.tot[2 * m];
+        if (d == 0.0) { S.reason[m] = BTFEM_EBREAKDOWN; S.its[m] = S.it; atomicMin(&S.fail, (int)BTFEM_EBREAKDOWN); }
+        else S.alpha[m] = S.rho[m] / d;
+      }
+      __syncthreads();
+      if (!S.fail) {
+        for (long long i = clo + threadIdx.x; i < chi; i += NT) {
+          const int ai = (int)(i / n), row = (int)(i - (long long)ai * n), m = S.act[ai];
+          const size_t off = (size_t)m * vs + row;
+          const double alpha = S.alpha[m];
+          const double2 rr = a.r[off], vv = a.v[off];
+          a.s[off] = make_double2(rr.x - alpha * vv.x, rr.y - alpha * vv.y);
+        }
+        PROF(5);
+        grid_barrier(gs);
+        PROF(6);
+        if (threadIdx.x == 0) { S.mode = MODE_T; S.bar_target = gs.target; }
+        __syncthreads();
+        continue;
+      }
+    } else if (mode == MODE_T) {
+      // ---- omega = (t,s) / (t,t) ; x <- x + alpha p + omega s ; r <- s - omega t ; rho' = (r, r^) ; ||r||
+      cb_grid_reduce<NT>(a, S, wacc, acc0, acc1, ai0, 2, 3, gs);
+      PROF(8);
+      if ((int)threadIdx.x < nact) {
+        const int m = S.act[threadIdx.x];
+        S.omega[m] = (S.tot[2 * m + 1] == 0.0) ? 0.0 : S.tot[2 * m] / S.tot[2 * m + 1];
+      }
+      __syncthreads();
+      acc0[0] = acc0[1] = acc1[0] = acc1[1] = 0.0;
+      {
+        const bool fresh = S.it == 0;   // zero initial guess: x starts from 0
+        for (long long i = clo + threadIdx.x; i < chi; i += NT) {
+          const int ai = (int)(i / n), row = (int)(i - (long long)ai * n), m = S.act[ai];
+          const size_t off = (size_t)m * vs + row;
+          const double alpha = S.alpha[m], omega = S.omega[m];
+          const double2 pp = a.p[off], ss = a.s[off], tt = a.t[off], qq = a.rp[off];
+          double2 xx = make_double2(0.0, 0.0);
+          if (!fresh) xx = a.u[off];
+          xx.x += alpha * pp.x + omega * ss.x;
+          xx.y += alpha * pp.y + omega * ss.y;
+          a.u[off] = xx;
+          const double2 rr = make_double2(ss.x - omega * tt.x, ss.y - omega * tt.y);
+          a.r[off] = rr;
+          const double t0 = rr.x * qq.x + rr.y * qq.y, t1 = rr.x * rr.x + rr.y * rr.y;
+          if (ai == aiv0) { acc0[0] += t0; acc0[1] += t1; }
+          else { acc1[0] += t0; acc1[1] += t1; }
+        }
+      }
+      PROF(9);
+      cb_grid_reduce<NT>(a, S, wacc, acc0, acc1, aiv0, 2, 5, gs);
+      PROF(10);
+      if (threadIdx.x < 32) {   // warp 0, one lane per active member: the convergence tests of KSPConvergedDefault
+        const int it = S.it + 1;
+        const unsigned int before = S.active;
+        __syncwarp();
+        if (lane < nact) {
+          const int m = S.act[lane];
+          const double rho_used = S.rho[m], omega = S.omega[m], rho_new = S.tot[2 * m], rnorm = sqrt(S.tot[2 * m + 1]);
+          S.rho_old[m] = rho_used;
+          S.rho[m] = rho_new;
+          S.rnorm[m] = rnorm;
+          int reason = 0;
+          if (!(rnorm == rnorm) || isinf(rnorm)) reason = BTFEM_ENAN;
+          else if (rnorm <= S.ttol[m]) reason = rnorm < a.ctrl->atol ? 3 : 2;
+          else if (rnorm >= a.ctrl->dtol * S.bn[m]) reason = BTFEM_EDTOL;
+          else if (rho_used == 0.0 || omega == 0.0) reason = BTFEM_EBREAKDOWN;
+          else if (it >= a.ctrl->maxit) reason = BTFEM_ENOTCONV;
+          if (reason != 0) {
+            S.reason[m] = reason;
+            S.its[m] = it;
+            atomicAnd(&S.active, ~(1u << m));
+            if (reason < 0) atomicMin(&S.fail, reason);
+          } else {
+            S.beta[m] = (rho_new / rho_used) * (S.alpha[m] / omega);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          S.it = it;
+          if (S.active != before) cb_rebuild(S, M);
+        }
+      }
+      __syncthreads();
+    } else {
+      // ---- ||r|| of every member: start of the Krylov solves of this step
+      cb_grid_reduce<NT>(a, S, wacc, acc0, acc1, ai0, 1, 0, gs);
+      PROF(10);
+      if (threadIdx.x < 32) {
+        const unsigned int before = S.active;
+        __syncwarp();
+        if (lane < nact) {
+          const int m = S.act[lane];
+          const double atol = a.ctrl->atol;
+          const double bn = sqrt(S.tot[2 * m]);
+          const double ttol = fmax(a.ctrl->rtol * bn, atol);
+          S.bn[m] = bn;
+          S.ttol[m] = ttol;
+          S.rho[m] = S.tot[2 * m]; S.rho_old[m] = 1.0; S.alpha[m] = 1.0; S.omega[m] = 1.0; S.rnorm[m] = bn;
+          int reason = 0;
+          if (!(bn == bn) || isinf(bn)) reason = BTFEM_ENAN;
+          else if (bn <= ttol) reason = bn < atol ? 3 : 2;
+          if (reason != 0) {
+            S.reason[m] = reason;
+            S.its[m] = 0;
+            atomicAnd(&S.active, ~(1u << m));
+            if (reason < 0) atomicMin(&S.fail, reason);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          S.it = 0;
+          if (S.active != before) cb_rebuild(S, M);
+        }
+      }
+      __syncthreads();
+    }
+    if (!S.fail && S.active != 0u) {
+      // ---- p <- r - omega*beta*v + beta*p   (first iteration: p = r), then v = A p.  The active set may just have
+      // shrunk: the chunk of this block is cut again from the members that go on
+      const int nact2 = S.nact;
+      const long long WV2 = (long long)nact2 * n;
+      const long long plo = WV2 * blockIdx.x / NB, phi = WV2 * (blockIdx.x + 1) / NB;
+      const bool first = S.it == 0;
+      for (long long i = plo + threadIdx.x; i < phi; i += NT) {
+        const int ai = (int)(i / n), row = (int)(i - (long long)ai * n), m = S.act[ai];
+        const size_t off = (size_t)m * vs + row;
+        const double2 rr = a.r[off];
+        if (first) {
+          a.p[off] = rr;
+        } else {
+          const double beta = S.beta[m], ob = S.omega[m] * beta;
+          const double2 vv = a.v[off];
+          double2 pp = a.p[off];
+          pp.x = rr.x - ob * vv.x + beta * pp.x;
+          pp.y = rr.y - ob * vv.y + beta * pp.y;
+          a.p[off] = pp;
+        }
+      }
+      PROF(1);
+      grid_barrier(gs);
+      PROF(2);
+      if (threadIdx.x == 0) { S.mode = MODE_V; S.bar_target = gs.target; }
+      __syncthreads();
+      continue;
+    }
+    // ---- every member has finished the time step (or one has failed, which ends the batch)
+    if (!S.fail) {
+      bool anyz = false;   // converged before the first iteration with a zero guess: PETSc returns x = 0
+      for (int m = 0; m < M; ++m)
+        if (S.its[m] == 0 && S.reason[m] > 0) {
+          anyz = true;
+          double2* u = a.u + (size_t)m * vs;
+          for (int i = blockIdx.x * NT + threadIdx.x; i < n; i += NB * NT) u[i] = make_double2(0.0, 0.0);
+        }
+      if (anyz) grid_barrier(gs);   // the next right-hand sides gather x
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int fail = S.fail;
+      for (int m = 0; m < M; ++m) {
+        const int it = S.its[m];
+        S.total_iters[m] += it;
+        S.max_iters[m] = max(S.max_iters[m], it);
+        if (blockIdx.x == 0) {
+          KrylovCtrl* ctrl = a.ctrl + m;
+          ctrl->bnorm = S.bn[m]; ctrl->ttol = S.ttol[m]; ctrl->rnorm = S.rnorm[m];
+          ctrl->rho = S.rho[m]; ctrl->rho_old = S.rho_old[m]; ctrl->alpha = S.alpha[m]; ctrl->omega = S.omega[m];
+          ctrl->iters = it; ctrl->reason = S.reason[m]; ctrl->done = 1;
+          ctrl->step = step; ctrl->step_next = step + 1;
+          ctrl->total_iters = S.total_iters[m]; ctrl->max_iters = S.max_iters[m];
+          if (fail) ctrl->failed = fail;   // a failure of any member stops every member (k_step_fail)
+        }
+      }
+      S.bar_target = gs.target;
+      if (!fail) {
+        S.step = step + 1;
+        S.mode = MODE_RHSP;
+        S.it = 0;
+        S.active = all;
+        for (int m = 0; m < M; ++m) { S.reason[m] = 0; S.its[m] = 0; }
+        if (step + 1 < a.step_end) load_step_scalars(step + 1);
+        cb_rebuild(S, M);
+      }
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.gridbar[32] = S.bar_target;
+#undef PROF
+}
+
+
 // ---- batched solves: the shared-operator SELL kernel.  The members of a batch (HARDI: directions x b-values on
 // one mesh) differ in the direction g and the scalar c only, so the matrix is read ONCE per slice for BM members:
 // (column, P|Q, Jx, Jy, Jz) = 44 bytes per nonzero for the whole group instead of 20 bytes per member, and it
@@ -1867,6 +2840,409 @@ __global__ void __launch_bounds__(TPB) k_hb_signal(SpmvArgs a, const double* __r
     a.sig_out[2 * mb] = tot[0];
     a.sig_out[2 * mb + 1] = tot[1];
   });
+}
+
+// ---- the member-interleaved batch as ONE cooperative kernel (BTFEM_BATCH_PERSIST=hb).  The passes of the member
+// layout are bound by the L1 wavefront rate: a 16-byte gather per lane touches ~32 different 128-byte lines per
+// warp-load (measured 1.6 clk per nonzero and member, k_bicgstab_coop_batch).  Here a warp works on 4 rows x 8 members:
+// x[row][member] is one full line per row, so a warp-load touches 4 lines; the direction-independent operator
+// ((P|Q), Jx, Jy, Jz) is read once per 8 members and J_g formed per member with the rounding of k_combine (k_hb_spmv).
+// Same phases, grid barrier and reductions as k_bicgstab_coop_batch; work units of a pass are "super-tasks" of 4
+// neighbouring slices (32 warps x 4 rows) dealt round-robin over the blocks, so that every block sees long and short
+// rows of the sorting windows alike.
+__device__ __forceinline__ void chb_rebuild(PbState& S, int M) {
+  int na = 0, ng = 0;
+  for (int m = 0; m < M; ++m)
+    if ((S.active >> m) & 1u) S.act[na++] = (unsigned char)m;
+  for (int g = 0; g * HB < M; ++g)
+    if ((S.active >> (g * HB)) & 0xffu) S.actg[ng++] = (unsigned char)g;
+  S.nact = na;
+  S.ngact = ng;
+}
+
+// acc[gi][q]: this thread's terms for member (lane & 7) of active group gi
+template <int NT>
+__device__ __forceinline__ void chb_grid_reduce(const SpmvArgs& a, PbState& S, double (*wacc)[2][2][HB], const double (&acc)[2][2],
+                                                int M, int nq, int slot, GridSync& g) {
+  constexpr int NWB = NT / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int gi = 0; gi < 2; ++gi)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      double t = acc[gi][q];
+      t += __shfl_xor_sync(0xffffffffu, t, 8);
+      t += __shfl_xor_sync(0xffffffffu, t, 16);
+      if (lane < HB) wacc[warp][gi][q][lane] = t;
+    }
+  __syncthreads();
+  if ((int)threadIdx.x < 2 * HB * nq) {   // block partial of (active group gi, member ml of it, q)
+    const int gi = threadIdx.x / (HB * nq), r = threadIdx.x - gi * HB * nq, ml = r / nq, q = r - ml * nq;
+    if (gi < S.ngact) {
+      const int m = S.actg[gi] * HB + ml;
+      if (m < M && ((S.active >> m) & 1u)) {
+        double t = 0.0;
+        for (int w = 0; w < NWB; ++w) t += wacc[w][gi][q][ml];
+        __stcg(a.partials + (size_t)m * a.part_stride + (size_t)(slot + q) * BT_MAX_PARTIALS + blockIdx.x, t);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) g.arrive_wait();
+  __syncthreads();
+  const int nval = S.nact * nq;
+  for (int i = warp; i < nval; i += NWB) {
+    const int m = S.act[i / nq], q = i % nq;
+    const double* pp = a.partials + (size_t)m * a.part_stride + (size_t)(slot + q) * BT_MAX_PARTIALS;
+    double t = 0.0;
+    for (unsigned int b = lane; b < gridDim.x; b += 32) t += __ldcg(pp + b);
+    t = warp_sum(t);
+    if (lane == 0) S.tot[2 * m + q] = t;
+  }
+  __syncthreads();
+}
+
+template <int NT, int U>
+__global__ void __launch_bounds__(NT, 1) k_bicgstab_coop_hb(SpmvArgs a) {
+  __shared__ PbState S;
+  __shared__ double wacc[NT / 32][2][2][HB];
+  static_assert(NT % 256 == 0, "a super-task is NT / 256 slices: 8 warps x 4 rows each");
+  constexpr int SPT = NT / 256;   // slices per super-task
+  const int M = a.pb.members;
+  for (int m = 0; m < M; ++m)
+    if (a.ctrl0[m].failed) return;   // uniform: written by an earlier launch only
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ml = lane & (HB - 1);
+  const unsigned int all = M >= 32 ? 0xffffffffu : (1u << M) - 1u;
+  const int n = a.n, NS = a.nslice, NB = gridDim.x;
+  const size_t npadHB = a.vec_stride / 7 * HB;
+  KrylovCtrl* ctrl0 = a.ctrl0;
+  auto load_step_scalars = [&](int step) {   // thread 0
+    for (int m = 0; m < M; ++m) {
+      S.cb[m] = ctrl0->theta_cb_scale * a.cb[(size_t)m * a.step_stride + step];
+      S.cA[m] = ctrl0->theta_cA_scale * a.cA[(size_t)m * a.step_stride + step];
+    }
+  };
+  if (threadIdx.x == 0) {
+    S.mode = MODE_RHSP;
+    S.step = a.step_begin;
+    S.it = 0;
+    S.fail = 0;
+    S.active = all;
+    for (int m = 0; m < M; ++m) {
+      S.total_iters[m] = ctrl0[m].total_iters;
+      S.max_iters[m] = ctrl0[m].max_iters;
+      S.reason[m] = 0;
+      S.its[m] = 0;
+      S.rho[m] = S.rho_old[m] = S.alpha[m] = S.omega[m] = 1.0;
+      S.beta[m] = 0.0;
+      S.bn[m] = S.ttol[m] = S.rnorm[m] = 0.0;
+      S.gd[m][0] = a.gdirs[3 * m]; S.gd[m][1] = a.gdirs[3 * m + 1]; S.gd[m][2] = a.gdirs[3 * m + 2];
+    }
+    S.bar_target = a.gridbar[32];
+    if (a.step_begin < a.step_end) load_step_scalars(a.step_begin);
+    chb_rebuild(S, M);
+  }
+  __syncthreads();
+  GridSync gs;
+  gs.count = a.gridbar;
+  gs.target = 0;
+  const bool prof_on = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  unsigned long long tprev = prof_on ? global_ns() : 0ull;
+#define PROF(k)                                   \
+  if (prof_on) {                                  \
+    const unsigned long long tn_ = global_ns();   \
+    a.prof[k] += tn_ - tprev;                     \
+    tprev = tn_;                                  \
+  }
+  const double atol = ctrl0->atol, rtol = ctrl0->rtol, dtol = ctrl0->dtol;
+  const int maxit = ctrl0->maxit;
+
+  for (;;) {
+    const int mode = S.mode, step = S.step;
+    if (step >= a.step_end || S.fail) break;
+    const int nact = S.nact, ngact = S.ngact;
+    const unsigned int active = S.active;
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    // rows of the (active group, row) space this block takes in the vector phases (8 members = one line per row)
+    const long long WV = (long long)ngact * n;
+    const long long rlo = WV * blockIdx.x / NB, rhi = WV * (blockIdx.x + 1) / NB;
+    const unsigned long long tp0 = a.prof ? global_ns() : 0ull;
+    // ---- pass over the super-tasks (active group, 4 slices) of this block
+    {
+      const int NST = (NS + SPT - 1) / SPT;
+      const int rslot = (warp & 7) * 4 + (lane >> 3);
+      for (int j = blockIdx.x; j < ngact * NST; j += NB) {
+        const int gi = j / NST, st = j - gi * NST, g = S.actg[gi];
+        const int slice = SPT * st + (warp >> 3);
+        if (slice >= NS) continue;
+        const int m = g * HB + ml;
+        const bool act = m < M && ((active >> m) & 1u);
+        const int mm = m < M ? m : 0;
+        const double gx = S.gd[mm][0], gy = S.gd[mm][1], gz = S.gd[mm][2];
+        const double cc = mode == MODE_RHSP ? S.cb[mm] : S.cA[mm];
+        double2* vb = a.u + (size_t)g * 7 * npadHB;   // u, r, rp, p, v, s, t of the group, npadHB apart
+        const double2* x = (mode == MODE_RHSP ? vb : (mode == MODE_V ? vb + 3 * npadHB : vb + 5 * npadHB)) + ml;
+        const int base = __ldg(a.slice_ptr + slice);
+        const int width = (__ldg(a.slice_ptr + slice + 1) - base) >> 5;
+        const int row = __ldg(a.sell_row + slice * 32 + rslot);   // -1: padding slot past the last row
+        const double di = row >= 0 ? __ldg(a.dinv + row) : 0.0;
+        const size_t e = (size_t)(row >= 0 ? row : 0) * HB + ml;
+        double2 op = make_double2(0.0, 0.0);
+        if (row >= 0 && act && mode != MODE_RHSP) op = (mode == MODE_V ? vb + 2 * npadHB : vb + 5 * npadHB)[e];
+        const int32_t* cp = a.sell_col + base + rslot;
+        const double2* pq = a.PQs + base + rslot;
+        const double2* jxy = a.Jxys + base + rslot;
+        const double* jz = a.Jzs + base + rslot;
+        double yr = 0.0, yi = 0.0;
+        for (int j0 = 0; j0 < width; j0 += U) {
+          int col[U];
+          double2 xv[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) col[u] = j0 + u < width ? __ldg(cp + (j0 + u) * 32) : -1;
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (col[u] >= 0) xv[u] = ldv_gather_f64x2(x + (size_t)col[u] * HB);
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (col[u] >= 0) {
+              const double2 pqv = __ldg(pq + (j0 + u) * 32), jv = __ldg(jxy + (j0 + u) * 32);
+              const double jzv = __ldg(jz + (j0 + u) * 32);
+              const double pa = mode == MODE_RHSP ? pqv.y : pqv.x;
+              const double pb = cc * comb_jg(gx, gy, gz, jv.x, jv.y, jzv, di);
+              yr = fma(pa, xv[u].x, yr);
+              yr = fma(-pb, xv[u].y, yr);
+              yi = fma(pa, xv[u].y, yi);
+              yi = fma(pb, xv[u].x, yi);
+            }
+        }
+        if (row >= 0 && act) {
+          const double2 y = make_double2(yr, yi);
+          double t0, t1 = 0.0;
+          if (mode == MODE_V) {
+            vb[4 * npadHB + e] = y;
+            t0 = y.x * op.x + y.y * op.y;
+          } else if (mode == MODE_T) {
+            vb[6 * npadHB + e] = y;
+            t0 = op.x * y.x + op.y * y.y;
+            t1 = y.x * y.x + y.y * y.y;
+          } else {
+            vb[npadHB + e] = y;
+            vb[2 * npadHB + e] = y;
+            t0 = y.x * y.x + y.y * y.y;
+          }
+          if (gi == 0) { acc[0][0] += t0; acc[0][1] += t1; }
+          else { acc[1][0] += t0; acc[1][1] += t1; }
+        }
+      }
+    }
+    if (a.prof && threadIdx.x == 0) a.prof[16 + blockIdx.x] += global_ns() - tp0;   // per-block time inside the passes
+    PROF(mode == MODE_RHSP ? 0 : (mode == MODE_V ? 3 : 7));
+    gs.target = S.bar_target;
+    if (mode == MODE_V) {
+      // ---- alpha = rho / (r^, v) ; s = r - alpha v
+      chb_grid_reduce<NT>(a, S, wacc, acc, M, 1, 2, gs);
+      PROF(4);
+      if ((int)threadIdx.x < nact) {
+        const int m = S.act[threadIdx.x];
+        const double d = S.tot[2 * m];
+        if (d == 0.0) { S.reason[m] = BTFEM_EBREAKDOWN; S.its[m] = S.it; atomicMin(&S.fail, (int)BTFEM_EBREAKDOWN); }
+        else S.alpha[m] = S.rho[m] / d;
+      }
+      __syncthreads();
+      if (!S.fail) {
+        for (long long i = rlo * HB + threadIdx.x; i < rhi * HB; i += NT) {
+          const long long rr_ = i / HB;
+          const int gi = (int)(rr_ / n), g = S.actg[gi], m = g * HB + ml;
+          if (m < M && ((active >> m) & 1u)) {
+            const size_t e = (size_t)(i - (long long)gi * n * HB);
+            double2* vb = a.u + (size_t)g * 7 * npadHB;
+            const double alpha = S.alpha[m];
+            const double2 rr = vb[npadHB + e], vv = vb[4 * npadHB + e];
+            vb[5 * npadHB + e] = make_double2(rr.x - alpha * vv.x, rr.y - alpha * vv.y);
+          }
+        }
+        PROF(5);
+        grid_barrier(gs);
+        PROF(6);
+        if (threadIdx.x == 0) { S.mode = MODE_T; S.bar_target = gs.target; }
+        __syncthreads();
+        continue;
+      }
+    } else if (mode == MODE_T) {
+      // ---- omega = (t,s) / (t,t) ; x <- x + alpha p + omega s ; r <- s - omega t ; rho' = (r, r^) ; ||r||
+      chb_grid_reduce<NT>(a, S, wacc, acc, M, 2, 3, gs);
+      PROF(8);
+      if ((int)threadIdx.x < nact) {
+        const int m = S.act[threadIdx.x];
+        S.omega[m] = (S.tot[2 * m + 1] == 0.0) ? 0.0 : S.tot[2 * m] / S.tot[2 * m + 1];
+      }
+      __syncthreads();
+      acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = 0.0;
+      {
+        const bool fresh = S.it == 0;   // zero initial guess: x starts from 0
+        for (long long i = rlo * HB + threadIdx.x; i < rhi * HB; i += NT) {
+          const long long rr_ = i / HB;
+          const int gi = (int)(rr_ / n), g = S.actg[gi], m = g * HB + ml;
+          if (m < M && ((active >> m) & 1u)) {
+            const size_t e = (size_t)(i - (long long)gi * n * HB);
+            double2* vb = a.u + (size_t)g * 7 * npadHB;
+            const double alpha = S.alpha[m], omega = S.omega[m];
+            const double2 pp = vb[3 * npadHB + e], ss = vb[5 * npadHB + e], tt = vb[6 * npadHB + e], qq = vb[2 * npadHB + e];
+            double2 xx = make_double2(0.0, 0.0);
+            if (!fresh) xx = vb[e];
+            xx.x += alpha * pp.x + omega * ss.x;
+            xx.y += alpha * pp.y + omega * ss.y;
+            vb[e] = xx;
+            const double2 rr = make_double2(ss.x - omega * tt.x, ss.y - omega * tt.y);
+            vb[npadHB + e] = rr;
+            const double t0 = rr.x * qq.x + rr.y * qq.y, t1 = rr.x * rr.x + rr.y * rr.y;
+            if (gi == 0) { acc[0][0] += t0; acc[0][1] += t1; }
+            else { acc[1][0] += t0; acc[1][1] += t1; }
+          }
+        }
+      }
+      PROF(9);
+      chb_grid_reduce<NT>(a, S, wacc, acc, M, 2, 5, gs);
+      PROF(10);
+      if (threadIdx.x < 32) {   // warp 0, one lane per active member: the convergence tests of KSPConvergedDefault
+        const int it = S.it + 1;
+        const unsigned int before = S.active;
+        __syncwarp();
+        if (lane < nact) {
+          const int m = S.act[lane];
+          const double rho_used = S.rho[m], omega = S.omega[m], rho_new = S.tot[2 * m], rnorm = sqrt(S.tot[2 * m + 1]);
+          S.rho_old[m] = rho_used;
+          S.rho[m] = rho_new;
+          S.rnorm[m] = rnorm;
+          int reason = 0;
+          if (!(rnorm == rnorm) || isinf(rnorm)) reason = BTFEM_ENAN;
+          else if (rnorm <= S.ttol[m]) reason = rnorm < atol ? 3 : 2;
+          else if (rnorm >= dtol * S.bn[m]) reason = BTFEM_EDTOL;
+          else if (rho_used == 0.0 || omega == 0.0) reason = BTFEM_EBREAKDOWN;
+          else if (it >= maxit) reason = BTFEM_ENOTCONV;
+          if (reason != 0) {
+            S.reason[m] = reason;
+            S.its[m] = it;
+            atomicAnd(&S.active, ~(1u << m));
+            if (reason < 0) atomicMin(&S.fail, reason);
+          } else {
+            S.beta[m] = (rho_new / rho_used) * (S.alpha[m] / omega);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          S.it = it;
+          if (S.active != before) chb_rebuild(S, M);
+        }
+      }
+      __syncthreads();
+    } else {
+      // ---- ||r|| of every member: start of the Krylov solves of this step
+      chb_grid_reduce<NT>(a, S, wacc, acc, M, 1, 0, gs);
+      PROF(10);
+      if (threadIdx.x < 32) {
+        const unsigned int before = S.active;
+        __syncwarp();
+        if (lane < nact) {
+          const int m = S.act[lane];
+          const double bn = sqrt(S.tot[2 * m]);
+          const double ttol = fmax(rtol * bn, atol);
+          S.bn[m] = bn;
+          S.ttol[m] = ttol;
+          S.rho[m] = S.tot[2 * m]; S.rho_old[m] = 1.0; S.alpha[m] = 1.0; S.omega[m] = 1.0; S.rnorm[m] = bn;
+          int reason = 0;
+          if (!(bn == bn) || isinf(bn)) reason = BTFEM_ENAN;
+          else if (bn <= ttol) reason = bn < atol ? 3 : 2;
+          if (reason != 0) {
+            S.reason[m] = reason;
+            S.its[m] = 0;
+            atomicAnd(&S.active, ~(1u << m));
+            if (reason < 0) atomicMin(&S.fail, reason);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          S.it = 0;
+          if (S.active != before) chb_rebuild(S, M);
+        }
+      }
+      __syncthreads();
+    }
+    if (!S.fail && S.active != 0u) {
+      // ---- p <- r - omega*beta*v + beta*p   (first iteration: p = r), then v = A p; chunks cut from the groups that go on
+      const unsigned int active2 = S.active;
+      const long long WV2 = (long long)S.ngact * n;
+      const long long plo = WV2 * blockIdx.x / NB, phi = WV2 * (blockIdx.x + 1) / NB;
+      const bool first = S.it == 0;
+      for (long long i = plo * HB + threadIdx.x; i < phi * HB; i += NT) {
+        const long long rr_ = i / HB;
+        const int gi = (int)(rr_ / n), g = S.actg[gi], m = g * HB + ml;
+        if (m < M && ((active2 >> m) & 1u)) {
+          const size_t e = (size_t)(i - (long long)gi * n * HB);
+          double2* vb = a.u + (size_t)g * 7 * npadHB;
+          const double2 rr = vb[npadHB + e];
+          if (first) {
+            vb[3 * npadHB + e] = rr;
+          } else {
+            const double beta = S.beta[m], ob = S.omega[m] * beta;
+            const double2 vv = vb[4 * npadHB + e];
+            double2 pp = vb[3 * npadHB + e];
+            pp.x = rr.x - ob * vv.x + beta * pp.x;
+            pp.y = rr.y - ob * vv.y + beta * pp.y;
+            vb[3 * npadHB + e] = pp;
+          }
+        }
+      }
+      PROF(1);
+      grid_barrier(gs);
+      PROF(2);
+      if (threadIdx.x == 0) { S.mode = MODE_V; S.bar_target = gs.target; }
+      __syncthreads();
+      continue;
+    }
+    // ---- every member has finished the time step (or one has failed, which ends the batch)
+    if (!S.fail) {
+      bool anyz = false;   // converged before the first iteration with a zero guess: PETSc returns x = 0
+      for (int m = 0; m < M; ++m)
+        if (S.its[m] == 0 && S.reason[m] > 0) {
+          anyz = true;
+          double2* u = a.u + (size_t)(m / HB) * 7 * npadHB + (m % HB);
+          for (int i = blockIdx.x * NT + threadIdx.x; i < n; i += NB * NT) u[(size_t)i * HB] = make_double2(0.0, 0.0);
+        }
+      if (anyz) grid_barrier(gs);   // the next right-hand sides gather x
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int fail = S.fail;
+      for (int m = 0; m < M; ++m) {
+        const int it = S.its[m];
+        S.total_iters[m] += it;
+        S.max_iters[m] = max(S.max_iters[m], it);
+        if (blockIdx.x == 0) {
+          KrylovCtrl* ctrl = ctrl0 + m;
+          ctrl->bnorm = S.bn[m]; ctrl->ttol = S.ttol[m]; ctrl->rnorm = S.rnorm[m];
+          ctrl->rho = S.rho[m]; ctrl->rho_old = S.rho_old[m]; ctrl->alpha = S.alpha[m]; ctrl->omega = S.omega[m];
+          ctrl->iters = it; ctrl->reason = S.reason[m]; ctrl->done = 1;
+          ctrl->step = step; ctrl->step_next = step + 1;
+          ctrl->total_iters = S.total_iters[m]; ctrl->max_iters = S.max_iters[m];
+          if (fail) ctrl->failed = fail;   // a failure of any member stops every member (k_step_fail)
+        }
+      }
+      S.bar_target = gs.target;
+      if (!fail) {
+        S.step = step + 1;
+        S.mode = MODE_RHSP;
+        S.it = 0;
+        S.active = all;
+        for (int m = 0; m < M; ++m) { S.reason[m] = 0; S.its[m] = 0; }
+        if (step + 1 < a.step_end) load_step_scalars(step + 1);
+        chb_rebuild(S, M);
+      }
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.gridbar[32] = S.bar_target;
+#undef PROF
 }
 
 // ------------------------------------------------------------------------------------ vector kernels
@@ -2807,9 +4183,32 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   const bool batch_ok = members > 1 && h->lanes == 0 && h->n_slice > 0;
   const bool hb = batch_ok && !periodic && !gmres && !part && !strong && !sa->nonzero_guess &&
                   layout_env && layout_env[0] == 'i';
-  const bool shared_ops = hb || (batch_ok && ((shared_env && shared_env[0] == '1') || (layout_env && layout_env[0] == 's')));
+  // BTFEM_BATCH_PERSIST=hb: the member-interleaved layout inside one cooperative kernel (k_bicgstab_coop_hb)
+  const char* pb_env0 = getenv("BTFEM_BATCH_PERSIST");
+  const bool chb = batch_ok && !hb && members <= PB_MAX && !periodic && !gmres && !(sa->pc == BTFEM_PC_ILU) && h->nv_own < 0 &&
+                   h->h_vmaster.empty() && !sa->nonzero_guess && pb_env0 && pb_env0[0] == 'h' &&
+                   !(getenv("BTFEM_LOOP") && getenv("BTFEM_LOOP")[0] == 'h');
+  const bool hbl = hb || chb;   // data in the interleaved layout
+  const bool shared_ops = hbl || (batch_ok && ((shared_env && shared_env[0] == '1') || (layout_env && layout_env[0] == 's')));
   const int groups = (members + HB - 1) / HB;
-  const int members_alloc = hb ? groups * HB : members;
+  const int members_alloc = hbl ? groups * HB : members;
+  // BTFEM_BATCH_PERSIST=ring (opt-in; batches of up to PB_MAX members on whole-mesh handles): the lock-step batch as
+  // ONE persistent kernel on the per-warp TMA rings (k_bicgstab_persistent_batch), one operator stream per gradient
+  // direction.  Measured slower than the kernel chain on the 46 k-vertex HARDI mesh (profiles/r2ag_*, r2ah_*).
+  const char* pb_env = getenv("BTFEM_BATCH_PERSIST");
+  const char* loop_env0 = getenv("BTFEM_LOOP");
+  const bool pbatch = batch_ok && members <= PB_MAX && !hb && !shared_ops && !periodic && !gmres && !ilu && !part &&
+                      !strong && !sa->nonzero_guess && bt_stream_kernel_usable(h) && h->ps_warps == PB_NW &&
+                      (pb_env && pb_env[0] == 'r') && !(loop_env0 && loop_env0[0] == 'h');
+  // Default for batches of up to PB_MAX members on whole-mesh handles: the many-warp cooperative kernel
+  // (k_bicgstab_coop_batch) on the SELL copies, one per direction.  BTFEM_BATCH_PERSIST=0: kernel chain.
+  const bool cbatch = batch_ok && members <= PB_MAX && !hb && !shared_ops && !pbatch && !periodic && !gmres && !ilu &&
+                      !part && !strong && !sa->nonzero_guess && h->nv_own < 0 &&
+                      !(pb_env && pb_env[0] == '0') && !(loop_env0 && loop_env0[0] == 'h') &&
+                      !(getenv("BTFEM_BATCH_DIRSHARE") && getenv("BTFEM_BATCH_DIRSHARE")[0] == '0');
+  PbArgs pba;
+  memset(&pba, 0, sizeof(pba));
+  std::vector<int32_t> member_dir;   // lives until the stream synchronisation behind the cA / cb upload
   if (shared_ops) {
     const int nd = (int)h->ndof;
     h->d_dinv.alloc(nd);
@@ -2834,6 +4233,69 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
       for (int d = 0; d < 3; ++d) gd[3 * b + d] = sav[b].gdir[d];
     h->d_gdirs.upload(gd.data(), gd.size(), st);
     BT_CUDA(cudaStreamSynchronize(st));   // gd is a host temporary
+  } else if (pbatch) {
+    // directions = runs of consecutive members with the same g (sweeps list the b-values of a direction together)
+    std::vector<int> first_of_dir;
+    std::vector<int> dir_of(members);
+    for (int b = 0; b < members; ++b) {
+      if (b == 0 || memcmp(sav[b].gdir, sav[b - 1].gdir, 3 * sizeof(double)) != 0) first_of_dir.push_back(b);
+      dir_of[b] = (int)first_of_dir.size() - 1;
+    }
+    const int ndir = (int)first_of_dir.size();
+    const size_t sbytes = (size_t)h->ps_units * 64;
+    const size_t sstr = (sbytes + 16 + 127) & ~(size_t)127;
+    h->d_PJt_b.alloc((size_t)ndir * sstr);
+    h->d_QJt_b.alloc((size_t)ndir * sstr);
+    const int nd = (int)h->ndof;
+    h->d_dinv.alloc(nd);
+    h->comb_dt = -1;   // d_dinv no longer belongs to what bt_combine cached
+    k_pdiag<<<(nd + TPB - 1) / TPB, TPB, 0, st>>>(nd, h->d_diagpos.p, h->d_vals[0].p, h->d_vals[1].p, h->d_vals[2].p,
+                                                  h->d_vals[6].p, h->d_vals[7].p, 1.0 / sa->dt, sa->theta, (int)sa->pc,
+                                                  h->d_dinv.p);
+    for (int d = 0; d < ndir; ++d) {
+      const double* g = sav[first_of_dir[d]].gdir;
+      unsigned char* Pt = h->d_PJt_b.p + (size_t)d * sstr;
+      unsigned char* Qt = h->d_QJt_b.p + (size_t)d * sstr;
+      // columns, row blocks and the zero padding values come from the handle's stream; k_combine writes the values
+      BT_CUDA(cudaMemcpyAsync(Pt, h->d_PJt.p, sbytes, cudaMemcpyDeviceToDevice, st));
+      BT_CUDA(cudaMemcpyAsync(Qt, h->d_QJt.p, sbytes, cudaMemcpyDeviceToDevice, st));
+      k_combine<<<(int)((h->nnz + TPB - 1) / TPB), TPB, 0, st>>>(
+          h->nnz, h->d_rowidx.p, h->d_vals[0].p, h->d_vals[1].p, h->d_vals[2].p, h->d_vals[6].p, h->d_vals[7].p,
+          h->d_vals[3].p, h->d_vals[4].p, h->d_vals[5].p, 1.0 / sa->dt, sa->theta, g[0], g[1], g[2], h->d_dinv.p,
+          nullptr, nullptr, nullptr, h->d_rowptr.p, h->d_sell_slot.p, h->d_slice_ptr.p, nullptr, nullptr,
+          h->d_ps_scol0.p, Pt, Qt, h->ps_col16 ? 1 : 0);
+    }
+    BT_CUDA(cudaGetLastError());
+    pba.members = members;
+    pba.stream_stride = sstr;
+    for (int b = 0; b < members;) {   // pass groups: up to PB_GM members of one direction
+      int e = b + 1;
+      while (e < members && e - b < PB_GM && dir_of[e] == dir_of[b]) ++e;
+      pba.g_m0[pba.groups] = (unsigned char)b;
+      pba.g_nm[pba.groups] = (unsigned char)(e - b);
+      pba.g_dir[pba.groups] = (unsigned char)dir_of[b];
+      ++pba.groups;
+      b = e;
+    }
+  } else if (members > 1 && !(getenv("BTFEM_BATCH_DIRSHARE") && getenv("BTFEM_BATCH_DIRSHARE")[0] == '0')) {
+    // A = P + i c J_g: b only enters through the scalar c, so the members of one direction share ONE operator copy
+    // (a 64 x 4 HARDI batch of 16 reads 4 copies -- L2-resident on a small mesh -- instead of streaming 16 from HBM)
+    member_dir.resize(members);
+    std::vector<int> first_of_dir;
+    for (int b = 0; b < members; ++b) {
+      int d = -1;
+      for (size_t k = 0; k < first_of_dir.size() && d < 0; ++k)
+        if (memcmp(sav[b].gdir, sav[first_of_dir[k]].gdir, 3 * sizeof(double)) == 0) d = (int)k;
+      if (d < 0) {
+        d = (int)first_of_dir.size();
+        first_of_dir.push_back(b);
+      }
+      member_dir[b] = d;
+    }
+    const int ndir = (int)first_of_dir.size();
+    if (ndir == 1) h->comb_dt = -1;   // bt_combine would otherwise take a batch of one direction for a cached single solve
+    for (int d = 0; d < ndir; ++d) bt_combine(h, sa->dt, sa->theta, sav[first_of_dir[d]].gdir, (int)sa->pc, d, ndir);
+    h->d_member_dir.upload(member_dir.data(), member_dir.size(), st);
   } else {
     for (int b = 0; b < members; ++b) bt_combine(h, sa->dt, sa->theta, sav[b].gdir, (int)sa->pc, b, members);
   }
@@ -2860,7 +4322,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     h->d_ubc.zero(st);
     h->d_rhs_add.zero(st);
   }
-  if (hb)
+  if (hbl)
     k_hb_set_ic<<<dim3((unsigned)(((size_t)n * HB + TPB - 1) / TPB), groups), TPB, 0, st>>>(
         n, (size_t)7 * h->vec_npad * HB, h->d_ic_dof.p, h->d_u.p);
   else
@@ -2882,6 +4344,43 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   if (shared_ops) {
     a.PQs = h->d_PQs.p; a.Jxys = h->d_Jxys.p; a.Jzs = h->d_Jzs.p; a.dinv = h->d_dinv.p; a.gdirs = h->d_gdirs.p;
   }
+  if (!member_dir.empty()) a.member_dir = h->d_member_dir.p;
+  const int cb_blocks = h->ps_req_blocks > 0 ? std::min(h->ps_req_blocks, (int)BT_NUM_SMS) : (int)BT_NUM_SMS;
+  if (cbatch || chb) {
+    a.pb.members = members;
+    a.step_begin = 0;
+    a.step_end = (int)sa->nsteps;
+  }
+  if (pbatch || cbatch || chb) {
+    if (h->d_gridbar.n != 64) {
+      h->d_gridbar.alloc(64);
+      h->d_gridbar.zero(st);
+    }
+    a.gridbar = h->d_gridbar.p;
+  }
+  if (pbatch) {
+    a.ps_blocks = h->ps_blocks;
+    a.ps_warps = h->ps_warps;
+    a.ps_c16 = h->ps_col16 ? 1 : 0;
+    a.ps_fence = !(getenv("BTFEM_PS_FENCE") && getenv("BTFEM_PS_FENCE")[0] == '0');
+    a.ps_ptr = h->d_ps_ptr.p;
+    a.ps_piece = h->d_ps_piece.p;
+    a.PJt = h->d_PJt_b.p;
+    a.QJt = h->d_QJt_b.p;
+    a.pb = pba;
+    a.step_begin = 0;
+    a.step_end = (int)sa->nsteps;
+    static bool pb_attr_set = false;
+    if (!pb_attr_set) {
+      BT_CUDA(cudaFuncSetAttribute(k_bicgstab_persistent_batch<PB_NW, PB_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb_smem()));
+      pb_attr_set = true;
+    }
+    if (h->d_gridbar.n != 64) {
+      h->d_gridbar.alloc(64);
+      h->d_gridbar.zero(st);
+    }
+    a.gridbar = h->d_gridbar.p;
+  }
   const int lanes = h->lanes;
   // keep the total block count near a few waves: the x-extent shrinks as the batch grows
   const int vgx = std::max(1, std::min(vec_grid(n), std::max(BT_NUM_SMS, BT_NUM_SMS * 8 / members)));
@@ -2890,7 +4389,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   const dim3 hb_sg(std::max(1, std::min((int)h->n_slice, std::max(BT_NUM_SMS, BT_NUM_SMS * 4 / groups))), groups);
   const dim3 hb_vg(std::max(1, std::min((int)(((size_t)n * HB + TPB - 1) / TPB), std::max(BT_NUM_SMS, BT_NUM_SMS * 8 / groups))),
                    groups);
-  if (hb) a.members = members;
+  if (hbl) a.members = members;
 
   // The BiCGStab iteration (of every member) as a CUDA graph.  Default ("device" loop): one graph per TIME STEP
   // -- u push / periodic terms / RHS, then a WHILE node whose body is the iteration and whose condition the
@@ -2989,8 +4488,8 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     a.gridbar = h->d_gridbar.p;
   }
   DevArray<unsigned long long> d_prof;
-  if (persist && getenv("BTFEM_PROFILE_PERSIST")) {
-    d_prof.alloc(16 + (size_t)a.ps_blocks * (a.ps_warps + 1));
+  if ((persist || pbatch || cbatch || chb) && getenv("BTFEM_PROFILE_PERSIST")) {
+    d_prof.alloc(16 + std::max((size_t)a.ps_blocks * (a.ps_warps + 1), (size_t)cb_blocks));
     d_prof.zero(st);
     a.prof = d_prof.p;
   }
@@ -3003,7 +4502,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   };
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t gexec = nullptr;
-  if (persist) {
+  if (persist || pbatch || cbatch || chb) {
     // nothing to capture
   } else if (dev_loop) {
     BT_CUDA(cudaGraphCreate(&graph, 0));
@@ -3094,6 +4593,30 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
       }
     }
   }
+  if (pbatch) {
+    void* kargs[] = {(void*)&a};
+    BT_CUDA(cudaLaunchCooperativeKernel((const void*)k_bicgstab_persistent_batch<PB_NW, PB_D>, dim3(a.ps_blocks),
+                                        dim3(PB_NW * 32), kargs, (size_t)pb_smem(), st));
+    persistent_launches = 1;
+  }
+  if (chb) {
+    void* kargs[] = {(void*)&a};
+    const int cfg = getenv("BTFEM_CHB_CFG") ? atoi(getenv("BTFEM_CHB_CFG")) : 0;   // tuning: threads per block, columns in flight
+    if (cfg == 1)
+      BT_CUDA(cudaLaunchCooperativeKernel((const void*)k_bicgstab_coop_hb<1024, 2>, dim3(cb_blocks), dim3(1024), kargs, 0, st));
+    else if (cfg == 2)
+      BT_CUDA(cudaLaunchCooperativeKernel((const void*)k_bicgstab_coop_hb<768, 4>, dim3(cb_blocks), dim3(768), kargs, 0, st));
+    else if (cfg == 3)
+      BT_CUDA(cudaLaunchCooperativeKernel((const void*)k_bicgstab_coop_hb<512, 8>, dim3(cb_blocks), dim3(512), kargs, 0, st));
+    else
+      BT_CUDA(cudaLaunchCooperativeKernel((const void*)k_bicgstab_coop_hb<CB_NT, CHB_U>, dim3(cb_blocks), dim3(CB_NT), kargs, 0, st));
+    persistent_launches = 1;
+  }
+  if (cbatch) {
+    void* kargs[] = {(void*)&a};
+    BT_CUDA(cudaLaunchCooperativeKernel((const void*)k_bicgstab_coop_batch<CB_NT>, dim3(cb_blocks), dim3(CB_NT), kargs, 0, st));
+    persistent_launches = 1;
+  }
   if (a.prof) {   // where block 0 spent the loop (us per iteration follow from total_iters)
     unsigned long long pr[16];
     BT_CUDA(cudaMemcpyAsync(pr, d_prof.p, sizeof(pr), cudaMemcpyDeviceToHost, st));
@@ -3103,7 +4626,21 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     fprintf(stderr, "[btfem] persistent kernel, block 0, ms per phase:");
     for (int k = 0; k < 11; ++k) fprintf(stderr, " %s %.2f |", names[k], 1e-6 * (double)pr[k]);
     fprintf(stderr, "\n");
-    if (const char* path = getenv("BTFEM_PROFILE_PERSIST_FILE")) {   // per-warp time inside the passes, ns
+    if (cbatch || chb) {   // spread of the blocks' pass times
+      std::vector<unsigned long long> bt((size_t)cb_blocks);
+      BT_CUDA(cudaMemcpy(bt.data(), d_prof.p + 16, sizeof(unsigned long long) * bt.size(), cudaMemcpyDeviceToHost));
+      std::vector<unsigned long long> so(bt);
+      std::sort(so.begin(), so.end());
+      fprintf(stderr, "[btfem] coop batch kernel, ms inside the passes per block: min %.2f | median %.2f | max %.2f | block 0 %.2f\n",
+              1e-6 * so.front(), 1e-6 * so[so.size() / 2], 1e-6 * so.back(), 1e-6 * bt[0]);
+      if (getenv("BTFEM_PROFILE_PERSIST_FILE")) {
+        if (FILE* f = fopen(getenv("BTFEM_PROFILE_PERSIST_FILE"), "w")) {
+          for (size_t i = 0; i < bt.size(); ++i) fprintf(f, "%zu %llu\n", i, bt[i]);
+          fclose(f);
+        }
+      }
+    }
+    if (!cbatch && !chb) if (const char* path = getenv("BTFEM_PROFILE_PERSIST_FILE")) {   // per-warp time inside the passes, ns
       std::vector<unsigned long long> w((size_t)a.ps_blocks * a.ps_warps);
       BT_CUDA(cudaMemcpy(w.data(), d_prof.p + 16, sizeof(unsigned long long) * w.size(), cudaMemcpyDeviceToHost));
       std::vector<int32_t> pp(w.size() + 1);
@@ -3143,7 +4680,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     }
   }
   if (dev_loop) {
-    for (int64_t step = 0; !persist && step < sa->nsteps; ++step) BT_CUDA(cudaGraphLaunch(gexec, st));
+    for (int64_t step = 0; !persist && !pbatch && !cbatch && !chb && step < sa->nsteps; ++step) BT_CUDA(cudaGraphLaunch(gexec, st));
     BT_CUDA(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl.p, sizeof(KrylovCtrl) * members, cudaMemcpyDeviceToHost, st));
     BT_CUDA(cudaStreamSynchronize(st));
     for (int b = 0; b < members; ++b) {
@@ -3155,7 +4692,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     }
     const int64_t passes = *std::max_element(total_iters.begin(), total_iters.end());
     n_kernels = (prologue_kernels + 2) * sa->nsteps + kernels_per_iter * passes;   // kernels that did work
-    if (persist) n_kernels = persistent_launches + (periodic ? 2 * sa->nsteps : 0);
+    if (persist || pbatch || cbatch || chb) n_kernels = persistent_launches + (periodic ? 2 * sa->nsteps : 0);
     if (iters_per_step) d_iters.download(iters_per_step, st);
   }
   for (int64_t step = 0; !dev_loop && step < sa->nsteps && !fail; ++step) {
@@ -3245,7 +4782,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     throw BtError{fail, "row-partitioned solve: a peer rank did not answer within the time limit"};
   }
   a.sig_out = d_sig.p;
-  if (hb) k_hb_signal<<<hb_vg, TPB, 0, st>>>(a, h->d_lumped.p, h->d_dof_comp.p);
+  if (hbl) k_hb_signal<<<hb_vg, TPB, 0, st>>>(a, h->d_lumped.p, h->d_dof_comp.p);
   else
   k_signal<<<vg, TPB, 0, st>>>(a, h->d_lumped.p, h->d_dof_comp.p);
   BT_CUDA(cudaGetLastError());
@@ -3257,7 +4794,7 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
   if (gexec) cudaGraphExecDestroy(gexec);
   if (graph) cudaGraphDestroy(graph);
-  h->have_solution = !hb;   // btfem_get_solution reads member 0's slab, which the interleaved layout does not have
+  h->have_solution = !hbl;   // btfem_get_solution reads member 0's slab, which the interleaved layout does not have
   for (int b = 0; b < members; ++b) {
     btfem_solve_out* out = &outv[b];
     out->signal_comp[0] = sig[2 * b];

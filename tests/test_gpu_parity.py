@@ -312,10 +312,12 @@ def test_gmres_restart_path():
     assert np.max(np.abs(res["iters"].astype(int) - ref["iters"].astype(int))) <= 2
 
 
-def test_batched_solves_equal_individual_solves():
-    """btfem_solve_batch: members (different directions and q) advanced in lock step.  A member gets exactly the same
-    bits whatever batch it travels in (same kernels, same reduction order per member); the one-at-a-time solves run
-    the persistent kernel (other grouping of the dot-product partial sums), so they agree to solver tolerance."""
+def test_batched_solves_equal_individual_solves(monkeypatch):
+    """btfem_solve_batch on the kernel chain (BTFEM_BATCH_PERSIST=0; the path of batches of more than 16 members):
+    members (different directions and q) advanced in lock step.  A member gets exactly the same bits whatever batch it
+    travels in (same kernels, same reduction order per member); the one-at-a-time solves run the persistent kernel
+    (other grouping of the dot-product partial sums), so they agree to solver tolerance."""
+    monkeypatch.setenv("BTFEM_BATCH_PERSIST", "0")
     _, xyz, tets, phase, co = CASES[3]
     seq = orc.pgse(2000.0, 6000.0)
     k = 200.0
@@ -455,6 +457,73 @@ def test_layered_sphere_parity_and_matrix_formalism():
             q = seq.q_from_b(b)
             res = fem.solve(200.0, 0.5, q * f, q * fp, [0, 0, 1], rtol=1e-10, atol=1e-12)
             assert abs(res["signal"] / res["voi"] - want) <= 3e-3 * want
+
+
+def test_persistent_batch_kernels(monkeypatch):
+    """Batches of up to 16 members run the whole time loop as ONE cooperative launch.  Default: the many-warp kernel on
+    the SELL copies (k_bicgstab_coop_batch, one operator copy per direction); BTFEM_BATCH_PERSIST=ring: the TMA-ring
+    kernel (k_bicgstab_persistent_batch; members of one direction travel through the passes in groups of up to 4:
+    groups of 4, 3, 2 and 1 units here).  Members drop out at different iterations; both agree with the one-at-a-time
+    persistent solves and with the kernel chain to solver tolerance; a failing member ends the batch."""
+    _, xyz, tets, phase, co = CASES[3]
+    seq = orc.pgse(2000.0, 6000.0)
+    k = 200.0
+    ts = orc.time_grid(seq.T, k)
+    f = np.array([seq.f(t) for t in ts])
+    fp = np.concatenate([[f[0]], f[:-1]])
+    dirs = meshes.fibonacci_hemisphere(3)
+    q = [seq.q_from_b(b) for b in (300.0, 1000.0, 2000.0, 3000.0, 4000.0)]
+    members = [(qq * f, qq * fp, dirs[0]) for qq in q]              # 5 members of one direction: groups of 4 + 1
+    members += [(qq * f, qq * fp, dirs[1]) for qq in q[:3]]         # 3 members
+    members += [(qq * f, qq * fp, dirs[2]) for qq in q[:2]]         # 2 members
+    par = dict(rtol=1e-10, atol=1e-14)
+    with btfem.BTFem(0) as fem:
+        _setup(fem, xyz, tets, phase, co)
+        single = [fem.solve(k, 0.5, cA, cb, g, **par) for cA, cb, g in members]
+        coop = fem.solve_batch(k, 0.5, members, **par)
+        assert coop[0]["n_kernels"] <= 3                              # one launch for the whole time loop (+ signal)
+        coop2 = fem.solve_batch(k, 0.5, members, **par)
+        coop_split = fem.solve_batch(k, 0.5, members[:3], **par) + fem.solve_batch(k, 0.5, members[3:], **par)
+        with pytest.raises(btfem.BTFemError):
+            fem.solve_batch(k, 0.5, members[:6], rtol=1e-30, atol=0.0, maxit=3)
+        coop_after = fem.solve_batch(k, 0.5, members[:6], **par)      # the handle is usable after the failure
+        monkeypatch.setenv("BTFEM_BATCH_PERSIST", "0")
+        chain = fem.solve_batch(k, 0.5, members, **par)
+        assert chain[0]["n_kernels"] > 100
+        monkeypatch.setenv("BTFEM_BATCH_PERSIST", "ring")
+        ring = fem.solve_batch(k, 0.5, members, **par)
+        assert ring[0]["n_kernels"] <= 3
+        ring2 = fem.solve_batch(k, 0.5, members, **par)
+        ring_split = fem.solve_batch(k, 0.5, members[:3], **par) + fem.solve_batch(k, 0.5, members[3:], **par)
+        with pytest.raises(btfem.BTFemError):
+            fem.solve_batch(k, 0.5, members[:6], rtol=1e-30, atol=0.0, maxit=3)
+        ring_after = fem.solve_batch(k, 0.5, members[:6], **par)
+        monkeypatch.setenv("BTFEM_BATCH_PERSIST", "hb")               # member-interleaved layout, cooperative kernel
+        chb = fem.solve_batch(k, 0.5, members, **par)                 # 10 members = 2 groups of 8 (the second partly empty)
+        assert chb[0]["n_kernels"] <= 3
+        chb2 = fem.solve_batch(k, 0.5, members, **par)
+        chb_split = fem.solve_batch(k, 0.5, members[:3], **par) + fem.solve_batch(k, 0.5, members[3:], **par)
+        with pytest.raises(btfem.BTFemError):
+            fem.solve_batch(k, 0.5, members[:6], rtol=1e-30, atol=0.0, maxit=3)
+        chb_after = fem.solve_batch(k, 0.5, members[:6], **par)
+
+    def close(x, y):
+        return abs(x["signal"] - y["signal"]) <= 1e-9 * abs(y["signal"]) and \
+            abs(x["total_iters"] - y["total_iters"]) <= max(3, 0.02 * y["total_iters"])
+
+    for i, s1 in enumerate(single):
+        assert coop[i]["signal"] == coop2[i]["signal"] and coop[i]["total_iters"] == coop2[i]["total_iters"]   # reproducible
+        assert ring[i]["signal"] == ring2[i]["signal"] and ring[i]["total_iters"] == ring2[i]["total_iters"]
+        assert ring[i]["signal"] == ring_split[i]["signal"]            # ring kernel: same bits whatever the batch
+        assert close(coop[i], s1) and close(ring[i], s1) and close(chain[i], s1) and close(coop_split[i], s1)
+        assert coop[i]["last_reason"] > 0 and ring[i]["last_reason"] > 0 and chb[i]["last_reason"] > 0
+        assert chb[i]["signal"] == chb2[i]["signal"] and chb[i]["total_iters"] == chb2[i]["total_iters"]
+        assert close(chb[i], s1) and close(chb_split[i], s1)
+    for i in range(6):
+        assert close(coop_after[i], single[i]) and ring_after[i]["signal"] == ring[i]["signal"]
+        assert close(chb_after[i], single[i])
+    assert len({round(s["signal"], 6) for s in coop}) == len(coop)
+    assert len({s["total_iters"] for s in coop}) > 3                    # members leave the iteration at different times
 
 
 def test_interleaved_batch_layout(monkeypatch):
