@@ -304,7 +304,8 @@ __global__ void k_combine_shared(int64_t nnz, const int32_t* __restrict__ rowidx
 // Lock-step batch inside ONE persistent kernel (k_bicgstab_persistent_batch): members that share a gradient direction
 // form a pass group -- they read ONE operator stream (the direction's P|Q, J_g values; b only enters through the
 // scalar c) -- of at most PB_GM members.
-constexpr int PB_MAX = 16;   // members per launch
+constexpr int PB_MAX = 16;   // members per launch of the TMA-ring and the member-interleaved batch kernels
+constexpr int CB_MAX = 32;   // members per launch of the many-warp batch kernel (and size of the shared Krylov state)
 constexpr int PB_GM = 4;     // members per pass group
 struct PbArgs {
   int members, groups;
@@ -599,6 +600,21 @@ __device__ __forceinline__ int ldv_stream_i32(const int32_t* p) {
 __device__ __forceinline__ double2 ldv_stream_f64x2(const double2* p) {
   double2 v;
   asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ldv_nc_i32(const int32_t* p) {
+  int v;
+  asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ldv_nc_f64(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ldv_nc_f64x2(const double2* p) {
+  double2 v;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
   return v;
 }
 __device__ __forceinline__ double2 ldv_gather_f64x2(const double2* p) {
@@ -1431,20 +1447,21 @@ constexpr int PB_NW = 8, PB_D = 3;
 constexpr int pb_smem() { return ps_smem(PB_NW, PB_D) + 2 * PB_MAX * PB_NW * 32 * 8; }
 
 struct PbState {
-  double rho[PB_MAX], rho_old[PB_MAX], alpha[PB_MAX], omega[PB_MAX], beta[PB_MAX];
-  double bn[PB_MAX], ttol[PB_MAX], rnorm[PB_MAX], cA[PB_MAX], cb[PB_MAX];
-  double tot[2 * PB_MAX];
-  double wsum[2 * PB_MAX][PB_NW];
-  long long total_iters[PB_MAX];
-  int max_iters[PB_MAX], its[PB_MAX], reason[PB_MAX];
+  double rho[CB_MAX], rho_old[CB_MAX], alpha[CB_MAX], omega[CB_MAX], beta[CB_MAX];
+  double bn[CB_MAX], ttol[CB_MAX], rnorm[CB_MAX], cA[CB_MAX], cb[CB_MAX];
+  double tot[2 * CB_MAX];
+  double wsum[2 * CB_MAX][PB_NW];
+  long long total_iters[CB_MAX];
+  int max_iters[CB_MAX], its[CB_MAX], reason[CB_MAX];
   unsigned int active;                  // bit m: member m still iterates in this time step
-  unsigned char gmask[PB_MAX];          // per group: its active members (bit j: member g_m0 + j)
-  unsigned char unit[PB_MAX][PB_GM];    // per group: the member behind unit j (its j-th active member)
-  unsigned char act[PB_MAX];            // active members, ascending
+  unsigned char gmask[CB_MAX];          // per group: its active members (bit j: member g_m0 + j)
+  unsigned char unit[CB_MAX][PB_GM];    // per group: the member behind unit j (its j-th active member)
+  unsigned char act[CB_MAX];            // active members, ascending
   int nact;
-  unsigned char actg[PB_MAX];           // member-interleaved form: groups of 8 members with an active member
+  int cut[2], cut_nact;                 // coop kernel: first and past-the-last item of this block; the nact they belong to
+  unsigned char actg[CB_MAX];           // member-interleaved form: groups of 8 members with an active member
   int ngact;
-  double gd[PB_MAX][3];                 // member-interleaved form: gradient direction of every member
+  double gd[CB_MAX][3];                 // member-interleaved form: gradient direction of every member
   int it, mode, step, fail;
   unsigned int bar_target;
 };
@@ -2001,7 +2018,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_bicgstab_persistent_batch(SpmvAr
 
 
 // ---- lock-step batches on a SMALL mesh as one cooperative kernel with many warps ("coop" batch kernel, the default for
-// batches of up to PB_MAX members on whole-mesh handles).  ncu on the kernel chain (profiles/r2ai_*) shows where a
+// batches of up to CB_MAX members on whole-mesh handles).  ncu on the kernel chain (profiles/r2ai_*) shows where a
 // 16-member iteration on a 46 k-vertex mesh goes: 52 us per batched SpMV although neither the operator bytes (one copy
 // per direction changes nothing), nor the gather locality (the SELL window changes nothing) bound it -- every block
 // walks ctrl -> schedule -> slice -> columns -> gather -> epilogue -> ticket for ONE slice per warp, 6.5 waves of
@@ -2016,7 +2033,11 @@ __global__ void __launch_bounds__(NW * 32, 1) k_bicgstab_persistent_batch(SpmvAr
 //    depend on the batch it travels in -- unlike the kernel chain).
 // The scalar recurrences, convergence tests and reason codes are those of k_bicgstab_persistent.
 constexpr int CB_NT = 1024;
-constexpr int CHB_U = 4;   // columns of a row in flight in k_bicgstab_coop_hb
+constexpr int CB_CH = 4;                       // columns of a slice per staged piece
+constexpr int CB_STAGE = CB_CH * (128 + 512);  // 32 lanes x (4-byte column + 16-byte value pair) per column
+constexpr int CB_C0 = 6;                       // cost of an item besides its columns (in columns), for the chunk cuts
+constexpr int cb_smem(int NT) { return NT / 32 * 2 * CB_STAGE; }
+constexpr int CHB_U = 2;   // columns of a row in flight in k_bicgstab_coop_hb (default variant: 1024 threads, 64 registers)
 
 // thread 0: the list of active members
 __device__ __forceinline__ void cb_rebuild(PbState& S, int M) {
@@ -2027,13 +2048,15 @@ __device__ __forceinline__ void cb_rebuild(PbState& S, int M) {
 }
 
 // acc0 / acc1: this thread's terms for the block's first member (active index ai0) and the one after it; nq values each.
+// wm != null: the terms are per-warp sums wm[warp][member][q] already (the passes); the thread terms are not used
 template <int NT>
 __device__ __forceinline__ void cb_grid_reduce(const SpmvArgs& a, PbState& S, double (*wacc)[4], const double (&acc0)[2],
-                                               const double (&acc1)[2], int ai0, int nq, int slot, GridSync& g) {
+                                               const double (&acc1)[2], int ai0, int nq, int slot, GridSync& g,
+                                               const double (*wm)[CB_MAX][2] = nullptr) {
   constexpr int NWB = NT / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nact = S.nact, nval = nact * nq;
-  {
+  if (!wm) {
     const double t0 = warp_sum(acc0[0]), t2 = warp_sum(acc1[0]);
     double t1 = 0.0, t3 = 0.0;
     if (nq == 2) { t1 = warp_sum(acc0[1]); t3 = warp_sum(acc1[1]); }
@@ -2043,7 +2066,9 @@ __device__ __forceinline__ void cb_grid_reduce(const SpmvArgs& a, PbState& S, do
   if ((int)threadIdx.x < nval) {   // block partial of value (ai, q): zero unless the block holds rows of that member
     const int ai = threadIdx.x / nq, q = threadIdx.x % nq, m = S.act[ai];
     double t = 0.0;
-    if (ai == ai0 || ai == ai0 + 1) {
+    if (wm) {
+      for (int w = 0; w < NWB; ++w) t += wm[w][m][q];
+    } else if (ai == ai0 || ai == ai0 + 1) {
       const int c = (ai - ai0) * 2 + q;
       for (int w = 0; w < NWB; ++w) t += wacc[w][c];
     }
@@ -2065,9 +2090,13 @@ __device__ __forceinline__ void cb_grid_reduce(const SpmvArgs& a, PbState& S, do
 
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) k_bicgstab_coop_batch(SpmvArgs a) {
+  extern __shared__ __align__(128) unsigned char cb_stage[];   // [warps][2 stages][CB_STAGE]
   __shared__ PbState S;
   __shared__ double wacc[NT / 32][4];
-  __shared__ int sdir[PB_MAX];
+  __shared__ double wm[NT / 32][CB_MAX][2];   // passes: per-warp sums of the dot-product terms of every member
+  __shared__ int sdir[CB_MAX];
+  unsigned long long l2_first;                // the operator streams past once per pass: evict-first in L2
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_first));
   constexpr int NWB = NT / 32;
   const int M = a.pb.members;
   for (int m = 0; m < M; ++m)
@@ -2098,6 +2127,7 @@ __global__ void __launch_bounds__(NT, 1) k_bicgstab_coop_batch(SpmvArgs a) {
       S.bn[m] = S.ttol[m] = S.rnorm[m] = 0.0;
     }
     S.bar_target = a.gridbar[32];
+    S.cut_nact = -1;
     if (a.step_begin < a.step_end) load_step_scalars(a.step_begin);
     cb_rebuild(S, M);
   }
@@ -2126,54 +2156,138 @@ __global__ void __launch_bounds__(NT, 1) k_bicgstab_coop_batch(SpmvArgs a) {
     double acc0[2] = {0.0, 0.0}, acc1[2] = {0.0, 0.0};
     int ai0;
     const unsigned long long tp0 = a.prof ? global_ns() : 0ull;
-    // ---- pass: y_m = (V.x + i c_m V.y) x_m over this block's chunk of the (active member, slice) items
+    // ---- pass: y_m = (V.x + i c_m V.y) x_m over this block's chunk of the (active member, slice) items.
+    // Columns and values of the NEXT piece (CB_CH columns of a slice; the next slice when this one ends) are on their
+    // way into this warp's shared-memory stage (cp.async, every lane its own entries) while the gathers of the current
+    // piece are in flight: per piece a warp waits for one memory round trip (the gather) instead of a chain of three
+    // (slice -> columns -> gather); ncu on the plain-load version: 36 % of the issue slots wait on those loads.
     {
-      const long long W = (long long)nact * NS;
-      const int blo = (int)(W * blockIdx.x / NB), bhi = (int)(W * (blockIdx.x + 1) / NB);
-      ai0 = blo / NS;
+      // Items are SLICE-major: a block owns a contiguous range of slices (cut once per launch, equal cost) and takes
+      // every active member through it, 32 neighbouring (slice, member) items at a time.  The members of a direction
+      // read the same operator slice at about the same time (one L2 -> L1 transfer serves them), and each gathered
+      // vector is live only in the row band of the block's slices -- with member-major chunks a 16-member pass had all
+      // operator copies and all gathered vectors in use at once (134 MB: ncu showed the gathers waiting on DRAM).
+      if (S.cut_nact < 0) {   // (uniform)
+        __syncthreads();
+        if (threadIdx.x < 2) {
+          // cost of a slice = its columns + CB_C0; prefix over the slices in closed form
+          const long long ptot = (long long)(__ldg(a.slice_ptr + NS) >> 5) + (long long)CB_C0 * NS;
+          const long long t = ptot * (blockIdx.x + threadIdx.x) / NB;
+          int lo = 0, hi = NS;   // smallest s with prefix(s) >= t
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((long long)(__ldg(a.slice_ptr + mid) >> 5) + (long long)CB_C0 * mid >= t) hi = mid; else lo = mid + 1;
+          }
+          S.cut[threadIdx.x] = lo;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) S.cut_nact = 0;
+      }
+      const int slo = S.cut[0], nitems = (S.cut[1] - slo) * nact;
+      for (int i = lane; i < 2 * CB_MAX; i += 32) (&wm[warp][0][0])[i] = 0.0;   // this warp's per-member sums
+      __syncwarp();
+      ai0 = 0;
       const double2* Vb = mode == MODE_RHSP ? a.QJs : a.PJs;
       const double2* xbase = mode == MODE_RHSP ? a.u : (mode == MODE_V ? a.p : a.s);
       const double2* opbase = mode == MODE_V ? a.rp : (mode == MODE_T ? a.s : nullptr);
       const double* ccs = mode == MODE_RHSP ? S.cb : S.cA;
-      int k = 0;
-      for (int i0 = blo; i0 < bhi; i0 += NWB, ++k) {
-        const int v = i0 + ((warp + 7 * k) & (NWB - 1));
-        if (v < bhi) {
-          const int ai = v / NS, s = v - ai * NS, m = S.act[ai];
-          const int base = __ldg(a.slice_ptr + s);
-          const int width = (__ldg(a.slice_ptr + s + 1) - base) >> 5;
-          const int row = __ldg(a.sell_row + s * 32 + lane);
-          const size_t off = (size_t)m * vs + (row >= 0 ? row : 0);
-          double2 op = make_double2(0.0, 0.0);
-          if (opbase && row >= 0) op = opbase[off];
-          const double2 y = slice_product<4>(a.sell_col + base + lane, Vb + (size_t)sdir[m] * a.mat_stride_sell + base + lane,
-                                             width, xbase + (size_t)m * vs, ccs[m]);
-          if (row >= 0) {
-            double t0, t1 = 0.0;
-            if (mode == MODE_V) {
-              a.v[off] = y;
-              t0 = y.x * op.x + y.y * op.y;
-            } else if (mode == MODE_T) {
-              a.t[off] = y;
-              t0 = op.x * y.x + op.y * y.y;
-              t1 = y.x * y.x + y.y * y.y;
-            } else {
-              a.r[off] = y;
-              a.rp[off] = y;
-              t0 = y.x * y.x + y.y * y.y;
+      unsigned char* my = cb_stage + (size_t)warp * 2 * CB_STAGE;
+      // item k of this warp: slice, member, extent.  width < 0: no such item
+      auto load_item = [&](int k, int& m, int& s, int& ai, int& base, int& width) {
+        const int v = NWB * k + ((warp + 7 * k) & (NWB - 1));
+        width = -1;
+        m = s = ai = base = 0;
+        if (v < nitems) {
+          const int sl = v / nact;
+          ai = v - sl * nact;
+          s = slo + sl;
+          m = S.act[ai];
+          base = __ldg(a.slice_ptr + s);
+          width = (__ldg(a.slice_ptr + s + 1) - base) >> 5;
+        }
+      };
+      auto issue = [&](int m, int base, int width, int j0, int b) {   // columns j0 .. j0 + CB_CH - 1 of a slice -> stage b
+        const int32_t* cp = a.sell_col + base + lane + j0 * 32;
+        const double2* vp = Vb + (size_t)sdir[m] * a.mat_stride_sell + base + lane + j0 * 32;
+        const uint32_t sc = smem_u32(my + b * CB_STAGE) + lane * 4, sv = smem_u32(my + b * CB_STAGE + CB_CH * 128) + lane * 16;
+#pragma unroll
+        for (int u = 0; u < CB_CH; ++u)
+          if (j0 + u < width) {
+            asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(sc + u * 128), "l"(cp + u * 32), "l"(l2_first) : "memory");
+            asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(sv + u * 512), "l"(vp + u * 32), "l"(l2_first) : "memory");
+          }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      int cm, cs, cai, cbase, cwidth, nm, ns, nai, nbase, nwidth;
+      load_item(0, cm, cs, cai, cbase, cwidth);
+      load_item(1, nm, ns, nai, nbase, nwidth);
+      int k = 1, pb = 0;
+      if (cwidth >= 0) issue(cm, cbase, cwidth, 0, 0);
+      while (cwidth >= 0) {
+        const int row = __ldg(a.sell_row + cs * 32 + lane);
+        const size_t off = (size_t)cm * vs + (row >= 0 ? row : 0);
+        double2 op = make_double2(0.0, 0.0);
+        if (opbase && row >= 0) op = opbase[off];
+        const double2* x = xbase + (size_t)cm * vs;
+        const double cc = ccs[cm];
+        double ar = 0.0, ai_ = 0.0;
+        int j0 = 0;
+        do {
+          // the piece after this one: further columns of this slice, or the first ones of the next item
+          if (j0 + CB_CH < cwidth) issue(cm, cbase, cwidth, j0 + CB_CH, pb ^ 1);
+          else if (nwidth >= 0) issue(nm, nbase, nwidth, 0, pb ^ 1);
+          else asm volatile("cp.async.commit_group;" ::: "memory");
+          asm volatile("cp.async.wait_group 1;" ::: "memory");   // this piece has landed (every lane reads only what it copied)
+          const int32_t* sc = reinterpret_cast<const int32_t*>(my + pb * CB_STAGE) + lane;
+          const double2* sv = reinterpret_cast<const double2*>(my + pb * CB_STAGE + CB_CH * 128) + lane;
+          double2 xv[CB_CH];
+#pragma unroll
+          for (int u = 0; u < CB_CH; ++u)
+            if (j0 + u < cwidth) xv[u] = ldv_gather_f64x2(x + sc[u * 32]);
+#pragma unroll
+          for (int u = 0; u < CB_CH; ++u)
+            if (j0 + u < cwidth) {
+              const double2 val = sv[u * 32];
+              const double pa = val.x, pb_ = cc * val.y;
+              ar = fma(pa, xv[u].x, ar);
+              ar = fma(-pb_, xv[u].y, ar);
+              ai_ = fma(pa, xv[u].y, ai_);
+              ai_ = fma(pb_, xv[u].x, ai_);
             }
-            if (ai == ai0) { acc0[0] += t0; acc0[1] += t1; }
-            else { acc1[0] += t0; acc1[1] += t1; }
+          pb ^= 1;
+          j0 += CB_CH;
+        } while (j0 < cwidth);
+        double t0 = 0.0, t1 = 0.0;
+        if (row >= 0) {
+          const double2 y = make_double2(ar, ai_);
+          if (mode == MODE_V) {
+            a.v[off] = y;
+            t0 = y.x * op.x + y.y * op.y;
+          } else if (mode == MODE_T) {
+            a.t[off] = y;
+            t0 = op.x * y.x + op.y * y.y;
+            t1 = y.x * y.x + y.y * y.y;
+          } else {
+            a.r[off] = y;
+            a.rp[off] = y;
+            t0 = y.x * y.x + y.y * y.y;
           }
         }
+        t0 = warp_sum(t0);
+        if (mode == MODE_T) t1 = warp_sum(t1);
+        if (lane == 0) { wm[warp][cm][0] += t0; wm[warp][cm][1] += t1; }
+        cm = nm; cs = ns; cai = nai; cbase = nbase; cwidth = nwidth;
+        ++k;
+        load_item(k, nm, ns, nai, nbase, nwidth);
       }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     if (a.prof && threadIdx.x == 0) a.prof[16 + blockIdx.x] += global_ns() - tp0;   // per-block time inside the passes
     PROF(mode == MODE_RHSP ? 0 : (mode == MODE_V ? 3 : 7));
     gs.target = S.bar_target;
     if (mode == MODE_V) {
       // ---- alpha = rho / (r^, v) ; s = r - alpha v
-      cb_grid_reduce<NT>(a, S, wacc, acc0, acc1, ai0, 1, 2, gs);
+      cb_grid_reduce<NT>(a, S, wacc, acc0, acc1, ai0, 1, 2, gs, wm);
       PROF(4);
       if ((int)threadIdx.x < nact) {
         const int m = S.act[threadIdx.x];
@@ -2199,7 +2313,7 @@ __global__ void __launch_bounds__(NT, 1) k_bicgstab_coop_batch(SpmvArgs a) {
       }
     } else if (mode == MODE_T) {
       // ---- omega = (t,s) / (t,t) ; x <- x + alpha p + omega s ; r <- s - omega t ; rho' = (r, r^) ; ||r||
-      cb_grid_reduce<NT>(a, S, wacc, acc0, acc1, ai0, 2, 3, gs);
+      cb_grid_reduce<NT>(a, S, wacc, acc0, acc1, ai0, 2, 3, gs, wm);
       PROF(8);
       if ((int)threadIdx.x < nact) {
         const int m = S.act[threadIdx.x];
@@ -2263,7 +2377,7 @@ __global__ void __launch_bounds__(NT, 1) k_bicgstab_coop_batch(SpmvArgs a) {
       __syncthreads();
     } else {
       // ---- ||r|| of every member: start of the Krylov solves of this step
-      cb_grid_reduce<NT>(a, S, wacc, acc0, acc1, ai0, 1, 0, gs);
+      cb_grid_reduce<NT>(a, S, wacc, acc0, acc1, ai0, 1, 0, gs, wm);
       PROF(10);
       if (threadIdx.x < 32) {
         const unsigned int before = S.active;
@@ -2994,26 +3108,40 @@ __global__ void __launch_bounds__(NT, 1) k_bicgstab_coop_hb(SpmvArgs a) {
         const double2* jxy = a.Jxys + base + rslot;
         const double* jz = a.Jzs + base + rslot;
         double yr = 0.0, yi = 0.0;
-        for (int j0 = 0; j0 < width; j0 += U) {
-          int col[U];
-          double2 xv[U];
+        // Every load of a round is issued before any is used (volatile asm: ptxas otherwise sinks each operator load
+        // next to its use -- ncu on the first version: one L2 round trip per COLUMN behind the gather), and the
+        // columns of the next round travel with them.
+        int col[U];
 #pragma unroll
-          for (int u = 0; u < U; ++u) col[u] = j0 + u < width ? __ldg(cp + (j0 + u) * 32) : -1;
+        for (int u = 0; u < U; ++u) col[u] = u < width ? ldv_nc_i32(cp + u * 32) : -1;
+        for (int j0 = 0; j0 < width; j0 += U) {
+          double2 xv[U], pqv[U], jv[U];
+          double jzv[U];
+          int coln[U];
 #pragma unroll
           for (int u = 0; u < U; ++u)
             if (col[u] >= 0) xv[u] = ldv_gather_f64x2(x + (size_t)col[u] * HB);
 #pragma unroll
           for (int u = 0; u < U; ++u)
             if (col[u] >= 0) {
-              const double2 pqv = __ldg(pq + (j0 + u) * 32), jv = __ldg(jxy + (j0 + u) * 32);
-              const double jzv = __ldg(jz + (j0 + u) * 32);
-              const double pa = mode == MODE_RHSP ? pqv.y : pqv.x;
-              const double pb = cc * comb_jg(gx, gy, gz, jv.x, jv.y, jzv, di);
+              pqv[u] = ldv_nc_f64x2(pq + (j0 + u) * 32);
+              jv[u] = ldv_nc_f64x2(jxy + (j0 + u) * 32);
+              jzv[u] = ldv_nc_f64(jz + (j0 + u) * 32);
+            }
+#pragma unroll
+          for (int u = 0; u < U; ++u) coln[u] = j0 + U + u < width ? ldv_nc_i32(cp + (j0 + U + u) * 32) : -1;
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (col[u] >= 0) {
+              const double pa = mode == MODE_RHSP ? pqv[u].y : pqv[u].x;
+              const double pb = cc * comb_jg(gx, gy, gz, jv[u].x, jv[u].y, jzv[u], di);
               yr = fma(pa, xv[u].x, yr);
               yr = fma(-pb, xv[u].y, yr);
               yi = fma(pa, xv[u].y, yi);
               yi = fma(pb, xv[u].x, yi);
             }
+#pragma unroll
+          for (int u = 0; u < U; ++u) col[u] = coln[u];
         }
         if (row >= 0 && act) {
           const double2 y = make_double2(yr, yi);
@@ -4200,9 +4328,9 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
   const bool pbatch = batch_ok && members <= PB_MAX && !hb && !shared_ops && !periodic && !gmres && !ilu && !part &&
                       !strong && !sa->nonzero_guess && bt_stream_kernel_usable(h) && h->ps_warps == PB_NW &&
                       (pb_env && pb_env[0] == 'r') && !(loop_env0 && loop_env0[0] == 'h');
-  // Default for batches of up to PB_MAX members on whole-mesh handles: the many-warp cooperative kernel
+  // Default for batches of up to CB_MAX members on whole-mesh handles: the many-warp cooperative kernel
   // (k_bicgstab_coop_batch) on the SELL copies, one per direction.  BTFEM_BATCH_PERSIST=0: kernel chain.
-  const bool cbatch = batch_ok && members <= PB_MAX && !hb && !shared_ops && !pbatch && !periodic && !gmres && !ilu &&
+  const bool cbatch = batch_ok && members <= CB_MAX && !hb && !shared_ops && !pbatch && !periodic && !gmres && !ilu &&
                       !part && !strong && !sa->nonzero_guess && h->nv_own < 0 &&
                       !(pb_env && pb_env[0] == '0') && !(loop_env0 && loop_env0[0] == 'h') &&
                       !(getenv("BTFEM_BATCH_DIRSHARE") && getenv("BTFEM_BATCH_DIRSHARE")[0] == '0');
@@ -4603,18 +4731,28 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     void* kargs[] = {(void*)&a};
     const int cfg = getenv("BTFEM_CHB_CFG") ? atoi(getenv("BTFEM_CHB_CFG")) : 0;   // tuning: threads per block, columns in flight
     if (cfg == 1)
-      BT_CUDA(cudaLaunchCooperativeKernel((const void*)k_bicgstab_coop_hb<1024, 2>, dim3(cb_blocks), dim3(1024), kargs, 0, st));
+      BT_CUDA(cudaLaunchCooperativeKernel((const void*)k_bicgstab_coop_hb<1024, 4>, dim3(cb_blocks), dim3(1024), kargs, 0, st));
     else if (cfg == 2)
-      BT_CUDA(cudaLaunchCooperativeKernel((const void*)k_bicgstab_coop_hb<768, 4>, dim3(cb_blocks), dim3(768), kargs, 0, st));
+      BT_CUDA(cudaLaunchCooperativeKernel((const void*)k_bicgstab_coop_hb<768, 3>, dim3(cb_blocks), dim3(768), kargs, 0, st));
     else if (cfg == 3)
-      BT_CUDA(cudaLaunchCooperativeKernel((const void*)k_bicgstab_coop_hb<512, 8>, dim3(cb_blocks), dim3(512), kargs, 0, st));
+      BT_CUDA(cudaLaunchCooperativeKernel((const void*)k_bicgstab_coop_hb<768, 4>, dim3(cb_blocks), dim3(768), kargs, 0, st));
+    else if (cfg == 4)
+      BT_CUDA(cudaLaunchCooperativeKernel((const void*)k_bicgstab_coop_hb<512, 4>, dim3(cb_blocks), dim3(512), kargs, 0, st));
+    else if (cfg == 5)
+      BT_CUDA(cudaLaunchCooperativeKernel((const void*)k_bicgstab_coop_hb<512, 6>, dim3(cb_blocks), dim3(512), kargs, 0, st));
     else
       BT_CUDA(cudaLaunchCooperativeKernel((const void*)k_bicgstab_coop_hb<CB_NT, CHB_U>, dim3(cb_blocks), dim3(CB_NT), kargs, 0, st));
     persistent_launches = 1;
   }
   if (cbatch) {
     void* kargs[] = {(void*)&a};
-    BT_CUDA(cudaLaunchCooperativeKernel((const void*)k_bicgstab_coop_batch<CB_NT>, dim3(cb_blocks), dim3(CB_NT), kargs, 0, st));
+    static bool cb_attr_set = false;
+    if (!cb_attr_set) {
+      BT_CUDA(cudaFuncSetAttribute(k_bicgstab_coop_batch<CB_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, cb_smem(CB_NT)));
+      cb_attr_set = true;
+    }
+    BT_CUDA(cudaLaunchCooperativeKernel((const void*)k_bicgstab_coop_batch<CB_NT>, dim3(cb_blocks), dim3(CB_NT), kargs,
+                                        (size_t)cb_smem(CB_NT), st));
     persistent_launches = 1;
   }
   if (a.prof) {   // where block 0 spent the loop (us per iteration follow from total_iters)

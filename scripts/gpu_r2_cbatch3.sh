@@ -1,0 +1,15 @@
+#!/bin/bash
+# coop batch kernel with cp.async-staged operator pieces and cost-balanced chunks
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -s -k "persistent_batch or batched_solves or interleaved_batch" > gpurun_out/r2ap_cbatch_pytest.txt 2>&1
+tail -5 gpurun_out/r2ap_cbatch_pytest.txt
+grep -q "passed" gpurun_out/r2ap_cbatch_pytest.txt || { echo "tests did not pass: skipping the sweep"; tail -60 gpurun_out/r2ap_cbatch_pytest.txt; exit 1; }
+{
+echo "== coop batch kernel: phases of block 0, one batch of 16"
+BTFEM_PROFILE_PERSIST=1 timeout 150 python scripts/hardi_bench.py 4 16 2>&1 | grep -E "HARDI|rror|persistent kernel|coop batch" | tail -3
+echo "== coop batch kernel (default), batch 16"
+timeout 150 python scripts/hardi_bench.py 64 16 2>&1 | grep -E "HARDI|rror" | tail -3
+echo "== coop batch kernel, batch 8"
+timeout 150 python scripts/hardi_bench.py 64 8 2>&1 | grep -E "HARDI|rror" | tail -3
+} > gpurun_out/r2ap_cbatch_hardi.txt 2>&1
+cat gpurun_out/r2ap_cbatch_hardi.txt
