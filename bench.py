@@ -390,6 +390,7 @@ def main():
 
     # ---- e2e through the reference-facing API, host buffers -> signal
     def e2e_once():
+        t_begin = time.perf_counter()
         mesh = dl.Mesh(xyz, tets)
         mesh.device = local_rank
         md = dl.MyDomain(mesh, mp)
@@ -406,27 +407,39 @@ def main():
         sim = dl.MRI_simulation()
         sim.k = k
         sim.verbose = False
+        t_solve = time.perf_counter()
         sim.solve(md, mp, ls)
         s = sim.stats["signal"] / sim.stats["voi"]
+        # where the step went: host + device set-up before solve(), the solve() call, and inside it the device loop
+        e2e_stats.append({"before_solve_s": round(t_solve - t_begin, 4), "solve_call_s": round(time.perf_counter() - t_solve, 4),
+                          "device_loop_s": round(1e-3 * sim.stats.get("loop_ms", 0.0), 4),
+                          "device_setup_s": round(1e-3 * sim.stats.get("setup_ms", 0.0), 4)})
         keep.append(sim.fem)        # teardown is not part of the reference's timed region either (measured: closing inside
-        return s                    # the region costs 0.14 s per solve, cudaFree of the IPC-exportable vector slab + pinned frees)
+        return s                    # the region costs 0.14 s per solve); the caller closes the handle between two steps
 
     import contextlib
     import io
     e2e_steps = max(1, min(args.steps, 2))
     keep = []
+    e2e_stats, e2e_times = [], []
     with contextlib.redirect_stdout(io.StringIO()):
         mp.set_gradient_dir(None, *g)
         e2e_once()
         keep.pop().close()
-        barrier()
-        t1 = time.perf_counter()
+        # every step is timed on its own (host buffers in -> normalized signal out, which ends with the device -> host
+        # read of the signal); the handle is closed BETWEEN two steps, untimed, so that the next step's device arrays come
+        # from the stream-ordered pool instead of fresh driver allocations (one 1.3 s outlier was seen with two live handles)
+        e2e_elapsed = 0.0
         for _ in range(e2e_steps):
+            barrier()
+            t1 = time.perf_counter()
             e2e_sig = e2e_once()
+            e2e_times.append(time.perf_counter() - t1)
+            e2e_elapsed += e2e_times[-1]
+            keep.pop().close()
         barrier()
-        e2e_elapsed = time.perf_counter() - t1
-        for fobj in keep:
-            fobj.close()
+    if os.environ.get("BENCH_DEBUG") and rank == 0:
+        sys.stderr.write("[bench] e2e steps (s): %s | incl. warm-up: %s\n" % (["%.3f" % t for t in e2e_times], e2e_stats))
 
     # ---- HARDI sweep (signals/s).  No collective inside: a rank that fails reports an infinite time, so the
     # max over ranks below cannot hang on it.
@@ -497,6 +510,7 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(fem.h2d_bytes + 3 * 8 * nsteps),
                         "d2h_bytes_per_step": int(8 * 8 + 4 * 8), "seconds_per_solve": e2e_max / e2e_steps,
+                        "rank0_steps": [dict(st, total_s=round(t, 4)) for st, t in zip(e2e_stats[1:], e2e_times)],
                         "normalized_signal": e2e_sig,
                         "api": "dmrifemlib.MyDomain/MRI_simulation.solve (host numpy mesh -> signal)"},
                 "roofline": None}

@@ -4330,7 +4330,9 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
                       (pb_env && pb_env[0] == 'r') && !(loop_env0 && loop_env0[0] == 'h');
   // Default for batches of up to CB_MAX members on whole-mesh handles: the many-warp cooperative kernel
   // (k_bicgstab_coop_batch) on the SELL copies, one per direction.  BTFEM_BATCH_PERSIST=0: kernel chain.
-  const bool cbatch = batch_ok && members <= CB_MAX && !hb && !shared_ops && !pbatch && !periodic && !gmres && !ilu &&
+  // (a block's chunk of the vector phases must not span more than two members: members <= blocks)
+  const int cb_blocks = h->ps_req_blocks > 0 ? std::min(h->ps_req_blocks, (int)BT_NUM_SMS) : (int)BT_NUM_SMS;
+  const bool cbatch = batch_ok && members <= CB_MAX && members <= cb_blocks && !hb && !shared_ops && !pbatch && !periodic && !gmres && !ilu &&
                       !part && !strong && !sa->nonzero_guess && h->nv_own < 0 &&
                       !(pb_env && pb_env[0] == '0') && !(loop_env0 && loop_env0[0] == 'h') &&
                       !(getenv("BTFEM_BATCH_DIRSHARE") && getenv("BTFEM_BATCH_DIRSHARE")[0] == '0');
@@ -4473,7 +4475,6 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     a.PQs = h->d_PQs.p; a.Jxys = h->d_Jxys.p; a.Jzs = h->d_Jzs.p; a.dinv = h->d_dinv.p; a.gdirs = h->d_gdirs.p;
   }
   if (!member_dir.empty()) a.member_dir = h->d_member_dir.p;
-  const int cb_blocks = h->ps_req_blocks > 0 ? std::min(h->ps_req_blocks, (int)BT_NUM_SMS) : (int)BT_NUM_SMS;
   if (cbatch || chb) {
     a.pb.members = members;
     a.step_begin = 0;

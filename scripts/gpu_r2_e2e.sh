@@ -1,3 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-BTFEM_TIMING=1 timeout 300 python scripts/e2e_profile.py 2>&1 | tail -60 | tee gpurun_out/r2s_e2e_profile.txt
+timeout 600 python scripts/e2e_profile.py > gpurun_out/r2au_e2e_profile.txt 2>&1
+tail -30 gpurun_out/r2au_e2e_profile.txt

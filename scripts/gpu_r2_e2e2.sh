@@ -1,10 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python bench.py --steps 3 --warmup 3 --no-hardi --no-cpu > gpurun_out/r2ae_bench_quick.json 2> gpurun_out/r2ae_bench_quick.err
-tail -3 gpurun_out/r2ae_bench_quick.err
-python - <<'PY'
+for i in 1 2; do
+BTFEM_TIMING=1 timeout 600 python bench.py --steps 2 --warmup 3 --no-hardi --no-full > gpurun_out/r2av_bench_$i.json 2> gpurun_out/r2av_bench_$i.err
+python - <<PY
 import json
-b=json.loads([l for l in open('gpurun_out/r2ae_bench_quick.json') if l.startswith('{')][-1])
-print('value',b['value'],'ms',b['ms_per_step'],'e2e',b['e2e']['value'],b['e2e']['seconds_per_solve'])
+d=json.loads(open("gpurun_out/r2av_bench_$i.json").read().strip().splitlines()[-1])
+print("run $i: value %.4g  ms/solve %.1f  e2e s/solve %.4f" % (d["value"], d["ms_per_step"], d["e2e"]["seconds_per_solve"]))
 PY
-timeout 300 python -m pytest tests/test_gpu_driver.py tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -3
+grep -E "assemble:|set_mesh|pattern:" gpurun_out/r2av_bench_$i.err | tail -24
+done

@@ -526,6 +526,31 @@ def test_persistent_batch_kernels(monkeypatch):
     assert len({s["total_iters"] for s in coop}) > 3                    # members leave the iteration at different times
 
 
+@pytest.mark.parametrize("share", [4, 8])
+def test_batch_on_an_sm_share(share):
+    """A handle confined to a few SMs (btfem_set_sm_partition): a batch of 6 runs the cooperative batch kernel on 8
+    blocks and falls back to the kernel chain on 4 (a block's chunk of the vector phases may span two members at most)."""
+    _, xyz, tets, phase, co = CASES[3]
+    seq = orc.pgse(2000.0, 6000.0)
+    k = 200.0
+    ts = orc.time_grid(seq.T, k)
+    f = np.array([seq.f(t) for t in ts])
+    fp = np.concatenate([[f[0]], f[:-1]])
+    dirs = meshes.fibonacci_hemisphere(3)
+    qs = [seq.q_from_b(b) for b in (500.0, 3000.0)]
+    members = [(q * f, q * fp, d) for d in dirs for q in qs]
+    par = dict(rtol=1e-10, atol=1e-14)
+    with btfem.BTFem(0) as fem:
+        fem.set_sm_partition(share)
+        _setup(fem, xyz, tets, phase, co)
+        single = [fem.solve(k, 0.5, cA, cb, g, **par) for cA, cb, g in members]
+        batch = fem.solve_batch(k, 0.5, members, **par)
+    assert (batch[0]["n_kernels"] <= 3) == (share >= len(members))
+    for s1, sb in zip(single, batch):
+        assert abs(s1["signal"] - sb["signal"]) <= 1e-9 * abs(sb["signal"])
+        assert abs(s1["total_iters"] - sb["total_iters"]) <= max(3, 0.02 * sb["total_iters"])
+
+
 def test_interleaved_batch_layout(monkeypatch):
     """BTFEM_BATCH_LAYOUT=interleaved (k_hb_*: groups of 8 members, member-innermost vectors, one shared
     direction-independent operator): a member gets the same bits whatever batch it travels in -- also across a group
