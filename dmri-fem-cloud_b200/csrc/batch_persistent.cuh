@@ -743,13 +743,16 @@ __global__ void __launch_bounds__(NT, 1) k_bicgstab_coop_batch(SpmvArgs a) {
       if (S.cut_nact < 0) {   // (uniform)
         __syncthreads();
         if (threadIdx.x < 2) {
-          // cost of a slice = its columns + CB_C0; prefix over the slices in closed form
-          const long long ptot = (long long)(__ldg(a.slice_ptr + NS) >> 5) + (long long)CB_C0 * NS;
+          // cost prefix over the slices: a.cb_cost (L1 wavefronts of a slice, counted on the host from its columns), or
+          // in closed form columns + CB_C0 per slice
+          const long long* pc = a.cb_cost;
+          const long long ptot = pc ? __ldg(pc + NS) : (long long)(__ldg(a.slice_ptr + NS) >> 5) + (long long)CB_C0 * NS;
           const long long t = ptot * (blockIdx.x + threadIdx.x) / NB;
           int lo = 0, hi = NS;   // smallest s with prefix(s) >= t
           while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if ((long long)(__ldg(a.slice_ptr + mid) >> 5) + (long long)CB_C0 * mid >= t) hi = mid; else lo = mid + 1;
+            const long long pm = pc ? __ldg(pc + mid) : (long long)(__ldg(a.slice_ptr + mid) >> 5) + (long long)CB_C0 * mid;
+            if (pm >= t) hi = mid; else lo = mid + 1;
           }
           S.cut[threadIdx.x] = lo;
         }

@@ -311,6 +311,7 @@ struct btfem {
   DevArray<int32_t> d_ps_first;    // [n_slice] index of the slice's first piece in d_ps_piece
   DevArray<unsigned char> d_PJt, d_QJt;   // [ps_units * 64] per-solve operator values + columns + rows, stream order
   DevArray<int32_t> d_member_dir;          // batch: operator copy used by every member
+  DevArray<long long> d_cb_cost;           // many-warp batch kernel: L1-wavefront cost prefix over the slices
   DevArray<unsigned char> d_PJt_b, d_QJt_b;   // persistent batch kernel: one stream pair per gradient direction of the batch
   DevArray<uint32_t> d_src;        // contribution ids sorted by (row,col), stable
   DevArray<int64_t> d_seg;         // [nnz+1] segment offsets into d_src

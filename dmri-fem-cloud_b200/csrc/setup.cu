@@ -977,6 +977,7 @@ void bt_build_pattern(btfem* h) {
   h->d_QJt.release();
   h->d_PJt_b.release();
   h->d_QJt_b.release();
+  h->d_cb_cost.release();
   if (h->nv_own < 0 && nslice > 0 && !getenv("BTFEM_NO_STREAM")) {
     const char* w_env = getenv("BTFEM_PS_WARPS");   // warps per block of the stream kernels: 8, 12 or 16
     const int wpb = (w_env && (atoi(w_env) == 12 || atoi(w_env) == 16)) ? atoi(w_env) : 8;

@@ -366,6 +366,7 @@ struct SpmvArgs {
   unsigned long long* prof;  // persistent kernel: optional phase timers of block 0 (BTFEM_PROFILE_PERSIST), or null
   int step_begin, step_end;  // persistent kernel: time steps of this launch
   PbArgs pb;                 // batch form of the persistent kernel
+  const long long* cb_cost;  // many-warp batch kernel: cost prefix over the slices [nslice + 1], or null
   DistView dist;             // row-partitioned solve: peers, LL buffers, send lists (dist.on == 0: whole mesh)
   // device-driven loop: the BiCGStab iteration is the body of a graph WHILE node whose condition the kernels set
   cudaGraphConditionalHandle cond;
@@ -2535,6 +2536,34 @@ static void solve_impl(btfem* h, int members, const btfem_solve_args* sav, btfem
     a.PQs = h->d_PQs.p; a.Jxys = h->d_Jxys.p; a.Jzs = h->d_Jzs.p; a.dinv = h->d_dinv.p; a.gdirs = h->d_gdirs.p;
   }
   if (!member_dir.empty()) a.member_dir = h->d_member_dir.p;
+  const bool line_cost = getenv("BTFEM_CB_LINE_COST") != nullptr;
+  if (cbatch && line_cost && h->d_cb_cost.n != (size_t)h->n_slice + 1) {
+    // BTFEM_CB_LINE_COST (experiment, measured negative: profiles/r2bc_*): cut the chunks by the L1 wavefronts of the
+    // slices -- per column of a slice the distinct 128-byte lines the 32 gathered entries fall into (1 .. 32), plus 5 for
+    // the coalesced column / value loads, plus a constant per slice -- counted once per handle, on the host, from the
+    // SELL columns.  The spread of the blocks' pass times gets wider (240 / 318 / 446 ms against 251 / 336 / 402 ms with
+    // cost = columns + 6): the lines per gather are not what makes a block slow.
+    std::vector<int32_t> sp(h->n_slice + 1), sc(h->nnz_sell);
+    BT_CUDA(cudaMemcpyAsync(sp.data(), h->d_slice_ptr.p, sizeof(int32_t) * sp.size(), cudaMemcpyDeviceToHost, st));
+    BT_CUDA(cudaMemcpyAsync(sc.data(), h->d_sell_col.p, sizeof(int32_t) * sc.size(), cudaMemcpyDeviceToHost, st));
+    BT_CUDA(cudaStreamSynchronize(st));
+    std::vector<long long> cost(h->n_slice + 1, 0);
+    for (int64_t sl = 0; sl < h->n_slice; ++sl) {
+      long long c = 8;
+      for (int base = sp[sl]; base < sp[sl + 1]; base += 32) {
+        int v[32];
+        for (int l = 0; l < 32; ++l) v[l] = sc[base + l] >> 3;   // 8 complex entries per 128-byte line
+        std::sort(v, v + 32);
+        int lines = 1;
+        for (int l = 1; l < 32; ++l) lines += v[l] != v[l - 1];
+        c += lines + 5;
+      }
+      cost[sl + 1] = cost[sl] + c;
+    }
+    h->d_cb_cost.upload(cost.data(), cost.size(), st);
+    BT_CUDA(cudaStreamSynchronize(st));   // cost is a host temporary
+  }
+  if (cbatch && line_cost && h->d_cb_cost.n == (size_t)h->n_slice + 1) a.cb_cost = h->d_cb_cost.p;
   if (cbatch || chb) {
     a.pb.members = members;
     a.step_begin = 0;
