@@ -149,9 +149,12 @@ def run_sweep_concurrent(fems, mri_para, sim, directions, bvalues, linsolver_par
 
 def gather_signals(n_units, mine, signals, dist=None):
     """Assemble the full signal table on every rank.  dist: an initialised torch.distributed module
-    (gloo or nccl) or None for a single process."""
+    (gloo or nccl), a partition.SocketComm / TorchComm / LocalComm object (no PyTorch needed for the first), or None for
+    a single process."""
     full = np.zeros(n_units)
     full[mine] = signals
+    if dist is not None and hasattr(dist, "sum") and hasattr(dist, "world"):      # a partition.*Comm object
+        return np.asarray(dist.sum(full)) if dist.world > 1 else full
     if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
         import torch
         t = torch.from_numpy(full)

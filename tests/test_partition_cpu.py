@@ -137,6 +137,9 @@ def _gloo_worker(rank, world, port, q, kind="gloo"):
     yl = (_operator(s["ops"]) @ xl)[:s["n_own"]]
     err = float(np.abs(yl - y[gd[:s["n_own"]]]).max())
     tot = comm.sum([s["n_own"]])
+    from dmri_fem_cloud_b200 import sweep                      # the signal table of a sharded sweep through the same object
+    full = sweep.gather_signals(world, [rank], np.array([rank + 1.0]), comm)
+    assert np.array_equal(full, np.arange(1.0, world + 1.0))
     comm.barrier()
     q.put((rank, err, int(tot[0]), gops.ndof))
     if dist is not None:
