@@ -429,6 +429,9 @@ def main():
         # every step is timed on its own (host buffers in -> normalized signal out, which ends with the device -> host
         # read of the signal); the handle is closed BETWEEN two steps, untimed, so that the next step's device arrays come
         # from the stream-ordered pool instead of fresh driver allocations (one 1.3 s outlier was seen with two live handles)
+        e2e_sampler = ClockSampler(local_rank)      # the e2e steps get their own clock / throttle record
+        if rank == 0:
+            e2e_sampler.start()
         e2e_elapsed = 0.0
         for _ in range(e2e_steps):
             barrier()
@@ -438,6 +441,7 @@ def main():
             e2e_elapsed += e2e_times[-1]
             keep.pop().close()
         barrier()
+        e2e_clocks = e2e_sampler.stop() if rank == 0 else None
     if os.environ.get("BENCH_DEBUG") and rank == 0:
         sys.stderr.write("[bench] e2e steps (s): %s | incl. warm-up: %s\n" % (["%.3f" % t for t in e2e_times], e2e_stats))
 
@@ -511,6 +515,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(fem.h2d_bytes + 3 * 8 * nsteps),
                         "d2h_bytes_per_step": int(8 * 8 + 4 * 8), "seconds_per_solve": e2e_max / e2e_steps,
                         "rank0_steps": [dict(st, total_s=round(t, 4)) for st, t in zip(e2e_stats[1:], e2e_times)],
+                        "clocks": e2e_clocks,
                         "normalized_signal": e2e_sig,
                         "api": "dmrifemlib.MyDomain/MRI_simulation.solve (host numpy mesh -> signal)"},
                 "roofline": None}
