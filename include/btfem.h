@@ -211,8 +211,12 @@ int btfem_solve(btfem_t* h, const btfem_solve_args* args, btfem_solve_out* out,
                 int32_t* iters_per_step /*[nsteps] or NULL*/);
 /* `members` independent solves on the same mesh in lock step (HARDI sweeps: the reference loops serially over
  * directions and b-values, ExplicitImplementation.ipynb cell 10): args[m] differ in gdir and cA/cb (q); nsteps, dt,
- * theta and the Krylov settings are taken from args[0].  One kernel launch covers all members, so small meshes
- * stop being launch-latency bound.  BiCGStab, no periodic BC. */
+ * theta and the Krylov settings are taken from args[0].  BiCGStab, no periodic BC.  Up to 32 members on a whole-mesh
+ * handle run their whole time loop as ONE cooperative kernel launch (members of one direction share an operator copy;
+ * a member that has converged in a time step drops out until the next one; a failing member ends the batch and the
+ * call returns its error); larger batches advance through one kernel chain per iteration that covers all members.
+ * Results are reproducible run to run; which batch a member travels in changes its dot-product grouping (agreement
+ * with the one-at-a-time solve to solver tolerance, 1e-9 relative in the tests). */
 int btfem_solve_batch(btfem_t* h, int32_t members, const btfem_solve_args* args /*[members]*/,
                       btfem_solve_out* out /*[members]*/);
 /* solution after the last solve, dof numbering, interleaved (re,im) */
