@@ -27,7 +27,6 @@ def test_recorded_convergence_box_signal():
     assert 3.0 < e8 / e16 < 5.0
 
 
-@pytest.mark.slow
 def test_recorded_convergence_box_signal_full():
     xyz, tets = meshes.box_mesh((-2.5,) * 3, (2.5,) * 3, 16, 16, 16)
     ops = orc.assemble(xyz, tets, D=2e-3)
@@ -130,7 +129,7 @@ def test_three_layer_sphere_vs_matrix_formalism():
     """T2_Relaxation.ipynb / MultilayeredStructures.ipynb cell 12, matrix formalism for the three-layer SPHERE
     R=[5,7.5,10], D=3e-3, kappa=5e-5, delta=Delta=40000: b=1000 -> .7886, 3000 -> .4932.  A whole-path 3-D
     two-compartment pin on curved, conforming interfaces (meshes.layered_sphere); coarse mesh here (0.9 % / 2.5 %),
-    the --runslow variant shows the convergence (0.2 % / 0.5 %)."""
+    the fine-mesh variant below shows the convergence (0.2 % / 0.5 %)."""
     s1, s3 = _sphere_signals(2, (4, 2, 2))
     assert abs(s1 - .7886) <= 0.012 * .7886 and abs(s3 - .4932) <= 0.03 * .4932
     xyz, tets, marker = meshes.layered_sphere((5.0, 7.5, 10.0), (2, 1, 1), 1)
@@ -140,7 +139,6 @@ def test_three_layer_sphere_vs_matrix_formalism():
     assert orc.tet_geometry(xyz, tets)[1].min() > 0
 
 
-@pytest.mark.slow
 def test_three_layer_sphere_vs_matrix_formalism_fine():
     s1, s3 = _sphere_signals(3, (6, 3, 3))
     assert abs(s1 - .7886) <= 0.003 * .7886 and abs(s3 - .4932) <= 0.006 * .4932
